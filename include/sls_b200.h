@@ -1,0 +1,144 @@
+/*
+ * sls_b200.h -- C ABI of the B200-native SLS engine (libsls_b200.so).
+ *
+ * This is the drop-in boundary for the reference's Rust/pyo3 module
+ * `moser_rust` (reference: rust/src/lib.rs).  Every entry point names the
+ * reference interface it replaces (file:line relative to the reference
+ * repository).  Plain pointers and sizes only: no C++ types, no torch types,
+ * no exceptions cross this boundary.  All functions return SLS_OK (0) or an
+ * SLS_ERR_* code; sls_last_error() gives the message for the calling thread.
+ *
+ * There is NO CPU fallback behind this interface: every compute entry point
+ * runs hand-written sm_100a CUDA kernels and fails with SLS_ERR_CUDA when no
+ * usable device is present.
+ *
+ * Randomness: the reference seeds each chain from OS entropy (lib.rs:206) and
+ * has no seed argument.  Here every chain owns two counter-based
+ * Philox4x32-10 streams keyed by (seed, global chain id); see DESIGN.md
+ * "Random streams".  Results are therefore independent of the number of GPUs
+ * a set of chains is sharded over.
+ */
+#ifndef SLS_B200_H
+#define SLS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* lib.rs:157-163 enum AlgoType; the strings of lib.rs:120-126 map to these */
+enum { SLS_ALGO_MOSER = 0, SLS_ALGO_MOSER_SINGLE = 1, SLS_ALGO_SCHOENING = 2, SLS_ALGO_PROBSAT = 3 };
+
+/* the reference signals all of these as Rust panics (pyo3 PanicException) */
+enum {
+    SLS_OK = 0,
+    SLS_ERR_IO = 1,           /* lib.rs:115  .expect("failed to read") */
+    SLS_ERR_PARSE = 2,        /* lib.rs:118  .expect("parse error") */
+    SLS_ERR_ALGO = 3,         /* lib.rs:125  panic!("Unknown algorithm type") */
+    SLS_ERR_WEIGHTS = 4,      /* lib.rs:209  gen_bool(p) with p outside [0,1]; weights shorter than var_count;
+                                 lib.rs:71   WeightedIndex InvalidWeight */
+    SLS_ERR_ALL_ZERO = 5,     /* lib.rs:71   WeightedIndex::new(..).unwrap() on all-zero weights */
+    SLS_ERR_EMPTY_CLAUSE = 6, /* lib.rs:52 / :71 choose()/WeightedIndex on an empty clause */
+    SLS_ERR_ARG = 7,
+    SLS_ERR_CUDA = 8,         /* no device, launch or allocation failure */
+    SLS_ERR_NOMEM = 9
+};
+
+const char *sls_last_error(void);
+
+/* ---- device ------------------------------------------------------------ */
+int sls_device_count(int *count);
+int sls_set_device(int device); /* per calling thread, like cudaSetDevice */
+
+/* ---- instance: replaces DimacsParser::parse + CnfFormula (lib.rs:115-118)
+ *      and the var_to_clauses mapping (lib.rs:186-199).  The clause CSR and the
+ *      occurrence CSR live in HBM for the lifetime of the handle. ----------- */
+typedef struct sls_instance sls_instance;
+
+int sls_instance_from_dimacs(const char *path, sls_instance **out);
+int sls_instance_from_dimacs_text(const char *text, size_t len, sls_instance **out);
+/* row_ptr[m+1], signed DIMACS literals (+v / -v, v in 1..n) */
+int sls_instance_from_csr(uint32_t n, uint32_t m, const uint64_t *row_ptr, const int32_t *signed_lits,
+                          sls_instance **out);
+void sls_instance_free(sls_instance *inst);
+uint32_t sls_instance_num_vars(const sls_instance *inst);    /* CnfFormula::var_count, lib.rs:186 */
+uint32_t sls_instance_num_clauses(const sls_instance *inst); /* CnfFormula::len, lib.rs:203 */
+uint64_t sls_instance_num_lits(const sls_instance *inst);
+uint32_t sls_instance_max_clause_len(const sls_instance *inst);
+int sls_instance_get_csr(const sls_instance *inst, uint64_t *row_ptr, int32_t *signed_lits);
+
+/* ---- clause evaluation: replaces clause_is_violated (lib.rs:13-18),
+ *      find_violated_clauses (lib.rs:176-181) and
+ *      {LCG,VCG}.get_violated_constraints (python/src/sat_representations.py:718-741,
+ *      :353-373).  assignments: B rows of n bytes (0/1), host memory.
+ *      violated_bits (optional): B rows of ceil(m/32) words, bit c%32 of word
+ *      c/32 set <=> clause c violated.  energy (optional): violated clauses
+ *      per row, every clause counted on its own (the Python semantics). ----- */
+int sls_eval_assignments(sls_instance *inst, const uint8_t *assignments, uint64_t batch, uint32_t *violated_bits,
+                         uint32_t *energy);
+
+/* ---- solver: replaces run_sls_python / run_sls (lib.rs:103-149, :165-335) */
+typedef struct {
+    int32_t algo;                /* SLS_ALGO_*            (algo_type_as_str) */
+    int32_t return_trajectories; /* lib.rs:110 */
+    int32_t pre_compute_mapping; /* lib.rs:111 */
+    int32_t reserved;
+    uint64_t nsteps;             /* lib.rs:108 */
+    uint64_t nruns;              /* lib.rs:109 */
+    double prob_flip_best;       /* lib.rs:112 */
+    uint64_t seed;               /* Philox key (no reference equivalent: lib.rs:206 uses OS entropy) */
+    uint64_t chain_offset;       /* global id of run 0 of this call (sharding over GPUs) */
+} sls_run_params;
+
+typedef struct {
+    /* caller-allocated host buffers (NULL = not wanted) */
+    uint8_t *best_assignment;  /* [n]      lib.rs:334 .0, valid iff has_best_assignment */
+    uint8_t *found;            /* [nruns]  lib.rs:334 .1 */
+    uint64_t *steps;           /* [nruns]  lib.rs:334 .3 numstep_local */
+    uint64_t *best_energy_run; /* [nruns]  per-run best energy (lib.rs:292-296) */
+    uint64_t *flips_run;       /* [nruns]  assignment toggles per run (throughput metric) */
+    uint32_t *traj;            /* [nruns][nsteps+1] lib.rs:334 .4 when return_trajectories */
+    uint64_t *traj_len;        /* [nruns]  valid prefix of each trajectory row (= steps+1) */
+    /* written by the call */
+    uint64_t best_energy;      /* lib.rs:334 .2 */
+    int32_t has_best_assignment; /* 0 <=> the reference returns an empty best_assignment */
+    int32_t reserved;
+    uint64_t total_steps;
+    uint64_t total_flips;
+    double kernel_ms;          /* device time of the walk kernel (CUDA events) */
+} sls_run_result;
+
+/* one call = one run_sls_python call on an already parsed instance: host buffers in,
+ * host buffers out, H2D/D2H inside. */
+int sls_run(sls_instance *inst, const double *w_init, size_t w_init_len, const double *w_resample,
+            size_t w_resample_len, const sls_run_params *params, sls_run_result *res);
+
+/* resident form: state for params->nruns chains stays in HBM between launches */
+typedef struct sls_solver sls_solver;
+
+int sls_solver_create(sls_instance *inst, const sls_run_params *params, sls_solver **out);
+void sls_solver_free(sls_solver *s);
+int sls_solver_set_weights(sls_solver *s, const double *w_init, size_t w_init_len, const double *w_resample,
+                           size_t w_resample_len);
+int sls_solver_set_seed(sls_solver *s, uint64_t seed, uint64_t chain_offset);
+/* asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream): init + walk of all chains */
+int sls_solver_launch(sls_solver *s, void *cuda_stream);
+int sls_solver_sync(sls_solver *s);
+/* device time of the last launch (ms, CUDA events on the launch stream); call after sync */
+int sls_solver_last_kernel_ms(sls_solver *s, double *ms);
+int sls_solver_fetch(sls_solver *s, sls_run_result *res);
+/* device-to-device export of the per-chain results for a collective (all device pointers,
+ * any may be NULL): found u8[nruns], steps u64[nruns], best_energy u32[nruns], flips u64[nruns] */
+int sls_solver_export_device(sls_solver *s, void *d_found, void *d_steps, void *d_best_energy, void *d_flips,
+                             void *cuda_stream);
+/* number of kernels the last launch enqueued (for launch accounting) */
+int sls_solver_launch_count(const sls_solver *s);
+/* description of the kernel variant the solver picked, e.g. "walk<k3,smem>" */
+const char *sls_solver_variant(const sls_solver *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

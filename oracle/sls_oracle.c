@@ -384,7 +384,8 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
 
 /* Per-chain streams.  counter = (block_lo, block_hi, chain_lo, chain_hi | stream<<30),
  * key = seed.  Stream 0 ("init"): block b holds the two u64 for variables 2b, 2b+1.
- * Stream 1 ("walk"): a sequence of u32 words consumed in reference draw order. */
+ * Stream 1 ("walk"): a sequence of u32 words consumed in reference draw order
+ * (32-bit draws take one word, 64-bit draws two words at an even position). */
 enum { STREAM_INIT = 0, STREAM_WALK = 1 };
 
 typedef struct {
@@ -421,8 +422,11 @@ static inline uint32_t next_u32(rng_stream *s)
     return s->buf[s->pos++ & 3];
 }
 
+/* 64-bit draws sit on even word positions (an odd cursor skips one word), so a u64
+ * never straddles two Philox blocks and lanes can fetch the draw of literal j directly. */
 static inline uint64_t next_u64(rng_stream *s)
 {
+    s->pos = (s->pos + 1) & ~1ull;
     uint64_t lo = next_u32(s);
     uint64_t hi = next_u32(s);
     return lo | (hi << 32);

@@ -1,0 +1,651 @@
+// api.cu -- the C ABI of include/sls_b200.h on top of the sm_100a kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sls_b200.h"
+#include "common.h"
+#include "eval.cuh"
+#include "instance.h"
+#include "walk_generic.cuh"
+#include "walk_k3.cuh"
+
+using namespace slsb;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_error;
+
+static int set_error(int code, const std::string& msg)
+{
+    g_error = msg;
+    return code;
+}
+
+extern "C" const char* sls_last_error(void) { return g_error.c_str(); }
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return set_error(SLS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+// ------------------------------------------------------------------ device
+extern "C" int sls_device_count(int* count)
+{
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return set_error(SLS_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *count = c;
+    return SLS_OK;
+}
+
+extern "C" int sls_set_device(int device)
+{
+    CUDA_TRY(cudaSetDevice(device));
+    return SLS_OK;
+}
+
+// ---------------------------------------------------------------- instance
+namespace {
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Upload every device array of the instance in one allocation.  Called lazily by the first
+// compute entry point so that parsing / inspection works on a machine without a GPU.
+int ensure_on_device(sls_instance* inst)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (inst->d_blob && inst->device == dev) return SLS_OK;
+    if (inst->d_blob) {
+        cudaFree(inst->d_blob);
+        inst->d_blob = nullptr;
+    }
+    const HostInstance& h = inst->host;
+    const size_t L = h.lits.size();
+    struct Seg {
+        const void* src;
+        size_t bytes;
+        size_t off;
+    };
+    std::vector<uint4> crec, orec;
+    if (h.k3) {
+        // clause records {l0,l1,l2,k}; occurrence records {clause, other a, other b, neg of the variable}
+        crec.resize(h.m);
+        for (uint32_t c = 0; c < h.m; c++) {
+            const uint32_t s = h.row_ptr[c], k = h.row_ptr[c + 1] - s;
+            uint32_t l[3] = {LIT_NONE, LIT_NONE, LIT_NONE};
+            for (uint32_t j = 0; j < k; j++) l[j] = h.lits[s + j];
+            crec[c] = make_uint4(l[0], l[1], l[2], k);
+        }
+        orec.resize(L + 32);  // padded: a warp may over-read one full round
+        std::vector<uint32_t> fill(h.occ_ptr.begin(), h.occ_ptr.end() - 1);
+        for (uint32_t c = 0; c < h.m; c++) {
+            const uint32_t s = h.row_ptr[c], k = h.row_ptr[c + 1] - s;
+            for (uint32_t j = 0; j < k; j++) {
+                uint32_t others[2] = {LIT_NONE, LIT_NONE};
+                uint32_t t = 0;
+                for (uint32_t q = 0; q < k; q++)
+                    if (q != j) others[t++] = h.lits[s + q];
+                const uint32_t lit = h.lits[s + j];
+                orec[fill[lit >> 1]++] = make_uint4(c, others[0], others[1], lit & 1u);
+            }
+        }
+        for (size_t i = L; i < orec.size(); i++) orec[i] = make_uint4(0, LIT_NONE, LIT_NONE, 0);
+    }
+    std::vector<Seg> segs = {
+        {h.row_ptr.data(), h.row_ptr.size() * 4, 0}, {h.lits.data(), L * 4, 0},
+        {h.occ_ptr.data(), h.occ_ptr.size() * 4, 0}, {h.occ.data(), L * 4, 0},
+        {h.has_duplicates ? h.canon.data() : nullptr, h.has_duplicates ? h.canon.size() * 4 : 0, 0},
+        {crec.data(), crec.size() * sizeof(uint4), 0}, {orec.data(), orec.size() * sizeof(uint4), 0},
+    };
+    size_t total = 0;
+    for (auto& s : segs) {
+        s.off = total;
+        total += align_up(std::max<size_t>(s.bytes, 16), 256);
+    }
+    char* blob = nullptr;
+    CUDA_TRY(cudaMalloc(&blob, total));
+    for (auto& s : segs)
+        if (s.bytes) {
+            cudaError_t e = cudaMemcpy(blob + s.off, s.src, s.bytes, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) {
+                cudaFree(blob);
+                return set_error(SLS_ERR_CUDA, std::string("cudaMemcpy(instance): ") + cudaGetErrorString(e));
+            }
+        }
+    inst->d_blob = blob;
+    inst->blob_bytes = total;
+    inst->device = dev;
+    DevInst& d = inst->dev;
+    d.n = h.n;
+    d.m = h.m;
+    d.nwords = (h.n + 31) / 32;
+    d.mwords = (h.m + 31) / 32;
+    d.ngroups = (d.mwords + 31) / 32;
+    d.uniform_k = h.uniform_k;
+    d.max_k = h.max_k;
+    d.flags = (h.has_duplicates ? INST_HAS_DUPLICATES : 0u) | (h.k3 ? INST_K3 : 0u);
+    d.row_ptr = reinterpret_cast<const uint32_t*>(blob + segs[0].off);
+    d.lits = reinterpret_cast<const uint32_t*>(blob + segs[1].off);
+    d.occ_ptr = reinterpret_cast<const uint32_t*>(blob + segs[2].off);
+    d.occ = reinterpret_cast<const uint32_t*>(blob + segs[3].off);
+    d.canon = h.has_duplicates ? reinterpret_cast<const uint32_t*>(blob + segs[4].off) : nullptr;
+    d.crec = h.k3 ? reinterpret_cast<const uint4*>(blob + segs[5].off) : nullptr;
+    d.orec = h.k3 ? reinterpret_cast<const uint4*>(blob + segs[6].off) : nullptr;
+    return SLS_OK;
+}
+
+int finish_handle(sls_instance* inst, const std::string& err, sls_instance** out)
+{
+    if (!err.empty()) {
+        delete inst;
+        return set_error(SLS_ERR_PARSE, "parse error: " + err);
+    }
+    *out = inst;
+    return SLS_OK;
+}
+
+}  // namespace
+
+extern "C" int sls_instance_from_dimacs_text(const char* text, size_t len, sls_instance** out)
+{
+    if (!out) return set_error(SLS_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    sls_instance* inst = new (std::nothrow) sls_instance();
+    if (!inst) return set_error(SLS_ERR_NOMEM, "out of memory");
+    return finish_handle(inst, parse_dimacs(text, len, inst->host), out);
+}
+
+extern "C" int sls_instance_from_dimacs(const char* path, sls_instance** out)
+{
+    if (!out) return set_error(SLS_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return set_error(SLS_ERR_IO, std::string("failed to read ") + path);
+    std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    if (f.bad()) return set_error(SLS_ERR_IO, std::string("failed to read ") + path);
+    return sls_instance_from_dimacs_text(text.data(), text.size(), out);
+}
+
+extern "C" int sls_instance_from_csr(uint32_t n, uint32_t m, const uint64_t* row_ptr, const int32_t* signed_lits,
+                                     sls_instance** out)
+{
+    if (!out || !row_ptr) return set_error(SLS_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    const uint64_t L = row_ptr[m];
+    if (L > 0xfffffff0ull) return set_error(SLS_ERR_ARG, "formula too large");
+    sls_instance* inst = new (std::nothrow) sls_instance();
+    if (!inst) return set_error(SLS_ERR_NOMEM, "out of memory");
+    HostInstance& h = inst->host;
+    h.n = n;
+    h.m = m;
+    h.row_ptr.resize(size_t(m) + 1);
+    for (uint32_t c = 0; c <= m; c++) h.row_ptr[c] = uint32_t(row_ptr[c]);
+    h.lits.resize(L);
+    for (uint64_t i = 0; i < L; i++) {
+        const int64_t s = signed_lits[i];
+        const uint64_t v = uint64_t(s < 0 ? -s : s);
+        if (s == 0 || v > n) {
+            delete inst;
+            return set_error(SLS_ERR_ARG, "literal out of range");
+        }
+        h.lits[i] = uint32_t((v - 1) << 1) | uint32_t(s < 0);
+    }
+    const std::string err = finalize_instance(h);
+    if (!err.empty()) {
+        delete inst;
+        return set_error(SLS_ERR_ARG, err);
+    }
+    *out = inst;
+    return SLS_OK;
+}
+
+extern "C" void sls_instance_free(sls_instance* inst)
+{
+    if (!inst) return;
+    if (inst->d_blob) cudaFree(inst->d_blob);
+    delete inst;
+}
+
+extern "C" uint32_t sls_instance_num_vars(const sls_instance* inst) { return inst->host.n; }
+extern "C" uint32_t sls_instance_num_clauses(const sls_instance* inst) { return inst->host.m; }
+extern "C" uint64_t sls_instance_num_lits(const sls_instance* inst) { return inst->host.lits.size(); }
+extern "C" uint32_t sls_instance_max_clause_len(const sls_instance* inst) { return inst->host.max_k; }
+
+extern "C" int sls_instance_get_csr(const sls_instance* inst, uint64_t* row_ptr, int32_t* signed_lits)
+{
+    const HostInstance& h = inst->host;
+    if (row_ptr)
+        for (uint32_t c = 0; c <= h.m; c++) row_ptr[c] = h.row_ptr[c];
+    if (signed_lits)
+        for (size_t i = 0; i < h.lits.size(); i++) {
+            const int32_t v = int32_t(h.lits[i] >> 1) + 1;
+            signed_lits[i] = (h.lits[i] & 1u) ? -v : v;
+        }
+    return SLS_OK;
+}
+
+// ------------------------------------------------------- clause evaluation
+extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignments, uint64_t batch,
+                                    uint32_t* violated_bits, uint32_t* energy)
+{
+    if (!inst || (!assignments && batch && inst->host.n)) return set_error(SLS_ERR_ARG, "NULL argument");
+    if (batch == 0) return SLS_OK;
+    int rc = ensure_on_device(inst);
+    if (rc) return rc;
+    const DevInst& I = inst->dev;
+    if (I.m == 0) {
+        if (energy) std::memset(energy, 0, batch * sizeof(uint32_t));
+        return SLS_OK;
+    }
+    const uint64_t nslices = (batch + 31) / 32;
+    if (nslices > 65535) return set_error(SLS_ERR_ARG, "batch too large for one call (max 2096128 rows)");
+    uint8_t* d_bytes = nullptr;
+    uint32_t *d_tbits = nullptr, *d_v = nullptr, *d_e = nullptr;
+    auto cleanup = [&] {
+        cudaFree(d_bytes);
+        cudaFree(d_tbits);
+        cudaFree(d_v);
+        cudaFree(d_e);
+    };
+    const size_t n1 = std::max<uint32_t>(I.n, 1);
+#define EV_TRY(expr)                                                                                     \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            cleanup();                                                                                   \
+            return set_error(SLS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+        }                                                                                                \
+    } while (0)
+    EV_TRY(cudaMalloc(&d_bytes, batch * n1));
+    EV_TRY(cudaMalloc(&d_tbits, nslices * n1 * 4));
+    EV_TRY(cudaMalloc(&d_e, batch * 4));
+    if (violated_bits) EV_TRY(cudaMalloc(&d_v, batch * (size_t)I.mwords * 4));
+    if (I.n) EV_TRY(cudaMemcpy(d_bytes, assignments, batch * (size_t)I.n, cudaMemcpyHostToDevice));
+    EV_TRY(cudaMemset(d_e, 0, batch * 4));
+    if (I.n) {
+        const uint64_t total = nslices * I.n;
+        transpose_assignments_kernel<<<(unsigned)((total + 255) / 256), 256>>>(d_bytes, d_tbits, I.n, batch,
+                                                                               (uint32_t)nslices);
+    }
+    {
+        constexpr int WARPS = 8;
+        // enough CTAs to fill the machine a few times over, at least 8 words per warp pass
+        uint32_t words_per_block = 256;
+        const uint32_t bx = (I.mwords + words_per_block - 1) / words_per_block;
+        dim3 grid(bx, (unsigned)nslices);
+        eval_sliced_kernel<WARPS><<<grid, WARPS * 32>>>(I, d_tbits, d_v, d_e, batch, words_per_block);
+    }
+    EV_TRY(cudaGetLastError());
+    EV_TRY(cudaDeviceSynchronize());
+    if (energy) EV_TRY(cudaMemcpy(energy, d_e, batch * 4, cudaMemcpyDeviceToHost));
+    if (violated_bits) EV_TRY(cudaMemcpy(violated_bits, d_v, batch * (size_t)I.mwords * 4, cudaMemcpyDeviceToHost));
+    cleanup();
+#undef EV_TRY
+    return SLS_OK;
+}
+
+// ------------------------------------------------------------------ solver
+struct sls_solver {
+    sls_instance* inst = nullptr;
+    sls_run_params p{};
+    WalkArgs args{};
+    bool smem_state = false;
+    bool k3 = false;
+    uint32_t wpb = 4;
+    size_t smem_bytes = 0;
+    int device = 0;
+    int num_sms = 0;
+    bool weights_set = false;
+    std::string variant;
+    // device buffers
+    uint64_t* d_thr = nullptr;
+    double* d_w = nullptr;
+    uint4* d_vrec = nullptr;
+    uint32_t* d_gstate = nullptr;
+    uint32_t* d_best_bits = nullptr;
+    uint8_t* d_found = nullptr;
+    uint8_t* d_has_best = nullptr;
+    uint64_t* d_steps = nullptr;
+    uint32_t* d_best_energy = nullptr;
+    uint64_t* d_flips = nullptr;
+    uint32_t* d_traj = nullptr;
+    int32_t* d_err = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t last_stream = nullptr;
+    int launches = 0;
+    double last_ms = 0.0;
+};
+
+extern "C" void sls_solver_free(sls_solver* s)
+{
+    if (!s) return;
+    cudaFree(s->d_thr);
+    cudaFree(s->d_w);
+    cudaFree(s->d_vrec);
+    cudaFree(s->d_gstate);
+    cudaFree(s->d_best_bits);
+    cudaFree(s->d_found);
+    cudaFree(s->d_has_best);
+    cudaFree(s->d_steps);
+    cudaFree(s->d_best_energy);
+    cudaFree(s->d_flips);
+    cudaFree(s->d_traj);
+    cudaFree(s->d_err);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+}
+
+extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* params, sls_solver** out)
+{
+    if (!inst || !params || !out) return set_error(SLS_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (params->algo < 0 || params->algo > 3) return set_error(SLS_ERR_ALGO, "Unknown algorithm type");
+    if (params->return_trajectories && params->nsteps + 1 > 0xffffffffull)
+        return set_error(SLS_ERR_ARG, "nsteps too large for trajectories");
+    int rc = ensure_on_device(inst);
+    if (rc) return rc;
+    sls_solver* s = new (std::nothrow) sls_solver();
+    if (!s) return set_error(SLS_ERR_NOMEM, "out of memory");
+    s->inst = inst;
+    s->p = *params;
+    const DevInst& I = inst->dev;
+    const uint64_t R = params->nruns;
+    const size_t R1 = std::max<uint64_t>(R, 1);
+
+#define SC_TRY(expr)                                                                                     \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            sls_solver_free(s);                                                                          \
+            return set_error(SLS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+        }                                                                                                \
+    } while (0)
+    SC_TRY(cudaGetDevice(&s->device));
+    int max_smem_optin = 0, smem_per_sm = 0;
+    SC_TRY(cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, s->device));
+    SC_TRY(cudaDeviceGetAttribute(&max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device));
+    SC_TRY(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, s->device));
+
+    // chain state slab: assignment bits | violated bits | level-1 counters
+    const uint32_t slab_words = (I.nwords + I.mwords + I.ngroups + 3u) & ~3u;
+    const size_t slab_bytes = size_t(slab_words) * 4;
+    // Tier choice: keep the chain state in shared memory when enough chains fit per SM to cover
+    // this call's share of chains (or at least 16 warps); otherwise the state lives in HBM.
+    uint32_t wpb = 4;
+    while (wpb > 1 && wpb * slab_bytes > (size_t)max_smem_optin) wpb >>= 1;
+    bool smem_ok = wpb * slab_bytes <= (size_t)max_smem_optin;
+    if (smem_ok) {
+        const size_t per_cta = wpb * slab_bytes + 1024;  // 1 KB reserved per CTA
+        const uint64_t ctas = std::min<uint64_t>(smem_per_sm / per_cta, 64 / wpb);
+        const uint64_t chains_per_sm = ctas * wpb;
+        const uint64_t needed = std::min<uint64_t>((R + s->num_sms - 1) / std::max(s->num_sms, 1), 16);
+        smem_ok = chains_per_sm >= std::max<uint64_t>(needed, 1);
+    }
+    // test hooks: SLS_B200_FORCE_STATE=hbm|smem, SLS_B200_FORCE_GENERIC=1
+    if (const char* f = std::getenv("SLS_B200_FORCE_STATE")) {
+        if (std::strcmp(f, "hbm") == 0) smem_ok = false;
+        if (std::strcmp(f, "smem") == 0 && wpb * slab_bytes <= (size_t)max_smem_optin) smem_ok = true;
+    }
+    s->smem_state = smem_ok;
+    s->wpb = smem_ok ? wpb : 4;
+    s->smem_bytes = smem_ok ? s->wpb * slab_bytes : 0;
+    s->k3 = (I.flags & INST_K3) != 0;
+    if (const char* f = std::getenv("SLS_B200_FORCE_GENERIC"))
+        if (f[0] == '1') s->k3 = false;
+    s->variant = std::string(s->k3 ? "walk_k3<" : "walk_generic<") + (s->smem_state ? "smem" : "hbm") + ">";
+
+    SC_TRY(cudaMalloc(&s->d_thr, std::max<size_t>(I.n, 1) * 8));
+    SC_TRY(cudaMalloc(&s->d_w, std::max<size_t>(I.n, 1) * 8));
+    if (s->k3) SC_TRY(cudaMalloc(&s->d_vrec, std::max<size_t>(I.n, 1) * sizeof(uint4)));
+    if (!s->smem_state) SC_TRY(cudaMalloc(&s->d_gstate, R1 * slab_bytes));
+    SC_TRY(cudaMalloc(&s->d_best_bits, R1 * std::max<size_t>(I.nwords, 1) * 4));
+    SC_TRY(cudaMalloc(&s->d_found, R1));
+    SC_TRY(cudaMalloc(&s->d_has_best, R1));
+    SC_TRY(cudaMalloc(&s->d_steps, R1 * 8));
+    SC_TRY(cudaMalloc(&s->d_best_energy, R1 * 4));
+    SC_TRY(cudaMalloc(&s->d_flips, R1 * 8));
+    SC_TRY(cudaMalloc(&s->d_err, 4));
+    if (params->return_trajectories) SC_TRY(cudaMalloc(&s->d_traj, R1 * (params->nsteps + 1) * 4));
+    SC_TRY(cudaEventCreate(&s->ev0));
+    SC_TRY(cudaEventCreate(&s->ev1));
+    if (s->smem_bytes) {
+        SC_TRY(cudaFuncSetAttribute(walk_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)s->smem_bytes));
+        SC_TRY(cudaFuncSetAttribute(walk_k3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)s->smem_bytes));
+    }
+#undef SC_TRY
+
+    WalkArgs& a = s->args;
+    a.inst = I;
+    a.thr_init = s->d_thr;
+    a.w = s->d_w;
+    a.vrec = s->d_vrec;
+    a.algo = params->algo;
+    a.mapping = params->pre_compute_mapping;
+    a.want_traj = params->return_trajectories;
+    a.pfb = params->prob_flip_best;
+    a.nsteps = params->nsteps;
+    a.nruns = R;
+    a.seed = params->seed;
+    a.chain_offset = params->chain_offset;
+    a.gstate = s->d_gstate;
+    a.slab_words = slab_words;
+    a.warps_per_block = s->wpb;
+    a.best_bits = s->d_best_bits;
+    a.found = s->d_found;
+    a.has_best = s->d_has_best;
+    a.steps = s->d_steps;
+    a.best_energy = s->d_best_energy;
+    a.flips = s->d_flips;
+    a.traj = s->d_traj;
+    a.err = s->d_err;
+    *out = s;
+    return SLS_OK;
+}
+
+extern "C" int sls_solver_set_seed(sls_solver* s, uint64_t seed, uint64_t chain_offset)
+{
+    s->p.seed = s->args.seed = seed;
+    s->p.chain_offset = s->args.chain_offset = chain_offset;
+    return SLS_OK;
+}
+
+extern "C" int sls_solver_set_weights(sls_solver* s, const double* w_init, size_t w_init_len, const double* w_resample,
+                                      size_t w_resample_len)
+{
+    const uint32_t n = s->inst->host.n;
+    // the reference indexes both vectors by variable (lib.rs:209, :29): a short vector panics
+    if (s->p.nruns > 0 && w_init_len < n) return set_error(SLS_ERR_WEIGHTS, "weights_initialize shorter than var_count");
+    if (s->p.nruns > 0 && w_resample_len < n && s->p.algo != SLS_ALGO_SCHOENING)
+        return set_error(SLS_ERR_WEIGHTS, "weights_resample shorter than var_count");
+    if (s->p.nruns == 0) {
+        s->weights_set = true;
+        return SLS_OK;
+    }
+    // rand 0.8.5 Bernoulli::new(p): p_int = (p * 2^64) as u64; p == 1 is ALWAYS_TRUE; else p must be in [0,1)
+    std::vector<uint64_t> thr(std::max<uint32_t>(n, 1));
+    for (uint32_t i = 0; i < n; i++) {
+        const double p = w_init[i];
+        if (p >= 0.0 && p < 1.0)
+            thr[i] = (uint64_t)(p * 18446744073709551616.0);
+        else if (p == 1.0)
+            thr[i] = ~0ull;
+        else
+            return set_error(SLS_ERR_WEIGHTS, "weights_initialize: p is outside range [0.0, 1.0]");
+    }
+    CUDA_TRY(cudaMemcpy(s->d_thr, thr.data(), size_t(n) * 8, cudaMemcpyHostToDevice));
+    if (w_resample_len >= n && n)
+        CUDA_TRY(cudaMemcpy(s->d_w, w_resample, size_t(n) * 8, cudaMemcpyHostToDevice));
+    else if (n)
+        CUDA_TRY(cudaMemset(s->d_w, 0, size_t(n) * 8));
+    if (s->d_vrec && n) {
+        // per-variable record of the k<=3 kernel: resample weight + occurrence range
+        const HostInstance& h = s->inst->host;
+        std::vector<uint4> vrec(n);
+        for (uint32_t v = 0; v < n; v++) {
+            const double w = w_resample_len >= n ? w_resample[v] : 0.0;
+            uint64_t bits;
+            std::memcpy(&bits, &w, 8);
+            vrec[v] = make_uint4((uint32_t)bits, (uint32_t)(bits >> 32), h.occ_ptr[v], h.occ_ptr[v + 1] - h.occ_ptr[v]);
+        }
+        CUDA_TRY(cudaMemcpy(s->d_vrec, vrec.data(), size_t(n) * sizeof(uint4), cudaMemcpyHostToDevice));
+    }
+    s->weights_set = true;
+    return SLS_OK;
+}
+
+extern "C" int sls_solver_launch(sls_solver* s, void* cuda_stream)
+{
+    if (!s->weights_set) return set_error(SLS_ERR_ARG, "sls_solver_set_weights was not called");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    s->last_stream = st;
+    s->launches = 0;
+    if (s->p.nruns == 0) return SLS_OK;
+    CUDA_TRY(cudaMemsetAsync(s->d_err, 0, 4, st));
+    const unsigned blocks = (unsigned)((s->p.nruns + s->wpb - 1) / s->wpb);
+    const unsigned threads = s->wpb * 32;
+    CUDA_TRY(cudaEventRecord(s->ev0, st));
+    const bool use_k3 = s->k3 && walk_k3_supports(s->args);
+    if (use_k3) {
+        if (s->smem_state)
+            walk_k3_kernel<true><<<blocks, threads, s->smem_bytes, st>>>(s->args);
+        else
+            walk_k3_kernel<false><<<blocks, threads, 0, st>>>(s->args);
+    } else {
+        if (s->smem_state)
+            walk_generic_kernel<true><<<blocks, threads, s->smem_bytes, st>>>(s->args);
+        else
+            walk_generic_kernel<false><<<blocks, threads, 0, st>>>(s->args);
+    }
+    s->launches = 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(s->ev1, st));
+    return SLS_OK;
+}
+
+extern "C" int sls_solver_sync(sls_solver* s)
+{
+    if (s->p.nruns == 0) return SLS_OK;
+    CUDA_TRY(cudaEventSynchronize(s->ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->last_ms = ms;
+    return SLS_OK;
+}
+
+extern "C" int sls_solver_last_kernel_ms(sls_solver* s, double* ms)
+{
+    *ms = s->last_ms;
+    return SLS_OK;
+}
+
+extern "C" int sls_solver_launch_count(const sls_solver* s) { return s->launches; }
+extern "C" const char* sls_solver_variant(const sls_solver* s) { return s->variant.c_str(); }
+
+extern "C" int sls_solver_export_device(sls_solver* s, void* d_found, void* d_steps, void* d_best_energy, void* d_flips,
+                                        void* cuda_stream)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const size_t R = s->p.nruns;
+    if (R == 0) return SLS_OK;
+    if (d_found) CUDA_TRY(cudaMemcpyAsync(d_found, s->d_found, R, cudaMemcpyDeviceToDevice, st));
+    if (d_steps) CUDA_TRY(cudaMemcpyAsync(d_steps, s->d_steps, R * 8, cudaMemcpyDeviceToDevice, st));
+    if (d_best_energy) CUDA_TRY(cudaMemcpyAsync(d_best_energy, s->d_best_energy, R * 4, cudaMemcpyDeviceToDevice, st));
+    if (d_flips) CUDA_TRY(cudaMemcpyAsync(d_flips, s->d_flips, R * 8, cudaMemcpyDeviceToDevice, st));
+    return SLS_OK;
+}
+
+extern "C" int sls_solver_fetch(sls_solver* s, sls_run_result* res)
+{
+    const HostInstance& h = s->inst->host;
+    const size_t R = s->p.nruns;
+    res->best_energy = h.m;  // lib.rs:320
+    res->has_best_assignment = 0;
+    res->total_steps = 0;
+    res->total_flips = 0;
+    res->kernel_ms = s->last_ms;
+    if (R == 0) return SLS_OK;
+    int rc = sls_solver_sync(s);
+    if (rc) return rc;
+    res->kernel_ms = s->last_ms;
+    int32_t err = 0;
+    CUDA_TRY(cudaMemcpy(&err, s->d_err, 4, cudaMemcpyDeviceToHost));
+    if (err) {
+        const char* msg = err == DERR_ALL_ZERO       ? "probsat: AllWeightsZero"
+                          : err == DERR_EMPTY_CLAUSE ? "an empty clause was selected"
+                          : err == DERR_WEIGHTS      ? "probsat: InvalidWeight"
+                                                     : "clause too long for the Moser-Tardos kernel (k > 1024)";
+        return set_error(err, msg);
+    }
+    std::vector<uint8_t> found(R), has_best(R);
+    std::vector<uint64_t> steps(R), flips(R);
+    std::vector<uint32_t> be(R);
+    CUDA_TRY(cudaMemcpy(found.data(), s->d_found, R, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(has_best.data(), s->d_has_best, R, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(steps.data(), s->d_steps, R * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(flips.data(), s->d_flips, R * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(be.data(), s->d_best_energy, R * 4, cudaMemcpyDeviceToHost));
+    // lib.rs:320-334: strict '<' arg-min in run order starting from formula.len()
+    uint64_t best = h.m;
+    size_t winner = R;
+    for (size_t r = 0; r < R; r++) {
+        if (be[r] < best) {
+            best = be[r];
+            winner = r;
+        }
+        res->total_steps += steps[r];
+        res->total_flips += flips[r];
+    }
+    res->best_energy = best;
+    if (winner < R && has_best[winner]) {
+        res->has_best_assignment = 1;
+        if (res->best_assignment) {
+            const uint32_t nwords = (h.n + 31) / 32;
+            std::vector<uint32_t> bits(std::max<uint32_t>(nwords, 1));
+            CUDA_TRY(cudaMemcpy(bits.data(), s->d_best_bits + winner * nwords, size_t(nwords) * 4,
+                                cudaMemcpyDeviceToHost));
+            for (uint32_t v = 0; v < h.n; v++) res->best_assignment[v] = (bits[v >> 5] >> (v & 31)) & 1u;
+        }
+    }
+    if (res->found) std::memcpy(res->found, found.data(), R);
+    if (res->steps) std::memcpy(res->steps, steps.data(), R * 8);
+    if (res->flips_run) std::memcpy(res->flips_run, flips.data(), R * 8);
+    if (res->best_energy_run)
+        for (size_t r = 0; r < R; r++) res->best_energy_run[r] = be[r];
+    if (s->p.return_trajectories) {
+        if (res->traj)
+            CUDA_TRY(cudaMemcpy(res->traj, s->d_traj, R * (s->p.nsteps + 1) * 4, cudaMemcpyDeviceToHost));
+        if (res->traj_len)
+            for (size_t r = 0; r < R; r++) res->traj_len[r] = steps[r] + 1;
+    }
+    return SLS_OK;
+}
+
+extern "C" int sls_run(sls_instance* inst, const double* w_init, size_t w_init_len, const double* w_resample,
+                       size_t w_resample_len, const sls_run_params* params, sls_run_result* res)
+{
+    sls_solver* s = nullptr;
+    int rc = sls_solver_create(inst, params, &s);
+    if (rc) return rc;
+    rc = sls_solver_set_weights(s, w_init, w_init_len, w_resample, w_resample_len);
+    if (!rc) rc = sls_solver_launch(s, nullptr);
+    if (!rc) rc = sls_solver_fetch(s, res);
+    sls_solver_free(s);
+    return rc;
+}

@@ -1,0 +1,67 @@
+// common.h -- shared host/device definitions of the B200 SLS engine.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include <vector_types.h>  // uint4 (host and device)
+
+namespace slsb {
+
+// Device view of one CNF instance.  The clause CSR replaces varisat's CnfFormula
+// (reference rust/src/lib.rs:118), the occurrence CSR replaces var_to_clauses
+// (lib.rs:186-199, clause ids in formula order, one entry per literal occurrence).
+struct DevInst {
+    uint32_t n;        // variables
+    uint32_t m;        // clauses (formula.len(), duplicates included)
+    uint32_t nwords;   // ceil(n/32)   assignment bitmap words
+    uint32_t mwords;   // ceil(m/32)   violated-set bitmap words
+    uint32_t ngroups;  // ceil(mwords/32) level-1 counters (1024 clauses each)
+    uint32_t uniform_k;// clause length when all clauses share it, else 0
+    uint32_t max_k;
+    uint32_t flags;    // INST_*
+    const uint32_t* row_ptr;  // [m+1]
+    const uint32_t* lits;     // [L]  2*var + neg (varisat Lit code)
+    const uint32_t* occ_ptr;  // [n+1]
+    const uint32_t* occ;      // [L]  clause ids
+    const uint32_t* canon;    // [m]  first clause with identical content; nullptr when all distinct
+    // k<=3 fast path (nullptr when the instance does not qualify):
+    const uint4* crec;        // [m]  {lit0, lit1, lit2, k}; absent literals = LIT_NONE
+    const uint4* orec;        // [L]  per occurrence of var v: {clause id, other lit a, other lit b, neg(v in clause)}
+};
+
+enum : uint32_t { INST_HAS_DUPLICATES = 1u, INST_K3 = 2u };
+static constexpr uint32_t LIT_NONE = 0xffffffffu;
+
+enum : int { ALGO_MOSER = 0, ALGO_MOSER_SINGLE = 1, ALGO_SCHOENING = 2, ALGO_PROBSAT = 3 };
+
+struct WalkArgs {
+    DevInst inst;
+    const uint64_t* thr_init;  // [n] Bernoulli thresholds of weights_initialize (lib.rs:208-210)
+    const double* w;           // [n] weights_resample
+    const uint4* vrec;         // [n] {weight lo, weight hi, occ_start, occ_len} (k<=3 path) or nullptr
+    int32_t algo;
+    int32_t mapping;           // pre_compute_mapping (only changes the greedy score, lib.rs:242-250)
+    int32_t want_traj;
+    int32_t pad;
+    double pfb;                // prob_flip_best
+    uint64_t nsteps;
+    uint64_t nruns;
+    uint64_t seed;
+    uint64_t chain_offset;
+    uint32_t* gstate;          // [nruns][slab_words] chain state when it lives in HBM
+    uint32_t slab_words;       // nwords + mwords + ngroups (+pad)
+    uint32_t warps_per_block;
+    uint32_t* best_bits;       // [nruns][nwords]
+    uint8_t* found;            // [nruns]
+    uint8_t* has_best;         // [nruns]
+    uint64_t* steps;           // [nruns]
+    uint32_t* best_energy;     // [nruns]
+    uint64_t* flips;           // [nruns]
+    uint32_t* traj;            // [nruns][nsteps+1] or nullptr
+    int32_t* err;              // first error code raised by any chain
+};
+
+// error codes raised on the device (same numbering as include/sls_b200.h)
+enum : int { DERR_WEIGHTS = 4, DERR_ALL_ZERO = 5, DERR_EMPTY_CLAUSE = 6, DERR_ARG = 7 };
+
+}  // namespace slsb

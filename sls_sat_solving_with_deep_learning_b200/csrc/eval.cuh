@@ -1,0 +1,97 @@
+// eval.cuh -- batched clause evaluation: violated bits + energy for B assignments.
+//
+// Device restatement of clause_is_violated / find_violated_clauses
+// (rust/src/lib.rs:13-18, :176-181) and of {LCG,VCG}.get_violated_constraints
+// (python/src/sat_representations.py:718-741, :353-373).
+#pragma once
+#include "common.h"
+
+namespace slsb {
+
+// assignments arrive as one byte per variable (the reference's Vec<bool> / int array):
+// pack 32 of them per word.  One thread per output word.
+__global__ void pack_assignments_kernel(const uint8_t* __restrict__ bytes, uint32_t* __restrict__ bits, uint32_t n,
+                                        uint32_t nwords, uint64_t batch)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= batch * nwords) return;
+    const uint64_t b = idx / nwords;
+    const uint32_t w = (uint32_t)(idx % nwords);
+    const uint8_t* row = bytes + b * n;
+    uint32_t word = 0;
+    const uint32_t v0 = w * 32u;
+    const uint32_t cnt = min(32u, n - v0);
+    for (uint32_t i = 0; i < cnt; i++) word |= (uint32_t)(row[v0 + i] != 0) << i;
+    bits[idx] = word;
+}
+
+// Bit-sliced evaluation.  A CTA owns one slice of 32 assignments and a range of clauses.
+// tbits is the transposed assignment: tbits[slice][v] holds, in bit b, the value of variable v
+// under assignment 32*slice + b, so one literal fetch serves 32 assignments with a single
+// bitwise op.  Each lane evaluates one clause for all 32 assignments, then the 32x32 result
+// tile is transposed with 32 ballots so that each assignment gets its violated-set word.
+__global__ void transpose_assignments_kernel(const uint8_t* __restrict__ bytes, uint32_t* __restrict__ tbits,
+                                             uint32_t n, uint64_t batch, uint32_t nslices)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)nslices * n) return;
+    const uint32_t slice = (uint32_t)(idx / n);
+    const uint32_t v = (uint32_t)(idx % n);
+    uint32_t word = 0;
+    const uint64_t b0 = (uint64_t)slice * 32u;
+    const uint32_t cnt = (uint32_t)min((uint64_t)32, batch - b0);
+    for (uint32_t i = 0; i < cnt; i++) word |= (uint32_t)(bytes[(b0 + i) * n + v] != 0) << i;
+    tbits[idx] = word;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) eval_sliced_kernel(const DevInst I, const uint32_t* __restrict__ tbits,
+                                                                 uint32_t* __restrict__ vout,
+                                                                 uint32_t* __restrict__ energy, uint64_t batch,
+                                                                 uint32_t words_per_block)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t slice = blockIdx.y;
+    const uint32_t* a = tbits + (size_t)slice * I.n;
+    const uint64_t b0 = (uint64_t)slice * 32u;
+    const uint32_t valid = (uint32_t)min((uint64_t)32, batch - b0);
+    const uint32_t w_begin = blockIdx.x * words_per_block;
+    const uint32_t w_end = min(I.mwords, w_begin + words_per_block);
+    uint32_t my_energy = 0;  // lane b accumulates the energy of assignment b0 + b
+    for (uint32_t w = w_begin + warp; w < w_end; w += WARPS) {
+        const uint32_t c = w * 32u + lane;
+        uint32_t viol = 0;  // bit b: clause c violated under assignment b0 + b
+        if (c < I.m) {
+            uint32_t s, e;
+            if (I.uniform_k) {
+                s = c * I.uniform_k;
+                e = s + I.uniform_k;
+            } else {
+                s = __ldg(I.row_ptr + c);
+                e = __ldg(I.row_ptr + c + 1);
+            }
+            viol = 0xffffffffu;
+            for (uint32_t j = s; j < e && viol; j++) {
+                const uint32_t l = __ldg(I.lits + j);
+                const uint32_t av = __ldg(a + (l >> 1));
+                // literal false  <=>  value == neg bit
+                viol &= (l & 1u) ? av : ~av;
+            }
+        }
+        // transpose: word for assignment b = ballot over lanes (clauses) of bit b
+        uint32_t mine = 0;
+#pragma unroll
+        for (int b = 0; b < 32; b++) {
+            const uint32_t word = __ballot_sync(0xffffffffu, (viol >> b) & 1u);
+            if (lane == b) mine = word;
+        }
+        if ((uint32_t)lane < valid) {
+            if (vout) vout[(b0 + lane) * I.mwords + w] = mine;
+            my_energy += __popc(mine);
+        }
+    }
+    if (energy && (uint32_t)lane < valid && my_energy) atomicAdd(energy + b0 + lane, my_energy);
+}
+
+}  // namespace slsb

@@ -1,0 +1,122 @@
+// philox.cuh -- counter-based per-chain random streams (Philox4x32-10).
+//
+// The reference seeds a ChaCha12 StdRng per chain from OS entropy
+// (rust/src/lib.rs:206-207), which is irreproducible by construction.  Here a
+// chain owns two Philox streams keyed by (seed, global chain id):
+//   counter = (block_lo, block_hi, chain_lo, chain_hi | stream << 30), key = seed
+//   stream 0 "init": block b holds the two u64 of variables 2b and 2b+1
+//   stream 1 "walk": u32 words consumed in the reference's draw order; 64-bit
+//                    draws take two words at an even position (an odd cursor
+//                    skips one word) so a draw never straddles two blocks and
+//                    lane j can fetch the draw of literal j on its own.
+// The distributions restate rand 0.8.5 (Standard f64, Bernoulli, UniformInt
+// sample_single, UniformFloat) as cited in DESIGN.md.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace slsb {
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+enum : uint32_t { STREAM_INIT = 0, STREAM_WALK = 1 };
+
+struct ChainKey {
+    uint2 key;
+    uint32_t chain_lo, chain_hi_stream;
+    __device__ __forceinline__ ChainKey(uint64_t seed, uint64_t chain, uint32_t stream)
+    {
+        key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        chain_lo = (uint32_t)chain;
+        chain_hi_stream = ((uint32_t)(chain >> 32) & 0x3fffffffu) | (stream << 30);
+    }
+    __device__ __forceinline__ uint4 block(uint64_t blk) const
+    {
+        return philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), chain_lo, chain_hi_stream), key);
+    }
+    // the u64 at even word position p
+    __device__ __forceinline__ uint64_t u64_at(uint64_t p) const
+    {
+        const uint4 b = block(p >> 2);
+        return (p & 2) ? ((uint64_t)b.w << 32 | b.z) : ((uint64_t)b.y << 32 | b.x);
+    }
+};
+
+// Sequential walk stream; every lane of the warp that owns the chain holds an identical copy.
+struct WalkStream {
+    ChainKey ck;
+    uint64_t pos;
+    uint64_t cached;
+    uint4 buf;
+    __device__ __forceinline__ WalkStream(uint64_t seed, uint64_t chain)
+        : ck(seed, chain, STREAM_WALK), pos(0), cached(~0ull), buf(make_uint4(0, 0, 0, 0))
+    {
+    }
+    __device__ __forceinline__ void fill(uint64_t blk)
+    {
+        if (blk != cached) {
+            buf = ck.block(blk);
+            cached = blk;
+        }
+    }
+    __device__ __forceinline__ uint32_t next_u32()
+    {
+        fill(pos >> 2);
+        const uint32_t sel = (uint32_t)pos & 3u;
+        pos++;
+        return sel == 0 ? buf.x : sel == 1 ? buf.y : sel == 2 ? buf.z : buf.w;
+    }
+    __device__ __forceinline__ uint64_t next_u64()
+    {
+        pos = (pos + 1) & ~1ull;
+        fill(pos >> 2);
+        const bool hi = (pos & 2) != 0;
+        pos += 2;
+        return hi ? ((uint64_t)buf.w << 32 | buf.z) : ((uint64_t)buf.y << 32 | buf.x);
+    }
+    // rand 0.8.5 Standard<f64>: (next_u64 >> 11) * 2^-53
+    __device__ __forceinline__ double next_f64() { return (double)(next_u64() >> 11) * 0x1p-53; }
+    // rand 0.8.5 UniformInt<u32>::sample_single(0, range): widening multiply + zone rejection
+    __device__ __forceinline__ uint32_t uniform_u32(uint32_t range)
+    {
+        const uint32_t zone = (range << __clz(range)) - 1u;
+        for (;;) {
+            const uint32_t v = next_u32();
+            const uint32_t lo = v * range;
+            if (lo <= zone) return __umulhi(v, range);
+        }
+    }
+    // rand 0.8.5 UniformInt<usize>::sample_single on a 64-bit target
+    __device__ __forceinline__ uint64_t uniform_u64(uint64_t range)
+    {
+        const uint64_t zone = (range << __clzll(range)) - 1ull;
+        for (;;) {
+            const uint64_t v = next_u64();
+            const uint64_t lo = v * range;
+            if (lo <= zone) return __umul64hi(v, range);
+        }
+    }
+    // reserve `count` aligned u64 slots; returns the word position of the first one
+    __device__ __forceinline__ uint64_t reserve_u64(uint64_t count)
+    {
+        pos = (pos + 1) & ~1ull;
+        const uint64_t p = pos;
+        pos += 2 * count;
+        return p;
+    }
+};
+
+__device__ __forceinline__ double u64_to_f64_53(uint64_t x) { return (double)(x >> 11) * 0x1p-53; }
+
+}  // namespace slsb

@@ -1,0 +1,449 @@
+// walk_generic.cuh -- one warp per chain, any clause shape.
+//
+// Device restatement of the reference's chain loop (rust/src/lib.rs:201-317):
+//   chain init lib.rs:206-223, violated-clause pick :229, greedy branch :231-268,
+//   MT resample :20-49, MT-single :77-101, Schoening :51-55, probSAT :57-75,
+//   incremental update :278-287, best tracking :292-296, trajectory :298-300.
+//
+// Chain state (one "slab" per chain, in shared memory or in HBM):
+//   abits [nwords]  assignment, 1 bit per variable
+//   vbits [mwords]  violated set, 1 bit per canonical clause id
+//   l1    [ngroups] number of set bits per 32 vbits words (1024 clauses)
+// The violated-clause pick is an exact rank select over vbits in increasing clause id
+// (prefix over l1 -> prefix over the 32 words of the group -> bit), so it is uniform over
+// the DISTINCT violated clause contents exactly as HashSet::iter().choose() is.
+#pragma once
+#include "common.h"
+#include "philox.cuh"
+
+namespace slsb {
+
+static constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// position of the r-th (0-based) set bit of w; requires r < popc(w)
+__device__ __forceinline__ uint32_t select_in_word(uint32_t w, uint32_t r)
+{
+    uint32_t pos = 0;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const uint32_t c = __popc((w >> pos) & ((1u << s) - 1u));
+        if (r >= c) {
+            r -= c;
+            pos += s;
+        }
+    }
+    return pos;
+}
+
+template <bool SMEM>
+struct Chain {
+    const DevInst& I;
+    uint32_t* abits;
+    uint32_t* vbits;
+    uint32_t* l1;
+    int lane;
+    uint32_t numfalse;
+
+    __device__ __forceinline__ Chain(const DevInst& inst, uint32_t* slab, int lane_)
+        : I(inst), abits(slab), vbits(slab + inst.nwords), l1(slab + inst.nwords + inst.mwords), lane(lane_), numfalse(0)
+    {
+    }
+
+    __device__ __forceinline__ uint32_t abit(uint32_t v) const { return (abits[v >> 5] >> (v & 31)) & 1u; }
+
+    __device__ __forceinline__ void clause_range(uint32_t c, uint32_t& s, uint32_t& e) const
+    {
+        if (I.uniform_k) {
+            s = c * I.uniform_k;
+            e = s + I.uniform_k;
+        } else {
+            s = __ldg(I.row_ptr + c);
+            e = __ldg(I.row_ptr + c + 1);
+        }
+    }
+
+    // lib.rs:13-18 with an optional tentatively flipped variable (the greedy branch, lib.rs:239/255)
+    __device__ __forceinline__ bool violated(uint32_t c, uint32_t flipped_var) const
+    {
+        uint32_t s, e;
+        clause_range(c, s, e);
+        for (uint32_t j = s; j < e; j++) {
+            const uint32_t l = __ldg(I.lits + j);
+            const uint32_t v = l >> 1;
+            uint32_t a = abit(v);
+            if (v == flipped_var) a ^= 1u;
+            if (a != (l & 1u)) return false;  // literal is true
+        }
+        return true;
+    }
+
+    // find_violated_clauses (lib.rs:176-181): rebuild vbits / l1 / numfalse from scratch
+    __device__ void full_scan()
+    {
+        const uint32_t* canon = I.canon;
+        numfalse = 0;
+        if (canon == nullptr) {
+            for (uint32_t g = 0; g < I.ngroups; g++) {
+                uint32_t acc = 0, mine = 0;
+                const uint32_t wend = min(32u, I.mwords - g * 32u);
+                for (uint32_t wi = 0; wi < wend; wi++) {
+                    const uint32_t c = (g * 32u + wi) * 32u + lane;
+                    const bool viol = c < I.m && violated(c, 0xffffffffu);
+                    const uint32_t word = __ballot_sync(FULL, viol);
+                    if ((uint32_t)lane == wi) mine = word;
+                    acc += __popc(word);
+                }
+                if ((uint32_t)lane < wend) vbits[g * 32u + lane] = mine;
+                if (lane == 0) l1[g] = acc;
+                numfalse += acc;
+            }
+        } else {
+            for (uint32_t w = lane; w < I.mwords; w += 32) vbits[w] = 0;
+            for (uint32_t g = lane; g < I.ngroups; g += 32) l1[g] = 0;
+            __syncwarp();
+            for (uint32_t base = 0; base < I.m; base += 32) {
+                const uint32_t c = base + lane;
+                bool fresh = false;
+                if (c < I.m && violated(c, 0xffffffffu)) {
+                    const uint32_t id = __ldg(canon + c);
+                    const uint32_t bit = 1u << (id & 31);
+                    const uint32_t old = atomicOr(&vbits[id >> 5], bit);
+                    if (!(old & bit)) {
+                        fresh = true;
+                        atomicAdd(&l1[id >> 10], 1u);
+                    }
+                }
+                numfalse += __popc(__ballot_sync(FULL, fresh));
+            }
+        }
+        __syncwarp();
+    }
+
+    // r-th violated clause in increasing canonical clause id; r < numfalse, warp-uniform
+    __device__ __forceinline__ uint32_t select(uint32_t r) const
+    {
+        uint32_t g = 0;
+        for (uint32_t gb = 0; gb < I.ngroups; gb += 32) {
+            const uint32_t gi = gb + lane;
+            const uint32_t cnt = gi < I.ngroups ? l1[gi] : 0u;
+            const uint32_t incl = warp_incl_scan(cnt, lane);
+            const uint32_t tot = __shfl_sync(FULL, incl, 31);
+            if (r < tot) {
+                const uint32_t src = __ffs(__ballot_sync(FULL, r < incl)) - 1;
+                g = gb + src;
+                r -= __shfl_sync(FULL, incl - cnt, src);
+                break;
+            }
+            r -= tot;
+        }
+        const uint32_t wi = g * 32u + lane;
+        const uint32_t word = wi < I.mwords ? vbits[wi] : 0u;
+        const uint32_t pc = __popc(word);
+        const uint32_t incl = warp_incl_scan(pc, lane);
+        const uint32_t src = __ffs(__ballot_sync(FULL, r < incl)) - 1;
+        r -= __shfl_sync(FULL, incl - pc, src);
+        const uint32_t wsel = __shfl_sync(FULL, word, src);
+        return (g * 32u + src) * 32u + select_in_word(wsel, r);
+    }
+
+    // lib.rs:278-287 for one flipped variable (assignment already holds the new value)
+    __device__ __forceinline__ void update_var(uint32_t v)
+    {
+        const uint32_t os = __ldg(I.occ_ptr + v), oe = __ldg(I.occ_ptr + v + 1);
+        for (uint32_t base = os; base < oe; base += 32) {
+            const uint32_t o = base + lane;
+            int delta = 0;
+            if (o < oe) {
+                const uint32_t cc = __ldg(I.occ + o);
+                const bool viol = violated(cc, 0xffffffffu);
+                const uint32_t id = I.canon ? __ldg(I.canon + cc) : cc;
+                const uint32_t bit = 1u << (id & 31);
+                if (viol) {
+                    const uint32_t old = atomicOr(&vbits[id >> 5], bit);  // HashSet::insert
+                    if (!(old & bit)) {
+                        delta = 1;
+                        atomicAdd(&l1[id >> 10], 1u);
+                    }
+                } else {
+                    const uint32_t old = atomicAnd(&vbits[id >> 5], ~bit);  // HashSet::remove
+                    if (old & bit) {
+                        delta = -1;
+                        atomicSub(&l1[id >> 10], 1u);
+                    }
+                }
+            }
+            numfalse += __popc(__ballot_sync(FULL, delta > 0));
+            numfalse -= __popc(__ballot_sync(FULL, delta < 0));
+        }
+        __syncwarp();
+    }
+
+    // greedy score of flipping v (lib.rs:236-256)
+    __device__ __forceinline__ uint64_t greedy_score(uint32_t v, bool mapping) const
+    {
+        const uint32_t os = __ldg(I.occ_ptr + v), oe = __ldg(I.occ_ptr + v + 1);
+        uint32_t after = 0, before = 0;
+        for (uint32_t base = os; base < oe; base += 32) {
+            const uint32_t o = base + lane;
+            bool cnt_after = false, cnt_before = false;
+            if (o < oe) {
+                const uint32_t cc = __ldg(I.occ + o);
+                const bool viol = violated(cc, v);
+                if (mapping) {
+                    cnt_after = viol;  // every var_to_clauses entry counts (lib.rs:243-247)
+                } else {
+                    // |find_violated_clauses(after flip)|: distinct contents only (lib.rs:249)
+                    const bool rep = (I.canon == nullptr || __ldg(I.canon + cc) == cc) &&
+                                     !(o > os && __ldg(I.occ + o - 1) == cc);
+                    cnt_after = rep && viol;
+                    cnt_before = rep && ((vbits[cc >> 5] >> (cc & 31)) & 1u);
+                }
+            }
+            after += __popc(__ballot_sync(FULL, cnt_after));
+            before += __popc(__ballot_sync(FULL, cnt_before));
+        }
+        return mapping ? (uint64_t)after : (uint64_t)numfalse - before + after;
+    }
+};
+
+// flip probability of lib.rs:29-30: (1-a)*w + a*(1-w)
+__device__ __forceinline__ double flip_prob(uint32_t a, double w) { return a ? (1.0 - w) : w; }
+
+template <bool SMEM>
+__global__ void __launch_bounds__(128) walk_generic_kernel(const WalkArgs A)
+{
+    extern __shared__ uint32_t smem_state[];
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint64_t run = (uint64_t)blockIdx.x * A.warps_per_block + warp;
+    if (run >= A.nruns) return;
+    const DevInst& I = A.inst;
+    uint32_t* slab = SMEM ? smem_state + (size_t)warp * A.slab_words : A.gstate + run * (size_t)A.slab_words;
+    Chain<SMEM> ch(I, slab, lane);
+    const uint64_t chain = A.chain_offset + run;
+
+    // ---- lib.rs:206-210: assignment[i] = gen_bool(weights_initialize[i]) on the init stream
+    {
+        const ChainKey ck(A.seed, chain, STREAM_INIT);
+        for (uint32_t w = lane; w < I.nwords; w += 32) {
+            uint32_t bits = 0;
+#pragma unroll 4
+            for (uint32_t b = 0; b < 16; b++) {
+                const uint32_t v0 = w * 32u + 2u * b;
+                if (v0 >= I.n) break;
+                const uint4 x = ck.block((uint64_t)(v0 >> 1));
+                const uint64_t t0 = __ldg(A.thr_init + v0);
+                const uint64_t u0 = (uint64_t)x.y << 32 | x.x;
+                bits |= (uint32_t)(t0 == ~0ull || u0 < t0) << (2u * b);
+                if (v0 + 1 < I.n) {
+                    const uint64_t t1 = __ldg(A.thr_init + v0 + 1);
+                    const uint64_t u1 = (uint64_t)x.w << 32 | x.z;
+                    bits |= (uint32_t)(t1 == ~0ull || u1 < t1) << (2u * b + 1u);
+                }
+            }
+            ch.abits[w] = bits;
+        }
+        __syncwarp();
+    }
+
+    WalkStream rng(A.seed, chain);
+    ch.full_scan();  // lib.rs:213-214
+
+    uint32_t best = I.m;  // lib.rs:203
+    bool has_best = false;
+    uint32_t* best_bits = A.best_bits + run * (size_t)I.nwords;
+    auto save_best = [&]() {
+        best = ch.numfalse;
+        has_best = true;
+        for (uint32_t w = lane; w < I.nwords; w += 32) best_bits[w] = ch.abits[w];
+    };
+    if (ch.numfalse < best) save_best();  // lib.rs:216-219
+    uint32_t* traj = A.want_traj ? A.traj + run * (A.nsteps + 1) : nullptr;
+    if (traj && lane == 0) traj[0] = ch.numfalse;  // lib.rs:221-223
+
+    uint64_t steps = 0, flips = 0;
+    int err = 0;
+    uint32_t mark_mask = 0;  // lane i keeps the MT marks of literals [32 i, 32 i + 32) of the picked clause
+
+    while (ch.numfalse > 0 && steps < A.nsteps) {  // lib.rs:225
+        steps++;
+        const uint32_t c = ch.select(rng.uniform_u32(ch.numfalse));  // lib.rs:229
+        uint32_t s, e;
+        ch.clause_range(c, s, e);
+        const uint32_t k = e - s;
+        const double ugreedy = rng.next_f64();  // lib.rs:231: drawn on every step
+
+        if (ugreedy < A.pfb) {
+            // ---- lib.rs:231-268 flip the literal with the fewest violations after the flip
+            uint32_t best_v = 0;
+            uint64_t min_viol = ~0ull;
+            for (uint32_t j = 0; j < k; j++) {
+                const uint32_t v = __ldg(I.lits + s + j) >> 1;
+                const uint64_t viol = ch.greedy_score(v, A.mapping != 0);
+                if (viol < min_viol) {
+                    min_viol = viol;
+                    best_v = v;
+                }
+            }
+            if (I.n == 0) {
+                err = DERR_EMPTY_CLAUSE;
+                break;
+            }
+            if (lane == 0) ch.abits[best_v >> 5] ^= 1u << (best_v & 31);
+            __syncwarp();
+            flips++;
+            ch.update_var(best_v);
+        } else if (A.algo == ALGO_MOSER || A.algo == ALGO_MOSER_SINGLE) {
+            // ---- lib.rs:24-35 / :81-92: one f64 per literal, in literal order
+            if (k > 1024) {
+                err = DERR_ARG;
+                break;
+            }
+            const uint64_t p0 = rng.reserve_u64(k);
+            uint32_t nmarks = 0;
+            for (uint32_t cb = 0; cb < k; cb += 32) {
+                const uint32_t j = cb + lane;
+                bool mark = false;
+                if (j < k) {
+                    const uint32_t v = __ldg(I.lits + s + j) >> 1;
+                    const double fp = flip_prob(ch.abit(v), __ldg(A.w + v));
+                    mark = u64_to_f64_53(rng.ck.u64_at(p0 + 2ull * j)) < fp;
+                }
+                const uint32_t mask = __ballot_sync(FULL, mark);
+                if ((uint32_t)lane == (cb >> 5)) mark_mask = mask;
+                nmarks += __popc(mask);
+            }
+            if (A.algo == ALGO_MOSER) {
+                // lib.rs:37-41: toggle every marked variable (a variable marked twice toggles twice)
+                for (uint32_t cb = 0; cb < k; cb += 32) {
+                    const uint32_t mask = __shfl_sync(FULL, mark_mask, cb >> 5);
+                    if ((mask >> lane) & 1u) {
+                        const uint32_t v = __ldg(I.lits + s + cb + lane) >> 1;
+                        atomicXor(&ch.abits[v >> 5], 1u << (v & 31));
+                    }
+                }
+                __syncwarp();
+                flips += nmarks;
+                for (uint32_t cb = 0; cb < k; cb += 32) {
+                    uint32_t mask = __shfl_sync(FULL, mark_mask, cb >> 5);
+                    while (mask) {
+                        const uint32_t j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        ch.update_var(__ldg(I.lits + s + cb + j) >> 1);
+                    }
+                }
+            } else if (nmarks) {
+                // lib.rs:94-99: flip one uniformly chosen marked variable
+                uint64_t pick = rng.uniform_u64(nmarks);
+                uint32_t v = 0;
+                for (uint32_t cb = 0; cb < k; cb += 32) {
+                    const uint32_t mask = __shfl_sync(FULL, mark_mask, cb >> 5);
+                    const uint32_t pc = __popc(mask);
+                    if (pick < pc) {
+                        v = __ldg(I.lits + s + cb + select_in_word(mask, (uint32_t)pick)) >> 1;
+                        break;
+                    }
+                    pick -= pc;
+                }
+                if (lane == 0) ch.abits[v >> 5] ^= 1u << (v & 31);
+                __syncwarp();
+                flips++;
+                ch.update_var(v);
+            }
+        } else if (A.algo == ALGO_SCHOENING) {
+            // ---- lib.rs:51-55
+            if (k == 0) {
+                err = DERR_EMPTY_CLAUSE;
+                break;
+            }
+            const uint32_t v = __ldg(I.lits + s + rng.uniform_u32(k)) >> 1;
+            if (lane == 0) ch.abits[v >> 5] ^= 1u << (v & 31);
+            __syncwarp();
+            flips++;
+            ch.update_var(v);
+        } else {
+            // ---- lib.rs:57-75 probSAT: WeightedIndex over the flip probabilities
+            if (k == 0) {
+                err = DERR_EMPTY_CLAUSE;
+                break;
+            }
+            // pass 1: total weight, summed in literal order like WeightedIndex::new
+            double total = 0.0;
+            bool invalid = false;
+            for (uint32_t cb = 0; cb < k; cb += 32) {
+                const uint32_t j = cb + lane;
+                double fp = 0.0;
+                if (j < k) {
+                    const uint32_t v = __ldg(I.lits + s + j) >> 1;
+                    fp = flip_prob(ch.abit(v), __ldg(A.w + v));
+                    invalid |= !(fp >= 0.0);
+                }
+                const uint32_t cnt = min(32u, k - cb);
+                for (uint32_t t = 0; t < cnt; t++) {
+                    const double f = __shfl_sync(FULL, fp, t);
+                    total = (cb + t == 0) ? f : total + f;
+                }
+            }
+            if (__any_sync(FULL, invalid)) {
+                err = DERR_WEIGHTS;
+                break;
+            }
+            if (total == 0.0) {
+                err = DERR_ALL_ZERO;
+                break;
+            }
+            // UniformFloat::new(0, total) then sample from 52 mantissa bits
+            double scale = total;
+            while (scale * (1.0 - 0x1p-52) >= total) scale = __longlong_as_double(__double_as_longlong(scale) - 1);
+            const double x = ((double)(rng.next_u64() >> 12) * 0x1p-52) * scale;
+            // pass 2: partition_point(cum <= x) over the first k-1 cumulative weights
+            uint32_t pick = 0;
+            double run_sum = 0.0;
+            for (uint32_t cb = 0; cb < k; cb += 32) {
+                const uint32_t j = cb + lane;
+                double fp = 0.0;
+                if (j < k) {
+                    const uint32_t v = __ldg(I.lits + s + j) >> 1;
+                    fp = flip_prob(ch.abit(v), __ldg(A.w + v));
+                }
+                double mycum = 0.0;
+                const uint32_t cnt = min(32u, k - cb);
+                for (uint32_t t = 0; t < cnt; t++) {
+                    const double f = __shfl_sync(FULL, fp, t);
+                    run_sum = (cb + t == 0) ? f : run_sum + f;
+                    if ((uint32_t)lane == t) mycum = run_sum;
+                }
+                pick += __popc(__ballot_sync(FULL, j + 1 < k && mycum <= x));
+            }
+            const uint32_t v = __ldg(I.lits + s + pick) >> 1;
+            if (lane == 0) ch.abits[v >> 5] ^= 1u << (v & 31);
+            __syncwarp();
+            flips++;
+            ch.update_var(v);
+        }
+
+        if (ch.numfalse < best) save_best();            // lib.rs:292-296
+        if (traj && lane == 0) traj[steps] = ch.numfalse;  // lib.rs:298-300
+    }
+
+    if (lane == 0) {
+        if (err) atomicCAS(A.err, 0, err);
+        A.found[run] = ch.numfalse == 0 && !err;  // lib.rs:305-307
+        A.has_best[run] = has_best;
+        A.steps[run] = steps;
+        A.best_energy[run] = best;
+        A.flips[run] = flips;
+    }
+}
+
+}  // namespace slsb

@@ -1,0 +1,246 @@
+"""CUDA path vs the CPU oracle on identical inputs and identical Philox streams (needs a B200).
+
+Bit-exact bar: violated-clause sets, energies, per-step trajectories, step counts, solved flags
+and best assignments must be identical.  All calls go through the C ABI (libsls_b200.so).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_assignments, golden_cnf, random_ksat
+from oracle import sls_oracle as so
+import sls_sat_solving_with_deep_learning_b200 as eng
+
+pytestmark = pytest.mark.gpu
+
+ALGOS = ["moser", "moser_single", "schoening", "probsat"]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    assert eng.device_count() > 0, "GPU tests need a CUDA device: the engine has no CPU fallback"
+    eng.set_device(0)
+
+
+def both(name):
+    return eng.Instance.from_dimacs(golden_cnf(name)), so.Instance.from_dimacs(golden_cnf(name))
+
+
+def assert_same_run(g, o):
+    assert (g.steps == o.steps).all()
+    assert (g.found == o.found).all()
+    assert (g.best_energy_run == o.best_energy_run).all()
+    assert (g.flips_run == o.flips_run).all()
+    assert g.best_energy == o.best_energy
+    assert (g.best_assignment is None) == (o.best_assignment is None)
+    if g.best_assignment is not None:
+        assert (g.best_assignment == o.best_assignment).all()
+    assert len(g.trajectories) == len(o.trajectories)
+    for a, b in zip(g.trajectories, o.trajectories):
+        assert a.shape == b.shape and (a == b).all()
+
+
+# ---- clause evaluation ------------------------------------------------------------------------
+def test_eval_reference_known_answers():  # python/tests/test_sat_instances.py:69-135
+    gi = eng.Instance.from_text("p cnf 1 2 \n 1 0 \n -1 0")
+    assert [int(eng.get_violated_constraints(gi, [a]).sum()) for a in (0, 1)] == [1, 1]
+    gi = eng.Instance.from_text("p cnf 3 2 \n 1 2 0 \n 3 0")
+    assert eng.get_violated_constraints(gi, [0, 0, 1]).tolist() == [1, 0]
+    assert eng.get_violated_constraints(gi, [0, 1, 1]).tolist() == [0, 0]
+    assert eng.get_violated_constraints(gi, [0, 1, 0]).tolist() == [0, 1]
+    import itertools
+
+    text = "p cnf 4 16 \n"
+    for bits in itertools.product([0, 1], repeat=4):
+        text += " ".join(str((i + 1) * (1 if b else -1)) for i, b in enumerate(bits)) + " 0 \n"
+    gi = eng.Instance.from_text(text)
+    viol, energy = eng.eval_assignments(gi, np.asarray(list(itertools.product([0, 1], repeat=4))))
+    assert (energy == 1).all() and (viol.sum(axis=1) == 1).all()
+
+
+def test_eval_golden_fixtures(expected):
+    for name, info in expected.items():
+        gi, oi = both(name)
+        rows = golden_assignments(name, gi.n)
+        viol, energy = eng.eval_assignments(gi, rows)
+        assert energy.tolist() == info["energies"], name
+        for b in range(rows.shape[0]):
+            assert (viol[b] == oi.eval_clauses(rows[b])).all(), (name, b)
+
+
+def test_eval_ragged_batches_and_shapes():
+    rng = np.random.default_rng(0)
+    for n, m, k in [(1, 1, 1), (33, 65, 2), (100, 31, 3), (257, 1025, 3), (64, 2049, 5)]:
+        clauses = random_ksat(n, m, min(k, n), seed=n + m)
+        gi = eng.Instance.from_clauses(n, clauses)
+        oi = so.Instance.from_clauses(n, clauses)
+        for B in (1, 31, 32, 33, 100):
+            a = rng.integers(0, 2, size=(B, n))
+            viol, energy = eng.eval_assignments(gi, a)
+            for b in range(B):
+                assert (viol[b] == oi.eval_clauses(a[b])).all()
+                assert energy[b] == oi.energy(a[b])
+    gi = eng.Instance.from_text("p cnf 3 2\n0\n1 2 0\n")  # an empty clause is always violated (lib.rs:13-18)
+    viol, energy = eng.eval_assignments(gi, [[1, 1, 1]])
+    assert viol.tolist() == [[1, 0]] and energy.tolist() == [1]
+
+
+def test_eval_full_size_c2_properties():
+    # BASELINE config 2 shape (n=10k, m=42k): size-independent properties
+    n, m = 10_000, 42_000
+    clauses = random_ksat(n, m, 3, seed=20260102)
+    gi = eng.Instance.from_clauses(n, clauses)
+    oi = so.Instance.from_clauses(n, clauses)
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 2, size=(96, n))
+    viol, energy = eng.eval_assignments(gi, a)
+    assert (viol.sum(axis=1) == energy).all()
+    for b in (0, 47, 95):
+        assert (viol[b] == oi.eval_clauses(a[b])).all()
+    # complementing an assignment and every literal sign gives the same violated set
+    neg = eng.Instance.from_clauses(n, [tuple(-l for l in c) for c in clauses])
+    viol2, energy2 = eng.eval_assignments(neg, 1 - a)
+    assert (viol2 == viol).all() and (energy2 == energy).all()
+
+
+# ---- the walk: trajectory-exact against the oracle ---------------------------------------------
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("pfb", [0.0, 0.35])
+@pytest.mark.parametrize("mapping", [True, False])
+def test_walk_k3_kernel_matches_oracle(algo, pfb, mapping):
+    name = "r3sat_test_random_KCNF3_200_869_9397183"
+    gi, oi = both(name)
+    rng = np.random.default_rng(3)
+    w_init = rng.uniform(0.05, 0.95, gi.n)
+    w_res = rng.uniform(0.05, 0.95, gi.n)
+    g = eng.run_sls(gi, algo, w_init, w_res, 600, 40, True, mapping, pfb, seed=21)
+    o = oi.run_sls(algo, w_init, w_res, 600, 40, True, mapping, pfb, seed=21)
+    assert_same_run(g, o)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("pfb", [0.0, 0.35])
+@pytest.mark.parametrize("mapping", [True, False])
+@pytest.mark.parametrize("name", ["ref_tests_medium", "g4sat_hard_ps_00041"])
+def test_walk_generic_kernel_matches_oracle(algo, pfb, mapping, name):
+    gi, oi = both(name)  # mixed clause lengths (k up to 6 / long pseudo-industrial clauses)
+    rng = np.random.default_rng(4)
+    w_init = rng.uniform(0.05, 0.95, gi.n)
+    w_res = rng.uniform(0.05, 0.95, gi.n)
+    g = eng.run_sls(gi, algo, w_init, w_res, 400, 24, True, mapping, pfb, seed=22)
+    o = oi.run_sls(algo, w_init, w_res, 400, 24, True, mapping, pfb, seed=22)
+    assert_same_run(g, o)
+
+
+@pytest.mark.parametrize("force", [{"SLS_B200_FORCE_GENERIC": "1"}, {"SLS_B200_FORCE_STATE": "hbm"},
+                                   {"SLS_B200_FORCE_GENERIC": "1", "SLS_B200_FORCE_STATE": "hbm"}])
+@pytest.mark.parametrize("algo", ALGOS)
+def test_walk_all_kernel_variants_agree(force, algo, monkeypatch):
+    name = "r3sat_test_random_KCNF3_300_990_9917523"
+    gi, oi = both(name)
+    w = np.full(gi.n, 0.5)
+    for k, v in force.items():
+        monkeypatch.setenv(k, v)
+    g = eng.run_sls(gi, algo, w, w, 500, 33, True, True, 0.2, seed=5)
+    o = oi.run_sls(algo, w, w, 500, 33, True, True, 0.2, seed=5)
+    assert_same_run(g, o)
+
+
+def test_walk_all_golden_instances(expected):
+    for name in expected:
+        gi, oi = both(name)
+        w = np.full(gi.n, 0.5)
+        for algo in ("moser", "probsat"):
+            g = eng.run_sls(gi, algo, w, w, 300, 10, True, True, 0.0, seed=8)
+            o = oi.run_sls(algo, w, w, 300, 10, True, True, 0.0, seed=8)
+            assert_same_run(g, o)
+
+
+def test_walk_duplicate_clauses_and_repeated_variables():
+    # duplicate contents are ONE violated-set element (lib.rs:176-181); a variable twice in a clause
+    # appears twice in var_to_clauses (lib.rs:190-195)
+    text = "p cnf 6 9\n1 2 3 0\n1 2 3 0\n-1 -2 0\n4 4 5 0\n-4 -5 6 0\n1 2 3 0\n-6 0\n3 -3 1 0\n-1 -1 0\n"
+    gi, oi = eng.Instance.from_text(text), so.Instance.from_text(text)
+    w = np.full(6, 0.5)
+    for algo in ALGOS:
+        for pfb in (0.0, 0.5):
+            for mapping in (True, False):
+                g = eng.run_sls(gi, algo, w * 0, w, 200, 50, True, mapping, pfb, seed=13)
+                o = oi.run_sls(algo, w * 0, w, 200, 50, True, mapping, pfb, seed=13)
+                assert_same_run(g, o)
+
+
+def test_walk_edge_cases():
+    gi, oi = both("ref_tests_medium")
+    w = np.full(gi.n, 0.5)
+    # nruns = 0 / nsteps = 0
+    g = eng.run_sls(gi, "moser", w, w, 10, 0, True)
+    assert g.best_energy == gi.m and g.best_assignment is None and len(g.found) == 0 and g.trajectories == []
+    assert_same_run(eng.run_sls(gi, "moser", w, w, 0, 7, True, seed=2), oi.run_sls("moser", w, w, 0, 7, True, seed=2))
+    # exact solution as initial weights: zero steps
+    sol = golden_assignments("ref_tests_medium", gi.n)[0].astype(float)
+    g = eng.run_sls(gi, "probsat", sol, sol, 50, 9, True, seed=1)
+    assert g.found.all() and (g.steps == 0).all() and (g.best_assignment == sol).all()
+    # every clause violated, nsteps = 0: the reference returns an empty best assignment
+    gi2 = eng.Instance.from_text("p cnf 2 2\n1 0\n2 0\n")
+    g = eng.run_sls(gi2, "moser", [0, 0], [0.5, 0.5], 0, 3)
+    assert g.best_energy == 2 and g.best_assignment is None and g.as_reference_tuple()[0] == []
+    # chain_offset keeps streams stable under sharding
+    a = eng.run_sls(gi, "probsat", w, w, 200, 16, True, seed=4)
+    b = eng.run_sls(gi, "probsat", w, w, 200, 8, True, seed=4, chain_offset=8)
+    assert all((x == y).all() for x, y in zip(a.trajectories[8:], b.trajectories))
+    # without trajectories the other outputs are unchanged
+    c = eng.run_sls(gi, "probsat", w, w, 200, 16, False, seed=4)
+    assert (a.steps == c.steps).all() and (a.best_assignment == c.best_assignment).all() and c.trajectories == []
+
+
+def test_walk_error_behaviour():
+    gi = eng.Instance.from_text("p cnf 2 2\n1 2 0\n-1 -2 0\n")
+    with pytest.raises(eng.PanicException):  # WeightedIndex AllWeightsZero (lib.rs:71)
+        eng.run_sls(gi, "probsat", [0, 0], [0.0, 0.0], 10, 4, seed=2)
+    with pytest.raises(eng.PanicException):  # gen_bool outside [0,1] (lib.rs:209)
+        eng.run_sls(gi, "moser", [0.5, 1.5], [0.5, 0.5], 10, 4)
+    with pytest.raises(eng.PanicException):  # short weight vector
+        eng.run_sls(gi, "moser", [0.5], [0.5, 0.5], 10, 4)
+    gi = eng.Instance.from_text("p cnf 2 2\n0\n1 2 0\n")  # empty clause: choose() on it panics
+    with pytest.raises(eng.PanicException):
+        eng.run_sls(gi, "schoening", [0.5, 0.5], [0.5, 0.5], 10, 4, seed=1)
+    # ... but Moser-Tardos just resamples nothing (lib.rs:24-35) and never terminates early
+    g = eng.run_sls(gi, "moser", [0.5, 0.5], [0.5, 0.5], 20, 4, seed=1)
+    assert (g.steps == 20).all() and not g.found.any()
+
+
+def test_run_sls_python_drop_in_tuple():
+    import moser_rust
+
+    moser_rust.set_seed(1234)
+    path = golden_cnf("r3sat_test_random_KCNF3_100_210_6416893")
+    p = np.ones(100) / 2
+    best, found, energy, steps, traj = moser_rust.run_sls_python("moser", path, p, p, 999, 20, True, True, 0)
+    assert isinstance(best, list) and isinstance(found, list) and isinstance(energy, int) and isinstance(steps, list)
+    assert len(found) == 20 and len(steps) == 20 and len(traj) == 20 and len(best) == 100
+    padded = np.array([np.pad(t, (0, 1000 - len(t))) for t in traj])  # evaluate_with_given_params.py:18-23
+    assert padded.shape == (20, 1000)
+    _, _, e2, _, t2 = moser_rust.run_sls_python(
+        "probsat", path, p, p, 99, 3, return_trajectories=False, pre_compute_mapping=True, prob_flip_best=0
+    )  # train_utils.py:293-303
+    assert len(t2) == 0 and isinstance(e2, int)
+    moser_rust.set_seed(None)
+
+
+def test_walk_c2_shape_statistics_and_invariants():
+    # BASELINE config 2 shape at reduced chain/step counts: first 3 chains trajectory-exact, all
+    # chains consistent with their own outputs
+    n, m = 10_000, 42_000
+    clauses = random_ksat(n, m, 3, seed=20260102)
+    gi = eng.Instance.from_clauses(n, clauses)
+    oi = so.Instance.from_clauses(n, clauses)
+    w = np.full(n, 0.5)
+    g = eng.run_sls(gi, "probsat", w, w, 3000, 256, True, True, 0.0, seed=99)
+    o = oi.run_sls("probsat", w, w, 3000, 3, True, True, 0.0, seed=99)
+    for r in range(3):
+        assert (g.trajectories[r] == o.trajectories[r]).all()
+    assert (g.flips_run == g.steps).all() and (g.steps == 3000).all()
+    assert oi.energy_distinct(g.best_assignment) == g.best_energy == g.best_energy_run.min()
+    assert all(t.min() == e for t, e in zip(g.trajectories, g.best_energy_run))
