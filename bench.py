@@ -313,13 +313,17 @@ def run_own(args, rank, world, local_rank):
 
 
 def main():
+    global NSTEPS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nsteps-per-chain", type=int, default=NSTEPS,
+                    help="profiling only: shorten the chains (the default is the BASELINE workload)")
     args = ap.parse_args()
+    NSTEPS = args.nsteps_per_chain
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
