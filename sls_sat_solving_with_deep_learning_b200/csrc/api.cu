@@ -135,6 +135,10 @@ int ensure_on_device(sls_instance* inst)
     d.nwords = (h.n + 31) / 32;
     d.mwords = (h.m + 31) / 32;
     d.ngroups = (d.mwords + 31) / 32;
+    d.off_v = (d.nwords + 3u) & ~3u;
+    d.off_l1 = d.off_v + ((d.mwords + 3u) & ~3u);
+    d.l1_pad = std::max(64u, (d.ngroups + 63u) & ~63u);
+    d.slab_words = d.off_l1 + d.l1_pad;
     d.uniform_k = h.uniform_k;
     d.max_k = h.max_k;
     d.flags = (h.has_duplicates ? INST_HAS_DUPLICATES : 0u) | (h.k3 ? INST_K3 : 0u);
@@ -314,7 +318,7 @@ struct sls_solver {
     // device buffers
     uint64_t* d_thr = nullptr;
     double* d_w = nullptr;
-    uint4* d_vrec = nullptr;
+    uint4* d_crecx = nullptr;
     uint32_t* d_gstate = nullptr;
     uint32_t* d_best_bits = nullptr;
     uint8_t* d_found = nullptr;
@@ -335,7 +339,7 @@ extern "C" void sls_solver_free(sls_solver* s)
     if (!s) return;
     cudaFree(s->d_thr);
     cudaFree(s->d_w);
-    cudaFree(s->d_vrec);
+    cudaFree(s->d_crecx);
     cudaFree(s->d_gstate);
     cudaFree(s->d_best_bits);
     cudaFree(s->d_found);
@@ -382,8 +386,7 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     SC_TRY(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, s->device));
 
     // chain state slab: assignment bits | violated bits | level-1 counters
-    const uint32_t slab_words = (I.nwords + I.mwords + I.ngroups + 3u) & ~3u;
-    const size_t slab_bytes = size_t(slab_words) * 4;
+    const size_t slab_bytes = size_t(I.slab_words) * 4;
     // Tier choice: keep the chain state in shared memory when enough chains fit per SM to cover
     // this call's share of chains (or at least 16 warps); otherwise the state lives in HBM.
     uint32_t wpb = 4;
@@ -411,7 +414,7 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
 
     SC_TRY(cudaMalloc(&s->d_thr, std::max<size_t>(I.n, 1) * 8));
     SC_TRY(cudaMalloc(&s->d_w, std::max<size_t>(I.n, 1) * 8));
-    if (s->k3) SC_TRY(cudaMalloc(&s->d_vrec, std::max<size_t>(I.n, 1) * sizeof(uint4)));
+    if (s->k3) SC_TRY(cudaMalloc(&s->d_crecx, std::max<size_t>(I.m, 1) * 4 * sizeof(uint4)));
     if (!s->smem_state) SC_TRY(cudaMalloc(&s->d_gstate, R1 * slab_bytes));
     SC_TRY(cudaMalloc(&s->d_best_bits, R1 * std::max<size_t>(I.nwords, 1) * 4));
     SC_TRY(cudaMalloc(&s->d_found, R1));
@@ -435,7 +438,7 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     a.inst = I;
     a.thr_init = s->d_thr;
     a.w = s->d_w;
-    a.vrec = s->d_vrec;
+    a.crecx = s->d_crecx;
     a.algo = params->algo;
     a.mapping = params->pre_compute_mapping;
     a.want_traj = params->return_trajectories;
@@ -445,7 +448,6 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     a.seed = params->seed;
     a.chain_offset = params->chain_offset;
     a.gstate = s->d_gstate;
-    a.slab_words = slab_words;
     a.warps_per_block = s->wpb;
     a.best_bits = s->d_best_bits;
     a.found = s->d_found;
@@ -494,17 +496,12 @@ extern "C" int sls_solver_set_weights(sls_solver* s, const double* w_init, size_
         CUDA_TRY(cudaMemcpy(s->d_w, w_resample, size_t(n) * 8, cudaMemcpyHostToDevice));
     else if (n)
         CUDA_TRY(cudaMemset(s->d_w, 0, size_t(n) * 8));
-    if (s->d_vrec && n) {
-        // per-variable record of the k<=3 kernel: resample weight + occurrence range
-        const HostInstance& h = s->inst->host;
-        std::vector<uint4> vrec(n);
-        for (uint32_t v = 0; v < n; v++) {
-            const double w = w_resample_len >= n ? w_resample[v] : 0.0;
-            uint64_t bits;
-            std::memcpy(&bits, &w, 8);
-            vrec[v] = make_uint4((uint32_t)bits, (uint32_t)(bits >> 32), h.occ_ptr[v], h.occ_ptr[v + 1] - h.occ_ptr[v]);
-        }
-        CUDA_TRY(cudaMemcpy(s->d_vrec, vrec.data(), size_t(n) * sizeof(uint4), cudaMemcpyHostToDevice));
+    if (s->d_crecx && s->inst->host.m) {
+        // 64-byte clause records of the k<=3 kernel: literals + occurrence ranges + resample weights
+        const DevInst& I = s->inst->dev;
+        build_crecx_kernel<<<(I.m + 255) / 256, 256>>>(I.crec, I.occ_ptr, s->d_w, s->d_crecx, I.m);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
     }
     s->weights_set = true;
     return SLS_OK;

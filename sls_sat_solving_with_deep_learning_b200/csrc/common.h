@@ -16,6 +16,10 @@ struct DevInst {
     uint32_t nwords;   // ceil(n/32)   assignment bitmap words
     uint32_t mwords;   // ceil(m/32)   violated-set bitmap words
     uint32_t ngroups;  // ceil(mwords/32) level-1 counters (1024 clauses each)
+    // chain-state slab layout (words): abits at 0, vbits at off_v, level-1 counters at off_l1;
+    // the counter array is zero-padded to l1_pad (a multiple of 64) entries so that a lane can
+    // fetch its two counters with one 8-byte load
+    uint32_t off_v, off_l1, l1_pad, slab_words;
     uint32_t uniform_k;// clause length when all clauses share it, else 0
     uint32_t max_k;
     uint32_t flags;    // INST_*
@@ -38,7 +42,7 @@ struct WalkArgs {
     DevInst inst;
     const uint64_t* thr_init;  // [n] Bernoulli thresholds of weights_initialize (lib.rs:208-210)
     const double* w;           // [n] weights_resample
-    const uint4* vrec;         // [n] {weight lo, weight hi, occ_start, occ_len} (k<=3 path) or nullptr
+    const uint4* crecx;        // [m][4] 64-byte clause record of the k<=3 path (walk_k3.cuh) or nullptr
     int32_t algo;
     int32_t mapping;           // pre_compute_mapping (only changes the greedy score, lib.rs:242-250)
     int32_t want_traj;
@@ -49,8 +53,8 @@ struct WalkArgs {
     uint64_t seed;
     uint64_t chain_offset;
     uint32_t* gstate;          // [nruns][slab_words] chain state when it lives in HBM
-    uint32_t slab_words;       // nwords + mwords + ngroups (+pad)
     uint32_t warps_per_block;
+    uint32_t pad2;
     uint32_t* best_bits;       // [nruns][nwords]
     uint8_t* found;            // [nruns]
     uint8_t* has_best;         // [nruns]

@@ -117,6 +117,80 @@ struct WalkStream {
     }
 };
 
+// Warp-cooperative view of the same walk stream: the 32 lanes of the warp that owns the chain hold
+// 32 consecutive Philox blocks (128 words), lane i the block base/4 + i, so one refill costs each
+// lane a single Philox evaluation and a draw is one or two shuffles.  Word positions, alignment
+// rules and distributions are exactly those of WalkStream; all methods are warp-collective and
+// return warp-uniform values.
+struct WarpStream {
+    ChainKey ck;
+    uint64_t base;  // word position of lane 0's block, multiple of 4
+    uint32_t off;   // cursor relative to base
+    uint4 blk;
+    int lane;
+    __device__ __forceinline__ WarpStream(uint64_t seed, uint64_t chain, int lane_)
+        : ck(seed, chain, STREAM_WALK), base(0), off(0), lane(lane_)
+    {
+        blk = ck.block((uint64_t)lane);
+    }
+    __device__ __forceinline__ uint64_t pos() const { return base + off; }
+    __device__ __forceinline__ void refill()
+    {
+        base += off & ~3u;
+        off &= 3u;
+        blk = ck.block((base >> 2) + lane);
+    }
+    __device__ __forceinline__ uint32_t next_u32()
+    {
+        if (off >= 128u) refill();
+        const uint32_t c = off & 3u;
+        const uint32_t mine = c == 0 ? blk.x : c == 1 ? blk.y : c == 2 ? blk.z : blk.w;
+        const uint32_t v = __shfl_sync(0xffffffffu, mine, off >> 2);
+        off++;
+        return v;
+    }
+    __device__ __forceinline__ uint64_t next_u64()
+    {
+        off = (off + 1u) & ~1u;
+        if (off >= 128u) refill();
+        const bool hi_half = (off & 2u) != 0;
+        const uint32_t lo = __shfl_sync(0xffffffffu, hi_half ? blk.z : blk.x, off >> 2);
+        const uint32_t hi = __shfl_sync(0xffffffffu, hi_half ? blk.w : blk.y, off >> 2);
+        off += 2u;
+        return (uint64_t)hi << 32 | lo;
+    }
+    // consume a 64-bit draw whose value is not needed
+    __device__ __forceinline__ void skip_u64() { off = ((off + 1u) & ~1u) + 2u; }
+    __device__ __forceinline__ double next_f64() { return (double)(next_u64() >> 11) * 0x1p-53; }
+    __device__ __forceinline__ uint32_t uniform_u32(uint32_t range)
+    {
+        const uint32_t zone = (range << __clz(range)) - 1u;
+        for (;;) {
+            const uint32_t v = next_u32();
+            if (v * range <= zone) return __umulhi(v, range);
+        }
+    }
+    __device__ __forceinline__ uint64_t uniform_u64(uint64_t range)
+    {
+        const uint64_t zone = (range << __clzll(range)) - 1ull;
+        for (;;) {
+            const uint64_t v = next_u64();
+            if (v * range <= zone) return __umul64hi(v, range);
+        }
+    }
+    // reserve `count` aligned u64 slots for per-lane direct generation (ck.u64_at)
+    __device__ __forceinline__ uint64_t reserve_u64(uint64_t count)
+    {
+        off = (off + 1u) & ~1u;
+        const uint64_t p = base + off;
+        const uint64_t np = p + 2 * count;
+        base = np & ~3ull;
+        off = (uint32_t)(np & 3ull);
+        blk = ck.block((base >> 2) + lane);
+        return p;
+    }
+};
+
 __device__ __forceinline__ double u64_to_f64_53(uint64_t x) { return (double)(x >> 11) * 0x1p-53; }
 
 }  // namespace slsb

@@ -55,7 +55,7 @@ struct Chain {
     uint32_t numfalse;
 
     __device__ __forceinline__ Chain(const DevInst& inst, uint32_t* slab, int lane_)
-        : I(inst), abits(slab), vbits(slab + inst.nwords), l1(slab + inst.nwords + inst.mwords), lane(lane_), numfalse(0)
+        : I(inst), abits(slab), vbits(slab + inst.off_v), l1(slab + inst.off_l1), lane(lane_), numfalse(0)
     {
     }
 
@@ -92,6 +92,8 @@ struct Chain {
     {
         const uint32_t* canon = I.canon;
         numfalse = 0;
+        for (uint32_t g = lane; g < I.l1_pad; g += 32) l1[g] = 0;
+        __syncwarp();
         if (canon == nullptr) {
             for (uint32_t g = 0; g < I.ngroups; g++) {
                 uint32_t acc = 0, mine = 0;
@@ -109,7 +111,6 @@ struct Chain {
             }
         } else {
             for (uint32_t w = lane; w < I.mwords; w += 32) vbits[w] = 0;
-            for (uint32_t g = lane; g < I.ngroups; g += 32) l1[g] = 0;
             __syncwarp();
             for (uint32_t base = 0; base < I.m; base += 32) {
                 const uint32_t c = base + lane;
@@ -129,22 +130,32 @@ struct Chain {
         __syncwarp();
     }
 
-    // r-th violated clause in increasing canonical clause id; r < numfalse, warp-uniform
+    // r-th violated clause in increasing canonical clause id; r < numfalse, warp-uniform.
+    // Level A: each lane owns two adjacent level-1 counters (one 8-byte load), a warp scan finds
+    // the group; level B: the 32 words of the group, a warp scan finds the word, a ballot the bit.
     __device__ __forceinline__ uint32_t select(uint32_t r) const
     {
         uint32_t g = 0;
-        for (uint32_t gb = 0; gb < I.ngroups; gb += 32) {
-            const uint32_t gi = gb + lane;
-            const uint32_t cnt = gi < I.ngroups ? l1[gi] : 0u;
-            const uint32_t incl = warp_incl_scan(cnt, lane);
-            const uint32_t tot = __shfl_sync(FULL, incl, 31);
-            if (r < tot) {
-                const uint32_t src = __ffs(__ballot_sync(FULL, r < incl)) - 1;
-                g = gb + src;
-                r -= __shfl_sync(FULL, incl - cnt, src);
-                break;
+        for (uint32_t gb = 0;; gb += 64) {
+            const uint2 cc = reinterpret_cast<const uint2*>(l1)[(gb >> 1) + lane];
+            const uint32_t both = cc.x + cc.y;
+            const uint32_t incl = warp_incl_scan(both, lane);
+            if (gb + 64 < I.l1_pad) {
+                const uint32_t tot = __shfl_sync(FULL, incl, 31);
+                if (r >= tot) {
+                    r -= tot;
+                    continue;
+                }
             }
-            r -= tot;
+            const uint32_t src = __ffs(__ballot_sync(FULL, r < incl)) - 1;
+            r -= __shfl_sync(FULL, incl - both, src);
+            const uint32_t first = __shfl_sync(FULL, cc.x, src);
+            g = gb + 2 * src;
+            if (r >= first) {
+                r -= first;
+                g++;
+            }
+            break;
         }
         const uint32_t wi = g * 32u + lane;
         const uint32_t word = wi < I.mwords ? vbits[wi] : 0u;
@@ -153,7 +164,9 @@ struct Chain {
         const uint32_t src = __ffs(__ballot_sync(FULL, r < incl)) - 1;
         r -= __shfl_sync(FULL, incl - pc, src);
         const uint32_t wsel = __shfl_sync(FULL, word, src);
-        return (g * 32u + src) * 32u + select_in_word(wsel, r);
+        // lane i holds the answer iff bit i is set and exactly r set bits lie below it
+        const bool hit = ((wsel >> lane) & 1u) && __popc(wsel & ((1u << lane) - 1u)) == r;
+        return (g * 32u + src) * 32u + (__ffs(__ballot_sync(FULL, hit)) - 1);
     }
 
     // lib.rs:278-287 for one flipped variable (assignment already holds the new value)
@@ -228,7 +241,7 @@ __global__ void __launch_bounds__(128) walk_generic_kernel(const WalkArgs A)
     const uint64_t run = (uint64_t)blockIdx.x * A.warps_per_block + warp;
     if (run >= A.nruns) return;
     const DevInst& I = A.inst;
-    uint32_t* slab = SMEM ? smem_state + (size_t)warp * A.slab_words : A.gstate + run * (size_t)A.slab_words;
+    uint32_t* slab = SMEM ? smem_state + (size_t)warp * I.slab_words : A.gstate + run * (size_t)I.slab_words;
     Chain<SMEM> ch(I, slab, lane);
     const uint64_t chain = A.chain_offset + run;
 
@@ -256,7 +269,7 @@ __global__ void __launch_bounds__(128) walk_generic_kernel(const WalkArgs A)
         __syncwarp();
     }
 
-    WalkStream rng(A.seed, chain);
+    WarpStream rng(A.seed, chain, lane);
     ch.full_scan();  // lib.rs:213-214
 
     uint32_t best = I.m;  // lib.rs:203
