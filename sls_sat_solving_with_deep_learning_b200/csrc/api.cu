@@ -132,11 +132,11 @@ int ensure_on_device(sls_instance* inst)
     DevInst& d = inst->dev;
     d.n = h.n;
     d.m = h.m;
-    d.nwords = (h.n + 31) / 32;
+    d.nwords = (h.n + 32) / 32;  // one spare bit: the dummy variable n of the k<=3 path
     d.mwords = (h.m + 31) / 32;
     d.ngroups = (d.mwords + 31) / 32;
     d.off_v = (d.nwords + 3u) & ~3u;
-    d.off_l1 = d.off_v + ((d.mwords + 3u) & ~3u);
+    d.off_l1 = d.off_v + ((d.mwords + 31u) & ~31u);  // vbits zero-padded to whole 32-word groups
     d.l1_pad = std::max(64u, (d.ngroups + 63u) & ~63u);
     d.slab_words = d.off_l1 + d.l1_pad;
     d.uniform_k = h.uniform_k;
@@ -407,14 +407,15 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     s->smem_state = smem_ok;
     s->wpb = smem_ok ? wpb : 4;
     s->smem_bytes = smem_ok ? s->wpb * slab_bytes : 0;
-    s->k3 = (I.flags & INST_K3) != 0;
+    // the fast kernel: k<=3 instance, chain state in shared memory, at most 64 level-1 counters
+    s->k3 = (I.flags & INST_K3) != 0 && s->smem_state && I.l1_pad == 64;
     if (const char* f = std::getenv("SLS_B200_FORCE_GENERIC"))
         if (f[0] == '1') s->k3 = false;
-    s->variant = std::string(s->k3 ? "walk_k3<" : "walk_generic<") + (s->smem_state ? "smem" : "hbm") + ">";
+    s->variant = s->k3 ? "walk_k3s<smem>" : std::string("walk_generic<") + (s->smem_state ? "smem" : "hbm") + ">";
 
     SC_TRY(cudaMalloc(&s->d_thr, std::max<size_t>(I.n, 1) * 8));
     SC_TRY(cudaMalloc(&s->d_w, std::max<size_t>(I.n, 1) * 8));
-    if (s->k3) SC_TRY(cudaMalloc(&s->d_crecx, std::max<size_t>(I.m, 1) * 4 * sizeof(uint4)));
+    if (s->k3) SC_TRY(cudaMalloc(&s->d_crecx, std::max<size_t>(I.m, 1) * CRECX_QUADS * sizeof(uint4)));
     if (!s->smem_state) SC_TRY(cudaMalloc(&s->d_gstate, R1 * slab_bytes));
     SC_TRY(cudaMalloc(&s->d_best_bits, R1 * std::max<size_t>(I.nwords, 1) * 4));
     SC_TRY(cudaMalloc(&s->d_found, R1));
@@ -429,7 +430,7 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     if (s->smem_bytes) {
         SC_TRY(cudaFuncSetAttribute(walk_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)s->smem_bytes));
-        SC_TRY(cudaFuncSetAttribute(walk_k3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SC_TRY(cudaFuncSetAttribute(walk_k3s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)s->smem_bytes));
     }
 #undef SC_TRY
@@ -496,10 +497,15 @@ extern "C" int sls_solver_set_weights(sls_solver* s, const double* w_init, size_
         CUDA_TRY(cudaMemcpy(s->d_w, w_resample, size_t(n) * 8, cudaMemcpyHostToDevice));
     else if (n)
         CUDA_TRY(cudaMemset(s->d_w, 0, size_t(n) * 8));
+    {
+        bool interior = w_resample_len >= n;
+        for (uint32_t i = 0; i < n && interior; i++) interior = w_resample[i] > 0.0 && w_resample[i] < 1.0;
+        s->args.wflags = interior ? WF_INTERIOR : 0u;
+    }
     if (s->d_crecx && s->inst->host.m) {
         // 64-byte clause records of the k<=3 kernel: literals + occurrence ranges + resample weights
         const DevInst& I = s->inst->dev;
-        build_crecx_kernel<<<(I.m + 255) / 256, 256>>>(I.crec, I.occ_ptr, s->d_w, s->d_crecx, I.m);
+        build_crecx_kernel<<<(I.m + 255) / 256, 256>>>(I.crec, I.occ_ptr, s->d_w, s->d_crecx, I.m, I.n);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaDeviceSynchronize());
     }
@@ -520,10 +526,7 @@ extern "C" int sls_solver_launch(sls_solver* s, void* cuda_stream)
     CUDA_TRY(cudaEventRecord(s->ev0, st));
     const bool use_k3 = s->k3 && walk_k3_supports(s->args);
     if (use_k3) {
-        if (s->smem_state)
-            walk_k3_kernel<true><<<blocks, threads, s->smem_bytes, st>>>(s->args);
-        else
-            walk_k3_kernel<false><<<blocks, threads, 0, st>>>(s->args);
+        walk_k3s_kernel<<<blocks, threads, s->smem_bytes, st>>>(s->args);
     } else {
         if (s->smem_state)
             walk_generic_kernel<true><<<blocks, threads, s->smem_bytes, st>>>(s->args);
@@ -613,7 +616,7 @@ extern "C" int sls_solver_fetch(sls_solver* s, sls_run_result* res)
     if (winner < R && has_best[winner]) {
         res->has_best_assignment = 1;
         if (res->best_assignment) {
-            const uint32_t nwords = (h.n + 31) / 32;
+            const uint32_t nwords = s->inst->dev.nwords;
             std::vector<uint32_t> bits(std::max<uint32_t>(nwords, 1));
             CUDA_TRY(cudaMemcpy(bits.data(), s->d_best_bits + winner * nwords, size_t(nwords) * 4,
                                 cudaMemcpyDeviceToHost));

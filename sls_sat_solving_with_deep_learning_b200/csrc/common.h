@@ -13,7 +13,7 @@ namespace slsb {
 struct DevInst {
     uint32_t n;        // variables
     uint32_t m;        // clauses (formula.len(), duplicates included)
-    uint32_t nwords;   // ceil(n/32)   assignment bitmap words
+    uint32_t nwords;   // ceil((n+1)/32) assignment bitmap words; bit n is a dummy variable that stays 0
     uint32_t mwords;   // ceil(m/32)   violated-set bitmap words
     uint32_t ngroups;  // ceil(mwords/32) level-1 counters (1024 clauses each)
     // chain-state slab layout (words): abits at 0, vbits at off_v, level-1 counters at off_l1;
@@ -42,11 +42,11 @@ struct WalkArgs {
     DevInst inst;
     const uint64_t* thr_init;  // [n] Bernoulli thresholds of weights_initialize (lib.rs:208-210)
     const double* w;           // [n] weights_resample
-    const uint4* crecx;        // [m][4] 64-byte clause record of the k<=3 path (walk_k3.cuh) or nullptr
+    const uint4* crecx;        // [m][6] 96-byte clause record of the k<=3 path (walk_k3.cuh) or nullptr
     int32_t algo;
     int32_t mapping;           // pre_compute_mapping (only changes the greedy score, lib.rs:242-250)
     int32_t want_traj;
-    int32_t pad;
+    uint32_t wflags;           // WF_*
     double pfb;                // prob_flip_best
     uint64_t nsteps;
     uint64_t nruns;
@@ -64,6 +64,10 @@ struct WalkArgs {
     uint32_t* traj;            // [nruns][nsteps+1] or nullptr
     int32_t* err;              // first error code raised by any chain
 };
+
+// weights_resample lies strictly inside (0,1): every flip probability is positive and finite,
+// so probSAT's InvalidWeight / AllWeightsZero checks (lib.rs:71) cannot fire
+enum : uint32_t { WF_INTERIOR = 1u };
 
 // error codes raised on the device (same numbering as include/sls_b200.h)
 enum : int { DERR_WEIGHTS = 4, DERR_ALL_ZERO = 5, DERR_EMPTY_CLAUSE = 6, DERR_ARG = 7 };

@@ -134,15 +134,29 @@ struct WarpStream {
         blk = ck.block((uint64_t)lane);
     }
     __device__ __forceinline__ uint64_t pos() const { return base + off; }
+    // The key passes through an opaque asm so that the compiler cannot hoist the Philox key
+    // schedule (18 adds) out of this rarely taken branch into the caller's per-step path.
     __device__ __forceinline__ void refill()
     {
         base += off & ~3u;
         off &= 3u;
-        blk = ck.block((base >> 2) + lane);
+        uint2 k = ck.key;
+        asm volatile("" : "+r"(k.x), "+r"(k.y));
+        const uint64_t b = (base >> 2) + lane;
+        blk = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)(b >> 32), ck.chain_lo, ck.chain_hi_stream), k);
     }
     __device__ __forceinline__ uint32_t next_u32()
     {
         if (off >= 128u) refill();
+        const uint32_t c = off & 3u;
+        const uint32_t mine = c == 0 ? blk.x : c == 1 ? blk.y : c == 2 ? blk.z : blk.w;
+        const uint32_t v = __shfl_sync(0xffffffffu, mine, off >> 2);
+        off++;
+        return v;
+    }
+    // caller guarantees off < 128 (the kernels refill once per step)
+    __device__ __forceinline__ uint32_t next_u32_unchecked()
+    {
         const uint32_t c = off & 3u;
         const uint32_t mine = c == 0 ? blk.x : c == 1 ? blk.y : c == 2 ? blk.z : blk.w;
         const uint32_t v = __shfl_sync(0xffffffffu, mine, off >> 2);

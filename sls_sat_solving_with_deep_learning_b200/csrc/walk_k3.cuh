@@ -1,14 +1,23 @@
-// walk_k3.cuh -- one warp per chain, instances whose clauses have at most 3 literals
-// (random 3-SAT: BASELINE configs 1, 2, 4, 5), no duplicate clause contents, no variable
-// twice in a clause.  Same algorithm and the same random draws as walk_generic.cuh
-// (reference rust/src/lib.rs:201-317); what changes is the memory layout, chosen so that one
-// step makes two dependent trips to L2 and everything else stays in registers / shared memory:
-//   crecx[c] = 64 bytes: {lit0, lit1, lit2, k | occ_start/occ_len of the three variables |
-//              the three resample weights (f64)} -- everything the flip rule needs, one
-//              broadcast load per step (built per call from the weights by build_crecx_kernel)
-//   orec[o]  = {clause, other lit a, other lit b, neg} one coalesced 16-byte load per lane:
-//              the clause content travels with the occurrence entry, so re-evaluating the
-//              clauses of the flipped variable (lib.rs:278-287) needs no row_ptr / lits gathers.
+// walk_k3.cuh -- the fast walk kernel: one warp per chain, chain state in shared memory,
+// instances whose clauses have at most 3 literals (random 3-SAT: BASELINE configs 1, 2, 4),
+// no duplicate clause contents, no variable twice in a clause, at most 65,536 clauses.
+//
+// Same algorithm and the same random draws as walk_generic.cuh (reference
+// rust/src/lib.rs:201-317, trajectory-identical); what changes is the data layout and the
+// instruction diet, because this loop is issue-bound (profiles/r01_*):
+//   crecx[c] = 96 bytes {lit0,lit1,lit2,k | occurrence ranges of the 3 variables |
+//              (w, 1-w) of the 3 variables}: everything the flip rule needs in ONE broadcast
+//              load per step (built per call from the weights by build_crecx_kernel);
+//   orec[o]  = {clause, other lit a, other lit b, neg}: the clause content travels with the
+//              occurrence entry, so re-evaluating the clauses of the flipped variable
+//              (lib.rs:278-287) is one coalesced 16-byte load per lane and two shared-memory
+//              bit tests -- no row_ptr / lits gathers.  An absent literal (k < 3) is encoded as
+//              the positive literal of the dummy variable n, whose bit is always 0, so the
+//              evaluation is branch-free;
+//   shared memory is addressed through the `sm[]` array directly (LDS/ATOMS with an
+//   immediate base), never through generic pointers.
+// A step makes two dependent trips to L2 (crecx, orec); everything else is registers,
+// shuffles and shared memory.
 #pragma once
 #include "common.h"
 #include "philox.cuh"
@@ -16,117 +25,110 @@
 
 namespace slsb {
 
-__host__ __device__ inline bool walk_k3_supports(const WalkArgs& a) { return a.inst.orec != nullptr && a.crecx != nullptr; }
+static constexpr uint32_t CRECX_QUADS = 6;  // uint4 per clause record
 
-// crecx[c] = { {l0,l1,l2,k}, {os0,ol0,os1,ol1}, {os2,ol2,w0.lo,w0.hi}, {w1.lo,w1.hi,w2.lo,w2.hi} }
+__host__ __device__ inline bool walk_k3_supports(const WalkArgs& a)
+{
+    return a.inst.orec != nullptr && a.crecx != nullptr && a.inst.l1_pad == 64;
+}
+
+// crecx[c] = { {l0,l1,l2,k}, {os0,ol0,os1,ol1}, {os2,ol2,0,0}, {w0,1-w0}, {w1,1-w1}, {w2,1-w2} }
 __global__ void build_crecx_kernel(const uint4* __restrict__ crec, const uint32_t* __restrict__ occ_ptr,
-                                   const double* __restrict__ w, uint4* __restrict__ crecx, uint32_t m)
+                                   const double* __restrict__ w, uint4* __restrict__ crecx, uint32_t m, uint32_t n)
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= m) return;
     const uint4 cr = crec[c];
-    const uint32_t lit[3] = {cr.x, cr.y, cr.z};
+    uint32_t lit[3] = {cr.x, cr.y, cr.z};
     uint32_t os[3], ol[3];
-    uint2 wb[3];
+    double wv[3], nwv[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         os[j] = ol[j] = 0;
-        wb[j] = make_uint2(0, 0);
+        wv[j] = nwv[j] = 0.0;
         if (lit[j] != LIT_NONE) {
             const uint32_t v = lit[j] >> 1;
             os[j] = occ_ptr[v];
             ol[j] = occ_ptr[v + 1] - os[j];
-            const double wv = w[v];
-            wb[j] = make_uint2((uint32_t)__double2loint(wv), (uint32_t)__double2hiint(wv));
+            wv[j] = w[v];
+            nwv[j] = 1.0 - wv[j];  // lib.rs:30: the flip probability of a variable that is currently true
+        } else {
+            lit[j] = n << 1;  // dummy variable n: always-false positive literal
         }
     }
-    uint4* out = crecx + 4 * (size_t)c;
-    out[0] = cr;
+    uint4* out = crecx + CRECX_QUADS * (size_t)c;
+    out[0] = make_uint4(lit[0], lit[1], lit[2], cr.w);
     out[1] = make_uint4(os[0], ol[0], os[1], ol[1]);
-    out[2] = make_uint4(os[2], ol[2], wb[0].x, wb[0].y);
-    out[3] = make_uint4(wb[1].x, wb[1].y, wb[2].x, wb[2].y);
+    out[2] = make_uint4(os[2], ol[2], 0, 0);
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+        out[3 + j] = make_uint4((uint32_t)__double2loint(wv[j]), (uint32_t)__double2hiint(wv[j]),
+                                (uint32_t)__double2loint(nwv[j]), (uint32_t)__double2hiint(nwv[j]));
 }
 
-template <bool SMEM>
-struct ChainK3 : Chain<SMEM> {
-    using Base = Chain<SMEM>;
-    using Base::abit;
-    using Base::abits;
-    using Base::I;
-    using Base::l1;
-    using Base::lane;
-    using Base::numfalse;
-    using Base::vbits;
-
-    __device__ __forceinline__ ChainK3(const DevInst& inst, uint32_t* slab, int lane_) : Base(inst, slab, lane_) {}
-
-    // literal l is false under the current assignment (an absent literal counts as false)
-    __device__ __forceinline__ bool lit_false(uint32_t l) const
-    {
-        const uint32_t v = l == LIT_NONE ? 0u : l >> 1;
-        return l == LIT_NONE || abit(v) == (l & 1u);
-    }
-
-    // lib.rs:278-287 for the flipped variable whose occurrence records are [os, os+len) and whose
-    // NEW value is av.  No duplicates on this path, so membership changes are detected with a plain
-    // read and only actual changes touch the bitmap / counters.
-    __device__ __forceinline__ void update_var(uint32_t av, uint32_t os, uint32_t len)
-    {
-        for (uint32_t base = 0; base < len; base += 32) {
-            const uint32_t o = base + lane;
-            bool ins = false, rem = false;
-            if (o < len) {
-                const uint4 rec = __ldg(I.orec + os + o);
-                const bool viol = (av == rec.w) && lit_false(rec.y) && lit_false(rec.z);
-                const uint32_t bit = 1u << (rec.x & 31);
-                const bool cur = (vbits[rec.x >> 5] & bit) != 0;
-                ins = viol && !cur;  // HashSet::insert of a new element
-                rem = !viol && cur;  // HashSet::remove of a present element
-                if (ins != rem) {
-                    atomicXor(&vbits[rec.x >> 5], bit);
-                    atomicAdd(&l1[rec.x >> 10], ins ? 1u : 0xffffffffu);
-                }
-            }
-            numfalse += __popc(__ballot_sync(FULL, ins));
-            numfalse -= __popc(__ballot_sync(FULL, rem));
-        }
-        __syncwarp();
-    }
-
-    // lib.rs:236-256: violations after tentatively flipping the variable (current value a)
-    __device__ __forceinline__ uint64_t greedy_score(uint32_t a, uint32_t os, uint32_t len, bool mapping) const
-    {
-        const uint32_t av = a ^ 1u;
-        uint32_t after = 0, before = 0;
-        for (uint32_t base = 0; base < len; base += 32) {
-            const uint32_t o = base + lane;
-            bool ca = false, cb = false;
-            if (o < len) {
-                const uint4 rec = __ldg(I.orec + os + o);
-                ca = (av == rec.w) && lit_false(rec.y) && lit_false(rec.z);
-                cb = (vbits[rec.x >> 5] >> (rec.x & 31)) & 1u;
-            }
-            after += __popc(__ballot_sync(FULL, ca));
-            before += __popc(__ballot_sync(FULL, cb));
-        }
-        return mapping ? (uint64_t)after : (uint64_t)numfalse - before + after;
-    }
-};
-
-template <bool SMEM>
-__global__ void __launch_bounds__(128, 8) walk_k3_kernel(const WalkArgs A)
+// inclusive warp scan, two instructions per level (shuffle with predicate + predicated add)
+__device__ __forceinline__ uint32_t warp_incl_scan_p(uint32_t v)
 {
-    extern __shared__ uint32_t smem_state[];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        asm volatile(
+            "{ .reg .pred p; .reg .u32 t;\n"
+            "  shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n"
+            "  @p add.u32 %0, %0, t; }\n"
+            : "+r"(v)
+            : "r"(d));
+    }
+    return v;
+}
+
+__device__ __forceinline__ uint32_t ffs0(uint32_t mask) { return __ffs(mask) - 1; }
+
+// Shared memory through explicit shared-space instructions on a 32-bit byte address: the hot loop
+// must never see a generic pointer to shared memory (the generic->shared conversion costs an
+// S2R SR_CgaCtaId + LEA per access on sm_100).
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void atoms_xor(uint32_t a, uint32_t v)
+{
+    asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void atoms_add(uint32_t a, uint32_t v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(128, 7) walk_k3s_kernel(const WalkArgs A)
+{
+    extern __shared__ uint32_t sm[];
     const int lane = threadIdx.x & 31;
     const uint32_t warp = threadIdx.x >> 5;
     const uint64_t run = (uint64_t)blockIdx.x * A.warps_per_block + warp;
     if (run >= A.nruns) return;
     const DevInst& I = A.inst;
-    uint32_t* slab = SMEM ? smem_state + (size_t)warp * I.slab_words : A.gstate + run * (size_t)I.slab_words;
-    ChainK3<SMEM> ch(I, slab, lane);
+    // byte addresses in the shared window
+    const uint32_t sA = (uint32_t)__cvta_generic_to_shared(sm) + warp * I.slab_words * 4u;  // abits
+    const uint32_t sV = sA + I.off_v * 4u;   // vbits (zero-padded to a multiple of 32 words)
+    const uint32_t sL = sA + I.off_l1 * 4u;  // 64 level-1 counters
     const uint64_t chain = A.chain_offset + run;
 
-    {  // lib.rs:206-210
+    // literal code l = 2*var + neg is TRUE iff bit(var) != neg
+    auto lit_true = [sA](uint32_t l) -> uint32_t { return ((lds32(sA + (l >> 6) * 4u) >> ((l >> 1) & 31u)) ^ l) & 1u; };
+
+    // ---- chain init: assignment from the init stream (lib.rs:206-210) ...
+    for (uint32_t i = lane; i < I.slab_words; i += 32) sts32(sA + i * 4u, 0u);
+    __syncwarp();
+    {
         const ChainKey ck(A.seed, chain, STREAM_INIT);
         for (uint32_t w = lane; w < I.nwords; w += 32) {
             uint32_t bits = 0;
@@ -144,42 +146,97 @@ __global__ void __launch_bounds__(128, 8) walk_k3_kernel(const WalkArgs A)
                     bits |= (uint32_t)(t1 == ~0ull || u1 < t1) << (2u * b + 1u);
                 }
             }
-            ch.abits[w] = bits;
+            sts32(sA + w * 4u, bits);
         }
         __syncwarp();
     }
+    // ... and the full scan (lib.rs:213-214, find_violated_clauses :176-181): one clause per lane,
+    // a ballot assembles each vbits word, the level-1 counter is the popcount sum of its 32 words
+    uint32_t nf = 0;
+    const uint4* __restrict__ crec = I.crec;
+    for (uint32_t g = 0; g < I.ngroups; g++) {
+        uint32_t acc = 0, mine = 0;
+        const uint32_t wend = min(32u, I.mwords - g * 32u);
+        for (uint32_t wi = 0; wi < wend; wi++) {
+            const uint32_t c = (g * 32u + wi) * 32u + lane;
+            bool viol = false;
+            if (c < I.m) {
+                const uint4 cr = __ldg(crec + c);
+                viol = !lit_true(cr.x) && (cr.w < 2 || !lit_true(cr.y)) && (cr.w < 3 || !lit_true(cr.z));
+            }
+            const uint32_t word = __ballot_sync(FULL, viol);
+            if ((uint32_t)lane == wi) mine = word;
+            acc += __popc(word);
+        }
+        if ((uint32_t)lane < wend) sts32(sV + (g * 32u + lane) * 4u, mine);
+        if (lane == 0) sts32(sL + g * 4u, acc);
+        nf += acc;
+    }
+    __syncwarp();
 
     WarpStream rng(A.seed, chain, lane);
-    ch.full_scan();  // lib.rs:213-214
-
     uint32_t best = I.m;
     bool has_best = false;
     uint32_t* best_bits = A.best_bits + run * (size_t)I.nwords;
     auto save_best = [&]() {
-        best = ch.numfalse;
+        best = nf;
         has_best = true;
-        for (uint32_t w = lane; w < I.nwords; w += 32) best_bits[w] = ch.abits[w];
+        for (uint32_t w = lane; w < I.nwords; w += 32) best_bits[w] = lds32(sA + w * 4u);
     };
-    if (ch.numfalse < best) save_best();
+    if (nf < best) save_best();
     uint32_t* traj = A.want_traj ? A.traj + run * (A.nsteps + 1) : nullptr;
-    if (traj && lane == 0) traj[0] = ch.numfalse;
+    if (traj && lane == 0) traj[0] = nf;
 
     uint64_t steps = 0, flips = 0;
     int err = 0;
     const bool mapping = A.mapping != 0;
     const int algo = A.algo;
     const bool greedy_possible = A.pfb > 0.0;
-    const uint4* crecx = A.crecx;
+    const bool check_weights = (A.wflags & WF_INTERIOR) == 0;  // some weight is 0, 1 or outside (0,1)
+    const uint4* __restrict__ crecx = A.crecx;
+    const uint4* __restrict__ orec = I.orec;
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
-    while (ch.numfalse > 0 && steps < A.nsteps) {
+    while (nf > 0 && steps < A.nsteps) {
         steps++;
-        const uint32_t c = ch.select(rng.uniform_u32(ch.numfalse));  // lib.rs:229
-        // one 64-byte record, same address in every lane
-        const uint4 q0 = __ldg(crecx + 4 * (size_t)c);
-        const uint4 q1 = __ldg(crecx + 4 * (size_t)c + 1);
-        const uint4 q2 = __ldg(crecx + 4 * (size_t)c + 2);
-        const uint4 q3 = __ldg(crecx + 4 * (size_t)c + 3);
+        if (rng.off > 128u - 16u) rng.refill();  // a step consumes at most 13 words outside rejection loops
+
+        // ---- lib.rs:229: uniform pick among the violated clauses
+        uint32_t r;
+        {
+            const uint32_t zone = (nf << __clz(nf)) - 1u;
+            uint32_t v = rng.next_u32_unchecked();
+            while (v * nf > zone) v = rng.next_u32();
+            r = __umulhi(v, nf);
+        }
+        // level A: lane owns counters 2*lane, 2*lane+1
+        const uint2 cc = lds64(sL + lane * 8u);
+        const uint32_t both = cc.x + cc.y;
+        const uint32_t inclA = warp_incl_scan_p(both);
+        const uint32_t srcA = ffs0(__ballot_sync(FULL, r < inclA));
+        r -= __shfl_sync(FULL, inclA - both, srcA);
+        const uint32_t first = __shfl_sync(FULL, cc.x, srcA);
+        const bool second = r >= first;
+        const uint32_t g = 2 * srcA + (second ? 1u : 0u);
+        if (second) r -= first;
+        // level B: the 32 words of group g
+        const uint32_t word = lds32(sV + (g * 32u + lane) * 4u);
+        const uint32_t pc = __popc(word);
+        const uint32_t inclB = warp_incl_scan_p(pc);
+        const uint32_t srcB = ffs0(__ballot_sync(FULL, r < inclB));
+        r -= __shfl_sync(FULL, inclB - pc, srcB);
+        const uint32_t wsel = __shfl_sync(FULL, word, srcB);
+        const bool hit = ((wsel >> lane) & 1u) && __popc(wsel & lt_mask) == r;
+        const uint32_t c = (g * 32u + srcB) * 32u + ffs0(__ballot_sync(FULL, hit));
+
+        // ---- the clause record: six 16-byte quads, same address in every lane, issued together
+        const uint4* rec = crecx + CRECX_QUADS * (size_t)c;
+        const uint4 q0 = __ldg(rec);
+        const uint4 q1 = __ldg(rec + 1);
+        const uint4 q2 = __ldg(rec + 2);
+        const uint4 p0 = __ldg(rec + 3), p1 = __ldg(rec + 4), p2 = __ldg(rec + 5);
         const uint32_t k = q0.w;
+
         // lib.rs:231: one f64 is drawn on every step, greedy or not
         bool greedy = false;
         if (greedy_possible)
@@ -187,90 +244,125 @@ __global__ void __launch_bounds__(128, 8) walk_k3_kernel(const WalkArgs A)
         else
             rng.skip_u64();
 
-        // current values of the clause's variables and their flip probabilities (lib.rs:29-30)
-        const uint32_t a0 = ch.abit(q0.x >> 1);
-        const uint32_t a1 = k > 1 ? ch.abit(q0.y >> 1) : 0u;
-        const uint32_t a2 = k > 2 ? ch.abit(q0.z >> 1) : 0u;
+        // current values of the clause's variables (the dummy variable reads 0)
+        const uint32_t a0 = lit_true(q0.x & ~1u), a1 = lit_true(q0.y & ~1u), a2 = lit_true(q0.z & ~1u);
 
-        int pick = -1;       // single-flip rules: index of the literal whose variable flips
-        uint32_t marks = 0;  // MT: bit j <=> literal j is resampled
+        uint32_t marks = 0;  // bit j <=> the variable of literal j flips in this step
         if (greedy) {
+            // lib.rs:236-256: score = violations after tentatively flipping the variable
             uint64_t min_viol = ~0ull;
-            const uint64_t s0 = ch.greedy_score(a0, q1.x, q1.y, mapping);
-            if (s0 < min_viol) {
-                min_viol = s0;
-                pick = 0;
-            }
-            if (k > 1) {
-                const uint64_t s1 = ch.greedy_score(a1, q1.z, q1.w, mapping);
-                if (s1 < min_viol) {
-                    min_viol = s1;
-                    pick = 1;
-                }
-            }
-            if (k > 2) {
-                const uint64_t s2 = ch.greedy_score(a2, q2.x, q2.y, mapping);
-                if (s2 < min_viol) {
-                    min_viol = s2;
-                    pick = 2;
+            const uint32_t aj[3] = {a0, a1, a2};
+            const uint32_t osj[3] = {q1.x, q1.z, q2.x}, olj[3] = {q1.y, q1.w, q2.y};
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                if ((uint32_t)j < k) {
+                    const uint32_t av = aj[j] ^ 1u;
+                    uint32_t after = 0, before = 0;
+                    for (uint32_t base = 0; base < olj[j]; base += 32) {
+                        const uint32_t o = base + lane;
+                        bool ca = false, cb = false;
+                        if (o < olj[j]) {
+                            const uint4 orc = __ldg(orec + osj[j] + o);
+                            ca = (av == orc.w) && !lit_true(orc.y) && !lit_true(orc.z);
+                            cb = (lds32(sV + (orc.x >> 5) * 4u) >> (orc.x & 31)) & 1u;
+                        }
+                        after += __popc(__ballot_sync(FULL, ca));
+                        before += __popc(__ballot_sync(FULL, cb));
+                    }
+                    const uint64_t viol = mapping ? (uint64_t)after : (uint64_t)nf - before + after;
+                    if (viol < min_viol) {
+                        min_viol = viol;
+                        marks = 1u << j;
+                    }
                 }
             }
         } else if (algo == ALGO_SCHOENING) {
-            pick = (int)rng.uniform_u32(k);
+            uint32_t v;
+            const uint32_t zone = (k << __clz(k)) - 1u;  // lib.rs:52 clause.choose(rng)
+            do v = rng.next_u32(); while (v * k > zone);
+            marks = 1u << __umulhi(v, k);
         } else {
-            const double fp0 = flip_prob(a0, __hiloint2double((int)q2.w, (int)q2.z));
-            const double fp1 = k > 1 ? flip_prob(a1, __hiloint2double((int)q3.y, (int)q3.x)) : 0.0;
-            const double fp2 = k > 2 ? flip_prob(a2, __hiloint2double((int)q3.w, (int)q3.z)) : 0.0;
+            // flip probabilities (lib.rs:29-30): w if the variable is false, 1-w if it is true
+            const double fp0 = a0 ? __hiloint2double((int)p0.w, (int)p0.z) : __hiloint2double((int)p0.y, (int)p0.x);
+            const double fp1 = a1 ? __hiloint2double((int)p1.w, (int)p1.z) : __hiloint2double((int)p1.y, (int)p1.x);
+            const double fp2 = a2 ? __hiloint2double((int)p2.w, (int)p2.z) : __hiloint2double((int)p2.y, (int)p2.x);
             if (algo == ALGO_PROBSAT) {
-                // WeightedIndex::new over fp[0..k), sampled with UniformFloat (lib.rs:71-72)
+                // WeightedIndex::new over fp[0..k) (absent literals carry weight 0), lib.rs:71
                 const double cum0 = fp0;
                 const double cum1 = k > 1 ? cum0 + fp1 : cum0;
                 const double total = k > 2 ? cum1 + fp2 : cum1;
-                if (!(fp0 >= 0.0) || !(fp1 >= 0.0) || !(fp2 >= 0.0)) {
-                    err = DERR_WEIGHTS;
-                    break;
+                if (check_weights) {
+                    if (!(fp0 >= 0.0) || !(fp1 >= 0.0) || !(fp2 >= 0.0)) {
+                        err = DERR_WEIGHTS;
+                        break;
+                    }
+                    if (total == 0.0) {
+                        err = DERR_ALL_ZERO;
+                        break;
+                    }
                 }
-                if (total == 0.0) {
-                    err = DERR_ALL_ZERO;
-                    break;
-                }
+                // UniformFloat::new(0, total) + sample from 52 mantissa bits, lib.rs:72
                 double scale = total;
                 while (scale * (1.0 - 0x1p-52) >= total) scale = __longlong_as_double(__double_as_longlong(scale) - 1);
                 const double x = ((double)(rng.next_u64() >> 12) * 0x1p-52) * scale;
-                pick = (k > 1 && cum0 <= x) ? ((k > 2 && cum1 <= x) ? 2 : 1) : 0;
+                // partition_point(cum <= x) over the first k-1 cumulative weights
+                marks = (k > 1 && cum0 <= x) ? ((k > 2 && cum1 <= x) ? 4u : 2u) : 1u;
             } else {
                 // lib.rs:24-35 / :81-92: one f64 per literal, in literal order
                 if (rng.next_f64() < fp0) marks |= 1u;
                 if (k > 1 && rng.next_f64() < fp1) marks |= 2u;
                 if (k > 2 && rng.next_f64() < fp2) marks |= 4u;
-                if (algo == ALGO_MOSER_SINGLE && marks) {  // lib.rs:94-99
-                    pick = (int)select_in_word(marks, (uint32_t)rng.uniform_u64(__popc(marks)));
-                    marks = 0;
-                }
+                if (algo == ALGO_MOSER_SINGLE && marks)  // lib.rs:94-99
+                    marks = 1u << select_in_word(marks, (uint32_t)rng.uniform_u64(__popc(marks)));
             }
         }
 
-        if (pick >= 0) marks = 1u << pick;
         if (marks) {
-            // toggle the marked variables (distinct on this path), then re-evaluate their clauses
-            if (lane < 3 && ((marks >> lane) & 1u)) {
-                const uint32_t v = (lane == 0 ? q0.x : lane == 1 ? q0.y : q0.z) >> 1;
-                atomicXor(&ch.abits[v >> 5], 1u << (v & 31));
+            // lib.rs:37-41: toggle the marked variables (distinct on this path) ...
+            if (lane == 0) {
+                if (marks & 1u) atoms_xor(sA + (q0.x >> 6) * 4u, 1u << ((q0.x >> 1) & 31u));
+                if (marks & 2u) atoms_xor(sA + (q0.y >> 6) * 4u, 1u << ((q0.y >> 1) & 31u));
+                if (marks & 4u) atoms_xor(sA + (q0.z >> 6) * 4u, 1u << ((q0.z >> 1) & 31u));
             }
             __syncwarp();
             flips += __popc(marks);
-            if (marks & 1u) ch.update_var(a0 ^ 1u, q1.x, q1.y);
-            if (marks & 2u) ch.update_var(a1 ^ 1u, q1.z, q1.w);
-            if (marks & 4u) ch.update_var(a2 ^ 1u, q2.x, q2.y);
+            // ... then re-evaluate every clause of each flipped variable (lib.rs:278-287)
+            for (uint32_t mk = marks; mk; mk &= mk - 1) {
+                const uint32_t j = ffs0(mk);
+                const uint32_t av = (j == 0 ? a0 : j == 1 ? a1 : a2) ^ 1u;  // the variable's new value
+                const uint32_t os = j == 0 ? q1.x : j == 1 ? q1.z : q2.x;
+                const uint32_t len = j == 0 ? q1.y : j == 1 ? q1.w : q2.y;
+                uint32_t base = 0;
+                do {
+                    const uint32_t o = base + lane;
+                    const bool act = o < len;
+                    uint4 orc = make_uint4(0, 0, 0, 2);  // inactive lanes: never violated, never present
+                    if (act) orc = __ldg(orec + os + o);
+                    const uint32_t va = sV + (orc.x >> 5) * 4u;
+                    const uint32_t vword = lds32(va);
+                    const uint32_t bit = 1u << (orc.x & 31);
+                    const bool viol = (av == orc.w) & !(lit_true(orc.y) | lit_true(orc.z));
+                    const bool cur = (vword & bit) != 0 && act;
+                    const bool ins = viol && !cur;  // HashSet::insert of a new element
+                    const bool rem = !viol && cur;  // HashSet::remove of a present element
+                    if (ins | rem) {
+                        atoms_xor(va, bit);
+                        atoms_add(sL + (orc.x >> 10) * 4u, ins ? 1u : 0xffffffffu);
+                    }
+                    nf += __popc(__ballot_sync(FULL, ins)) - __popc(__ballot_sync(FULL, rem));
+                    base += 32;
+                } while (base < len);
+                __syncwarp();
+            }
         }
 
-        if (ch.numfalse < best) save_best();               // lib.rs:292-296
-        if (traj && lane == 0) traj[steps] = ch.numfalse;  // lib.rs:298-300
+        if (nf < best) save_best();                        // lib.rs:292-296
+        if (traj && lane == 0) traj[steps] = nf;           // lib.rs:298-300
     }
 
     if (lane == 0) {
         if (err) atomicCAS(A.err, 0, err);
-        A.found[run] = ch.numfalse == 0 && !err;
+        A.found[run] = nf == 0 && !err;
         A.has_best[run] = has_best;
         A.steps[run] = steps;
         A.best_energy[run] = best;
