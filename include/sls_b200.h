@@ -138,6 +138,33 @@ int sls_solver_launch_count(const sls_solver *s);
 /* description of the kernel variant the solver picked, e.g. "walk<k3,smem>" */
 const char *sls_solver_variant(const sls_solver *s);
 
+/* ---- oracle forward: replaces network.apply(params, graph) for the shipped network type
+ *      ("interaction" + LCG: python/src/model.py:127-144, call sites
+ *      python/src/evaluate_with_given_params.py:116, :297, :306 and python/src/train_utils.py:279)
+ *      and LCG.get_model_probabilities (python/src/sat_representations.py:756-780).
+ *      The dense layers run on tcgen05 tensor cores (TF32 inputs, FP32 accumulate). ------------- */
+typedef struct sls_gnn_model sls_gnn_model;
+
+/* blob = all parameters as float32 in haiku construction order (python/src/model.py:11-61):
+ *   edge embed w[2][D], b[D]; node embed w[2][D], b[D];
+ *   per step: edge MLP w1[K1e][h1], b1[h1], w2[h1][h2], b2[h2], ln_scale[h2], ln_offset[h2];
+ *             node MLP w1[K1n][h1], ... (same order);   K1e = de + 2 dn, K1n = dn + 2 h2,
+ *             de = dn = D in step 0 and h2 afterwards;
+ *   readout w[h2], b[1].   Weights are [in][out] row-major exactly as haiku stores them. */
+int sls_gnn_model_create(const float *blob, uint64_t blob_len, int32_t num_steps, int32_t embed_dim, int32_t h1,
+                         int32_t h2, sls_gnn_model **out);
+void sls_gnn_model_free(sls_gnn_model *m);
+/* jraph.GraphsTuple in, decoded_nodes[N] out (host buffers): nodes[N][2], edges[E][2] (the one-hot
+ * features of python/src/sat_instances.py:65-73), senders[E], receivers[E].  kernel_ms optional. */
+int sls_gnn_forward_graph(sls_gnn_model *m, uint64_t n_node, uint64_t n_edge, const float *nodes, const float *edges,
+                          const int32_t *senders, const int32_t *receivers, float *decoded, double *kernel_ms);
+/* batched form: builds the LCG graphs of n_inst parsed instances (LCG.get_graph,
+ * python/src/sat_representations.py:607-666), runs one forward over the concatenation and returns
+ * p[sum n_i] = P(x = True) per variable (and optionally decoded[sum N_i], N_i = 2 n_i + m_i). */
+int sls_gnn_forward_lcg(sls_gnn_model *m, sls_instance *const *insts, uint32_t n_inst, float *prob, float *decoded,
+                        double *kernel_ms);
+int sls_gnn_launch_count(const sls_gnn_model *m);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,10 +14,10 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "lib", "libsls_b200.so")
-_SOURCES = ["csrc/api.cu", "csrc/instance.cpp"]
+_SOURCES = ["csrc/api.cu", "csrc/gnn_api.cu", "csrc/instance.cpp"]
 _HEADERS = [
     "csrc/common.h", "csrc/philox.cuh", "csrc/instance.h", "csrc/eval.cuh", "csrc/walk_generic.cuh",
-    "csrc/walk_k3.cuh", "../include/sls_b200.h",
+    "csrc/walk_k3.cuh", "csrc/gnn_kernels.cuh", "../include/sls_b200.h",
 ]
 
 NVCC_FLAGS = [
@@ -116,6 +116,11 @@ SYMBOLS = {
     "sls_solver_export_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sls_solver_launch_count": (C.c_int, [_vp]),
     "sls_solver_variant": (C.c_char_p, [_vp]),
+    "sls_gnn_model_create": (C.c_int, [_vp, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_vp)]),
+    "sls_gnn_model_free": (None, [_vp]),
+    "sls_gnn_forward_graph": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_double)]),
+    "sls_gnn_forward_lcg": (C.c_int, [_vp, C.POINTER(_vp), C.c_uint32, _vp, _vp, C.POINTER(C.c_double)]),
+    "sls_gnn_launch_count": (C.c_int, [_vp]),
 }
 
 _lib = None

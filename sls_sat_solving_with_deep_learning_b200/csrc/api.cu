@@ -31,6 +31,9 @@ static int set_error(int code, const std::string& msg)
 
 extern "C" const char* sls_last_error(void) { return g_error.c_str(); }
 
+// shared with gnn_api.cu
+int sls_set_error_internal(int code, const std::string& msg) { return set_error(code, msg); }
+
 #define CUDA_TRY(expr)                                                                                   \
     do {                                                                                                 \
         cudaError_t _e = (expr);                                                                         \

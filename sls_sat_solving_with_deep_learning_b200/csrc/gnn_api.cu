@@ -1,0 +1,401 @@
+// gnn_api.cu -- C ABI of the GNN oracle forward (include/sls_b200.h, section "oracle forward").
+//
+// Host side of the reference's oracle call path:
+//   network.apply(params, graph)                 python/src/evaluate_with_given_params.py:116
+//   LCG.get_graph + get_problem_from_cnf          python/src/sat_representations.py:607-666,
+//                                                 python/src/sat_instances.py:50-73  (sls_gnn_forward_lcg)
+//   LCG.get_model_probabilities                   python/src/sat_representations.py:775-780
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sls_b200.h"
+#include "gnn_kernels.cuh"
+#include "instance.h"
+
+int sls_set_error_internal(int code, const std::string& msg);  // api.cu
+
+namespace {
+
+using namespace gnn;
+
+int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// round-to-nearest (ties away, like cvt.rna.tf32.f32) to a 10-bit mantissa
+float round_tf32_host(float x)
+{
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & 0xffffe000u;
+    std::memcpy(&x, &u, 4);
+    return x;
+}
+
+struct DevMlp {
+    int k1 = 0, h1 = 0, h2 = 0, k1_slabs = 0, k2_slabs = 0, n1 = 0, n2 = 0;
+    float *w1t_hi = nullptr, *w1t_lo = nullptr, *b1 = nullptr, *w2t_hi = nullptr, *w2t_lo = nullptr, *b2 = nullptr, *ln_scale = nullptr,
+          *ln_offset = nullptr;
+};
+
+#define G_TRY(expr)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess) return sls_set_error_internal(SLS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+int upload(const std::vector<float>& h, float** d)
+{
+    G_TRY(cudaMalloc(d, std::max<size_t>(h.size(), 1) * sizeof(float)));
+    if (!h.empty()) G_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return SLS_OK;
+}
+
+}  // namespace
+
+struct sls_gnn_model {
+    int num_steps = 0, embed = 0, h1 = 0, h2 = 0;
+    float *edge_embed_w = nullptr, *edge_embed_b = nullptr, *node_embed_w = nullptr, *node_embed_b = nullptr;
+    std::vector<DevMlp> edge_mlp, node_mlp;
+    float* readout_w = nullptr;
+    float readout_b = 0.f;
+    std::vector<void*> allocs;
+    int launches = 0;
+};
+
+extern "C" void sls_gnn_model_free(sls_gnn_model* m)
+{
+    if (!m) return;
+    for (void* p : m->allocs) cudaFree(p);
+    delete m;
+}
+
+namespace {
+
+// haiku Linear stores w as [in][out]; the tensor-core B operand wants [out][in] (K-major), zero padded
+int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& out)
+{
+    out.k1 = k1;
+    out.h1 = h1;
+    out.h2 = h2;
+    out.k1_slabs = (k1 + SLAB_K - 1) / SLAB_K;
+    out.k2_slabs = (h1 + SLAB_K - 1) / SLAB_K;
+    out.n1 = round_up(h1, 16);
+    out.n2 = round_up(h2, 16);
+    const int k1p = out.k1_slabs * SLAB_K, k2p = out.k2_slabs * SLAB_K;
+    // 3xTF32: w = hi + lo with hi = tf32(w), lo = tf32(w - hi)
+    std::vector<float> w1h((size_t)out.n1 * k1p, 0.f), w1l(w1h.size(), 0.f), b1(out.n1, 0.f);
+    std::vector<float> w2h((size_t)out.n2 * k2p, 0.f), w2l(w2h.size(), 0.f), b2(out.n2, 0.f);
+    for (int k = 0; k < k1; k++)
+        for (int n = 0; n < h1; n++) {
+            const float w = p[(size_t)k * h1 + n], hi = round_tf32_host(w);
+            w1h[(size_t)n * k1p + k] = hi;
+            w1l[(size_t)n * k1p + k] = round_tf32_host(w - hi);
+        }
+    p += (size_t)k1 * h1;
+    std::copy(p, p + h1, b1.begin());
+    p += h1;
+    for (int k = 0; k < h1; k++)
+        for (int n = 0; n < h2; n++) {
+            const float w = p[(size_t)k * h2 + n], hi = round_tf32_host(w);
+            w2h[(size_t)n * k2p + k] = hi;
+            w2l[(size_t)n * k2p + k] = round_tf32_host(w - hi);
+        }
+    p += (size_t)h1 * h2;
+    std::copy(p, p + h2, b2.begin());
+    p += h2;
+    std::vector<float> sc(p, p + h2), of(p + h2, p + 2 * h2);
+    p += 2 * h2;
+    int rc;
+    if ((rc = upload(w1h, &out.w1t_hi)) || (rc = upload(w1l, &out.w1t_lo)) || (rc = upload(b1, &out.b1)) || (rc = upload(w2h, &out.w2t_hi)) ||
+        (rc = upload(w2l, &out.w2t_lo)) || (rc = upload(b2, &out.b2)) || (rc = upload(sc, &out.ln_scale)) ||
+        (rc = upload(of, &out.ln_offset)))
+        return rc;
+    for (float* q : {out.w1t_hi, out.w1t_lo, out.b1, out.w2t_hi, out.w2t_lo, out.b2, out.ln_scale, out.ln_offset}) m->allocs.push_back(q);
+    return SLS_OK;
+}
+
+uint64_t expected_blob_len(int steps, int D, int h1, int h2)
+{
+    uint64_t n = 2 * (2ull * D + D);
+    for (int t = 0; t < steps; t++) {
+        const int de = t == 0 ? D : h2, dn = t == 0 ? D : h2;
+        const uint64_t k1e = de + 2ull * dn, k1n = dn + 2ull * h2;
+        n += k1e * h1 + h1 + (uint64_t)h1 * h2 + h2 + 2ull * h2;
+        n += k1n * h1 + h1 + (uint64_t)h1 * h2 + h2 + 2ull * h2;
+    }
+    return n + h2 + 1;
+}
+
+}  // namespace
+
+extern "C" int sls_gnn_model_create(const float* blob, uint64_t blob_len, int32_t num_steps, int32_t embed_dim, int32_t h1, int32_t h2,
+                                    sls_gnn_model** out)
+{
+    if (!blob || !out) return sls_set_error_internal(SLS_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (num_steps < 1 || embed_dim < 4 || embed_dim % 4 || h1 < 4 || h2 < 4 || h2 % 4 || h1 > MAX_N || h2 > MAX_N)
+        return sls_set_error_internal(SLS_ERR_ARG, "unsupported network shape (need embed, h2 multiples of 4; h1, h2 <= 208)");
+    if (blob_len != expected_blob_len(num_steps, embed_dim, h1, h2))
+        return sls_set_error_internal(SLS_ERR_ARG, "parameter blob has the wrong length for this network shape");
+    int dev = 0;
+    G_TRY(cudaGetDevice(&dev));
+    sls_gnn_model* m = new (std::nothrow) sls_gnn_model();
+    if (!m) return sls_set_error_internal(SLS_ERR_NOMEM, "out of memory");
+    m->num_steps = num_steps;
+    m->embed = embed_dim;
+    m->h1 = h1;
+    m->h2 = h2;
+    const float* p = blob;
+    const int D = embed_dim;
+    int rc = SLS_OK;
+    auto up = [&](size_t n, float** d) {
+        std::vector<float> h(p, p + n);
+        p += n;
+        int r = upload(h, d);
+        if (!r) m->allocs.push_back(*d);
+        return r;
+    };
+    if ((rc = up(2 * D, &m->edge_embed_w)) || (rc = up(D, &m->edge_embed_b)) || (rc = up(2 * D, &m->node_embed_w)) ||
+        (rc = up(D, &m->node_embed_b))) {
+        sls_gnn_model_free(m);
+        return rc;
+    }
+    m->edge_mlp.resize(num_steps);
+    m->node_mlp.resize(num_steps);
+    for (int t = 0; t < num_steps && !rc; t++) {
+        const int de = t == 0 ? D : h2, dn = t == 0 ? D : h2;
+        rc = pack_mlp(m, p, de + 2 * dn, h1, h2, m->edge_mlp[t]);
+        if (!rc) rc = pack_mlp(m, p, dn + 2 * h2, h1, h2, m->node_mlp[t]);
+    }
+    if (!rc) rc = up(h2, &m->readout_w);
+    if (rc) {
+        sls_gnn_model_free(m);
+        return rc;
+    }
+    m->readout_b = *p;
+    cudaError_t e = cudaFuncSetAttribute(mlp_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
+    if (e != cudaSuccess) {
+        sls_gnn_model_free(m);
+        return sls_set_error_internal(SLS_ERR_CUDA, std::string("cudaFuncSetAttribute(mlp_ln_kernel): ") + cudaGetErrorString(e));
+    }
+    *out = m;
+    return SLS_OK;
+}
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    template <class T>
+    T* as() { return static_cast<T*>(p); }
+};
+
+int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t* i0, int d0, const float* s1, const int32_t* i1, int d1,
+               const float* s2, const int32_t* i2, int d2, int64_t rows, float* out)
+{
+    if (rows == 0) return SLS_OK;
+    MlpArgs a{};
+    a.src[0] = s0, a.src[1] = s1, a.src[2] = s2;
+    a.idx[0] = i0, a.idx[1] = i1, a.idx[2] = i2;
+    a.d[0] = d0, a.d[1] = d1, a.d[2] = d2;
+    a.rows = (int32_t)rows;
+    a.k1_slabs = w.k1_slabs, a.k2_slabs = w.k2_slabs, a.n1 = w.n1, a.n2 = w.n2, a.h2 = w.h2;
+    a.w1t_hi = w.w1t_hi, a.w1t_lo = w.w1t_lo, a.b1 = w.b1, a.w2t_hi = w.w2t_hi, a.w2t_lo = w.w2t_lo, a.b2 = w.b2;
+    a.ln_scale = w.ln_scale, a.ln_offset = w.ln_offset;
+    a.out = out;
+    const unsigned blocks = (unsigned)((rows + TILE_M - 1) / TILE_M);
+    mlp_ln_kernel<<<blocks, MLP_THREADS, MLP_SMEM_BYTES>>>(a);
+    m->launches++;
+    G_TRY(cudaGetLastError());
+    return SLS_OK;
+}
+
+// the whole forward on device-resident inputs; decoded_dev[N]
+int forward_device(sls_gnn_model* m, int64_t N, int64_t E, const float* d_nodes, const float* d_edges, const int32_t* d_send,
+                   const int32_t* d_recv, const int64_t* d_sptr, const int32_t* d_sids, const int64_t* d_rptr, const int32_t* d_rids,
+                   float* d_decoded)
+{
+    const int D = m->embed, H = m->h2;
+    DevBuf e_a, e_b, h_a, h_b, sent, recv;
+    const size_t ew = std::max(D, H), hw = std::max(D, H);
+    G_TRY(cudaMalloc(&e_a.p, std::max<int64_t>(E, 1) * ew * sizeof(float)));
+    G_TRY(cudaMalloc(&e_b.p, std::max<int64_t>(E, 1) * ew * sizeof(float)));
+    G_TRY(cudaMalloc(&h_a.p, std::max<int64_t>(N, 1) * hw * sizeof(float)));
+    G_TRY(cudaMalloc(&h_b.p, std::max<int64_t>(N, 1) * hw * sizeof(float)));
+    G_TRY(cudaMalloc(&sent.p, std::max<int64_t>(N, 1) * H * sizeof(float)));
+    G_TRY(cudaMalloc(&recv.p, std::max<int64_t>(N, 1) * H * sizeof(float)));
+    float *e = e_a.as<float>(), *e2 = e_b.as<float>(), *h = h_a.as<float>(), *h2 = h_b.as<float>();
+    if (E) embed_kernel<<<(unsigned)((E * D + 255) / 256), 256>>>(d_edges, m->edge_embed_w, m->edge_embed_b, e, E, D);
+    if (N) embed_kernel<<<(unsigned)((N * D + 255) / 256), 256>>>(d_nodes, m->node_embed_w, m->node_embed_b, h, N, D);
+    m->launches += 2;
+    int de = D, dn = D;
+    for (int t = 0; t < m->num_steps; t++) {
+        // edge update sees [edges | nodes[senders] | nodes[receivers]]  (jraph InteractionNetwork + concatenated_args)
+        int rc = launch_mlp(m, m->edge_mlp[t], e, nullptr, de, h, d_send, dn, h, d_recv, dn, E, e2);
+        if (rc) return rc;
+        std::swap(e, e2);
+        de = H;
+        // node update sees [nodes | segment_sum(new edges, senders) | segment_sum(new edges, receivers)]
+        if (N) {
+            const unsigned blocks = (unsigned)((N * 32 + 255) / 256);
+            segment_sum_kernel<<<blocks, 256>>>(e, d_sptr, d_sids, sent.as<float>(), N, H);
+            segment_sum_kernel<<<blocks, 256>>>(e, d_rptr, d_rids, recv.as<float>(), N, H);
+            m->launches += 2;
+        }
+        rc = launch_mlp(m, m->node_mlp[t], h, nullptr, dn, sent.as<float>(), nullptr, H, recv.as<float>(), nullptr, H, N, h2);
+        if (rc) return rc;
+        std::swap(h, h2);
+        dn = H;
+    }
+    if (N) {
+        readout_kernel<<<(unsigned)((N * 32 + 255) / 256), 256>>>(h, m->readout_w, m->readout_b, d_decoded, N, H);
+        m->launches++;
+    }
+    G_TRY(cudaGetLastError());
+    G_TRY(cudaDeviceSynchronize());
+    return SLS_OK;
+}
+
+// CSR of edge ids per node, edges of one node in increasing edge id (stable counting sort)
+void build_csr(int64_t N, int64_t E, const int32_t* key, std::vector<int64_t>& ptr, std::vector<int32_t>& ids)
+{
+    ptr.assign(N + 1, 0);
+    for (int64_t i = 0; i < E; i++) ptr[key[i] + 1]++;
+    for (int64_t v = 0; v < N; v++) ptr[v + 1] += ptr[v];
+    ids.resize(std::max<int64_t>(E, 1));
+    std::vector<int64_t> fill(ptr.begin(), ptr.end() - 1);
+    for (int64_t i = 0; i < E; i++) ids[fill[key[i]]++] = (int32_t)i;
+}
+
+template <class T>
+int to_device(const std::vector<T>& h, DevBuf& d)
+{
+    G_TRY(cudaMalloc(&d.p, std::max<size_t>(h.size(), 1) * sizeof(T)));
+    if (!h.empty()) G_TRY(cudaMemcpy(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SLS_OK;
+}
+
+int forward_host_graph(sls_gnn_model* m, int64_t N, int64_t E, const float* nodes, const float* edges, const int32_t* senders,
+                       const int32_t* receivers, float* decoded, DevBuf* keep_decoded, double* kernel_ms)
+{
+    for (int64_t i = 0; i < E; i++)
+        if (senders[i] < 0 || senders[i] >= N || receivers[i] < 0 || receivers[i] >= N)
+            return sls_set_error_internal(SLS_ERR_ARG, "edge endpoint out of range");
+    std::vector<int64_t> sptr, rptr;
+    std::vector<int32_t> sids, rids;
+    build_csr(N, E, senders, sptr, sids);
+    build_csr(N, E, receivers, rptr, rids);
+    DevBuf d_nodes, d_edges, d_send, d_recv, d_sptr, d_sids, d_rptr, d_rids, d_dec;
+    int rc;
+    std::vector<float> hn(nodes, nodes + 2 * N), he(edges, edges + 2 * E);
+    std::vector<int32_t> hs(senders, senders + E), hr(receivers, receivers + E);
+    if ((rc = to_device(hn, d_nodes)) || (rc = to_device(he, d_edges)) || (rc = to_device(hs, d_send)) || (rc = to_device(hr, d_recv)) ||
+        (rc = to_device(sptr, d_sptr)) || (rc = to_device(sids, d_sids)) || (rc = to_device(rptr, d_rptr)) ||
+        (rc = to_device(rids, d_rids)))
+        return rc;
+    G_TRY(cudaMalloc(&d_dec.p, std::max<int64_t>(N, 1) * sizeof(float)));
+    cudaEvent_t e0, e1;
+    G_TRY(cudaEventCreate(&e0));
+    G_TRY(cudaEventCreate(&e1));
+    m->launches = 0;
+    G_TRY(cudaEventRecord(e0));
+    rc = forward_device(m, N, E, d_nodes.as<float>(), d_edges.as<float>(), d_send.as<int32_t>(), d_recv.as<int32_t>(),
+                        d_sptr.as<int64_t>(), d_sids.as<int32_t>(), d_rptr.as<int64_t>(), d_rids.as<int32_t>(), d_dec.as<float>());
+    if (!rc) {
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (kernel_ms) *kernel_ms = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+    if (decoded && N) G_TRY(cudaMemcpy(decoded, d_dec.p, N * sizeof(float), cudaMemcpyDeviceToHost));
+    if (keep_decoded) std::swap(keep_decoded->p, d_dec.p);
+    return SLS_OK;
+}
+
+}  // namespace
+
+extern "C" int sls_gnn_forward_graph(sls_gnn_model* m, uint64_t n_node, uint64_t n_edge, const float* nodes, const float* edges,
+                                     const int32_t* senders, const int32_t* receivers, float* decoded, double* kernel_ms)
+{
+    if (!m || (n_node && !nodes) || (n_edge && (!edges || !senders || !receivers)))
+        return sls_set_error_internal(SLS_ERR_ARG, "NULL argument");
+    if (n_node > 0x7fffffffull || n_edge > 0x7fffffffull) return sls_set_error_internal(SLS_ERR_ARG, "graph too large for one call");
+    return forward_host_graph(m, (int64_t)n_node, (int64_t)n_edge, nodes, edges, senders, receivers, decoded, nullptr, kernel_ms);
+}
+
+extern "C" int sls_gnn_forward_lcg(sls_gnn_model* m, sls_instance* const* insts, uint32_t n_inst, float* prob, float* decoded,
+                                   double* kernel_ms)
+{
+    if (!m || (n_inst && !insts)) return sls_set_error_internal(SLS_ERR_ARG, "NULL argument");
+    // LCG.get_graph for every instance, concatenated (sat_representations.py:607-666): per instance
+    // 2n literal nodes (2j = negative, 2j+1 = positive literal of variable j) then its non-empty
+    // clauses; one edge literal -> clause per literal occurrence in file order, then one edge
+    // positive -> negative literal per variable.
+    std::vector<float> nodes, edges;
+    std::vector<int32_t> send, recv;
+    std::vector<int64_t> var_node0;
+    int64_t node_off = 0;
+    for (uint32_t i = 0; i < n_inst; i++) {
+        const slsb::HostInstance& h = insts[i]->host;
+        const int64_t n = h.n;
+        int64_t m_ne = 0;
+        for (int64_t j = 0; j < 2 * n; j++) {
+            nodes.push_back(0.f);  // np.eye(2)[1] and np.eye(2)[-1] are both [0, 1] (sat_instances.py:69)
+            nodes.push_back(1.f);
+        }
+        for (uint32_t c = 0; c < h.m; c++) {
+            const uint32_t s = h.row_ptr[c], e = h.row_ptr[c + 1];
+            if (s == e) continue;  // sat_instances.py:50 drops empty clauses
+            for (uint32_t j = s; j < e; j++) {
+                const uint32_t v = h.lits[j] >> 1;
+                for (uint32_t q = s; q < j; q++)
+                    if ((h.lits[q] >> 1) == v)
+                        return sls_set_error_internal(SLS_ERR_ARG, "Multiple occurrences of single variable in constraint");
+                const bool positive = !(h.lits[j] & 1u);
+                send.push_back((int32_t)(node_off + 2 * v + (positive ? 1 : 0)));
+                recv.push_back((int32_t)(node_off + 2 * n + m_ne));
+                edges.push_back(1.f);  // np.eye(2)[0]
+                edges.push_back(0.f);
+            }
+            nodes.push_back(1.f);  // clause node: np.eye(2)[0]
+            nodes.push_back(0.f);
+            m_ne++;
+        }
+        for (int64_t j = 0; j < n; j++) {
+            send.push_back((int32_t)(node_off + 2 * j + 1));
+            recv.push_back((int32_t)(node_off + 2 * j));
+            edges.push_back(0.f);  // np.eye(2)[1]
+            edges.push_back(1.f);
+            var_node0.push_back(node_off + 2 * j);
+        }
+        node_off += 2 * n + m_ne;
+        if (node_off > 0x7fffffffll || (int64_t)send.size() > 0x7fffffffll)
+            return sls_set_error_internal(SLS_ERR_ARG, "batch too large for one call");
+    }
+    const int64_t N = node_off, E = (int64_t)send.size();
+    DevBuf d_dec;
+    int rc = forward_host_graph(m, N, E, nodes.data(), edges.data(), send.data(), recv.data(), decoded, &d_dec, kernel_ms);
+    if (rc) return rc;
+    if (prob && !var_node0.empty()) {
+        DevBuf d_v0, d_p;
+        if ((rc = to_device(var_node0, d_v0))) return rc;
+        const int64_t nv = (int64_t)var_node0.size();
+        G_TRY(cudaMalloc(&d_p.p, nv * sizeof(float)));
+        pair_prob_kernel<<<(unsigned)((nv + 255) / 256), 256>>>(d_dec.as<float>(), d_v0.as<int64_t>(), d_p.as<float>(), nv);
+        m->launches++;
+        G_TRY(cudaGetLastError());
+        G_TRY(cudaMemcpy(prob, d_p.p, nv * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return SLS_OK;
+}
+
+extern "C" int sls_gnn_launch_count(const sls_gnn_model* m) { return m ? m->launches : 0; }

@@ -1,0 +1,387 @@
+// gnn_kernels.cuh -- GNN oracle forward (LCG + interaction network) on sm_100a.
+//
+// Device restatement of the reference's oracle forward:
+//   python/src/model.py:11-18    get_embedding (Linear 2->32 on nodes and edges)        -> embed_kernel
+//   python/src/model.py:21-61    apply_interaction: per step, jraph.InteractionNetwork with
+//                                update_fn = LayerNorm(ReLU(Linear(ReLU(Linear(concat))))) -> mlp_ln_kernel
+//                                and segment_sum aggregation of the NEW edges per sender /
+//                                receiver                                                -> segment_sum_kernel
+//   python/src/model.py:144      readout Linear(H->1)                                     -> readout_kernel
+//   python/src/sat_representations.py:775-780 LCG.get_model_probabilities (pair softmax)  -> pair_prob_kernel
+//
+// The two dense contractions of every update (K1 x H and H x H, K1 = 96 / 432 / 600, H = 200)
+// run on the 5th-generation tensor cores: tcgen05.mma kind::tf32 with the accumulators in TMEM,
+// operands staged in shared memory in the canonical K-major SWIZZLE_128B layout, completion
+// tracked with mbarriers via tcgen05.commit.  One CTA owns a tile of 128 rows (edges or nodes) and
+// runs the whole update for it: gather -> GEMM1 -> bias+ReLU -> GEMM2 -> bias+ReLU -> LayerNorm ->
+// global.  Nothing but the tile's inputs and its normalised output touches HBM; the hidden
+// activation goes TMEM -> registers -> shared memory slab by slab as GEMM2 consumes it.
+//
+// Precision: a single TF32 product (10-bit mantissa) accumulates to |dp| = 1.7e-3 over the 20
+// dense layers, above the 1e-3 contract, so every contraction is error-compensated ("3xTF32"):
+// x = hi + lo with hi = tf32(x), lo = tf32(x - hi), and A*B ~= A_hi*B_hi + A_lo*B_hi + A_hi*B_lo
+// (three MMAs into the same fp32 accumulator; the dropped lo*lo term is 2^-22 relative).  Weights
+// are split on the host, activations while they are staged.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gnn {
+
+static constexpr int TILE_M = 128;       // rows per CTA = UMMA M
+static constexpr int SLAB_K = 32;        // tf32 elements per 128-byte swizzle row
+static constexpr int MAX_N = 208;        // padded output width (multiple of 16, >= hidden)
+static constexpr int A_SLAB_BYTES = TILE_M * 128;   // 16 KB
+static constexpr int B_SLAB_BYTES = MAX_N * 128;    // 26 KB
+// one pipeline stage = one K-slab of all four operands: A_hi | A_lo | B_hi | B_lo
+static constexpr int STAGE_BYTES = 2 * A_SLAB_BYTES + 2 * B_SLAB_BYTES;  // 84 KB
+static constexpr int STAGES = 2;
+static constexpr int TMEM_COLS = 512;
+static constexpr int ACC2_COL = 256;
+static constexpr int MLP_THREADS = 128;
+static constexpr int MLP_SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
+
+struct MlpArgs {
+    // up to three gathered input segments: row i of the A matrix is
+    //   [ src0[idx0 ? idx0[i] : i][0:d0] | src1[idx1 ? idx1[i] : i][0:d1] | src2[...][0:d2] ]
+    const float* src[3];
+    const int32_t* idx[3];
+    int32_t d[3];
+    int32_t rows;        // number of rows (edges or nodes)
+    int32_t k1_slabs;    // ceil((d0+d1+d2)/32)
+    int32_t k2_slabs;    // ceil(h1/32)
+    int32_t n1, n2;      // padded output widths of the two linears (multiples of 16, <= 208)
+    int32_t h2;          // true output width (LayerNorm length)
+    const float* w1t_hi; // [n1][k1_slabs*32] transposed weights, TF32-rounded, zero padded
+    const float* w1t_lo; // [n1][k1_slabs*32] TF32-rounded residual w - hi
+    const float* b1;     // [n1] zero padded
+    const float* w2t_hi; // [n2][k2_slabs*32]
+    const float* w2t_lo;
+    const float* b2;     // [n2]
+    const float* ln_scale;   // [h2]
+    const float* ln_offset;  // [h2]
+    float* out;          // [rows][h2]
+};
+
+// ---- small PTX helpers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{ .reg .pred p;\n"
+        "WAIT_%=:\n"
+        "  mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "  @!p bra WAIT_%=;\n }"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+// tcgen05.commit: the mbarrier is arrived on when all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{ .reg .pred p;\n"
+        "  setp.ne.b32 p, %4, 0;\n"
+        "  tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p; }\n"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address
+// >> 4 in bits [0,14), leading byte offset (unused for swizzled K-major, 1) in [16,30), stride byte
+// offset = 1024 B between 8-row groups in [32,46), version 1 in [46,48), layout type 2 in [61,64)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr)
+{
+    return (uint64_t)((addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, M x N
+__host__ __device__ constexpr uint32_t idesc_tf32(int m, int n)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// byte offset of (row r, 16-byte unit u) inside a K-major SWIZZLE_128B slab: rows are 128 B apart,
+// 8-row groups 1024 B apart, the unit index is XORed with r % 8 (Swizzle<3,4,3>)
+__device__ __forceinline__ uint32_t sw128_off(uint32_t r, uint32_t u) { return (r >> 3) * 1024u + (r & 7u) * 128u + ((u ^ (r & 7u)) << 4); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// Round to the nearest TF32 value (10-bit mantissa).  The tensor core ignores the low 13 mantissa
+// bits of an fp32 operand, so operands are rounded explicitly before they are staged.
+__device__ __forceinline__ float round_tf32(float x)
+{
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// ---- the fused update: LayerNorm(ReLU(Linear2(ReLU(Linear1(gathered rows))))) -------------------
+__global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B atoms need 1024-byte alignment
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sBar = base + STAGES * STAGE_BYTES;            // one mbarrier per stage
+    const uint32_t sTmem = sBar + 8 * STAGES;                     // TMEM base address written by tcgen05.alloc
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));   // generic alias of `base`
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int row0 = blockIdx.x * TILE_M;
+    const int my_row = min(row0 + tid, P.rows - 1);  // rows past the end re-read the last row; their output is not stored
+
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; i++) mbar_init(sBar + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + (sTmem - base));
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;  // this warp's TMEM lane quarter (row = lane)
+
+    // source row pointers of this thread's A row
+    const float* rp[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        rp[j] = nullptr;
+        if (P.d[j] > 0) {
+            const int r = P.idx[j] ? __ldg(P.idx[j] + my_row) : my_row;
+            rp[j] = P.src[j] + (size_t)r * P.d[j];
+        }
+    }
+    const int kA = P.d[0] + P.d[1] + P.d[2];
+    const int k1p = P.k1_slabs * SLAB_K, k2p = P.k2_slabs * SLAB_K;
+
+    // write one 16-byte unit of this thread's row, split into TF32 hi / lo, into the stage's A slabs
+    auto put_split = [&](uint32_t stage_base, int u, float4 x) {
+        float4 hi, lo;
+        hi.x = round_tf32(x.x), hi.y = round_tf32(x.y), hi.z = round_tf32(x.z), hi.w = round_tf32(x.w);
+        lo.x = round_tf32(x.x - hi.x), lo.y = round_tf32(x.y - hi.y), lo.z = round_tf32(x.z - hi.z), lo.w = round_tf32(x.w - hi.w);
+        const uint32_t off = sw128_off(tid, u);
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + A_SLAB_BYTES + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+    };
+    // B slabs (weights, already split): cp.async straight into the swizzled layout
+    auto stage_b = [&](uint32_t stage_base, const float* w_hi, const float* w_lo, int n_pad, int kp, int s) {
+        const uint32_t bHi = stage_base + 2 * A_SLAB_BYTES, bLo = bHi + B_SLAB_BYTES;
+        for (int n = tid; n < n_pad; n += MLP_THREADS) {
+            const size_t o = (size_t)n * kp + s * SLAB_K;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                cp_async16(bHi + sw128_off(n, u), w_hi + o + u * 4);
+                cp_async16(bLo + sw128_off(n, u), w_lo + o + u * 4);
+            }
+        }
+        cp_async_commit();
+    };
+    // GEMM1 A slab: this thread's gathered row, columns [32 s, 32 s + 32)
+    auto stage_a1 = [&](uint32_t stage_base, int s) {
+        float4 x[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int col = s * SLAB_K + u * 4;
+            x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col < kA) {
+                const float* p = col < P.d[0] ? rp[0] + col : col < P.d[0] + P.d[1] ? rp[1] + (col - P.d[0]) : rp[2] + (col - P.d[0] - P.d[1]);
+                x[u] = __ldg(reinterpret_cast<const float4*>(p));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) put_split(stage_base, u, x[u]);
+    };
+    // GEMM2 A slab: Y1 = ReLU(acc1 + b1), columns [32 s, 32 s + 32), straight out of TMEM
+    auto stage_a2 = [&](uint32_t stage_base, int s) {
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int c0 = s * SLAB_K + half * 16;
+            float v[16];
+            if (c0 < P.n1) {
+                tmem_ld16(tmem + lane_base + (uint32_t)c0, v);
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + __ldg(P.b1 + c0 + i), 0.f);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) put_split(stage_base, half * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        }
+    };
+
+    uint32_t stage_phase = 0;  // bit st = parity the next wait on stage barrier st expects
+    auto wait_stage = [&](int st) {
+        mbar_wait(sBar + 8 * st, (stage_phase >> st) & 1u);
+        stage_phase ^= 1u << st;
+    };
+    // Pipeline over `nslabs` K-slabs with STAGES buffers.  Slab s is staged into buffer s % STAGES
+    // (after the MMAs of slab s - STAGES, its previous occupant, have completed), then one thread
+    // issues its 12 MMAs and a tcgen05.commit on the buffer's mbarrier.  The MMAs run asynchronously
+    // while all threads stage the next slab.  Every commit is waited on exactly once (the last
+    // min(STAGES, nslabs) in the drain), so when run_gemm returns the accumulator is complete.
+    auto run_gemm = [&](int nslabs, int n_pad, int kp, uint32_t acc_col, const float* w_hi, const float* w_lo, auto&& stage_a) {
+        const uint32_t idesc = idesc_tf32(TILE_M, n_pad);
+        for (int s = 0; s < nslabs; s++) {
+            const int st = s % STAGES;
+            const uint32_t sb = base + st * STAGE_BYTES;
+            if (s >= STAGES) wait_stage(st);
+            stage_b(sb, w_hi, w_lo, n_pad, kp, s);
+            stage_a(sb, s);
+            cp_async_wait<0>();
+            fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t aHi = sb, aLo = sb + A_SLAB_BYTES, bHi = sb + 2 * A_SLAB_BYTES, bLo = bHi + B_SLAB_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {  // 4 k-steps of 8 tf32 (32 bytes) per 128-byte slab row
+                    const uint32_t o = kk * 32;
+                    umma_tf32(tmem + acc_col, smem_desc_sw128(aHi + o), smem_desc_sw128(bHi + o), idesc, (s | kk) != 0 ? 1u : 0u);
+                    umma_tf32(tmem + acc_col, smem_desc_sw128(aLo + o), smem_desc_sw128(bHi + o), idesc, 1u);
+                    umma_tf32(tmem + acc_col, smem_desc_sw128(aHi + o), smem_desc_sw128(bLo + o), idesc, 1u);
+                }
+                umma_commit(sBar + 8 * st);
+            }
+        }
+        for (int j = max(0, nslabs - STAGES); j < nslabs; j++) wait_stage(j % STAGES);
+        tc_fence_after();
+    };
+
+    // ---------------- GEMM1: acc1[128 x n1] = A[128 x K1] * W1 -----------------
+    run_gemm(P.k1_slabs, P.n1, k1p, 0u, P.w1t_hi, P.w1t_lo, stage_a1);
+    // ---------------- GEMM2: acc2[128 x n2] = ReLU(acc1 + b1)[128 x h1] * W2 -----------------
+    run_gemm(P.k2_slabs, P.n2, k2p, (uint32_t)ACC2_COL, P.w2t_hi, P.w2t_lo, stage_a2);
+
+    // ---------------- epilogue 2: LayerNorm(ReLU(acc2 + b2)) -> global --------------------------
+    {
+        const int H = P.h2;
+        float sum = 0.f;
+        for (int c0 = 0; c0 < H; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem + lane_base + (uint32_t)(ACC2_COL + c0), v);
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                if (c0 + i < H) sum += fmaxf(v[i] + __ldg(P.b2 + c0 + i), 0.f);
+        }
+        const float mean = sum / (float)H;
+        float sq = 0.f;
+        for (int c0 = 0; c0 < H; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem + lane_base + (uint32_t)(ACC2_COL + c0), v);
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                if (c0 + i < H) {
+                    const float d = fmaxf(v[i] + __ldg(P.b2 + c0 + i), 0.f) - mean;
+                    sq += d * d;
+                }
+        }
+        const float rstd = rsqrtf(sq / (float)H + 1e-5f);  // haiku LayerNorm: biased variance, eps = 1e-5
+        const int grow = row0 + tid;
+        for (int c0 = 0; c0 < H; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem + lane_base + (uint32_t)(ACC2_COL + c0), v);
+            if (grow < P.rows) {
+                float* o = P.out + (size_t)grow * H + c0;
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    if (c0 + i < H) {
+                        const float x = fmaxf(v[i] + __ldg(P.b2 + c0 + i), 0.f);
+                        o[i] = (x - mean) * rstd * __ldg(P.ln_scale + c0 + i) + __ldg(P.ln_offset + c0 + i);
+                    }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+// ---- small kernels -------------------------------------------------------------------------------
+// Linear(2 -> D): out[i][c] = x[i][0]*w[0][c] + x[i][1]*w[1][c] + b[c]     (model.py:13-16)
+__global__ void embed_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                             float* __restrict__ out, int64_t rows, int D)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * D) return;
+    const int64_t r = i / D;
+    const int c = (int)(i % D);
+    out[i] = x[2 * r] * w[c] + x[2 * r + 1] * w[D + c] + b[c];
+}
+
+// jraph.utils.segment_sum over a CSR of edge ids (edge order inside a segment = increasing edge id,
+// i.e. the order a sequential scatter-add visits them): out[v] = sum_{j in [ptr[v], ptr[v+1])} e[ids[j]]
+__global__ void segment_sum_kernel(const float* __restrict__ e, const int64_t* __restrict__ ptr, const int32_t* __restrict__ ids,
+                                   float* __restrict__ out, int64_t n_node, int H)
+{
+    const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (v >= n_node) return;
+    const int64_t s = ptr[v], t = ptr[v + 1];
+    for (int c = lane; c < H; c += 32) {
+        float acc = 0.f;
+        for (int64_t j = s; j < t; j++) acc += __ldg(e + (size_t)__ldg(ids + j) * H + c);
+        out[(size_t)v * H + c] = acc;
+    }
+}
+
+// readout Linear(H -> 1): one warp per node (model.py:144)
+__global__ void readout_kernel(const float* __restrict__ h, const float* __restrict__ w, float b, float* __restrict__ out,
+                               int64_t n_node, int H)
+{
+    const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (v >= n_node) return;
+    float acc = 0.f;
+    for (int c = lane; c < H; c += 32) acc += h[(size_t)v * H + c] * __ldg(w + c);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) out[v] = acc + b;
+}
+
+// LCG.get_model_probabilities: softmax over (decoded[2j], decoded[2j+1]) -> column 1
+// (sat_representations.py:775-780); var_node0[j] = node index of the negative literal of variable j
+__global__ void pair_prob_kernel(const float* __restrict__ decoded, const int64_t* __restrict__ var_node0, float* __restrict__ p,
+                                 int64_t n_vars)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_vars) return;
+    const int64_t v0 = var_node0[j];
+    const float a = decoded[v0], b = decoded[v0 + 1];
+    const float mx = fmaxf(a, b);
+    const float ea = __expf(a - mx), eb = __expf(b - mx);
+    p[j] = eb / (ea + eb);
+}
+
+}  // namespace gnn

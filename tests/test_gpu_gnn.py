@@ -1,0 +1,85 @@
+"""CUDA oracle forward vs the NumPy restatement (oracle/gnn_oracle.py), tolerance from BASELINE.json:
+probabilities within 1e-3 of the fp32 reference.  Parameters are haiku-style random initialisations
+(the pre-trained files are not shipped with the reference checkout)."""
+import numpy as np
+import pytest
+
+from conftest import golden_cnf, random_ksat
+from oracle import gnn_oracle as go
+import sls_sat_solving_with_deep_learning_b200 as eng
+from sls_sat_solving_with_deep_learning_b200 import gnn
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-3  # BASELINE.json north_star: "the oracle's probabilities match JAX within 1e-3 in fp32"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    assert eng.device_count() > 0
+    eng.set_device(0)
+
+
+def clauses_of(inst):
+    row, lits = inst.csr()
+    return [lits[int(row[c]):int(row[c + 1])].tolist() for c in range(inst.m)]
+
+
+@pytest.mark.parametrize("layers,steps,bias", [((200, 200), 5, 0.0), ((200, 200), 5, 0.3), ((32, 32), 2, 0.2), ((64, 48), 3, 0.2)])
+def test_forward_graph_matches_numpy_oracle(layers, steps, bias):
+    n, m = 60, 250
+    clauses = random_ksat(n, m, 3, seed=5)
+    graph = go.lcg_graph(n, clauses)
+    params = go.init_params(seed=42, mlp_layers=layers, num_steps=steps, bias_scale=bias)
+    ref64 = go.forward(params, graph, dtype=np.float64, num_steps=steps)
+    ref32 = go.forward(params, graph, dtype=np.float32, num_steps=steps)
+    net = gnn.InteractionNetworkLCG(params, num_message_passing_steps=steps)
+    dec = net.apply(graph)
+    assert dec.shape == (graph["n_node"], 1)
+    p_gpu = gnn.get_model_probabilities(dec, n)
+    p_ref = go.model_probabilities(ref64, n)
+    err_p = np.abs(p_gpu - p_ref).max()
+    err_d = np.abs(dec - ref64).max()
+    print(f"layers={layers} steps={steps}: max|dp|={err_p:.2e} max|ddecoded|={err_d:.2e} "
+          f"(fp32 numpy vs fp64: {np.abs(ref32 - ref64).max():.2e})")
+    assert err_p < PROB_TOL
+
+
+def test_batched_lcg_equals_per_instance_graphs():
+    names = ["r3sat_test_random_KCNF3_100_210_6416893", "ref_tests_medium", "g4sat_easy_ca_00092",
+             "r3sat_test_random_KCNF3_200_869_9397183"]
+    insts = [eng.Instance.from_dimacs(golden_cnf(nm)) for nm in names]
+    params = go.init_params(seed=7, bias_scale=0.1)
+    net = gnn.InteractionNetworkLCG(params)
+    probs, dec = net.probabilities(insts, return_decoded=True)
+    off = 0
+    for inst, p in zip(insts, probs):
+        graph = go.lcg_graph(inst.n, clauses_of(inst))
+        ref = go.forward(params, graph, dtype=np.float64)
+        p_ref = go.model_probabilities(ref, inst.n)
+        assert p.shape == (inst.n,)
+        assert np.abs(p - p_ref).max() < PROB_TOL
+        one = net.apply(graph)
+        assert np.abs(one.ravel() - dec[off:off + graph["n_node"]]).max() < 2e-3
+        off += graph["n_node"]
+
+
+def test_graph_edge_cases():
+    params = go.init_params(seed=3, mlp_layers=(32, 32), num_steps=2, bias_scale=0.1)
+    net = gnn.InteractionNetworkLCG(params, num_message_passing_steps=2)
+    # tiny graph (1 tile, mostly padding rows), odd node count, mixed clause lengths
+    graph = go.lcg_graph(3, [(1, 2), (3,), (-1, -2, 3)])
+    dec = net.apply(graph)
+    ref = go.forward(params, graph, dtype=np.float64, num_steps=2)
+    assert np.abs(gnn.get_model_probabilities(dec, 3) - go.model_probabilities(ref, 3)).max() < PROB_TOL
+    # exactly 128 and 129 edges: tile boundary
+    for m in (41, 42, 43):
+        clauses = random_ksat(5, m, 3, seed=m, sort_vars=True) if m <= 80 else None
+        graph = go.lcg_graph(5, clauses)
+        dec = net.apply(graph)
+        ref = go.forward(params, graph, dtype=np.float64, num_steps=2)
+        assert np.abs(gnn.get_model_probabilities(dec, 5) - go.model_probabilities(ref, 5)).max() < PROB_TOL
+    with pytest.raises(eng.PanicException):  # python/tests/test_sat_instances.py:32-44
+        net.probabilities([eng.Instance.from_text("p cnf 1 1 \n 1 -1 0")])
+    with pytest.raises(ValueError):
+        gnn.InteractionNetworkLCG({"linear": {"w": np.zeros((2, 32)), "b": np.zeros(32)}})
