@@ -3,6 +3,7 @@
 Public surface (mirrors the reference's interface for this path):
   run_sls_python          drop-in for moser_rust.run_sls_python (rust/src/lib.rs:103-149)
   run_sls, ResidentSolver the same solver on a parsed instance / with HBM-resident chain state
+  run_sls_batch           many instances x nruns chains in one launch
   Instance                DIMACS / CSR -> clause + occurrence CSR in HBM
   get_violated_constraints, eval_assignments   clause evaluation (sat_representations.py:718-741)
 """
@@ -16,6 +17,7 @@ from .solver import (  # noqa: F401
     eval_assignments,
     get_violated_constraints,
     run_sls,
+    run_sls_batch,
     run_sls_python,
     set_device,
     set_seed,

@@ -652,3 +652,250 @@ extern "C" int sls_run(sls_instance* inst, const double* w_init, size_t w_init_l
     sls_solver_free(s);
     return rc;
 }
+
+// ------------------------------------------------------------------ batched solver
+// Many instances, the same solver parameters, one launch per kernel variant: replaces the
+// per-instance loop of python/src/evaluate_with_given_params.py:108-138 (oracle -> run_sls_python
+// for every file, sequentially) for the throughput configs (BASELINE configs 1, 3, 4).
+namespace {
+
+struct Pool {
+    char* base = nullptr;
+    size_t size = 0;
+    ~Pool() { cudaFree(base); }
+};
+
+struct ItemPlan {
+    bool smem = false, k3 = false;
+    uint32_t wpb = 4;
+    size_t smem_bytes = 0;
+    // element offsets into the pools
+    size_t off_n = 0, off_bits = 0, off_run = 0, off_crecx = 0, off_gstate = 0;
+};
+
+}  // namespace
+
+extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const double* w_init, const double* w_resample,
+                             const uint64_t* var_offsets, const sls_run_params* params, sls_run_result* results)
+{
+    if ((n_inst && (!insts || !results || !var_offsets)) || !params) return set_error(SLS_ERR_ARG, "NULL argument");
+    if (params->algo < 0 || params->algo > 3) return set_error(SLS_ERR_ALGO, "Unknown algorithm type");
+    if (params->return_trajectories)
+        return set_error(SLS_ERR_ARG, "sls_run_batch does not return trajectories; use sls_run per instance for them");
+    const uint64_t R = params->nruns;
+    for (uint32_t i = 0; i < n_inst; i++) {
+        results[i].best_energy = insts[i]->host.m;
+        results[i].has_best_assignment = 0;
+        results[i].total_steps = results[i].total_flips = 0;
+        results[i].kernel_ms = 0.0;
+    }
+    if (n_inst == 0 || R == 0) return SLS_OK;
+
+    int device = 0, num_sms = 0, max_smem_optin = 0, smem_per_sm = 0;
+    CUDA_TRY(cudaGetDevice(&device));
+    CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device));
+
+    // ---- plan: kernel variant and pool offsets per instance
+    std::vector<ItemPlan> plan(n_inst);
+    size_t tot_n = 0, tot_bits = 0, tot_run = 0, tot_crecx = 0, tot_gstate = 0;
+    const bool force_generic = [] { const char* f = std::getenv("SLS_B200_FORCE_GENERIC"); return f && f[0] == '1'; }();
+    const char* force_state = std::getenv("SLS_B200_FORCE_STATE");
+    for (uint32_t i = 0; i < n_inst; i++) {
+        int rc = ensure_on_device(insts[i]);
+        if (rc) return rc;
+        const DevInst& I = insts[i]->dev;
+        ItemPlan& pl = plan[i];
+        const size_t slab_bytes = size_t(I.slab_words) * 4;
+        pl.wpb = 4;
+        // in a batch the machine is filled by other instances, so shared memory is used whenever
+        // at least 8 chains (2 CTAs) of this instance fit per SM
+        pl.smem = pl.wpb * slab_bytes <= (size_t)max_smem_optin && 2 * (pl.wpb * slab_bytes + 1024) <= (size_t)smem_per_sm;
+        if (force_state && std::strcmp(force_state, "hbm") == 0) pl.smem = false;
+        pl.smem_bytes = pl.smem ? pl.wpb * slab_bytes : 0;
+        pl.k3 = (I.flags & INST_K3) != 0 && pl.smem && I.l1_pad == 64 && !force_generic;
+        pl.off_n = tot_n, pl.off_bits = tot_bits, pl.off_run = tot_run, pl.off_crecx = tot_crecx, pl.off_gstate = tot_gstate;
+        tot_n += std::max<uint32_t>(I.n, 1);
+        tot_bits += R * std::max<uint32_t>(I.nwords, 1);
+        tot_run += R;
+        if (pl.k3) tot_crecx += size_t(I.m) * CRECX_QUADS;
+        if (!pl.smem) tot_gstate += R * size_t(I.slab_words);
+    }
+
+    // ---- weights: validate and convert on the host, one upload per pool
+    std::vector<uint64_t> thr(tot_n, 0);
+    std::vector<double> wres(tot_n, 0.0);
+    std::vector<uint32_t> wflags(n_inst, 0);
+    for (uint32_t i = 0; i < n_inst; i++) {
+        const uint32_t n = insts[i]->host.n;
+        const double* wi = w_init + var_offsets[i];
+        const double* wr = w_resample + var_offsets[i];
+        if (var_offsets[i + 1] - var_offsets[i] < n) return set_error(SLS_ERR_WEIGHTS, "weights shorter than var_count");
+        bool interior = true;
+        for (uint32_t v = 0; v < n; v++) {
+            const double p = wi[v];
+            if (p >= 0.0 && p < 1.0)
+                thr[plan[i].off_n + v] = (uint64_t)(p * 18446744073709551616.0);
+            else if (p == 1.0)
+                thr[plan[i].off_n + v] = ~0ull;
+            else
+                return set_error(SLS_ERR_WEIGHTS, "weights_initialize: p is outside range [0.0, 1.0]");
+            wres[plan[i].off_n + v] = wr[v];
+            interior = interior && wr[v] > 0.0 && wr[v] < 1.0;
+        }
+        wflags[i] = interior ? WF_INTERIOR : 0u;
+    }
+
+    Pool p_thr, p_w, p_crecx, p_bits, p_found, p_hasbest, p_steps, p_flips, p_best, p_gstate, p_err, p_items, p_cta;
+    auto alloc = [&](Pool& p, size_t bytes) -> cudaError_t {
+        p.size = std::max<size_t>(bytes, 16);
+        return cudaMalloc(&p.base, p.size);
+    };
+    CUDA_TRY(alloc(p_thr, tot_n * 8));
+    CUDA_TRY(alloc(p_w, tot_n * 8));
+    CUDA_TRY(alloc(p_crecx, tot_crecx * sizeof(uint4)));
+    CUDA_TRY(alloc(p_bits, tot_bits * 4));
+    CUDA_TRY(alloc(p_found, tot_run));
+    CUDA_TRY(alloc(p_hasbest, tot_run));
+    CUDA_TRY(alloc(p_steps, tot_run * 8));
+    CUDA_TRY(alloc(p_flips, tot_run * 8));
+    CUDA_TRY(alloc(p_best, tot_run * 4));
+    CUDA_TRY(alloc(p_gstate, tot_gstate * 4));
+    CUDA_TRY(alloc(p_err, size_t(n_inst) * 4));
+    CUDA_TRY(cudaMemcpy(p_thr.base, thr.data(), tot_n * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(p_w.base, wres.data(), tot_n * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(p_err.base, 0, size_t(n_inst) * 4));
+
+    // ---- per-instance kernel arguments, grouped by variant: 0 = k3s, 1 = generic<smem>, 2 = generic<hbm>
+    std::vector<WalkArgs> items[3];
+    std::vector<uint32_t> cta_begin[3], owner[3];
+    size_t smem_max[3] = {0, 0, 0};
+    for (uint32_t i = 0; i < n_inst; i++) {
+        const DevInst& I = insts[i]->dev;
+        const ItemPlan& pl = plan[i];
+        WalkArgs a{};
+        a.inst = I;
+        a.thr_init = reinterpret_cast<uint64_t*>(p_thr.base) + pl.off_n;
+        a.w = reinterpret_cast<double*>(p_w.base) + pl.off_n;
+        a.crecx = pl.k3 ? reinterpret_cast<uint4*>(p_crecx.base) + pl.off_crecx : nullptr;
+        a.algo = params->algo;
+        a.mapping = params->pre_compute_mapping;
+        a.want_traj = 0;
+        a.wflags = wflags[i];
+        a.pfb = params->prob_flip_best;
+        a.nsteps = params->nsteps;
+        a.nruns = R;
+        a.seed = params->seed + i;  // instance i uses seed + i: identical to sls_run(inst_i, seed + i)
+        a.chain_offset = params->chain_offset;
+        a.gstate = pl.smem ? nullptr : reinterpret_cast<uint32_t*>(p_gstate.base) + pl.off_gstate;
+        a.warps_per_block = pl.wpb;
+        a.best_bits = reinterpret_cast<uint32_t*>(p_bits.base) + pl.off_bits;
+        a.found = reinterpret_cast<uint8_t*>(p_found.base) + pl.off_run;
+        a.has_best = reinterpret_cast<uint8_t*>(p_hasbest.base) + pl.off_run;
+        a.steps = reinterpret_cast<uint64_t*>(p_steps.base) + pl.off_run;
+        a.best_energy = reinterpret_cast<uint32_t*>(p_best.base) + pl.off_run;
+        a.flips = reinterpret_cast<uint64_t*>(p_flips.base) + pl.off_run;
+        a.traj = nullptr;
+        a.err = reinterpret_cast<int32_t*>(p_err.base) + i;
+        if (pl.k3 && I.m)
+            build_crecx_kernel<<<(I.m + 255) / 256, 256>>>(I.crec, I.occ_ptr, a.w, const_cast<uint4*>(a.crecx), I.m, I.n);
+        const int g = pl.k3 ? 0 : pl.smem ? 1 : 2;
+        if (cta_begin[g].empty()) cta_begin[g].push_back(0);
+        cta_begin[g].push_back(cta_begin[g].back() + (uint32_t)((R + pl.wpb - 1) / pl.wpb));
+        items[g].push_back(a);
+        owner[g].push_back(i);
+        smem_max[g] = std::max(smem_max[g], pl.smem_bytes);
+    }
+    CUDA_TRY(cudaGetLastError());
+
+    cudaEvent_t ev0, ev1;
+    CUDA_TRY(cudaEventCreate(&ev0));
+    CUDA_TRY(cudaEventCreate(&ev1));
+    Pool d_items[3], d_cta[3];
+    for (int g = 0; g < 3; g++) {
+        if (items[g].empty()) continue;
+        CUDA_TRY(alloc(d_items[g], items[g].size() * sizeof(WalkArgs)));
+        CUDA_TRY(alloc(d_cta[g], cta_begin[g].size() * 4));
+        CUDA_TRY(cudaMemcpy(d_items[g].base, items[g].data(), items[g].size() * sizeof(WalkArgs), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d_cta[g].base, cta_begin[g].data(), cta_begin[g].size() * 4, cudaMemcpyHostToDevice));
+    }
+    if (smem_max[0]) CUDA_TRY(cudaFuncSetAttribute(walk_k3s_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[0]));
+    if (smem_max[1])
+        CUDA_TRY(cudaFuncSetAttribute(walk_generic_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[1]));
+    CUDA_TRY(cudaEventRecord(ev0));
+    for (int g = 0; g < 3; g++) {
+        if (items[g].empty()) continue;
+        const WalkArgs* di = reinterpret_cast<const WalkArgs*>(d_items[g].base);
+        const uint32_t* dc = reinterpret_cast<const uint32_t*>(d_cta[g].base);
+        const uint32_t ni = (uint32_t)items[g].size(), blocks = cta_begin[g].back();
+        if (g == 0)
+            walk_k3s_batch_kernel<<<blocks, 128, smem_max[0]>>>(di, dc, ni);
+        else if (g == 1)
+            walk_generic_batch_kernel<true><<<blocks, 128, smem_max[1]>>>(di, dc, ni);
+        else
+            walk_generic_batch_kernel<false><<<blocks, 128, 0>>>(di, dc, ni);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ev1));
+    CUDA_TRY(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+
+    // ---- results: pooled D2H, per-instance reduction (lib.rs:320-334)
+    std::vector<int32_t> err(n_inst);
+    CUDA_TRY(cudaMemcpy(err.data(), p_err.base, size_t(n_inst) * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n_inst; i++)
+        if (err[i]) {
+            const char* msg = err[i] == DERR_ALL_ZERO       ? "probsat: AllWeightsZero"
+                              : err[i] == DERR_EMPTY_CLAUSE ? "an empty clause was selected"
+                              : err[i] == DERR_WEIGHTS      ? "probsat: InvalidWeight"
+                                                            : "clause too long for the Moser-Tardos kernel (k > 1024)";
+            return set_error(err[i], std::string(msg) + " (instance " + std::to_string(i) + ")");
+        }
+    std::vector<uint8_t> found(tot_run), has_best(tot_run);
+    std::vector<uint64_t> steps(tot_run), flips(tot_run);
+    std::vector<uint32_t> be(tot_run);
+    CUDA_TRY(cudaMemcpy(found.data(), p_found.base, tot_run, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(has_best.data(), p_hasbest.base, tot_run, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(steps.data(), p_steps.base, tot_run * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(flips.data(), p_flips.base, tot_run * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(be.data(), p_best.base, tot_run * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> bits;
+    for (uint32_t i = 0; i < n_inst; i++) {
+        const HostInstance& h = insts[i]->host;
+        const ItemPlan& pl = plan[i];
+        sls_run_result& r = results[i];
+        r.kernel_ms = ms;
+        uint64_t best = h.m;
+        size_t winner = R;
+        for (size_t q = 0; q < R; q++) {
+            const size_t k = pl.off_run + q;
+            if (be[k] < best) {
+                best = be[k];
+                winner = q;
+            }
+            r.total_steps += steps[k];
+            r.total_flips += flips[k];
+        }
+        r.best_energy = best;
+        if (winner < R && has_best[pl.off_run + winner]) {
+            r.has_best_assignment = 1;
+            if (r.best_assignment) {
+                const uint32_t nwords = insts[i]->dev.nwords;
+                bits.resize(std::max<uint32_t>(nwords, 1));
+                CUDA_TRY(cudaMemcpy(bits.data(), reinterpret_cast<uint32_t*>(p_bits.base) + pl.off_bits + winner * nwords,
+                                    size_t(nwords) * 4, cudaMemcpyDeviceToHost));
+                for (uint32_t v = 0; v < h.n; v++) r.best_assignment[v] = (bits[v >> 5] >> (v & 31)) & 1u;
+            }
+        }
+        if (r.found) std::memcpy(r.found, found.data() + pl.off_run, R);
+        if (r.steps) std::memcpy(r.steps, steps.data() + pl.off_run, R * 8);
+        if (r.flips_run) std::memcpy(r.flips_run, flips.data() + pl.off_run, R * 8);
+        if (r.best_energy_run)
+            for (size_t q = 0; q < R; q++) r.best_energy_run[q] = be[pl.off_run + q];
+    }
+    return SLS_OK;
+}

@@ -233,12 +233,11 @@ struct Chain {
 __device__ __forceinline__ double flip_prob(uint32_t a, double w) { return a ? (1.0 - w) : w; }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(128) walk_generic_kernel(const WalkArgs A)
+__device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t block, uint32_t* smem_state)
 {
-    extern __shared__ uint32_t smem_state[];
     const int lane = threadIdx.x & 31;
     const uint32_t warp = threadIdx.x >> 5;
-    const uint64_t run = (uint64_t)blockIdx.x * A.warps_per_block + warp;
+    const uint64_t run = (uint64_t)block * A.warps_per_block + warp;
     if (run >= A.nruns) return;
     const DevInst& I = A.inst;
     uint32_t* slab = SMEM ? smem_state + (size_t)warp * I.slab_words : A.gstate + run * (size_t)I.slab_words;
@@ -457,6 +456,45 @@ __global__ void __launch_bounds__(128) walk_generic_kernel(const WalkArgs A)
         A.best_energy[run] = best;
         A.flips[run] = flips;
     }
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(128) walk_generic_kernel(const WalkArgs A)
+{
+    extern __shared__ uint32_t smem_state[];
+    walk_generic_body<SMEM>(A, blockIdx.x, smem_state);
+}
+
+// Batched form: many instances in one launch.  cta_begin[i] = first CTA of item i (n_items + 1
+// entries); a CTA finds its item by binary search and works from a shared-memory copy of its
+// WalkArgs, so thousands of 100-chain solves fill the machine instead of one small grid each.
+__device__ __forceinline__ uint32_t find_item(const uint32_t* __restrict__ cta_begin, uint32_t n_items, uint32_t cta)
+{
+    uint32_t lo = 0, hi = n_items;  // invariant: cta_begin[lo] <= cta < cta_begin[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(cta_begin + mid) <= cta) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void load_item(WalkArgs& dst, const WalkArgs* src)
+{
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
+    for (uint32_t i = threadIdx.x; i < sizeof(WalkArgs) / 4; i += blockDim.x) d[i] = __ldg(s + i);
+    __syncthreads();
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(128) walk_generic_batch_kernel(const WalkArgs* __restrict__ items, const uint32_t* __restrict__ cta_begin,
+                                                                 uint32_t n_items)
+{
+    extern __shared__ uint32_t smem_state[];
+    __shared__ WalkArgs item;
+    const uint32_t it = find_item(cta_begin, n_items, blockIdx.x);
+    load_item(item, items + it);
+    walk_generic_body<SMEM>(item, blockIdx.x - __ldg(cta_begin + it), smem_state);
 }
 
 }  // namespace slsb

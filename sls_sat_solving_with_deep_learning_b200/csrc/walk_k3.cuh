@@ -108,12 +108,12 @@ __device__ __forceinline__ void atoms_add(uint32_t a, uint32_t v)
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(128, 7) walk_k3s_kernel(const WalkArgs A)
+// `block` = index of this CTA among the CTAs of the item (instance) described by A
+__device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block, uint32_t* sm)
 {
-    extern __shared__ uint32_t sm[];
     const int lane = threadIdx.x & 31;
     const uint32_t warp = threadIdx.x >> 5;
-    const uint64_t run = (uint64_t)blockIdx.x * A.warps_per_block + warp;
+    const uint64_t run = (uint64_t)block * A.warps_per_block + warp;
     if (run >= A.nruns) return;
     const DevInst& I = A.inst;
     // byte addresses in the shared window
@@ -191,13 +191,15 @@ __global__ void __launch_bounds__(128, 7) walk_k3s_kernel(const WalkArgs A)
     int err = 0;
     const bool mapping = A.mapping != 0;
     const int algo = A.algo;
-    const bool greedy_possible = A.pfb > 0.0;
+    const double pfb = A.pfb;
+    const uint64_t nsteps = A.nsteps;
+    const bool greedy_possible = pfb > 0.0;
     const bool check_weights = (A.wflags & WF_INTERIOR) == 0;  // some weight is 0, 1 or outside (0,1)
     const uint4* __restrict__ crecx = A.crecx;
     const uint4* __restrict__ orec = I.orec;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
-    while (nf > 0 && steps < A.nsteps) {
+    while (nf > 0 && steps < nsteps) {
         steps++;
         if (rng.off > 128u - 16u) rng.refill();  // a step consumes at most 13 words outside rejection loops
 
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(128, 7) walk_k3s_kernel(const WalkArgs A)
         // lib.rs:231: one f64 is drawn on every step, greedy or not
         bool greedy = false;
         if (greedy_possible)
-            greedy = rng.next_f64() < A.pfb;
+            greedy = rng.next_f64() < pfb;
         else
             rng.skip_u64();
 
@@ -368,6 +370,22 @@ __global__ void __launch_bounds__(128, 7) walk_k3s_kernel(const WalkArgs A)
         A.best_energy[run] = best;
         A.flips[run] = flips;
     }
+}
+
+__global__ void __launch_bounds__(128, 7) walk_k3s_kernel(const WalkArgs A)
+{
+    extern __shared__ uint32_t sm[];
+    walk_k3s_body(A, blockIdx.x, sm);
+}
+
+__global__ void __launch_bounds__(128, 6) walk_k3s_batch_kernel(const WalkArgs* __restrict__ items, const uint32_t* __restrict__ cta_begin,
+                                                                uint32_t n_items)
+{
+    extern __shared__ uint32_t sm[];
+    __shared__ WalkArgs item;
+    const uint32_t it = find_item(cta_begin, n_items, blockIdx.x);
+    load_item(item, items + it);
+    walk_k3s_body(item, blockIdx.x - __ldg(cta_begin + it), sm);
 }
 
 }  // namespace slsb

@@ -249,6 +249,48 @@ def run_sls(
     return buf.to_result(inst.n, nruns, bool(return_trajectories))
 
 
+def run_sls_batch(
+    instances,
+    algo: str,
+    weights_initialize,
+    weights_resample,
+    nsteps: int,
+    nruns: int,
+    pre_compute_mapping: bool = True,
+    prob_flip_best: float = 0.0,
+    seed: int = 0,
+    chain_offset: int = 0,
+):
+    """Many instances in one launch (sls_run_batch): ``weights_*`` are lists with one vector per instance.
+    Returns a list of :class:`SlsResult`; entry i equals ``run_sls(instances[i], ..., seed=seed + i)``."""
+    instances = list(instances)
+    k = len(instances)
+    p = _make_params(algo, nsteps, nruns, False, pre_compute_mapping, prob_flip_best, seed, chain_offset)
+    wi = [_weights(w) for w in weights_initialize]
+    wr = [_weights(w) for w in weights_resample]
+    if len(wi) != k or len(wr) != k:
+        raise ValueError("one weight vector per instance is required")
+    lens = [max(len(a), len(b)) for a, b in zip(wi, wr)]
+    off = np.zeros(k + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    cat_i = np.zeros(max(int(off[-1]), 1), dtype=np.float64)
+    cat_r = np.zeros(max(int(off[-1]), 1), dtype=np.float64)
+    for i in range(k):
+        if len(wi[i]) < instances[i].n or (len(wr[i]) < instances[i].n and algo != "schoening"):
+            raise PanicException(4, "weights shorter than var_count")
+        cat_i[int(off[i]): int(off[i]) + len(wi[i])] = wi[i]
+        cat_r[int(off[i]): int(off[i]) + len(wr[i])] = wr[i]
+    bufs = [_Buffers(inst.n, nruns, nsteps, False) for inst in instances]
+    results = (_lib.RunResult * max(k, 1))(*[b.res for b in bufs])
+    handles = (C.c_void_p * max(k, 1))(*[inst._h.value for inst in instances])
+    _check(_lib.load().sls_run_batch(handles, k, cat_i.ctypes.data, cat_r.ctypes.data, off.ctypes.data, C.byref(p), results))
+    out = []
+    for i, b in enumerate(bufs):
+        b.res = results[i]
+        out.append(b.to_result(instances[i].n, nruns, False))
+    return out
+
+
 class ResidentSolver:
     """State for ``nruns`` chains kept in HBM between launches (sls_solver_* of the C ABI)."""
 

@@ -244,3 +244,52 @@ def test_walk_c2_shape_statistics_and_invariants():
     assert (g.flips_run == g.steps).all() and (g.steps == 3000).all()
     assert oi.energy_distinct(g.best_assignment) == g.best_energy == g.best_energy_run.min()
     assert all(t.min() == e for t, e in zip(g.trajectories, g.best_energy_run))
+
+
+# ---- batched form: many instances per launch ---------------------------------------------------
+@pytest.mark.parametrize("algo", ["moser", "probsat"])
+@pytest.mark.parametrize("force", [{}, {"SLS_B200_FORCE_STATE": "hbm"}, {"SLS_B200_FORCE_GENERIC": "1"}])
+def test_batch_equals_per_instance_runs(expected, algo, force, monkeypatch):
+    for k, v in force.items():
+        monkeypatch.setenv(k, v)
+    names = sorted(expected)  # mixes k<=3 instances (fast kernel) with long-clause G4SAT ones (generic kernel)
+    insts = [eng.Instance.from_dimacs(golden_cnf(nm)) for nm in names]
+    rng = np.random.default_rng(11)
+    w_init = [rng.uniform(0.1, 0.9, i.n) for i in insts]
+    w_res = [rng.uniform(0.1, 0.9, i.n) for i in insts]
+    batch = eng.run_sls_batch(insts, algo, w_init, w_res, 250, 20, True, 0.1, seed=40)
+    assert len(batch) == len(insts)
+    for i, (inst, b) in enumerate(zip(insts, batch)):
+        one = eng.run_sls(inst, algo, w_init[i], w_res[i], 250, 20, False, True, 0.1, seed=40 + i)
+        assert (b.steps == one.steps).all() and (b.found == one.found).all(), names[i]
+        assert (b.best_energy_run == one.best_energy_run).all() and (b.flips_run == one.flips_run).all()
+        assert b.best_energy == one.best_energy
+        assert (b.best_assignment is None) == (one.best_assignment is None)
+        if b.best_assignment is not None:
+            assert (b.best_assignment == one.best_assignment).all()
+    # ... and against the oracle for two of them
+    for i in (0, len(insts) - 1):
+        oi = so.Instance.from_dimacs(golden_cnf(names[i]))
+        o = oi.run_sls(algo, w_init[i], w_res[i], 250, 20, False, True, 0.1, seed=40 + i)
+        assert (batch[i].steps == o.steps).all() and batch[i].best_energy == o.best_energy
+
+
+def test_batch_many_small_instances_config1_shape():
+    # BASELINE config 1 shape: hundreds of small random 3-SAT instances x 100 chains in one launch
+    insts, sols = [], []
+    for i in range(300):
+        n = 100 + (i % 3) * 100
+        m = int(n * (1.0 + 3.0 * (i % 7) / 7))
+        insts.append(eng.Instance.from_clauses(n, random_ksat(n, m, 3, seed=1000 + i)))
+    w = [np.full(i.n, 0.5) for i in insts]
+    res = eng.run_sls_batch(insts, "probsat", w, w, 2000, 100, True, 0.0, seed=7)
+    for inst, r in zip(insts, res):
+        assert r.found.shape == (100,) and (r.steps <= 2000).all()
+        assert ((r.steps < 2000) <= r.found).all()  # a chain stops early only when it has solved the instance
+        if r.found.any():
+            viol, energy = eng.eval_assignments(inst, r.best_assignment[None, :])
+            assert energy[0] == 0 and r.best_energy == 0
+    one = eng.run_sls(insts[17], "probsat", w[17], w[17], 2000, 100, False, True, 0.0, seed=7 + 17)
+    assert (res[17].steps == one.steps).all()
+    with pytest.raises(eng.PanicException):
+        eng.run_sls_batch(insts[:2], "walksat", w[:2], w[:2], 10, 1)
