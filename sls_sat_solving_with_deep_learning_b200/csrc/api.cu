@@ -141,7 +141,9 @@ int ensure_on_device(sls_instance* inst)
     d.off_v = (d.nwords + 3u) & ~3u;
     d.off_l1 = d.off_v + ((d.mwords + 31u) & ~31u);  // vbits zero-padded to whole 32-word groups
     d.l1_pad = std::max(64u, (d.ngroups + 63u) & ~63u);
-    d.slab_words = d.off_l1 + d.l1_pad;
+    d.l2_pad = d.l1_pad > 64 ? ((d.l1_pad / 64 + 63u) & ~63u) : 0u;
+    d.off_l2 = d.off_l1 + d.l1_pad;
+    d.slab_words = d.off_l2 + d.l2_pad;
     d.uniform_k = h.uniform_k;
     d.max_k = h.max_k;
     d.flags = (h.has_duplicates ? INST_HAS_DUPLICATES : 0u) | (h.k3 ? INST_K3 : 0u);

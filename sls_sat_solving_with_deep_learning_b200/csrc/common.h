@@ -20,6 +20,9 @@ struct DevInst {
     // the counter array is zero-padded to l1_pad (a multiple of 64) entries so that a lane can
     // fetch its two counters with one 8-byte load
     uint32_t off_v, off_l1, l1_pad, slab_words;
+    // second counter level (one counter per 64 level-1 counters = 65,536 clauses), only when
+    // l1_pad > 64; zero-padded to l2_pad (a multiple of 64) entries at word offset off_l2
+    uint32_t off_l2, l2_pad;
     uint32_t uniform_k;// clause length when all clauses share it, else 0
     uint32_t max_k;
     uint32_t flags;    // INST_*

@@ -51,12 +51,21 @@ struct Chain {
     uint32_t* abits;
     uint32_t* vbits;
     uint32_t* l1;
+    uint32_t* l2;  // nullptr unless the instance has more than 64 level-1 counters
     int lane;
     uint32_t numfalse;
 
     __device__ __forceinline__ Chain(const DevInst& inst, uint32_t* slab, int lane_)
-        : I(inst), abits(slab), vbits(slab + inst.off_v), l1(slab + inst.off_l1), lane(lane_), numfalse(0)
+        : I(inst), abits(slab), vbits(slab + inst.off_v), l1(slab + inst.off_l1), l2(inst.l2_pad ? slab + inst.off_l2 : nullptr),
+          lane(lane_), numfalse(0)
     {
+    }
+
+    // membership change of canonical clause id: level-1 and (if present) level-2 counters
+    __device__ __forceinline__ void count(uint32_t id, uint32_t delta)
+    {
+        atomicAdd(&l1[id >> 10], delta);
+        if (l2) atomicAdd(&l2[id >> 16], delta);
     }
 
     __device__ __forceinline__ uint32_t abit(uint32_t v) const { return (abits[v >> 5] >> (v & 31)) & 1u; }
@@ -128,35 +137,59 @@ struct Chain {
             }
         }
         __syncwarp();
+        if (l2) {
+            for (uint32_t j = lane; j < I.l2_pad; j += 32) {
+                uint32_t acc = 0;
+                if (j * 64u < I.l1_pad)
+                    for (uint32_t i = 0; i < 64; i++) acc += l1[j * 64u + i];
+                l2[j] = acc;
+            }
+            __syncwarp();
+        }
+    }
+
+    // One round of the counter search: `cnt` holds two adjacent counters per lane (64 per round,
+    // zero-padded); finds the counter containing rank r, subtracts the ranks before it from r and
+    // returns its index; when `more` rounds follow and r lies beyond this one, returns 64.
+    __device__ __forceinline__ uint32_t pick64(const uint32_t* cnt, uint32_t& r, bool more) const
+    {
+        const uint2 cc = reinterpret_cast<const uint2*>(cnt)[lane];
+        const uint32_t both = cc.x + cc.y;
+        const uint32_t incl = warp_incl_scan(both, lane);
+        if (more) {
+            const uint32_t tot = __shfl_sync(FULL, incl, 31);
+            if (r >= tot) {
+                r -= tot;
+                return 64;
+            }
+        }
+        const uint32_t src = __ffs(__ballot_sync(FULL, r < incl)) - 1;
+        r -= __shfl_sync(FULL, incl - both, src);
+        const uint32_t first = __shfl_sync(FULL, cc.x, src);
+        if (r >= first) {
+            r -= first;
+            return 2 * src + 1;
+        }
+        return 2 * src;
     }
 
     // r-th violated clause in increasing canonical clause id; r < numfalse, warp-uniform.
-    // Level A: each lane owns two adjacent level-1 counters (one 8-byte load), a warp scan finds
-    // the group; level B: the 32 words of the group, a warp scan finds the word, a ballot the bit.
+    // Counter levels (each lane owns two adjacent counters, one 8-byte load, a warp scan finds the
+    // counter): level 2 (65,536 clauses per counter, only for more than 65,536 clauses) -> level 1
+    // (1024 clauses) -> the 32 words of the group (popc + warp scan) -> the bit (ballot).
     __device__ __forceinline__ uint32_t select(uint32_t r) const
     {
-        uint32_t g = 0;
-        for (uint32_t gb = 0;; gb += 64) {
-            const uint2 cc = reinterpret_cast<const uint2*>(l1)[(gb >> 1) + lane];
-            const uint32_t both = cc.x + cc.y;
-            const uint32_t incl = warp_incl_scan(both, lane);
-            if (gb + 64 < I.l1_pad) {
-                const uint32_t tot = __shfl_sync(FULL, incl, 31);
-                if (r >= tot) {
-                    r -= tot;
-                    continue;
+        uint32_t gb = 0;
+        if (l2) {
+            for (uint32_t jb = 0;; jb += 64) {
+                const uint32_t j = pick64(l2 + jb, r, jb + 64 < I.l2_pad);
+                if (j < 64) {
+                    gb = (jb + j) * 64u;
+                    break;
                 }
             }
-            const uint32_t src = __ffs(__ballot_sync(FULL, r < incl)) - 1;
-            r -= __shfl_sync(FULL, incl - both, src);
-            const uint32_t first = __shfl_sync(FULL, cc.x, src);
-            g = gb + 2 * src;
-            if (r >= first) {
-                r -= first;
-                g++;
-            }
-            break;
         }
+        const uint32_t g = gb + pick64(l1 + gb, r, false);
         const uint32_t wi = g * 32u + lane;
         const uint32_t word = wi < I.mwords ? vbits[wi] : 0u;
         const uint32_t pc = __popc(word);
@@ -185,13 +218,13 @@ struct Chain {
                     const uint32_t old = atomicOr(&vbits[id >> 5], bit);  // HashSet::insert
                     if (!(old & bit)) {
                         delta = 1;
-                        atomicAdd(&l1[id >> 10], 1u);
+                        count(id, 1u);
                     }
                 } else {
                     const uint32_t old = atomicAnd(&vbits[id >> 5], ~bit);  // HashSet::remove
                     if (old & bit) {
                         delta = -1;
-                        atomicSub(&l1[id >> 10], 1u);
+                        count(id, 0xffffffffu);
                     }
                 }
             }
@@ -459,7 +492,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
 }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(128) walk_generic_kernel(const WalkArgs A)
+__global__ void __launch_bounds__(128, 4) walk_generic_kernel(const WalkArgs A)
 {
     extern __shared__ uint32_t smem_state[];
     walk_generic_body<SMEM>(A, blockIdx.x, smem_state);
@@ -487,7 +520,7 @@ __device__ __forceinline__ void load_item(WalkArgs& dst, const WalkArgs* src)
 }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(128) walk_generic_batch_kernel(const WalkArgs* __restrict__ items, const uint32_t* __restrict__ cta_begin,
+__global__ void __launch_bounds__(128, 4) walk_generic_batch_kernel(const WalkArgs* __restrict__ items, const uint32_t* __restrict__ cta_begin,
                                                                  uint32_t n_items)
 {
     extern __shared__ uint32_t smem_state[];

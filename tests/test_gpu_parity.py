@@ -293,3 +293,19 @@ def test_batch_many_small_instances_config1_shape():
     assert (res[17].steps == one.steps).all()
     with pytest.raises(eng.PanicException):
         eng.run_sls_batch(insts[:2], "walksat", w[:2], w[:2], 10, 1)
+
+
+@pytest.mark.parametrize("force", [{}, {"SLS_B200_FORCE_STATE": "hbm"}])
+def test_walk_more_than_65536_clauses_uses_second_counter_level(force, monkeypatch):
+    # > 64 level-1 counters: the rank select goes through the level-2 counters (config-5 tier)
+    for k, v in force.items():
+        monkeypatch.setenv(k, v)
+    n, m = 30_000, 130_000
+    clauses = random_ksat(n, m, 3, seed=77)
+    gi = eng.Instance.from_clauses(n, clauses)
+    oi = so.Instance.from_clauses(n, clauses)
+    w = np.full(n, 0.5)
+    for algo in ("probsat", "moser"):
+        g = eng.run_sls(gi, algo, w, w, 400, 6, True, True, 0.0, seed=3)
+        o = oi.run_sls(algo, w, w, 400, 6, True, True, 0.0, seed=3)
+        assert_same_run(g, o)
