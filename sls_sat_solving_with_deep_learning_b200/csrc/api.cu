@@ -326,6 +326,8 @@ struct sls_solver {
     uint4* d_crecx = nullptr;
     uint32_t* d_gstate = nullptr;
     uint32_t* d_best_bits = nullptr;
+    uint32_t* d_flip_log = nullptr;
+    uint64_t log_cap = 0;
     uint8_t* d_found = nullptr;
     uint8_t* d_has_best = nullptr;
     uint64_t* d_steps = nullptr;
@@ -347,6 +349,7 @@ extern "C" void sls_solver_free(sls_solver* s)
     cudaFree(s->d_crecx);
     cudaFree(s->d_gstate);
     cudaFree(s->d_best_bits);
+    cudaFree(s->d_flip_log);
     cudaFree(s->d_found);
     cudaFree(s->d_has_best);
     cudaFree(s->d_steps);
@@ -423,6 +426,15 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     if (s->k3) SC_TRY(cudaMalloc(&s->d_crecx, std::max<size_t>(I.m, 1) * CRECX_QUADS * sizeof(uint4)));
     if (!s->smem_state) SC_TRY(cudaMalloc(&s->d_gstate, R1 * slab_bytes));
     SC_TRY(cudaMalloc(&s->d_best_bits, R1 * std::max<size_t>(I.nwords, 1) * 4));
+    if (!s->smem_state) {
+        // flip log instead of cloning the assignment on every improvement (lib.rs:294) when the log
+        // of the whole walk is no larger than four assignment copies
+        const uint64_t per_step = params->algo == SLS_ALGO_MOSER ? std::max<uint32_t>(I.max_k, 1) : 1;
+        if (params->nsteps < (1ull << 40) && params->nsteps * per_step + 1 <= 4ull * I.nwords) {
+            s->log_cap = params->nsteps * per_step + 1;
+            SC_TRY(cudaMalloc(&s->d_flip_log, R1 * s->log_cap * 4));
+        }
+    }
     SC_TRY(cudaMalloc(&s->d_found, R1));
     SC_TRY(cudaMalloc(&s->d_has_best, R1));
     SC_TRY(cudaMalloc(&s->d_steps, R1 * 8));
@@ -456,6 +468,8 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     a.gstate = s->d_gstate;
     a.warps_per_block = s->wpb;
     a.best_bits = s->d_best_bits;
+    a.flip_log = s->d_flip_log;
+    a.log_cap = s->log_cap;
     a.found = s->d_found;
     a.has_best = s->d_has_best;
     a.steps = s->d_steps;

@@ -307,10 +307,24 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
     uint32_t best = I.m;  // lib.rs:203
     bool has_best = false;
     uint32_t* best_bits = A.best_bits + run * (size_t)I.nwords;
+    // lib.rs:294 clones the whole assignment on every improvement.  With a large instance in HBM
+    // that copy would dominate the walk, so there the chain logs the variables it flips and the best
+    // assignment is rebuilt once at the end: current assignment with the flips after the best point undone.
+    uint32_t* flog = A.flip_log ? A.flip_log + run * (size_t)A.log_cap : nullptr;
+    uint32_t nlog = 0, best_pos = 0;
+    auto log_flip = [&](uint32_t v) {  // warp-uniform v
+        if (flog) {
+            if (lane == 0) flog[nlog] = v;
+            nlog++;
+        }
+    };
     auto save_best = [&]() {
         best = ch.numfalse;
         has_best = true;
-        for (uint32_t w = lane; w < I.nwords; w += 32) best_bits[w] = ch.abits[w];
+        if (flog)
+            best_pos = nlog;
+        else
+            for (uint32_t w = lane; w < I.nwords; w += 32) best_bits[w] = ch.abits[w];
     };
     if (ch.numfalse < best) save_best();  // lib.rs:216-219
     uint32_t* traj = A.want_traj ? A.traj + run * (A.nsteps + 1) : nullptr;
@@ -347,6 +361,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
             if (lane == 0) ch.abits[best_v >> 5] ^= 1u << (best_v & 31);
             __syncwarp();
             flips++;
+            log_flip(best_v);
             ch.update_var(best_v);
         } else if (A.algo == ALGO_MOSER || A.algo == ALGO_MOSER_SINGLE) {
             // ---- lib.rs:24-35 / :81-92: one f64 per literal, in literal order
@@ -384,7 +399,9 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
                     while (mask) {
                         const uint32_t j = __ffs(mask) - 1;
                         mask &= mask - 1;
-                        ch.update_var(__ldg(I.lits + s + cb + j) >> 1);
+                        const uint32_t v = __ldg(I.lits + s + cb + j) >> 1;
+                        log_flip(v);
+                        ch.update_var(v);
                     }
                 }
             } else if (nmarks) {
@@ -403,6 +420,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
                 if (lane == 0) ch.abits[v >> 5] ^= 1u << (v & 31);
                 __syncwarp();
                 flips++;
+                log_flip(v);
                 ch.update_var(v);
             }
         } else if (A.algo == ALGO_SCHOENING) {
@@ -415,6 +433,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
             if (lane == 0) ch.abits[v >> 5] ^= 1u << (v & 31);
             __syncwarp();
             flips++;
+            log_flip(v);
             ch.update_var(v);
         } else {
             // ---- lib.rs:57-75 probSAT: WeightedIndex over the flip probabilities
@@ -474,6 +493,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
             if (lane == 0) ch.abits[v >> 5] ^= 1u << (v & 31);
             __syncwarp();
             flips++;
+            log_flip(v);
             ch.update_var(v);
         }
 
@@ -481,6 +501,16 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
         if (traj && lane == 0) traj[steps] = ch.numfalse;  // lib.rs:298-300
     }
 
+    if (flog && has_best) {
+        // best assignment = current assignment with the flips logged after the best point undone
+        __syncwarp();
+        for (uint32_t w = lane; w < I.nwords; w += 32) best_bits[w] = ch.abits[w];
+        __syncwarp();
+        for (uint32_t i = best_pos + lane; i < nlog; i += 32) {
+            const uint32_t v = flog[i];
+            atomicXor(&best_bits[v >> 5], 1u << (v & 31));
+        }
+    }
     if (lane == 0) {
         if (err) atomicCAS(A.err, 0, err);
         A.found[run] = ch.numfalse == 0 && !err;  // lib.rs:305-307

@@ -309,3 +309,21 @@ def test_walk_more_than_65536_clauses_uses_second_counter_level(force, monkeypat
         g = eng.run_sls(gi, algo, w, w, 400, 6, True, True, 0.0, seed=3)
         o = oi.run_sls(algo, w, w, 400, 6, True, True, 0.0, seed=3)
         assert_same_run(g, o)
+
+
+def test_walk_hbm_tier_flip_log_best_assignment(monkeypatch):
+    # HBM tier with a short step budget: the best assignment is rebuilt from the flip log
+    monkeypatch.setenv("SLS_B200_FORCE_STATE", "hbm")
+    n, m = 30_000, 126_000
+    clauses = random_ksat(n, m, 3, seed=78)
+    gi = eng.Instance.from_clauses(n, clauses)
+    oi = so.Instance.from_clauses(n, clauses)
+    w = np.full(n, 0.5)
+    for algo in ("probsat", "moser", "moser_single", "schoening"):
+        for pfb in (0.0, 0.5):
+            g = eng.run_sls(gi, algo, w, w, 300, 5, True, True, pfb, seed=4)  # 300 * k + 1 <= 4 * nwords: log in use
+            o = oi.run_sls(algo, w, w, 300, 5, True, True, pfb, seed=4)
+            assert_same_run(g, o)
+    g = eng.run_sls(gi, "probsat", w, w, 5000, 3, False, True, 0.0, seed=4)  # too long for the log: direct copies
+    o = oi.run_sls("probsat", w, w, 5000, 3, False, True, 0.0, seed=4)
+    assert_same_run(g, o)
