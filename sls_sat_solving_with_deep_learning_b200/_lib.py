@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libsls_b200.so")
 _SOURCES = ["csrc/api.cu", "csrc/gnn_api.cu", "csrc/instance.cpp"]
 _HEADERS = [
     "csrc/common.h", "csrc/philox.cuh", "csrc/instance.h", "csrc/eval.cuh", "csrc/walk_generic.cuh",
-    "csrc/walk_k3.cuh", "csrc/gnn_kernels.cuh", "../include/sls_b200.h",
+    "csrc/walk_k3.cuh", "csrc/init_sliced.cuh", "csrc/gnn_kernels.cuh", "../include/sls_b200.h",
 ]
 
 NVCC_FLAGS = [

@@ -14,6 +14,7 @@
 #include "../../include/sls_b200.h"
 #include "common.h"
 #include "eval.cuh"
+#include "init_sliced.cuh"
 #include "instance.h"
 #include "walk_generic.cuh"
 #include "walk_k3.cuh"
@@ -327,6 +328,9 @@ struct sls_solver {
     uint32_t* d_gstate = nullptr;
     uint32_t* d_best_bits = nullptr;
     uint32_t* d_flip_log = nullptr;
+    uint32_t* d_nf_init = nullptr;   // HBM tier: initial energies from the sliced init
+    uint32_t* d_tbits = nullptr;     // HBM tier: transposed assignments of one chunk of slices
+    uint32_t tbits_slices = 0;
     uint64_t log_cap = 0;
     uint8_t* d_found = nullptr;
     uint8_t* d_has_best = nullptr;
@@ -350,6 +354,8 @@ extern "C" void sls_solver_free(sls_solver* s)
     cudaFree(s->d_gstate);
     cudaFree(s->d_best_bits);
     cudaFree(s->d_flip_log);
+    cudaFree(s->d_nf_init);
+    cudaFree(s->d_tbits);
     cudaFree(s->d_found);
     cudaFree(s->d_has_best);
     cudaFree(s->d_steps);
@@ -426,6 +432,14 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     if (s->k3) SC_TRY(cudaMalloc(&s->d_crecx, std::max<size_t>(I.m, 1) * CRECX_QUADS * sizeof(uint4)));
     if (!s->smem_state) SC_TRY(cudaMalloc(&s->d_gstate, R1 * slab_bytes));
     SC_TRY(cudaMalloc(&s->d_best_bits, R1 * std::max<size_t>(I.nwords, 1) * 4));
+    if (!s->smem_state && !(I.flags & INST_HAS_DUPLICATES) && I.n > 0 && I.m > 0) {
+        // chains are initialised 32 at a time by the sliced kernels (init_sliced.cuh); the transposed
+        // assignments of one chunk of slices are kept in a scratch buffer of at most ~1 GB
+        const uint64_t nslices = (R + 31) / 32;
+        s->tbits_slices = (uint32_t)std::min<uint64_t>(nslices, std::max<uint64_t>(1, (1ull << 28) / I.n));
+        SC_TRY(cudaMalloc(&s->d_tbits, size_t(s->tbits_slices) * I.n * 4));
+        SC_TRY(cudaMalloc(&s->d_nf_init, R1 * 4));
+    }
     if (!s->smem_state) {
         // flip log instead of cloning the assignment on every improvement (lib.rs:294) when the log
         // of the whole walk is no larger than four assignment copies
@@ -469,6 +483,7 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     a.warps_per_block = s->wpb;
     a.best_bits = s->d_best_bits;
     a.flip_log = s->d_flip_log;
+    a.nf_init = s->d_nf_init;
     a.log_cap = s->log_cap;
     a.found = s->d_found;
     a.has_best = s->d_has_best;
@@ -543,6 +558,25 @@ extern "C" int sls_solver_launch(sls_solver* s, void* cuda_stream)
     const unsigned blocks = (unsigned)((s->p.nruns + s->wpb - 1) / s->wpb);
     const unsigned threads = s->wpb * 32;
     CUDA_TRY(cudaEventRecord(s->ev0, st));
+    if (s->d_nf_init) {
+        // HBM tier: prepare every chain's slab with the sliced kernels
+        const DevInst& I = s->args.inst;
+        const uint64_t R = s->p.nruns;
+        CUDA_TRY(cudaMemsetAsync(s->d_gstate, 0, R * size_t(I.slab_words) * 4, st));
+        const uint32_t nslices = (uint32_t)((R + 31) / 32);
+        const uint32_t words_per_block = 64;
+        for (uint32_t s0 = 0; s0 < nslices; s0 += s->tbits_slices) {
+            const uint32_t cnt = std::min(s->tbits_slices, nslices - s0);
+            dim3 g1((I.nwords + words_per_block - 1) / words_per_block, cnt);
+            init_assign_sliced_kernel<<<g1, 128, 0, st>>>(s->args, s->d_tbits, s0, words_per_block);
+            dim3 g2((I.ngroups + 3) / 4, cnt);
+            init_scan_sliced_kernel<<<g2, 128, 0, st>>>(s->args, s->d_tbits, s0);
+            s->launches += 2;
+        }
+        init_counters_kernel<<<(unsigned)((R * 32 + 127) / 128), 128, 0, st>>>(s->args);
+        s->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
     const bool use_k3 = s->k3 && walk_k3_supports(s->args);
     if (use_k3) {
         walk_k3s_kernel<<<blocks, threads, s->smem_bytes, st>>>(s->args);
@@ -552,7 +586,7 @@ extern "C" int sls_solver_launch(sls_solver* s, void* cuda_stream)
         else
             walk_generic_kernel<false><<<blocks, threads, 0, st>>>(s->args);
     }
-    s->launches = 1;
+    s->launches += 1;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s->ev1, st));
     return SLS_OK;

@@ -59,6 +59,7 @@ struct WalkArgs {
     uint32_t warps_per_block;
     uint32_t pad2;
     uint32_t* best_bits;       // [nruns][nwords]
+    uint32_t* nf_init;         // [nruns] initial energy when the slab was prepared by init_sliced.cuh, else nullptr
     uint32_t* flip_log;        // [nruns][log_cap] flipped variables (HBM tier with a bounded step budget) or nullptr
     uint64_t log_cap;
     uint8_t* found;            // [nruns]

@@ -277,32 +277,37 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
     Chain<SMEM> ch(I, slab, lane);
     const uint64_t chain = A.chain_offset + run;
 
+    if (A.nf_init) {
+        // the slab was prepared 32 chains at a time by init_sliced.cuh
+        ch.numfalse = A.nf_init[run];
+    } else {
     // ---- lib.rs:206-210: assignment[i] = gen_bool(weights_initialize[i]) on the init stream
-    {
-        const ChainKey ck(A.seed, chain, STREAM_INIT);
-        for (uint32_t w = lane; w < I.nwords; w += 32) {
-            uint32_t bits = 0;
+        {
+            const ChainKey ck(A.seed, chain, STREAM_INIT);
+            for (uint32_t w = lane; w < I.nwords; w += 32) {
+                uint32_t bits = 0;
 #pragma unroll 4
-            for (uint32_t b = 0; b < 16; b++) {
-                const uint32_t v0 = w * 32u + 2u * b;
-                if (v0 >= I.n) break;
-                const uint4 x = ck.block((uint64_t)(v0 >> 1));
-                const uint64_t t0 = __ldg(A.thr_init + v0);
-                const uint64_t u0 = (uint64_t)x.y << 32 | x.x;
-                bits |= (uint32_t)(t0 == ~0ull || u0 < t0) << (2u * b);
-                if (v0 + 1 < I.n) {
-                    const uint64_t t1 = __ldg(A.thr_init + v0 + 1);
-                    const uint64_t u1 = (uint64_t)x.w << 32 | x.z;
-                    bits |= (uint32_t)(t1 == ~0ull || u1 < t1) << (2u * b + 1u);
+                for (uint32_t b = 0; b < 16; b++) {
+                    const uint32_t v0 = w * 32u + 2u * b;
+                    if (v0 >= I.n) break;
+                    const uint4 x = ck.block((uint64_t)(v0 >> 1));
+                    const uint64_t t0 = __ldg(A.thr_init + v0);
+                    const uint64_t u0 = (uint64_t)x.y << 32 | x.x;
+                    bits |= (uint32_t)(t0 == ~0ull || u0 < t0) << (2u * b);
+                    if (v0 + 1 < I.n) {
+                        const uint64_t t1 = __ldg(A.thr_init + v0 + 1);
+                        const uint64_t u1 = (uint64_t)x.w << 32 | x.z;
+                        bits |= (uint32_t)(t1 == ~0ull || u1 < t1) << (2u * b + 1u);
+                    }
                 }
+                ch.abits[w] = bits;
             }
-            ch.abits[w] = bits;
+            __syncwarp();
         }
-        __syncwarp();
+        ch.full_scan();  // lib.rs:213-214
     }
 
     WarpStream rng(A.seed, chain, lane);
-    ch.full_scan();  // lib.rs:213-214
 
     uint32_t best = I.m;  // lib.rs:203
     bool has_best = false;
