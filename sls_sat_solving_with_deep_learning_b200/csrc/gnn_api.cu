@@ -37,7 +37,7 @@ float round_tf32_host(float x)
 
 struct DevMlp {
     int k1 = 0, h1 = 0, h2 = 0, k1_slabs = 0, k2_slabs = 0, n1 = 0, n2 = 0;
-    float *w1t_hi = nullptr, *w1t_lo = nullptr, *b1 = nullptr, *w2t_hi = nullptr, *w2t_lo = nullptr, *b2 = nullptr, *ln_scale = nullptr,
+    float *w1_hi = nullptr, *w1_lo = nullptr, *b1 = nullptr, *w2_hi = nullptr, *w2_lo = nullptr, *b2 = nullptr, *ln_scale = nullptr,
           *ln_offset = nullptr;
 };
 
@@ -86,14 +86,21 @@ int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& 
     out.n1 = round_up(h1, 16);
     out.n2 = round_up(h2, 16);
     const int k1p = out.k1_slabs * SLAB_K, k2p = out.k2_slabs * SLAB_K;
-    // 3xTF32: w = hi + lo with hi = tf32(w), lo = tf32(w - hi)
+    // 3xTF32: w = hi + lo with hi = tf32(w), lo = tf32(w - hi).  Stored as shared-memory slab images:
+    // slab s = W^T[n][32 s .. 32 s + 31] for all n, in the K-major SWIZZLE_128B layout the kernel's
+    // UMMA descriptors expect (8-row groups of 1024 B, 16-byte unit index XOR n % 8), zero padded.
+    auto img_index = [](int n_pad, int s, int n, int k_in_slab) {
+        const int u = k_in_slab >> 2, e = k_in_slab & 3;
+        return (size_t)s * n_pad * SLAB_K + (size_t)(n >> 3) * 256 + (size_t)(n & 7) * 32 + (size_t)((u ^ (n & 7)) << 2) + e;
+    };
     std::vector<float> w1h((size_t)out.n1 * k1p, 0.f), w1l(w1h.size(), 0.f), b1(out.n1, 0.f);
     std::vector<float> w2h((size_t)out.n2 * k2p, 0.f), w2l(w2h.size(), 0.f), b2(out.n2, 0.f);
     for (int k = 0; k < k1; k++)
         for (int n = 0; n < h1; n++) {
             const float w = p[(size_t)k * h1 + n], hi = round_tf32_host(w);
-            w1h[(size_t)n * k1p + k] = hi;
-            w1l[(size_t)n * k1p + k] = round_tf32_host(w - hi);
+            const size_t ix = img_index(out.n1, k / SLAB_K, n, k % SLAB_K);
+            w1h[ix] = hi;
+            w1l[ix] = round_tf32_host(w - hi);
         }
     p += (size_t)k1 * h1;
     std::copy(p, p + h1, b1.begin());
@@ -101,8 +108,9 @@ int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& 
     for (int k = 0; k < h1; k++)
         for (int n = 0; n < h2; n++) {
             const float w = p[(size_t)k * h2 + n], hi = round_tf32_host(w);
-            w2h[(size_t)n * k2p + k] = hi;
-            w2l[(size_t)n * k2p + k] = round_tf32_host(w - hi);
+            const size_t ix = img_index(out.n2, k / SLAB_K, n, k % SLAB_K);
+            w2h[ix] = hi;
+            w2l[ix] = round_tf32_host(w - hi);
         }
     p += (size_t)h1 * h2;
     std::copy(p, p + h2, b2.begin());
@@ -110,11 +118,11 @@ int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& 
     std::vector<float> sc(p, p + h2), of(p + h2, p + 2 * h2);
     p += 2 * h2;
     int rc;
-    if ((rc = upload(w1h, &out.w1t_hi)) || (rc = upload(w1l, &out.w1t_lo)) || (rc = upload(b1, &out.b1)) || (rc = upload(w2h, &out.w2t_hi)) ||
-        (rc = upload(w2l, &out.w2t_lo)) || (rc = upload(b2, &out.b2)) || (rc = upload(sc, &out.ln_scale)) ||
+    if ((rc = upload(w1h, &out.w1_hi)) || (rc = upload(w1l, &out.w1_lo)) || (rc = upload(b1, &out.b1)) || (rc = upload(w2h, &out.w2_hi)) ||
+        (rc = upload(w2l, &out.w2_lo)) || (rc = upload(b2, &out.b2)) || (rc = upload(sc, &out.ln_scale)) ||
         (rc = upload(of, &out.ln_offset)))
         return rc;
-    for (float* q : {out.w1t_hi, out.w1t_lo, out.b1, out.w2t_hi, out.w2t_lo, out.b2, out.ln_scale, out.ln_offset}) m->allocs.push_back(q);
+    for (float* q : {out.w1_hi, out.w1_lo, out.b1, out.w2_hi, out.w2_lo, out.b2, out.ln_scale, out.ln_offset}) m->allocs.push_back(q);
     return SLS_OK;
 }
 
@@ -205,7 +213,7 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
     a.d[0] = d0, a.d[1] = d1, a.d[2] = d2;
     a.rows = (int32_t)rows;
     a.k1_slabs = w.k1_slabs, a.k2_slabs = w.k2_slabs, a.n1 = w.n1, a.n2 = w.n2, a.h2 = w.h2;
-    a.w1t_hi = w.w1t_hi, a.w1t_lo = w.w1t_lo, a.b1 = w.b1, a.w2t_hi = w.w2t_hi, a.w2t_lo = w.w2t_lo, a.b2 = w.b2;
+    a.w1_hi = w.w1_hi, a.w1_lo = w.w1_lo, a.b1 = w.b1, a.w2_hi = w.w2_hi, a.w2_lo = w.w2_lo, a.b2 = w.b2;
     a.ln_scale = w.ln_scale, a.ln_offset = w.ln_offset;
     a.out = out;
     const unsigned blocks = (unsigned)((rows + TILE_M - 1) / TILE_M);

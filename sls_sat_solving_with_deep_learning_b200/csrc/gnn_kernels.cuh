@@ -11,8 +11,9 @@
 //
 // The two dense contractions of every update (K1 x H and H x H, K1 = 96 / 432 / 600, H = 200)
 // run on the 5th-generation tensor cores: tcgen05.mma kind::tf32 with the accumulators in TMEM,
-// operands staged in shared memory in the canonical K-major SWIZZLE_128B layout, completion
-// tracked with mbarriers via tcgen05.commit.  One CTA owns a tile of 128 rows (edges or nodes) and
+// operands staged in shared memory in the canonical K-major SWIZZLE_128B layout (weights by TMA
+// bulk copies of pre-swizzled slab images, activations by the threads), completion tracked with
+// mbarriers via tcgen05.commit.  One CTA owns a tile of 128 rows (edges or nodes) and
 // runs the whole update for it: gather -> GEMM1 -> bias+ReLU -> GEMM2 -> bias+ReLU -> LayerNorm ->
 // global.  Nothing but the tile's inputs and its normalised output touches HBM; the hidden
 // activation goes TMEM -> registers -> shared memory slab by slab as GEMM2 consumes it.
@@ -33,13 +34,19 @@ static constexpr int SLAB_K = 32;        // tf32 elements per 128-byte swizzle r
 static constexpr int MAX_N = 208;        // padded output width (multiple of 16, >= hidden)
 static constexpr int A_SLAB_BYTES = TILE_M * 128;   // 16 KB
 static constexpr int B_SLAB_BYTES = MAX_N * 128;    // 26 KB
-// one pipeline stage = one K-slab of all four operands: A_hi | A_lo | B_hi | B_lo
-static constexpr int STAGE_BYTES = 2 * A_SLAB_BYTES + 2 * B_SLAB_BYTES;  // 84 KB
-static constexpr int STAGES = 2;
+// pipeline buffers: A_STAGES x (A_hi | A_lo) filled by the threads, B_STAGES x (B_hi | B_lo) filled
+// by TMA bulk copies of pre-swizzled weight slab images
+static constexpr int A_STAGES = 2;
+static constexpr int B_STAGES = 3;
+static constexpr int A_STAGE_BYTES = 2 * A_SLAB_BYTES;   // 32 KB
+static constexpr int B_STAGE_BYTES = 2 * B_SLAB_BYTES;   // 52 KB
+static constexpr int DONE_BARS = 6;                      // lcm(A_STAGES, B_STAGES): one per slab index mod 6
 static constexpr int TMEM_COLS = 512;
 static constexpr int ACC2_COL = 256;
 static constexpr int MLP_THREADS = 128;
-static constexpr int MLP_SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
+static constexpr int PAR_BYTES = 3 * MAX_N * 4;          // b2 | ln_scale | ln_offset staged in shared memory
+static constexpr int OUT_PITCH = 204;                   // floats per row of the output tile (816 B: conflict-free 16-byte stores)
+static constexpr int MLP_SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 256 + PAR_BYTES + 1024;  // + barriers + alignment slack
 
 struct MlpArgs {
     // up to three gathered input segments: row i of the A matrix is
@@ -52,11 +59,13 @@ struct MlpArgs {
     int32_t k2_slabs;    // ceil(h1/32)
     int32_t n1, n2;      // padded output widths of the two linears (multiples of 16, <= 208)
     int32_t h2;          // true output width (LayerNorm length)
-    const float* w1t_hi; // [n1][k1_slabs*32] transposed weights, TF32-rounded, zero padded
-    const float* w1t_lo; // [n1][k1_slabs*32] TF32-rounded residual w - hi
+    // weights as shared-memory slab images: [k_slabs][n_pad * 32] floats, slab s holding W^T[n][32 s .. 32 s + 31]
+    // already in the K-major SWIZZLE_128B layout (sw128_off), so one bulk copy per slab stages it
+    const float* w1_hi;  // TF32-rounded weights
+    const float* w1_lo;  // TF32-rounded residual w - hi
     const float* b1;     // [n1] zero padded
-    const float* w2t_hi; // [n2][k2_slabs*32]
-    const float* w2t_lo;
+    const float* w2_hi;
+    const float* w2_lo;
     const float* b2;     // [n2]
     const float* ln_scale;   // [h2]
     const float* ln_offset;  // [h2]
@@ -66,13 +75,6 @@ struct MlpArgs {
 // ---- small PTX helpers -----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -89,6 +91,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "  mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "  @!p bra WAIT_%=;\n }"
         ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (contiguous bytes), completion counted on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar) : "memory");
 }
 // tcgen05.commit: the mbarrier is arrived on when all previously issued MMAs have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar)
@@ -148,8 +160,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sBar = base + STAGES * STAGE_BYTES;            // one mbarrier per stage
-    const uint32_t sTmem = sBar + 8 * STAGES;                     // TMEM base address written by tcgen05.alloc
+    const uint32_t sAst = base;                                   // A stages
+    const uint32_t sBst = base + A_STAGES * A_STAGE_BYTES;        // B stages
+    const uint32_t sFull = sBst + B_STAGES * B_STAGE_BYTES;       // B_STAGES "weights landed" mbarriers
+    const uint32_t sDone = sFull + 8 * B_STAGES;                  // DONE_BARS "MMAs of slab j done" mbarriers
+    const uint32_t sTmem = sDone + 8 * DONE_BARS;                 // TMEM base address written by tcgen05.alloc
+    const uint32_t sPar = sFull + 128;                            // b2[MAX_N] | ln_scale[MAX_N] | ln_offset[MAX_N] (16-byte aligned)
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));   // generic alias of `base`
 
     const int tid = threadIdx.x;
@@ -158,8 +174,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
     const int my_row = min(row0 + tid, P.rows - 1);  // rows past the end re-read the last row; their output is not stored
 
     if (tid == 0) {
-        for (int i = 0; i < STAGES; i++) mbar_init(sBar + 8 * i, 1);
+        for (int i = 0; i < B_STAGES; i++) mbar_init(sFull + 8 * i, 1);
+        for (int i = 0; i < DONE_BARS; i++) mbar_init(sDone + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < MAX_N; i += MLP_THREADS) {  // epilogue parameters -> shared memory (read as broadcasts)
+        const bool in = i < P.h2;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + i * 4), "f"(i < P.n2 ? __ldg(P.b2 + i) : 0.f) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + (MAX_N + i) * 4), "f"(in ? __ldg(P.ln_scale + i) : 0.f) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + (2 * MAX_N + i) * 4), "f"(in ? __ldg(P.ln_offset + i) : 0.f) : "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "r"(TMEM_COLS) : "memory");
@@ -182,9 +205,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
         }
     }
     const int kA = P.d[0] + P.d[1] + P.d[2];
-    const int k1p = P.k1_slabs * SLAB_K, k2p = P.k2_slabs * SLAB_K;
 
-    // write one 16-byte unit of this thread's row, split into TF32 hi / lo, into the stage's A slabs
+    // write one 16-byte unit of this thread's row, split into TF32 hi / lo, into an A stage
     auto put_split = [&](uint32_t stage_base, int u, float4 x) {
         float4 hi, lo;
         hi.x = round_tf32(x.x), hi.y = round_tf32(x.y), hi.z = round_tf32(x.z), hi.w = round_tf32(x.w);
@@ -193,22 +215,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + A_SLAB_BYTES + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
     };
-    // B slabs (weights, already split): cp.async straight into the swizzled layout
-    auto stage_b = [&](uint32_t stage_base, const float* w_hi, const float* w_lo, int n_pad, int kp, int s) {
-        const uint32_t bHi = stage_base + 2 * A_SLAB_BYTES, bLo = bHi + B_SLAB_BYTES;
-        for (int n = tid; n < n_pad; n += MLP_THREADS) {
-            const size_t o = (size_t)n * kp + s * SLAB_K;
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                cp_async16(bHi + sw128_off(n, u), w_hi + o + u * 4);
-                cp_async16(bLo + sw128_off(n, u), w_lo + o + u * 4);
-            }
-        }
-        cp_async_commit();
-    };
-    // GEMM1 A slab: this thread's gathered row, columns [32 s, 32 s + 32)
-    auto stage_a1 = [&](uint32_t stage_base, int s) {
-        float4 x[8];
+    // GEMM1 A slab: this thread's gathered row, columns [32 s, 32 s + 32), into registers
+    auto load_a1 = [&](int s, float4* x) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             const int col = s * SLAB_K + u * 4;
@@ -218,8 +226,6 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
                 x[u] = __ldg(reinterpret_cast<const float4*>(p));
             }
         }
-#pragma unroll
-        for (int u = 0; u < 8; u++) put_split(stage_base, u, x[u]);
     };
     // GEMM2 A slab: Y1 = ReLU(acc1 + b1), columns [32 s, 32 s + 32), straight out of TMEM
     auto stage_a2 = [&](uint32_t stage_base, int s) {
@@ -240,31 +246,48 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
         }
     };
 
-    uint32_t stage_phase = 0;  // bit st = parity the next wait on stage barrier st expects
-    auto wait_stage = [&](int st) {
-        mbar_wait(sBar + 8 * st, (stage_phase >> st) & 1u);
-        stage_phase ^= 1u << st;
-    };
-    // Pipeline over `nslabs` K-slabs with STAGES buffers.  Slab s is staged into buffer s % STAGES
-    // (after the MMAs of slab s - STAGES, its previous occupant, have completed), then one thread
-    // issues its 12 MMAs and a tcgen05.commit on the buffer's mbarrier.  The MMAs run asynchronously
-    // while all threads stage the next slab.  Every commit is waited on exactly once (the last
-    // min(STAGES, nslabs) in the drain), so when run_gemm returns the accumulator is complete.
-    auto run_gemm = [&](int nslabs, int n_pad, int kp, uint32_t acc_col, const float* w_hi, const float* w_lo, auto&& stage_a) {
+    // Pipeline.  `gs` numbers the K-slabs of both GEMMs consecutively; slab j uses A stage j % 2, B
+    // stage j % 3, signals its completion (tcgen05.commit after its 12 MMAs) on sDone[j % 6] and its
+    // weights arrive on sFull[j % 3].  A stage j % 2 is refilled by all threads once slab j - 2 is done;
+    // B stage j % 3 is refilled by thread 0 (two bulk copies, prefetch distance 2) once slab j - 3 is
+    // done.  The gathered A rows of the next slab are loaded into registers before the MMAs of the
+    // current slab are issued, so their latency overlaps the tensor work.
+    uint32_t gs = 0;
+    auto wait_done = [&](uint32_t j) { mbar_wait(sDone + 8 * (j % DONE_BARS), (j / DONE_BARS) & 1u); };
+    auto run_gemm = [&](int nslabs, int n_pad, uint32_t acc_col, const float* img_hi, const float* img_lo, bool gemm1) {
         const uint32_t idesc = idesc_tf32(TILE_M, n_pad);
-        for (int s = 0; s < nslabs; s++) {
-            const int st = s % STAGES;
-            const uint32_t sb = base + st * STAGE_BYTES;
-            if (s >= STAGES) wait_stage(st);
-            stage_b(sb, w_hi, w_lo, n_pad, kp, s);
-            stage_a(sb, s);
-            cp_async_wait<0>();
+        const uint32_t bbytes = (uint32_t)n_pad * 128u;
+        const size_t bfloats = (size_t)n_pad * SLAB_K;
+        const uint32_t g0 = gs;
+        auto issue_b = [&](uint32_t j, int s) {  // thread 0 only
+            const uint32_t bs = sBst + (j % B_STAGES) * B_STAGE_BYTES, bar = sFull + 8 * (j % B_STAGES);
+            if (j >= (uint32_t)B_STAGES) wait_done(j - B_STAGES);
+            mbar_expect_tx(bar, 2 * bbytes);
+            bulk_g2s(bs, img_hi + (size_t)s * bfloats, bbytes, bar);
+            bulk_g2s(bs + B_SLAB_BYTES, img_lo + (size_t)s * bfloats, bbytes, bar);
+        };
+        if (tid == 0)
+            for (int p = 0; p < B_STAGES - 1 && p < nslabs; p++) issue_b(g0 + p, p);
+        float4 xa[8];
+        if (gemm1) load_a1(0, xa);
+        for (int s = 0; s < nslabs; s++, gs++) {
+            const uint32_t sa = sAst + (gs % A_STAGES) * A_STAGE_BYTES;
+            if (gs >= (uint32_t)A_STAGES) wait_done(gs - A_STAGES);
+            if (gemm1) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) put_split(sa, u, xa[u]);
+                if (s + 1 < nslabs) load_a1(s + 1, xa);
+            } else {
+                stage_a2(sa, s);
+            }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
             tc_fence_before();
             __syncthreads();
             if (tid == 0) {
+                mbar_wait(sFull + 8 * (gs % B_STAGES), (gs / B_STAGES) & 1u);  // this slab's weights have landed
                 tc_fence_after();
-                const uint32_t aHi = sb, aLo = sb + A_SLAB_BYTES, bHi = sb + 2 * A_SLAB_BYTES, bLo = bHi + B_SLAB_BYTES;
+                const uint32_t aHi = sa, aLo = sa + A_SLAB_BYTES;
+                const uint32_t bHi = sBst + (gs % B_STAGES) * B_STAGE_BYTES, bLo = bHi + B_SLAB_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < 4; kk++) {  // 4 k-steps of 8 tf32 (32 bytes) per 128-byte slab row
                     const uint32_t o = kk * 32;
@@ -272,55 +295,77 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
                     umma_tf32(tmem + acc_col, smem_desc_sw128(aLo + o), smem_desc_sw128(bHi + o), idesc, 1u);
                     umma_tf32(tmem + acc_col, smem_desc_sw128(aHi + o), smem_desc_sw128(bLo + o), idesc, 1u);
                 }
-                umma_commit(sBar + 8 * st);
+                umma_commit(sDone + 8 * (gs % DONE_BARS));
+                if (s + B_STAGES - 1 < nslabs) issue_b(gs + B_STAGES - 1, s + B_STAGES - 1);
             }
         }
-        for (int j = max(0, nslabs - STAGES); j < nslabs; j++) wait_stage(j % STAGES);
+        wait_done(gs - 1);  // the last slab's commit covers every MMA issued before it
         tc_fence_after();
     };
 
     // ---------------- GEMM1: acc1[128 x n1] = A[128 x K1] * W1 -----------------
-    run_gemm(P.k1_slabs, P.n1, k1p, 0u, P.w1t_hi, P.w1t_lo, stage_a1);
+    run_gemm(P.k1_slabs, P.n1, 0u, P.w1_hi, P.w1_lo, true);
     // ---------------- GEMM2: acc2[128 x n2] = ReLU(acc1 + b1)[128 x h1] * W2 -----------------
-    run_gemm(P.k2_slabs, P.n2, k2p, (uint32_t)ACC2_COL, P.w2t_hi, P.w2t_lo, stage_a2);
+    run_gemm(P.k2_slabs, P.n2, (uint32_t)ACC2_COL, P.w2_hi, P.w2_lo, false);
 
-    // ---------------- epilogue 2: LayerNorm(ReLU(acc2 + b2)) -> global --------------------------
+    // ---------------- epilogue 2: LayerNorm(ReLU(acc2 + b2)) -> shared tile -> coalesced global stores ----
     {
         const int H = P.h2;
+        auto lds4 = [](uint32_t a) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+            return v;
+        };
+        // x = ReLU(acc + b2) for 16 columns starting at c0 (columns >= H come out as 0: zero weights, zero bias)
+        auto load_x = [&](int c0, float* x) {
+            tmem_ld16(tmem + lane_base + (uint32_t)(ACC2_COL + c0), x);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float4 b = lds4(sPar + (c0 + 4 * q) * 4);
+                x[4 * q] = fmaxf(x[4 * q] + b.x, 0.f), x[4 * q + 1] = fmaxf(x[4 * q + 1] + b.y, 0.f);
+                x[4 * q + 2] = fmaxf(x[4 * q + 2] + b.z, 0.f), x[4 * q + 3] = fmaxf(x[4 * q + 3] + b.w, 0.f);
+            }
+        };
         float sum = 0.f;
         for (int c0 = 0; c0 < H; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem + lane_base + (uint32_t)(ACC2_COL + c0), v);
+            float x[16];
+            load_x(c0, x);
 #pragma unroll
-            for (int i = 0; i < 16; i++)
-                if (c0 + i < H) sum += fmaxf(v[i] + __ldg(P.b2 + c0 + i), 0.f);
+            for (int i = 0; i < 16; i++) sum += x[i];  // padding columns contribute exact zeros
         }
         const float mean = sum / (float)H;
         float sq = 0.f;
         for (int c0 = 0; c0 < H; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem + lane_base + (uint32_t)(ACC2_COL + c0), v);
+            float x[16];
+            load_x(c0, x);
 #pragma unroll
             for (int i = 0; i < 16; i++)
-                if (c0 + i < H) {
-                    const float d = fmaxf(v[i] + __ldg(P.b2 + c0 + i), 0.f) - mean;
-                    sq += d * d;
-                }
+                if (c0 + i < H) sq += (x[i] - mean) * (x[i] - mean);
         }
         const float rstd = rsqrtf(sq / (float)H + 1e-5f);  // haiku LayerNorm: biased variance, eps = 1e-5
-        const int grow = row0 + tid;
+        // the B stages are idle now (all MMAs done, all bulk copies consumed): use them as the output tile
+        const uint32_t sOut = sBst;
         for (int c0 = 0; c0 < H; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem + lane_base + (uint32_t)(ACC2_COL + c0), v);
-            if (grow < P.rows) {
-                float* o = P.out + (size_t)grow * H + c0;
+            float x[16];
+            load_x(c0, x);
 #pragma unroll
-                for (int i = 0; i < 16; i++)
-                    if (c0 + i < H) {
-                        const float x = fmaxf(v[i] + __ldg(P.b2 + c0 + i), 0.f);
-                        o[i] = (x - mean) * rstd * __ldg(P.ln_scale + c0 + i) + __ldg(P.ln_offset + c0 + i);
-                    }
+            for (int q = 0; q < 4; q++) {
+                if (c0 + 4 * q < H) {  // H is a multiple of 4
+                    const float4 sc = lds4(sPar + (MAX_N + c0 + 4 * q) * 4), of = lds4(sPar + (2 * MAX_N + c0 + 4 * q) * 4);
+                    const float y0 = (x[4 * q] - mean) * rstd * sc.x + of.x, y1 = (x[4 * q + 1] - mean) * rstd * sc.y + of.y;
+                    const float y2 = (x[4 * q + 2] - mean) * rstd * sc.z + of.z, y3 = (x[4 * q + 3] - mean) * rstd * sc.w + of.w;
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sOut + (tid * OUT_PITCH + c0 + 4 * q) * 4), "f"(y0), "f"(y1),
+                                 "f"(y2), "f"(y3) : "memory");
+                }
             }
+        }
+        __syncthreads();
+        const int rows_here = min(TILE_M, P.rows - row0);
+        const int q_per_row = H / 4;
+        float4* out4 = reinterpret_cast<float4*>(P.out + (size_t)row0 * H);
+        for (int i = tid; i < rows_here * q_per_row; i += MLP_THREADS) {
+            const int r = i / q_per_row, q = i - r * q_per_row;
+            out4[i] = lds4(sOut + (r * OUT_PITCH + 4 * q) * 4);  // consecutive threads -> consecutive 16-byte chunks of the output
         }
     }
     tc_fence_before();
