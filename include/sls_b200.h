@@ -119,10 +119,12 @@ int sls_run(sls_instance *inst, const double *w_init, size_t w_init_len, const d
  * trajectories), one launch per kernel variant instead of one small grid per instance.  Replaces the
  * sequential per-file loop of python/src/evaluate_with_given_params.py:108-138.  w_init / w_resample
  * are the per-instance weight vectors concatenated; instance i owns [var_offsets[i], var_offsets[i+1]).
- * Instance i runs with seed params->seed + i, i.e. results[i] is identical to sls_run(insts[i], ...,
- * seed + i).  results[i] carries caller-allocated per-instance buffers like sls_run. */
+ * Instance i runs with seed instance_seeds[i] (or params->seed + i when instance_seeds is NULL), i.e.
+ * results[i] is identical to sls_run(insts[i], ..., that seed): sharding a batch over processes does not
+ * change any instance's result.  results[i] carries caller-allocated per-instance buffers like sls_run. */
 int sls_run_batch(sls_instance *const *insts, uint32_t n_inst, const double *w_init, const double *w_resample,
-                  const uint64_t *var_offsets, const sls_run_params *params, sls_run_result *results);
+                  const uint64_t *var_offsets, const uint64_t *instance_seeds, const sls_run_params *params,
+                  sls_run_result *results);
 
 /* resident form: state for params->nruns chains stays in HBM between launches */
 typedef struct sls_solver sls_solver;

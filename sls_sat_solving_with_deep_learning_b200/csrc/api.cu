@@ -726,7 +726,8 @@ struct ItemPlan {
 }  // namespace
 
 extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const double* w_init, const double* w_resample,
-                             const uint64_t* var_offsets, const sls_run_params* params, sls_run_result* results)
+                             const uint64_t* var_offsets, const uint64_t* instance_seeds, const sls_run_params* params,
+                             sls_run_result* results)
 {
     if ((n_inst && (!insts || !results || !var_offsets)) || !params) return set_error(SLS_ERR_ARG, "NULL argument");
     if (params->algo < 0 || params->algo > 3) return set_error(SLS_ERR_ALGO, "Unknown algorithm type");
@@ -836,7 +837,7 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         a.pfb = params->prob_flip_best;
         a.nsteps = params->nsteps;
         a.nruns = R;
-        a.seed = params->seed + i;  // instance i uses seed + i: identical to sls_run(inst_i, seed + i)
+        a.seed = instance_seeds ? instance_seeds[i] : params->seed + i;  // identical to sls_run(inst_i, that seed)
         a.chain_offset = params->chain_offset;
         a.gstate = pl.smem ? nullptr : reinterpret_cast<uint32_t*>(p_gstate.base) + pl.off_gstate;
         a.warps_per_block = pl.wpb;

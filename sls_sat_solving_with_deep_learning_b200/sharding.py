@@ -114,3 +114,33 @@ def run_sls_sharded(
         total_flips=int(g_flips.sum()),
         kernel_ms=float(getattr(local, "kernel_ms", 0.0)),
     )
+
+
+def run_batch_sharded(runner: Callable, costs: Sequence[float], nruns: int, *, device: str = "cpu", group=None):
+    """Partition a batch of instances over the ranks (:func:`instance_shard`), solve each rank's share
+    with ``runner(indices) -> list of results`` (e.g. ``lambda idx: eng.run_sls_batch([insts[i] for i in
+    idx], ...)`` -- pass ``seed`` handling inside the runner so that instance i keeps its own seed), and
+    return on every rank the per-chain tables of the whole batch:
+    ``found[n_inst, nruns]``, ``steps[n_inst, nruns]``, ``best_energy[n_inst]``, ``flips[n_inst]``.
+    Every instance is owned by exactly one rank, so one sum-all_reduce of zero-initialised tables is
+    the gather."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n_inst = len(costs)
+    mine = instance_shard(costs, world)[rank]
+    results = runner(mine) if mine else []
+    dev = torch.device(device)
+    found = torch.zeros((n_inst, nruns), dtype=torch.int32, device=dev)
+    steps = torch.zeros((n_inst, nruns), dtype=torch.int64, device=dev)
+    best = torch.zeros(n_inst, dtype=torch.int64, device=dev)
+    flips = torch.zeros(n_inst, dtype=torch.int64, device=dev)
+    for i, r in zip(mine, results):
+        found[i] = torch.as_tensor(np.asarray(r.found, dtype=np.int32), device=dev)
+        steps[i] = torch.as_tensor(np.asarray(r.steps, dtype=np.int64), device=dev)
+        best[i] = int(r.best_energy)
+        flips[i] = int(r.total_flips)
+    for t in (found, steps, best, flips):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return found.cpu().numpy().astype(bool), steps.cpu().numpy().astype(np.uint64), best.cpu().numpy(), flips.cpu().numpy()

@@ -260,9 +260,11 @@ def run_sls_batch(
     prob_flip_best: float = 0.0,
     seed: int = 0,
     chain_offset: int = 0,
+    instance_seeds=None,
 ):
     """Many instances in one launch (sls_run_batch): ``weights_*`` are lists with one vector per instance.
-    Returns a list of :class:`SlsResult`; entry i equals ``run_sls(instances[i], ..., seed=seed + i)``."""
+    Returns a list of :class:`SlsResult`; entry i equals ``run_sls(instances[i], ..., seed=instance_seeds[i])``
+    (``seed + i`` when ``instance_seeds`` is None)."""
     instances = list(instances)
     k = len(instances)
     p = _make_params(algo, nsteps, nruns, False, pre_compute_mapping, prob_flip_best, seed, chain_offset)
@@ -283,7 +285,13 @@ def run_sls_batch(
     bufs = [_Buffers(inst.n, nruns, nsteps, False) for inst in instances]
     results = (_lib.RunResult * max(k, 1))(*[b.res for b in bufs])
     handles = (C.c_void_p * max(k, 1))(*[inst._h.value for inst in instances])
-    _check(_lib.load().sls_run_batch(handles, k, cat_i.ctypes.data, cat_r.ctypes.data, off.ctypes.data, C.byref(p), results))
+    seeds = None
+    if instance_seeds is not None:
+        seeds = np.ascontiguousarray(np.asarray(instance_seeds, dtype=np.uint64))
+        if seeds.shape != (k,):
+            raise ValueError("instance_seeds needs one seed per instance")
+    _check(_lib.load().sls_run_batch(handles, k, cat_i.ctypes.data, cat_r.ctypes.data, off.ctypes.data,
+                                     seeds.ctypes.data if seeds is not None else None, C.byref(p), results))
     out = []
     for i, b in enumerate(bufs):
         b.res = results[i]

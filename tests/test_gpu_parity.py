@@ -291,6 +291,12 @@ def test_batch_many_small_instances_config1_shape():
             assert energy[0] == 0 and r.best_energy == 0
     one = eng.run_sls(insts[17], "probsat", w[17], w[17], 2000, 100, False, True, 0.0, seed=7 + 17)
     assert (res[17].steps == one.steps).all()
+    # explicit per-instance seeds: a shard of the batch reproduces the same results (sharding.run_batch_sharded)
+    shard = [3, 17, 200]
+    part = eng.run_sls_batch([insts[i] for i in shard], "probsat", [w[i] for i in shard], [w[i] for i in shard], 2000, 100,
+                             True, 0.0, instance_seeds=[7 + i for i in shard])
+    for i, r in zip(shard, part):
+        assert (r.steps == res[i].steps).all() and r.best_energy == res[i].best_energy
     with pytest.raises(eng.PanicException):
         eng.run_sls_batch(insts[:2], "walksat", w[:2], w[:2], 10, 1)
 

@@ -77,3 +77,42 @@ def test_two_rank_run_equals_single_rank(tmp_path, algo, nruns):
     assert (got["best_run"] == ref.best_energy_run).all() and (got["flips"] == ref.flips_run).all()
     assert int(got["best"]) == ref.best_energy and int(got["total_flips"]) == ref.total_flips
     assert (got["assignment"] == ref.best_assignment).all()
+
+
+def _batch_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import json
+
+    from oracle import sls_oracle as so
+
+    names = sorted(json.load(open(os.path.join(ROOT, "tests", "golden", "expected.json"))))[:7]
+    insts = [so.Instance.from_dimacs(golden_cnf(nm)) for nm in names]
+
+    def runner(indices):  # instance i keeps seed 40 + i wherever it runs (the sls_run_batch convention)
+        return [insts[i].run_sls("probsat", np.full(insts[i].n, 0.5), np.full(insts[i].n, 0.5), 200, 6, False, True, 0.0,
+                                 seed=40 + i, nthreads=1) for i in indices]
+
+    found, steps, best, flips = sharding.run_batch_sharded(runner, [i.num_lits for i in insts], 6)
+    if rank == 0:
+        np.savez(out, found=found, steps=steps, best=best, flips=flips)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_instance_sharding_equals_single_rank(tmp_path):
+    import json
+
+    from oracle import sls_oracle as so
+
+    out = str(tmp_path / "batch.npz")
+    mp.spawn(_batch_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    names = sorted(json.load(open(os.path.join(ROOT, "tests", "golden", "expected.json"))))[:7]
+    for i, nm in enumerate(names):
+        oi = so.Instance.from_dimacs(golden_cnf(nm))
+        w = np.full(oi.n, 0.5)
+        ref = oi.run_sls("probsat", w, w, 200, 6, False, True, 0.0, seed=40 + i, nthreads=1)
+        assert (got["found"][i] == ref.found).all() and (got["steps"][i] == ref.steps).all()
+        assert got["best"][i] == ref.best_energy and got["flips"][i] == ref.total_flips
