@@ -10,7 +10,9 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sls_b200.h"
@@ -224,7 +226,8 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
 }
 
 // the whole forward on device-resident inputs; decoded_dev[N]
-int forward_device(sls_gnn_model* m, int64_t N, int64_t E, const float* d_nodes, const float* d_edges, const int32_t* d_send,
+int forward_device(sls_gnn_model* m, int64_t N, int64_t E, const float* d_nodes, const float* d_edges, const uint8_t* d_node_type,
+                   const uint8_t* d_edge_type, const int32_t* d_send,
                    const int32_t* d_recv, const int64_t* d_sptr, const int32_t* d_sids, const int64_t* d_rptr, const int32_t* d_rids,
                    float* d_decoded)
 {
@@ -238,8 +241,14 @@ int forward_device(sls_gnn_model* m, int64_t N, int64_t E, const float* d_nodes,
     G_TRY(cudaMalloc(&sent.p, std::max<int64_t>(N, 1) * H * sizeof(float)));
     G_TRY(cudaMalloc(&recv.p, std::max<int64_t>(N, 1) * H * sizeof(float)));
     float *e = e_a.as<float>(), *e2 = e_b.as<float>(), *h = h_a.as<float>(), *h2 = h_b.as<float>();
-    if (E) embed_kernel<<<(unsigned)((E * D + 255) / 256), 256>>>(d_edges, m->edge_embed_w, m->edge_embed_b, e, E, D);
-    if (N) embed_kernel<<<(unsigned)((N * D + 255) / 256), 256>>>(d_nodes, m->node_embed_w, m->node_embed_b, h, N, D);
+    if (E && d_edge_type)
+        embed_onehot_kernel<<<(unsigned)((E * D + 255) / 256), 256>>>(d_edge_type, m->edge_embed_w, m->edge_embed_b, e, E, D);
+    else if (E)
+        embed_kernel<<<(unsigned)((E * D + 255) / 256), 256>>>(d_edges, m->edge_embed_w, m->edge_embed_b, e, E, D);
+    if (N && d_node_type)
+        embed_onehot_kernel<<<(unsigned)((N * D + 255) / 256), 256>>>(d_node_type, m->node_embed_w, m->node_embed_b, h, N, D);
+    else if (N)
+        embed_kernel<<<(unsigned)((N * D + 255) / 256), 256>>>(d_nodes, m->node_embed_w, m->node_embed_b, h, N, D);
     m->launches += 2;
     int de = D, dn = D;
     for (int t = 0; t < m->num_steps; t++) {
@@ -312,7 +321,7 @@ int forward_host_graph(sls_gnn_model* m, int64_t N, int64_t E, const float* node
     G_TRY(cudaEventCreate(&e1));
     m->launches = 0;
     G_TRY(cudaEventRecord(e0));
-    rc = forward_device(m, N, E, d_nodes.as<float>(), d_edges.as<float>(), d_send.as<int32_t>(), d_recv.as<int32_t>(),
+    rc = forward_device(m, N, E, d_nodes.as<float>(), d_edges.as<float>(), nullptr, nullptr, d_send.as<int32_t>(), d_recv.as<int32_t>(),
                         d_sptr.as<int64_t>(), d_sids.as<int32_t>(), d_rptr.as<int64_t>(), d_rids.as<int32_t>(), d_dec.as<float>());
     if (!rc) {
         cudaEventRecord(e1);
@@ -340,68 +349,160 @@ extern "C" int sls_gnn_forward_graph(sls_gnn_model* m, uint64_t n_node, uint64_t
     return forward_host_graph(m, (int64_t)n_node, (int64_t)n_edge, nodes, edges, senders, receivers, decoded, nullptr, kernel_ms);
 }
 
+namespace {
+
+// One instance's slice of the batched LCG graph (LCG.get_graph, sat_representations.py:607-666):
+// 2n literal nodes (2j = negative, 2j+1 = positive literal of variable j) then its non-empty
+// clauses; one edge literal -> clause per literal occurrence in file order, then one edge
+// positive -> negative literal per variable.  Also both segment CSRs, written directly:
+// receivers are clause nodes (their edges are contiguous) or negative literals (the pair edge);
+// senders are literal nodes (their occurrences in increasing edge id, then the pair edge).
+struct LcgPlan {
+    int64_t node_off = 0, edge_off = 0, var_off = 0;
+    int64_t m_ne = 0, L_ne = 0;
+    bool dup_var = false;
+};
+
+void lcg_count(const slsb::HostInstance& h, LcgPlan& pl)
+{
+    pl.m_ne = pl.L_ne = 0;
+    for (uint32_t c = 0; c < h.m; c++) {
+        const uint32_t s = h.row_ptr[c], e = h.row_ptr[c + 1];
+        if (s == e) continue;  // sat_instances.py:50 drops empty clauses
+        pl.m_ne++;
+        pl.L_ne += e - s;
+        for (uint32_t j = s + 1; j < e && !pl.dup_var; j++)
+            for (uint32_t q = s; q < j; q++)
+                if ((h.lits[q] >> 1) == (h.lits[j] >> 1)) pl.dup_var = true;  // sat_representations.py:647-650 asserts
+    }
+}
+
+void lcg_fill(const slsb::HostInstance& h, const LcgPlan& pl, int32_t* send, int32_t* recv, uint8_t* node_type, uint8_t* edge_type,
+              int64_t* sptr, int32_t* sids, int64_t* rptr, int32_t* rids, int64_t* var_node0)
+{
+    const int64_t n = h.n, no = pl.node_off, eo = pl.edge_off;
+    const int64_t E = pl.L_ne + n;
+    // node types: literal nodes one-hot index 1 (np.eye(2)[1] and np.eye(2)[-1] are both [0,1]), clause nodes 0
+    for (int64_t j = 0; j < 2 * n; j++) node_type[no + j] = 1;
+    for (int64_t j = 0; j < pl.m_ne; j++) node_type[no + 2 * n + j] = 0;
+    // edges + receiver CSR + sender degree
+    std::vector<int64_t> deg(2 * n + 1, 0);
+    int64_t ei = 0, cn = 0;
+    for (uint32_t c = 0; c < h.m; c++) {
+        const uint32_t s = h.row_ptr[c], e = h.row_ptr[c + 1];
+        if (s == e) continue;
+        for (uint32_t j = s; j < e; j++, ei++) {
+            const uint32_t lit = h.lits[j];
+            const int64_t node = 2 * (int64_t)(lit >> 1) + ((lit & 1u) ? 0 : 1);
+            send[eo + ei] = (int32_t)(no + node);
+            recv[eo + ei] = (int32_t)(no + 2 * n + cn);
+            edge_type[eo + ei] = 0;
+            deg[node + 1]++;
+        }
+        cn++;
+    }
+    for (int64_t j = 0; j < n; j++) {
+        send[eo + pl.L_ne + j] = (int32_t)(no + 2 * j + 1);
+        recv[eo + pl.L_ne + j] = (int32_t)(no + 2 * j);
+        edge_type[eo + pl.L_ne + j] = 1;
+        deg[2 * j + 1 + 1]++;
+        var_node0[pl.var_off + j] = no + 2 * j;
+    }
+    // receiver ids: the instance's block of rids is [pair edges (for literal nodes) | clause edges (for clause nodes)]
+    //   literal node 2j   -> rids[eo + j]            = pair edge j      (rptr = eo + j .. eo + j + 1)
+    //   literal node 2j+1 -> empty                    (rptr = eo + j + 1)
+    //   clause node cn    -> rids[eo + n + first .. ] = its clause edges
+    for (int64_t j = 0; j < 2 * n; j++) rptr[no + j] = eo + (j + 1) / 2;
+    for (int64_t j = 0; j < n; j++) rids[eo + j] = (int32_t)(eo + pl.L_ne + j);
+    ei = 0, cn = 0;
+    for (uint32_t c = 0; c < h.m; c++) {
+        const uint32_t s = h.row_ptr[c], e = h.row_ptr[c + 1];
+        if (s == e) continue;
+        rptr[no + 2 * n + cn] = eo + n + ei;
+        for (uint32_t j = s; j < e; j++, ei++) rids[eo + n + ei] = (int32_t)(eo + ei);
+        cn++;
+    }
+    // sender ids: counting sort by literal node, stable in edge id; clause nodes send nothing
+    for (int64_t j = 0; j < 2 * n; j++) deg[j + 1] += deg[j];
+    for (int64_t j = 0; j < 2 * n; j++) sptr[no + j] = eo + deg[j];
+    for (int64_t j = 0; j < pl.m_ne; j++) sptr[no + 2 * n + j] = eo + E;
+    std::vector<int64_t> fill(deg.begin(), deg.end() - 1);
+    for (int64_t k = 0; k < E; k++) sids[eo + fill[send[eo + k] - no]++] = (int32_t)(eo + k);
+}
+
+}  // namespace
+
 extern "C" int sls_gnn_forward_lcg(sls_gnn_model* m, sls_instance* const* insts, uint32_t n_inst, float* prob, float* decoded,
                                    double* kernel_ms)
 {
     if (!m || (n_inst && !insts)) return sls_set_error_internal(SLS_ERR_ARG, "NULL argument");
-    // LCG.get_graph for every instance, concatenated (sat_representations.py:607-666): per instance
-    // 2n literal nodes (2j = negative, 2j+1 = positive literal of variable j) then its non-empty
-    // clauses; one edge literal -> clause per literal occurrence in file order, then one edge
-    // positive -> negative literal per variable.
-    std::vector<float> nodes, edges;
-    std::vector<int32_t> send, recv;
-    std::vector<int64_t> var_node0;
-    int64_t node_off = 0;
+    // Graph construction is per instance and independent: plan (count) in parallel, prefix the
+    // offsets, fill every instance's slice of the batched arrays in parallel.
+    std::vector<LcgPlan> plan(n_inst);
+    const unsigned T = std::max(1u, std::min(std::thread::hardware_concurrency(), std::min(32u, n_inst)));
+    auto parallel_for = [&](auto&& fn) {
+        std::atomic<uint32_t> next{0};
+        auto work = [&] {
+            for (uint32_t i; (i = next.fetch_add(1)) < n_inst;) fn(i);
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < T; t++) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+    };
+    parallel_for([&](uint32_t i) { lcg_count(insts[i]->host, plan[i]); });
+    int64_t N = 0, E = 0, V = 0;
     for (uint32_t i = 0; i < n_inst; i++) {
-        const slsb::HostInstance& h = insts[i]->host;
-        const int64_t n = h.n;
-        int64_t m_ne = 0;
-        for (int64_t j = 0; j < 2 * n; j++) {
-            nodes.push_back(0.f);  // np.eye(2)[1] and np.eye(2)[-1] are both [0, 1] (sat_instances.py:69)
-            nodes.push_back(1.f);
-        }
-        for (uint32_t c = 0; c < h.m; c++) {
-            const uint32_t s = h.row_ptr[c], e = h.row_ptr[c + 1];
-            if (s == e) continue;  // sat_instances.py:50 drops empty clauses
-            for (uint32_t j = s; j < e; j++) {
-                const uint32_t v = h.lits[j] >> 1;
-                for (uint32_t q = s; q < j; q++)
-                    if ((h.lits[q] >> 1) == v)
-                        return sls_set_error_internal(SLS_ERR_ARG, "Multiple occurrences of single variable in constraint");
-                const bool positive = !(h.lits[j] & 1u);
-                send.push_back((int32_t)(node_off + 2 * v + (positive ? 1 : 0)));
-                recv.push_back((int32_t)(node_off + 2 * n + m_ne));
-                edges.push_back(1.f);  // np.eye(2)[0]
-                edges.push_back(0.f);
-            }
-            nodes.push_back(1.f);  // clause node: np.eye(2)[0]
-            nodes.push_back(0.f);
-            m_ne++;
-        }
-        for (int64_t j = 0; j < n; j++) {
-            send.push_back((int32_t)(node_off + 2 * j + 1));
-            recv.push_back((int32_t)(node_off + 2 * j));
-            edges.push_back(0.f);  // np.eye(2)[1]
-            edges.push_back(1.f);
-            var_node0.push_back(node_off + 2 * j);
-        }
-        node_off += 2 * n + m_ne;
-        if (node_off > 0x7fffffffll || (int64_t)send.size() > 0x7fffffffll)
-            return sls_set_error_internal(SLS_ERR_ARG, "batch too large for one call");
+        if (plan[i].dup_var) return sls_set_error_internal(SLS_ERR_ARG, "Multiple occurrences of single variable in constraint");
+        plan[i].node_off = N, plan[i].edge_off = E, plan[i].var_off = V;
+        N += 2 * (int64_t)insts[i]->host.n + plan[i].m_ne;
+        E += plan[i].L_ne + insts[i]->host.n;
+        V += insts[i]->host.n;
+        if (N > 0x7fffffffll || E > 0x7fffffffll) return sls_set_error_internal(SLS_ERR_ARG, "batch too large for one call");
     }
-    const int64_t N = node_off, E = (int64_t)send.size();
-    DevBuf d_dec;
-    int rc = forward_host_graph(m, N, E, nodes.data(), edges.data(), send.data(), recv.data(), decoded, &d_dec, kernel_ms);
+    std::vector<int32_t> send(std::max<int64_t>(E, 1)), recv(send.size()), sids(send.size()), rids(send.size());
+    std::vector<uint8_t> node_type(std::max<int64_t>(N, 1)), edge_type(send.size());
+    std::vector<int64_t> sptr(N + 1, 0), rptr(N + 1, 0), var_node0(std::max<int64_t>(V, 1));
+    parallel_for([&](uint32_t i) {
+        lcg_fill(insts[i]->host, plan[i], send.data(), recv.data(), node_type.data(), edge_type.data(), sptr.data(), sids.data(),
+                 rptr.data(), rids.data(), var_node0.data());
+    });
+    sptr[N] = E;
+    rptr[N] = E;
+
+    DevBuf d_nt, d_et, d_send, d_recv, d_sptr, d_sids, d_rptr, d_rids, d_dec;
+    int rc;
+    if ((rc = to_device(node_type, d_nt)) || (rc = to_device(edge_type, d_et)) || (rc = to_device(send, d_send)) ||
+        (rc = to_device(recv, d_recv)) || (rc = to_device(sptr, d_sptr)) || (rc = to_device(sids, d_sids)) ||
+        (rc = to_device(rptr, d_rptr)) || (rc = to_device(rids, d_rids)))
+        return rc;
+    G_TRY(cudaMalloc(&d_dec.p, std::max<int64_t>(N, 1) * sizeof(float)));
+    cudaEvent_t e0, e1;
+    G_TRY(cudaEventCreate(&e0));
+    G_TRY(cudaEventCreate(&e1));
+    m->launches = 0;
+    G_TRY(cudaEventRecord(e0));
+    rc = forward_device(m, N, E, nullptr, nullptr, d_nt.as<uint8_t>(), d_et.as<uint8_t>(), d_send.as<int32_t>(), d_recv.as<int32_t>(),
+                        d_sptr.as<int64_t>(), d_sids.as<int32_t>(), d_rptr.as<int64_t>(), d_rids.as<int32_t>(), d_dec.as<float>());
+    if (!rc) {
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (kernel_ms) *kernel_ms = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
     if (rc) return rc;
-    if (prob && !var_node0.empty()) {
+    if (decoded && N) G_TRY(cudaMemcpy(decoded, d_dec.p, N * sizeof(float), cudaMemcpyDeviceToHost));
+    if (prob && V) {
         DevBuf d_v0, d_p;
         if ((rc = to_device(var_node0, d_v0))) return rc;
-        const int64_t nv = (int64_t)var_node0.size();
-        G_TRY(cudaMalloc(&d_p.p, nv * sizeof(float)));
-        pair_prob_kernel<<<(unsigned)((nv + 255) / 256), 256>>>(d_dec.as<float>(), d_v0.as<int64_t>(), d_p.as<float>(), nv);
+        G_TRY(cudaMalloc(&d_p.p, V * sizeof(float)));
+        pair_prob_kernel<<<(unsigned)((V + 255) / 256), 256>>>(d_dec.as<float>(), d_v0.as<int64_t>(), d_p.as<float>(), V);
         m->launches++;
         G_TRY(cudaGetLastError());
-        G_TRY(cudaMemcpy(prob, d_p.p, nv * sizeof(float), cudaMemcpyDeviceToHost));
+        G_TRY(cudaMemcpy(prob, d_p.p, V * sizeof(float), cudaMemcpyDeviceToHost));
     }
     return SLS_OK;
 }

@@ -385,6 +385,17 @@ __global__ void embed_kernel(const float* __restrict__ x, const float* __restric
     out[i] = x[2 * r] * w[c] + x[2 * r + 1] * w[D + c] + b[c];
 }
 
+// Same embedding when the 2-vector input is one-hot and given as its index (LCG: nodes are
+// literal [0,1] or clause [1,0], edges clause-edge [1,0] or pair-edge [0,1]; sat_instances.py:65-73)
+__global__ void embed_onehot_kernel(const uint8_t* __restrict__ type, const float* __restrict__ w, const float* __restrict__ b,
+                                    float* __restrict__ out, int64_t rows, int D)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * D) return;
+    const int c = (int)(i % D);
+    out[i] = w[(int)type[i / D] * D + c] + b[c];
+}
+
 // jraph.utils.segment_sum over a CSR of edge ids (edge order inside a segment = increasing edge id,
 // i.e. the order a sequential scatter-add visits them): out[v] = sum_{j in [ptr[v], ptr[v+1])} e[ids[j]]
 __global__ void segment_sum_kernel(const float* __restrict__ e, const int64_t* __restrict__ ptr, const int32_t* __restrict__ ids,
