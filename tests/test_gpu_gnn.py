@@ -83,3 +83,23 @@ def test_graph_edge_cases():
         net.probabilities([eng.Instance.from_text("p cnf 1 1 \n 1 -1 0")])
     with pytest.raises(ValueError):
         gnn.InteractionNetworkLCG({"linear": {"w": np.zeros((2, 32)), "b": np.zeros(32)}})
+
+
+def test_reference_call_site_shape():
+    # the four lines of python/src/evaluate_with_given_params.py:97-101,116-121 with this module in place of haiku
+    from functools import partial
+
+    hk = gnn  # stands in for `import haiku as hk`
+    n = 40
+    clauses = random_ksat(n, 160, 3, seed=9)
+    problem_graph = go.lcg_graph(n, clauses)
+    params = go.init_params(seed=5, mlp_layers=(32, 32), num_steps=5, bias_scale=0.1)
+    network_definition = gnn.get_network_definition(network_type="interaction", graph_representation="LCG")
+    network_definition = partial(network_definition, mlp_layers=[32, 32])
+    network = hk.without_apply_rng(hk.transform(network_definition))
+    decoded_nodes = network.apply(params, problem_graph)
+    model_probabilities = gnn.get_model_probabilities(decoded_nodes, n).ravel()
+    ref = go.model_probabilities(go.forward(params, problem_graph, dtype=np.float64), n)
+    assert decoded_nodes.shape == (problem_graph["n_node"], 1) and np.abs(model_probabilities - ref).max() < PROB_TOL
+    with pytest.raises(ValueError):
+        gnn.get_network_definition("GCN", "LCG")
