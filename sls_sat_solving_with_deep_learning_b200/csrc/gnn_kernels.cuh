@@ -398,18 +398,39 @@ __global__ void embed_onehot_kernel(const uint8_t* __restrict__ type, const floa
 
 // jraph.utils.segment_sum over a CSR of edge ids (edge order inside a segment = increasing edge id,
 // i.e. the order a sequential scatter-add visits them): out[v] = sum_{j in [ptr[v], ptr[v+1])} e[ids[j]]
-__global__ void segment_sum_kernel(const float* __restrict__ e, const int64_t* __restrict__ ptr, const int32_t* __restrict__ ids,
-                                   float* __restrict__ out, int64_t n_node, int H)
+// One warp per node, 16-byte loads (lane l owns float4 l and l+32 of the row), edge ids fetched 32 at
+// a time and broadcast by shuffle so the row loads of consecutive edges are independent and in flight
+// together.  The additions of one output element happen in list order (deterministic).
+__global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restrict__ e, const int64_t* __restrict__ ptr,
+                                                          const int32_t* __restrict__ ids, float* __restrict__ out, int64_t n_node, int H)
 {
     const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (v >= n_node) return;
     const int64_t s = ptr[v], t = ptr[v + 1];
-    for (int c = lane; c < H; c += 32) {
-        float acc = 0.f;
-        for (int64_t j = s; j < t; j++) acc += __ldg(e + (size_t)__ldg(ids + j) * H + c);
-        out[(size_t)v * H + c] = acc;
+    const int q = H >> 2;  // float4 per row (H is a multiple of 4, at most 64 float4 = 256 columns)
+    const bool has0 = lane < q, has1 = lane + 32 < q;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    for (int64_t base = s; base < t; base += 32) {
+        const int cnt = (int)min((int64_t)32, t - base);
+        const int32_t my_id = lane < cnt ? __ldg(ids + base + lane) : 0;
+#pragma unroll 4
+        for (int k = 0; k < cnt; k++) {
+            const int32_t id = __shfl_sync(0xffffffffu, my_id, k);
+            const float4* row = reinterpret_cast<const float4*>(e + (size_t)id * H);
+            if (has0) {
+                const float4 x = __ldg(row + lane);
+                a0.x += x.x, a0.y += x.y, a0.z += x.z, a0.w += x.w;
+            }
+            if (has1) {
+                const float4 x = __ldg(row + lane + 32);
+                a1.x += x.x, a1.y += x.y, a1.z += x.z, a1.w += x.w;
+            }
+        }
     }
+    float4* o = reinterpret_cast<float4*>(out + (size_t)v * H);
+    if (has0) o[lane] = a0;
+    if (has1) o[lane + 32] = a1;
 }
 
 // readout Linear(H -> 1): one warp per node (model.py:144)
