@@ -401,13 +401,14 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
 
     // chain state slab: assignment bits | violated bits | level-1 counters
     const size_t slab_bytes = size_t(I.slab_words) * 4;
+    const size_t chain_bytes = slab_bytes + RING_WORDS * 4;  // + the chain's random-word ring (walk_k3.cuh)
     // Tier choice: keep the chain state in shared memory when enough chains fit per SM to cover
     // this call's share of chains (or at least 16 warps); otherwise the state lives in HBM.
     uint32_t wpb = 4;
-    while (wpb > 1 && wpb * slab_bytes > (size_t)max_smem_optin) wpb >>= 1;
-    bool smem_ok = wpb * slab_bytes <= (size_t)max_smem_optin;
+    while (wpb > 1 && wpb * chain_bytes > (size_t)max_smem_optin) wpb >>= 1;
+    bool smem_ok = wpb * chain_bytes <= (size_t)max_smem_optin;
     if (smem_ok) {
-        const size_t per_cta = wpb * slab_bytes + 1024;  // 1 KB reserved per CTA
+        const size_t per_cta = wpb * chain_bytes + 1024;  // 1 KB reserved per CTA
         const uint64_t ctas = std::min<uint64_t>(smem_per_sm / per_cta, 64 / wpb);
         const uint64_t chains_per_sm = ctas * wpb;
         const uint64_t needed = std::min<uint64_t>((R + s->num_sms - 1) / std::max(s->num_sms, 1), 16);
@@ -416,11 +417,11 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     // test hooks: SLS_B200_FORCE_STATE=hbm|smem, SLS_B200_FORCE_GENERIC=1
     if (const char* f = std::getenv("SLS_B200_FORCE_STATE")) {
         if (std::strcmp(f, "hbm") == 0) smem_ok = false;
-        if (std::strcmp(f, "smem") == 0 && wpb * slab_bytes <= (size_t)max_smem_optin) smem_ok = true;
+        if (std::strcmp(f, "smem") == 0 && wpb * chain_bytes <= (size_t)max_smem_optin) smem_ok = true;
     }
     s->smem_state = smem_ok;
     s->wpb = smem_ok ? wpb : 4;
-    s->smem_bytes = smem_ok ? s->wpb * slab_bytes : 0;
+    s->smem_bytes = smem_ok ? s->wpb * chain_bytes : 0;
     // the fast kernel: k<=3 instance, chain state in shared memory, at most 64 level-1 counters
     s->k3 = (I.flags & INST_K3) != 0 && s->smem_state && I.l1_pad == 64;
     if (const char* f = std::getenv("SLS_B200_FORCE_GENERIC"))
@@ -758,7 +759,7 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         if (rc) return rc;
         const DevInst& I = insts[i]->dev;
         ItemPlan& pl = plan[i];
-        const size_t slab_bytes = size_t(I.slab_words) * 4;
+        const size_t slab_bytes = size_t(I.slab_words) * 4 + RING_WORDS * 4;  // slab + random-word ring
         pl.wpb = 4;
         // in a batch the machine is filled by other instances, so shared memory is used whenever
         // at least 8 chains (2 CTAs) of this instance fit per SM

@@ -108,6 +108,63 @@ __device__ __forceinline__ void atoms_add(uint32_t a, uint32_t v)
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
+// The chain's walk stream (same word positions, alignment rules and distributions as WalkStream /
+// WarpStream in philox.cuh) buffered in a 128-word ring in shared memory: on a refill every lane
+// evaluates one Philox block and stores its four words; a draw is then a single broadcast LDS.
+static constexpr uint32_t RING_WORDS = 128;
+struct RingStream {
+    ChainKey ck;
+    uint64_t base;  // word position of ring[0], multiple of 4
+    uint32_t off;   // cursor relative to base
+    uint32_t ring;  // shared-window byte address of the ring
+    int lane;
+    __device__ __forceinline__ RingStream(uint64_t seed, uint64_t chain, uint32_t ring_addr, int lane_)
+        : ck(seed, chain, STREAM_WALK), base(0), off(0), ring(ring_addr), lane(lane_)
+    {
+        fill();
+    }
+    __device__ __forceinline__ void refill()
+    {
+        base += off & ~3u;
+        off &= 3u;
+        fill();
+    }
+    __device__ __forceinline__ void fill()
+    {
+        uint2 k = ck.key;
+        asm volatile("" : "+r"(k.x), "+r"(k.y));  // keep the key schedule inside this cold path
+        const uint64_t b = (base >> 2) + lane;
+        const uint4 x = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)(b >> 32), ck.chain_lo, ck.chain_hi_stream), k);
+        __syncwarp();  // earlier readers of the ring are done
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ring + lane * 16u), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+        __syncwarp();
+    }
+    __device__ __forceinline__ uint32_t next_u32_unchecked() { return lds32(ring + 4u * off++); }
+    __device__ __forceinline__ uint32_t next_u32()
+    {
+        if (off >= RING_WORDS) refill();
+        return next_u32_unchecked();
+    }
+    __device__ __forceinline__ uint64_t next_u64()
+    {
+        off = (off + 1u) & ~1u;
+        if (off >= RING_WORDS) refill();
+        const uint2 v = lds64(ring + 4u * off);
+        off += 2u;
+        return (uint64_t)v.y << 32 | v.x;
+    }
+    __device__ __forceinline__ void skip_u64() { off = ((off + 1u) & ~1u) + 2u; }
+    __device__ __forceinline__ double next_f64() { return (double)(next_u64() >> 11) * 0x1p-53; }
+    __device__ __forceinline__ uint64_t uniform_u64(uint64_t range)
+    {
+        const uint64_t zone = (range << __clzll(range)) - 1ull;
+        for (;;) {
+            const uint64_t v = next_u64();
+            if (v * range <= zone) return __umul64hi(v, range);
+        }
+    }
+};
+
 // `block` = index of this CTA among the CTAs of the item (instance) described by A
 __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block, uint32_t* sm)
 {
@@ -117,9 +174,12 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
     if (run >= A.nruns) return;
     const DevInst& I = A.inst;
     // byte addresses in the shared window
-    const uint32_t sA = (uint32_t)__cvta_generic_to_shared(sm) + warp * I.slab_words * 4u;  // abits
-    const uint32_t sV = sA + I.off_v * 4u;   // vbits (zero-padded to a multiple of 32 words)
-    const uint32_t sL = sA + I.off_l1 * 4u;  // 64 level-1 counters
+    uint32_t sA = (uint32_t)__cvta_generic_to_shared(sm) + warp * I.slab_words * 4u;  // abits
+    uint32_t sV = sA + I.off_v * 4u;   // vbits (zero-padded to a multiple of 32 words)
+    uint32_t sL = sA + I.off_l1 * 4u;  // 64 level-1 counters
+    // opaque to the optimiser: otherwise the shared-window base (S2UR SR_CgaCtaId + ULEA) is rematerialised
+    // at several places inside the step loop instead of living in three registers
+    asm volatile("" : "+r"(sA), "+r"(sV), "+r"(sL));
     const uint64_t chain = A.chain_offset + run;
 
     // literal code l = 2*var + neg is TRUE iff bit(var) != neg
@@ -174,7 +234,8 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
     }
     __syncwarp();
 
-    WarpStream rng(A.seed, chain, lane);
+    // the rings of the CTA's chains sit behind their slabs
+    RingStream rng(A.seed, chain, (uint32_t)__cvta_generic_to_shared(sm) + (A.warps_per_block * I.slab_words + warp * RING_WORDS) * 4u, lane);
     uint32_t best = I.m;
     bool has_best = false;
     uint32_t* best_bits = A.best_bits + run * (size_t)I.nwords;
@@ -201,7 +262,7 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
 
     while (nf > 0 && steps < nsteps) {
         steps++;
-        if (rng.off > 128u - 16u) rng.refill();  // a step consumes at most 13 words outside rejection loops
+        if (rng.off > RING_WORDS - 16u) rng.refill();  // a step consumes at most 13 words outside rejection loops
 
         // ---- lib.rs:229: uniform pick among the violated clauses
         uint32_t r;
