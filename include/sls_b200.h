@@ -140,6 +140,10 @@ int sls_solver_sync(sls_solver *s);
 /* device time of the last launch (ms, CUDA events on the launch stream); call after sync */
 int sls_solver_last_kernel_ms(sls_solver *s, double *ms);
 int sls_solver_fetch(sls_solver *s, sls_run_result *res);
+/* Trajectories of the last launch, packed: row r (steps[r]+1 energies, rust/src/lib.rs:298-300) starts at
+ * offsets[r] in `packed`; offsets has nruns+1 entries.  Call once with packed == NULL to learn the total
+ * (offsets[nruns]), then with a buffer of at least that many words.  Only the valid prefixes cross PCIe. */
+int sls_solver_fetch_trajectories(sls_solver *s, uint32_t *packed, uint64_t capacity_words, uint64_t *offsets);
 /* device-to-device export of the per-chain results for a collective (all device pointers,
  * any may be NULL): found u8[nruns], steps u64[nruns], best_energy u32[nruns], flips u64[nruns] */
 int sls_solver_export_device(sls_solver *s, void *d_found, void *d_steps, void *d_best_energy, void *d_flips,

@@ -691,6 +691,40 @@ extern "C" int sls_solver_fetch(sls_solver* s, sls_run_result* res)
     return SLS_OK;
 }
 
+extern "C" int sls_solver_fetch_trajectories(sls_solver* s, uint32_t* packed, uint64_t capacity_words, uint64_t* offsets)
+{
+    if (!s->p.return_trajectories) return set_error(SLS_ERR_ARG, "the solver was created without return_trajectories");
+    if (!offsets) return set_error(SLS_ERR_ARG, "NULL argument");
+    const size_t R = s->p.nruns;
+    offsets[0] = 0;
+    if (R == 0) return SLS_OK;
+    int rc = sls_solver_sync(s);
+    if (rc) return rc;
+    std::vector<uint64_t> steps(R);
+    CUDA_TRY(cudaMemcpy(steps.data(), s->d_steps, R * 8, cudaMemcpyDeviceToHost));
+    for (size_t r = 0; r < R; r++) offsets[r + 1] = offsets[r] + steps[r] + 1;
+    if (!packed) return SLS_OK;
+    const uint64_t total = offsets[R];
+    if (capacity_words < total) return set_error(SLS_ERR_ARG, "trajectory buffer too small");
+    uint64_t* d_off = nullptr;
+    uint32_t* d_packed = nullptr;
+    CUDA_TRY(cudaMalloc(&d_off, (R + 1) * 8));
+    cudaError_t e = cudaMalloc(&d_packed, std::max<uint64_t>(total, 1) * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d_off, offsets, (R + 1) * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        uint64_t longest = 0;
+        for (size_t r = 0; r < R; r++) longest = std::max(longest, steps[r] + 1);
+        dim3 grid((unsigned)std::min<uint64_t>((longest + 255) / 256, 1024), (unsigned)std::min<uint64_t>(R, 65535));
+        pack_trajectories_kernel<<<grid, 256>>>(s->d_traj, s->p.nsteps + 1, d_off, d_packed, R);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(packed, d_packed, total * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_off);
+    cudaFree(d_packed);
+    if (e != cudaSuccess) return set_error(SLS_ERR_CUDA, std::string("fetch_trajectories: ") + cudaGetErrorString(e));
+    return SLS_OK;
+}
+
 extern "C" int sls_run(sls_instance* inst, const double* w_init, size_t w_init_len, const double* w_resample,
                        size_t w_resample_len, const sls_run_params* params, sls_run_result* res)
 {

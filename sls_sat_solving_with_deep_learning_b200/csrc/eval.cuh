@@ -8,24 +8,8 @@
 
 namespace slsb {
 
-// assignments arrive as one byte per variable (the reference's Vec<bool> / int array):
-// pack 32 of them per word.  One thread per output word.
-__global__ void pack_assignments_kernel(const uint8_t* __restrict__ bytes, uint32_t* __restrict__ bits, uint32_t n,
-                                        uint32_t nwords, uint64_t batch)
-{
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= batch * nwords) return;
-    const uint64_t b = idx / nwords;
-    const uint32_t w = (uint32_t)(idx % nwords);
-    const uint8_t* row = bytes + b * n;
-    uint32_t word = 0;
-    const uint32_t v0 = w * 32u;
-    const uint32_t cnt = min(32u, n - v0);
-    for (uint32_t i = 0; i < cnt; i++) word |= (uint32_t)(row[v0 + i] != 0) << i;
-    bits[idx] = word;
-}
-
-// Bit-sliced evaluation.  A CTA owns one slice of 32 assignments and a range of clauses.
+// Bit-sliced evaluation: assignments arrive as one byte per variable (the reference's Vec<bool> /
+// int array).  A CTA owns one slice of 32 assignments and a range of clauses.
 // tbits is the transposed assignment: tbits[slice][v] holds, in bit b, the value of variable v
 // under assignment 32*slice + b, so one literal fetch serves 32 assignments with a single
 // bitwise op.  Each lane evaluates one clause for all 32 assignments, then the 32x32 result
@@ -92,6 +76,20 @@ __global__ void __launch_bounds__(WARPS * 32) eval_sliced_kernel(const DevInst I
         }
     }
     if (energy && (uint32_t)lane < valid && my_energy) atomicAdd(energy + b0 + lane, my_energy);
+}
+
+// Trajectory rows are written at a fixed pitch (nsteps+1) while a run needs only steps+1 entries
+// (rust/src/lib.rs:298-300 pushes one energy per executed step); pack the valid prefixes back to back
+// so that only they cross PCIe.  offsets[r] = start of row r in the packed buffer (offsets[R] = total).
+__global__ void pack_trajectories_kernel(const uint32_t* __restrict__ traj, uint64_t pitch, const uint64_t* __restrict__ offsets,
+                                         uint32_t* __restrict__ packed, uint64_t nruns)
+{
+    for (uint64_t r = blockIdx.y; r < nruns; r += gridDim.y) {
+        const uint64_t beg = offsets[r], len = offsets[r + 1] - beg;
+        const uint32_t* src = traj + r * pitch;
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x)
+            packed[beg + i] = src[i];
+    }
 }
 
 }  // namespace slsb

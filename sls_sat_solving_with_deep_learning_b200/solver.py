@@ -240,13 +240,22 @@ def run_sls(
     chain_offset: int = 0,
 ) -> SlsResult:
     """run_sls (lib.rs:165-335) on an already parsed instance, with an explicit seed."""
-    p = _make_params(algo, nsteps, nruns, return_trajectories, pre_compute_mapping, prob_flip_best, seed, chain_offset)
+    if return_trajectories:
+        # resident path: only the valid prefix of every trajectory row crosses PCIe
+        s = ResidentSolver(inst, algo, nsteps, nruns, True, pre_compute_mapping, prob_flip_best, seed, chain_offset)
+        try:
+            s.set_weights(weights_initialize, weights_resample)
+            s.launch()
+            return s.fetch()
+        finally:
+            s.close()
+    p = _make_params(algo, nsteps, nruns, False, pre_compute_mapping, prob_flip_best, seed, chain_offset)
     wi, wr = _weights(weights_initialize), _weights(weights_resample)
-    buf = _Buffers(inst.n, nruns, nsteps, bool(return_trajectories))
+    buf = _Buffers(inst.n, nruns, nsteps, False)
     _check(
         _lib.load().sls_run(inst._h, wi.ctypes.data, wi.size, wr.ctypes.data, wr.size, C.byref(p), C.byref(buf.res))
     )
-    return buf.to_result(inst.n, nruns, bool(return_trajectories))
+    return buf.to_result(inst.n, nruns, False)
 
 
 def run_sls_batch(
@@ -344,9 +353,16 @@ class ResidentSolver:
         )
 
     def fetch(self) -> SlsResult:
-        buf = _Buffers(self.inst.n, self.nruns, self.nsteps, self.want_traj)
+        buf = _Buffers(self.inst.n, self.nruns, self.nsteps, False)  # trajectories are fetched packed, below
         _check(_lib.load().sls_solver_fetch(self._h, C.byref(buf.res)))
-        return buf.to_result(self.inst.n, self.nruns, self.want_traj)
+        res = buf.to_result(self.inst.n, self.nruns, False)
+        if self.want_traj:
+            off = np.zeros(self.nruns + 1, dtype=np.uint64)
+            _check(_lib.load().sls_solver_fetch_trajectories(self._h, None, 0, off.ctypes.data))
+            packed = np.zeros(max(int(off[-1]), 1), dtype=np.uint32)
+            _check(_lib.load().sls_solver_fetch_trajectories(self._h, packed.ctypes.data, packed.size, off.ctypes.data))
+            res.trajectories = [packed[int(off[r]): int(off[r + 1])] for r in range(self.nruns)]
+        return res
 
     def close(self):
         if getattr(self, "_h", None):
