@@ -43,7 +43,8 @@ static constexpr int B_STAGE_BYTES = 2 * B_SLAB_BYTES;   // 52 KB
 static constexpr int DONE_BARS = 6;                      // lcm(A_STAGES, B_STAGES): one per slab index mod 6
 static constexpr int TMEM_COLS = 512;
 static constexpr int ACC2_COL = 256;
-static constexpr int MLP_THREADS = 128;
+static constexpr int MLP_PRODUCERS = 128;                // warps 0-3: stage A rows, run the epilogues (thread = row)
+static constexpr int MLP_THREADS = MLP_PRODUCERS + 32;   // warp 4: one lane issues the weight copies and the MMAs
 static constexpr int PAR_BYTES = 3 * MAX_N * 4;          // b2 | ln_scale | ln_offset staged in shared memory
 static constexpr int OUT_PITCH = 204;                   // floats per row of the output tile (816 B: conflict-free 16-byte stores)
 static constexpr int MLP_SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 256 + PAR_BYTES + 1024;  // + barriers + alignment slack
@@ -91,6 +92,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "  mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "  @!p bra WAIT_%=;\n }"
         ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
@@ -164,18 +169,21 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
     const uint32_t sBst = base + A_STAGES * A_STAGE_BYTES;        // B stages
     const uint32_t sFull = sBst + B_STAGES * B_STAGE_BYTES;       // B_STAGES "weights landed" mbarriers
     const uint32_t sDone = sFull + 8 * B_STAGES;                  // DONE_BARS "MMAs of slab j done" mbarriers
-    const uint32_t sTmem = sDone + 8 * DONE_BARS;                 // TMEM base address written by tcgen05.alloc
+    const uint32_t sArdy = sDone + 8 * DONE_BARS;                 // A_STAGES "A stage filled by all producers" mbarriers
+    const uint32_t sTmem = sArdy + 8 * A_STAGES;                  // TMEM base address written by tcgen05.alloc
     const uint32_t sPar = sFull + 128;                            // b2[MAX_N] | ln_scale[MAX_N] | ln_offset[MAX_N] (16-byte aligned)
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));   // generic alias of `base`
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int row0 = blockIdx.x * TILE_M;
-    const int my_row = min(row0 + tid, P.rows - 1);  // rows past the end re-read the last row; their output is not stored
+    const bool producer = tid < MLP_PRODUCERS;
+    const int my_row = min(row0 + (producer ? tid : 0), P.rows - 1);  // rows past the end re-read the last row; their output is not stored
 
     if (tid == 0) {
         for (int i = 0; i < B_STAGES; i++) mbar_init(sFull + 8 * i, 1);
         for (int i = 0; i < DONE_BARS; i++) mbar_init(sDone + 8 * i, 1);
+        for (int i = 0; i < A_STAGES; i++) mbar_init(sArdy + 8 * i, MLP_PRODUCERS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < MAX_N; i += MLP_THREADS) {  // epilogue parameters -> shared memory (read as broadcasts)
@@ -246,70 +254,78 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
         }
     };
 
-    // Pipeline.  `gs` numbers the K-slabs of both GEMMs consecutively; slab j uses A stage j % 2, B
-    // stage j % 3, signals its completion (tcgen05.commit after its 12 MMAs) on sDone[j % 6] and its
-    // weights arrive on sFull[j % 3].  A stage j % 2 is refilled by all threads once slab j - 2 is done;
-    // B stage j % 3 is refilled by thread 0 (two bulk copies, prefetch distance 2) once slab j - 3 is
-    // done.  The gathered A rows of the next slab are loaded into registers before the MMAs of the
-    // current slab are issued, so their latency overlaps the tensor work.
-    uint32_t gs = 0;
+    // Pipeline, warp-specialised.  Slabs of both GEMMs are numbered consecutively (j); slab j uses A
+    // stage j % 2 and B stage j % 3.
+    //   producers (threads 0..127): wait until slab j-2 is done, fill A stage j % 2 (GEMM1: gathered
+    //     rows prefetched into registers one slab ahead; GEMM2: ReLU(acc1 + b1) straight out of TMEM),
+    //     fence, arrive on sArdy[j % 2];
+    //   issuer (thread 128): keeps two weight slabs in flight (two TMA bulk copies per slab into B stage
+    //     j % 3 once slab j-3 is done, completion on sFull[j % 3]), waits for sArdy and sFull of slab j,
+    //     issues its 12 MMAs and a tcgen05.commit on sDone[j % 6].
+    // Nothing in the loop is a CTA-wide barrier, so staging of slab j+1 overlaps the MMAs of slab j.
     auto wait_done = [&](uint32_t j) { mbar_wait(sDone + 8 * (j % DONE_BARS), (j / DONE_BARS) & 1u); };
-    auto run_gemm = [&](int nslabs, int n_pad, uint32_t acc_col, const float* img_hi, const float* img_lo, bool gemm1) {
-        const uint32_t idesc = idesc_tf32(TILE_M, n_pad);
-        const uint32_t bbytes = (uint32_t)n_pad * 128u;
-        const size_t bfloats = (size_t)n_pad * SLAB_K;
-        const uint32_t g0 = gs;
-        auto issue_b = [&](uint32_t j, int s) {  // thread 0 only
-            const uint32_t bs = sBst + (j % B_STAGES) * B_STAGE_BYTES, bar = sFull + 8 * (j % B_STAGES);
-            if (j >= (uint32_t)B_STAGES) wait_done(j - B_STAGES);
-            mbar_expect_tx(bar, 2 * bbytes);
-            bulk_g2s(bs, img_hi + (size_t)s * bfloats, bbytes, bar);
-            bulk_g2s(bs + B_SLAB_BYTES, img_lo + (size_t)s * bfloats, bbytes, bar);
-        };
-        if (tid == 0)
-            for (int p = 0; p < B_STAGES - 1 && p < nslabs; p++) issue_b(g0 + p, p);
+    const uint32_t n1s = (uint32_t)P.k1_slabs, n2s = (uint32_t)P.k2_slabs;
+    if (producer) {
         float4 xa[8];
-        if (gemm1) load_a1(0, xa);
-        for (int s = 0; s < nslabs; s++, gs++) {
-            const uint32_t sa = sAst + (gs % A_STAGES) * A_STAGE_BYTES;
-            if (gs >= (uint32_t)A_STAGES) wait_done(gs - A_STAGES);
-            if (gemm1) {
+        load_a1(0, xa);
+        for (uint32_t j = 0; j < n1s + n2s; j++) {
+            const uint32_t sa = sAst + (j % A_STAGES) * A_STAGE_BYTES;
+            if (j >= (uint32_t)A_STAGES) wait_done(j - A_STAGES);
+            if (j < n1s) {
 #pragma unroll
                 for (int u = 0; u < 8; u++) put_split(sa, u, xa[u]);
-                if (s + 1 < nslabs) load_a1(s + 1, xa);
+                if (j + 1 < n1s) load_a1((int)j + 1, xa);
             } else {
-                stage_a2(sa, s);
+                if (j == n1s) {  // GEMM2 reads GEMM1's accumulator: every GEMM1 MMA must have completed
+                    wait_done(n1s - 1);
+                    tc_fence_after();
+                }
+                stage_a2(sa, (int)(j - n1s));
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
             tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                mbar_wait(sFull + 8 * (gs % B_STAGES), (gs / B_STAGES) & 1u);  // this slab's weights have landed
-                tc_fence_after();
-                const uint32_t aHi = sa, aLo = sa + A_SLAB_BYTES;
-                const uint32_t bHi = sBst + (gs % B_STAGES) * B_STAGE_BYTES, bLo = bHi + B_SLAB_BYTES;
-#pragma unroll
-                for (int kk = 0; kk < 4; kk++) {  // 4 k-steps of 8 tf32 (32 bytes) per 128-byte slab row
-                    const uint32_t o = kk * 32;
-                    umma_tf32(tmem + acc_col, smem_desc_sw128(aHi + o), smem_desc_sw128(bHi + o), idesc, (s | kk) != 0 ? 1u : 0u);
-                    umma_tf32(tmem + acc_col, smem_desc_sw128(aLo + o), smem_desc_sw128(bHi + o), idesc, 1u);
-                    umma_tf32(tmem + acc_col, smem_desc_sw128(aHi + o), smem_desc_sw128(bLo + o), idesc, 1u);
-                }
-                umma_commit(sDone + 8 * (gs % DONE_BARS));
-                if (s + B_STAGES - 1 < nslabs) issue_b(gs + B_STAGES - 1, s + B_STAGES - 1);
-            }
+            mbar_arrive(sArdy + 8 * (j % A_STAGES));
         }
-        wait_done(gs - 1);  // the last slab's commit covers every MMA issued before it
+        wait_done(n1s + n2s - 1);  // the last slab's commit covers every MMA issued before it
         tc_fence_after();
-    };
-
-    // ---------------- GEMM1: acc1[128 x n1] = A[128 x K1] * W1 -----------------
-    run_gemm(P.k1_slabs, P.n1, 0u, P.w1_hi, P.w1_lo, true);
-    // ---------------- GEMM2: acc2[128 x n2] = ReLU(acc1 + b1)[128 x h1] * W2 -----------------
-    run_gemm(P.k2_slabs, P.n2, (uint32_t)ACC2_COL, P.w2_hi, P.w2_lo, false);
+    } else if (tid == MLP_PRODUCERS) {
+        auto issue_b = [&](uint32_t j) {
+            const bool g1 = j < n1s;
+            const int n_pad = g1 ? P.n1 : P.n2;
+            const uint32_t s = g1 ? j : j - n1s, bbytes = (uint32_t)n_pad * 128u;
+            const float* hi = (g1 ? P.w1_hi : P.w2_hi) + (size_t)s * n_pad * SLAB_K;
+            const float* lo = (g1 ? P.w1_lo : P.w2_lo) + (size_t)s * n_pad * SLAB_K;
+            const uint32_t bs = sBst + (j % B_STAGES) * B_STAGE_BYTES, bar = sFull + 8 * (j % B_STAGES);
+            if (j >= (uint32_t)B_STAGES) wait_done(j - B_STAGES);
+            mbar_expect_tx(bar, 2 * bbytes);
+            bulk_g2s(bs, hi, bbytes, bar);
+            bulk_g2s(bs + B_SLAB_BYTES, lo, bbytes, bar);
+        };
+        for (uint32_t j = 0; j < (uint32_t)(B_STAGES - 1) && j < n1s + n2s; j++) issue_b(j);
+        for (uint32_t j = 0; j < n1s + n2s; j++) {
+            const bool g1 = j < n1s;
+            const uint32_t idesc = idesc_tf32(TILE_M, g1 ? P.n1 : P.n2);
+            const uint32_t acc = tmem + (g1 ? 0u : (uint32_t)ACC2_COL);
+            const uint32_t first = g1 ? 0u : n1s;  // first slab of this GEMM overwrites the accumulator
+            mbar_wait(sArdy + 8 * (j % A_STAGES), (j / A_STAGES) & 1u);
+            mbar_wait(sFull + 8 * (j % B_STAGES), (j / B_STAGES) & 1u);
+            tc_fence_after();
+            const uint32_t aHi = sAst + (j % A_STAGES) * A_STAGE_BYTES, aLo = aHi + A_SLAB_BYTES;
+            const uint32_t bHi = sBst + (j % B_STAGES) * B_STAGE_BYTES, bLo = bHi + B_SLAB_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {  // 4 k-steps of 8 tf32 (32 bytes) per 128-byte slab row
+                const uint32_t o = kk * 32;
+                umma_tf32(acc, smem_desc_sw128(aHi + o), smem_desc_sw128(bHi + o), idesc, (j != first || kk != 0) ? 1u : 0u);
+                umma_tf32(acc, smem_desc_sw128(aLo + o), smem_desc_sw128(bHi + o), idesc, 1u);
+                umma_tf32(acc, smem_desc_sw128(aHi + o), smem_desc_sw128(bLo + o), idesc, 1u);
+            }
+            umma_commit(sDone + 8 * (j % DONE_BARS));
+            if (j + B_STAGES - 1 < n1s + n2s) issue_b(j + B_STAGES - 1);
+        }
+    }
 
     // ---------------- epilogue 2: LayerNorm(ReLU(acc2 + b2)) -> shared tile -> coalesced global stores ----
-    {
+    if (producer) {
         const int H = P.h2;
         auto lds4 = [](uint32_t a) {
             float4 v;
@@ -359,11 +375,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
                 }
             }
         }
-        __syncthreads();
+        asm volatile("bar.sync 1, %0;" ::"n"(MLP_PRODUCERS) : "memory");  // producers only
         const int rows_here = min(TILE_M, P.rows - row0);
         const int q_per_row = H / 4;
         float4* out4 = reinterpret_cast<float4*>(P.out + (size_t)row0 * H);
-        for (int i = tid; i < rows_here * q_per_row; i += MLP_THREADS) {
+        for (int i = tid; i < rows_here * q_per_row; i += MLP_PRODUCERS) {
             const int r = i / q_per_row, q = i - r * q_per_row;
             out4[i] = lds4(sOut + (r * OUT_PITCH + 4 * q) * 4);  // consecutive threads -> consecutive 16-byte chunks of the output
         }
