@@ -144,6 +144,11 @@ int sls_solver_fetch(sls_solver *s, sls_run_result *res);
  * offsets[r] in `packed`; offsets has nruns+1 entries.  Call once with packed == NULL to learn the total
  * (offsets[nruns]), then with a buffer of at least that many words.  Only the valid prefixes cross PCIe. */
 int sls_solver_fetch_trajectories(sls_solver *s, uint32_t *packed, uint64_t capacity_words, uint64_t *offsets);
+/* Per-step mean and median energy over the runs of the last launch, computed on the device: every
+ * trajectory zero-padded to nsteps+1 entries, then np.mean / np.median over runs per step -- the reduction
+ * of python/src/evaluate_with_given_params.py:18-23, :141-156 (before its division by the clause count).
+ * mean / median: host arrays of nsteps+1 doubles (either may be NULL).  Needs return_trajectories. */
+int sls_solver_trajectory_stats(sls_solver *s, double *mean, double *median);
 /* device-to-device export of the per-chain results for a collective (all device pointers,
  * any may be NULL): found u8[nruns], steps u64[nruns], best_energy u32[nruns], flips u64[nruns] */
 int sls_solver_export_device(sls_solver *s, void *d_found, void *d_steps, void *d_best_energy, void *d_flips,

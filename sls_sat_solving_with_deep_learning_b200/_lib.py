@@ -115,6 +115,7 @@ SYMBOLS = {
     "sls_solver_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "sls_solver_fetch": (C.c_int, [_vp, C.POINTER(RunResult)]),
     "sls_solver_fetch_trajectories": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
+    "sls_solver_trajectory_stats": (C.c_int, [_vp, _vp, _vp]),
     "sls_solver_export_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sls_solver_launch_count": (C.c_int, [_vp]),
     "sls_solver_variant": (C.c_char_p, [_vp]),

@@ -725,6 +725,32 @@ extern "C" int sls_solver_fetch_trajectories(sls_solver* s, uint32_t* packed, ui
     return SLS_OK;
 }
 
+extern "C" int sls_solver_trajectory_stats(sls_solver* s, double* mean, double* median)
+{
+    if (!s->p.return_trajectories) return set_error(SLS_ERR_ARG, "the solver was created without return_trajectories");
+    const size_t R = s->p.nruns;
+    const uint64_t n1 = s->p.nsteps + 1;
+    if (R == 0) return set_error(SLS_ERR_ARG, "no runs");
+    int rc = sls_solver_sync(s);
+    if (rc) return rc;
+    double *d_mean = nullptr, *d_median = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (mean) e = cudaMalloc(&d_mean, n1 * 8);
+    if (e == cudaSuccess && median) e = cudaMalloc(&d_median, n1 * 8);
+    if (e == cudaSuccess) {
+        const uint64_t warps = n1;
+        trajectory_stats_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256>>>(s->d_traj, n1, s->d_steps, (uint32_t)R, n1,
+                                                                               s->inst->host.m, d_mean, d_median);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && mean) e = cudaMemcpy(mean, d_mean, n1 * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && median) e = cudaMemcpy(median, d_median, n1 * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_mean);
+    cudaFree(d_median);
+    if (e != cudaSuccess) return set_error(SLS_ERR_CUDA, std::string("trajectory_stats: ") + cudaGetErrorString(e));
+    return SLS_OK;
+}
+
 extern "C" int sls_run(sls_instance* inst, const double* w_init, size_t w_init_len, const double* w_resample,
                        size_t w_resample_len, const sls_run_params* params, sls_run_result* res)
 {

@@ -92,4 +92,46 @@ __global__ void pack_trajectories_kernel(const uint32_t* __restrict__ traj, uint
     }
 }
 
+// Per-step statistics over the runs of one call, on the device: what the reference's evaluation does
+// in NumPy on [n_runs, n_steps] arrays (python/src/evaluate_with_given_params.py:18-23, :141-156):
+// every trajectory is zero-padded after its last entry (np.pad), then mean and median over runs per step.
+// One warp per step; consecutive steps sit in consecutive warps so the strided reads share sectors.
+// The median of R non-negative integers is found by bisection on the value with ballot counts.
+__global__ void __launch_bounds__(256) trajectory_stats_kernel(const uint32_t* __restrict__ traj, uint64_t pitch,
+                                                               const uint64_t* __restrict__ steps, uint32_t nruns, uint64_t nsteps1,
+                                                               uint32_t vmax, double* __restrict__ mean, double* __restrict__ median)
+{
+    const uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (t >= nsteps1) return;
+    auto value = [&](uint32_t r) -> uint32_t { return (r < nruns && t <= __ldg(steps + r)) ? __ldg(traj + (uint64_t)r * pitch + t) : 0u; };
+    // mean
+    uint64_t sum = 0;
+    for (uint32_t r = lane; r < nruns; r += 32) sum += value(r);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    // k-th smallest (0-based) by bisection: smallest x with count(v <= x) > k
+    auto kth = [&](uint32_t k) -> uint32_t {
+        uint32_t lo = 0, hi = vmax;
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            uint32_t cnt = 0;
+            for (uint32_t rb = 0; rb < nruns; rb += 32) {
+                const uint32_t r = rb + lane;
+                cnt += __popc(__ballot_sync(0xffffffffu, r < nruns && value(r) <= mid));
+            }
+            if (cnt > k)
+                hi = mid;
+            else
+                lo = mid + 1;
+        }
+        return lo;
+    };
+    if (median) {
+        const uint32_t a = kth((nruns - 1) / 2), b = (nruns & 1u) ? a : kth(nruns / 2);  // np.median averages the two middle values
+        if (lane == 0) median[t] = 0.5 * ((double)a + (double)b);
+    }
+    if (lane == 0 && mean) mean[t] = (double)sum / (double)nruns;
+}
+
 }  // namespace slsb

@@ -364,6 +364,15 @@ class ResidentSolver:
             res.trajectories = [packed[int(off[r]): int(off[r + 1])] for r in range(self.nruns)]
         return res
 
+    def trajectory_stats(self):
+        """(mean[nsteps+1], median[nsteps+1]) of the energy over runs per step, trajectories zero-padded after
+        their last entry: the NumPy reduction of evaluate_with_given_params.py:18-23, :141-156 done on the GPU
+        (divide by the clause count to get the reference's normalised curves)."""
+        mean = np.zeros(self.nsteps + 1, dtype=np.float64)
+        median = np.zeros(self.nsteps + 1, dtype=np.float64)
+        _check(_lib.load().sls_solver_trajectory_stats(self._h, mean.ctypes.data, median.ctypes.data))
+        return mean, median
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.load().sls_solver_free(self._h)

@@ -333,3 +333,20 @@ def test_walk_hbm_tier_flip_log_best_assignment(monkeypatch):
     g = eng.run_sls(gi, "probsat", w, w, 5000, 3, False, True, 0.0, seed=4)  # too long for the log: direct copies
     o = oi.run_sls("probsat", w, w, 5000, 3, False, True, 0.0, seed=4)
     assert_same_run(g, o)
+
+
+def test_trajectory_statistics_match_numpy_protocol():
+    # python/src/evaluate_with_given_params.py:18-23, :141-156: pad with zeros, mean / median over runs
+    gi, _ = both("r3sat_test_random_KCNF3_200_640_1042686")
+    w = np.full(gi.n, 0.5)
+    for nruns in (100, 37, 64):
+        s = eng.ResidentSolver(gi, "probsat", 1500, nruns, True, True, 0.0, seed=6)
+        s.set_weights(w, w)
+        s.launch()
+        res = s.fetch()
+        mean, median = s.trajectory_stats()
+        padded = np.array([np.pad(t, (0, 1501 - len(t))) for t in res.trajectories])
+        assert res.found.any() and not res.found.all()  # some rows are padded, some are full length
+        assert np.allclose(mean, padded.mean(axis=0), rtol=0, atol=1e-12)
+        assert (median == np.median(padded, axis=0)).all()
+        s.close()
