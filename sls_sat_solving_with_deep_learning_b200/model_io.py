@@ -131,8 +131,8 @@ def load_model(path: str):
 
 def load_oracle(path: str, num_message_passing_steps: int = 5):
     """Model file -> ready network (the first half of evaluate_with_given_params.py:66-101)."""
-    from .gnn import get_network_definition
+    from .gnn import InteractionNetworkLCG, get_network_definition
 
     params, md = load_model(path)
-    net = get_network_definition(md.network_type, md.graph_representation)(params, num_message_passing_steps)
-    return net, md
+    get_network_definition(md.network_type, md.graph_representation)  # raises for anything but interaction + LCG
+    return InteractionNetworkLCG(params, num_message_passing_steps), md

@@ -352,11 +352,15 @@ class ResidentSolver:
             )
         )
 
-    def fetch(self) -> SlsResult:
+    def fetch_summary(self) -> SlsResult:
+        """Everything but the trajectories (which stay on the device)."""
+        return self.fetch(with_trajectories=False)
+
+    def fetch(self, with_trajectories: bool = True) -> SlsResult:
         buf = _Buffers(self.inst.n, self.nruns, self.nsteps, False)  # trajectories are fetched packed, below
         _check(_lib.load().sls_solver_fetch(self._h, C.byref(buf.res)))
         res = buf.to_result(self.inst.n, self.nruns, False)
-        if self.want_traj:
+        if self.want_traj and with_trajectories:
             off = np.zeros(self.nruns + 1, dtype=np.uint64)
             _check(_lib.load().sls_solver_fetch_trajectories(self._h, None, 0, off.ctypes.data))
             packed = np.zeros(max(int(off[-1]), 1), dtype=np.uint32)
