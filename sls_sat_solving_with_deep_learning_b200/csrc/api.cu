@@ -13,6 +13,7 @@
 
 #include "../../include/sls_b200.h"
 #include "common.h"
+#include "devmem.h"
 #include "eval.cuh"
 #include "init_sliced.cuh"
 #include "instance.h"
@@ -74,7 +75,7 @@ int ensure_on_device(sls_instance* inst)
     CUDA_TRY(cudaGetDevice(&dev));
     if (inst->d_blob && inst->device == dev) return SLS_OK;
     if (inst->d_blob) {
-        cudaFree(inst->d_blob);
+        dfree(inst->d_blob);
         inst->d_blob = nullptr;
     }
     const HostInstance& h = inst->host;
@@ -121,12 +122,12 @@ int ensure_on_device(sls_instance* inst)
         total += align_up(std::max<size_t>(s.bytes, 16), 256);
     }
     char* blob = nullptr;
-    CUDA_TRY(cudaMalloc(&blob, total));
+    CUDA_TRY(dmalloc(&blob, total));
     for (auto& s : segs)
         if (s.bytes) {
             cudaError_t e = cudaMemcpy(blob + s.off, s.src, s.bytes, cudaMemcpyHostToDevice);
             if (e != cudaSuccess) {
-                cudaFree(blob);
+                dfree(blob);
                 return set_error(SLS_ERR_CUDA, std::string("cudaMemcpy(instance): ") + cudaGetErrorString(e));
             }
         }
@@ -226,7 +227,7 @@ extern "C" int sls_instance_from_csr(uint32_t n, uint32_t m, const uint64_t* row
 extern "C" void sls_instance_free(sls_instance* inst)
 {
     if (!inst) return;
-    if (inst->d_blob) cudaFree(inst->d_blob);
+    if (inst->d_blob) dfree(inst->d_blob);
     delete inst;
 }
 
@@ -266,10 +267,10 @@ extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignmen
     uint8_t* d_bytes = nullptr;
     uint32_t *d_tbits = nullptr, *d_v = nullptr, *d_e = nullptr;
     auto cleanup = [&] {
-        cudaFree(d_bytes);
-        cudaFree(d_tbits);
-        cudaFree(d_v);
-        cudaFree(d_e);
+        dfree(d_bytes);
+        dfree(d_tbits);
+        dfree(d_v);
+        dfree(d_e);
     };
     const size_t n1 = std::max<uint32_t>(I.n, 1);
 #define EV_TRY(expr)                                                                                     \
@@ -280,10 +281,10 @@ extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignmen
             return set_error(SLS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
         }                                                                                                \
     } while (0)
-    EV_TRY(cudaMalloc(&d_bytes, batch * n1));
-    EV_TRY(cudaMalloc(&d_tbits, nslices * n1 * 4));
-    EV_TRY(cudaMalloc(&d_e, batch * 4));
-    if (violated_bits) EV_TRY(cudaMalloc(&d_v, batch * (size_t)I.mwords * 4));
+    EV_TRY(dmalloc(&d_bytes, batch * n1));
+    EV_TRY(dmalloc(&d_tbits, nslices * n1 * 4));
+    EV_TRY(dmalloc(&d_e, batch * 4));
+    if (violated_bits) EV_TRY(dmalloc(&d_v, batch * (size_t)I.mwords * 4));
     if (I.n) EV_TRY(cudaMemcpy(d_bytes, assignments, batch * (size_t)I.n, cudaMemcpyHostToDevice));
     EV_TRY(cudaMemset(d_e, 0, batch * 4));
     if (I.n) {
@@ -348,21 +349,21 @@ struct sls_solver {
 extern "C" void sls_solver_free(sls_solver* s)
 {
     if (!s) return;
-    cudaFree(s->d_thr);
-    cudaFree(s->d_w);
-    cudaFree(s->d_crecx);
-    cudaFree(s->d_gstate);
-    cudaFree(s->d_best_bits);
-    cudaFree(s->d_flip_log);
-    cudaFree(s->d_nf_init);
-    cudaFree(s->d_tbits);
-    cudaFree(s->d_found);
-    cudaFree(s->d_has_best);
-    cudaFree(s->d_steps);
-    cudaFree(s->d_best_energy);
-    cudaFree(s->d_flips);
-    cudaFree(s->d_traj);
-    cudaFree(s->d_err);
+    dfree(s->d_thr);
+    dfree(s->d_w);
+    dfree(s->d_crecx);
+    dfree(s->d_gstate);
+    dfree(s->d_best_bits);
+    dfree(s->d_flip_log);
+    dfree(s->d_nf_init);
+    dfree(s->d_tbits);
+    dfree(s->d_found);
+    dfree(s->d_has_best);
+    dfree(s->d_steps);
+    dfree(s->d_best_energy);
+    dfree(s->d_flips);
+    dfree(s->d_traj);
+    dfree(s->d_err);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     delete s;
@@ -428,18 +429,18 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
         if (f[0] == '1') s->k3 = false;
     s->variant = s->k3 ? "walk_k3s<smem>" : std::string("walk_generic<") + (s->smem_state ? "smem" : "hbm") + ">";
 
-    SC_TRY(cudaMalloc(&s->d_thr, std::max<size_t>(I.n, 1) * 8));
-    SC_TRY(cudaMalloc(&s->d_w, std::max<size_t>(I.n, 1) * 8));
-    if (s->k3) SC_TRY(cudaMalloc(&s->d_crecx, std::max<size_t>(I.m, 1) * CRECX_QUADS * sizeof(uint4)));
-    if (!s->smem_state) SC_TRY(cudaMalloc(&s->d_gstate, R1 * slab_bytes));
-    SC_TRY(cudaMalloc(&s->d_best_bits, R1 * std::max<size_t>(I.nwords, 1) * 4));
+    SC_TRY(dmalloc(&s->d_thr, std::max<size_t>(I.n, 1) * 8));
+    SC_TRY(dmalloc(&s->d_w, std::max<size_t>(I.n, 1) * 8));
+    if (s->k3) SC_TRY(dmalloc(&s->d_crecx, std::max<size_t>(I.m, 1) * CRECX_QUADS * sizeof(uint4)));
+    if (!s->smem_state) SC_TRY(dmalloc(&s->d_gstate, R1 * slab_bytes));
+    SC_TRY(dmalloc(&s->d_best_bits, R1 * std::max<size_t>(I.nwords, 1) * 4));
     if (!s->smem_state && !(I.flags & INST_HAS_DUPLICATES) && I.n > 0 && I.m > 0) {
         // chains are initialised 32 at a time by the sliced kernels (init_sliced.cuh); the transposed
         // assignments of one chunk of slices are kept in a scratch buffer of at most ~1 GB
         const uint64_t nslices = (R + 31) / 32;
         s->tbits_slices = (uint32_t)std::min<uint64_t>(nslices, std::max<uint64_t>(1, (1ull << 28) / I.n));
-        SC_TRY(cudaMalloc(&s->d_tbits, size_t(s->tbits_slices) * I.n * 4));
-        SC_TRY(cudaMalloc(&s->d_nf_init, R1 * 4));
+        SC_TRY(dmalloc(&s->d_tbits, size_t(s->tbits_slices) * I.n * 4));
+        SC_TRY(dmalloc(&s->d_nf_init, R1 * 4));
     }
     if (!s->smem_state) {
         // flip log instead of cloning the assignment on every improvement (lib.rs:294) when the log
@@ -447,16 +448,16 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
         const uint64_t per_step = params->algo == SLS_ALGO_MOSER ? std::max<uint32_t>(I.max_k, 1) : 1;
         if (params->nsteps < (1ull << 40) && params->nsteps * per_step + 1 <= 4ull * I.nwords) {
             s->log_cap = params->nsteps * per_step + 1;
-            SC_TRY(cudaMalloc(&s->d_flip_log, R1 * s->log_cap * 4));
+            SC_TRY(dmalloc(&s->d_flip_log, R1 * s->log_cap * 4));
         }
     }
-    SC_TRY(cudaMalloc(&s->d_found, R1));
-    SC_TRY(cudaMalloc(&s->d_has_best, R1));
-    SC_TRY(cudaMalloc(&s->d_steps, R1 * 8));
-    SC_TRY(cudaMalloc(&s->d_best_energy, R1 * 4));
-    SC_TRY(cudaMalloc(&s->d_flips, R1 * 8));
-    SC_TRY(cudaMalloc(&s->d_err, 4));
-    if (params->return_trajectories) SC_TRY(cudaMalloc(&s->d_traj, R1 * (params->nsteps + 1) * 4));
+    SC_TRY(dmalloc(&s->d_found, R1));
+    SC_TRY(dmalloc(&s->d_has_best, R1));
+    SC_TRY(dmalloc(&s->d_steps, R1 * 8));
+    SC_TRY(dmalloc(&s->d_best_energy, R1 * 4));
+    SC_TRY(dmalloc(&s->d_flips, R1 * 8));
+    SC_TRY(dmalloc(&s->d_err, 4));
+    if (params->return_trajectories) SC_TRY(dmalloc(&s->d_traj, R1 * (params->nsteps + 1) * 4));
     SC_TRY(cudaEventCreate(&s->ev0));
     SC_TRY(cudaEventCreate(&s->ev1));
     if (s->smem_bytes) {
@@ -708,8 +709,8 @@ extern "C" int sls_solver_fetch_trajectories(sls_solver* s, uint32_t* packed, ui
     if (capacity_words < total) return set_error(SLS_ERR_ARG, "trajectory buffer too small");
     uint64_t* d_off = nullptr;
     uint32_t* d_packed = nullptr;
-    CUDA_TRY(cudaMalloc(&d_off, (R + 1) * 8));
-    cudaError_t e = cudaMalloc(&d_packed, std::max<uint64_t>(total, 1) * 4);
+    CUDA_TRY(dmalloc(&d_off, (R + 1) * 8));
+    cudaError_t e = dmalloc(&d_packed, std::max<uint64_t>(total, 1) * 4);
     if (e == cudaSuccess) e = cudaMemcpy(d_off, offsets, (R + 1) * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         uint64_t longest = 0;
@@ -719,8 +720,8 @@ extern "C" int sls_solver_fetch_trajectories(sls_solver* s, uint32_t* packed, ui
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(packed, d_packed, total * 4, cudaMemcpyDeviceToHost);
-    cudaFree(d_off);
-    cudaFree(d_packed);
+    dfree(d_off);
+    dfree(d_packed);
     if (e != cudaSuccess) return set_error(SLS_ERR_CUDA, std::string("fetch_trajectories: ") + cudaGetErrorString(e));
     return SLS_OK;
 }
@@ -735,8 +736,8 @@ extern "C" int sls_solver_trajectory_stats(sls_solver* s, double* mean, double* 
     if (rc) return rc;
     double *d_mean = nullptr, *d_median = nullptr;
     cudaError_t e = cudaSuccess;
-    if (mean) e = cudaMalloc(&d_mean, n1 * 8);
-    if (e == cudaSuccess && median) e = cudaMalloc(&d_median, n1 * 8);
+    if (mean) e = dmalloc(&d_mean, n1 * 8);
+    if (e == cudaSuccess && median) e = dmalloc(&d_median, n1 * 8);
     if (e == cudaSuccess) {
         const uint64_t warps = n1;
         trajectory_stats_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256>>>(s->d_traj, n1, s->d_steps, (uint32_t)R, n1,
@@ -745,8 +746,8 @@ extern "C" int sls_solver_trajectory_stats(sls_solver* s, double* mean, double* 
     }
     if (e == cudaSuccess && mean) e = cudaMemcpy(mean, d_mean, n1 * 8, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && median) e = cudaMemcpy(median, d_median, n1 * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d_mean);
-    cudaFree(d_median);
+    dfree(d_mean);
+    dfree(d_median);
     if (e != cudaSuccess) return set_error(SLS_ERR_CUDA, std::string("trajectory_stats: ") + cudaGetErrorString(e));
     return SLS_OK;
 }
@@ -773,7 +774,7 @@ namespace {
 struct Pool {
     char* base = nullptr;
     size_t size = 0;
-    ~Pool() { cudaFree(base); }
+    ~Pool() { dfree(base); }
 };
 
 struct ItemPlan {
@@ -862,7 +863,7 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     Pool p_thr, p_w, p_crecx, p_bits, p_found, p_hasbest, p_steps, p_flips, p_best, p_gstate, p_err, p_items, p_cta;
     auto alloc = [&](Pool& p, size_t bytes) -> cudaError_t {
         p.size = std::max<size_t>(bytes, 16);
-        return cudaMalloc(&p.base, p.size);
+        return dmalloc(&p.base, p.size);
     };
     CUDA_TRY(alloc(p_thr, tot_n * 8));
     CUDA_TRY(alloc(p_w, tot_n * 8));

@@ -1,0 +1,92 @@
+// devmem.h -- device allocations of the library go through the driver's stream-ordered pool.
+//
+// The reference-facing call (run_sls_python, rust/src/lib.rs:103-149) allocates and frees its working set on
+// every call; with cudaMalloc / cudaFree that is a page-table update per buffer and showed up as 10-350 ms of
+// jitter around a 180 ms kernel.  The pool keeps freed blocks mapped (up to the release threshold) so a repeated
+// call of the same shape allocates without talking to the OS.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <mutex>
+
+namespace slsb {
+
+constexpr int kMaxDevices = 64;
+constexpr uint64_t kPoolKeepBytes = 4ull << 30;  // freed memory above this goes back to the driver at the next sync
+
+struct DevMemState {
+    std::mutex mu;
+    cudaStream_t stream[kMaxDevices] = {};
+    bool ready[kMaxDevices] = {};
+};
+
+inline DevMemState& devmem_state()
+{
+    static DevMemState st;
+    return st;
+}
+
+// Stream the pool operations of `device` are ordered on (created on first use; the device must be current).
+inline cudaError_t devmem_stream(int device, cudaStream_t* out)
+{
+    DevMemState& st = devmem_state();
+    if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(st.mu);
+    if (!st.ready[device]) {
+        cudaMemPool_t pool;
+        cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
+        if (e != cudaSuccess) return e;
+        uint64_t keep = kPoolKeepBytes;
+        e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamCreateWithFlags(&st.stream[device], cudaStreamNonBlocking);
+        if (e != cudaSuccess) return e;
+        st.ready[device] = true;
+    }
+    *out = st.stream[device];
+    return cudaSuccess;
+}
+
+// Allocation on the current device, usable from any stream on return.
+template <class T>
+inline cudaError_t dmalloc(T** p, size_t bytes)
+{
+    *p = nullptr;
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return e;
+    cudaStream_t st;
+    e = devmem_stream(device, &st);
+    if (e != cudaSuccess) return e;
+    void* q = nullptr;
+    e = cudaMallocAsync(&q, bytes ? bytes : 1, st);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    *p = static_cast<T*>(q);
+    return cudaSuccess;
+}
+
+// Same contract as cudaFree: waits for the device to be idle, so no kernel can still be using the block when
+// a later dmalloc hands it out again.  NULL is ignored.
+inline void dfree(void* p)
+{
+    if (!p) return;
+    cudaPointerAttributes attr;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    if (attr.device != prev) cudaSetDevice(attr.device);
+    cudaStream_t st;
+    if (devmem_stream(attr.device, &st) == cudaSuccess) {
+        cudaDeviceSynchronize();
+        cudaFreeAsync(p, st);
+    }
+    if (attr.device != prev) cudaSetDevice(prev);
+}
+
+}  // namespace slsb

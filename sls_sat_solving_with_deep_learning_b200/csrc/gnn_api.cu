@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/sls_b200.h"
+#include "devmem.h"
 #include "gnn_kernels.cuh"
 #include "instance.h"
 
@@ -24,6 +25,8 @@ int sls_set_error_internal(int code, const std::string& msg);  // api.cu
 namespace {
 
 using namespace gnn;
+using slsb::dfree;
+using slsb::dmalloc;
 
 int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
@@ -51,7 +54,7 @@ struct DevMlp {
 
 int upload(const std::vector<float>& h, float** d)
 {
-    G_TRY(cudaMalloc(d, std::max<size_t>(h.size(), 1) * sizeof(float)));
+    G_TRY(dmalloc(d, std::max<size_t>(h.size(), 1) * sizeof(float)));
     if (!h.empty()) G_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
     return SLS_OK;
 }
@@ -71,7 +74,7 @@ struct sls_gnn_model {
 extern "C" void sls_gnn_model_free(sls_gnn_model* m)
 {
     if (!m) return;
-    for (void* p : m->allocs) cudaFree(p);
+    for (void* p : m->allocs) dfree(p);
     delete m;
 }
 
@@ -200,7 +203,7 @@ namespace {
 
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { cudaFree(p); }
+    ~DevBuf() { dfree(p); }
     template <class T>
     T* as() { return static_cast<T*>(p); }
 };
@@ -234,12 +237,12 @@ int forward_device(sls_gnn_model* m, int64_t N, int64_t E, const float* d_nodes,
     const int D = m->embed, H = m->h2;
     DevBuf e_a, e_b, h_a, h_b, sent, recv;
     const size_t ew = std::max(D, H), hw = std::max(D, H);
-    G_TRY(cudaMalloc(&e_a.p, std::max<int64_t>(E, 1) * ew * sizeof(float)));
-    G_TRY(cudaMalloc(&e_b.p, std::max<int64_t>(E, 1) * ew * sizeof(float)));
-    G_TRY(cudaMalloc(&h_a.p, std::max<int64_t>(N, 1) * hw * sizeof(float)));
-    G_TRY(cudaMalloc(&h_b.p, std::max<int64_t>(N, 1) * hw * sizeof(float)));
-    G_TRY(cudaMalloc(&sent.p, std::max<int64_t>(N, 1) * H * sizeof(float)));
-    G_TRY(cudaMalloc(&recv.p, std::max<int64_t>(N, 1) * H * sizeof(float)));
+    G_TRY(dmalloc(&e_a.p, std::max<int64_t>(E, 1) * ew * sizeof(float)));
+    G_TRY(dmalloc(&e_b.p, std::max<int64_t>(E, 1) * ew * sizeof(float)));
+    G_TRY(dmalloc(&h_a.p, std::max<int64_t>(N, 1) * hw * sizeof(float)));
+    G_TRY(dmalloc(&h_b.p, std::max<int64_t>(N, 1) * hw * sizeof(float)));
+    G_TRY(dmalloc(&sent.p, std::max<int64_t>(N, 1) * H * sizeof(float)));
+    G_TRY(dmalloc(&recv.p, std::max<int64_t>(N, 1) * H * sizeof(float)));
     float *e = e_a.as<float>(), *e2 = e_b.as<float>(), *h = h_a.as<float>(), *h2 = h_b.as<float>();
     if (E && d_edge_type)
         embed_onehot_kernel<<<(unsigned)((E * D + 255) / 256), 256>>>(d_edge_type, m->edge_embed_w, m->edge_embed_b, e, E, D);
@@ -292,7 +295,7 @@ void build_csr(int64_t N, int64_t E, const int32_t* key, std::vector<int64_t>& p
 template <class T>
 int to_device(const std::vector<T>& h, DevBuf& d)
 {
-    G_TRY(cudaMalloc(&d.p, std::max<size_t>(h.size(), 1) * sizeof(T)));
+    G_TRY(dmalloc(&d.p, std::max<size_t>(h.size(), 1) * sizeof(T)));
     if (!h.empty()) G_TRY(cudaMemcpy(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
     return SLS_OK;
 }
@@ -315,7 +318,7 @@ int forward_host_graph(sls_gnn_model* m, int64_t N, int64_t E, const float* node
         (rc = to_device(sptr, d_sptr)) || (rc = to_device(sids, d_sids)) || (rc = to_device(rptr, d_rptr)) ||
         (rc = to_device(rids, d_rids)))
         return rc;
-    G_TRY(cudaMalloc(&d_dec.p, std::max<int64_t>(N, 1) * sizeof(float)));
+    G_TRY(dmalloc(&d_dec.p, std::max<int64_t>(N, 1) * sizeof(float)));
     cudaEvent_t e0, e1;
     G_TRY(cudaEventCreate(&e0));
     G_TRY(cudaEventCreate(&e1));
@@ -476,7 +479,7 @@ extern "C" int sls_gnn_forward_lcg(sls_gnn_model* m, sls_instance* const* insts,
         (rc = to_device(recv, d_recv)) || (rc = to_device(sptr, d_sptr)) || (rc = to_device(sids, d_sids)) ||
         (rc = to_device(rptr, d_rptr)) || (rc = to_device(rids, d_rids)))
         return rc;
-    G_TRY(cudaMalloc(&d_dec.p, std::max<int64_t>(N, 1) * sizeof(float)));
+    G_TRY(dmalloc(&d_dec.p, std::max<int64_t>(N, 1) * sizeof(float)));
     cudaEvent_t e0, e1;
     G_TRY(cudaEventCreate(&e0));
     G_TRY(cudaEventCreate(&e1));
@@ -498,7 +501,7 @@ extern "C" int sls_gnn_forward_lcg(sls_gnn_model* m, sls_instance* const* insts,
     if (prob && V) {
         DevBuf d_v0, d_p;
         if ((rc = to_device(var_node0, d_v0))) return rc;
-        G_TRY(cudaMalloc(&d_p.p, V * sizeof(float)));
+        G_TRY(dmalloc(&d_p.p, V * sizeof(float)));
         pair_prob_kernel<<<(unsigned)((V + 255) / 256), 256>>>(d_dec.as<float>(), d_v0.as<int64_t>(), d_p.as<float>(), V);
         m->launches++;
         G_TRY(cudaGetLastError());
