@@ -184,10 +184,25 @@ extern "C" int sls_instance_from_dimacs(const char* path, sls_instance** out)
 {
     if (!out) return set_error(SLS_ERR_ARG, "out is NULL");
     *out = nullptr;
-    std::ifstream f(path, std::ios::binary);
+    if (!path) return set_error(SLS_ERR_ARG, "path is NULL");
+    FILE* f = std::fopen(path, "rb");
     if (!f) return set_error(SLS_ERR_IO, std::string("failed to read ") + path);
-    std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-    if (f.bad()) return set_error(SLS_ERR_IO, std::string("failed to read ") + path);
+    std::string text;
+    bool ok = true;
+    if (std::fseek(f, 0, SEEK_END) == 0) {  // regular file: one read of the whole text
+        const long size = std::ftell(f);
+        std::rewind(f);
+        if (size > 0) {
+            text.resize(size_t(size));
+            text.resize(std::fread(&text[0], 1, size_t(size), f));
+        }
+    }
+    char chunk[1 << 16];  // whatever is left (pipes, files growing under us)
+    size_t got;
+    while ((got = std::fread(chunk, 1, sizeof chunk, f)) > 0) text.append(chunk, got);
+    ok = !std::ferror(f);
+    std::fclose(f);
+    if (!ok) return set_error(SLS_ERR_IO, std::string("failed to read ") + path);
     return sls_instance_from_dimacs_text(text.data(), text.size(), out);
 }
 

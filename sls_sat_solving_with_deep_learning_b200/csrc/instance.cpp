@@ -7,7 +7,6 @@
 
 #include <algorithm>
 #include <cstring>
-#include <unordered_map>
 
 namespace slsb {
 
@@ -164,26 +163,29 @@ std::string finalize_instance(HostInstance& h)
     h.canon.resize(m);
     h.has_duplicates = false;
     {
-        std::unordered_multimap<uint64_t, uint32_t> seen;
-        seen.reserve(size_t(m) * 2);
+        // open-addressing table of clause ids keyed by a content hash (linear probing, <= 50 % load)
+        size_t cap = 16;
+        while (cap < size_t(m) * 2) cap <<= 1;
+        const uint32_t EMPTY = 0xffffffffu;
+        std::vector<uint32_t> slot(cap, EMPTY);
         for (uint32_t c = 0; c < m; c++) {
             const uint32_t* l = h.lits.data() + h.row_ptr[c];
             const uint32_t k = h.row_ptr[c + 1] - h.row_ptr[c];
             uint64_t hash = 1469598103934665603ull ^ k;
             for (uint32_t j = 0; j < k; j++) hash = (hash ^ l[j]) * 1099511628211ull;
+            size_t i = size_t(hash ^ (hash >> 29)) & (cap - 1);
             uint32_t rep = c;
-            auto range = seen.equal_range(hash);
-            for (auto it = range.first; it != range.second; ++it) {
-                const uint32_t o = it->second;
-                if (h.row_ptr[o + 1] - h.row_ptr[o] == k &&
-                    std::equal(l, l + k, h.lits.data() + h.row_ptr[o])) {
+            while (slot[i] != EMPTY) {
+                const uint32_t o = slot[i];
+                if (h.row_ptr[o + 1] - h.row_ptr[o] == k && std::equal(l, l + k, h.lits.data() + h.row_ptr[o])) {
                     rep = o;
                     break;
                 }
+                i = (i + 1) & (cap - 1);
             }
             h.canon[c] = rep;
             if (rep == c)
-                seen.emplace(hash, c);
+                slot[i] = c;
             else
                 h.has_duplicates = true;
         }
