@@ -478,8 +478,8 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     if (s->smem_bytes) {
         SC_TRY(cudaFuncSetAttribute(walk_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)s->smem_bytes));
-        SC_TRY(cudaFuncSetAttribute(walk_k3s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)s->smem_bytes));
+        SC_TRY(cudaFuncSetAttribute(walk_k3s_kernel_for(params->algo, params->prob_flip_best),
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     }
 #undef SC_TRY
 
@@ -596,7 +596,7 @@ extern "C" int sls_solver_launch(sls_solver* s, void* cuda_stream)
     }
     const bool use_k3 = s->k3 && walk_k3_supports(s->args);
     if (use_k3) {
-        walk_k3s_kernel<<<blocks, threads, s->smem_bytes, st>>>(s->args);
+        walk_k3s_kernel_for(s->p.algo, s->p.prob_flip_best)<<<blocks, threads, s->smem_bytes, st>>>(s->args);
     } else {
         if (s->smem_state)
             walk_generic_kernel<true><<<blocks, threads, s->smem_bytes, st>>>(s->args);
@@ -948,7 +948,8 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         CUDA_TRY(cudaMemcpy(d_items[g].base, items[g].data(), items[g].size() * sizeof(WalkArgs), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(d_cta[g].base, cta_begin[g].data(), cta_begin[g].size() * 4, cudaMemcpyHostToDevice));
     }
-    if (smem_max[0]) CUDA_TRY(cudaFuncSetAttribute(walk_k3s_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[0]));
+    const WalkK3BatchKernel k3_batch = walk_k3s_batch_kernel_for(params->algo, params->prob_flip_best);
+    if (smem_max[0]) CUDA_TRY(cudaFuncSetAttribute(k3_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[0]));
     if (smem_max[1])
         CUDA_TRY(cudaFuncSetAttribute(walk_generic_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[1]));
     CUDA_TRY(cudaEventRecord(ev0));
@@ -958,7 +959,7 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         const uint32_t* dc = reinterpret_cast<const uint32_t*>(d_cta[g].base);
         const uint32_t ni = (uint32_t)items[g].size(), blocks = cta_begin[g].back();
         if (g == 0)
-            walk_k3s_batch_kernel<<<blocks, 128, smem_max[0]>>>(di, dc, ni);
+            k3_batch<<<blocks, 128, smem_max[0]>>>(di, dc, ni);
         else if (g == 1)
             walk_generic_batch_kernel<true><<<blocks, 128, smem_max[1]>>>(di, dc, ni);
         else

@@ -108,6 +108,17 @@ __device__ __forceinline__ void atoms_add(uint32_t a, uint32_t v)
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
+// Predicated forms: the condition travels as a predicate, so a lane-dependent update is one guarded
+// instruction instead of a divergent region (BSSY / BRA / BSYNC around one RED).
+__device__ __forceinline__ void atoms_xor_if(bool p, uint32_t a, uint32_t v)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q red.shared.xor.b32 [%1], %2; }" ::"r"((uint32_t)p), "r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void atoms_add_if(bool p, uint32_t a, uint32_t v)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q red.shared.add.u32 [%1], %2; }" ::"r"((uint32_t)p), "r"(a), "r"(v) : "memory");
+}
+
 // The chain's walk stream (same word positions, alignment rules and distributions as WalkStream /
 // WarpStream in philox.cuh) buffered in a 128-word ring in shared memory: on a refill every lane
 // evaluates one Philox block and stores its four words; a draw is then a single broadcast LDS.
@@ -153,8 +164,17 @@ struct RingStream {
         off += 2u;
         return (uint64_t)v.y << 32 | v.x;
     }
+    // the *_unchecked draws rely on the caller having made sure the ring holds the words (top of the step)
+    __device__ __forceinline__ uint64_t next_u64_unchecked()
+    {
+        off = (off + 1u) & ~1u;
+        const uint2 v = lds64(ring + 4u * off);
+        off += 2u;
+        return (uint64_t)v.y << 32 | v.x;
+    }
     __device__ __forceinline__ void skip_u64() { off = ((off + 1u) & ~1u) + 2u; }
     __device__ __forceinline__ double next_f64() { return (double)(next_u64() >> 11) * 0x1p-53; }
+    __device__ __forceinline__ double next_f64_unchecked() { return (double)(next_u64_unchecked() >> 11) * 0x1p-53; }
     __device__ __forceinline__ uint64_t uniform_u64(uint64_t range)
     {
         const uint64_t zone = (range << __clzll(range)) - 1ull;
@@ -165,7 +185,10 @@ struct RingStream {
     }
 };
 
-// `block` = index of this CTA among the CTAs of the item (instance) described by A
+// `block` = index of this CTA among the CTAs of the item (instance) described by A.
+// ALGO and GREEDY (prob_flip_best > 0) are compile-time: every instantiation carries only its own flip rule,
+// which keeps the step loop short enough for the instruction cache and frees registers.
+template <int ALGO, bool GREEDY>
 __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block, uint32_t* sm)
 {
     const int lane = threadIdx.x & 31;
@@ -183,7 +206,7 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
     const uint64_t chain = A.chain_offset + run;
 
     // literal code l = 2*var + neg is TRUE iff bit(var) != neg
-    auto lit_true = [sA](uint32_t l) -> uint32_t { return ((lds32(sA + (l >> 6) * 4u) >> ((l >> 1) & 31u)) ^ l) & 1u; };
+    auto lit_true = [sA](uint32_t l) -> uint32_t { return (__funnelshift_r(lds32(sA + (l >> 6) * 4u), 0u, l >> 1) ^ l) & 1u; };
 
     // ---- chain init: assignment from the init stream (lib.rs:206-210) ...
     for (uint32_t i = lane; i < I.slab_words; i += 32) sts32(sA + i * 4u, 0u);
@@ -251,27 +274,36 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
     uint64_t steps = 0, flips = 0;
     int err = 0;
     const bool mapping = A.mapping != 0;
-    const int algo = A.algo;
     const double pfb = A.pfb;
     const uint64_t nsteps = A.nsteps;
-    const bool greedy_possible = pfb > 0.0;
     const bool check_weights = (A.wflags & WF_INTERIOR) == 0;  // some weight is 0, 1 or outside (0,1)
     const uint4* __restrict__ crecx = A.crecx;
     const uint4* __restrict__ orec = I.orec;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     while (nf > 0 && steps < nsteps) {
-        steps++;
-        if (rng.off > RING_WORDS - 16u) rng.refill();  // a step consumes at most 13 words outside rejection loops
+        // The only refill on the common path: a step consumes at most 13 words outside rejection loops.
+        if (rng.off > RING_WORDS - 16u) rng.refill();
 
-        // ---- lib.rs:229: uniform pick among the violated clauses
-        uint32_t r;
-        {
-            const uint32_t zone = (nf << __clz(nf)) - 1u;
-            uint32_t v = rng.next_u32_unchecked();
-            while (v * nf > zone) v = rng.next_u32();
-            r = __umulhi(v, nf);
-        }
+        // ---- lib.rs:229: uniform pick among the violated clauses (UniformInt zone rejection: a rejected
+        // word is consumed and the draw repeats -- through the refill check above)
+        const uint32_t zone = (nf << __clz(nf)) - 1u;
+        const uint32_t pick = rng.next_u32_unchecked();
+        if (pick * nf > zone) continue;
+        steps++;
+        uint32_t r = __umulhi(pick, nf);
+
+        // lib.rs:231: one f64 is drawn on every step, greedy or not
+        bool greedy = false;
+        if (GREEDY)
+            greedy = rng.next_f64_unchecked() < pfb;
+        else
+            rng.skip_u64();
+        // probSAT's single draw (lib.rs:72) does not depend on the clause: fetch and convert it now so that
+        // the conversion overlaps the rank-select below
+        double u_ps = 0.0;
+        if (ALGO == ALGO_PROBSAT && !greedy) u_ps = (double)(rng.next_u64_unchecked() >> 12) * 0x1p-52;
+
         // level A: lane owns counters 2*lane, 2*lane+1
         const uint2 cc = lds64(sL + lane * 8u);
         const uint32_t both = cc.x + cc.y;
@@ -292,26 +324,20 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
         const bool hit = ((wsel >> lane) & 1u) && __popc(wsel & lt_mask) == r;
         const uint32_t c = (g * 32u + srcB) * 32u + ffs0(__ballot_sync(FULL, hit));
 
-        // ---- the clause record: six 16-byte quads, same address in every lane, issued together
+        // ---- the clause record: 16-byte quads, same address in every lane, issued together
         const uint4* rec = crecx + CRECX_QUADS * (size_t)c;
         const uint4 q0 = __ldg(rec);
         const uint4 q1 = __ldg(rec + 1);
         const uint4 q2 = __ldg(rec + 2);
-        const uint4 p0 = __ldg(rec + 3), p1 = __ldg(rec + 4), p2 = __ldg(rec + 5);
         const uint32_t k = q0.w;
 
-        // lib.rs:231: one f64 is drawn on every step, greedy or not
-        bool greedy = false;
-        if (greedy_possible)
-            greedy = rng.next_f64() < pfb;
-        else
-            rng.skip_u64();
-
-        // current values of the clause's variables (the dummy variable reads 0)
-        const uint32_t a0 = lit_true(q0.x & ~1u), a1 = lit_true(q0.y & ~1u), a2 = lit_true(q0.z & ~1u);
+        // Current values of the clause's variables.  The clause is violated, so each of its literals is false:
+        // the variable's value equals the literal's negation bit (the dummy literal of a short clause is
+        // positive and its variable reads 0) -- no shared-memory read.
+        const uint32_t a0 = q0.x & 1u, a1 = q0.y & 1u, a2 = q0.z & 1u;
 
         uint32_t marks = 0;  // bit j <=> the variable of literal j flips in this step
-        if (greedy) {
+        if (GREEDY && greedy) {
             // lib.rs:236-256: score = violations after tentatively flipping the variable
             uint64_t min_viol = ~0ull;
             const uint32_t aj[3] = {a0, a1, a2};
@@ -339,17 +365,18 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
                     }
                 }
             }
-        } else if (algo == ALGO_SCHOENING) {
+        } else if (ALGO == ALGO_SCHOENING) {
             uint32_t v;
-            const uint32_t zone = (k << __clz(k)) - 1u;  // lib.rs:52 clause.choose(rng)
-            do v = rng.next_u32(); while (v * k > zone);
+            const uint32_t zk = (k << __clz(k)) - 1u;  // lib.rs:52 clause.choose(rng)
+            do v = rng.next_u32(); while (v * k > zk);
             marks = 1u << __umulhi(v, k);
         } else {
             // flip probabilities (lib.rs:29-30): w if the variable is false, 1-w if it is true
+            const uint4 p0 = __ldg(rec + 3), p1 = __ldg(rec + 4), p2 = __ldg(rec + 5);
             const double fp0 = a0 ? __hiloint2double((int)p0.w, (int)p0.z) : __hiloint2double((int)p0.y, (int)p0.x);
             const double fp1 = a1 ? __hiloint2double((int)p1.w, (int)p1.z) : __hiloint2double((int)p1.y, (int)p1.x);
             const double fp2 = a2 ? __hiloint2double((int)p2.w, (int)p2.z) : __hiloint2double((int)p2.y, (int)p2.x);
-            if (algo == ALGO_PROBSAT) {
+            if (ALGO == ALGO_PROBSAT) {
                 // WeightedIndex::new over fp[0..k) (absent literals carry weight 0), lib.rs:71
                 const double cum0 = fp0;
                 const double cum1 = k > 1 ? cum0 + fp1 : cum0;
@@ -367,27 +394,28 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
                 // UniformFloat::new(0, total) + sample from 52 mantissa bits, lib.rs:72
                 double scale = total;
                 while (scale * (1.0 - 0x1p-52) >= total) scale = __longlong_as_double(__double_as_longlong(scale) - 1);
-                const double x = ((double)(rng.next_u64() >> 12) * 0x1p-52) * scale;
+                const double x = u_ps * scale;
                 // partition_point(cum <= x) over the first k-1 cumulative weights
                 marks = (k > 1 && cum0 <= x) ? ((k > 2 && cum1 <= x) ? 4u : 2u) : 1u;
             } else {
                 // lib.rs:24-35 / :81-92: one f64 per literal, in literal order
-                if (rng.next_f64() < fp0) marks |= 1u;
-                if (k > 1 && rng.next_f64() < fp1) marks |= 2u;
-                if (k > 2 && rng.next_f64() < fp2) marks |= 4u;
-                if (algo == ALGO_MOSER_SINGLE && marks)  // lib.rs:94-99
+                if (rng.next_f64_unchecked() < fp0) marks |= 1u;
+                if (k > 1 && rng.next_f64_unchecked() < fp1) marks |= 2u;
+                if (k > 2 && rng.next_f64_unchecked() < fp2) marks |= 4u;
+                if (ALGO == ALGO_MOSER_SINGLE && marks)  // lib.rs:94-99
                     marks = 1u << select_in_word(marks, (uint32_t)rng.uniform_u64(__popc(marks)));
             }
         }
 
         if (marks) {
             // lib.rs:37-41: toggle the marked variables (distinct on this path) ...
-            if (lane == 0) {
-                if (marks & 1u) atoms_xor(sA + (q0.x >> 6) * 4u, 1u << ((q0.x >> 1) & 31u));
-                if (marks & 2u) atoms_xor(sA + (q0.y >> 6) * 4u, 1u << ((q0.y >> 1) & 31u));
-                if (marks & 4u) atoms_xor(sA + (q0.z >> 6) * 4u, 1u << ((q0.z >> 1) & 31u));
-            }
-            __syncwarp();
+            const bool l0 = lane == 0;
+            atoms_xor_if(l0 && (marks & 1u), sA + (q0.x >> 6) * 4u, 1u << ((q0.x >> 1) & 31u));
+            atoms_xor_if(l0 && (marks & 2u), sA + (q0.y >> 6) * 4u, 1u << ((q0.y >> 1) & 31u));
+            atoms_xor_if(l0 && (marks & 4u), sA + (q0.z >> 6) * 4u, 1u << ((q0.z >> 1) & 31u));
+            // A clause never holds a variable twice, so re-evaluating the clauses of one flipped variable reads
+            // only other variables: the toggles must be visible only when several variables flip (MT)
+            if (ALGO == ALGO_MOSER && !(GREEDY && greedy)) __syncwarp();
             flips += __popc(marks);
             // ... then re-evaluate every clause of each flipped variable (lib.rs:278-287)
             for (uint32_t mk = marks; mk; mk &= mk - 1) {
@@ -408,10 +436,8 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
                     const bool cur = (vword & bit) != 0 && act;
                     const bool ins = viol && !cur;  // HashSet::insert of a new element
                     const bool rem = !viol && cur;  // HashSet::remove of a present element
-                    if (ins | rem) {
-                        atoms_xor(va, bit);
-                        atoms_add(sL + (orc.x >> 10) * 4u, ins ? 1u : 0xffffffffu);
-                    }
+                    atoms_xor_if(ins | rem, va, bit);
+                    atoms_add_if(ins | rem, sL + (orc.x >> 10) * 4u, ins ? 1u : 0xffffffffu);
                     nf += __popc(__ballot_sync(FULL, ins)) - __popc(__ballot_sync(FULL, rem));
                     base += 32;
                 } while (base < len);
@@ -433,12 +459,14 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
     }
 }
 
+template <int ALGO, bool GREEDY>
 __global__ void __launch_bounds__(128, 7) walk_k3s_kernel(const WalkArgs A)
 {
     extern __shared__ uint32_t sm[];
-    walk_k3s_body(A, blockIdx.x, sm);
+    walk_k3s_body<ALGO, GREEDY>(A, blockIdx.x, sm);
 }
 
+template <int ALGO, bool GREEDY>
 __global__ void __launch_bounds__(128, 6) walk_k3s_batch_kernel(const WalkArgs* __restrict__ items, const uint32_t* __restrict__ cta_begin,
                                                                 uint32_t n_items)
 {
@@ -446,7 +474,41 @@ __global__ void __launch_bounds__(128, 6) walk_k3s_batch_kernel(const WalkArgs* 
     __shared__ WalkArgs item;
     const uint32_t it = find_item(cta_begin, n_items, blockIdx.x);
     load_item(item, items + it);
-    walk_k3s_body(item, blockIdx.x - __ldg(cta_begin + it), sm);
+    walk_k3s_body<ALGO, GREEDY>(item, blockIdx.x - __ldg(cta_begin + it), sm);
+}
+
+// Host-side choice of the instantiation for (algo, prob_flip_best > 0).
+using WalkK3Kernel = void (*)(const WalkArgs);
+using WalkK3BatchKernel = void (*)(const WalkArgs*, const uint32_t*, uint32_t);
+
+template <bool GREEDY>
+inline WalkK3Kernel walk_k3s_kernel_for_algo(int algo)
+{
+    switch (algo) {
+        case ALGO_MOSER: return walk_k3s_kernel<ALGO_MOSER, GREEDY>;
+        case ALGO_MOSER_SINGLE: return walk_k3s_kernel<ALGO_MOSER_SINGLE, GREEDY>;
+        case ALGO_SCHOENING: return walk_k3s_kernel<ALGO_SCHOENING, GREEDY>;
+        default: return walk_k3s_kernel<ALGO_PROBSAT, GREEDY>;
+    }
+}
+inline WalkK3Kernel walk_k3s_kernel_for(int algo, double pfb)
+{
+    return pfb > 0.0 ? walk_k3s_kernel_for_algo<true>(algo) : walk_k3s_kernel_for_algo<false>(algo);
+}
+
+template <bool GREEDY>
+inline WalkK3BatchKernel walk_k3s_batch_kernel_for_algo(int algo)
+{
+    switch (algo) {
+        case ALGO_MOSER: return walk_k3s_batch_kernel<ALGO_MOSER, GREEDY>;
+        case ALGO_MOSER_SINGLE: return walk_k3s_batch_kernel<ALGO_MOSER_SINGLE, GREEDY>;
+        case ALGO_SCHOENING: return walk_k3s_batch_kernel<ALGO_SCHOENING, GREEDY>;
+        default: return walk_k3s_batch_kernel<ALGO_PROBSAT, GREEDY>;
+    }
+}
+inline WalkK3BatchKernel walk_k3s_batch_kernel_for(int algo, double pfb)
+{
+    return pfb > 0.0 ? walk_k3s_batch_kernel_for_algo<true>(algo) : walk_k3s_batch_kernel_for_algo<false>(algo);
 }
 
 }  // namespace slsb
