@@ -108,15 +108,12 @@ __device__ __forceinline__ void atoms_add(uint32_t a, uint32_t v)
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
-// Predicated forms: the condition travels as a predicate, so a lane-dependent update is one guarded
-// instruction instead of a divergent region (BSSY / BRA / BSYNC around one RED).
-__device__ __forceinline__ void atoms_xor_if(bool p, uint32_t a, uint32_t v)
+// a : b on a predicate, as one SEL (the compiler otherwise turns three selects on one condition into a branch)
+__device__ __forceinline__ uint32_t selp(bool p, uint32_t a, uint32_t b)
 {
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q red.shared.xor.b32 [%1], %2; }" ::"r"((uint32_t)p), "r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ void atoms_add_if(bool p, uint32_t a, uint32_t v)
-{
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q red.shared.add.u32 [%1], %2; }" ::"r"((uint32_t)p), "r"(a), "r"(v) : "memory");
+    uint32_t r;
+    asm("{ .reg .pred q; setp.ne.u32 q, %3, 0; selp.u32 %0, %1, %2, q; }" : "=r"(r) : "r"(a), "r"(b), "r"((uint32_t)p));
+    return r;
 }
 
 // The chain's walk stream (same word positions, alignment rules and distributions as WalkStream /
@@ -336,112 +333,133 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
         // positive and its variable reads 0) -- no shared-memory read.
         const uint32_t a0 = q0.x & 1u, a1 = q0.y & 1u, a2 = q0.z & 1u;
 
-        uint32_t marks = 0;  // bit j <=> the variable of literal j flips in this step
-        if (GREEDY && greedy) {
-            // lib.rs:236-256: score = violations after tentatively flipping the variable
-            uint64_t min_viol = ~0ull;
-            const uint32_t aj[3] = {a0, a1, a2};
-            const uint32_t osj[3] = {q1.x, q1.z, q2.x}, olj[3] = {q1.y, q1.w, q2.y};
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                if ((uint32_t)j < k) {
-                    const uint32_t av = aj[j] ^ 1u;
-                    uint32_t after = 0, before = 0;
-                    for (uint32_t base = 0; base < olj[j]; base += 32) {
-                        const uint32_t o = base + lane;
-                        bool ca = false, cb = false;
-                        if (o < olj[j]) {
-                            const uint4 orc = __ldg(orec + osj[j] + o);
-                            ca = (av == orc.w) && !lit_true(orc.y) && !lit_true(orc.z);
-                            cb = (lds32(sV + (orc.x >> 5) * 4u) >> (orc.x & 31)) & 1u;
-                        }
-                        after += __popc(__ballot_sync(FULL, ca));
-                        before += __popc(__ballot_sync(FULL, cb));
-                    }
-                    const uint64_t viol = mapping ? (uint64_t)after : (uint64_t)nf - before + after;
-                    if (viol < min_viol) {
-                        min_viol = viol;
-                        marks = 1u << j;
-                    }
+        // Re-evaluation of every clause of a flipped variable (lib.rs:278-287): one occurrence record per lane.
+        // A clause never holds a variable twice, so only OTHER variables' bits are read here.
+        auto update_var = [&](uint32_t os, uint32_t len, uint32_t av) {
+            uint32_t base = 0;
+            do {
+                const uint32_t o = base + lane;
+                const bool act = o < len;
+                uint4 orc = make_uint4(0, 0, 0, 2);  // inactive lanes: never violated, never present
+                if (act) orc = __ldg(orec + os + o);
+                const uint32_t va = sV + (orc.x >> 5) * 4u;
+                const uint32_t vword = lds32(va);
+                const uint32_t bit = 1u << (orc.x & 31);
+                const bool viol = (av == orc.w) & !(lit_true(orc.y) | lit_true(orc.z));
+                const bool cur = (vword & bit) != 0 && act;
+                const bool ins = viol && !cur;  // HashSet::insert of a new element
+                const bool rem = !viol && cur;  // HashSet::remove of a present element
+                if (ins | rem) {
+                    atoms_xor(va, bit);
+                    atoms_add(sL + (orc.x >> 10) * 4u, ins ? 1u : 0xffffffffu);
                 }
-            }
-        } else if (ALGO == ALGO_SCHOENING) {
-            uint32_t v;
-            const uint32_t zk = (k << __clz(k)) - 1u;  // lib.rs:52 clause.choose(rng)
-            do v = rng.next_u32(); while (v * k > zk);
-            marks = 1u << __umulhi(v, k);
-        } else {
-            // flip probabilities (lib.rs:29-30): w if the variable is false, 1-w if it is true
+                nf += __popc(__ballot_sync(FULL, ins)) - __popc(__ballot_sync(FULL, rem));
+                base += 32;
+            } while (base < len);
+            __syncwarp();
+        };
+
+        if (ALGO == ALGO_MOSER && !(GREEDY && greedy)) {
+            // lib.rs:24-35: one f64 per literal, in literal order; every marked variable flips
             const uint4 p0 = __ldg(rec + 3), p1 = __ldg(rec + 4), p2 = __ldg(rec + 5);
             const double fp0 = a0 ? __hiloint2double((int)p0.w, (int)p0.z) : __hiloint2double((int)p0.y, (int)p0.x);
             const double fp1 = a1 ? __hiloint2double((int)p1.w, (int)p1.z) : __hiloint2double((int)p1.y, (int)p1.x);
             const double fp2 = a2 ? __hiloint2double((int)p2.w, (int)p2.z) : __hiloint2double((int)p2.y, (int)p2.x);
-            if (ALGO == ALGO_PROBSAT) {
-                // WeightedIndex::new over fp[0..k) (absent literals carry weight 0), lib.rs:71
-                const double cum0 = fp0;
-                const double cum1 = k > 1 ? cum0 + fp1 : cum0;
-                const double total = k > 2 ? cum1 + fp2 : cum1;
-                if (check_weights) {
-                    if (!(fp0 >= 0.0) || !(fp1 >= 0.0) || !(fp2 >= 0.0)) {
-                        err = DERR_WEIGHTS;
-                        break;
-                    }
-                    if (total == 0.0) {
-                        err = DERR_ALL_ZERO;
-                        break;
+            uint32_t marks = 0;  // bit j <=> the variable of literal j flips in this step
+            if (rng.next_f64_unchecked() < fp0) marks |= 1u;
+            if (k > 1 && rng.next_f64_unchecked() < fp1) marks |= 2u;
+            if (k > 2 && rng.next_f64_unchecked() < fp2) marks |= 4u;
+            if (marks) {
+                // lib.rs:37-41: toggle the marked variables (distinct on this path); lane j owns literal j
+                const uint32_t lj = selp(lane == 0, q0.x, selp(lane == 1, q0.y, q0.z));
+                if (lane < 3 && ((marks >> lane) & 1u)) atoms_xor(sA + (lj >> 6) * 4u, 1u << ((lj >> 1) & 31u));
+                __syncwarp();  // several variables flip: the re-evaluation below reads the other ones
+                flips += __popc(marks);
+                for (uint32_t mk = marks; mk; mk &= mk - 1) {
+                    const uint32_t j = ffs0(mk);
+                    update_var(selp(j == 0, q1.x, selp(j == 1, q1.z, q2.x)), selp(j == 0, q1.y, selp(j == 1, q1.w, q2.y)),
+                               selp(j == 0, a0, selp(j == 1, a1, a2)) ^ 1u);
+                }
+            }
+        } else {
+            // every other rule flips at most one variable: literal j of the clause
+            uint32_t j = 3;  // 3 = nothing to flip (MT-single without a mark)
+            if (GREEDY && greedy) {
+                // lib.rs:236-256: score = violations after tentatively flipping the variable; first strict minimum
+                uint64_t min_viol = ~0ull;
+                const uint32_t aj[3] = {a0, a1, a2};
+                const uint32_t osj[3] = {q1.x, q1.z, q2.x}, olj[3] = {q1.y, q1.w, q2.y};
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    if ((uint32_t)t < k) {
+                        const uint32_t av = aj[t] ^ 1u;
+                        uint32_t after = 0, before = 0;
+                        for (uint32_t base = 0; base < olj[t]; base += 32) {
+                            const uint32_t o = base + lane;
+                            bool ca = false, cb = false;
+                            if (o < olj[t]) {
+                                const uint4 orc = __ldg(orec + osj[t] + o);
+                                ca = (av == orc.w) && !lit_true(orc.y) && !lit_true(orc.z);
+                                cb = (lds32(sV + (orc.x >> 5) * 4u) >> (orc.x & 31)) & 1u;
+                            }
+                            after += __popc(__ballot_sync(FULL, ca));
+                            before += __popc(__ballot_sync(FULL, cb));
+                        }
+                        const uint64_t viol = mapping ? (uint64_t)after : (uint64_t)nf - before + after;
+                        if (viol < min_viol) {
+                            min_viol = viol;
+                            j = t;
+                        }
                     }
                 }
-                // UniformFloat::new(0, total) + sample from 52 mantissa bits, lib.rs:72
-                double scale = total;
-                while (scale * (1.0 - 0x1p-52) >= total) scale = __longlong_as_double(__double_as_longlong(scale) - 1);
-                const double x = u_ps * scale;
-                // partition_point(cum <= x) over the first k-1 cumulative weights
-                marks = (k > 1 && cum0 <= x) ? ((k > 2 && cum1 <= x) ? 4u : 2u) : 1u;
+            } else if (ALGO == ALGO_SCHOENING) {
+                uint32_t v;
+                const uint32_t zk = (k << __clz(k)) - 1u;  // lib.rs:52 clause.choose(rng)
+                do v = rng.next_u32(); while (v * k > zk);
+                j = __umulhi(v, k);
             } else {
-                // lib.rs:24-35 / :81-92: one f64 per literal, in literal order
-                if (rng.next_f64_unchecked() < fp0) marks |= 1u;
-                if (k > 1 && rng.next_f64_unchecked() < fp1) marks |= 2u;
-                if (k > 2 && rng.next_f64_unchecked() < fp2) marks |= 4u;
-                if (ALGO == ALGO_MOSER_SINGLE && marks)  // lib.rs:94-99
-                    marks = 1u << select_in_word(marks, (uint32_t)rng.uniform_u64(__popc(marks)));
+                // flip probabilities (lib.rs:29-30): w if the variable is false, 1-w if it is true
+                const uint4 p0 = __ldg(rec + 3), p1 = __ldg(rec + 4), p2 = __ldg(rec + 5);
+                const double fp0 = a0 ? __hiloint2double((int)p0.w, (int)p0.z) : __hiloint2double((int)p0.y, (int)p0.x);
+                const double fp1 = a1 ? __hiloint2double((int)p1.w, (int)p1.z) : __hiloint2double((int)p1.y, (int)p1.x);
+                const double fp2 = a2 ? __hiloint2double((int)p2.w, (int)p2.z) : __hiloint2double((int)p2.y, (int)p2.x);
+                if (ALGO == ALGO_PROBSAT) {
+                    // WeightedIndex::new over fp[0..k) (absent literals carry weight 0), lib.rs:71
+                    const double cum0 = fp0;
+                    const double cum1 = k > 1 ? cum0 + fp1 : cum0;
+                    const double total = k > 2 ? cum1 + fp2 : cum1;
+                    if (check_weights) {
+                        if (!(fp0 >= 0.0) || !(fp1 >= 0.0) || !(fp2 >= 0.0)) {
+                            err = DERR_WEIGHTS;
+                            break;
+                        }
+                        if (total == 0.0) {
+                            err = DERR_ALL_ZERO;
+                            break;
+                        }
+                    }
+                    // UniformFloat::new(0, total) + sample from 52 mantissa bits, lib.rs:72
+                    double scale = total;
+                    while (scale * (1.0 - 0x1p-52) >= total) scale = __longlong_as_double(__double_as_longlong(scale) - 1);
+                    const double x = u_ps * scale;
+                    // partition_point(cum <= x) over the first k-1 cumulative weights
+                    const bool ge0 = k > 1 && cum0 <= x, ge1 = k > 2 && cum1 <= x;
+                    j = selp(ge0, selp(ge1, 2u, 1u), 0u);
+                } else {
+                    // MT-single, lib.rs:81-99: mark like MT, then flip one uniformly chosen marked variable
+                    uint32_t marks = 0;
+                    if (rng.next_f64_unchecked() < fp0) marks |= 1u;
+                    if (k > 1 && rng.next_f64_unchecked() < fp1) marks |= 2u;
+                    if (k > 2 && rng.next_f64_unchecked() < fp2) marks |= 4u;
+                    if (marks) j = select_in_word(marks, (uint32_t)rng.uniform_u64(__popc(marks)));
+                }
             }
-        }
-
-        if (marks) {
-            // lib.rs:37-41: toggle the marked variables (distinct on this path) ...
-            const bool l0 = lane == 0;
-            atoms_xor_if(l0 && (marks & 1u), sA + (q0.x >> 6) * 4u, 1u << ((q0.x >> 1) & 31u));
-            atoms_xor_if(l0 && (marks & 2u), sA + (q0.y >> 6) * 4u, 1u << ((q0.y >> 1) & 31u));
-            atoms_xor_if(l0 && (marks & 4u), sA + (q0.z >> 6) * 4u, 1u << ((q0.z >> 1) & 31u));
-            // A clause never holds a variable twice, so re-evaluating the clauses of one flipped variable reads
-            // only other variables: the toggles must be visible only when several variables flip (MT)
-            if (ALGO == ALGO_MOSER && !(GREEDY && greedy)) __syncwarp();
-            flips += __popc(marks);
-            // ... then re-evaluate every clause of each flipped variable (lib.rs:278-287)
-            for (uint32_t mk = marks; mk; mk &= mk - 1) {
-                const uint32_t j = ffs0(mk);
-                const uint32_t av = (j == 0 ? a0 : j == 1 ? a1 : a2) ^ 1u;  // the variable's new value
-                const uint32_t os = j == 0 ? q1.x : j == 1 ? q1.z : q2.x;
-                const uint32_t len = j == 0 ? q1.y : j == 1 ? q1.w : q2.y;
-                uint32_t base = 0;
-                do {
-                    const uint32_t o = base + lane;
-                    const bool act = o < len;
-                    uint4 orc = make_uint4(0, 0, 0, 2);  // inactive lanes: never violated, never present
-                    if (act) orc = __ldg(orec + os + o);
-                    const uint32_t va = sV + (orc.x >> 5) * 4u;
-                    const uint32_t vword = lds32(va);
-                    const uint32_t bit = 1u << (orc.x & 31);
-                    const bool viol = (av == orc.w) & !(lit_true(orc.y) | lit_true(orc.z));
-                    const bool cur = (vword & bit) != 0 && act;
-                    const bool ins = viol && !cur;  // HashSet::insert of a new element
-                    const bool rem = !viol && cur;  // HashSet::remove of a present element
-                    atoms_xor_if(ins | rem, va, bit);
-                    atoms_add_if(ins | rem, sL + (orc.x >> 10) * 4u, ins ? 1u : 0xffffffffu);
-                    nf += __popc(__ballot_sync(FULL, ins)) - __popc(__ballot_sync(FULL, rem));
-                    base += 32;
-                } while (base < len);
-                __syncwarp();
+            if (ALGO != ALGO_MOSER_SINGLE || j < 3) {
+                const uint32_t lit = selp(j == 0, q0.x, selp(j == 1, q0.y, q0.z));
+                if (lane == 0) atoms_xor(sA + (lit >> 6) * 4u, 1u << ((lit >> 1) & 31u));  // lib.rs:37-41
+                flips++;
+                // no barrier: the re-evaluation never reads the flipped variable itself, and it ends with one
+                update_var(selp(j == 0, q1.x, selp(j == 1, q1.z, q2.x)), selp(j == 0, q1.y, selp(j == 1, q1.w, q2.y)), (lit & 1u) ^ 1u);
             }
         }
 
