@@ -556,7 +556,7 @@ extern "C" int sls_solver_set_weights(sls_solver* s, const double* w_init, size_
     if (s->d_crecx && s->inst->host.m) {
         // 64-byte clause records of the k<=3 kernel: literals + occurrence ranges + resample weights
         const DevInst& I = s->inst->dev;
-        build_crecx_kernel<<<(I.m + 255) / 256, 256>>>(I.crec, I.occ_ptr, s->d_w, s->d_crecx, I.m, I.n);
+        build_crecx_kernel<<<(I.m + 255) / 256, 256>>>(I.crec, I.occ_ptr, s->d_w, s->d_crecx, I.m, I.n, s->p.algo);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaDeviceSynchronize());
     }
@@ -927,7 +927,7 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         a.traj = nullptr;
         a.err = reinterpret_cast<int32_t*>(p_err.base) + i;
         if (pl.k3 && I.m)
-            build_crecx_kernel<<<(I.m + 255) / 256, 256>>>(I.crec, I.occ_ptr, a.w, const_cast<uint4*>(a.crecx), I.m, I.n);
+            build_crecx_kernel<<<(I.m + 255) / 256, 256>>>(I.crec, I.occ_ptr, a.w, const_cast<uint4*>(a.crecx), I.m, I.n, params->algo);
         const int g = pl.k3 ? 0 : pl.smem ? 1 : 2;
         if (cta_begin[g].empty()) cta_begin[g].push_back(0);
         cta_begin[g].push_back(cta_begin[g].back() + (uint32_t)((R + pl.wpb - 1) / pl.wpb));

@@ -5,9 +5,9 @@
 // Same algorithm and the same random draws as walk_generic.cuh (reference
 // rust/src/lib.rs:201-317, trajectory-identical); what changes is the data layout and the
 // instruction diet, because this loop is issue-bound (profiles/r01_*):
-//   crecx[c] = 96 bytes {lit0,lit1,lit2,k | occurrence ranges of the 3 variables |
-//              (w, 1-w) of the 3 variables}: everything the flip rule needs in ONE broadcast
-//              load per step (built per call from the weights by build_crecx_kernel);
+//   crecx[c] = 64 bytes {lit0,lit1,lit2,k | occurrence ranges of the 3 variables | the clause's flip
+//              probabilities, already reduced to what the rule needs}: everything a step needs in ONE
+//              broadcast load (built per set of weights by build_crecx_kernel, see there);
 //   orec[o]  = {clause, other lit a, other lit b, neg}: the clause content travels with the
 //              occurrence entry, so re-evaluating the clauses of the flipped variable
 //              (lib.rs:278-287) is one coalesced 16-byte load per lane and two shared-memory
@@ -25,45 +25,67 @@
 
 namespace slsb {
 
-static constexpr uint32_t CRECX_QUADS = 6;  // uint4 per clause record
+static constexpr uint32_t CRECX_QUADS = 4;  // uint4 per clause record (64 bytes: two sectors)
 
 __host__ __device__ inline bool walk_k3_supports(const WalkArgs& a)
 {
     return a.inst.orec != nullptr && a.crecx != nullptr && a.inst.l1_pad == 64;
 }
 
-// crecx[c] = { {l0,l1,l2,k}, {os0,ol0,os1,ol1}, {os2,ol2,0,0}, {w0,1-w0}, {w1,1-w1}, {w2,1-w2} }
+// The flip rule of a step only ever looks at a VIOLATED clause, and in a violated clause every literal is
+// false: the value of variable j is the literal's negation bit.  The flip probabilities of lib.rs:29-30
+// (w if the variable is false, 1-w if it is true) are therefore a static property of the clause, and so is
+// everything probSAT derives from them (WeightedIndex's cumulative sums and UniformFloat's scale, lib.rs:71-72).
+// They are computed here, once per set of weights, with the same double operations in the same order as the
+// per-step code of walk_generic.cuh:
+//   crecx[c] = { {l0,l1,l2, k | err<<8}, {os0,ol0,os1,ol1}, {os2,ol2, X}, {Y, Z} }   (X, Y, Z doubles)
+//   probSAT:  X = scale, Y = cum0, Z = cum1;  err = DERR_WEIGHTS / DERR_ALL_ZERO if WeightedIndex::new fails
+//   MT rules: X = fp0,   Y = fp1,  Z = fp2    (absent literals: 0)
 __global__ void build_crecx_kernel(const uint4* __restrict__ crec, const uint32_t* __restrict__ occ_ptr,
-                                   const double* __restrict__ w, uint4* __restrict__ crecx, uint32_t m, uint32_t n)
+                                   const double* __restrict__ w, uint4* __restrict__ crecx, uint32_t m, uint32_t n, int algo)
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= m) return;
     const uint4 cr = crec[c];
     uint32_t lit[3] = {cr.x, cr.y, cr.z};
     uint32_t os[3], ol[3];
-    double wv[3], nwv[3];
+    double fp[3];
 #pragma unroll
     for (int j = 0; j < 3; j++) {
         os[j] = ol[j] = 0;
-        wv[j] = nwv[j] = 0.0;
+        fp[j] = 0.0;
         if (lit[j] != LIT_NONE) {
             const uint32_t v = lit[j] >> 1;
             os[j] = occ_ptr[v];
             ol[j] = occ_ptr[v + 1] - os[j];
-            wv[j] = w[v];
-            nwv[j] = 1.0 - wv[j];  // lib.rs:30: the flip probability of a variable that is currently true
+            const double wv = w[v];
+            fp[j] = (lit[j] & 1u) ? 1.0 - wv : wv;  // negative literal false <=> variable true
         } else {
             lit[j] = n << 1;  // dummy variable n: always-false positive literal
         }
     }
+    double X = fp[0], Y = fp[1], Z = fp[2];
+    uint32_t err = 0;
+    if (algo == ALGO_PROBSAT) {
+        const double cum0 = fp[0], cum1 = cum0 + fp[1], total = cum1 + fp[2];
+        if (!(fp[0] >= 0.0) || !(fp[1] >= 0.0) || !(fp[2] >= 0.0))
+            err = DERR_WEIGHTS;
+        else if (total == 0.0)
+            err = DERR_ALL_ZERO;
+        // UniformFloat::new(0, total): the largest scale with scale * (1 - 2^-52) < total
+        double scale = total;
+        if (!err)
+            while (scale * (1.0 - 0x1p-52) >= total) scale = __longlong_as_double(__double_as_longlong(scale) - 1);
+        X = scale;
+        Y = cum0;
+        Z = cum1;
+    }
     uint4* out = crecx + CRECX_QUADS * (size_t)c;
-    out[0] = make_uint4(lit[0], lit[1], lit[2], cr.w);
+    out[0] = make_uint4(lit[0], lit[1], lit[2], cr.w | err << 8);
     out[1] = make_uint4(os[0], ol[0], os[1], ol[1]);
-    out[2] = make_uint4(os[2], ol[2], 0, 0);
-#pragma unroll
-    for (int j = 0; j < 3; j++)
-        out[3 + j] = make_uint4((uint32_t)__double2loint(wv[j]), (uint32_t)__double2hiint(wv[j]),
-                                (uint32_t)__double2loint(nwv[j]), (uint32_t)__double2hiint(nwv[j]));
+    out[2] = make_uint4(os[2], ol[2], (uint32_t)__double2loint(X), (uint32_t)__double2hiint(X));
+    out[3] = make_uint4((uint32_t)__double2loint(Y), (uint32_t)__double2hiint(Y), (uint32_t)__double2loint(Z),
+                        (uint32_t)__double2hiint(Z));
 }
 
 // inclusive warp scan, two instructions per level (shuffle with predicate + predicated add)
@@ -268,12 +290,13 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
     uint32_t* traj = A.want_traj ? A.traj + run * (A.nsteps + 1) : nullptr;
     if (traj && lane == 0) traj[0] = nf;
 
+    // probSAT, Schoening and the greedy move flip exactly one variable per step: no separate counter
+    constexpr bool COUNT_FLIPS = ALGO == ALGO_MOSER || ALGO == ALGO_MOSER_SINGLE;
     uint64_t steps = 0, flips = 0;
     int err = 0;
     const bool mapping = A.mapping != 0;
     const double pfb = A.pfb;
     const uint64_t nsteps = A.nsteps;
-    const bool check_weights = (A.wflags & WF_INTERIOR) == 0;  // some weight is 0, 1 or outside (0,1)
     const uint4* __restrict__ crecx = A.crecx;
     const uint4* __restrict__ orec = I.orec;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -281,13 +304,16 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
     while (nf > 0 && steps < nsteps) {
         // The only refill on the common path: a step consumes at most 13 words outside rejection loops.
         if (rng.off > RING_WORDS - 16u) rng.refill();
-
-        // ---- lib.rs:229: uniform pick among the violated clauses (UniformInt zone rejection: a rejected
-        // word is consumed and the draw repeats -- through the refill check above)
-        const uint32_t zone = (nf << __clz(nf)) - 1u;
-        const uint32_t pick = rng.next_u32_unchecked();
-        if (pick * nf > zone) continue;
         steps++;
+
+        // ---- lib.rs:229: uniform pick among the violated clauses (UniformInt: widening multiply, the low half
+        // is rejected above `zone` -- up to half of the draws when nf is just above a power of two)
+        const uint32_t zone = (nf << __clz(nf)) - 1u;
+        uint32_t pick = rng.next_u32_unchecked();
+        while (pick * nf > zone) {
+            if (rng.off > RING_WORDS - 14u) rng.refill();
+            pick = rng.next_u32_unchecked();
+        }
         uint32_t r = __umulhi(pick, nf);
 
         // lib.rs:231: one f64 is drawn on every step, greedy or not
@@ -326,7 +352,11 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
         const uint4 q0 = __ldg(rec);
         const uint4 q1 = __ldg(rec + 1);
         const uint4 q2 = __ldg(rec + 2);
-        const uint32_t k = q0.w;
+        const uint4 q3 = __ldg(rec + 3);
+        const uint32_t k = q0.w & 0xffu;
+        const double dX = __hiloint2double((int)q2.w, (int)q2.z);
+        const double dY = __hiloint2double((int)q3.y, (int)q3.x);
+        const double dZ = __hiloint2double((int)q3.w, (int)q3.z);
 
         // Current values of the clause's variables.  The clause is violated, so each of its literals is false:
         // the variable's value equals the literal's negation bit (the dummy literal of a short clause is
@@ -334,37 +364,35 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
         const uint32_t a0 = q0.x & 1u, a1 = q0.y & 1u, a2 = q0.z & 1u;
 
         // Re-evaluation of every clause of a flipped variable (lib.rs:278-287): one occurrence record per lane.
-        // A clause never holds a variable twice, so only OTHER variables' bits are read here.
+        // A clause never holds a variable twice, so only OTHER variables' bits are read here.  Lanes past the end
+        // of the list re-read its last record (same sector, same banks) and are masked out.
+        auto update_round = [&](uint32_t os, uint32_t len, uint32_t av, uint32_t base) {
+            const uint32_t o = base + lane;
+            const bool act = o < len;
+            const uint4 orc = __ldg(orec + os + min(o, len - 1u));
+            const uint32_t va = sV + (orc.x >> 5) * 4u;
+            const uint32_t vword = lds32(va);
+            const uint32_t bit = 1u << (orc.x & 31);
+            const bool viol = act & (av == orc.w) & !(lit_true(orc.y) | lit_true(orc.z));
+            const bool cur = act & ((vword & bit) != 0);
+            const bool ins = viol && !cur;  // HashSet::insert of a new element
+            const bool rem = !viol && cur;  // HashSet::remove of a present element
+            if (ins | rem) {
+                atoms_xor(va, bit);
+                atoms_add(sL + (orc.x >> 10) * 4u, ins ? 1u : 0xffffffffu);
+            }
+            nf += __popc(__ballot_sync(FULL, ins)) - __popc(__ballot_sync(FULL, rem));
+        };
         auto update_var = [&](uint32_t os, uint32_t len, uint32_t av) {
-            uint32_t base = 0;
-            do {
-                const uint32_t o = base + lane;
-                const bool act = o < len;
-                uint4 orc = make_uint4(0, 0, 0, 2);  // inactive lanes: never violated, never present
-                if (act) orc = __ldg(orec + os + o);
-                const uint32_t va = sV + (orc.x >> 5) * 4u;
-                const uint32_t vword = lds32(va);
-                const uint32_t bit = 1u << (orc.x & 31);
-                const bool viol = (av == orc.w) & !(lit_true(orc.y) | lit_true(orc.z));
-                const bool cur = (vword & bit) != 0 && act;
-                const bool ins = viol && !cur;  // HashSet::insert of a new element
-                const bool rem = !viol && cur;  // HashSet::remove of a present element
-                if (ins | rem) {
-                    atoms_xor(va, bit);
-                    atoms_add(sL + (orc.x >> 10) * 4u, ins ? 1u : 0xffffffffu);
-                }
-                nf += __popc(__ballot_sync(FULL, ins)) - __popc(__ballot_sync(FULL, rem));
-                base += 32;
-            } while (base < len);
+            update_round(os, len, av, 0);
+            if (len > 32)  // a variable with more than 32 occurrences: rare on the instances this kernel serves
+                for (uint32_t base = 32; base < len; base += 32) update_round(os, len, av, base);
             __syncwarp();
         };
 
         if (ALGO == ALGO_MOSER && !(GREEDY && greedy)) {
             // lib.rs:24-35: one f64 per literal, in literal order; every marked variable flips
-            const uint4 p0 = __ldg(rec + 3), p1 = __ldg(rec + 4), p2 = __ldg(rec + 5);
-            const double fp0 = a0 ? __hiloint2double((int)p0.w, (int)p0.z) : __hiloint2double((int)p0.y, (int)p0.x);
-            const double fp1 = a1 ? __hiloint2double((int)p1.w, (int)p1.z) : __hiloint2double((int)p1.y, (int)p1.x);
-            const double fp2 = a2 ? __hiloint2double((int)p2.w, (int)p2.z) : __hiloint2double((int)p2.y, (int)p2.x);
+            const double fp0 = dX, fp1 = dY, fp2 = dZ;
             uint32_t marks = 0;  // bit j <=> the variable of literal j flips in this step
             if (rng.next_f64_unchecked() < fp0) marks |= 1u;
             if (k > 1 && rng.next_f64_unchecked() < fp1) marks |= 2u;
@@ -374,7 +402,7 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
                 const uint32_t lj = selp(lane == 0, q0.x, selp(lane == 1, q0.y, q0.z));
                 if (lane < 3 && ((marks >> lane) & 1u)) atoms_xor(sA + (lj >> 6) * 4u, 1u << ((lj >> 1) & 31u));
                 __syncwarp();  // several variables flip: the re-evaluation below reads the other ones
-                flips += __popc(marks);
+                if (COUNT_FLIPS) flips += __popc(marks);
                 for (uint32_t mk = marks; mk; mk &= mk - 1) {
                     const uint32_t j = ffs0(mk);
                     update_var(selp(j == 0, q1.x, selp(j == 1, q1.z, q2.x)), selp(j == 0, q1.y, selp(j == 1, q1.w, q2.y)),
@@ -418,46 +446,29 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
                 do v = rng.next_u32(); while (v * k > zk);
                 j = __umulhi(v, k);
             } else {
-                // flip probabilities (lib.rs:29-30): w if the variable is false, 1-w if it is true
-                const uint4 p0 = __ldg(rec + 3), p1 = __ldg(rec + 4), p2 = __ldg(rec + 5);
-                const double fp0 = a0 ? __hiloint2double((int)p0.w, (int)p0.z) : __hiloint2double((int)p0.y, (int)p0.x);
-                const double fp1 = a1 ? __hiloint2double((int)p1.w, (int)p1.z) : __hiloint2double((int)p1.y, (int)p1.x);
-                const double fp2 = a2 ? __hiloint2double((int)p2.w, (int)p2.z) : __hiloint2double((int)p2.y, (int)p2.x);
                 if (ALGO == ALGO_PROBSAT) {
-                    // WeightedIndex::new over fp[0..k) (absent literals carry weight 0), lib.rs:71
-                    const double cum0 = fp0;
-                    const double cum1 = k > 1 ? cum0 + fp1 : cum0;
-                    const double total = k > 2 ? cum1 + fp2 : cum1;
-                    if (check_weights) {
-                        if (!(fp0 >= 0.0) || !(fp1 >= 0.0) || !(fp2 >= 0.0)) {
-                            err = DERR_WEIGHTS;
-                            break;
-                        }
-                        if (total == 0.0) {
-                            err = DERR_ALL_ZERO;
-                            break;
-                        }
+                    // lib.rs:71-72 on the precomputed record: WeightedIndex::new's verdict, then one uniform
+                    // sample in [0, total) and partition_point(cum <= x) over the cumulative weights (x < total, and
+                    // an absent literal repeats the previous sum, so no test on k is needed)
+                    if (q0.w > 0xffu) {
+                        err = (int)(q0.w >> 8);
+                        break;
                     }
-                    // UniformFloat::new(0, total) + sample from 52 mantissa bits, lib.rs:72
-                    double scale = total;
-                    while (scale * (1.0 - 0x1p-52) >= total) scale = __longlong_as_double(__double_as_longlong(scale) - 1);
-                    const double x = u_ps * scale;
-                    // partition_point(cum <= x) over the first k-1 cumulative weights
-                    const bool ge0 = k > 1 && cum0 <= x, ge1 = k > 2 && cum1 <= x;
-                    j = selp(ge0, selp(ge1, 2u, 1u), 0u);
+                    const double x = u_ps * dX;
+                    j = (dY <= x ? 1u : 0u) + (dZ <= x ? 1u : 0u);
                 } else {
                     // MT-single, lib.rs:81-99: mark like MT, then flip one uniformly chosen marked variable
                     uint32_t marks = 0;
-                    if (rng.next_f64_unchecked() < fp0) marks |= 1u;
-                    if (k > 1 && rng.next_f64_unchecked() < fp1) marks |= 2u;
-                    if (k > 2 && rng.next_f64_unchecked() < fp2) marks |= 4u;
+                    if (rng.next_f64_unchecked() < dX) marks |= 1u;
+                    if (k > 1 && rng.next_f64_unchecked() < dY) marks |= 2u;
+                    if (k > 2 && rng.next_f64_unchecked() < dZ) marks |= 4u;
                     if (marks) j = select_in_word(marks, (uint32_t)rng.uniform_u64(__popc(marks)));
                 }
             }
             if (ALGO != ALGO_MOSER_SINGLE || j < 3) {
                 const uint32_t lit = selp(j == 0, q0.x, selp(j == 1, q0.y, q0.z));
                 if (lane == 0) atoms_xor(sA + (lit >> 6) * 4u, 1u << ((lit >> 1) & 31u));  // lib.rs:37-41
-                flips++;
+                if (COUNT_FLIPS) flips++;
                 // no barrier: the re-evaluation never reads the flipped variable itself, and it ends with one
                 update_var(selp(j == 0, q1.x, selp(j == 1, q1.z, q2.x)), selp(j == 0, q1.y, selp(j == 1, q1.w, q2.y)), (lit & 1u) ^ 1u);
             }
@@ -473,7 +484,7 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
         A.has_best[run] = has_best;
         A.steps[run] = steps;
         A.best_energy[run] = best;
-        A.flips[run] = flips;
+        A.flips[run] = COUNT_FLIPS ? flips : steps - (err ? 1u : 0u);
     }
 }
 
