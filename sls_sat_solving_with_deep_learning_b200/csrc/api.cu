@@ -100,7 +100,7 @@ int ensure_on_device(sls_instance* inst)
         for (uint32_t c = 0; c < h.m; c++) {
             const uint32_t s = h.row_ptr[c], k = h.row_ptr[c + 1] - s;
             for (uint32_t j = 0; j < k; j++) {
-                uint32_t others[2] = {LIT_NONE, LIT_NONE};
+                uint32_t others[2] = {h.n << 1, h.n << 1};  // absent: positive literal of the dummy variable n (bit always 0)
                 uint32_t t = 0;
                 for (uint32_t q = 0; q < k; q++)
                     if (q != j) others[t++] = h.lits[s + q];
@@ -108,7 +108,7 @@ int ensure_on_device(sls_instance* inst)
                 orec[fill[lit >> 1]++] = make_uint4(c, others[0], others[1], lit & 1u);
             }
         }
-        for (size_t i = L; i < orec.size(); i++) orec[i] = make_uint4(0, LIT_NONE, LIT_NONE, 0);
+        for (size_t i = L; i < orec.size(); i++) orec[i] = make_uint4(0, h.n << 1, h.n << 1, 2);
     }
     std::vector<Seg> segs = {
         {h.row_ptr.data(), h.row_ptr.size() * 4, 0}, {h.lits.data(), L * 4, 0},

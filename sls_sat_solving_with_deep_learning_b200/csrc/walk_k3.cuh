@@ -79,6 +79,10 @@ __global__ void build_crecx_kernel(const uint4* __restrict__ crec, const uint32_
         X = scale;
         Y = cum0;
         Z = cum1;
+        if (err) {  // the step that meets this clause still runs (see the walk): make it pick literal 0, which exists
+            X = 0.0;
+            Y = Z = __longlong_as_double(0x7ff0000000000000ll);
+        }
     }
     uint4* out = crecx + CRECX_QUADS * (size_t)c;
     out[0] = make_uint4(lit[0], lit[1], lit[2], cr.w | err << 8);
@@ -296,12 +300,12 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
     int err = 0;
     const bool mapping = A.mapping != 0;
     const double pfb = A.pfb;
-    const uint64_t nsteps = A.nsteps;
+    uint64_t budget = A.nsteps;  // steps this chain may still reach (cut short by a failing clause)
     const uint4* __restrict__ crecx = A.crecx;
     const uint4* __restrict__ orec = I.orec;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
-    while (nf > 0 && steps < nsteps) {
+    while (nf > 0 && steps < budget) {
         // The only refill on the common path: a step consumes at most 13 words outside rejection loops.
         if (rng.off > RING_WORDS - 16u) rng.refill();
         steps++;
@@ -326,6 +330,7 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
         // the conversion overlaps the rank-select below
         double u_ps = 0.0;
         if (ALGO == ALGO_PROBSAT && !greedy) u_ps = (double)(rng.next_u64_unchecked() >> 12) * 0x1p-52;
+        asm volatile("" : "+r"(r), "+d"(u_ps));  // pins the conversion before the rank-select instead of after the L2 trip
 
         // level A: lane owns counters 2*lane, 2*lane+1
         const uint2 cc = lds64(sL + lane * 8u);
@@ -450,9 +455,12 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
                     // lib.rs:71-72 on the precomputed record: WeightedIndex::new's verdict, then one uniform
                     // sample in [0, total) and partition_point(cum <= x) over the cumulative weights (x < total, and
                     // an absent literal repeats the previous sum, so no test on k is needed)
-                    if (q0.w > 0xffu) {
+                    // (no branch on the verdict here: it would split the record's four loads into two dependent
+                    // trips to L2.  A failed clause ends the walk through the step budget; the call then fails
+                    // as a whole and nothing of this chain is returned.)
+                    if (q0.w > 0xffu && !err) {
                         err = (int)(q0.w >> 8);
-                        break;
+                        budget = steps;
                     }
                     const double x = u_ps * dX;
                     j = (dY <= x ? 1u : 0u) + (dZ <= x ? 1u : 0u);
@@ -484,7 +492,7 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
         A.has_best[run] = has_best;
         A.steps[run] = steps;
         A.best_energy[run] = best;
-        A.flips[run] = COUNT_FLIPS ? flips : steps - (err ? 1u : 0u);
+        A.flips[run] = COUNT_FLIPS ? flips : steps;
     }
 }
 

@@ -119,6 +119,62 @@ def test_walk_k3_kernel_matches_oracle(algo, pfb, mapping):
     assert_same_run(g, o)
 
 
+def _mixed_short_clauses(n, m, seed):
+    """Distinct clauses of 1..3 literals over distinct variables: the fast kernel's absent-literal paths."""
+    rng = np.random.default_rng(seed)
+    seen, out = set(), []
+    while len(out) < m:
+        k = int(rng.integers(1, 4))
+        vs = sorted(rng.choice(n, size=k, replace=False) + 1)
+        c = tuple(int(v) * (1 if rng.integers(0, 2) else -1) for v in vs)
+        if c not in seen:
+            seen.add(c)
+            out.append(c)
+    return out
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("pfb", [0.0, 0.35])
+def test_walk_k3_kernel_short_clauses_match_oracle(algo, pfb):
+    # clauses with 1 and 2 literals next to 3-literal ones (absent literals = the dummy variable), both on an
+    # instance a warp covers in one round and on one with several counter groups
+    for n, m, seed in [(2, 2, 0), (40, 150, 1), (700, 2600, 2)]:
+        clauses = [(1, 2), (-1, -2)] if n == 2 else _mixed_short_clauses(n, m, seed)
+        gi = eng.Instance.from_clauses(n, clauses)
+        oi = so.Instance.from_clauses(n, clauses)
+        rng = np.random.default_rng(seed)
+        w_init = rng.uniform(0.05, 0.95, n)
+        w_res = rng.uniform(0.05, 0.95, n)
+        s = eng.ResidentSolver(gi, algo, 300, 24, True, True, pfb, seed=5)
+        assert s.variant.startswith("walk_k3s"), s.variant
+        s.close()
+        g = eng.run_sls(gi, algo, w_init, w_res, 300, 24, True, True, pfb, seed=5)
+        o = oi.run_sls(algo, w_init, w_res, 300, 24, True, True, pfb, seed=5)
+        assert_same_run(g, o)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_walk_k3_kernel_boundary_weights_match_oracle(algo):
+    # resample weights of exactly 0 and 1 on some variables: zero flip probabilities inside a clause
+    # (WeightedIndex with zero entries, Bernoulli marks that never / always fire); probSAT fails as a whole when a
+    # violated clause has only zero weights -- both sides must then fail
+    name = "r3sat_test_random_KCNF3_100_210_6416893"
+    gi, oi = both(name)
+    rng = np.random.default_rng(9)
+    w_res = rng.uniform(0.05, 0.95, gi.n)
+    w_res[rng.choice(gi.n, 12, replace=False)] = 0.0
+    w_res[rng.choice(gi.n, 12, replace=False)] = 1.0
+    w_init = rng.uniform(0.05, 0.95, gi.n)
+    try:
+        o = oi.run_sls(algo, w_init, w_res, 400, 24, True, True, 0.0, seed=8)
+    except Exception:
+        with pytest.raises(eng.PanicException):
+            eng.run_sls(gi, algo, w_init, w_res, 400, 24, True, True, 0.0, seed=8)
+        return
+    g = eng.run_sls(gi, algo, w_init, w_res, 400, 24, True, True, 0.0, seed=8)
+    assert_same_run(g, o)
+
+
 @pytest.mark.parametrize("algo", ALGOS)
 @pytest.mark.parametrize("pfb", [0.0, 0.35])
 @pytest.mark.parametrize("mapping", [True, False])
