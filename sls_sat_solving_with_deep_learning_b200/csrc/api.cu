@@ -478,7 +478,7 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     if (s->smem_bytes) {
         SC_TRY(cudaFuncSetAttribute(walk_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)s->smem_bytes));
-        SC_TRY(cudaFuncSetAttribute(walk_k3s_kernel_for(params->algo, params->prob_flip_best),
+        SC_TRY(cudaFuncSetAttribute(walk_k3s_kernel_for(params->algo, params->prob_flip_best, params->return_trajectories != 0),
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     }
 #undef SC_TRY
@@ -596,7 +596,7 @@ extern "C" int sls_solver_launch(sls_solver* s, void* cuda_stream)
     }
     const bool use_k3 = s->k3 && walk_k3_supports(s->args);
     if (use_k3) {
-        walk_k3s_kernel_for(s->p.algo, s->p.prob_flip_best)<<<blocks, threads, s->smem_bytes, st>>>(s->args);
+        walk_k3s_kernel_for(s->p.algo, s->p.prob_flip_best, s->p.return_trajectories != 0)<<<blocks, threads, s->smem_bytes, st>>>(s->args);
     } else {
         if (s->smem_state)
             walk_generic_kernel<true><<<blocks, threads, s->smem_bytes, st>>>(s->args);

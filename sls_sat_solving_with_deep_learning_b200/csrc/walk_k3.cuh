@@ -149,18 +149,21 @@ static constexpr uint32_t RING_WORDS = 128;
 struct RingStream {
     ChainKey ck;
     uint64_t base;  // word position of ring[0], multiple of 4
-    uint32_t off;   // cursor relative to base
-    uint32_t ring;  // shared-window byte address of the ring
+    uint32_t cur;   // cursor: shared-window byte address of the next word
+    uint32_t ring;  // shared-window byte address of the ring (16-byte aligned)
     int lane;
     __device__ __forceinline__ RingStream(uint64_t seed, uint64_t chain, uint32_t ring_addr, int lane_)
-        : ck(seed, chain, STREAM_WALK), base(0), off(0), ring(ring_addr), lane(lane_)
+        : ck(seed, chain, STREAM_WALK), base(0), cur(ring_addr), ring(ring_addr), lane(lane_)
     {
         fill();
     }
+    // fewer than `words` words left in the ring?
+    __device__ __forceinline__ bool low(uint32_t words) const { return cur > ring + (RING_WORDS - words) * 4u; }
     __device__ __forceinline__ void refill()
     {
+        const uint32_t off = (cur - ring) >> 2;
         base += off & ~3u;
-        off &= 3u;
+        cur = ring + (off & 3u) * 4u;
         fill();
     }
     __device__ __forceinline__ void fill()
@@ -173,29 +176,34 @@ struct RingStream {
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ring + lane * 16u), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
         __syncwarp();
     }
-    __device__ __forceinline__ uint32_t next_u32_unchecked() { return lds32(ring + 4u * off++); }
+    // the *_unchecked draws rely on the caller having made sure the ring holds the words (top of the step)
+    __device__ __forceinline__ uint32_t next_u32_unchecked()
+    {
+        const uint32_t v = lds32(cur);
+        cur += 4u;
+        return v;
+    }
     __device__ __forceinline__ uint32_t next_u32()
     {
-        if (off >= RING_WORDS) refill();
+        if (low(1)) refill();
         return next_u32_unchecked();
+    }
+    __device__ __forceinline__ uint64_t next_u64_unchecked()
+    {
+        cur = (cur + 4u) & ~7u;  // 64-bit draws sit on even word positions
+        const uint2 v = lds64(cur);
+        cur += 8u;
+        return (uint64_t)v.y << 32 | v.x;
     }
     __device__ __forceinline__ uint64_t next_u64()
     {
-        off = (off + 1u) & ~1u;
-        if (off >= RING_WORDS) refill();
-        const uint2 v = lds64(ring + 4u * off);
-        off += 2u;
+        cur = (cur + 4u) & ~7u;
+        if (low(2)) refill();
+        const uint2 v = lds64(cur);
+        cur += 8u;
         return (uint64_t)v.y << 32 | v.x;
     }
-    // the *_unchecked draws rely on the caller having made sure the ring holds the words (top of the step)
-    __device__ __forceinline__ uint64_t next_u64_unchecked()
-    {
-        off = (off + 1u) & ~1u;
-        const uint2 v = lds64(ring + 4u * off);
-        off += 2u;
-        return (uint64_t)v.y << 32 | v.x;
-    }
-    __device__ __forceinline__ void skip_u64() { off = ((off + 1u) & ~1u) + 2u; }
+    __device__ __forceinline__ void skip_u64() { cur = ((cur + 4u) & ~7u) + 8u; }
     __device__ __forceinline__ double next_f64() { return (double)(next_u64() >> 11) * 0x1p-53; }
     __device__ __forceinline__ double next_f64_unchecked() { return (double)(next_u64_unchecked() >> 11) * 0x1p-53; }
     __device__ __forceinline__ uint64_t uniform_u64(uint64_t range)
@@ -211,7 +219,7 @@ struct RingStream {
 // `block` = index of this CTA among the CTAs of the item (instance) described by A.
 // ALGO and GREEDY (prob_flip_best > 0) are compile-time: every instantiation carries only its own flip rule,
 // which keeps the step loop short enough for the instruction cache and frees registers.
-template <int ALGO, bool GREEDY>
+template <int ALGO, bool GREEDY, bool TRAJ>
 __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block, uint32_t* sm)
 {
     const int lane = threadIdx.x & 31;
@@ -283,16 +291,14 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
     // the rings of the CTA's chains sit behind their slabs
     RingStream rng(A.seed, chain, (uint32_t)__cvta_generic_to_shared(sm) + (A.warps_per_block * I.slab_words + warp * RING_WORDS) * 4u, lane);
     uint32_t best = I.m;
-    bool has_best = false;
     uint32_t* best_bits = A.best_bits + run * (size_t)I.nwords;
     auto save_best = [&]() {
         best = nf;
-        has_best = true;
         for (uint32_t w = lane; w < I.nwords; w += 32) best_bits[w] = lds32(sA + w * 4u);
     };
     if (nf < best) save_best();
-    uint32_t* traj = A.want_traj ? A.traj + run * (A.nsteps + 1) : nullptr;
-    if (traj && lane == 0) traj[0] = nf;
+    uint32_t* traj = TRAJ ? A.traj + run * (A.nsteps + 1) : nullptr;
+    if (TRAJ && lane == 0) traj[0] = nf;
 
     // probSAT, Schoening and the greedy move flip exactly one variable per step: no separate counter
     constexpr bool COUNT_FLIPS = ALGO == ALGO_MOSER || ALGO == ALGO_MOSER_SINGLE;
@@ -305,204 +311,211 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
     const uint4* __restrict__ orec = I.orec;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
+    // 64-bit step budget, 32-bit counter inside a chunk (the loop test and the increment stay single instructions)
     while (nf > 0 && steps < budget) {
-        // The only refill on the common path: a step consumes at most 13 words outside rejection loops.
-        if (rng.off > RING_WORDS - 16u) rng.refill();
-        steps++;
+        uint32_t lim = (uint32_t)min(budget - steps, (uint64_t)0x40000000u), i = 0;
+        while (nf > 0 && i < lim) {
+            // The only refill on the common path: a step consumes at most 13 words outside rejection loops.
+            if (rng.low(16)) rng.refill();
+            i++;
 
-        // ---- lib.rs:229: uniform pick among the violated clauses (UniformInt: widening multiply, the low half
-        // is rejected above `zone` -- up to half of the draws when nf is just above a power of two)
-        const uint32_t zone = (nf << __clz(nf)) - 1u;
-        uint32_t pick = rng.next_u32_unchecked();
-        while (pick * nf > zone) {
-            if (rng.off > RING_WORDS - 14u) rng.refill();
-            pick = rng.next_u32_unchecked();
-        }
-        uint32_t r = __umulhi(pick, nf);
-
-        // lib.rs:231: one f64 is drawn on every step, greedy or not
-        bool greedy = false;
-        if (GREEDY)
-            greedy = rng.next_f64_unchecked() < pfb;
-        else
-            rng.skip_u64();
-        // probSAT's single draw (lib.rs:72) does not depend on the clause: fetch and convert it now so that
-        // the conversion overlaps the rank-select below
-        double u_ps = 0.0;
-        if (ALGO == ALGO_PROBSAT && !greedy) u_ps = (double)(rng.next_u64_unchecked() >> 12) * 0x1p-52;
-        asm volatile("" : "+r"(r), "+d"(u_ps));  // pins the conversion before the rank-select instead of after the L2 trip
-
-        // level A: lane owns counters 2*lane, 2*lane+1
-        const uint2 cc = lds64(sL + lane * 8u);
-        const uint32_t both = cc.x + cc.y;
-        const uint32_t inclA = warp_incl_scan_p(both);
-        const uint32_t srcA = ffs0(__ballot_sync(FULL, r < inclA));
-        r -= __shfl_sync(FULL, inclA - both, srcA);
-        const uint32_t first = __shfl_sync(FULL, cc.x, srcA);
-        const bool second = r >= first;
-        const uint32_t g = 2 * srcA + (second ? 1u : 0u);
-        if (second) r -= first;
-        // level B: the 32 words of group g
-        const uint32_t word = lds32(sV + (g * 32u + lane) * 4u);
-        const uint32_t pc = __popc(word);
-        const uint32_t inclB = warp_incl_scan_p(pc);
-        const uint32_t srcB = ffs0(__ballot_sync(FULL, r < inclB));
-        r -= __shfl_sync(FULL, inclB - pc, srcB);
-        const uint32_t wsel = __shfl_sync(FULL, word, srcB);
-        const bool hit = ((wsel >> lane) & 1u) && __popc(wsel & lt_mask) == r;
-        const uint32_t c = (g * 32u + srcB) * 32u + ffs0(__ballot_sync(FULL, hit));
-
-        // ---- the clause record: 16-byte quads, same address in every lane, issued together
-        const uint4* rec = crecx + CRECX_QUADS * (size_t)c;
-        const uint4 q0 = __ldg(rec);
-        const uint4 q1 = __ldg(rec + 1);
-        const uint4 q2 = __ldg(rec + 2);
-        const uint4 q3 = __ldg(rec + 3);
-        const uint32_t k = q0.w & 0xffu;
-        const double dX = __hiloint2double((int)q2.w, (int)q2.z);
-        const double dY = __hiloint2double((int)q3.y, (int)q3.x);
-        const double dZ = __hiloint2double((int)q3.w, (int)q3.z);
-
-        // Current values of the clause's variables.  The clause is violated, so each of its literals is false:
-        // the variable's value equals the literal's negation bit (the dummy literal of a short clause is
-        // positive and its variable reads 0) -- no shared-memory read.
-        const uint32_t a0 = q0.x & 1u, a1 = q0.y & 1u, a2 = q0.z & 1u;
-
-        // Re-evaluation of every clause of a flipped variable (lib.rs:278-287): one occurrence record per lane.
-        // A clause never holds a variable twice, so only OTHER variables' bits are read here.  Lanes past the end
-        // of the list re-read its last record (same sector, same banks) and are masked out.
-        auto update_round = [&](uint32_t os, uint32_t len, uint32_t av, uint32_t base) {
-            const uint32_t o = base + lane;
-            const bool act = o < len;
-            const uint4 orc = __ldg(orec + os + min(o, len - 1u));
-            const uint32_t va = sV + (orc.x >> 5) * 4u;
-            const uint32_t vword = lds32(va);
-            const uint32_t bit = 1u << (orc.x & 31);
-            const bool viol = act & (av == orc.w) & !(lit_true(orc.y) | lit_true(orc.z));
-            const bool cur = act & ((vword & bit) != 0);
-            const bool ins = viol && !cur;  // HashSet::insert of a new element
-            const bool rem = !viol && cur;  // HashSet::remove of a present element
-            if (ins | rem) {
-                atoms_xor(va, bit);
-                atoms_add(sL + (orc.x >> 10) * 4u, ins ? 1u : 0xffffffffu);
+            // ---- lib.rs:229: uniform pick among the violated clauses (UniformInt: widening multiply, the low half
+            // is rejected above `zone` -- up to half of the draws when nf is just above a power of two)
+            const uint32_t zone = (nf << __clz(nf)) - 1u;
+            uint32_t pick = rng.next_u32_unchecked();
+            while (pick * nf > zone) {
+                if (rng.low(14)) rng.refill();
+                pick = rng.next_u32_unchecked();
             }
-            nf += __popc(__ballot_sync(FULL, ins)) - __popc(__ballot_sync(FULL, rem));
-        };
-        auto update_var = [&](uint32_t os, uint32_t len, uint32_t av) {
-            update_round(os, len, av, 0);
-            if (len > 32)  // a variable with more than 32 occurrences: rare on the instances this kernel serves
-                for (uint32_t base = 32; base < len; base += 32) update_round(os, len, av, base);
-            __syncwarp();
-        };
+            uint32_t r = __umulhi(pick, nf);
 
-        if (ALGO == ALGO_MOSER && !(GREEDY && greedy)) {
-            // lib.rs:24-35: one f64 per literal, in literal order; every marked variable flips
-            const double fp0 = dX, fp1 = dY, fp2 = dZ;
-            uint32_t marks = 0;  // bit j <=> the variable of literal j flips in this step
-            if (rng.next_f64_unchecked() < fp0) marks |= 1u;
-            if (k > 1 && rng.next_f64_unchecked() < fp1) marks |= 2u;
-            if (k > 2 && rng.next_f64_unchecked() < fp2) marks |= 4u;
-            if (marks) {
-                // lib.rs:37-41: toggle the marked variables (distinct on this path); lane j owns literal j
-                const uint32_t lj = selp(lane == 0, q0.x, selp(lane == 1, q0.y, q0.z));
-                if (lane < 3 && ((marks >> lane) & 1u)) atoms_xor(sA + (lj >> 6) * 4u, 1u << ((lj >> 1) & 31u));
-                __syncwarp();  // several variables flip: the re-evaluation below reads the other ones
-                if (COUNT_FLIPS) flips += __popc(marks);
-                for (uint32_t mk = marks; mk; mk &= mk - 1) {
-                    const uint32_t j = ffs0(mk);
-                    update_var(selp(j == 0, q1.x, selp(j == 1, q1.z, q2.x)), selp(j == 0, q1.y, selp(j == 1, q1.w, q2.y)),
-                               selp(j == 0, a0, selp(j == 1, a1, a2)) ^ 1u);
+            // lib.rs:231: one f64 is drawn on every step, greedy or not
+            bool greedy = false;
+            if (GREEDY)
+                greedy = rng.next_f64_unchecked() < pfb;
+            else
+                rng.skip_u64();
+            // probSAT's single draw (lib.rs:72) does not depend on the clause: fetch and convert it now so that
+            // the conversion overlaps the rank-select below
+            double u_ps = 0.0;
+            if (ALGO == ALGO_PROBSAT && !greedy) u_ps = (double)(rng.next_u64_unchecked() >> 12) * 0x1p-52;
+            asm volatile("" : "+r"(r), "+d"(u_ps));  // pins the conversion before the rank-select instead of after the L2 trip
+
+            // level A: lane owns counters 2*lane, 2*lane+1
+            const uint2 cc = lds64(sL + lane * 8u);
+            const uint32_t both = cc.x + cc.y;
+            const uint32_t inclA = warp_incl_scan_p(both);
+            const uint32_t srcA = __popc(__ballot_sync(FULL, r >= inclA));  // lanes below the crossing form a prefix
+            r -= __shfl_sync(FULL, inclA - both, srcA);
+            const uint32_t first = __shfl_sync(FULL, cc.x, srcA);
+            const bool second = r >= first;
+            const uint32_t g = 2 * srcA + (second ? 1u : 0u);
+            if (second) r -= first;
+            // level B: the 32 words of group g
+            const uint32_t word = lds32(sV + (g * 32u + lane) * 4u);
+            const uint32_t pc = __popc(word);
+            const uint32_t inclB = warp_incl_scan_p(pc);
+            const uint32_t srcB = __popc(__ballot_sync(FULL, r >= inclB));
+            r -= __shfl_sync(FULL, inclB - pc, srcB);
+            const uint32_t wsel = __shfl_sync(FULL, word, srcB);
+            const bool hit = ((wsel >> lane) & 1u) && __popc(wsel & lt_mask) == r;
+            const uint32_t c = (g * 32u + srcB) * 32u + (31u - __clz(__ballot_sync(FULL, hit)));  // exactly one lane hits
+
+            // ---- the clause record: 16-byte quads, same address in every lane, issued together
+            const uint4* rec = crecx + CRECX_QUADS * (size_t)c;
+            const uint4 q0 = __ldg(rec);
+            const uint4 q1 = __ldg(rec + 1);
+            const uint4 q2 = __ldg(rec + 2);
+            const uint4 q3 = __ldg(rec + 3);
+            const uint32_t k = q0.w & 0xffu;
+            const double dX = __hiloint2double((int)q2.w, (int)q2.z);
+            const double dY = __hiloint2double((int)q3.y, (int)q3.x);
+            const double dZ = __hiloint2double((int)q3.w, (int)q3.z);
+
+            // Current values of the clause's variables.  The clause is violated, so each of its literals is false:
+            // the variable's value equals the literal's negation bit (the dummy literal of a short clause is
+            // positive and its variable reads 0) -- no shared-memory read.
+            const uint32_t a0 = q0.x & 1u, a1 = q0.y & 1u, a2 = q0.z & 1u;
+
+            // Re-evaluation of every clause of a flipped variable (lib.rs:278-287): one occurrence record per lane.
+            // A clause never holds a variable twice, so only OTHER variables' bits are read here.  Lanes past the end
+            // of the list re-read its last record (same sector, same banks) and are masked out.
+            auto update_round = [&](uint32_t os, uint32_t len, uint32_t av, uint32_t base) {
+                const uint32_t o = base + lane;
+                const bool act = o < len;
+                const uint4 orc = __ldg(orec + os + min(o, len - 1u));
+                const uint32_t va = sV + (orc.x >> 5) * 4u;
+                const uint32_t vword = lds32(va);
+                const uint32_t bit = 1u << (orc.x & 31);
+                const bool viol = act & (av == orc.w) & !(lit_true(orc.y) | lit_true(orc.z));
+                const bool cur = act & ((vword & bit) != 0);
+                const bool ins = viol && !cur;  // HashSet::insert of a new element
+                const bool rem = !viol && cur;  // HashSet::remove of a present element
+                if (ins | rem) {
+                    atoms_xor(va, bit);
+                    atoms_add(sL + (orc.x >> 10) * 4u, ins ? 1u : 0xffffffffu);
                 }
-            }
-        } else {
-            // every other rule flips at most one variable: literal j of the clause
-            uint32_t j = 3;  // 3 = nothing to flip (MT-single without a mark)
-            if (GREEDY && greedy) {
-                // lib.rs:236-256: score = violations after tentatively flipping the variable; first strict minimum
-                uint64_t min_viol = ~0ull;
-                const uint32_t aj[3] = {a0, a1, a2};
-                const uint32_t osj[3] = {q1.x, q1.z, q2.x}, olj[3] = {q1.y, q1.w, q2.y};
-#pragma unroll
-                for (int t = 0; t < 3; t++) {
-                    if ((uint32_t)t < k) {
-                        const uint32_t av = aj[t] ^ 1u;
-                        uint32_t after = 0, before = 0;
-                        for (uint32_t base = 0; base < olj[t]; base += 32) {
-                            const uint32_t o = base + lane;
-                            bool ca = false, cb = false;
-                            if (o < olj[t]) {
-                                const uint4 orc = __ldg(orec + osj[t] + o);
-                                ca = (av == orc.w) && !lit_true(orc.y) && !lit_true(orc.z);
-                                cb = (lds32(sV + (orc.x >> 5) * 4u) >> (orc.x & 31)) & 1u;
-                            }
-                            after += __popc(__ballot_sync(FULL, ca));
-                            before += __popc(__ballot_sync(FULL, cb));
-                        }
-                        const uint64_t viol = mapping ? (uint64_t)after : (uint64_t)nf - before + after;
-                        if (viol < min_viol) {
-                            min_viol = viol;
-                            j = t;
-                        }
+                nf += __popc(__ballot_sync(FULL, ins)) - __popc(__ballot_sync(FULL, rem));
+            };
+            auto update_var = [&](uint32_t os, uint32_t len, uint32_t av) {
+                update_round(os, len, av, 0);
+                if (len > 32)  // a variable with more than 32 occurrences: rare on the instances this kernel serves
+                    for (uint32_t base = 32; base < len; base += 32) update_round(os, len, av, base);
+                __syncwarp();
+            };
+
+            if (ALGO == ALGO_MOSER && !(GREEDY && greedy)) {
+                // lib.rs:24-35: one f64 per literal, in literal order; every marked variable flips
+                const double fp0 = dX, fp1 = dY, fp2 = dZ;
+                uint32_t marks = 0;  // bit j <=> the variable of literal j flips in this step
+                if (rng.next_f64_unchecked() < fp0) marks |= 1u;
+                if (k > 1 && rng.next_f64_unchecked() < fp1) marks |= 2u;
+                if (k > 2 && rng.next_f64_unchecked() < fp2) marks |= 4u;
+                if (marks) {
+                    // lib.rs:37-41: toggle the marked variables (distinct on this path); lane j owns literal j
+                    const uint32_t lj = selp(lane == 0, q0.x, selp(lane == 1, q0.y, q0.z));
+                    if (lane < 3 && ((marks >> lane) & 1u)) atoms_xor(sA + (lj >> 6) * 4u, 1u << ((lj >> 1) & 31u));
+                    __syncwarp();  // several variables flip: the re-evaluation below reads the other ones
+                    if (COUNT_FLIPS) flips += __popc(marks);
+                    for (uint32_t mk = marks; mk; mk &= mk - 1) {
+                        const uint32_t j = ffs0(mk);
+                        update_var(selp(j == 0, q1.x, selp(j == 1, q1.z, q2.x)), selp(j == 0, q1.y, selp(j == 1, q1.w, q2.y)),
+                                   selp(j == 0, a0, selp(j == 1, a1, a2)) ^ 1u);
                     }
                 }
-            } else if (ALGO == ALGO_SCHOENING) {
-                uint32_t v;
-                const uint32_t zk = (k << __clz(k)) - 1u;  // lib.rs:52 clause.choose(rng)
-                do v = rng.next_u32(); while (v * k > zk);
-                j = __umulhi(v, k);
             } else {
-                if (ALGO == ALGO_PROBSAT) {
-                    // lib.rs:71-72 on the precomputed record: WeightedIndex::new's verdict, then one uniform
-                    // sample in [0, total) and partition_point(cum <= x) over the cumulative weights (x < total, and
-                    // an absent literal repeats the previous sum, so no test on k is needed)
-                    // (no branch on the verdict here: it would split the record's four loads into two dependent
-                    // trips to L2.  A failed clause ends the walk through the step budget; the call then fails
-                    // as a whole and nothing of this chain is returned.)
-                    if (q0.w > 0xffu && !err) {
-                        err = (int)(q0.w >> 8);
-                        budget = steps;
+                // every other rule flips at most one variable: literal j of the clause
+                uint32_t j = 3;  // 3 = nothing to flip (MT-single without a mark)
+                if (GREEDY && greedy) {
+                    // lib.rs:236-256: score = violations after tentatively flipping the variable; first strict minimum
+                    uint64_t min_viol = ~0ull;
+                    const uint32_t aj[3] = {a0, a1, a2};
+                    const uint32_t osj[3] = {q1.x, q1.z, q2.x}, olj[3] = {q1.y, q1.w, q2.y};
+    #pragma unroll
+                    for (int t = 0; t < 3; t++) {
+                        if ((uint32_t)t < k) {
+                            const uint32_t av = aj[t] ^ 1u;
+                            uint32_t after = 0, before = 0;
+                            for (uint32_t base = 0; base < olj[t]; base += 32) {
+                                const uint32_t o = base + lane;
+                                bool ca = false, cb = false;
+                                if (o < olj[t]) {
+                                    const uint4 orc = __ldg(orec + osj[t] + o);
+                                    ca = (av == orc.w) && !lit_true(orc.y) && !lit_true(orc.z);
+                                    cb = (lds32(sV + (orc.x >> 5) * 4u) >> (orc.x & 31)) & 1u;
+                                }
+                                after += __popc(__ballot_sync(FULL, ca));
+                                before += __popc(__ballot_sync(FULL, cb));
+                            }
+                            const uint64_t viol = mapping ? (uint64_t)after : (uint64_t)nf - before + after;
+                            if (viol < min_viol) {
+                                min_viol = viol;
+                                j = t;
+                            }
+                        }
                     }
-                    const double x = u_ps * dX;
-                    j = (dY <= x ? 1u : 0u) + (dZ <= x ? 1u : 0u);
+                } else if (ALGO == ALGO_SCHOENING) {
+                    uint32_t v;
+                    const uint32_t zk = (k << __clz(k)) - 1u;  // lib.rs:52 clause.choose(rng)
+                    do v = rng.next_u32(); while (v * k > zk);
+                    j = __umulhi(v, k);
                 } else {
-                    // MT-single, lib.rs:81-99: mark like MT, then flip one uniformly chosen marked variable
-                    uint32_t marks = 0;
-                    if (rng.next_f64_unchecked() < dX) marks |= 1u;
-                    if (k > 1 && rng.next_f64_unchecked() < dY) marks |= 2u;
-                    if (k > 2 && rng.next_f64_unchecked() < dZ) marks |= 4u;
-                    if (marks) j = select_in_word(marks, (uint32_t)rng.uniform_u64(__popc(marks)));
+                    if (ALGO == ALGO_PROBSAT) {
+                        // lib.rs:71-72 on the precomputed record: WeightedIndex::new's verdict, then one uniform
+                        // sample in [0, total) and partition_point(cum <= x) over the cumulative weights (x < total, and
+                        // an absent literal repeats the previous sum, so no test on k is needed)
+                        // (no branch on the verdict here: it would split the record's four loads into two dependent
+                        // trips to L2.  A failed clause ends the walk through the step budget; the call then fails
+                        // as a whole and nothing of this chain is returned.)
+                        if (q0.w > 0xffu && !err) {
+                            err = (int)(q0.w >> 8);
+                            lim = i;
+                            budget = steps + i;
+                        }
+                        const double x = u_ps * dX;
+                        j = (dY <= x ? 1u : 0u) + (dZ <= x ? 1u : 0u);
+                    } else {
+                        // MT-single, lib.rs:81-99: mark like MT, then flip one uniformly chosen marked variable
+                        uint32_t marks = 0;
+                        if (rng.next_f64_unchecked() < dX) marks |= 1u;
+                        if (k > 1 && rng.next_f64_unchecked() < dY) marks |= 2u;
+                        if (k > 2 && rng.next_f64_unchecked() < dZ) marks |= 4u;
+                        if (marks) j = select_in_word(marks, (uint32_t)rng.uniform_u64(__popc(marks)));
+                    }
+                }
+                if (ALGO != ALGO_MOSER_SINGLE || j < 3) {
+                    const uint32_t lit = selp(j == 0, q0.x, selp(j == 1, q0.y, q0.z));
+                    if (lane == 0) atoms_xor(sA + (lit >> 6) * 4u, 1u << ((lit >> 1) & 31u));  // lib.rs:37-41
+                    if (COUNT_FLIPS) flips++;
+                    // no barrier: the re-evaluation never reads the flipped variable itself, and it ends with one
+                    update_var(selp(j == 0, q1.x, selp(j == 1, q1.z, q2.x)), selp(j == 0, q1.y, selp(j == 1, q1.w, q2.y)), (lit & 1u) ^ 1u);
                 }
             }
-            if (ALGO != ALGO_MOSER_SINGLE || j < 3) {
-                const uint32_t lit = selp(j == 0, q0.x, selp(j == 1, q0.y, q0.z));
-                if (lane == 0) atoms_xor(sA + (lit >> 6) * 4u, 1u << ((lit >> 1) & 31u));  // lib.rs:37-41
-                if (COUNT_FLIPS) flips++;
-                // no barrier: the re-evaluation never reads the flipped variable itself, and it ends with one
-                update_var(selp(j == 0, q1.x, selp(j == 1, q1.z, q2.x)), selp(j == 0, q1.y, selp(j == 1, q1.w, q2.y)), (lit & 1u) ^ 1u);
-            }
-        }
 
-        if (nf < best) save_best();                        // lib.rs:292-296
-        if (traj && lane == 0) traj[steps] = nf;           // lib.rs:298-300
+            if (nf < best) save_best();                        // lib.rs:292-296
+            if (TRAJ && lane == 0) traj[steps + i] = nf;       // lib.rs:298-300
+        }
+        steps += i;
     }
 
     if (lane == 0) {
         if (err) atomicCAS(A.err, 0, err);
         A.found[run] = nf == 0 && !err;
-        A.has_best[run] = has_best;
+        A.has_best[run] = best < I.m;  // best starts at m (lib.rs:216) and every improvement is saved
         A.steps[run] = steps;
         A.best_energy[run] = best;
         A.flips[run] = COUNT_FLIPS ? flips : steps;
     }
 }
 
-template <int ALGO, bool GREEDY>
+template <int ALGO, bool GREEDY, bool TRAJ>
 __global__ void __launch_bounds__(128, 7) walk_k3s_kernel(const WalkArgs A)
 {
     extern __shared__ uint32_t sm[];
-    walk_k3s_body<ALGO, GREEDY>(A, blockIdx.x, sm);
+    walk_k3s_body<ALGO, GREEDY, TRAJ>(A, blockIdx.x, sm);
 }
 
+// the batched form never records trajectories (sls_run_batch refuses them)
 template <int ALGO, bool GREEDY>
 __global__ void __launch_bounds__(128, 6) walk_k3s_batch_kernel(const WalkArgs* __restrict__ items, const uint32_t* __restrict__ cta_begin,
                                                                 uint32_t n_items)
@@ -511,26 +524,27 @@ __global__ void __launch_bounds__(128, 6) walk_k3s_batch_kernel(const WalkArgs* 
     __shared__ WalkArgs item;
     const uint32_t it = find_item(cta_begin, n_items, blockIdx.x);
     load_item(item, items + it);
-    walk_k3s_body<ALGO, GREEDY>(item, blockIdx.x - __ldg(cta_begin + it), sm);
+    walk_k3s_body<ALGO, GREEDY, false>(item, blockIdx.x - __ldg(cta_begin + it), sm);
 }
 
-// Host-side choice of the instantiation for (algo, prob_flip_best > 0).
+// Host-side choice of the instantiation for (algo, prob_flip_best > 0, trajectories).
 using WalkK3Kernel = void (*)(const WalkArgs);
 using WalkK3BatchKernel = void (*)(const WalkArgs*, const uint32_t*, uint32_t);
 
-template <bool GREEDY>
+template <bool GREEDY, bool TRAJ>
 inline WalkK3Kernel walk_k3s_kernel_for_algo(int algo)
 {
     switch (algo) {
-        case ALGO_MOSER: return walk_k3s_kernel<ALGO_MOSER, GREEDY>;
-        case ALGO_MOSER_SINGLE: return walk_k3s_kernel<ALGO_MOSER_SINGLE, GREEDY>;
-        case ALGO_SCHOENING: return walk_k3s_kernel<ALGO_SCHOENING, GREEDY>;
-        default: return walk_k3s_kernel<ALGO_PROBSAT, GREEDY>;
+        case ALGO_MOSER: return walk_k3s_kernel<ALGO_MOSER, GREEDY, TRAJ>;
+        case ALGO_MOSER_SINGLE: return walk_k3s_kernel<ALGO_MOSER_SINGLE, GREEDY, TRAJ>;
+        case ALGO_SCHOENING: return walk_k3s_kernel<ALGO_SCHOENING, GREEDY, TRAJ>;
+        default: return walk_k3s_kernel<ALGO_PROBSAT, GREEDY, TRAJ>;
     }
 }
-inline WalkK3Kernel walk_k3s_kernel_for(int algo, double pfb)
+inline WalkK3Kernel walk_k3s_kernel_for(int algo, double pfb, bool traj)
 {
-    return pfb > 0.0 ? walk_k3s_kernel_for_algo<true>(algo) : walk_k3s_kernel_for_algo<false>(algo);
+    if (pfb > 0.0) return traj ? walk_k3s_kernel_for_algo<true, true>(algo) : walk_k3s_kernel_for_algo<true, false>(algo);
+    return traj ? walk_k3s_kernel_for_algo<false, true>(algo) : walk_k3s_kernel_for_algo<false, false>(algo);
 }
 
 template <bool GREEDY>
