@@ -108,6 +108,13 @@ __device__ __forceinline__ uint32_t warp_incl_scan_p(uint32_t v)
 }
 
 __device__ __forceinline__ uint32_t ffs0(uint32_t mask) { return __ffs(mask) - 1; }
+// index of the highest set bit (one FLO)
+__device__ __forceinline__ uint32_t bfind(uint32_t mask)
+{
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(mask));
+    return r;
+}
 
 // Shared memory through explicit shared-space instructions on a 32-bit byte address: the hot loop
 // must never see a generic pointer to shared memory (the generic->shared conversion costs an
@@ -306,7 +313,7 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
     int err = 0;
     const bool mapping = A.mapping != 0;
     const double pfb = A.pfb;
-    uint64_t budget = A.nsteps;  // steps this chain may still reach (cut short by a failing clause)
+    const uint64_t budget = A.nsteps;
     const uint4* __restrict__ crecx = A.crecx;
     const uint4* __restrict__ orec = I.orec;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -315,15 +322,13 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
     while (nf > 0 && steps < budget) {
         uint32_t lim = (uint32_t)min(budget - steps, (uint64_t)0x40000000u), i = 0;
         while (nf > 0 && i < lim) {
-            // The only refill on the common path: a step consumes at most 13 words outside rejection loops.
-            if (rng.low(16)) rng.refill();
-            i++;
+            i++;  // (the ring holds at least 16 words here: a step consumes at most 13 outside rejection loops)
 
             // ---- lib.rs:229: uniform pick among the violated clauses (UniformInt: widening multiply, the low half
             // is rejected above `zone` -- up to half of the draws when nf is just above a power of two)
-            const uint32_t zone = (nf << __clz(nf)) - 1u;
+            const uint32_t zone1 = nf << __clz(nf);  // rand's zone + 1 (top bit set, so no wrap)
             uint32_t pick = rng.next_u32_unchecked();
-            while (pick * nf > zone) {
+            while (pick * nf >= zone1) {
                 if (rng.low(14)) rng.refill();
                 pick = rng.next_u32_unchecked();
             }
@@ -359,7 +364,7 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
             r -= __shfl_sync(FULL, inclB - pc, srcB);
             const uint32_t wsel = __shfl_sync(FULL, word, srcB);
             const bool hit = ((wsel >> lane) & 1u) && __popc(wsel & lt_mask) == r;
-            const uint32_t c = (g * 32u + srcB) * 32u + (31u - __clz(__ballot_sync(FULL, hit)));  // exactly one lane hits
+            const uint32_t c = (g * 32u + srcB) * 32u + bfind(__ballot_sync(FULL, hit));  // exactly one lane hits
 
             // ---- the clause record: 16-byte quads, same address in every lane, issued together
             const uint4* rec = crecx + CRECX_QUADS * (size_t)c;
@@ -467,10 +472,9 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
                         // (no branch on the verdict here: it would split the record's four loads into two dependent
                         // trips to L2.  A failed clause ends the walk through the step budget; the call then fails
                         // as a whole and nothing of this chain is returned.)
-                        if (q0.w > 0xffu && !err) {
+                        if (q0.w > 0xffu) {
                             err = (int)(q0.w >> 8);
                             lim = i;
-                            budget = steps + i;
                         }
                         const double x = u_ps * dX;
                         j = (dY <= x ? 1u : 0u) + (dZ <= x ? 1u : 0u);
@@ -492,10 +496,16 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
                 }
             }
 
-            if (nf < best) save_best();                        // lib.rs:292-296
+            // one rarely taken region for both housekeeping jobs: a new best assignment (lib.rs:292-296) and the
+            // ring refill that guarantees the next step its 16 words
+            if ((nf < best) | rng.low(16)) {
+                if (nf < best) save_best();
+                if (rng.low(16)) rng.refill();
+            }
             if (TRAJ && lane == 0) traj[steps + i] = nf;       // lib.rs:298-300
         }
         steps += i;
+        if (err) break;
     }
 
     if (lane == 0) {
