@@ -291,9 +291,9 @@ def run_own(args, rank, world, local_rank):
             "gpu_launches": int(args.steps * solver.launch_count()),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one walk_k3s launch (ncu --set full,
-                         # profiles/r01_v3_walk_k3s_summary.md): 6.85 MB + 0.60 MB, independent of the step count
+                         # profiles/r01_final_walk_k3s_summary.md): 5.51 MB + 0.86 MB, independent of the step count
                          # because instance and chain state never leave L2 / shared memory
-                         "traffic": 7.45e6, "peak_source": peak_src,
+                         "traffic": 6.37e6, "peak_source": peak_src,
                          "bytes_per_flip": BYTES_PER_FLIP, "kernel_ms": kms,
                          "note": "latency-bound walk: state in shared memory, instance in L2; see DESIGN.md"},
         }
