@@ -78,6 +78,9 @@ int sls_instance_get_csr(const sls_instance *inst, uint64_t *row_ptr, int32_t *s
  *      per row, every clause counted on its own (the Python semantics). ----- */
 int sls_eval_assignments(sls_instance *inst, const uint8_t *assignments, uint64_t batch, uint32_t *violated_bits,
                          uint32_t *energy);
+/* device time (ms, CUDA events: transposition + evaluation kernels, no copies) of the calling thread's last
+ * sls_eval_assignments -- measurement only, no reference equivalent */
+double sls_eval_last_kernel_ms(void);
 
 /* ---- solver: replaces run_sls_python / run_sls (lib.rs:103-149, :165-335) */
 typedef struct {

@@ -6,6 +6,7 @@ Public surface (mirrors the reference's interface for this path):
   run_sls_batch           many instances x nruns chains in one launch
   Instance                DIMACS / CSR -> clause + occurrence CSR in HBM
   get_violated_constraints, eval_assignments   clause evaluation (sat_representations.py:718-741)
+  candidate_energies      the training loader's candidate energies (data_utils.py:123-129)
 """
 from .solver import (  # noqa: F401
     ALGOS,
@@ -13,8 +14,10 @@ from .solver import (  # noqa: F401
     PanicException,
     ResidentSolver,
     SlsResult,
+    candidate_energies,
     device_count,
     eval_assignments,
+    eval_last_kernel_ms,
     get_violated_constraints,
     run_sls,
     run_sls_batch,

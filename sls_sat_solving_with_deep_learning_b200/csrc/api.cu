@@ -140,7 +140,7 @@ int ensure_on_device(sls_instance* inst)
     d.nwords = (h.n + 32) / 32;  // one spare bit: the dummy variable n of the k<=3 path
     d.mwords = (h.m + 31) / 32;
     d.ngroups = (d.mwords + 31) / 32;
-    d.off_v = (d.nwords + 3u) & ~3u;
+    d.off_v = (d.nwords + 7u) & ~7u;  // vbits rows start on a 32-byte sector (tile stores of init_sliced.cuh)
     d.off_l1 = d.off_v + ((d.mwords + 31u) & ~31u);  // vbits zero-padded to whole 32-word groups
     d.l1_pad = std::max(64u, (d.ngroups + 63u) & ~63u);
     d.l2_pad = d.l1_pad > 64 ? ((d.l1_pad / 64 + 63u) & ~63u) : 0u;
@@ -265,6 +265,8 @@ extern "C" int sls_instance_get_csr(const sls_instance* inst, uint64_t* row_ptr,
 }
 
 // ------------------------------------------------------- clause evaluation
+static thread_local double g_last_eval_ms = 0.0;  // device time of the calling thread's last sls_eval_assignments
+
 extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignments, uint64_t batch,
                                     uint32_t* violated_bits, uint32_t* energy)
 {
@@ -277,17 +279,23 @@ extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignmen
         if (energy) std::memset(energy, 0, batch * sizeof(uint32_t));
         return SLS_OK;
     }
-    const uint64_t nslices = (batch + 31) / 32;
-    if (nslices > 65535) return set_error(SLS_ERR_ARG, "batch too large for one call (max 2096128 rows)");
+    const uint64_t nslices = (batch + SLICE_W - 1) / SLICE_W;
+    if (nslices > 65535) return set_error(SLS_ERR_ARG, "batch too large for one call (max 16776960 rows)");
     uint8_t* d_bytes = nullptr;
-    uint32_t *d_tbits = nullptr, *d_v = nullptr, *d_e = nullptr;
+    uint32_t *d_tq = nullptr, *d_v = nullptr, *d_e = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     auto cleanup = [&] {
         dfree(d_bytes);
-        dfree(d_tbits);
+        dfree(d_tq);
         dfree(d_v);
         dfree(d_e);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
     };
     const size_t n1 = std::max<uint32_t>(I.n, 1);
+    // device rows of violated bits are padded to whole tiles so that a tile row is one aligned 32-byte sector
+    const uint32_t ntiles = (I.mwords + TILE_WORDS - 1) / TILE_WORDS;
+    const uint32_t pitch = ntiles * TILE_WORDS;
 #define EV_TRY(expr)                                                                                     \
     do {                                                                                                 \
         cudaError_t _e = (expr);                                                                         \
@@ -297,32 +305,51 @@ extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignmen
         }                                                                                                \
     } while (0)
     EV_TRY(dmalloc(&d_bytes, batch * n1));
-    EV_TRY(dmalloc(&d_tbits, nslices * n1 * 4));
+    EV_TRY(dmalloc(&d_tq, nslices * n1 * SLICE_Q * 4));
     EV_TRY(dmalloc(&d_e, batch * 4));
-    if (violated_bits) EV_TRY(dmalloc(&d_v, batch * (size_t)I.mwords * 4));
+    if (violated_bits) EV_TRY(dmalloc(&d_v, batch * (size_t)pitch * 4));
+    EV_TRY(cudaEventCreate(&ev0));
+    EV_TRY(cudaEventCreate(&ev1));
     if (I.n) EV_TRY(cudaMemcpy(d_bytes, assignments, batch * (size_t)I.n, cudaMemcpyHostToDevice));
-    EV_TRY(cudaMemset(d_e, 0, batch * 4));
+    EV_TRY(cudaEventRecord(ev0));
+    EV_TRY(cudaMemsetAsync(d_e, 0, batch * 4));
     if (I.n) {
         const uint64_t total = nslices * I.n;
-        transpose_assignments_kernel<<<(unsigned)((total + 255) / 256), 256>>>(d_bytes, d_tbits, I.n, batch,
-                                                                               (uint32_t)nslices);
+        transpose_assignments_kernel<<<(unsigned)((total + 255) / 256), 256>>>(d_bytes, d_tq, I.n, batch, (uint32_t)nslices);
     }
     {
-        constexpr int WARPS = 8;
-        // enough CTAs to fill the machine a few times over, at least 8 words per warp pass
-        uint32_t words_per_block = 256;
-        const uint32_t bx = (I.mwords + words_per_block - 1) / words_per_block;
-        dim3 grid(bx, (unsigned)nslices);
-        eval_sliced_kernel<WARPS><<<grid, WARPS * 32>>>(I, d_tbits, d_v, d_e, batch, words_per_block);
+        constexpr int WARPS = 4;
+        // Small tiles-per-CTA: with many more CTAs per slice than the machine holds, the resident CTAs belong to
+        // one or two adjacent slices (blockIdx.x runs fastest) and their tq arrays (32 B per variable) stay in L2.
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, inst->device);
+        const uint64_t want_ctas = (uint64_t)sms * 32;
+        uint32_t tiles_per_block = (uint32_t)std::max<uint64_t>(WARPS, (ntiles + want_ctas - 1) / want_ctas);
+        tiles_per_block = (tiles_per_block + WARPS - 1) / WARPS * WARPS;
+        dim3 grid((ntiles + tiles_per_block - 1) / tiles_per_block, (unsigned)nslices);
+        if (d_v)
+            eval_sliced_kernel<WARPS, true><<<grid, WARPS * 32>>>(I, d_tq, d_v, pitch, d_e, batch, tiles_per_block);
+        else
+            eval_sliced_kernel<WARPS, false><<<grid, WARPS * 32>>>(I, d_tq, nullptr, pitch, d_e, batch, tiles_per_block);
     }
     EV_TRY(cudaGetLastError());
-    EV_TRY(cudaDeviceSynchronize());
+    EV_TRY(cudaEventRecord(ev1));
+    EV_TRY(cudaEventSynchronize(ev1));
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        g_last_eval_ms = ms;
+    }
     if (energy) EV_TRY(cudaMemcpy(energy, d_e, batch * 4, cudaMemcpyDeviceToHost));
-    if (violated_bits) EV_TRY(cudaMemcpy(violated_bits, d_v, batch * (size_t)I.mwords * 4, cudaMemcpyDeviceToHost));
+    if (violated_bits)
+        EV_TRY(cudaMemcpy2D(violated_bits, (size_t)I.mwords * 4, d_v, (size_t)pitch * 4, (size_t)I.mwords * 4, batch,
+                            cudaMemcpyDeviceToHost));
     cleanup();
 #undef EV_TRY
     return SLS_OK;
 }
+
+extern "C" double sls_eval_last_kernel_ms(void) { return g_last_eval_ms; }
 
 // ------------------------------------------------------------------ solver
 struct sls_solver {
@@ -450,11 +477,12 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     if (!s->smem_state) SC_TRY(dmalloc(&s->d_gstate, R1 * slab_bytes));
     SC_TRY(dmalloc(&s->d_best_bits, R1 * std::max<size_t>(I.nwords, 1) * 4));
     if (!s->smem_state && !(I.flags & INST_HAS_DUPLICATES) && I.n > 0 && I.m > 0) {
-        // chains are initialised 32 at a time by the sliced kernels (init_sliced.cuh); the transposed
-        // assignments of one chunk of slices are kept in a scratch buffer of at most ~1 GB
-        const uint64_t nslices = (R + 31) / 32;
-        s->tbits_slices = (uint32_t)std::min<uint64_t>(nslices, std::max<uint64_t>(1, (1ull << 28) / I.n));
-        SC_TRY(dmalloc(&s->d_tbits, size_t(s->tbits_slices) * I.n * 4));
+        // chains are initialised 256 at a time by the sliced kernels (init_sliced.cuh); the transposed
+        // assignments of one chunk of slices (32 bytes per variable and slice) are kept in a scratch buffer
+        // of at most ~1 GB
+        const uint64_t nslices = (R + SLICE_W - 1) / SLICE_W;
+        s->tbits_slices = (uint32_t)std::min<uint64_t>(nslices, std::max<uint64_t>(1, (1ull << 25) / I.n));
+        SC_TRY(dmalloc(&s->d_tbits, size_t(s->tbits_slices) * I.n * SLICE_Q * 4));
         SC_TRY(dmalloc(&s->d_nf_init, R1 * 4));
     }
     if (!s->smem_state) {
@@ -580,14 +608,15 @@ extern "C" int sls_solver_launch(sls_solver* s, void* cuda_stream)
         const DevInst& I = s->args.inst;
         const uint64_t R = s->p.nruns;
         CUDA_TRY(cudaMemsetAsync(s->d_gstate, 0, R * size_t(I.slab_words) * 4, st));
-        const uint32_t nslices = (uint32_t)((R + 31) / 32);
-        const uint32_t words_per_block = 64;
+        const uint32_t nslices = (uint32_t)((R + SLICE_W - 1) / SLICE_W);
+        const uint32_t words_per_block = 16;
+        constexpr int SCAN_WARPS = 4;
         for (uint32_t s0 = 0; s0 < nslices; s0 += s->tbits_slices) {
             const uint32_t cnt = std::min(s->tbits_slices, nslices - s0);
             dim3 g1((I.nwords + words_per_block - 1) / words_per_block, cnt);
-            init_assign_sliced_kernel<<<g1, 128, 0, st>>>(s->args, s->d_tbits, s0, words_per_block);
-            dim3 g2((I.ngroups + 3) / 4, cnt);
-            init_scan_sliced_kernel<<<g2, 128, 0, st>>>(s->args, s->d_tbits, s0);
+            init_assign_sliced_kernel<<<g1, 256, 0, st>>>(s->args, s->d_tbits, s0, words_per_block);
+            dim3 g2((I.ngroups + SCAN_WARPS - 1) / SCAN_WARPS, cnt);
+            init_scan_sliced_kernel<SCAN_WARPS><<<g2, SCAN_WARPS * 32, 0, st>>>(s->args, s->d_tbits, s0);
             s->launches += 2;
         }
         init_counters_kernel<<<(unsigned)((R * 32 + 127) / 128), 128, 0, st>>>(s->args);

@@ -8,74 +8,212 @@
 
 namespace slsb {
 
-// Bit-sliced evaluation: assignments arrive as one byte per variable (the reference's Vec<bool> /
-// int array).  A CTA owns one slice of 32 assignments and a range of clauses.
-// tbits is the transposed assignment: tbits[slice][v] holds, in bit b, the value of variable v
-// under assignment 32*slice + b, so one literal fetch serves 32 assignments with a single
-// bitwise op.  Each lane evaluates one clause for all 32 assignments, then the 32x32 result
-// tile is transposed with 32 ballots so that each assignment gets its violated-set word.
-__global__ void transpose_assignments_kernel(const uint8_t* __restrict__ bytes, uint32_t* __restrict__ tbits,
-                                             uint32_t n, uint64_t batch, uint32_t nslices)
+// ---------------------------------------------------------------------------------------------
+// Bit-sliced evaluation, 256 assignments per literal fetch.
+//
+// A "slice" is a group of SLICE_W = 256 assignments (or chains, for the HBM-tier chain init of
+// init_sliced.cuh).  tq[slice][v] holds the 256 values of variable v as 8 words = 32 bytes = exactly one
+// memory sector, so the random gather a literal costs brings in nothing but useful bits (with the
+// former 32-wide slices 7/8 of every gathered sector was discarded and the kernel ran at the L2's sector rate,
+// not at its byte rate).  A lane owns one clause and evaluates it for the whole slice with bitwise ops;
+// the 32 clauses of a warp form 32x32 bit tiles that are transposed in registers (5 shuffle rounds per tile
+// instead of 32 ballots) so that each assignment gets its violated-set word; the words of 8 consecutive
+// clause words are staged in shared memory and leave as whole 32-byte sectors per assignment.
+static constexpr uint32_t SLICE_W = 256, SLICE_Q = SLICE_W / 32, TILE_WORDS = 8;
+
+// Transposes of the eight 32x32 bit tiles a row of clauses holds (x[q], one tile row per lane): on return lane b
+// holds column b of every tile (bit i = row i).  The eight tiles advance round by round, so eight independent
+// shuffles are in flight at a time; transposing them one after the other exposes the full shuffle latency 40
+// times per row (measured: 19 % issue utilisation, every sample on the instruction after a SHFL).
+__device__ __forceinline__ void transpose32x8(uint32_t (&x)[SLICE_Q], int lane)
+{
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        // m: the bit positions whose index has bit j clear
+        const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const bool hi = (lane & j) != 0;
+        const uint32_t keep = hi ? ~m : m;  // this lane's diagonal block stays
+        uint32_t y[SLICE_Q];
+#pragma unroll
+        for (uint32_t q = 0; q < SLICE_Q; q++) y[q] = __shfl_xor_sync(0xffffffffu, x[q], j);
+#pragma unroll
+        for (uint32_t q = 0; q < SLICE_Q; q++) {
+            const uint32_t moved = hi ? (y[q] >> j) : (y[q] << j);  // the partner's off-diagonal block, moved across
+            x[q] = (x[q] & keep) | (moved & ~keep);
+        }
+    }
+}
+
+// The gathered sector of tq: asked to stay in L2 (every clause of the slice comes back to this array at random),
+// while the literal stream and the outputs pass through with evict-first hints.
+// (sm_100 has 256-bit global loads: the whole sector is one instruction.)
+struct Sector {
+    uint32_t w[SLICE_Q];
+};
+__device__ __forceinline__ Sector ldg_sector_keep(const uint32_t* p)
+{
+    Sector v;
+    asm("ld.global.nc.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7])
+        : "l"(p));
+    return v;
+}
+
+// one literal's contribution: literal false <=> value == negation bit
+__device__ __forceinline__ void and_literal(uint32_t (&viol)[SLICE_Q], uint32_t l, const Sector& a)
+{
+    const uint32_t flip = (l & 1u) ? 0u : 0xffffffffu;  // positive literal: false where the value is 0
+#pragma unroll
+    for (uint32_t q = 0; q < SLICE_Q; q++) viol[q] &= a.w[q] ^ flip;
+}
+
+// Clause rows of a tile, software-pipelined.  A lane owns clause 32*(w0 + wi) + lane in row wi.  While the caller
+// transposes row wi, the four sector gathers of row wi+1 and the literal words of row wi+2 are in flight: the
+// scan is bound by memory latency (DRAM for the literal stream, L2 for the gathers), not by any throughput.
+// The first four literals of a clause travel through the pipeline; longer clauses finish with a plain loop.
+struct ClauseRows {
+    const DevInst& I;
+    const uint32_t* __restrict__ tq;
+    uint32_t c_next;             // clause whose literals are loaded next
+    uint32_t s_cur, e_cur, s_nxt, e_nxt;
+    bool ok_cur, ok_nxt;         // clause index < m
+    uint32_t l_cur[4], l_nxt[4];
+    Sector a[4];
+
+    __device__ __forceinline__ void fetch_lits(uint32_t c, uint32_t& s, uint32_t& e, bool& ok, uint32_t (&l)[4])
+    {
+        ok = c < I.m;
+        s = e = 0;
+        if (ok) {
+            if (I.uniform_k) {
+                s = c * I.uniform_k;
+                e = s + I.uniform_k;
+            } else {
+                s = __ldcs(I.row_ptr + c);
+                e = __ldcs(I.row_ptr + c + 1);
+            }
+        }
+#pragma unroll
+        for (uint32_t t = 0; t < 4; t++) l[t] = e > s ? __ldcs(I.lits + min(s + t, e - 1u)) : 0u;  // tail: last literal again
+    }
+    __device__ __forceinline__ void gather(const uint32_t (&l)[4])
+    {
+#pragma unroll
+        for (uint32_t t = 0; t < 4; t++) a[t] = ldg_sector_keep(tq + (size_t)(l[t] >> 1) * SLICE_Q);
+    }
+    // c0 = this lane's clause in row 0
+    __device__ __forceinline__ ClauseRows(const DevInst& I_, const uint32_t* tq_, uint32_t c0) : I(I_), tq(tq_)
+    {
+        fetch_lits(c0, s_cur, e_cur, ok_cur, l_cur);
+        gather(l_cur);
+        fetch_lits(c0 + 32u, s_nxt, e_nxt, ok_nxt, l_nxt);
+        c_next = c0 + 64u;
+    }
+    // viol[q] bit b <=> this lane's clause of the current row is violated under assignment 32q + b; then advance
+    __device__ __forceinline__ void next(uint32_t (&viol)[SLICE_Q])
+    {
+        const uint32_t init = ok_cur ? 0xffffffffu : 0u;  // an empty clause is violated everywhere (lib.rs:13-18)
+#pragma unroll
+        for (uint32_t q = 0; q < SLICE_Q; q++) viol[q] = init;
+        if (e_cur > s_cur) {
+#pragma unroll
+            for (uint32_t t = 0; t < 4; t++) and_literal(viol, l_cur[t], a[t]);  // AND is idempotent: repeats are harmless
+            for (uint32_t j = s_cur + 4; j < e_cur; j++) {
+                const uint32_t l = __ldcs(I.lits + j);
+                and_literal(viol, l, ldg_sector_keep(tq + (size_t)(l >> 1) * SLICE_Q));
+            }
+        }
+        s_cur = s_nxt;
+        e_cur = e_nxt;
+        ok_cur = ok_nxt;
+#pragma unroll
+        for (uint32_t t = 0; t < 4; t++) l_cur[t] = l_nxt[t];
+        gather(l_cur);
+        fetch_lits(c_next, s_nxt, e_nxt, ok_nxt, l_nxt);
+        c_next += 32u;
+    }
+};
+
+// bytes[b][v] (the reference's int / bool arrays, one byte per variable) -> tq[slice][v][q]
+__global__ void transpose_assignments_kernel(const uint8_t* __restrict__ bytes, uint32_t* __restrict__ tq, uint32_t n, uint64_t batch,
+                                             uint32_t nslices)
 {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (uint64_t)nslices * n) return;
     const uint32_t slice = (uint32_t)(idx / n);
     const uint32_t v = (uint32_t)(idx % n);
-    uint32_t word = 0;
-    const uint64_t b0 = (uint64_t)slice * 32u;
-    const uint32_t cnt = (uint32_t)min((uint64_t)32, batch - b0);
-    for (uint32_t i = 0; i < cnt; i++) word |= (uint32_t)(bytes[(b0 + i) * n + v] != 0) << i;
-    tbits[idx] = word;
+    const uint64_t b0 = (uint64_t)slice * SLICE_W;
+    uint32_t w[SLICE_Q];
+#pragma unroll
+    for (uint32_t q = 0; q < SLICE_Q; q++) {
+        uint32_t word = 0;
+        const uint64_t r0 = b0 + 32u * q;
+        if (r0 < batch) {
+            const uint32_t cnt = (uint32_t)min((uint64_t)32, batch - r0);
+            for (uint32_t i = 0; i < cnt; i++) word |= (uint32_t)(bytes[(r0 + i) * n + v] != 0) << i;
+        }
+        w[q] = word;
+    }
+    uint4* out = reinterpret_cast<uint4*>(tq + idx * SLICE_Q);
+    out[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    out[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) eval_sliced_kernel(const DevInst I, const uint32_t* __restrict__ tbits,
-                                                                 uint32_t* __restrict__ vout,
-                                                                 uint32_t* __restrict__ energy, uint64_t batch,
-                                                                 uint32_t words_per_block)
+// grid: (tile chunks, slices); a warp works through tiles of TILE_WORDS clause words x 256 assignments.
+// vout rows have a pitch of `pitch` words (a multiple of 8, so that a tile row is one aligned sector).
+// OUT = false: energies only (no staging buffer, twice the resident warps).
+template <int WARPS, bool OUT>
+__global__ void __launch_bounds__(WARPS * 32) eval_sliced_kernel(const DevInst I, const uint32_t* __restrict__ tq_all,
+                                                                 uint32_t* __restrict__ vout, uint32_t pitch,
+                                                                 uint32_t* __restrict__ energy, uint64_t batch, uint32_t tiles_per_block)
 {
+    __shared__ uint32_t stage[OUT ? WARPS : 1][OUT ? SLICE_W : 1][TILE_WORDS + 1];  // +1: the column stores of a tile hit 32 banks
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const uint32_t slice = blockIdx.y;
-    const uint32_t* a = tbits + (size_t)slice * I.n;
-    const uint64_t b0 = (uint64_t)slice * 32u;
-    const uint32_t valid = (uint32_t)min((uint64_t)32, batch - b0);
-    const uint32_t w_begin = blockIdx.x * words_per_block;
-    const uint32_t w_end = min(I.mwords, w_begin + words_per_block);
-    uint32_t my_energy = 0;  // lane b accumulates the energy of assignment b0 + b
-    for (uint32_t w = w_begin + warp; w < w_end; w += WARPS) {
-        const uint32_t c = w * 32u + lane;
-        uint32_t viol = 0;  // bit b: clause c violated under assignment b0 + b
-        if (c < I.m) {
-            uint32_t s, e;
-            if (I.uniform_k) {
-                s = c * I.uniform_k;
-                e = s + I.uniform_k;
-            } else {
-                s = __ldg(I.row_ptr + c);
-                e = __ldg(I.row_ptr + c + 1);
-            }
-            viol = 0xffffffffu;
-            for (uint32_t j = s; j < e && viol; j++) {
-                const uint32_t l = __ldg(I.lits + j);
-                const uint32_t av = __ldg(a + (l >> 1));
-                // literal false  <=>  value == neg bit
-                viol &= (l & 1u) ? av : ~av;
-            }
-        }
-        // transpose: word for assignment b = ballot over lanes (clauses) of bit b
-        uint32_t mine = 0;
+    const uint32_t* tq = tq_all + (size_t)slice * I.n * SLICE_Q;
+    const uint64_t b0 = (uint64_t)slice * SLICE_W;
+    const uint32_t valid = (uint32_t)min((uint64_t)SLICE_W, batch - b0);
+    const uint32_t ntiles = (I.mwords + TILE_WORDS - 1) / TILE_WORDS;
+    const uint32_t t_begin = blockIdx.x * tiles_per_block;
+    const uint32_t t_end = min(ntiles, t_begin + tiles_per_block);
+    uint32_t my_energy[SLICE_Q];  // lane b, entry q: energy of assignment b0 + 32q + b
 #pragma unroll
-        for (int b = 0; b < 32; b++) {
-            const uint32_t word = __ballot_sync(0xffffffffu, (viol >> b) & 1u);
-            if (lane == b) mine = word;
+    for (uint32_t q = 0; q < SLICE_Q; q++) my_energy[q] = 0;
+    // a warp owns a contiguous run of tiles, so the row pipeline runs through from its first to its last row
+    const uint32_t per_warp = tiles_per_block / WARPS;  // tiles_per_block is a multiple of WARPS
+    const uint32_t t0 = min(t_end, t_begin + warp * per_warp), t1 = min(t_end, t0 + per_warp);
+    ClauseRows rows(I, tq, t0 * TILE_WORDS * 32u + lane);
+    for (uint32_t t = t0; t < t1; t++) {
+#pragma unroll 1
+        for (uint32_t wi = 0; wi < TILE_WORDS; wi++) {
+            uint32_t viol[SLICE_Q];
+            rows.next(viol);
+            transpose32x8(viol, lane);
+#pragma unroll
+            for (uint32_t q = 0; q < SLICE_Q; q++) {
+                my_energy[q] += __popc(viol[q]);
+                if (OUT) stage[warp][32u * q + lane][wi] = viol[q];
+            }
         }
-        if ((uint32_t)lane < valid) {
-            if (vout) vout[(b0 + lane) * I.mwords + w] = mine;
-            my_energy += __popc(mine);
+        if (OUT) {
+            __syncwarp();
+            // one store instruction = 4 assignments x 8 words = four whole sectors
+            const uint32_t j = lane & 7u, w = t * TILE_WORDS + j;
+            for (uint32_t r = 0; r < SLICE_W / 4; r++) {
+                const uint32_t a = r * 4u + (lane >> 3);
+                if (a < valid && w < pitch) __stcs(vout + (b0 + a) * (size_t)pitch + w, stage[warp][a][j]);  // written once, never re-read here
+            }
+            __syncwarp();
         }
     }
-    if (energy && (uint32_t)lane < valid && my_energy) atomicAdd(energy + b0 + lane, my_energy);
+    if (energy) {
+#pragma unroll
+        for (uint32_t q = 0; q < SLICE_Q; q++) {
+            const uint32_t a = 32u * q + lane;
+            if (a < valid && my_energy[q]) atomicAdd(energy + b0 + a, my_energy[q]);
+        }
+    }
 }
 
 // Trajectory rows are written at a fixed pitch (nsteps+1) while a run needs only steps+1 entries

@@ -1,44 +1,47 @@
-// init_sliced.cuh -- chain initialisation for the HBM tier, 32 chains at a time.
+// init_sliced.cuh -- chain initialisation for the HBM tier, 256 chains at a time.
 //
 // Restates the reference's per-chain setup (rust/src/lib.rs:206-214: assignment[i] =
 // gen_bool(weights_initialize[i]); violated = find_violated_clauses(assignment), :176-181) for
 // instances whose chain state lives in HBM (BASELINE config 5: 4*10^6 clauses, 640 KB per chain).
 // Doing the full clause scan inside the walk kernel costs one literal fetch and k scattered
-// assignment reads per clause PER CHAIN.  Here a "slice" of 32 chains is processed together:
+// assignment reads per clause PER CHAIN.  Here a "slice" of SLICE_W = 256 chains is processed together
+// (same layout and clause evaluation as eval.cuh):
 //   init_assign_sliced_kernel : lane = chain; every lane evaluates its chain's Philox init stream,
-//                               a ballot per variable yields the transposed word tbits[slice][v]
-//                               (bit c = value of v in chain 32*slice + c) and 16 blocks yield the
+//                               a ballot per variable yields one word of the transposed tq[slice][v]
+//                               (8 words = the variable's value in the 256 chains) and 16 blocks yield the
 //                               chain's own abits word;
-//   init_scan_sliced_kernel   : lane = clause; one literal fetch + one tbits word per literal
-//                               evaluates the clause for 32 chains with bitwise ops, a 32x32
-//                               ballot transpose turns it into per-chain vbits words and level-1
-//                               counters (the streaming, bandwidth-bound form of lib.rs:176-181);
+//   init_scan_sliced_kernel   : lane = clause; one literal fetch + one 32-byte sector of tq per literal
+//                               evaluates the clause for 256 chains with bitwise ops, register transposes
+//                               turn 32x32 tiles into per-chain vbits words, staged in shared memory and
+//                               written as whole sectors, plus the level-1 counters (the streaming,
+//                               bandwidth-bound form of lib.rs:176-181);
 //   init_counters_kernel      : warp = chain; level-2 counters and the initial energy.
 // The walk kernel then starts from the prepared slab (WalkArgs::nf_init != nullptr).
 // Not used when the instance has duplicate clause contents (canonical ids need the atomic path).
 #pragma once
 #include "common.h"
+#include "eval.cuh"
 #include "philox.cuh"
 
 namespace slsb {
 
-// grid: (word chunks, slices in this launch); block: 128 threads = 4 warps, each warp owns whole
-// assignment words w (variables 32w .. 32w+31) of the slice's 32 chains.
-__global__ void __launch_bounds__(128) init_assign_sliced_kernel(const WalkArgs A, uint32_t* __restrict__ tbits, uint32_t slice0,
+// grid: (word chunks, slices in this launch); block: 8 warps, warp q owns chains 32q .. 32q+31 of the slice
+// and works through the block's assignment words w (variables 32w .. 32w+31).
+__global__ void __launch_bounds__(256) init_assign_sliced_kernel(const WalkArgs A, uint32_t* __restrict__ tq_all, uint32_t slice0,
                                                                  uint32_t words_per_block)
 {
     const DevInst& I = A.inst;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
     const uint32_t slice = slice0 + blockIdx.y;
-    const uint64_t run_raw = (uint64_t)slice * 32u + lane;
+    const uint64_t run_raw = (uint64_t)slice * SLICE_W + 32u * q + lane;
     const bool valid = run_raw < A.nruns;
     const uint64_t run = valid ? run_raw : A.nruns - 1;
     const ChainKey ck(A.seed, A.chain_offset + run, STREAM_INIT);
     uint32_t* abits = A.gstate + run * (size_t)I.slab_words;
-    uint32_t* tb = tbits + (size_t)blockIdx.y * I.n;
+    uint32_t* tq = tq_all + (size_t)blockIdx.y * I.n * SLICE_Q;
     const uint32_t w_begin = blockIdx.x * words_per_block;
     const uint32_t w_end = min(I.nwords, w_begin + words_per_block);
-    for (uint32_t w = w_begin + warp; w < w_end; w += 4) {
+    for (uint32_t w = w_begin; w < w_end; w++) {
         uint32_t bits = 0, tmine = 0;
 #pragma unroll 4
         for (uint32_t b = 0; b < 16; b++) {
@@ -60,57 +63,54 @@ __global__ void __launch_bounds__(128) init_assign_sliced_kernel(const WalkArgs 
         }
         if (valid) abits[w] = bits;
         const uint32_t v = w * 32u + lane;
-        if (v < I.n) tb[v] = tmine;  // one coalesced 128-byte store per assignment word
+        if (v < I.n) tq[(size_t)v * SLICE_Q + q] = tmine;  // the 8 warps of the block complete the sector of v
     }
 }
 
-// grid: (level-1 groups / 4, slices in this launch); each warp owns one level-1 group = 32 vbits
-// words = 1024 clauses and produces, for each of the slice's 32 chains, those 32 words and the counter.
-__global__ void __launch_bounds__(128) init_scan_sliced_kernel(const WalkArgs A, const uint32_t* __restrict__ tbits, uint32_t slice0)
+// grid: (level-1 groups / WARPS, slices in this launch); each warp owns one level-1 group = 32 vbits
+// words = 1024 clauses = 4 tiles and produces, for each of the slice's 256 chains, those words and the counter.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) init_scan_sliced_kernel(const WalkArgs A, const uint32_t* __restrict__ tq_all, uint32_t slice0)
 {
+    __shared__ uint32_t stage[WARPS][SLICE_W][TILE_WORDS + 1];
     const DevInst& I = A.inst;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t g = blockIdx.x * 4 + warp;
+    const uint32_t g = blockIdx.x * WARPS + warp;
     if (g >= I.ngroups) return;
     const uint32_t slice = slice0 + blockIdx.y;
-    const uint64_t run = (uint64_t)slice * 32u + lane;  // this lane's chain when it stores
-    const bool valid = run < A.nruns;
-    const uint32_t* tb = tbits + (size_t)blockIdx.y * I.n;
-    uint32_t* slab = A.gstate + (valid ? run : 0) * (size_t)I.slab_words;
-    uint32_t acc = 0;
-    const uint32_t wend = min(32u, I.mwords - g * 32u);
-    for (uint32_t wi = 0; wi < wend; wi++) {
-        const uint32_t w = g * 32u + wi;
-        const uint32_t c = w * 32u + lane;
-        uint32_t viol = 0;  // bit ch: clause c violated in chain 32*slice + ch
-        if (c < I.m) {
-            uint32_t s, e;
-            if (I.uniform_k) {
-                s = c * I.uniform_k;
-                e = s + I.uniform_k;
-            } else {
-                s = __ldg(I.row_ptr + c);
-                e = __ldg(I.row_ptr + c + 1);
-            }
-            viol = 0xffffffffu;  // empty clause: violated everywhere (lib.rs:13-18)
-            for (uint32_t j = s; j < e && viol; j++) {
-                const uint32_t l = __ldg(I.lits + j);
-                const uint32_t av = __ldg(tb + (l >> 1));
-                viol &= (l & 1u) ? av : ~av;  // literal false <=> value == neg bit
-            }
-        }
-        uint32_t mine = 0;  // transpose: lane ch collects the word of chain ch
+    const uint64_t run0 = (uint64_t)slice * SLICE_W;
+    const uint32_t valid = (uint32_t)min((uint64_t)SLICE_W, A.nruns - run0);
+    const uint32_t* tq = tq_all + (size_t)blockIdx.y * I.n * SLICE_Q;
+    uint32_t acc[SLICE_Q];  // lane b, entry q: violated clauses of chain run0 + 32q + b in this group
 #pragma unroll
-        for (int b = 0; b < 32; b++) {
-            const uint32_t word = __ballot_sync(0xffffffffu, (viol >> b) & 1u);
-            if (lane == b) mine = word;
+    for (uint32_t q = 0; q < SLICE_Q; q++) acc[q] = 0;
+    ClauseRows rows(I, tq, g * 1024u + lane);  // the 32 rows of the group, pipelined across its four tiles
+    for (uint32_t t = 0; t < 32 / TILE_WORDS; t++) {
+        const uint32_t w0 = g * 32u + t * TILE_WORDS;  // first vbits word of the tile (whole groups exist in the slab)
+#pragma unroll 1
+        for (uint32_t wi = 0; wi < TILE_WORDS; wi++) {
+            uint32_t viol[SLICE_Q];
+            rows.next(viol);
+            transpose32x8(viol, lane);
+#pragma unroll
+            for (uint32_t q = 0; q < SLICE_Q; q++) {
+                acc[q] += __popc(viol[q]);
+                stage[warp][32u * q + lane][wi] = viol[q];
+            }
         }
-        if (valid) {
-            slab[I.off_v + w] = mine;
-            acc += __popc(mine);
+        __syncwarp();
+        const uint32_t j = lane & 7u;
+        for (uint32_t r = 0; r < SLICE_W / 4; r++) {
+            const uint32_t a = r * 4u + (lane >> 3);
+            if (a < valid) __stcs(A.gstate + (run0 + a) * (size_t)I.slab_words + I.off_v + w0 + j, stage[warp][a][j]);
         }
+        __syncwarp();
     }
-    if (valid) slab[I.off_l1 + g] = acc;
+#pragma unroll
+    for (uint32_t q = 0; q < SLICE_Q; q++) {
+        const uint32_t a = 32u * q + lane;
+        if (a < valid) A.gstate[(run0 + a) * (size_t)I.slab_words + I.off_l1 + g] = acc[q];
+    }
 }
 
 // one warp per chain: level-2 counters and the initial number of violated clauses

@@ -143,6 +143,25 @@ def eval_assignments(inst: Instance, assignments, want_bits: bool = True):
     return violated, energy[:B]
 
 
+def eval_last_kernel_ms() -> float:
+    """Device time of this thread's last :func:`eval_assignments` (transposition + evaluation kernels, no copies)."""
+    return float(_lib.load().sls_eval_last_kernel_ms())
+
+
+def candidate_energies(inst: Instance, candidates) -> np.ndarray:
+    """Energies of a stack of candidate assignments as the training loader computes them
+    (python/src/data_utils.py:123-129: ``vmap(get_violated_constraints)`` over the candidates, summed and divided
+    by the number of clauses).  The Python problem drops empty clauses when it reads the CNF
+    (sat_instances.py:50); they are removed from both the count and the denominator here."""
+    _, energy = eval_assignments(inst, candidates, want_bits=False)
+    row, _ = inst.csr()
+    n_empty = int(np.count_nonzero(np.diff(row.astype(np.int64)) == 0))
+    m = inst.m - n_empty
+    if m == 0:
+        return np.zeros(len(energy), dtype=np.float32)
+    return ((energy.astype(np.int64) - n_empty) / m).astype(np.float32)
+
+
 def get_violated_constraints(inst: Instance, assignment) -> np.ndarray:
     """sat_representations.py:718-741: 1 for each violated clause, 0 otherwise."""
     v, _ = eval_assignments(inst, np.asarray(assignment)[None, :])

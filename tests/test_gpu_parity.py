@@ -86,6 +86,34 @@ def test_eval_ragged_batches_and_shapes():
     assert viol.tolist() == [[1, 0]] and energy.tolist() == [1]
 
 
+def test_eval_batches_spanning_slices_and_candidate_energies(expected):
+    # batches around the 256-assignment slice width, rows compared one by one with the oracle
+    rng = np.random.default_rng(5)
+    n, m = 300, 1300
+    clauses = random_ksat(n, m, 3, seed=77)
+    gi = eng.Instance.from_clauses(n, clauses)
+    oi = so.Instance.from_clauses(n, clauses)
+    for B in (255, 256, 257, 600):
+        a = rng.integers(0, 2, size=(B, n))
+        viol, energy = eng.eval_assignments(gi, a)
+        assert eng.eval_last_kernel_ms() > 0
+        for b in list(range(0, B, 37)) + [B - 1]:
+            assert (viol[b] == oi.eval_clauses(a[b])).all()
+        assert (viol.sum(axis=1) == energy).all()
+        _, e2 = eng.eval_assignments(gi, a, want_bits=False)  # energy-only mode
+        assert (e2 == energy).all()
+    # data_utils.py:123-130: candidate energies, the first candidate of every shipped file is the solution
+    for name, info in expected.items():
+        gi, _ = both(name)
+        rows = golden_assignments(name, gi.n)
+        e = eng.candidate_energies(gi, rows)
+        row, _ = gi.csr()
+        m_nonempty = int(np.count_nonzero(np.diff(row.astype(np.int64)) > 0))
+        want = (np.asarray(info["energies"]) - (gi.m - m_nonempty)) / m_nonempty
+        assert np.allclose(e, want.astype(np.float32))
+        assert e[0] == 0
+
+
 def test_eval_full_size_c2_properties():
     # BASELINE config 2 shape (n=10k, m=42k): size-independent properties
     n, m = 10_000, 42_000
@@ -370,6 +398,18 @@ def test_walk_more_than_65536_clauses_uses_second_counter_level(force, monkeypat
     for algo in ("probsat", "moser"):
         g = eng.run_sls(gi, algo, w, w, 400, 6, True, True, 0.0, seed=3)
         o = oi.run_sls(algo, w, w, 400, 6, True, True, 0.0, seed=3)
+        assert_same_run(g, o)
+
+
+def test_walk_hbm_tier_more_chains_than_one_slice(monkeypatch):
+    # the HBM tier initialises chains 256 at a time: 300 chains = one full slice + a partial one
+    monkeypatch.setenv("SLS_B200_FORCE_STATE", "hbm")
+    name = "r3sat_test_random_KCNF3_200_869_9397183"
+    gi, oi = both(name)
+    w = np.random.default_rng(2).uniform(0.1, 0.9, gi.n)
+    for algo in ("probsat", "moser"):
+        g = eng.run_sls(gi, algo, w, w, 60, 300, True, True, 0.0, seed=12)
+        o = oi.run_sls(algo, w, w, 60, 300, True, True, 0.0, seed=12)
         assert_same_run(g, o)
 
 
