@@ -446,3 +446,25 @@ def test_trajectory_statistics_match_numpy_protocol():
         assert np.allclose(mean, padded.mean(axis=0), rtol=0, atol=1e-12)
         assert (median == np.median(padded, axis=0)).all()
         s.close()
+
+
+def test_repeated_calls_do_not_leak_device_memory():
+    # every call allocates and frees its working set through the stream-ordered pool (csrc/devmem.h)
+    import torch
+
+    torch.cuda.mem_get_info()  # creates torch's context before the baseline is taken
+    gi, _ = both("r3sat_test_random_KCNF3_200_869_9397183")
+    w = np.full(gi.n, 0.5)
+    path = golden_cnf("r3sat_test_random_KCNF3_200_869_9397183")
+    import moser_rust
+
+    for i in range(3):
+        eng.run_sls(gi, "probsat", w, w, 50, 64, True, True, 0.0, seed=i)
+        moser_rust.run_sls_python("moser", path, w, w, 50, 64, False, True, 0)
+    free0, _ = torch.cuda.mem_get_info()
+    for i in range(40):
+        eng.run_sls(gi, "probsat", w, w, 50, 64, True, True, 0.0, seed=i)
+        moser_rust.run_sls_python("moser", path, w, w, 50, 64, False, True, 0)
+        eng.eval_assignments(gi, np.zeros((70, gi.n), dtype=np.uint8))
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < (64 << 20), (free0, free1)
