@@ -468,3 +468,53 @@ def test_repeated_calls_do_not_leak_device_memory():
         eng.eval_assignments(gi, np.zeros((70, gi.n), dtype=np.uint8))
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < (64 << 20), (free0, free1)
+
+
+def _fuzz_instance(rng):
+    """Small random formulas covering every shape the kernels distinguish: pure 3-SAT (fast kernel), mixed short
+    clauses, long clauses, duplicate clause contents, a variable twice in a clause (also with both signs)."""
+    kind = rng.integers(0, 5)
+    n = int(rng.integers(1, 60))
+    m = int(rng.integers(1, 220))
+    clauses = []
+    for _ in range(m):
+        if kind == 0:
+            k = min(3, n)
+        elif kind == 1:
+            k = int(rng.integers(1, min(3, n) + 1))
+        else:
+            k = int(rng.integers(1, min(9, n) + 1))
+        vs = rng.choice(n, size=k, replace=False) + 1
+        c = [int(v) * (1 if rng.integers(0, 2) else -1) for v in vs]
+        if kind == 3 and rng.random() < 0.2:
+            c.append(c[0] if rng.random() < 0.5 else -c[0])  # repeated variable
+        clauses.append(tuple(c))
+        if kind >= 3 and rng.random() < 0.15:
+            clauses.append(tuple(c))  # duplicate content
+    return n, clauses
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_walk_fuzz_against_oracle(seed):
+    rng = np.random.default_rng(1000 + seed)
+    for case in range(8):
+        n, clauses = _fuzz_instance(rng)
+        gi = eng.Instance.from_clauses(n, clauses)
+        oi = so.Instance.from_clauses(n, clauses)
+        algo = ALGOS[int(rng.integers(0, 4))]
+        pfb = float(rng.choice([0.0, 0.0, 0.3, 1.0]))
+        mapping = bool(rng.integers(0, 2))
+        w_init = rng.uniform(0, 1, n)
+        w_res = rng.uniform(0.02, 0.98, n)
+        if rng.random() < 0.3:
+            w_init[rng.integers(0, n)] = float(rng.integers(0, 2))  # exact 0 / 1 initial probabilities
+        nsteps, nruns = int(rng.integers(0, 400)), int(rng.integers(1, 40))
+        sd = int(rng.integers(0, 2**62))
+        g = eng.run_sls(gi, algo, w_init, w_res, nsteps, nruns, True, mapping, pfb, seed=sd)
+        o = oi.run_sls(algo, w_init, w_res, nsteps, nruns, True, mapping, pfb, seed=sd)
+        assert_same_run(g, o)
+        a = rng.integers(0, 2, size=(int(rng.integers(1, 300)), n))
+        viol, energy = eng.eval_assignments(gi, a)
+        for b in (0, len(a) - 1):
+            assert (viol[b] == oi.eval_clauses(a[b])).all()
+            assert energy[b] == oi.energy(a[b])
