@@ -19,6 +19,7 @@
 #include "instance.h"
 #include "walk_generic.cuh"
 #include "walk_k3.cuh"
+#include "walk_k3h.cuh"
 
 using namespace slsb;
 
@@ -357,7 +358,8 @@ struct sls_solver {
     sls_run_params p{};
     WalkArgs args{};
     bool smem_state = false;
-    bool k3 = false;
+    bool k3 = false;   // walk_k3s: k<=3, state in shared memory
+    bool k3h = false;  // walk_k3h: k<=3, state in HBM
     uint32_t wpb = 4;
     size_t smem_bytes = 0;
     int device = 0;
@@ -469,11 +471,18 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     s->k3 = (I.flags & INST_K3) != 0 && s->smem_state && I.l1_pad == 64;
     if (const char* f = std::getenv("SLS_B200_FORCE_GENERIC"))
         if (f[0] == '1') s->k3 = false;
-    s->variant = s->k3 ? "walk_k3s<smem>" : std::string("walk_generic<") + (s->smem_state ? "smem" : "hbm") + ">";
+    // ... and its HBM-state sibling: same records, the slab prepared by the sliced init kernels (which need distinct
+    // clause contents -- guaranteed for k<=3 instances -- and a non-empty formula), at most 64 x 64 level-1 counters
+    s->k3h = (I.flags & INST_K3) != 0 && !s->smem_state && I.n > 0 && I.m > 0 && I.l1_pad <= 64u * 64u &&
+             (I.l2_pad == 0 || I.l2_pad == 64);
+    if (const char* f = std::getenv("SLS_B200_FORCE_GENERIC"))
+        if (f[0] == '1') s->k3h = false;
+    if (s->k3h) s->smem_bytes = size_t(s->wpb) * K3H_SMEM_WORDS * 4;  // random-word ring + level-2 counters per chain
+    s->variant = s->k3 ? "walk_k3s<smem>" : s->k3h ? "walk_k3h<hbm>" : std::string("walk_generic<") + (s->smem_state ? "smem" : "hbm") + ">";
 
     SC_TRY(dmalloc(&s->d_thr, std::max<size_t>(I.n, 1) * 8));
     SC_TRY(dmalloc(&s->d_w, std::max<size_t>(I.n, 1) * 8));
-    if (s->k3) SC_TRY(dmalloc(&s->d_crecx, std::max<size_t>(I.m, 1) * CRECX_QUADS * sizeof(uint4)));
+    if (s->k3 || s->k3h) SC_TRY(dmalloc(&s->d_crecx, std::max<size_t>(I.m, 1) * CRECX_QUADS * sizeof(uint4)));
     if (!s->smem_state) SC_TRY(dmalloc(&s->d_gstate, R1 * slab_bytes));
     SC_TRY(dmalloc(&s->d_best_bits, R1 * std::max<size_t>(I.nwords, 1) * 4));
     if (!s->smem_state && !(I.flags & INST_HAS_DUPLICATES) && I.n > 0 && I.m > 0) {
@@ -626,6 +635,8 @@ extern "C" int sls_solver_launch(sls_solver* s, void* cuda_stream)
     const bool use_k3 = s->k3 && walk_k3_supports(s->args);
     if (use_k3) {
         walk_k3s_kernel_for(s->p.algo, s->p.prob_flip_best, s->p.return_trajectories != 0)<<<blocks, threads, s->smem_bytes, st>>>(s->args);
+    } else if (s->k3h && walk_k3h_supports(s->args)) {
+        walk_k3h_kernel_for(s->p.algo, s->p.prob_flip_best, s->p.return_trajectories != 0)<<<blocks, threads, s->smem_bytes, st>>>(s->args);
     } else {
         if (s->smem_state)
             walk_generic_kernel<true><<<blocks, threads, s->smem_bytes, st>>>(s->args);
