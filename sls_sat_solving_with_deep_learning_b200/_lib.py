@@ -15,10 +15,13 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "lib", "libsls_b200.so")
 _SOURCES = ["csrc/api.cu", "csrc/gnn_api.cu", "csrc/instance.cpp"]
-_HEADERS = [
-    "csrc/common.h", "csrc/philox.cuh", "csrc/instance.h", "csrc/eval.cuh", "csrc/walk_generic.cuh",
-    "csrc/walk_k3.cuh", "csrc/init_sliced.cuh", "csrc/gnn_kernels.cuh", "../include/sls_b200.h",
-]
+def _headers():
+    """Every header the library is built from (staleness check): all of csrc/ plus the public C header."""
+    import glob
+
+    hs = sorted(glob.glob(os.path.join(_PKG, "csrc", "*.h")) + glob.glob(os.path.join(_PKG, "csrc", "*.cuh")))
+    return [os.path.relpath(h, _PKG) for h in hs] + ["../include/sls_b200.h"]
+
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -41,7 +44,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(os.path.join(_PKG, f)) > t for f in _SOURCES + _HEADERS)
+    return any(os.path.getmtime(os.path.join(_PKG, f)) > t for f in _SOURCES + _headers())
 
 
 def build_native(force: bool = False, verbose: bool = False) -> str:

@@ -163,18 +163,31 @@ __device__ __forceinline__ void walk_k3h_body(const WalkArgs& A, uint32_t block,
             const uint32_t a0 = q0.x & 1u, a1 = q0.y & 1u, a2 = q0.z & 1u;
 
             // re-evaluation of every clause of a flipped variable (lib.rs:278-287), one occurrence record per lane
-            auto update_var = [&](uint32_t os, uint32_t len, uint32_t av) {
+            auto update_var = [&](uint32_t os, uint32_t len, uint32_t av, bool single) {
                 for (uint32_t base = 0; base < len; base += 32) {
                     const uint32_t o = base + lane;
                     const bool act = o < len;
                     const uint4 orc = __ldg(orec + os + min(o, len - 1u));  // past the end: the last record again, masked
                     uint32_t* const va = pV + (orc.x >> 5);
-                    const uint32_t vword = __ldcg(va);
                     const uint32_t bit = 1u << (orc.x & 31);
-                    const bool viol = act & (av == orc.w) & !(lit_true(orc.y) | lit_true(orc.z));
-                    const bool cur = act & ((vword & bit) != 0);
-                    const bool ins = viol && !cur;  // HashSet::insert of a new element
-                    const bool rem = !viol && cur;  // HashSet::remove of a present element
+                    // Every read here is a random sector of HBM, so only the needed ones are made.  The variable's
+                    // literal in this clause either became true -- the clause is satisfied now, and it can only
+                    // have been in the violated set before (one read of vbits) -- or became false: then the clause
+                    // was satisfied by it before, i.e. not in the set, and it enters the set iff the other two
+                    // literals are false (two reads of abits).  1.5 reads per occurrence instead of 3.
+                    // (Only when this is the step's single flip: with several flips the set may already have been
+                    // updated for this clause by an earlier variable of the same step.)
+                    bool rem = false, ins = false;  // HashSet::remove of a present element / insert of a new one
+                    if (single) {
+                        const bool now_true = act & (av != orc.w), now_false = act & (av == orc.w);
+                        if (now_true) rem = (__ldcg(va) & bit) != 0;
+                        if (now_false) ins = !(lit_true(orc.y) | lit_true(orc.z));
+                    } else {
+                        const bool viol = act & (av == orc.w) & !(lit_true(orc.y) | lit_true(orc.z));
+                        const bool cur = act & ((__ldcg(va) & bit) != 0);
+                        ins = viol && !cur;
+                        rem = !viol && cur;
+                    }
                     if (ins | rem) {
                         const uint32_t delta = ins ? 1u : 0xffffffffu;
                         red_xor(va, bit);
@@ -213,7 +226,7 @@ __device__ __forceinline__ void walk_k3h_body(const WalkArgs& A, uint32_t block,
                     for (uint32_t mk = marks; mk; mk &= mk - 1) {
                         const uint32_t j = ffs0(mk);
                         update_var(selp(j == 0, q1.x, selp(j == 1, q1.z, q2.x)), selp(j == 0, q1.y, selp(j == 1, q1.w, q2.y)),
-                                   selp(j == 0, a0, selp(j == 1, a1, a2)) ^ 1u);
+                                   selp(j == 0, a0, selp(j == 1, a1, a2)) ^ 1u, (marks & (marks - 1)) == 0);
                     }
                 }
             } else {
@@ -271,7 +284,7 @@ __device__ __forceinline__ void walk_k3h_body(const WalkArgs& A, uint32_t block,
                     const uint32_t lit = selp(j == 0, q0.x, selp(j == 1, q0.y, q0.z));
                     toggle(lit);  // lib.rs:37-41 (the re-evaluation never reads the flipped variable itself)
                     if (COUNT_FLIPS) flips++;
-                    update_var(selp(j == 0, q1.x, selp(j == 1, q1.z, q2.x)), selp(j == 0, q1.y, selp(j == 1, q1.w, q2.y)), (lit & 1u) ^ 1u);
+                    update_var(selp(j == 0, q1.x, selp(j == 1, q1.z, q2.x)), selp(j == 0, q1.y, selp(j == 1, q1.w, q2.y)), (lit & 1u) ^ 1u, true);
                 }
             }
 
