@@ -370,6 +370,8 @@ struct sls_solver {
     uint64_t* d_thr = nullptr;
     double* d_w = nullptr;
     uint4* d_crecx = nullptr;
+    double* d_ftab = nullptr;    // generic kernel: static flip tables (build_flip_tables_kernel)
+    double* d_cscale = nullptr;
     uint32_t* d_gstate = nullptr;
     uint32_t* d_best_bits = nullptr;
     uint32_t* d_flip_log = nullptr;
@@ -396,6 +398,8 @@ extern "C" void sls_solver_free(sls_solver* s)
     dfree(s->d_thr);
     dfree(s->d_w);
     dfree(s->d_crecx);
+    dfree(s->d_ftab);
+    dfree(s->d_cscale);
     dfree(s->d_gstate);
     dfree(s->d_best_bits);
     dfree(s->d_flip_log);
@@ -483,6 +487,10 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     SC_TRY(dmalloc(&s->d_thr, std::max<size_t>(I.n, 1) * 8));
     SC_TRY(dmalloc(&s->d_w, std::max<size_t>(I.n, 1) * 8));
     if (s->k3 || s->k3h) SC_TRY(dmalloc(&s->d_crecx, std::max<size_t>(I.m, 1) * CRECX_QUADS * sizeof(uint4)));
+    if (!(s->k3 || s->k3h) && params->algo != SLS_ALGO_SCHOENING) {
+        SC_TRY(dmalloc(&s->d_ftab, std::max<size_t>(inst->host.lits.size(), 1) * 8));
+        SC_TRY(dmalloc(&s->d_cscale, std::max<size_t>(I.m, 1) * 8));
+    }
     if (!s->smem_state) SC_TRY(dmalloc(&s->d_gstate, R1 * slab_bytes));
     SC_TRY(dmalloc(&s->d_best_bits, R1 * std::max<size_t>(I.nwords, 1) * 4));
     if (!s->smem_state && !(I.flags & INST_HAS_DUPLICATES) && I.n > 0 && I.m > 0) {
@@ -525,6 +533,8 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     a.thr_init = s->d_thr;
     a.w = s->d_w;
     a.crecx = s->d_crecx;
+    a.ftab = s->d_ftab;
+    a.cscale = s->d_cscale;
     a.algo = params->algo;
     a.mapping = params->pre_compute_mapping;
     a.want_traj = params->return_trajectories;
@@ -594,6 +604,12 @@ extern "C" int sls_solver_set_weights(sls_solver* s, const double* w_init, size_
         // 64-byte clause records of the k<=3 kernel: literals + occurrence ranges + resample weights
         const DevInst& I = s->inst->dev;
         build_crecx_kernel<<<(I.m + 255) / 256, 256>>>(I.crec, I.occ_ptr, s->d_w, s->d_crecx, I.m, I.n, s->p.algo);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    if (s->d_ftab && s->inst->host.m) {
+        const DevInst& I = s->inst->dev;
+        build_flip_tables_kernel<<<(I.m + 127) / 128, 128>>>(I, s->d_w, s->p.algo, s->d_ftab, s->d_cscale);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaDeviceSynchronize());
     }
@@ -837,7 +853,7 @@ struct ItemPlan {
     uint32_t wpb = 4;
     size_t smem_bytes = 0;
     // element offsets into the pools
-    size_t off_n = 0, off_bits = 0, off_run = 0, off_crecx = 0, off_gstate = 0;
+    size_t off_n = 0, off_bits = 0, off_run = 0, off_crecx = 0, off_gstate = 0, off_ftab = 0, off_cscale = 0;
 };
 
 }  // namespace
@@ -867,7 +883,7 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
 
     // ---- plan: kernel variant and pool offsets per instance
     std::vector<ItemPlan> plan(n_inst);
-    size_t tot_n = 0, tot_bits = 0, tot_run = 0, tot_crecx = 0, tot_gstate = 0;
+    size_t tot_n = 0, tot_bits = 0, tot_run = 0, tot_crecx = 0, tot_gstate = 0, tot_ftab = 0, tot_cscale = 0;
     const bool force_generic = [] { const char* f = std::getenv("SLS_B200_FORCE_GENERIC"); return f && f[0] == '1'; }();
     const char* force_state = std::getenv("SLS_B200_FORCE_STATE");
     for (uint32_t i = 0; i < n_inst; i++) {
@@ -888,6 +904,11 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         tot_bits += R * std::max<uint32_t>(I.nwords, 1);
         tot_run += R;
         if (pl.k3) tot_crecx += size_t(I.m) * CRECX_QUADS;
+        pl.off_ftab = tot_ftab, pl.off_cscale = tot_cscale;
+        if (!pl.k3 && params->algo != SLS_ALGO_SCHOENING) {
+            tot_ftab += insts[i]->host.lits.size();
+            tot_cscale += I.m;
+        }
         if (!pl.smem) tot_gstate += R * size_t(I.slab_words);
     }
 
@@ -915,7 +936,7 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         wflags[i] = interior ? WF_INTERIOR : 0u;
     }
 
-    Pool p_thr, p_w, p_crecx, p_bits, p_found, p_hasbest, p_steps, p_flips, p_best, p_gstate, p_err, p_items, p_cta;
+    Pool p_thr, p_w, p_crecx, p_ftab, p_cscale, p_bits, p_found, p_hasbest, p_steps, p_flips, p_best, p_gstate, p_err, p_items, p_cta;
     auto alloc = [&](Pool& p, size_t bytes) -> cudaError_t {
         p.size = std::max<size_t>(bytes, 16);
         return dmalloc(&p.base, p.size);
@@ -923,6 +944,8 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     CUDA_TRY(alloc(p_thr, tot_n * 8));
     CUDA_TRY(alloc(p_w, tot_n * 8));
     CUDA_TRY(alloc(p_crecx, tot_crecx * sizeof(uint4)));
+    CUDA_TRY(alloc(p_ftab, tot_ftab * 8));
+    CUDA_TRY(alloc(p_cscale, tot_cscale * 8));
     CUDA_TRY(alloc(p_bits, tot_bits * 4));
     CUDA_TRY(alloc(p_found, tot_run));
     CUDA_TRY(alloc(p_hasbest, tot_run));
@@ -966,6 +989,13 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         a.flips = reinterpret_cast<uint64_t*>(p_flips.base) + pl.off_run;
         a.traj = nullptr;
         a.err = reinterpret_cast<int32_t*>(p_err.base) + i;
+        if (!pl.k3 && params->algo != SLS_ALGO_SCHOENING) {
+            a.ftab = reinterpret_cast<double*>(p_ftab.base) + pl.off_ftab;
+            a.cscale = reinterpret_cast<double*>(p_cscale.base) + pl.off_cscale;
+            if (I.m)
+                build_flip_tables_kernel<<<(I.m + 127) / 128, 128>>>(I, a.w, params->algo, const_cast<double*>(a.ftab),
+                                                                     const_cast<double*>(a.cscale));
+        }
         if (pl.k3 && I.m)
             build_crecx_kernel<<<(I.m + 255) / 256, 256>>>(I.crec, I.occ_ptr, a.w, const_cast<uint4*>(a.crecx), I.m, I.n, params->algo);
         const int g = pl.k3 ? 0 : pl.smem ? 1 : 2;

@@ -45,7 +45,9 @@ struct WalkArgs {
     DevInst inst;
     const uint64_t* thr_init;  // [n] Bernoulli thresholds of weights_initialize (lib.rs:208-210)
     const double* w;           // [n] weights_resample
-    const uint4* crecx;        // [m][6] 96-byte clause record of the k<=3 path (walk_k3.cuh) or nullptr
+    const uint4* crecx;        // [m][4] 64-byte clause record of the k<=3 kernels (walk_k3.cuh) or nullptr
+    const double* ftab;        // [L]  generic kernel: per literal position, MT rules: flip probability; probSAT: running sum
+    const double* cscale;      // [m]  generic kernel, probSAT: UniformFloat scale of the clause, or -(error code)
     int32_t algo;
     int32_t mapping;           // pre_compute_mapping (only changes the greedy score, lib.rs:242-250)
     int32_t want_traj;

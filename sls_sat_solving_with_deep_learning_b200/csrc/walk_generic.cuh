@@ -265,6 +265,51 @@ struct Chain {
 // flip probability of lib.rs:29-30: (1-a)*w + a*(1-w)
 __device__ __forceinline__ double flip_prob(uint32_t a, double w) { return a ? (1.0 - w) : w; }
 
+// The flip rules only ever look at a VIOLATED clause, whose literals are all false: the value of a variable is
+// its literal's negation bit, so the flip probabilities (lib.rs:29-30) are a static property of the literal
+// position (see build_crecx_kernel in walk_k3.cuh for the k<=3 form).  One thread per clause, the same double
+// operations in the same order as WeightedIndex::new / UniformFloat::new (lib.rs:71-72):
+//   MT rules:  ftab[s+j] = flip probability of literal j
+//   probSAT:   ftab[s+j] = sum of the flip probabilities of literals 0..j, cscale[c] = UniformFloat's scale, or
+//              -(DERR_WEIGHTS | DERR_ALL_ZERO) when WeightedIndex::new fails on this clause
+__global__ void build_flip_tables_kernel(const DevInst I, const double* __restrict__ w, int algo, double* __restrict__ ftab,
+                                         double* __restrict__ cscale)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= I.m) return;
+    uint32_t s, e;
+    if (I.uniform_k) {
+        s = c * I.uniform_k;
+        e = s + I.uniform_k;
+    } else {
+        s = I.row_ptr[c];
+        e = I.row_ptr[c + 1];
+    }
+    double run = 0.0;
+    bool invalid = false;
+    for (uint32_t j = s; j < e; j++) {
+        const uint32_t l = I.lits[j];
+        const double fp = flip_prob(l & 1u, w[l >> 1]);
+        if (algo == ALGO_PROBSAT) {
+            invalid |= !(fp >= 0.0);
+            run = (j == s) ? fp : run + fp;
+            ftab[j] = run;
+        } else {
+            ftab[j] = fp;
+        }
+    }
+    if (algo == ALGO_PROBSAT) {
+        double scale = run;
+        if (invalid)
+            scale = -(double)DERR_WEIGHTS;
+        else if (run == 0.0)
+            scale = -(double)DERR_ALL_ZERO;  // also the empty clause; the walk reports that one first
+        else
+            while (scale * (1.0 - 0x1p-52) >= run) scale = __longlong_as_double(__double_as_longlong(scale) - 1);
+        cscale[c] = scale;
+    }
+}
+
 template <bool SMEM>
 __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t block, uint32_t* smem_state)
 {
@@ -379,11 +424,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
             for (uint32_t cb = 0; cb < k; cb += 32) {
                 const uint32_t j = cb + lane;
                 bool mark = false;
-                if (j < k) {
-                    const uint32_t v = __ldg(I.lits + s + j) >> 1;
-                    const double fp = flip_prob(ch.abit(v), __ldg(A.w + v));
-                    mark = u64_to_f64_53(rng.ck.u64_at(p0 + 2ull * j)) < fp;
-                }
+                if (j < k) mark = u64_to_f64_53(rng.ck.u64_at(p0 + 2ull * j)) < __ldg(A.ftab + s + j);
                 const uint32_t mask = __ballot_sync(FULL, mark);
                 if ((uint32_t)lane == (cb >> 5)) mark_mask = mask;
                 nmarks += __popc(mask);
@@ -446,53 +487,18 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
                 err = DERR_EMPTY_CLAUSE;
                 break;
             }
-            // pass 1: total weight, summed in literal order like WeightedIndex::new
-            double total = 0.0;
-            bool invalid = false;
-            for (uint32_t cb = 0; cb < k; cb += 32) {
-                const uint32_t j = cb + lane;
-                double fp = 0.0;
-                if (j < k) {
-                    const uint32_t v = __ldg(I.lits + s + j) >> 1;
-                    fp = flip_prob(ch.abit(v), __ldg(A.w + v));
-                    invalid |= !(fp >= 0.0);
-                }
-                const uint32_t cnt = min(32u, k - cb);
-                for (uint32_t t = 0; t < cnt; t++) {
-                    const double f = __shfl_sync(FULL, fp, t);
-                    total = (cb + t == 0) ? f : total + f;
-                }
-            }
-            if (__any_sync(FULL, invalid)) {
-                err = DERR_WEIGHTS;
+            // WeightedIndex::new's verdict and UniformFloat's scale come precomputed (build_flip_tables_kernel)
+            const double scale = __ldg(A.cscale + c);
+            if (!(scale > 0.0)) {
+                err = (int)(-scale);
                 break;
             }
-            if (total == 0.0) {
-                err = DERR_ALL_ZERO;
-                break;
-            }
-            // UniformFloat::new(0, total) then sample from 52 mantissa bits
-            double scale = total;
-            while (scale * (1.0 - 0x1p-52) >= total) scale = __longlong_as_double(__double_as_longlong(scale) - 1);
+            // sample from 52 mantissa bits, then partition_point(cum <= x) over the first k-1 running sums
             const double x = ((double)(rng.next_u64() >> 12) * 0x1p-52) * scale;
-            // pass 2: partition_point(cum <= x) over the first k-1 cumulative weights
             uint32_t pick = 0;
-            double run_sum = 0.0;
-            for (uint32_t cb = 0; cb < k; cb += 32) {
+            for (uint32_t cb = 0; cb + 1 < k; cb += 32) {
                 const uint32_t j = cb + lane;
-                double fp = 0.0;
-                if (j < k) {
-                    const uint32_t v = __ldg(I.lits + s + j) >> 1;
-                    fp = flip_prob(ch.abit(v), __ldg(A.w + v));
-                }
-                double mycum = 0.0;
-                const uint32_t cnt = min(32u, k - cb);
-                for (uint32_t t = 0; t < cnt; t++) {
-                    const double f = __shfl_sync(FULL, fp, t);
-                    run_sum = (cb + t == 0) ? f : run_sum + f;
-                    if ((uint32_t)lane == t) mycum = run_sum;
-                }
-                pick += __popc(__ballot_sync(FULL, j + 1 < k && mycum <= x));
+                pick += __popc(__ballot_sync(FULL, j + 1 < k && __ldg(A.ftab + s + j) <= x));
             }
             const uint32_t v = __ldg(I.lits + s + pick) >> 1;
             if (lane == 0) ch.abits[v >> 5] ^= 1u << (v & 31);
