@@ -521,7 +521,7 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     SC_TRY(cudaEventCreate(&s->ev0));
     SC_TRY(cudaEventCreate(&s->ev1));
     if (s->smem_bytes) {
-        SC_TRY(cudaFuncSetAttribute(walk_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SC_TRY(cudaFuncSetAttribute(walk_generic_kernel_for<true>(params->algo), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)s->smem_bytes));
         SC_TRY(cudaFuncSetAttribute(walk_k3s_kernel_for(params->algo, params->prob_flip_best, params->return_trajectories != 0),
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
@@ -655,9 +655,9 @@ extern "C" int sls_solver_launch(sls_solver* s, void* cuda_stream)
         walk_k3h_kernel_for(s->p.algo, s->p.prob_flip_best, s->p.return_trajectories != 0)<<<blocks, threads, s->smem_bytes, st>>>(s->args);
     } else {
         if (s->smem_state)
-            walk_generic_kernel<true><<<blocks, threads, s->smem_bytes, st>>>(s->args);
+            walk_generic_kernel_for<true>(s->p.algo)<<<blocks, threads, s->smem_bytes, st>>>(s->args);
         else
-            walk_generic_kernel<false><<<blocks, threads, 0, st>>>(s->args);
+            walk_generic_kernel_for<false>(s->p.algo)<<<blocks, threads, 0, st>>>(s->args);
     }
     s->launches += 1;
     CUDA_TRY(cudaGetLastError());
@@ -1021,7 +1021,7 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     const WalkK3BatchKernel k3_batch = walk_k3s_batch_kernel_for(params->algo, params->prob_flip_best);
     if (smem_max[0]) CUDA_TRY(cudaFuncSetAttribute(k3_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[0]));
     if (smem_max[1])
-        CUDA_TRY(cudaFuncSetAttribute(walk_generic_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[1]));
+        CUDA_TRY(cudaFuncSetAttribute(walk_generic_batch_kernel_for<true>(params->algo), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[1]));
     CUDA_TRY(cudaEventRecord(ev0));
     for (int g = 0; g < 3; g++) {
         if (items[g].empty()) continue;
@@ -1031,9 +1031,9 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         if (g == 0)
             k3_batch<<<blocks, 128, smem_max[0]>>>(di, dc, ni);
         else if (g == 1)
-            walk_generic_batch_kernel<true><<<blocks, 128, smem_max[1]>>>(di, dc, ni);
+            walk_generic_batch_kernel_for<true>(params->algo)<<<blocks, 128, smem_max[1]>>>(di, dc, ni);
         else
-            walk_generic_batch_kernel<false><<<blocks, 128, 0>>>(di, dc, ni);
+            walk_generic_batch_kernel_for<false>(params->algo)<<<blocks, 128, 0>>>(di, dc, ni);
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev1));

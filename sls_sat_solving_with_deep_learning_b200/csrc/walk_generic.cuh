@@ -310,7 +310,8 @@ __global__ void build_flip_tables_kernel(const DevInst I, const double* __restri
     }
 }
 
-template <bool SMEM>
+// ALGO is compile-time: every instantiation carries only its own flip rule (fewer registers, shorter loop)
+template <bool SMEM, int ALGO>
 __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t block, uint32_t* smem_state)
 {
     const int lane = threadIdx.x & 31;
@@ -413,7 +414,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
             flips++;
             log_flip(best_v);
             ch.update_var(best_v);
-        } else if (A.algo == ALGO_MOSER || A.algo == ALGO_MOSER_SINGLE) {
+        } else if (ALGO == ALGO_MOSER || ALGO == ALGO_MOSER_SINGLE) {
             // ---- lib.rs:24-35 / :81-92: one f64 per literal, in literal order
             if (k > 1024) {
                 err = DERR_ARG;
@@ -429,7 +430,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
                 if ((uint32_t)lane == (cb >> 5)) mark_mask = mask;
                 nmarks += __popc(mask);
             }
-            if (A.algo == ALGO_MOSER) {
+            if (ALGO == ALGO_MOSER) {
                 // lib.rs:37-41: toggle every marked variable (a variable marked twice toggles twice)
                 for (uint32_t cb = 0; cb < k; cb += 32) {
                     const uint32_t mask = __shfl_sync(FULL, mark_mask, cb >> 5);
@@ -469,7 +470,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
                 log_flip(v);
                 ch.update_var(v);
             }
-        } else if (A.algo == ALGO_SCHOENING) {
+        } else if (ALGO == ALGO_SCHOENING) {
             // ---- lib.rs:51-55
             if (k == 0) {
                 err = DERR_EMPTY_CLAUSE;
@@ -532,11 +533,11 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
     }
 }
 
-template <bool SMEM>
+template <bool SMEM, int ALGO>
 __global__ void __launch_bounds__(128, 4) walk_generic_kernel(const WalkArgs A)
 {
     extern __shared__ uint32_t smem_state[];
-    walk_generic_body<SMEM>(A, blockIdx.x, smem_state);
+    walk_generic_body<SMEM, ALGO>(A, blockIdx.x, smem_state);
 }
 
 // Batched form: many instances in one launch.  cta_begin[i] = first CTA of item i (n_items + 1
@@ -560,7 +561,7 @@ __device__ __forceinline__ void load_item(WalkArgs& dst, const WalkArgs* src)
     __syncthreads();
 }
 
-template <bool SMEM>
+template <bool SMEM, int ALGO>
 __global__ void __launch_bounds__(128, 4) walk_generic_batch_kernel(const WalkArgs* __restrict__ items, const uint32_t* __restrict__ cta_begin,
                                                                  uint32_t n_items)
 {
@@ -568,7 +569,31 @@ __global__ void __launch_bounds__(128, 4) walk_generic_batch_kernel(const WalkAr
     __shared__ WalkArgs item;
     const uint32_t it = find_item(cta_begin, n_items, blockIdx.x);
     load_item(item, items + it);
-    walk_generic_body<SMEM>(item, blockIdx.x - __ldg(cta_begin + it), smem_state);
+    walk_generic_body<SMEM, ALGO>(item, blockIdx.x - __ldg(cta_begin + it), smem_state);
+}
+
+// Host-side choice of the instantiation.
+using WalkGenericKernel = void (*)(const WalkArgs);
+using WalkGenericBatchKernel = void (*)(const WalkArgs*, const uint32_t*, uint32_t);
+template <bool SMEM>
+inline WalkGenericKernel walk_generic_kernel_for(int algo)
+{
+    switch (algo) {
+        case ALGO_MOSER: return walk_generic_kernel<SMEM, ALGO_MOSER>;
+        case ALGO_MOSER_SINGLE: return walk_generic_kernel<SMEM, ALGO_MOSER_SINGLE>;
+        case ALGO_SCHOENING: return walk_generic_kernel<SMEM, ALGO_SCHOENING>;
+        default: return walk_generic_kernel<SMEM, ALGO_PROBSAT>;
+    }
+}
+template <bool SMEM>
+inline WalkGenericBatchKernel walk_generic_batch_kernel_for(int algo)
+{
+    switch (algo) {
+        case ALGO_MOSER: return walk_generic_batch_kernel<SMEM, ALGO_MOSER>;
+        case ALGO_MOSER_SINGLE: return walk_generic_batch_kernel<SMEM, ALGO_MOSER_SINGLE>;
+        case ALGO_SCHOENING: return walk_generic_batch_kernel<SMEM, ALGO_SCHOENING>;
+        default: return walk_generic_batch_kernel<SMEM, ALGO_PROBSAT>;
+    }
 }
 
 }  // namespace slsb
