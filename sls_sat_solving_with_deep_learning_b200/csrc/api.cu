@@ -595,11 +595,6 @@ extern "C" int sls_solver_set_weights(sls_solver* s, const double* w_init, size_
         CUDA_TRY(cudaMemcpy(s->d_w, w_resample, size_t(n) * 8, cudaMemcpyHostToDevice));
     else if (n)
         CUDA_TRY(cudaMemset(s->d_w, 0, size_t(n) * 8));
-    {
-        bool interior = w_resample_len >= n;
-        for (uint32_t i = 0; i < n && interior; i++) interior = w_resample[i] > 0.0 && w_resample[i] < 1.0;
-        s->args.wflags = interior ? WF_INTERIOR : 0u;
-    }
     if (s->d_crecx && s->inst->host.m) {
         // 64-byte clause records of the k<=3 kernel: literals + occurrence ranges + resample weights
         const DevInst& I = s->inst->dev;
@@ -915,13 +910,11 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     // ---- weights: validate and convert on the host, one upload per pool
     std::vector<uint64_t> thr(tot_n, 0);
     std::vector<double> wres(tot_n, 0.0);
-    std::vector<uint32_t> wflags(n_inst, 0);
     for (uint32_t i = 0; i < n_inst; i++) {
         const uint32_t n = insts[i]->host.n;
         const double* wi = w_init + var_offsets[i];
         const double* wr = w_resample + var_offsets[i];
         if (var_offsets[i + 1] - var_offsets[i] < n) return set_error(SLS_ERR_WEIGHTS, "weights shorter than var_count");
-        bool interior = true;
         for (uint32_t v = 0; v < n; v++) {
             const double p = wi[v];
             if (p >= 0.0 && p < 1.0)
@@ -931,9 +924,7 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
             else
                 return set_error(SLS_ERR_WEIGHTS, "weights_initialize: p is outside range [0.0, 1.0]");
             wres[plan[i].off_n + v] = wr[v];
-            interior = interior && wr[v] > 0.0 && wr[v] < 1.0;
         }
-        wflags[i] = interior ? WF_INTERIOR : 0u;
     }
 
     Pool p_thr, p_w, p_crecx, p_ftab, p_cscale, p_bits, p_found, p_hasbest, p_steps, p_flips, p_best, p_gstate, p_err, p_items, p_cta;
@@ -973,7 +964,6 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         a.algo = params->algo;
         a.mapping = params->pre_compute_mapping;
         a.want_traj = 0;
-        a.wflags = wflags[i];
         a.pfb = params->prob_flip_best;
         a.nsteps = params->nsteps;
         a.nruns = R;

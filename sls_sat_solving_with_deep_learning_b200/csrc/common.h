@@ -44,14 +44,14 @@ enum : int { ALGO_MOSER = 0, ALGO_MOSER_SINGLE = 1, ALGO_SCHOENING = 2, ALGO_PRO
 struct WalkArgs {
     DevInst inst;
     const uint64_t* thr_init;  // [n] Bernoulli thresholds of weights_initialize (lib.rs:208-210)
-    const double* w;           // [n] weights_resample
+    const double* w;           // [n] weights_resample (input of the record / table builders; the walks read those)
     const uint4* crecx;        // [m][4] 64-byte clause record of the k<=3 kernels (walk_k3.cuh) or nullptr
     const double* ftab;        // [L]  generic kernel: per literal position, MT rules: flip probability; probSAT: running sum
     const double* cscale;      // [m]  generic kernel, probSAT: UniformFloat scale of the clause, or -(error code)
     int32_t algo;
     int32_t mapping;           // pre_compute_mapping (only changes the greedy score, lib.rs:242-250)
     int32_t want_traj;
-    uint32_t wflags;           // WF_*
+    uint32_t reserved;
     double pfb;                // prob_flip_best
     uint64_t nsteps;
     uint64_t nruns;
@@ -72,10 +72,6 @@ struct WalkArgs {
     uint32_t* traj;            // [nruns][nsteps+1] or nullptr
     int32_t* err;              // first error code raised by any chain
 };
-
-// weights_resample lies strictly inside (0,1): every flip probability is positive and finite,
-// so probSAT's InvalidWeight / AllWeightsZero checks (lib.rs:71) cannot fire
-enum : uint32_t { WF_INTERIOR = 1u };
 
 // error codes raised on the device (same numbering as include/sls_b200.h)
 enum : int { DERR_WEIGHTS = 4, DERR_ALL_ZERO = 5, DERR_EMPTY_CLAUSE = 6, DERR_ARG = 7 };

@@ -388,7 +388,7 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
             auto update_round = [&](uint32_t os, uint32_t len, uint32_t av, uint32_t base) {
                 const uint32_t o = base + lane;
                 const bool act = o < len;
-                const uint4 orc = __ldg(orec + os + min(o, len - 1u));
+                const uint4 orc = __ldg(orec + (os + min(o, len - 1u)));  // one 32-bit index, one widening multiply-add
                 const uint32_t va = sV + (orc.x >> 5) * 4u;
                 const uint32_t vword = lds32(va);
                 const uint32_t bit = 1u << (orc.x & 31);
