@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(128, 7) walk_k3s_kernel(const WalkArgs A)
 
 // the batched form never records trajectories (sls_run_batch refuses them)
 template <int ALGO, bool GREEDY>
-__global__ void __launch_bounds__(128, 6) walk_k3s_batch_kernel(const WalkArgs* __restrict__ items, const uint32_t* __restrict__ cta_begin,
+__global__ void __launch_bounds__(128, 9) walk_k3s_batch_kernel(const WalkArgs* __restrict__ items, const uint32_t* __restrict__ cta_begin,
                                                                 uint32_t n_items)
 {
     extern __shared__ uint32_t sm[];
