@@ -19,6 +19,7 @@
 #include "instance.h"
 #include "walk_generic.cuh"
 #include "walk_k3.cuh"
+#include "walk_k3d.cuh"
 #include "walk_k3h.cuh"
 
 using namespace slsb;
@@ -950,9 +951,11 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     CUDA_TRY(cudaMemset(p_err.base, 0, size_t(n_inst) * 4));
 
     // ---- per-instance kernel arguments, grouped by variant: 0 = k3s, 1 = generic<smem>, 2 = generic<hbm>
-    std::vector<WalkArgs> items[3];
-    std::vector<uint32_t> cta_begin[3], owner[3];
-    size_t smem_max[3] = {0, 0, 0};
+    // (3 = k3d: two chains per warp, small k<=3 instances; test hook SLS_B200_NO_DUAL=1)
+    const bool no_dual = [] { const char* f = std::getenv("SLS_B200_NO_DUAL"); return f && f[0] == '1'; }();
+    std::vector<WalkArgs> items[4];
+    std::vector<uint32_t> cta_begin[4], owner[4];
+    size_t smem_max[4] = {0, 0, 0, 0};
     for (uint32_t i = 0; i < n_inst; i++) {
         const DevInst& I = insts[i]->dev;
         const ItemPlan& pl = plan[i];
@@ -988,20 +991,29 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         }
         if (pl.k3 && I.m)
             build_crecx_kernel<<<(I.m + 255) / 256, 256>>>(I.crec, I.occ_ptr, a.w, const_cast<uint4*>(a.crecx), I.m, I.n, params->algo);
-        const int g = pl.k3 ? 0 : pl.smem ? 1 : 2;
+        // small k<=3 instances run two chains per warp (walk_k3d.cuh): 4 warps = 8 chains per CTA
+        const bool dual = pl.k3 && !no_dual && walk_k3d_supports(a);
+        uint32_t chains_per_cta = pl.wpb;
+        size_t smem_bytes = pl.smem_bytes;
+        if (dual) {
+            a.warps_per_block = 4;
+            chains_per_cta = 8;
+            smem_bytes = size_t(chains_per_cta) * (size_t(I.slab_words) + HRING_WORDS) * 4;
+        }
+        const int g = dual ? 3 : pl.k3 ? 0 : pl.smem ? 1 : 2;
         if (cta_begin[g].empty()) cta_begin[g].push_back(0);
-        cta_begin[g].push_back(cta_begin[g].back() + (uint32_t)((R + pl.wpb - 1) / pl.wpb));
+        cta_begin[g].push_back(cta_begin[g].back() + (uint32_t)((R + chains_per_cta - 1) / chains_per_cta));
         items[g].push_back(a);
         owner[g].push_back(i);
-        smem_max[g] = std::max(smem_max[g], pl.smem_bytes);
+        smem_max[g] = std::max(smem_max[g], smem_bytes);
     }
     CUDA_TRY(cudaGetLastError());
 
     cudaEvent_t ev0, ev1;
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
-    Pool d_items[3], d_cta[3];
-    for (int g = 0; g < 3; g++) {
+    Pool d_items[4], d_cta[4];
+    for (int g = 0; g < 4; g++) {
         if (items[g].empty()) continue;
         CUDA_TRY(alloc(d_items[g], items[g].size() * sizeof(WalkArgs)));
         CUDA_TRY(alloc(d_cta[g], cta_begin[g].size() * 4));
@@ -1012,13 +1024,17 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     if (smem_max[0]) CUDA_TRY(cudaFuncSetAttribute(k3_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[0]));
     if (smem_max[1])
         CUDA_TRY(cudaFuncSetAttribute(walk_generic_batch_kernel_for<true>(params->algo), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[1]));
+    const WalkK3BatchKernel k3d_batch = walk_k3d_batch_kernel_for(params->algo);
+    if (smem_max[3]) CUDA_TRY(cudaFuncSetAttribute(k3d_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[3]));
     CUDA_TRY(cudaEventRecord(ev0));
-    for (int g = 0; g < 3; g++) {
+    for (int g = 0; g < 4; g++) {
         if (items[g].empty()) continue;
         const WalkArgs* di = reinterpret_cast<const WalkArgs*>(d_items[g].base);
         const uint32_t* dc = reinterpret_cast<const uint32_t*>(d_cta[g].base);
         const uint32_t ni = (uint32_t)items[g].size(), blocks = cta_begin[g].back();
-        if (g == 0)
+        if (g == 3)
+            k3d_batch<<<blocks, 128, smem_max[3]>>>(di, dc, ni);
+        else if (g == 0)
             k3_batch<<<blocks, 128, smem_max[0]>>>(di, dc, ni);
         else if (g == 1)
             walk_generic_batch_kernel_for<true>(params->algo)<<<blocks, 128, smem_max[1]>>>(di, dc, ni);

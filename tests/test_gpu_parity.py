@@ -518,3 +518,41 @@ def test_walk_fuzz_against_oracle(seed):
         for b in (0, len(a) - 1):
             assert (viol[b] == oi.eval_clauses(a[b])).all()
             assert energy[b] == oi.energy(a[b])
+
+
+@pytest.mark.parametrize("algo", ["moser", "probsat"])
+@pytest.mark.parametrize("dual", [True, False])
+def test_batch_two_chains_per_warp_matches_oracle(expected, algo, dual, monkeypatch):
+    # without the greedy mix, small k<=3 instances of a batch run two chains per warp (walk_k3d.cuh): every chain
+    # must still follow the oracle's trajectory (steps, solved flag, best energy, best assignment), also with a
+    # chain count that leaves half-empty warps, boundary weights and short clauses
+    if not dual:
+        monkeypatch.setenv("SLS_B200_NO_DUAL", "1")
+    rng = np.random.default_rng(17)
+    names = [n for n in expected if n.startswith("r3sat")]
+    insts, oracles = [], []
+    for n in names:
+        g, o = both(n)
+        insts.append(g)
+        oracles.append(o)
+    for n, m, seed in [(40, 150, 1), (700, 2600, 2), (2, 2, 0)]:
+        clauses = [(1, 2), (-1, -2)] if n == 2 else _mixed_short_clauses(n, m, seed)
+        insts.append(eng.Instance.from_clauses(n, clauses))
+        oracles.append(so.Instance.from_clauses(n, clauses))
+    w_init = [rng.uniform(0.05, 0.95, g.n) for g in insts]
+    w_res = [rng.uniform(0.05, 0.95, g.n) for g in insts]
+    if algo == "moser":
+        w_res[0][:5] = 0.0
+        w_res[0][5:10] = 1.0
+    for nruns in (21, 8):
+        batch = eng.run_sls_batch(insts, algo, w_init, w_res, 300, nruns, True, 0.0, seed=70)
+        for i, (oi, r) in enumerate(zip(oracles, batch)):
+            o = oi.run_sls(algo, w_init[i], w_res[i], 300, nruns, False, True, 0.0, seed=70 + i)
+            assert (r.steps == o.steps).all(), i
+            assert (r.found == o.found).all(), i
+            assert (r.best_energy_run == o.best_energy_run).all(), i
+            assert (r.flips_run == o.flips_run).all(), i
+            assert r.best_energy == o.best_energy
+            assert (r.best_assignment is None) == (o.best_assignment is None)
+            if r.best_assignment is not None:
+                assert (r.best_assignment == o.best_assignment).all(), i
