@@ -116,6 +116,8 @@ __device__ __forceinline__ void walk_k3d_body(const WalkArgs& A, uint32_t block,
     const uint64_t chain = A.chain_offset + (valid ? run : 0);
 
     auto hballot = [hshift](bool p) -> uint32_t { return (__ballot_sync(FULL, p) >> hshift) & 0xffffu; };
+    const uint32_t hmask = 0xffffu << hshift;
+    auto hcount = [hmask](bool p) -> uint32_t { return __popc(__ballot_sync(FULL, p) & hmask); };  // votes in this half
     auto hshfl = [](uint32_t v, uint32_t src) -> uint32_t { return __shfl_sync(FULL, v, src, 16); };
     // literal code l = 2*var + neg is TRUE iff bit(var) != neg
     auto lit_true = [sA](uint32_t l) -> uint32_t { return (__funnelshift_r(lds32(sA + (l >> 6) * 4u), 0u, l >> 1) ^ l) & 1u; };
@@ -206,11 +208,13 @@ __device__ __forceinline__ void walk_k3d_body(const WalkArgs& A, uint32_t block,
                 atoms_xor(va, bit);
                 atoms_add(sL + (orc.x >> 10) * 4u, ins ? 1u : 0xffffffffu);
             }
-            nf += __popc(hballot(ins)) - __popc(hballot(rem));
+            nf += hcount(ins) - hcount(rem);
         }
         __syncwarp();
     };
 
+    const bool few_groups = I.ngroups <= 4;
+    const uint32_t lt_lo = (1u << l16) - 1u, lt_hi = (1u << (l16 + 16)) - 1u;
     bool active = nf > 0 && budget > 0;  // per chain
     while (__any_sync(FULL, active)) {
         if (active) steps++;
@@ -242,21 +246,36 @@ __device__ __forceinline__ void walk_k3d_body(const WalkArgs& A, uint32_t block,
         }
 
         // ---- exact rank select: level-1 counter per lane -> 32 words (two per lane) -> bit
-        const uint32_t cntA = lds32(sL + l16 * 4u);
-        const uint32_t inclA = half_incl_scan(cntA);
-        const uint32_t g = __popc(hballot(r >= inclA)) & 15u;  // (an idle chain has r = 0 and may see an empty set)
-        r -= hshfl(inclA - cntA, g);
+        uint32_t g;
+        if (few_groups) {
+            // at most four level-1 counters (4096 clauses): every lane reads them all and walks the prefix itself
+            uint4 c4;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c4.x), "=r"(c4.y), "=r"(c4.z), "=r"(c4.w) : "r"(sL));
+            const uint32_t p1 = c4.x, p2 = p1 + c4.y, p3 = p2 + c4.z;
+            g = (r >= p1 ? 1u : 0u) + (r >= p2 ? 1u : 0u) + (r >= p3 ? 1u : 0u);
+            r -= g == 0 ? 0u : g == 1 ? p1 : g == 2 ? p2 : p3;
+            g = active ? g : 0u;  // (an idle chain has r = 0 and may see an empty set)
+        } else {
+            const uint32_t cntA = lds32(sL + l16 * 4u);
+            const uint32_t inclA = half_incl_scan(cntA);
+            g = hcount(r >= inclA) & 15u;
+            r -= hshfl(inclA - cntA, g);
+        }
         const uint2 ww = lds64(sV + (g * 32u + 2u * l16) * 4u);
         const uint32_t pc0 = __popc(ww.x), pc = pc0 + __popc(ww.y);
         const uint32_t inclB = half_incl_scan(pc);
-        const uint32_t srcB = __popc(hballot(r >= inclB)) & 15u;
+        const uint32_t srcB = hcount(r >= inclB) & 15u;
         r -= hshfl(inclB - pc, srcB);
         const uint32_t w0 = hshfl(ww.x, srcB), w1 = hshfl(ww.y, srcB);
         const uint32_t first = __popc(w0);
         const bool second = r >= first;
         if (second) r -= first;
         const uint32_t wsel = second ? w1 : w0;
-        const uint32_t c = active ? (g * 32u + 2u * srcB + (second ? 1u : 0u)) * 32u + select_in_word(wsel, r) : 0u;
+        // the r-th set bit of wsel: a lane tests positions l16 and l16 + 16, exactly one test of the half hits
+        const bool hit_lo = ((wsel >> l16) & 1u) && __popc(wsel & lt_lo) == r;
+        const bool hit_hi = ((wsel >> (l16 + 16)) & 1u) && __popc(wsel & lt_hi) == r;
+        const uint32_t pos = bfind(hballot(hit_lo) | hballot(hit_hi) << 16);
+        const uint32_t c = active ? (g * 32u + 2u * srcB + (second ? 1u : 0u)) * 32u + (pos & 31u) : 0u;
 
         // ---- the clause record (see build_crecx_kernel)
         const uint4* rec = crecx + CRECX_QUADS * c;
