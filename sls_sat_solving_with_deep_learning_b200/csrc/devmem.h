@@ -4,21 +4,29 @@
 // every call; with cudaMalloc / cudaFree that is a page-table update per buffer and showed up as 10-350 ms of
 // jitter around a 180 ms kernel.  The pool keeps freed blocks mapped (up to the release threshold) so a repeated
 // call of the same shape allocates without talking to the OS.
+//
+// Large buffers (GNN activations, HBM-tier chain state: hundreds of MB to tens of GB) do NOT go through the pool:
+// growing the pool by gigabytes costs ~30 ms per GB, and keeping such blocks cached would take them away from the
+// application's own allocator (torch uses cudaMalloc, which cannot see the pool's free memory).  They use plain
+// cudaMalloc / cudaFree, which is cheap at that size.
 #pragma once
 #include <cuda_runtime.h>
 
 #include <cstdint>
 #include <mutex>
+#include <unordered_set>
 
 namespace slsb {
 
 constexpr int kMaxDevices = 64;
 constexpr uint64_t kPoolKeepBytes = 4ull << 30;  // freed memory above this goes back to the driver at the next sync
+constexpr size_t kPoolMaxBlock = 32u << 20;       // larger requests bypass the pool
 
 struct DevMemState {
     std::mutex mu;
     cudaStream_t stream[kMaxDevices] = {};
     bool ready[kMaxDevices] = {};
+    std::unordered_set<void*> direct;  // blocks that came from cudaMalloc
 };
 
 inline DevMemState& devmem_state()
@@ -53,6 +61,16 @@ template <class T>
 inline cudaError_t dmalloc(T** p, size_t bytes)
 {
     *p = nullptr;
+    if (bytes > kPoolMaxBlock) {
+        void* q = nullptr;
+        const cudaError_t e = cudaMalloc(&q, bytes);
+        if (e != cudaSuccess) return e;
+        DevMemState& st = devmem_state();
+        std::lock_guard<std::mutex> lock(st.mu);
+        st.direct.insert(q);
+        *p = static_cast<T*>(q);
+        return cudaSuccess;
+    }
     int device = 0;
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) return e;
@@ -73,6 +91,15 @@ inline cudaError_t dmalloc(T** p, size_t bytes)
 inline void dfree(void* p)
 {
     if (!p) return;
+    {
+        DevMemState& st = devmem_state();
+        std::unique_lock<std::mutex> lock(st.mu);
+        if (st.direct.erase(p)) {
+            lock.unlock();
+            cudaFree(p);  // waits for the device like every cudaFree
+            return;
+        }
+    }
     cudaPointerAttributes attr;
     int prev = 0;
     cudaGetDevice(&prev);

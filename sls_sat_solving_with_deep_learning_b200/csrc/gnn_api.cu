@@ -69,12 +69,17 @@ struct sls_gnn_model {
     float readout_b = 0.f;
     std::vector<void*> allocs;
     int launches = 0;
+    // Activation workspace (edge / node feature ping-pong buffers and the two aggregates): one block, grown on
+    // demand and kept across calls, so a repeated forward of the same batch shape allocates nothing.
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
 };
 
 extern "C" void sls_gnn_model_free(sls_gnn_model* m)
 {
     if (!m) return;
     for (void* p : m->allocs) dfree(p);
+    dfree(m->ws);
     delete m;
 }
 
@@ -232,18 +237,23 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
 int forward_device(sls_gnn_model* m, int64_t N, int64_t E, const float* d_nodes, const float* d_edges, const uint8_t* d_node_type,
                    const uint8_t* d_edge_type, const int32_t* d_send,
                    const int32_t* d_recv, const int64_t* d_sptr, const int32_t* d_sids, const int64_t* d_rptr, const int32_t* d_rids,
-                   float* d_decoded)
+                   float* d_decoded, cudaEvent_t ev0, cudaEvent_t ev1)
 {
     const int D = m->embed, H = m->h2;
-    DevBuf e_a, e_b, h_a, h_b, sent, recv;
     const size_t ew = std::max(D, H), hw = std::max(D, H);
-    G_TRY(dmalloc(&e_a.p, std::max<int64_t>(E, 1) * ew * sizeof(float)));
-    G_TRY(dmalloc(&e_b.p, std::max<int64_t>(E, 1) * ew * sizeof(float)));
-    G_TRY(dmalloc(&h_a.p, std::max<int64_t>(N, 1) * hw * sizeof(float)));
-    G_TRY(dmalloc(&h_b.p, std::max<int64_t>(N, 1) * hw * sizeof(float)));
-    G_TRY(dmalloc(&sent.p, std::max<int64_t>(N, 1) * H * sizeof(float)));
-    G_TRY(dmalloc(&recv.p, std::max<int64_t>(N, 1) * H * sizeof(float)));
-    float *e = e_a.as<float>(), *e2 = e_b.as<float>(), *h = h_a.as<float>(), *h2 = h_b.as<float>();
+    auto part = [](int64_t rows, size_t width) { return (size_t)(std::max<int64_t>(rows, 1) * width * sizeof(float) + 255) & ~(size_t)255; };
+    const size_t be = part(E, ew), bh = part(N, hw), ba = part(N, H);
+    const size_t need = 2 * be + 2 * bh + 2 * ba;
+    if (need > m->ws_bytes) {
+        dfree(m->ws);
+        m->ws = nullptr, m->ws_bytes = 0;
+        G_TRY(dmalloc(&m->ws, need));
+        m->ws_bytes = need;
+    }
+    char* base = static_cast<char*>(m->ws);
+    float *e = (float*)base, *e2 = (float*)(base + be), *h = (float*)(base + 2 * be), *h2 = (float*)(base + 2 * be + bh);
+    float *sent = (float*)(base + 2 * be + 2 * bh), *recv = (float*)(base + 2 * be + 2 * bh + ba);
+    if (ev0) G_TRY(cudaEventRecord(ev0));
     if (E && d_edge_type)
         embed_onehot_kernel<<<(unsigned)((E * D + 255) / 256), 256>>>(d_edge_type, m->edge_embed_w, m->edge_embed_b, e, E, D);
     else if (E)
@@ -263,11 +273,11 @@ int forward_device(sls_gnn_model* m, int64_t N, int64_t E, const float* d_nodes,
         // node update sees [nodes | segment_sum(new edges, senders) | segment_sum(new edges, receivers)]
         if (N) {
             const unsigned blocks = (unsigned)((N * 32 + 255) / 256);
-            segment_sum_kernel<<<blocks, 256>>>(e, d_sptr, d_sids, sent.as<float>(), N, H);
-            segment_sum_kernel<<<blocks, 256>>>(e, d_rptr, d_rids, recv.as<float>(), N, H);
+            segment_sum_kernel<<<blocks, 256>>>(e, d_sptr, d_sids, sent, N, H);
+            segment_sum_kernel<<<blocks, 256>>>(e, d_rptr, d_rids, recv, N, H);
             m->launches += 2;
         }
-        rc = launch_mlp(m, m->node_mlp[t], h, nullptr, dn, sent.as<float>(), nullptr, H, recv.as<float>(), nullptr, H, N, h2);
+        rc = launch_mlp(m, m->node_mlp[t], h, nullptr, dn, sent, nullptr, H, recv, nullptr, H, N, h2);
         if (rc) return rc;
         std::swap(h, h2);
         dn = H;
@@ -277,6 +287,7 @@ int forward_device(sls_gnn_model* m, int64_t N, int64_t E, const float* d_nodes,
         m->launches++;
     }
     G_TRY(cudaGetLastError());
+    if (ev1) G_TRY(cudaEventRecord(ev1));
     G_TRY(cudaDeviceSynchronize());
     return SLS_OK;
 }
@@ -323,11 +334,9 @@ int forward_host_graph(sls_gnn_model* m, int64_t N, int64_t E, const float* node
     G_TRY(cudaEventCreate(&e0));
     G_TRY(cudaEventCreate(&e1));
     m->launches = 0;
-    G_TRY(cudaEventRecord(e0));
     rc = forward_device(m, N, E, d_nodes.as<float>(), d_edges.as<float>(), nullptr, nullptr, d_send.as<int32_t>(), d_recv.as<int32_t>(),
-                        d_sptr.as<int64_t>(), d_sids.as<int32_t>(), d_rptr.as<int64_t>(), d_rids.as<int32_t>(), d_dec.as<float>());
+                        d_sptr.as<int64_t>(), d_sids.as<int32_t>(), d_rptr.as<int64_t>(), d_rids.as<int32_t>(), d_dec.as<float>(), e0, e1);
     if (!rc) {
-        cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
@@ -484,11 +493,9 @@ extern "C" int sls_gnn_forward_lcg(sls_gnn_model* m, sls_instance* const* insts,
     G_TRY(cudaEventCreate(&e0));
     G_TRY(cudaEventCreate(&e1));
     m->launches = 0;
-    G_TRY(cudaEventRecord(e0));
     rc = forward_device(m, N, E, nullptr, nullptr, d_nt.as<uint8_t>(), d_et.as<uint8_t>(), d_send.as<int32_t>(), d_recv.as<int32_t>(),
-                        d_sptr.as<int64_t>(), d_sids.as<int32_t>(), d_rptr.as<int64_t>(), d_rids.as<int32_t>(), d_dec.as<float>());
+                        d_sptr.as<int64_t>(), d_sids.as<int32_t>(), d_rptr.as<int64_t>(), d_rids.as<int32_t>(), d_dec.as<float>(), e0, e1);
     if (!rc) {
-        cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
