@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -9,6 +10,7 @@
 #include <fstream>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sls_b200.h"
@@ -69,38 +71,39 @@ namespace {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// Upload every device array of the instance in one allocation.  Called lazily by the first
-// compute entry point so that parsing / inspection works on a machine without a GPU.
-int ensure_on_device(sls_instance* inst)
+// The device image of an instance: every array back to back (256-byte aligned segments), built on the host
+// without touching CUDA, so that the images of a batch can be built by several threads.
+struct InstImage {
+    std::vector<char> bytes;
+    size_t off[7] = {};
+};
+
+void build_image(const HostInstance& h, InstImage& img)
 {
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (inst->d_blob && inst->device == dev) return SLS_OK;
-    if (inst->d_blob) {
-        dfree(inst->d_blob);
-        inst->d_blob = nullptr;
-    }
-    const HostInstance& h = inst->host;
     const size_t L = h.lits.size();
-    struct Seg {
-        const void* src;
-        size_t bytes;
-        size_t off;
-    };
-    std::vector<uint4> crec, orec;
+    const size_t n_orec = h.k3 ? L + 32 : 0;  // padded: a warp may over-read one full round
+    const size_t seg_bytes[7] = {h.row_ptr.size() * 4, L * 4, h.occ_ptr.size() * 4, L * 4, h.has_duplicates ? h.canon.size() * 4 : 0,
+                                 h.k3 ? h.m * sizeof(uint4) : 0, n_orec * sizeof(uint4)};
+    size_t total = 0;
+    for (int i = 0; i < 7; i++) {
+        img.off[i] = total;
+        total += align_up(std::max<size_t>(seg_bytes[i], 16), 256);
+    }
+    img.bytes.assign(total, 0);
+    char* b = img.bytes.data();
+    const void* src[5] = {h.row_ptr.data(), h.lits.data(), h.occ_ptr.data(), h.occ.data(), h.has_duplicates ? h.canon.data() : nullptr};
+    for (int i = 0; i < 5; i++)
+        if (seg_bytes[i]) std::memcpy(b + img.off[i], src[i], seg_bytes[i]);
     if (h.k3) {
         // clause records {l0,l1,l2,k}; occurrence records {clause, other a, other b, neg of the variable}
-        crec.resize(h.m);
+        uint4* crec = reinterpret_cast<uint4*>(b + img.off[5]);
+        uint4* orec = reinterpret_cast<uint4*>(b + img.off[6]);
+        std::vector<uint32_t> fill(h.occ_ptr.begin(), h.occ_ptr.end() - 1);
         for (uint32_t c = 0; c < h.m; c++) {
             const uint32_t s = h.row_ptr[c], k = h.row_ptr[c + 1] - s;
             uint32_t l[3] = {LIT_NONE, LIT_NONE, LIT_NONE};
             for (uint32_t j = 0; j < k; j++) l[j] = h.lits[s + j];
             crec[c] = make_uint4(l[0], l[1], l[2], k);
-        }
-        orec.resize(L + 32);  // padded: a warp may over-read one full round
-        std::vector<uint32_t> fill(h.occ_ptr.begin(), h.occ_ptr.end() - 1);
-        for (uint32_t c = 0; c < h.m; c++) {
-            const uint32_t s = h.row_ptr[c], k = h.row_ptr[c + 1] - s;
             for (uint32_t j = 0; j < k; j++) {
                 uint32_t others[2] = {h.n << 1, h.n << 1};  // absent: positive literal of the dummy variable n (bit always 0)
                 uint32_t t = 0;
@@ -110,31 +113,23 @@ int ensure_on_device(sls_instance* inst)
                 orec[fill[lit >> 1]++] = make_uint4(c, others[0], others[1], lit & 1u);
             }
         }
-        for (size_t i = L; i < orec.size(); i++) orec[i] = make_uint4(0, h.n << 1, h.n << 1, 2);
+        for (size_t i = L; i < n_orec; i++) orec[i] = make_uint4(0, h.n << 1, h.n << 1, 2);
     }
-    std::vector<Seg> segs = {
-        {h.row_ptr.data(), h.row_ptr.size() * 4, 0}, {h.lits.data(), L * 4, 0},
-        {h.occ_ptr.data(), h.occ_ptr.size() * 4, 0}, {h.occ.data(), L * 4, 0},
-        {h.has_duplicates ? h.canon.data() : nullptr, h.has_duplicates ? h.canon.size() * 4 : 0, 0},
-        {crec.data(), crec.size() * sizeof(uint4), 0}, {orec.data(), orec.size() * sizeof(uint4), 0},
-    };
-    size_t total = 0;
-    for (auto& s : segs) {
-        s.off = total;
-        total += align_up(std::max<size_t>(s.bytes, 16), 256);
-    }
+}
+
+// One allocation and ONE host-to-device copy per instance.
+int commit_image(sls_instance* inst, const InstImage& img, int dev)
+{
+    const HostInstance& h = inst->host;
     char* blob = nullptr;
-    CUDA_TRY(dmalloc(&blob, total));
-    for (auto& s : segs)
-        if (s.bytes) {
-            cudaError_t e = cudaMemcpy(blob + s.off, s.src, s.bytes, cudaMemcpyHostToDevice);
-            if (e != cudaSuccess) {
-                dfree(blob);
-                return set_error(SLS_ERR_CUDA, std::string("cudaMemcpy(instance): ") + cudaGetErrorString(e));
-            }
-        }
+    CUDA_TRY(dmalloc(&blob, img.bytes.size()));
+    cudaError_t e = cudaMemcpy(blob, img.bytes.data(), img.bytes.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        dfree(blob);
+        return set_error(SLS_ERR_CUDA, std::string("cudaMemcpy(instance): ") + cudaGetErrorString(e));
+    }
     inst->d_blob = blob;
-    inst->blob_bytes = total;
+    inst->blob_bytes = img.bytes.size();
     inst->device = dev;
     DevInst& d = inst->dev;
     d.n = h.n;
@@ -151,15 +146,78 @@ int ensure_on_device(sls_instance* inst)
     d.uniform_k = h.uniform_k;
     d.max_k = h.max_k;
     d.flags = (h.has_duplicates ? INST_HAS_DUPLICATES : 0u) | (h.k3 ? INST_K3 : 0u);
-    d.row_ptr = reinterpret_cast<const uint32_t*>(blob + segs[0].off);
-    d.lits = reinterpret_cast<const uint32_t*>(blob + segs[1].off);
-    d.occ_ptr = reinterpret_cast<const uint32_t*>(blob + segs[2].off);
-    d.occ = reinterpret_cast<const uint32_t*>(blob + segs[3].off);
-    d.canon = h.has_duplicates ? reinterpret_cast<const uint32_t*>(blob + segs[4].off) : nullptr;
-    d.crec = h.k3 ? reinterpret_cast<const uint4*>(blob + segs[5].off) : nullptr;
-    d.orec = h.k3 ? reinterpret_cast<const uint4*>(blob + segs[6].off) : nullptr;
+    d.row_ptr = reinterpret_cast<const uint32_t*>(blob + img.off[0]);
+    d.lits = reinterpret_cast<const uint32_t*>(blob + img.off[1]);
+    d.occ_ptr = reinterpret_cast<const uint32_t*>(blob + img.off[2]);
+    d.occ = reinterpret_cast<const uint32_t*>(blob + img.off[3]);
+    d.canon = h.has_duplicates ? reinterpret_cast<const uint32_t*>(blob + img.off[4]) : nullptr;
+    d.crec = h.k3 ? reinterpret_cast<const uint4*>(blob + img.off[5]) : nullptr;
+    d.orec = h.k3 ? reinterpret_cast<const uint4*>(blob + img.off[6]) : nullptr;
     return SLS_OK;
 }
+
+// Upload the instance.  Called lazily by the first compute entry point so that parsing / inspection works on a
+// machine without a GPU.
+int ensure_on_device(sls_instance* inst)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (inst->d_blob && inst->device == dev) return SLS_OK;
+    if (inst->d_blob) {
+        dfree(inst->d_blob);
+        inst->d_blob = nullptr;
+    }
+    InstImage img;
+    build_image(inst->host, img);
+    return commit_image(inst, img, dev);
+}
+
+// The same for a batch: the images of the instances that are not resident yet are built by up to 16 host threads,
+// then committed one copy each (a batch of config 4 is 1250 instances of ~200 KB).
+int ensure_batch_on_device(sls_instance* const* insts, uint32_t n_inst)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::vector<uint32_t> todo;
+    for (uint32_t i = 0; i < n_inst; i++) {
+        if (!insts[i]) return set_error(SLS_ERR_ARG, "NULL instance handle in batch");
+        if (insts[i]->d_blob && insts[i]->device == dev) continue;
+        bool seen = false;  // the same handle may appear more than once in a batch
+        for (uint32_t j : todo) seen |= insts[j] == insts[i];
+        if (!seen) todo.push_back(i);
+    }
+    if (todo.empty()) return SLS_OK;
+    const size_t chunk = 64;  // images alive at a time: bounds the host staging memory
+    std::vector<InstImage> imgs(std::min(chunk, todo.size()));
+    for (size_t base = 0; base < todo.size(); base += chunk) {
+        const size_t cnt = std::min(chunk, todo.size() - base);
+        const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>({(size_t)std::thread::hardware_concurrency(), (size_t)16, cnt}));
+        std::atomic<size_t> next{0};
+        auto work = [&] {
+            for (size_t k; (k = next.fetch_add(1)) < cnt;) build_image(insts[todo[base + k]]->host, imgs[k]);
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < T; t++) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+        for (size_t k = 0; k < cnt; k++) {
+            sls_instance* inst = insts[todo[base + k]];
+            if (inst->d_blob) {
+                dfree(inst->d_blob);
+                inst->d_blob = nullptr;
+            }
+            int rc = commit_image(inst, imgs[k], dev);
+            if (rc) return rc;
+        }
+    }
+    return SLS_OK;
+}
+
+}  // namespace
+
+int slsb_ensure_batch_on_device(sls_instance* const* insts, uint32_t n_inst) { return ensure_batch_on_device(insts, n_inst); }
+
+namespace {
 
 int finish_handle(sls_instance* inst, const std::string& err, sls_instance** out)
 {
@@ -882,9 +940,11 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     size_t tot_n = 0, tot_bits = 0, tot_run = 0, tot_crecx = 0, tot_gstate = 0, tot_ftab = 0, tot_cscale = 0;
     const bool force_generic = [] { const char* f = std::getenv("SLS_B200_FORCE_GENERIC"); return f && f[0] == '1'; }();
     const char* force_state = std::getenv("SLS_B200_FORCE_STATE");
-    for (uint32_t i = 0; i < n_inst; i++) {
-        int rc = ensure_on_device(insts[i]);
+    {
+        int rc = ensure_batch_on_device(insts, n_inst);
         if (rc) return rc;
+    }
+    for (uint32_t i = 0; i < n_inst; i++) {
         const DevInst& I = insts[i]->dev;
         ItemPlan& pl = plan[i];
         const size_t slab_bytes = size_t(I.slab_words) * 4 + RING_WORDS * 4;  // slab + random-word ring
@@ -1068,7 +1128,14 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     CUDA_TRY(cudaMemcpy(steps.data(), p_steps.base, tot_run * 8, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(flips.data(), p_flips.base, tot_run * 8, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(be.data(), p_best.base, tot_run * 4, cudaMemcpyDeviceToHost));
-    std::vector<uint32_t> bits;
+    // best assignments: one copy of the whole pool when it is small (a batch of small instances would otherwise pay
+    // one synchronous copy per instance), else only the winning chain's words
+    std::vector<uint32_t> bits, all_bits;
+    const bool bits_at_once = tot_bits * 4 <= (64u << 20);
+    if (bits_at_once) {
+        all_bits.resize(std::max<size_t>(tot_bits, 1));
+        CUDA_TRY(cudaMemcpy(all_bits.data(), p_bits.base, tot_bits * 4, cudaMemcpyDeviceToHost));
+    }
     for (uint32_t i = 0; i < n_inst; i++) {
         const HostInstance& h = insts[i]->host;
         const ItemPlan& pl = plan[i];
@@ -1090,10 +1157,14 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
             r.has_best_assignment = 1;
             if (r.best_assignment) {
                 const uint32_t nwords = insts[i]->dev.nwords;
-                bits.resize(std::max<uint32_t>(nwords, 1));
-                CUDA_TRY(cudaMemcpy(bits.data(), reinterpret_cast<uint32_t*>(p_bits.base) + pl.off_bits + winner * nwords,
-                                    size_t(nwords) * 4, cudaMemcpyDeviceToHost));
-                for (uint32_t v = 0; v < h.n; v++) r.best_assignment[v] = (bits[v >> 5] >> (v & 31)) & 1u;
+                const uint32_t* wb = all_bits.data() + pl.off_bits + winner * nwords;
+                if (!bits_at_once) {
+                    bits.resize(std::max<uint32_t>(nwords, 1));
+                    CUDA_TRY(cudaMemcpy(bits.data(), reinterpret_cast<uint32_t*>(p_bits.base) + pl.off_bits + winner * nwords,
+                                        size_t(nwords) * 4, cudaMemcpyDeviceToHost));
+                    wb = bits.data();
+                }
+                for (uint32_t v = 0; v < h.n; v++) r.best_assignment[v] = (wb[v >> 5] >> (v & 31)) & 1u;
             }
         }
         if (r.found) std::memcpy(r.found, found.data() + pl.off_run, R);

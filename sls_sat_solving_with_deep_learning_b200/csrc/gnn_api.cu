@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <atomic>
@@ -73,6 +74,9 @@ struct sls_gnn_model {
     // demand and kept across calls, so a repeated forward of the same batch shape allocates nothing.
     void* ws = nullptr;
     size_t ws_bytes = 0;
+    // graph workspace of the batched LCG path (edge lists, segment CSRs, outputs), same policy
+    void* gws = nullptr;
+    size_t gws_bytes = 0;
 };
 
 extern "C" void sls_gnn_model_free(sls_gnn_model* m)
@@ -80,6 +84,7 @@ extern "C" void sls_gnn_model_free(sls_gnn_model* m)
     if (!m) return;
     for (void* p : m->allocs) dfree(p);
     dfree(m->ws);
+    dfree(m->gws);
     delete m;
 }
 
@@ -444,6 +449,86 @@ void lcg_fill(const slsb::HostInstance& h, const LcgPlan& pl, int32_t* send, int
 
 }  // namespace
 
+namespace {
+
+// The batched path for resident instances: the graph arrays are produced on the device (gnn_kernels.cuh,
+// lcg_*_kernel) from the instances' CSRs in HBM, so nothing but two small per-instance tables goes up and only
+// the probabilities come back.
+int forward_lcg_device(sls_gnn_model* m, sls_instance* const* insts, uint32_t n_inst, const std::vector<LcgPlan>& plan, int64_t N, int64_t E,
+                       int64_t V, float* prob, float* decoded, double* kernel_ms)
+{
+    int rc = slsb_ensure_batch_on_device(insts, n_inst);
+    if (rc) return rc;
+    std::vector<LcgItem> items(n_inst);
+    std::vector<int64_t> begins(2 * (size_t)(n_inst + 1));  // clause_begin | var_begin
+    int64_t C = 0;
+    for (uint32_t i = 0; i < n_inst; i++) {
+        const slsb::DevInst& d = insts[i]->dev;
+        LcgItem& it = items[i];
+        it.row_ptr = d.row_ptr, it.lits = d.lits, it.occ_ptr = d.occ_ptr, it.occ = d.occ;
+        it.n = d.n, it.m = d.m, it.L = (uint32_t)insts[i]->host.lits.size(), it.pad = 0;
+        it.node_off = plan[i].node_off, it.edge_off = plan[i].edge_off, it.var_off = plan[i].var_off, it.clause_off = C;
+        begins[i] = C;
+        begins[n_inst + 1 + i] = plan[i].var_off;
+        C += d.m;
+    }
+    begins[n_inst] = C;
+    begins[2 * (size_t)n_inst + 1] = V;
+
+    auto a256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t bE4 = a256((size_t)E * 4), bN8 = a256((size_t)(N + 1) * 8), bV8 = a256((size_t)V * 8), bN1 = a256((size_t)N), bE1 = a256((size_t)E),
+                 bN4 = a256((size_t)N * 4), bV4 = a256((size_t)V * 4), bItems = a256(items.size() * sizeof(LcgItem)),
+                 bBegins = a256(begins.size() * 8);
+    const size_t need = 4 * bE4 + 2 * bN8 + bV8 + bN1 + bE1 + bN4 + bV4 + bItems + bBegins;
+    if (need > m->gws_bytes) {
+        dfree(m->gws);
+        m->gws = nullptr, m->gws_bytes = 0;
+        G_TRY(dmalloc(&m->gws, need));
+        m->gws_bytes = need;
+    }
+    char* p = static_cast<char*>(m->gws);
+    auto take = [&p](size_t bytes) { char* q = p; p += bytes; return q; };
+    LcgOut o{};
+    o.send = (int32_t*)take(bE4), o.recv = (int32_t*)take(bE4), o.sids = (int32_t*)take(bE4), o.rids = (int32_t*)take(bE4);
+    o.sptr = (int64_t*)take(bN8), o.rptr = (int64_t*)take(bN8), o.var_node0 = (int64_t*)take(bV8);
+    o.node_type = (uint8_t*)take(bN1), o.edge_type = (uint8_t*)take(bE1);
+    o.N = N, o.E = E;
+    float* d_dec = (float*)take(bN4);
+    float* d_p = (float*)take(bV4);
+    LcgItem* d_items = (LcgItem*)take(bItems);
+    int64_t* d_begins = (int64_t*)take(bBegins);
+    G_TRY(cudaMemcpy(d_items, items.data(), items.size() * sizeof(LcgItem), cudaMemcpyHostToDevice));
+    G_TRY(cudaMemcpy(d_begins, begins.data(), begins.size() * 8, cudaMemcpyHostToDevice));
+    m->launches = 0;
+    if (C) lcg_clauses_kernel<<<(unsigned)((C + 255) / 256), 256>>>(d_items, d_begins, n_inst, C, o);
+    lcg_variables_kernel<<<(unsigned)((V + 127) / 128), 128>>>(d_items, d_begins + n_inst + 1, n_inst, V, o);
+    G_TRY(cudaGetLastError());
+    cudaEvent_t e0, e1;
+    G_TRY(cudaEventCreate(&e0));
+    G_TRY(cudaEventCreate(&e1));
+    rc = forward_device(m, N, E, nullptr, nullptr, o.node_type, o.edge_type, o.send, o.recv, o.sptr, o.sids, o.rptr, o.rids, d_dec, e0, e1);
+    m->launches += 2;
+    if (!rc) {
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (kernel_ms) *kernel_ms = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+    if (decoded && N) G_TRY(cudaMemcpy(decoded, d_dec, N * sizeof(float), cudaMemcpyDeviceToHost));
+    if (prob && V) {
+        pair_prob_kernel<<<(unsigned)((V + 255) / 256), 256>>>(d_dec, o.var_node0, d_p, V);
+        m->launches++;
+        G_TRY(cudaGetLastError());
+        G_TRY(cudaMemcpy(prob, d_p, V * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return SLS_OK;
+}
+
+}  // namespace
+
 extern "C" int sls_gnn_forward_lcg(sls_gnn_model* m, sls_instance* const* insts, uint32_t n_inst, float* prob, float* decoded,
                                    double* kernel_ms)
 {
@@ -472,6 +557,11 @@ extern "C" int sls_gnn_forward_lcg(sls_gnn_model* m, sls_instance* const* insts,
         V += insts[i]->host.n;
         if (N > 0x7fffffffll || E > 0x7fffffffll) return sls_set_error_internal(SLS_ERR_ARG, "batch too large for one call");
     }
+    // test hook: SLS_B200_LCG_HOST=1 forces the host-built graph arrays
+    bool device_build = V > 0 && !([] { const char* f = std::getenv("SLS_B200_LCG_HOST"); return f && f[0] == '1'; }());
+    for (uint32_t i = 0; i < n_inst && device_build; i++) device_build = plan[i].m_ne == insts[i]->host.m;
+    if (device_build) return forward_lcg_device(m, insts, n_inst, plan, N, E, V, prob, decoded, kernel_ms);
+
     std::vector<int32_t> send(std::max<int64_t>(E, 1)), recv(send.size()), sids(send.size()), rids(send.size());
     std::vector<uint8_t> node_type(std::max<int64_t>(N, 1)), edge_type(send.size());
     std::vector<int64_t> sptr(N + 1, 0), rptr(N + 1, 0), var_node0(std::max<int64_t>(V, 1));

@@ -477,4 +477,109 @@ __global__ void pair_prob_kernel(const float* __restrict__ decoded, const int64_
     p[j] = eb / (ea + eb);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// LCG graph of a batch of resident instances, built on the device from their clause / occurrence CSRs
+// (LCG.get_graph, sat_representations.py:607-666, with sat_instances.py:50-73; same node / edge numbering as the
+// host builder in gnn_api.cu).  Instance i owns nodes [node_off, node_off + 2n + m): literal nodes 2j (negative) and
+// 2j+1 (positive) then one node per clause; edges [edge_off, edge_off + L + n): one literal -> clause edge per
+// literal occurrence in file order, then one positive -> negative edge per variable.  The two segment CSRs
+// (edge ids per sender / per receiver, increasing edge id) are written directly.  Instances with empty clauses
+// (which the reference drops) take the host path.
+struct LcgItem {
+    const uint32_t* row_ptr;
+    const uint32_t* lits;
+    const uint32_t* occ_ptr;
+    const uint32_t* occ;
+    uint32_t n, m, L, pad;
+    int64_t node_off, edge_off, var_off, clause_off;  // clause_off: position of the first clause in the batch-wide clause numbering
+};
+
+__device__ __forceinline__ uint32_t lcg_find(const int64_t* __restrict__ begin, uint32_t n_items, int64_t x)
+{
+    uint32_t lo = 0, hi = n_items;  // invariant: begin[lo] <= x < begin[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(begin + mid) <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+struct LcgOut {
+    int32_t *send, *recv, *sids, *rids;
+    int64_t *sptr, *rptr, *var_node0;
+    uint8_t *node_type, *edge_type;
+    int64_t N, E;  // totals of the batch: sptr[N] = rptr[N] = E
+};
+
+// one thread per clause of the batch
+__global__ void lcg_clauses_kernel(const LcgItem* __restrict__ items, const int64_t* __restrict__ clause_begin, uint32_t n_items,
+                                   int64_t total_clauses, LcgOut o)
+{
+    const int64_t gc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gc >= total_clauses) return;
+    const uint32_t it = lcg_find(clause_begin, n_items, gc);
+    const LcgItem I = items[it];
+    const uint32_t c = (uint32_t)(gc - I.clause_off);
+    const int64_t no = I.node_off, eo = I.edge_off, n = I.n;
+    const uint32_t s = __ldg(I.row_ptr + c), e = __ldg(I.row_ptr + c + 1);
+    const int64_t node = no + 2 * n + c;
+    o.node_type[node] = 0;
+    o.rptr[node] = eo + n + s;
+    o.sptr[node] = eo + I.L + n;  // clause nodes send nothing
+    for (uint32_t j = s; j < e; j++) {
+        const uint32_t lit = __ldg(I.lits + j);
+        o.send[eo + j] = (int32_t)(no + 2 * (int64_t)(lit >> 1) + ((lit & 1u) ? 0 : 1));
+        o.recv[eo + j] = (int32_t)node;
+        o.edge_type[eo + j] = 0;
+        o.rids[eo + n + j] = (int32_t)(eo + j);
+    }
+}
+
+// one thread per variable of the batch
+__global__ void lcg_variables_kernel(const LcgItem* __restrict__ items, const int64_t* __restrict__ var_begin, uint32_t n_items,
+                                     int64_t total_vars, LcgOut o)
+{
+    const int64_t gv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gv >= total_vars) return;
+    const uint32_t it = lcg_find(var_begin, n_items, gv);
+    const LcgItem I = items[it];
+    const uint32_t v = (uint32_t)(gv - I.var_off);
+    const int64_t no = I.node_off, eo = I.edge_off;
+    const int64_t neg = no + 2 * (int64_t)v, pos = neg + 1, pair = eo + I.L + v;
+    o.node_type[neg] = 1;  // np.eye(2)[1] and np.eye(2)[-1] are both [0,1]
+    o.node_type[pos] = 1;
+    o.send[pair] = (int32_t)pos;
+    o.recv[pair] = (int32_t)neg;
+    o.edge_type[pair] = 1;
+    o.var_node0[gv] = neg;
+    if (gv == 0) o.sptr[o.N] = o.rptr[o.N] = o.E;
+    // receivers: the negative literal receives the pair edge, the positive literal nothing
+    o.rptr[neg] = eo + v;
+    o.rptr[pos] = eo + v + 1;
+    o.rids[eo + v] = (int32_t)pair;
+    // senders: occurrences of the negative literal, then of the positive literal (increasing edge id = increasing
+    // literal position, the order of the occurrence list), then the pair edge
+    const uint32_t os = __ldg(I.occ_ptr + v), oe = __ldg(I.occ_ptr + v + 1);
+    const int64_t base = eo + os + v;  // every earlier variable contributed its occurrences and one pair edge
+    auto position = [&](uint32_t c) -> uint32_t {
+        uint32_t j = __ldg(I.row_ptr + c);
+        while ((__ldg(I.lits + j) >> 1) != v) j++;  // the variable occurs in the clause (exactly once: duplicates are refused)
+        return j;
+    };
+    uint32_t nneg = 0;
+    for (uint32_t q = os; q < oe; q++) nneg += __ldg(I.lits + position(__ldg(I.occ + q))) & 1u;
+    o.sptr[neg] = base;
+    o.sptr[pos] = base + nneg;
+    uint32_t in = 0, ip = 0;
+    for (uint32_t q = os; q < oe; q++) {
+        const uint32_t j = position(__ldg(I.occ + q));
+        if (__ldg(I.lits + j) & 1u)
+            o.sids[base + in++] = (int32_t)(eo + j);
+        else
+            o.sids[base + nneg + ip++] = (int32_t)(eo + j);
+    }
+    o.sids[base + (oe - os)] = (int32_t)pair;
+}
+
 }  // namespace gnn

@@ -37,3 +37,7 @@ struct sls_instance {
     void* d_blob = nullptr;   // one allocation holding every device array
     size_t blob_bytes = 0;
 };
+
+// Makes every instance of a batch resident on the current device (defined in api.cu): images of the missing ones
+// are built by several host threads, one allocation and one host-to-device copy each.
+int slsb_ensure_batch_on_device(sls_instance* const* insts, uint32_t n_inst);

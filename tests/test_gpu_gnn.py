@@ -64,6 +64,27 @@ def test_batched_lcg_equals_per_instance_graphs():
         off += graph["n_node"]
 
 
+def test_device_built_lcg_graph_equals_host_built(monkeypatch):
+    # sls_gnn_forward_lcg derives the graph arrays on the device from the resident CSRs; SLS_B200_LCG_HOST=1 forces
+    # the host builder.  Same arrays, same deterministic kernels: identical floats.
+    names = ["r3sat_test_random_KCNF3_100_210_6416893", "g4sat_easy_ca_00092", "ref_tests_medium", "g4sat_easy_ca_00092"]
+    insts = [eng.Instance.from_dimacs(golden_cnf(nm)) for nm in names]
+    insts.append(eng.Instance.from_clauses(4, [(1, -2), (3,), (-1, 2, -3, 4), (2, 3)]))
+    net = gnn.InteractionNetworkLCG(go.init_params(seed=11, bias_scale=0.1))
+    p_dev, d_dev = net.probabilities(insts, return_decoded=True)
+    monkeypatch.setenv("SLS_B200_LCG_HOST", "1")
+    p_host, d_host = net.probabilities(insts, return_decoded=True)
+    assert np.array_equal(d_dev, d_host)
+    assert all(np.array_equal(a, b) for a, b in zip(p_dev, p_host))
+    monkeypatch.delenv("SLS_B200_LCG_HOST")
+    # an empty clause is dropped by the reference (sat_instances.py:50): such a batch takes the host path
+    with_empty = eng.Instance.from_text("p cnf 3 3\n1 -2 0\n0\n2 3 0\n")
+    plain = eng.Instance.from_clauses(3, [(1, -2), (2, 3)])
+    p_a = net.probabilities([insts[0], with_empty])[1]
+    p_b = net.probabilities([insts[0], plain])[1]
+    assert np.array_equal(p_a, p_b)
+
+
 def test_graph_edge_cases():
     params = go.init_params(seed=3, mlp_layers=(32, 32), num_steps=2, bias_scale=0.1)
     net = gnn.InteractionNetworkLCG(params, num_message_passing_steps=2)
