@@ -386,11 +386,29 @@ extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignmen
         const uint64_t want_ctas = (uint64_t)sms * 32;
         uint32_t tiles_per_block = (uint32_t)std::max<uint64_t>(WARPS, (ntiles + want_ctas - 1) / want_ctas);
         tiles_per_block = (tiles_per_block + WARPS - 1) / WARPS * WARPS;
-        dim3 grid((ntiles + tiles_per_block - 1) / tiles_per_block, (unsigned)nslices);
-        if (d_v)
+        if (d_v) {
+            dim3 grid((ntiles + tiles_per_block - 1) / tiles_per_block, (unsigned)nslices);
             eval_sliced_kernel<WARPS, true><<<grid, WARPS * 32>>>(I, d_tq, d_v, pitch, d_e, batch, tiles_per_block);
-        else
-            eval_sliced_kernel<WARPS, false><<<grid, WARPS * 32>>>(I, d_tq, nullptr, pitch, d_e, batch, tiles_per_block);
+        } else {
+            // energies only: vertical counters, flushed every 7 tiles -- a warp wants a long run of tiles (14 = two
+            // flushes) as long as that still leaves every SM its 12 resident warps
+            const uint64_t warps_machine = (uint64_t)sms * 12, ctas_machine = (uint64_t)sms * 3;  // 168 registers: 3 CTAs per SM
+            uint32_t per_warp = (uint32_t)std::min<uint64_t>(14, std::max<uint64_t>(1, (uint64_t)ntiles * nslices / warps_machine));
+            if (per_warp >= 7) {  // among 7..14 tiles per warp take the run length that wastes least of the last wave
+                double best_eff = 0.0;
+                for (uint32_t pw = 7; pw <= 14; pw++) {
+                    const uint64_t ctas = (uint64_t)((ntiles + pw * WARPS - 1) / (pw * WARPS)) * nslices;
+                    const double waves = (double)ctas / (double)ctas_machine, eff = waves / std::ceil(waves);
+                    if (eff >= best_eff) best_eff = eff, per_warp = pw;
+                }
+            }
+            tiles_per_block = per_warp * WARPS;
+            dim3 grid((ntiles + tiles_per_block - 1) / tiles_per_block, (unsigned)nslices);
+            if (I.uniform_k && I.uniform_k <= 3)  // three pipelined literals
+                eval_energy_sliced_kernel<WARPS, 3><<<grid, WARPS * 32>>>(I, d_tq, d_e, batch, tiles_per_block);
+            else
+                eval_energy_sliced_kernel<WARPS, 4><<<grid, WARPS * 32>>>(I, d_tq, d_e, batch, tiles_per_block);
+        }
     }
     EV_TRY(cudaGetLastError());
     EV_TRY(cudaEventRecord(ev1));

@@ -71,16 +71,17 @@ __device__ __forceinline__ void and_literal(uint32_t (&viol)[SLICE_Q], uint32_t 
 // transposes row wi, the four sector gathers of row wi+1 and the literal words of row wi+2 are in flight: the
 // scan is bound by memory latency (DRAM for the literal stream, L2 for the gathers), not by any throughput.
 // The first four literals of a clause travel through the pipeline; longer clauses finish with a plain loop.
-struct ClauseRows {
+template <int NL = 4>
+struct ClauseRowsT {
     const DevInst& I;
     const uint32_t* __restrict__ tq;
     uint32_t c_next;             // clause whose literals are loaded next
     uint32_t s_cur, e_cur, s_nxt, e_nxt;
     bool ok_cur, ok_nxt;         // clause index < m
-    uint32_t l_cur[4], l_nxt[4];
-    Sector a[4];
+    uint32_t l_cur[NL], l_nxt[NL];
+    Sector a[NL];
 
-    __device__ __forceinline__ void fetch_lits(uint32_t c, uint32_t& s, uint32_t& e, bool& ok, uint32_t (&l)[4])
+    __device__ __forceinline__ void fetch_lits(uint32_t c, uint32_t& s, uint32_t& e, bool& ok, uint32_t (&l)[NL])
     {
         ok = c < I.m;
         s = e = 0;
@@ -94,15 +95,15 @@ struct ClauseRows {
             }
         }
 #pragma unroll
-        for (uint32_t t = 0; t < 4; t++) l[t] = e > s ? __ldcs(I.lits + min(s + t, e - 1u)) : 0u;  // tail: last literal again
+        for (uint32_t t = 0; t < NL; t++) l[t] = e > s ? __ldcs(I.lits + min(s + t, e - 1u)) : 0u;  // tail: last literal again
     }
-    __device__ __forceinline__ void gather(const uint32_t (&l)[4])
+    __device__ __forceinline__ void gather(const uint32_t (&l)[NL])
     {
 #pragma unroll
-        for (uint32_t t = 0; t < 4; t++) a[t] = ldg_sector_keep(tq + (size_t)(l[t] >> 1) * SLICE_Q);
+        for (uint32_t t = 0; t < NL; t++) a[t] = ldg_sector_keep(tq + (size_t)(l[t] >> 1) * SLICE_Q);
     }
     // c0 = this lane's clause in row 0
-    __device__ __forceinline__ ClauseRows(const DevInst& I_, const uint32_t* tq_, uint32_t c0) : I(I_), tq(tq_)
+    __device__ __forceinline__ ClauseRowsT(const DevInst& I_, const uint32_t* tq_, uint32_t c0) : I(I_), tq(tq_)
     {
         fetch_lits(c0, s_cur, e_cur, ok_cur, l_cur);
         gather(l_cur);
@@ -117,8 +118,8 @@ struct ClauseRows {
         for (uint32_t q = 0; q < SLICE_Q; q++) viol[q] = init;
         if (e_cur > s_cur) {
 #pragma unroll
-            for (uint32_t t = 0; t < 4; t++) and_literal(viol, l_cur[t], a[t]);  // AND is idempotent: repeats are harmless
-            for (uint32_t j = s_cur + 4; j < e_cur; j++) {
+            for (uint32_t t = 0; t < NL; t++) and_literal(viol, l_cur[t], a[t]);  // AND is idempotent: repeats are harmless
+            for (uint32_t j = s_cur + NL; j < e_cur; j++) {
                 const uint32_t l = __ldcs(I.lits + j);
                 and_literal(viol, l, ldg_sector_keep(tq + (size_t)(l >> 1) * SLICE_Q));
             }
@@ -127,12 +128,14 @@ struct ClauseRows {
         e_cur = e_nxt;
         ok_cur = ok_nxt;
 #pragma unroll
-        for (uint32_t t = 0; t < 4; t++) l_cur[t] = l_nxt[t];
+        for (uint32_t t = 0; t < NL; t++) l_cur[t] = l_nxt[t];
         gather(l_cur);
         fetch_lits(c_next, s_nxt, e_nxt, ok_nxt, l_nxt);
         c_next += 32u;
     }
 };
+
+using ClauseRows = ClauseRowsT<4>;
 
 // bytes[b][v] (the reference's int / bool arrays, one byte per variable) -> tq[slice][v][q]
 __global__ void transpose_assignments_kernel(const uint8_t* __restrict__ bytes, uint32_t* __restrict__ tq, uint32_t n, uint64_t batch,
@@ -213,6 +216,97 @@ __global__ void __launch_bounds__(WARPS * 32) eval_sliced_kernel(const DevInst I
             const uint32_t a = 32u * q + lane;
             if (a < valid && my_energy[q]) atomicAdd(energy + b0 + a, my_energy[q]);
         }
+    }
+}
+
+// Energies only (candidate energies, data_utils.py:123-130; sls_eval_assignments without the violated bits): no
+// transposition per row.  A lane keeps, for its own clauses, a bit-sliced ("vertical") counter per assignment: six
+// planes of 8 words, plane p holding bit p of the 256 counts.  Rows enter through carry-save adders, four rows per
+// round (Harley-Seal: 14 three-input logic ops per word per four rows); after at most 60 rows the planes are
+// transposed once (lane b then holds the plane bits of all 32 lanes for its assignments) and folded into the
+// energies with popcounts.  What remains per row is the literal stream, the sector gathers and ~60 logic
+// instructions: the kernel runs at the L2's random-sector rate (tools/ubench.cu measures that ceiling).
+__device__ __forceinline__ void csa(uint32_t& sum_io, uint32_t& carry, uint32_t a, uint32_t b)
+{
+    const uint32_t s = sum_io;
+    carry = (a & b) | (s & (a ^ b));  // one LOP3 (majority)
+    sum_io = s ^ a ^ b;               // one LOP3
+}
+
+template <int WARPS, int NL>
+__global__ void __launch_bounds__(WARPS * 32) eval_energy_sliced_kernel(const DevInst I, const uint32_t* __restrict__ tq_all,
+                                                                        uint32_t* __restrict__ energy, uint64_t batch, uint32_t tiles_per_block)
+{
+    constexpr int NP = 6;               // planes: counts up to 63
+    constexpr uint32_t FLUSH_TILES = 7; // 56 rows between flushes
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t slice = blockIdx.y;
+    const uint32_t* tq = tq_all + (size_t)slice * I.n * SLICE_Q;
+    const uint64_t b0 = (uint64_t)slice * SLICE_W;
+    const uint32_t valid = (uint32_t)min((uint64_t)SLICE_W, batch - b0);
+    const uint32_t ntiles = (I.mwords + TILE_WORDS - 1) / TILE_WORDS;
+    const uint32_t t_begin = blockIdx.x * tiles_per_block;
+    const uint32_t t_end = min(ntiles, t_begin + tiles_per_block);
+    const uint32_t per_warp = tiles_per_block / WARPS;  // tiles_per_block is a multiple of WARPS
+    const uint32_t t0 = min(t_end, t_begin + warp * per_warp), t1 = min(t_end, t0 + per_warp);
+    uint32_t my_energy[SLICE_Q];  // lane b, entry q: energy of assignment b0 + 32q + b
+    uint32_t P[NP][SLICE_Q];
+#pragma unroll
+    for (uint32_t q = 0; q < SLICE_Q; q++) {
+        my_energy[q] = 0;
+#pragma unroll
+        for (int p = 0; p < NP; p++) P[p][q] = 0;
+    }
+    auto flush = [&]() {
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            transpose32x8(P[p], lane);
+#pragma unroll
+            for (uint32_t q = 0; q < SLICE_Q; q++) {
+                my_energy[q] += (uint32_t)__popc(P[p][q]) << p;
+                P[p][q] = 0;
+            }
+        }
+    };
+    ClauseRowsT<NL> rows(I, tq, t0 * TILE_WORDS * 32u + lane);
+    uint32_t since_flush = 0;
+    for (uint32_t t = t0; t < t1; t++) {
+        uint32_t A[SLICE_Q], C1[SLICE_Q];
+#pragma unroll
+        for (uint32_t wi = 0; wi < TILE_WORDS; wi++) {
+            uint32_t viol[SLICE_Q];
+            rows.next(viol);
+#pragma unroll
+            for (uint32_t q = 0; q < SLICE_Q; q++) {
+                if ((wi & 1u) == 0) {
+                    A[q] = viol[q];
+                } else if ((wi & 3u) == 1) {
+                    csa(P[0][q], C1[q], A[q], viol[q]);
+                } else {
+                    uint32_t c2, c3;
+                    csa(P[0][q], c2, A[q], viol[q]);
+                    csa(P[1][q], c3, C1[q], c2);
+#pragma unroll
+                    for (int p = 2; p < NP - 1; p++) {  // ripple the fours
+                        const uint32_t tcarry = P[p][q] & c3;
+                        P[p][q] ^= c3;
+                        c3 = tcarry;
+                    }
+                    P[NP - 1][q] ^= c3;
+                }
+            }
+        }
+        if (++since_flush == FLUSH_TILES) {
+            flush();
+            since_flush = 0;
+        }
+    }
+    if (since_flush) flush();
+#pragma unroll
+    for (uint32_t q = 0; q < SLICE_Q; q++) {
+        const uint32_t a = 32u * q + lane;
+        if (a < valid && my_energy[q]) atomicAdd(energy + b0 + a, my_energy[q]);
     }
 }
 
