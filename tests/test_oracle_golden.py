@@ -235,3 +235,45 @@ def test_probsat_picks_proportionally_to_flip_probability():
         r = inst.run_sls("probsat", np.zeros(3), w, 1, 1, False, seed=6, chain_offset=chain)
         acc += r.best_assignment
     assert np.abs(acc / R - w / w.sum()).max() < 0.03
+
+
+# ---- the C oracle against an independent, naive model of lib.rs (oracle/sls_model.py) ----------------
+# Different data structures (hash set of clause contents, per-variable clause lists), different generator
+# (Mersenne Twister), different element order: only distributions can agree.  Two-sample tests at a fixed
+# false-alarm level; the chains of both sides are independent samples of what should be one process.
+def _ks_two_sample(a, b):
+    a, b = np.sort(np.asarray(a, float)), np.sort(np.asarray(b, float))
+    grid = np.concatenate([a, b])
+    d = np.abs(np.searchsorted(a, grid, side="right") / a.size - np.searchsorted(b, grid, side="right") / b.size).max()
+    return d, np.sqrt(-0.5 * np.log(0.001 / 2) * (a.size + b.size) / (a.size * b.size))  # critical value at alpha = 0.001
+
+
+@pytest.mark.parametrize("algo,pfb,mapping", [("moser", 0.0, True), ("probsat", 0.0, True), ("moser_single", 0.0, True),
+                                              ("schoening", 0.0, False), ("probsat", 0.4, True), ("moser", 0.3, False)])
+def test_c_oracle_and_naive_model_agree_in_distribution(algo, pfb, mapping):
+    from conftest import random_ksat
+    from oracle import sls_model
+
+    n, m, S, R = 40, 150, 400, 300  # alpha = 3.75: a few hundred steps, some chains hit the budget
+    clauses = random_ksat(n, m, 3, seed=31)
+    inst = so.Instance.from_clauses(n, clauses)
+    rng = np.random.default_rng(3)
+    wi, wr = rng.uniform(0.2, 0.8, n), rng.uniform(0.3, 0.7, n)  # a non-uniform oracle: weights matter
+    c = inst.run_sls(algo, wi, wr, S, R, True, mapping, pfb, seed=99)
+    p = sls_model.run_sls(algo, n, clauses, wi.tolist(), wr.tolist(), S, R, True, mapping, pfb, seed=7)
+    # solve fraction: two-proportion z test
+    f1, f2 = float(np.mean(c.found)), float(np.mean(p.found))
+    pool = (f1 + f2) / 2
+    z = abs(f1 - f2) / max(np.sqrt(2 * pool * (1 - pool) / R), 1e-9)
+    assert z < 4.0, (f1, f2)
+    # step counts (capped at the budget), initial energy and energy after 20 steps: Kolmogorov-Smirnov
+    for name, a, b in [("steps", c.steps, p.steps),
+                       ("initial energy", [t[0] for t in c.trajectories], [t[0] for t in p.trajectories]),
+                       ("energy after 20 steps", [t[min(20, len(t) - 1)] for t in c.trajectories],
+                        [t[min(20, len(t) - 1)] for t in p.trajectories])]:
+        d, crit = _ks_two_sample(a, b)
+        assert d < crit, (name, d, crit)
+    # and both honour the invariants of lib.rs:292-300
+    for r in (c, p):
+        assert all((t[-1] == 0) == bool(f) for t, f in zip(r.trajectories, r.found))
+        assert all(len(t) == s + 1 for t, s in zip(r.trajectories, r.steps))
