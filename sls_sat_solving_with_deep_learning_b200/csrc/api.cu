@@ -1029,11 +1029,14 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     CUDA_TRY(cudaMemset(p_err.base, 0, size_t(n_inst) * 4));
 
     // ---- per-instance kernel arguments, grouped by variant: 0 = k3s, 1 = generic<smem>, 2 = generic<hbm>
-    // (3 = k3d: two chains per warp, small k<=3 instances; test hook SLS_B200_NO_DUAL=1)
+    // (3 = k3d: two chains per warp, small k<=3 instances, 4 = four chains per warp for the smallest;
+    // test hooks SLS_B200_NO_DUAL=1, SLS_B200_NO_QUAD=1)
     const bool no_dual = [] { const char* f = std::getenv("SLS_B200_NO_DUAL"); return f && f[0] == '1'; }();
-    std::vector<WalkArgs> items[4];
-    std::vector<uint32_t> cta_begin[4], owner[4];
-    size_t smem_max[4] = {0, 0, 0, 0};
+    const bool no_quad = [] { const char* f = std::getenv("SLS_B200_NO_QUAD"); return f && f[0] == '1'; }();
+    constexpr int NG = 5;
+    std::vector<WalkArgs> items[NG];
+    std::vector<uint32_t> cta_begin[NG], owner[NG];
+    size_t smem_max[NG] = {0, 0, 0, 0, 0};
     for (uint32_t i = 0; i < n_inst; i++) {
         const DevInst& I = insts[i]->dev;
         const ItemPlan& pl = plan[i];
@@ -1071,14 +1074,15 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
             build_crecx_kernel<<<(I.m + 255) / 256, 256>>>(I.crec, I.occ_ptr, a.w, const_cast<uint4*>(a.crecx), I.m, I.n, params->algo);
         // small k<=3 instances run two chains per warp (walk_k3d.cuh): 4 warps = 8 chains per CTA
         const bool dual = pl.k3 && !no_dual && walk_k3d_supports(a);
+        const bool quad = dual && !no_quad && walk_k3q_supports(a);
         uint32_t chains_per_cta = pl.wpb;
         size_t smem_bytes = pl.smem_bytes;
         if (dual) {
             a.warps_per_block = 4;
-            chains_per_cta = 8;
+            chains_per_cta = quad ? 16 : 8;
             smem_bytes = size_t(chains_per_cta) * (size_t(I.slab_words) + HRING_WORDS) * 4;
         }
-        const int g = dual ? 3 : pl.k3 ? 0 : pl.smem ? 1 : 2;
+        const int g = quad ? 4 : dual ? 3 : pl.k3 ? 0 : pl.smem ? 1 : 2;
         if (cta_begin[g].empty()) cta_begin[g].push_back(0);
         cta_begin[g].push_back(cta_begin[g].back() + (uint32_t)((R + chains_per_cta - 1) / chains_per_cta));
         items[g].push_back(a);
@@ -1090,8 +1094,8 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     cudaEvent_t ev0, ev1;
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
-    Pool d_items[4], d_cta[4];
-    for (int g = 0; g < 4; g++) {
+    Pool d_items[NG], d_cta[NG];
+    for (int g = 0; g < NG; g++) {
         if (items[g].empty()) continue;
         CUDA_TRY(alloc(d_items[g], items[g].size() * sizeof(WalkArgs)));
         CUDA_TRY(alloc(d_cta[g], cta_begin[g].size() * 4));
@@ -1102,15 +1106,18 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     if (smem_max[0]) CUDA_TRY(cudaFuncSetAttribute(k3_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[0]));
     if (smem_max[1])
         CUDA_TRY(cudaFuncSetAttribute(walk_generic_batch_kernel_for<true>(params->algo), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[1]));
-    const WalkK3BatchKernel k3d_batch = walk_k3d_batch_kernel_for(params->algo);
+    const WalkK3BatchKernel k3d_batch = walk_k3d_batch_kernel_for(params->algo, 16), k3q_batch = walk_k3d_batch_kernel_for(params->algo, 8);
     if (smem_max[3]) CUDA_TRY(cudaFuncSetAttribute(k3d_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[3]));
+    if (smem_max[4]) CUDA_TRY(cudaFuncSetAttribute(k3q_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[4]));
     CUDA_TRY(cudaEventRecord(ev0));
-    for (int g = 0; g < 4; g++) {
+    for (int g = 0; g < NG; g++) {
         if (items[g].empty()) continue;
         const WalkArgs* di = reinterpret_cast<const WalkArgs*>(d_items[g].base);
         const uint32_t* dc = reinterpret_cast<const uint32_t*>(d_cta[g].base);
         const uint32_t ni = (uint32_t)items[g].size(), blocks = cta_begin[g].back();
-        if (g == 3)
+        if (g == 4)
+            k3q_batch<<<blocks, 128, smem_max[4]>>>(di, dc, ni);
+        else if (g == 3)
             k3d_batch<<<blocks, 128, smem_max[3]>>>(di, dc, ni);
         else if (g == 0)
             k3_batch<<<blocks, 128, smem_max[0]>>>(di, dc, ni);

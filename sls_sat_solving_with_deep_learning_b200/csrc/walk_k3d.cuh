@@ -8,6 +8,10 @@
 // step's worth of instructions.  (Per-half lane masks were measured and rejected: every collective with a
 // non-uniform mask compiles to a MATCH.ANY / BRA.DIV sequence, see DESIGN.md.)
 //
+// The same body with LANES = 8 carries FOUR chains per warp (quarter-warps); it serves the smallest instances (at most
+// four level-1 counters = 4096 clauses: configs 1 and 4), where an occurrence list (~13 entries) takes two rounds of 8
+// lanes and the 32 words of a counter group are four per lane.
+//
 // Same records (crecx / orec), same random streams and the same trajectory per chain as walk_k3.cuh.
 // Restrictions (the caller falls back to walk_k3s_batch_kernel otherwise): at most 16 level-1 counters
 // (16,384 clauses), rules "moser" and "probsat" without the greedy mix, no trajectories.
@@ -26,17 +30,20 @@ __host__ __device__ inline bool walk_k3d_supports(const WalkArgs& a)
            (a.algo == ALGO_MOSER || a.algo == ALGO_PROBSAT);
 }
 
-// inclusive scan over the 16 lanes of a half-warp
-__device__ __forceinline__ uint32_t half_incl_scan(uint32_t v)
+__host__ __device__ inline bool walk_k3q_supports(const WalkArgs& a) { return walk_k3d_supports(a) && a.inst.ngroups <= 4; }
+
+// inclusive scan over the LANES lanes of a sub-warp (shfl.up clamp operand: (32 - LANES) << 8)
+template <int LANES>
+__device__ __forceinline__ uint32_t sub_incl_scan(uint32_t v)
 {
 #pragma unroll
-    for (int d = 1; d < 16; d <<= 1) {
+    for (int d = 1; d < LANES; d <<= 1) {
         asm volatile(
             "{ .reg .pred p; .reg .u32 t;\n"
-            "  shfl.sync.up.b32 t|p, %0, %1, 0x1000, 0xffffffff;\n"
+            "  shfl.sync.up.b32 t|p, %0, %1, %2, 0xffffffff;\n"
             "  @p add.u32 %0, %0, t; }\n"
             : "+r"(v)
-            : "r"(d));
+            : "r"(d), "n"((32 - LANES) << 8));
     }
     return v;
 }
@@ -44,7 +51,9 @@ __device__ __forceinline__ uint32_t half_incl_scan(uint32_t v)
 // The walk stream of one chain, buffered in a 64-word ring that the chain's 16 lanes refill together.
 // Every method that contains a barrier is called by all 32 lanes of the warp (both chains), with `need` telling
 // which half actually refills.
+template <int LANES>
 struct HalfRing {
+    static constexpr int BLOCKS = 16 / LANES;  // Philox blocks per lane and refill
     ChainKey ck;
     uint64_t base;  // word position of ring[0], multiple of 4
     uint32_t cur;   // shared-window byte address of the next word
@@ -58,15 +67,23 @@ struct HalfRing {
     __device__ __forceinline__ bool low(uint32_t words) const { return cur > ring + (HRING_WORDS - words) * 4u; }
     __device__ __forceinline__ void fill_together(bool need)
     {
-        uint4 x = make_uint4(0, 0, 0, 0);
+        uint4 x[BLOCKS];
         if (need) {
             uint2 k = ck.key;
             asm volatile("" : "+r"(k.x), "+r"(k.y));  // keep the key schedule inside this cold path
-            const uint64_t b = (base >> 2) + l16;
-            x = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)(b >> 32), ck.chain_lo, ck.chain_hi_stream), k);
+#pragma unroll
+            for (int i = 0; i < BLOCKS; i++) {
+                const uint64_t b = (base >> 2) + l16 + i * LANES;
+                x[i] = philox4x32_10(make_uint4((uint32_t)b, (uint32_t)(b >> 32), ck.chain_lo, ck.chain_hi_stream), k);
+            }
         }
         __syncwarp();  // earlier readers of the rings are done
-        if (need) asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ring + l16 * 16u), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+        if (need) {
+#pragma unroll
+            for (int i = 0; i < BLOCKS; i++)
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ring + (l16 + i * LANES) * 16u), "r"(x[i].x), "r"(x[i].y), "r"(x[i].z),
+                             "r"(x[i].w) : "memory");
+        }
         __syncwarp();
     }
     __device__ __forceinline__ void refill_together(bool need)
@@ -96,38 +113,41 @@ struct HalfRing {
 };
 
 // `block` = index of this CTA among the CTAs of the item; a CTA of W warps carries 2W chains
-template <int ALGO>
+template <int ALGO, int LANES>
 __device__ __forceinline__ void walk_k3d_body(const WalkArgs& A, uint32_t block, uint32_t* sm)
 {
+    constexpr uint32_t CH = 32 / LANES;    // chains per warp
+    constexpr uint32_t PER = 32 / LANES;   // bit positions / words / clauses a lane owns where a full warp owns one
+    constexpr uint32_t SUBMASK = LANES == 16 ? 0xffffu : 0xffu;
     const int lane = threadIdx.x & 31;
-    const int l16 = lane & 15;
-    const uint32_t half = (uint32_t)lane >> 4, hshift = half * 16u;
+    const int l16 = lane & (LANES - 1);    // lane within the chain's sub-warp
+    const uint32_t half = (uint32_t)lane / LANES, hshift = half * LANES;
     const uint32_t warp = threadIdx.x >> 5;
-    const uint32_t slot = warp * 2u + half;  // this chain's slot in the CTA
-    const uint64_t run = ((uint64_t)block * A.warps_per_block + warp) * 2u + half;
+    const uint32_t slot = warp * CH + half;  // this chain's slot in the CTA
+    const uint64_t run = ((uint64_t)block * A.warps_per_block + warp) * CH + half;
     const bool valid = run < A.nruns;
     if (!__any_sync(FULL, valid)) return;  // (warp-uniform)
     const DevInst& I = A.inst;
-    const uint32_t nslots = A.warps_per_block * 2u;
+    const uint32_t nslots = A.warps_per_block * CH;
     uint32_t sA = (uint32_t)__cvta_generic_to_shared(sm) + slot * I.slab_words * 4u;  // abits
     uint32_t sV = sA + I.off_v * 4u;                                                   // vbits
     uint32_t sL = sA + I.off_l1 * 4u;                                                  // level-1 counters
     asm volatile("" : "+r"(sA), "+r"(sV), "+r"(sL));  // keep the three bases in registers (see walk_k3.cuh)
     const uint64_t chain = A.chain_offset + (valid ? run : 0);
 
-    auto hballot = [hshift](bool p) -> uint32_t { return (__ballot_sync(FULL, p) >> hshift) & 0xffffu; };
-    const uint32_t hmask = 0xffffu << hshift;
+    auto hballot = [hshift](bool p) -> uint32_t { return (__ballot_sync(FULL, p) >> hshift) & SUBMASK; };
+    const uint32_t hmask = SUBMASK << hshift;
     auto hcount = [hmask](bool p) -> uint32_t { return __popc(__ballot_sync(FULL, p) & hmask); };  // votes in this half
-    auto hshfl = [](uint32_t v, uint32_t src) -> uint32_t { return __shfl_sync(FULL, v, src, 16); };
+    auto hshfl = [](uint32_t v, uint32_t src) -> uint32_t { return __shfl_sync(FULL, v, src, LANES); };
     // literal code l = 2*var + neg is TRUE iff bit(var) != neg
     auto lit_true = [sA](uint32_t l) -> uint32_t { return (__funnelshift_r(lds32(sA + (l >> 6) * 4u), 0u, l >> 1) ^ l) & 1u; };
 
     // ---- chain init: assignment from the init stream (lib.rs:206-210) ...
-    for (uint32_t i = l16; i < I.slab_words; i += 16) sts32(sA + i * 4u, 0u);
+    for (uint32_t i = l16; i < I.slab_words; i += LANES) sts32(sA + i * 4u, 0u);
     __syncwarp();
     {
         const ChainKey ck(A.seed, chain, STREAM_INIT);
-        for (uint32_t w = l16; w < I.nwords; w += 16) {
+        for (uint32_t w = l16; w < I.nwords; w += LANES) {
             uint32_t bits = 0;
 #pragma unroll 4
             for (uint32_t b = 0; b < 16; b++) {
@@ -147,24 +167,26 @@ __device__ __forceinline__ void walk_k3d_body(const WalkArgs& A, uint32_t block,
         }
         __syncwarp();
     }
-    // ... and the full scan (lib.rs:213-214): a lane evaluates clauses l16 and l16+16 of every vbits word
+    // ... and the full scan (lib.rs:213-214): a lane evaluates clauses l16, l16 + LANES, ... of every vbits word
     uint32_t nf = 0;
     const uint4* __restrict__ crec = I.crec;
     for (uint32_t g = 0; g < I.ngroups; g++) {
         uint32_t acc = 0;
         const uint32_t wend = min(32u, I.mwords - g * 32u);
         for (uint32_t wi = 0; wi < wend; wi++) {
-            bool viol[2];
+            bool viol[PER];
 #pragma unroll
-            for (uint32_t h = 0; h < 2; h++) {
-                const uint32_t c = (g * 32u + wi) * 32u + h * 16u + l16;
+            for (uint32_t h = 0; h < PER; h++) {
+                const uint32_t c = (g * 32u + wi) * 32u + h * LANES + l16;
                 viol[h] = false;
                 if (c < I.m) {
                     const uint4 cr = __ldg(crec + c);
                     viol[h] = !lit_true(cr.x) && (cr.w < 2 || !lit_true(cr.y)) && (cr.w < 3 || !lit_true(cr.z));
                 }
             }
-            const uint32_t word = hballot(viol[0]) | hballot(viol[1]) << 16;
+            uint32_t word = 0;
+#pragma unroll
+            for (uint32_t h = 0; h < PER; h++) word |= hballot(viol[h]) << (h * LANES);
             if (l16 == 0) sts32(sV + (g * 32u + wi) * 4u, word);
             acc += __popc(word);
         }
@@ -175,12 +197,12 @@ __device__ __forceinline__ void walk_k3d_body(const WalkArgs& A, uint32_t block,
     if (!valid) nf = 0;  // an absent chain never steps
 
     // the rings of the CTA's chains sit behind their slabs
-    HalfRing rng(A.seed, chain, (uint32_t)__cvta_generic_to_shared(sm) + (nslots * I.slab_words + slot * HRING_WORDS) * 4u, l16);
+    HalfRing<LANES> rng(A.seed, chain, (uint32_t)__cvta_generic_to_shared(sm) + (nslots * I.slab_words + slot * HRING_WORDS) * 4u, l16);
     uint32_t best = I.m;
     uint32_t* best_bits = A.best_bits + (valid ? run : 0) * (size_t)I.nwords;
     auto save_best = [&]() {
         best = nf;
-        for (uint32_t w = l16; w < I.nwords; w += 16) best_bits[w] = lds32(sA + w * 4u);
+        for (uint32_t w = l16; w < I.nwords; w += LANES) best_bits[w] = lds32(sA + w * 4u);
     };
     if (valid && nf < best) save_best();
 
@@ -192,29 +214,43 @@ __device__ __forceinline__ void walk_k3d_body(const WalkArgs& A, uint32_t block,
 
     // Re-evaluation of the clauses of a flipped variable (lib.rs:278-287) for both chains at once: a lane owns one
     // occurrence record of its chain's variable; len = 0 for a half that has nothing to update this round.
+    // (RPL = records per lane and round.  Two per lane for quarter-warps -- one trip to L2 for a typical list of ~13
+    // entries instead of two dependent ones -- was measured and is slower: 5.35 vs 5.62 G flips/s on the C1-shaped
+    // batch; the walk is bound by issue slots there, not by that latency.)
+    constexpr uint32_t RPL = 1;
     auto update_var = [&](uint32_t os, uint32_t len, uint32_t av) {
-        for (uint32_t base = 0; __any_sync(FULL, base < len); base += 16) {
-            const uint32_t o = base + l16;
-            const bool act = o < len;
-            const uint4 orc = __ldg(orec + (os + min(o, max(len, 1u) - 1u)));  // past the end: a valid record, masked
-            const uint32_t va = sV + (orc.x >> 5) * 4u;
-            const uint32_t vword = lds32(va);
-            const uint32_t bit = 1u << (orc.x & 31);
-            const bool viol = act & (av == orc.w) & !(lit_true(orc.y) | lit_true(orc.z));
-            const bool cur = act & ((vword & bit) != 0);
-            const bool ins = viol && !cur;  // HashSet::insert of a new element
-            const bool rem = !viol && cur;  // HashSet::remove of a present element
-            if (ins | rem) {
-                atoms_xor(va, bit);
-                atoms_add(sL + (orc.x >> 10) * 4u, ins ? 1u : 0xffffffffu);
+        for (uint32_t base = 0; __any_sync(FULL, base < len); base += RPL * LANES) {
+            uint4 orc[RPL];
+            bool act[RPL];
+#pragma unroll
+            for (uint32_t h = 0; h < RPL; h++) {
+                const uint32_t o = base + l16 + h * LANES;
+                act[h] = o < len;
+                orc[h] = __ldg(orec + (os + min(o, max(len, 1u) - 1u)));  // past the end: a valid record, masked
             }
-            nf += hcount(ins) - hcount(rem);
+#pragma unroll
+            for (uint32_t h = 0; h < RPL; h++) {
+                const uint32_t va = sV + (orc[h].x >> 5) * 4u;
+                const uint32_t vword = lds32(va);
+                const uint32_t bit = 1u << (orc[h].x & 31);
+                const bool viol = act[h] & (av == orc[h].w) & !(lit_true(orc[h].y) | lit_true(orc[h].z));
+                const bool cur = act[h] & ((vword & bit) != 0);
+                const bool ins = viol && !cur;  // HashSet::insert of a new element
+                const bool rem = !viol && cur;  // HashSet::remove of a present element
+                if (ins | rem) {
+                    atoms_xor(va, bit);
+                    atoms_add(sL + (orc[h].x >> 10) * 4u, ins ? 1u : 0xffffffffu);
+                }
+                nf += hcount(ins) - hcount(rem);
+            }
         }
         __syncwarp();
     };
 
     const bool few_groups = I.ngroups <= 4;
-    const uint32_t lt_lo = (1u << l16) - 1u, lt_hi = (1u << (l16 + 16)) - 1u;
+    uint32_t lt[PER];  // bits below position l16 + h * LANES
+#pragma unroll
+    for (uint32_t h = 0; h < PER; h++) lt[h] = (1u << (l16 + h * LANES)) - 1u;
     bool active = nf > 0 && budget > 0;  // per chain
     while (__any_sync(FULL, active)) {
         if (active) steps++;
@@ -255,27 +291,48 @@ __device__ __forceinline__ void walk_k3d_body(const WalkArgs& A, uint32_t block,
             g = (r >= p1 ? 1u : 0u) + (r >= p2 ? 1u : 0u) + (r >= p3 ? 1u : 0u);
             r -= g == 0 ? 0u : g == 1 ? p1 : g == 2 ? p2 : p3;
             g = active ? g : 0u;  // (an idle chain has r = 0 and may see an empty set)
-        } else {
+        } else if (LANES == 16) {
             const uint32_t cntA = lds32(sL + l16 * 4u);
-            const uint32_t inclA = half_incl_scan(cntA);
+            const uint32_t inclA = sub_incl_scan<LANES>(cntA);
             g = hcount(r >= inclA) & 15u;
             r -= hshfl(inclA - cntA, g);
+        } else {
+            g = 0;  // (not reached: the four-chain form is only chosen for instances with at most four counters)
         }
-        const uint2 ww = lds64(sV + (g * 32u + 2u * l16) * 4u);
-        const uint32_t pc0 = __popc(ww.x), pc = pc0 + __popc(ww.y);
-        const uint32_t inclB = half_incl_scan(pc);
-        const uint32_t srcB = hcount(r >= inclB) & 15u;
+        // the lane's PER words of the group, their popcounts, and the scan over the sub-warp
+        uint32_t ww[PER];
+        if constexpr (LANES == 16) {
+            const uint2 t = lds64(sV + (g * 32u + 2u * l16) * 4u);
+            ww[0] = t.x, ww[1] = t.y;
+        } else {
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ww[0]), "=r"(ww[1]), "=r"(ww[2]), "=r"(ww[3]) : "r"(sV + (g * 32u + 4u * l16) * 4u));
+        }
+        uint32_t pc = 0;
+#pragma unroll
+        for (uint32_t h = 0; h < PER; h++) pc += __popc(ww[h]);
+        const uint32_t inclB = sub_incl_scan<LANES>(pc);
+        const uint32_t srcB = hcount(r >= inclB) & (LANES - 1);
         r -= hshfl(inclB - pc, srcB);
-        const uint32_t w0 = hshfl(ww.x, srcB), w1 = hshfl(ww.y, srcB);
-        const uint32_t first = __popc(w0);
-        const bool second = r >= first;
-        if (second) r -= first;
-        const uint32_t wsel = second ? w1 : w0;
-        // the r-th set bit of wsel: a lane tests positions l16 and l16 + 16, exactly one test of the half hits
-        const bool hit_lo = ((wsel >> l16) & 1u) && __popc(wsel & lt_lo) == r;
-        const bool hit_hi = ((wsel >> (l16 + 16)) & 1u) && __popc(wsel & lt_hi) == r;
-        const uint32_t pos = bfind(hballot(hit_lo) | hballot(hit_hi) << 16);
-        const uint32_t c = active ? (g * 32u + 2u * srcB + (second ? 1u : 0u)) * 32u + (pos & 31u) : 0u;
+        // every lane walks its own words with the rank (meaningful in lane srcB only), then srcB's verdict is broadcast
+        uint32_t widx = 0, wmine = ww[0], rr = r;
+#pragma unroll
+        for (uint32_t h = 0; h + 1 < PER; h++) {
+            const uint32_t cnt = __popc(ww[h]);
+            const bool next = widx == h && rr >= cnt;
+            if (next) rr -= cnt, widx = h + 1, wmine = ww[h + 1];
+        }
+        const uint32_t wsel = hshfl(wmine, srcB);
+        const uint32_t wr = hshfl(widx | rr << 2, srcB);
+        r = wr >> 2;
+        // the r-th set bit of wsel: a lane tests positions l16 + h * LANES, exactly one test of the sub-warp hits
+        uint32_t hits = 0;
+#pragma unroll
+        for (uint32_t h = 0; h < PER; h++) {
+            const bool hit = ((wsel >> (l16 + h * LANES)) & 1u) && __popc(wsel & lt[h]) == r;
+            hits |= hballot(hit) << (h * LANES);
+        }
+        const uint32_t pos = bfind(hits);
+        const uint32_t c = active ? (g * 32u + PER * srcB + (wr & 3u)) * 32u + (pos & 31u) : 0u;
 
         // ---- the clause record (see build_crecx_kernel)
         const uint4* rec = crecx + CRECX_QUADS * c;
@@ -344,7 +401,7 @@ __device__ __forceinline__ void walk_k3d_body(const WalkArgs& A, uint32_t block,
     }
 }
 
-template <int ALGO>
+template <int ALGO, int LANES>
 __global__ void __launch_bounds__(128, 8) walk_k3d_batch_kernel(const WalkArgs* __restrict__ items, const uint32_t* __restrict__ cta_begin,
                                                                 uint32_t n_items)
 {
@@ -352,12 +409,14 @@ __global__ void __launch_bounds__(128, 8) walk_k3d_batch_kernel(const WalkArgs* 
     __shared__ WalkArgs item;
     const uint32_t it = find_item(cta_begin, n_items, blockIdx.x);
     load_item(item, items + it);
-    walk_k3d_body<ALGO>(item, blockIdx.x - __ldg(cta_begin + it), sm);
+    walk_k3d_body<ALGO, LANES>(item, blockIdx.x - __ldg(cta_begin + it), sm);
 }
 
-inline WalkK3BatchKernel walk_k3d_batch_kernel_for(int algo)
+// lanes = 16: two chains per warp; lanes = 8: four
+inline WalkK3BatchKernel walk_k3d_batch_kernel_for(int algo, int lanes)
 {
-    return algo == ALGO_MOSER ? walk_k3d_batch_kernel<ALGO_MOSER> : walk_k3d_batch_kernel<ALGO_PROBSAT>;
+    if (lanes == 8) return algo == ALGO_MOSER ? walk_k3d_batch_kernel<ALGO_MOSER, 8> : walk_k3d_batch_kernel<ALGO_PROBSAT, 8>;
+    return algo == ALGO_MOSER ? walk_k3d_batch_kernel<ALGO_MOSER, 16> : walk_k3d_batch_kernel<ALGO_PROBSAT, 16>;
 }
 
 }  // namespace slsb

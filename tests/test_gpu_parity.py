@@ -521,13 +521,17 @@ def test_walk_fuzz_against_oracle(seed):
 
 
 @pytest.mark.parametrize("algo", ["moser", "probsat"])
-@pytest.mark.parametrize("dual", [True, False])
+@pytest.mark.parametrize("dual", ["quad", "dual", "single"])
 def test_batch_two_chains_per_warp_matches_oracle(expected, algo, dual, monkeypatch):
     # without the greedy mix, small k<=3 instances of a batch run two chains per warp (walk_k3d.cuh): every chain
     # must still follow the oracle's trajectory (steps, solved flag, best energy, best assignment), also with a
     # chain count that leaves half-empty warps, boundary weights and short clauses
-    if not dual:
+    # ("quad": the smallest instances -- at most 4096 clauses -- run four chains per warp, the rest two; "dual": two
+    # everywhere; "single": walk_k3s_batch, one chain per warp)
+    if dual == "single":
         monkeypatch.setenv("SLS_B200_NO_DUAL", "1")
+    if dual == "dual":
+        monkeypatch.setenv("SLS_B200_NO_QUAD", "1")
     rng = np.random.default_rng(17)
     names = [n for n in expected if n.startswith("r3sat")]
     insts, oracles = [], []
@@ -535,7 +539,7 @@ def test_batch_two_chains_per_warp_matches_oracle(expected, algo, dual, monkeypa
         g, o = both(n)
         insts.append(g)
         oracles.append(o)
-    for n, m, seed in [(40, 150, 1), (700, 2600, 2), (2, 2, 0)]:
+    for n, m, seed in [(40, 150, 1), (700, 2600, 2), (2, 2, 0), (1100, 4096, 3), (1200, 4500, 4)]:  # 4096 clauses: the last four-chain size
         clauses = [(1, 2), (-1, -2)] if n == 2 else _mixed_short_clauses(n, m, seed)
         insts.append(eng.Instance.from_clauses(n, clauses))
         oracles.append(so.Instance.from_clauses(n, clauses))
@@ -544,7 +548,7 @@ def test_batch_two_chains_per_warp_matches_oracle(expected, algo, dual, monkeypa
     if algo == "moser":
         w_res[0][:5] = 0.0
         w_res[0][5:10] = 1.0
-    for nruns in (21, 8):
+    for nruns in (21, 8, 3):
         batch = eng.run_sls_batch(insts, algo, w_init, w_res, 300, nruns, True, 0.0, seed=70)
         for i, (oi, r) in enumerate(zip(oracles, batch)):
             o = oi.run_sls(algo, w_init[i], w_res[i], 300, nruns, False, True, 0.0, seed=70 + i)
