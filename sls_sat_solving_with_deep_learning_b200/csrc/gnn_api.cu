@@ -200,7 +200,8 @@ extern "C" int sls_gnn_model_create(const float* blob, uint64_t blob_len, int32_
         return rc;
     }
     m->readout_b = *p;
-    cudaError_t e = cudaFuncSetAttribute(mlp_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(mlp_ln_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
     if (e != cudaSuccess) {
         sls_gnn_model_free(m);
         return sls_set_error_internal(SLS_ERR_CUDA, std::string("cudaFuncSetAttribute(mlp_ln_kernel): ") + cudaGetErrorString(e));
@@ -232,7 +233,16 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
     a.ln_scale = w.ln_scale, a.ln_offset = w.ln_offset;
     a.out = out;
     const unsigned blocks = (unsigned)((rows + TILE_M - 1) / TILE_M);
-    mlp_ln_kernel<<<blocks, MLP_THREADS, MLP_SMEM_BYTES>>>(a);
+    // persistent three-role kernel, one CTA per SM; SLS_B200_GNN_ONE_TILE=1 selects the one-tile-per-CTA kernel
+    static const bool one_tile = [] { const char* f = std::getenv("SLS_B200_GNN_ONE_TILE"); return f && f[0] == '1'; }();
+    if (one_tile) {
+        mlp_ln_kernel<<<blocks, MLP_THREADS, MLP_SMEM_BYTES>>>(a);
+    } else {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        mlp_ln_persistent_kernel<<<std::min<unsigned>(blocks, (unsigned)sms), MLPP_THREADS, MLP_SMEM_BYTES>>>(a);
+    }
     m->launches++;
     G_TRY(cudaGetLastError());
     return SLS_OK;

@@ -389,6 +389,253 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
+// ---- the same update as a persistent, three-role kernel ------------------------------------------
+// One CTA per SM walks over tiles (tile = blockIdx.x, += gridDim.x).  Roles:
+//   warps 0-3  producers: stage the A operand slab by slab (GEMM1: gathered rows; GEMM2: ReLU(acc1 + b1) out of TMEM);
+//   warp  4    one lane issues the weight copies (TMA bulk) and the MMAs;
+//   warps 5-8  epilogue: LayerNorm(ReLU(acc2 + b2)) out of TMEM straight to global memory.
+// With the epilogue on its own warps, the producers go from the last GEMM2 slab of a tile directly to the first GEMM1
+// slab of the next one, so the tensor pipe keeps running through the epilogue, the TMEM allocation, the barrier setup
+// and the parameter staging that the one-tile kernel pays per tile.  Slabs are numbered globally (J) across tiles, so
+// the stage / barrier parities of the one-tile kernel carry over unchanged; two more barriers hand acc2 back and forth:
+//   sAccFull (tcgen05.commit after the last slab of a tile) -> epilogue may read acc2,
+//   sAccFree (128 epilogue threads, after their last TMEM read) -> the issuer may overwrite acc2 (first GEMM2 MMA of
+//   the next tile).  acc1 needs no barrier: the producers read it (GEMM2 staging of tile t) before they stage, in
+//   program order, the GEMM1 slabs whose MMAs overwrite it.
+static constexpr int MLPP_THREADS = MLP_PRODUCERS + 32 + 128;
+
+__global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(const MlpArgs P)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sAst = base;
+    const uint32_t sBst = base + A_STAGES * A_STAGE_BYTES;
+    const uint32_t sFull = sBst + B_STAGES * B_STAGE_BYTES;
+    const uint32_t sDone = sFull + 8 * B_STAGES;
+    const uint32_t sArdy = sDone + 8 * DONE_BARS;
+    const uint32_t sAccFull = sArdy + 8 * A_STAGES;
+    const uint32_t sAccFree = sAccFull + 8;
+    const uint32_t sTmem = sAccFree + 8;
+    const uint32_t sPar = sFull + 128;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const bool producer = tid < MLP_PRODUCERS;
+    const bool epilogue = tid >= MLP_PRODUCERS + 32;
+    const int ntiles = (P.rows + TILE_M - 1) / TILE_M;
+
+    if (tid == 0) {
+        for (int i = 0; i < B_STAGES; i++) mbar_init(sFull + 8 * i, 1);
+        for (int i = 0; i < DONE_BARS; i++) mbar_init(sDone + 8 * i, 1);
+        for (int i = 0; i < A_STAGES; i++) mbar_init(sArdy + 8 * i, MLP_PRODUCERS);
+        mbar_init(sAccFull, 1);
+        mbar_init(sAccFree, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < MAX_N; i += MLPP_THREADS) {
+        const bool in = i < P.h2;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + i * 4), "f"(i < P.n2 ? __ldg(P.b2 + i) : 0.f) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + (MAX_N + i) * 4), "f"(in ? __ldg(P.ln_scale + i) : 0.f) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + (2 * MAX_N + i) * 4), "f"(in ? __ldg(P.ln_offset + i) : 0.f) : "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + (sTmem - base));
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;  // a warp reaches the TMEM lane quarter warp % 4
+    const uint32_t n1s = (uint32_t)P.k1_slabs, n2s = (uint32_t)P.k2_slabs, S = n1s + n2s;
+    auto wait_done = [&](uint32_t J) { mbar_wait(sDone + 8 * (J % DONE_BARS), (J / DONE_BARS) & 1u); };
+
+    if (producer) {
+        const int kA = P.d[0] + P.d[1] + P.d[2];
+        auto put_split = [&](uint32_t stage_base, int u, float4 x) {
+            float4 hi, lo;
+            hi.x = round_tf32(x.x), hi.y = round_tf32(x.y), hi.z = round_tf32(x.z), hi.w = round_tf32(x.w);
+            lo.x = round_tf32(x.x - hi.x), lo.y = round_tf32(x.y - hi.y), lo.z = round_tf32(x.z - hi.z), lo.w = round_tf32(x.w - hi.w);
+            const uint32_t off = sw128_off(tid, u);
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + A_SLAB_BYTES + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+        };
+        const float* rp[3] = {nullptr, nullptr, nullptr};
+        auto set_rows = [&](int tile) {
+            const int my_row = min(tile * TILE_M + tid, P.rows - 1);  // rows past the end re-read the last row; never stored
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+                if (P.d[j] > 0) {
+                    const int r = P.idx[j] ? __ldg(P.idx[j] + my_row) : my_row;
+                    rp[j] = P.src[j] + (size_t)r * P.d[j];
+                }
+        };
+        auto load_a1 = [&](int s, float4* x) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int col = s * SLAB_K + u * 4;
+                x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col < kA) {
+                    const float* p = col < P.d[0] ? rp[0] + col : col < P.d[0] + P.d[1] ? rp[1] + (col - P.d[0]) : rp[2] + (col - P.d[0] - P.d[1]);
+                    x[u] = __ldg(reinterpret_cast<const float4*>(p));
+                }
+            }
+        };
+        auto stage_a2 = [&](uint32_t stage_base, int s) {
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const int c0 = s * SLAB_K + half * 16;
+                float v[16];
+                if (c0 < P.n1) {
+                    tmem_ld16(tmem + lane_base + (uint32_t)c0, v);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + __ldg(P.b1 + c0 + i), 0.f);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) put_split(stage_base, half * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+            }
+        };
+        float4 xa[8];
+        uint32_t J = 0;
+        if ((int)blockIdx.x < ntiles) {
+            set_rows(blockIdx.x);
+            load_a1(0, xa);
+        }
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int next_tile = tile + gridDim.x;
+            for (uint32_t j = 0; j < S; j++, J++) {
+                const uint32_t sa = sAst + (J % A_STAGES) * A_STAGE_BYTES;
+                if (J >= (uint32_t)A_STAGES) wait_done(J - A_STAGES);
+                if (j < n1s) {
+#pragma unroll
+                    for (int u = 0; u < 8; u++) put_split(sa, u, xa[u]);
+                    if (j + 1 < n1s) load_a1((int)j + 1, xa);
+                } else {
+                    if (j == n1s) {  // GEMM2 reads GEMM1's accumulator: every GEMM1 MMA must have completed
+                        wait_done(J - 1);
+                        tc_fence_after();
+                        if (next_tile < ntiles) {  // the next tile's first slab travels while this tile's GEMM2 is staged
+                            set_rows(next_tile);
+                            load_a1(0, xa);
+                        }
+                    }
+                    stage_a2(sa, (int)(j - n1s));
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(sArdy + 8 * (J % A_STAGES));
+            }
+        }
+    } else if (tid == MLP_PRODUCERS) {
+        uint32_t it = 0;
+        uint32_t my_tiles = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) my_tiles++;
+        const uint32_t total = my_tiles * S;
+        auto issue_b = [&](uint32_t J) {
+            const uint32_t j = J % S;
+            const bool g1 = j < n1s;
+            const int n_pad = g1 ? P.n1 : P.n2;
+            const uint32_t s = g1 ? j : j - n1s, bbytes = (uint32_t)n_pad * 128u;
+            const float* hi = (g1 ? P.w1_hi : P.w2_hi) + (size_t)s * n_pad * SLAB_K;
+            const float* lo = (g1 ? P.w1_lo : P.w2_lo) + (size_t)s * n_pad * SLAB_K;
+            const uint32_t bs = sBst + (J % B_STAGES) * B_STAGE_BYTES, bar = sFull + 8 * (J % B_STAGES);
+            if (J >= (uint32_t)B_STAGES) wait_done(J - B_STAGES);
+            mbar_expect_tx(bar, 2 * bbytes);
+            bulk_g2s(bs, hi, bbytes, bar);
+            bulk_g2s(bs + B_SLAB_BYTES, lo, bbytes, bar);
+        };
+        for (uint32_t J = 0; J < (uint32_t)(B_STAGES - 1) && J < total; J++) issue_b(J);
+        for (uint32_t J = 0; J < total; J++) {
+            const uint32_t j = J % S;
+            if (j == 0 && J) it++;
+            const bool g1 = j < n1s;
+            const uint32_t idesc = idesc_tf32(TILE_M, g1 ? P.n1 : P.n2);
+            const uint32_t acc = tmem + (g1 ? 0u : (uint32_t)ACC2_COL);
+            const uint32_t first = g1 ? 0u : n1s;
+            mbar_wait(sArdy + 8 * (J % A_STAGES), (J / A_STAGES) & 1u);
+            mbar_wait(sFull + 8 * (J % B_STAGES), (J / B_STAGES) & 1u);
+            if (j == n1s && it > 0) mbar_wait(sAccFree, (it - 1) & 1u);  // the epilogue of the previous tile has read acc2
+            tc_fence_after();
+            const uint32_t aHi = sAst + (J % A_STAGES) * A_STAGE_BYTES, aLo = aHi + A_SLAB_BYTES;
+            const uint32_t bHi = sBst + (J % B_STAGES) * B_STAGE_BYTES, bLo = bHi + B_SLAB_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                const uint32_t o = kk * 32;
+                umma_tf32(acc, smem_desc_sw128(aHi + o), smem_desc_sw128(bHi + o), idesc, (j != first || kk != 0) ? 1u : 0u);
+                umma_tf32(acc, smem_desc_sw128(aLo + o), smem_desc_sw128(bHi + o), idesc, 1u);
+                umma_tf32(acc, smem_desc_sw128(aHi + o), smem_desc_sw128(bLo + o), idesc, 1u);
+            }
+            umma_commit(sDone + 8 * (J % DONE_BARS));
+            if (j == S - 1) umma_commit(sAccFull);
+            if (J + B_STAGES - 1 < total) issue_b(J + B_STAGES - 1);
+        }
+    } else if (epilogue) {
+        const int H = P.h2;
+        const int erow = (warp & 3) * 32 + (tid & 31);  // row of the tile = TMEM lane
+        auto lds4 = [](uint32_t a) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+            return v;
+        };
+        auto load_x = [&](int c0, float* x) {
+            tmem_ld16(tmem + lane_base + (uint32_t)(ACC2_COL + c0), x);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float4 b = lds4(sPar + (c0 + 4 * q) * 4);
+                x[4 * q] = fmaxf(x[4 * q] + b.x, 0.f), x[4 * q + 1] = fmaxf(x[4 * q + 1] + b.y, 0.f);
+                x[4 * q + 2] = fmaxf(x[4 * q + 2] + b.z, 0.f), x[4 * q + 3] = fmaxf(x[4 * q + 3] + b.w, 0.f);
+            }
+        };
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+            mbar_wait(sAccFull, it & 1u);
+            tc_fence_after();
+            float sum = 0.f;
+            for (int c0 = 0; c0 < H; c0 += 16) {
+                float x[16];
+                load_x(c0, x);
+#pragma unroll
+                for (int i = 0; i < 16; i++) sum += x[i];
+            }
+            const float mean = sum / (float)H;
+            float sq = 0.f;
+            for (int c0 = 0; c0 < H; c0 += 16) {
+                float x[16];
+                load_x(c0, x);
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    if (c0 + i < H) sq += (x[i] - mean) * (x[i] - mean);
+            }
+            const float rstd = rsqrtf(sq / (float)H + 1e-5f);
+            const int row = tile * TILE_M + erow;
+            float* orow = P.out + (size_t)min(row, P.rows - 1) * H;
+            for (int c0 = 0; c0 < H; c0 += 16) {
+                float x[16];
+                load_x(c0, x);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (c0 + 4 * q < H && row < P.rows) {  // H is a multiple of 4
+                        const float4 sc = lds4(sPar + (MAX_N + c0 + 4 * q) * 4), of = lds4(sPar + (2 * MAX_N + c0 + 4 * q) * 4);
+                        float4 y;
+                        y.x = (x[4 * q] - mean) * rstd * sc.x + of.x, y.y = (x[4 * q + 1] - mean) * rstd * sc.y + of.y;
+                        y.z = (x[4 * q + 2] - mean) * rstd * sc.z + of.z, y.w = (x[4 * q + 3] - mean) * rstd * sc.w + of.w;
+                        *reinterpret_cast<float4*>(orow + c0 + 4 * q) = y;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(sAccFree);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
 // ---- small kernels -------------------------------------------------------------------------------
 // Linear(2 -> D): out[i][c] = x[i][0]*w[0][c] + x[i][1]*w[1][c] + b[c]     (model.py:13-16)
 __global__ void embed_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
