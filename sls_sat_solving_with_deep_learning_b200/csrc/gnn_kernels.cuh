@@ -93,6 +93,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "  @!p bra WAIT_%=;\n }"
         ::"r"(bar), "r"(parity) : "memory");
 }
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t p;
+    asm volatile("{ .reg .pred q; elect.sync _|q, 0xffffffff; selp.u32 %0, 1, 0, q; }" : "=r"(p));
+    return p != 0;
+}
+// the same for a long wait (the epilogue warps wait a whole tile): sleep between polls instead of taking issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{ .reg .pred p;\n"
+        "WAITR_%=:\n"
+        "  mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "  @p bra DONER_%=;\n"
+        "  nanosleep.u32 256;\n"
+        "  bra WAITR_%=;\n"
+        "DONER_%=:\n }"
+        ::"r"(bar), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -402,7 +422,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
 //   sAccFree (128 epilogue threads, after their last TMEM read) -> the issuer may overwrite acc2 (first GEMM2 MMA of
 //   the next tile).  acc1 needs no barrier: the producers read it (GEMM2 staging of tile t) before they stage, in
 //   program order, the GEMM1 slabs whose MMAs overwrite it.
-static constexpr int MLPP_THREADS = MLP_PRODUCERS + 32 + 128;
+// Eight producer warps: two threads per row, each staging half of a slab (16 of its 32 columns).  A producer warp is
+// latency-bound (gather -> split -> swizzled stores, ~425 instructions per slab with four warps: measured 2.3x the MMA
+// time of a slab, tensor pipe 43 % busy); with eight, staging a slab takes about as long as its twelve MMAs.
+static constexpr int MLPP_PRODUCERS = 256;
+static constexpr int MLPP_THREADS = MLPP_PRODUCERS + 32 + 128;
 
 __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(const MlpArgs P)
 {
@@ -421,14 +445,17 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    const bool producer = tid < MLP_PRODUCERS;
-    const bool epilogue = tid >= MLP_PRODUCERS + 32;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // the same value, provably warp-uniform
+    const bool producer = tid < MLPP_PRODUCERS;
+    const bool epilogue = tid >= MLPP_PRODUCERS + 32;
+    const int prow = tid & (TILE_M - 1);  // producers: row of the tile (two threads per row)
+    const int part = tid >> 7;            // producers: which half of a slab's 32 columns
     const int ntiles = (P.rows + TILE_M - 1) / TILE_M;
 
     if (tid == 0) {
         for (int i = 0; i < B_STAGES; i++) mbar_init(sFull + 8 * i, 1);
         for (int i = 0; i < DONE_BARS; i++) mbar_init(sDone + 8 * i, 1);
-        for (int i = 0; i < A_STAGES; i++) mbar_init(sArdy + 8 * i, MLP_PRODUCERS);
+        for (int i = 0; i < A_STAGES; i++) mbar_init(sArdy + 8 * i, MLPP_PRODUCERS);
         mbar_init(sAccFull, 1);
         mbar_init(sAccFree, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -457,13 +484,13 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
             float4 hi, lo;
             hi.x = round_tf32(x.x), hi.y = round_tf32(x.y), hi.z = round_tf32(x.z), hi.w = round_tf32(x.w);
             lo.x = round_tf32(x.x - hi.x), lo.y = round_tf32(x.y - hi.y), lo.z = round_tf32(x.z - hi.z), lo.w = round_tf32(x.w - hi.w);
-            const uint32_t off = sw128_off(tid, u);
+            const uint32_t off = sw128_off(prow, u);
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + A_SLAB_BYTES + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
         };
         const float* rp[3] = {nullptr, nullptr, nullptr};
         auto set_rows = [&](int tile) {
-            const int my_row = min(tile * TILE_M + tid, P.rows - 1);  // rows past the end re-read the last row; never stored
+            const int my_row = min(tile * TILE_M + prow, P.rows - 1);  // rows past the end re-read the last row; never stored
 #pragma unroll
             for (int j = 0; j < 3; j++)
                 if (P.d[j] > 0) {
@@ -473,8 +500,8 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
         };
         auto load_a1 = [&](int s, float4* x) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int col = s * SLAB_K + u * 4;
+            for (int u = 0; u < 4; u++) {
+                const int col = s * SLAB_K + (part * 4 + u) * 4;
                 x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (col < kA) {
                     const float* p = col < P.d[0] ? rp[0] + col : col < P.d[0] + P.d[1] ? rp[1] + (col - P.d[0]) : rp[2] + (col - P.d[0] - P.d[1]);
@@ -483,8 +510,8 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
             }
         };
         auto stage_a2 = [&](uint32_t stage_base, int s) {
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
+            {
+                const int half = part;
                 const int c0 = s * SLAB_K + half * 16;
                 float v[16];
                 if (c0 < P.n1) {
@@ -499,7 +526,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
                 for (int q = 0; q < 4; q++) put_split(stage_base, half * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
             }
         };
-        float4 xa[8];
+        float4 xa[4];
         uint32_t J = 0;
         if ((int)blockIdx.x < ntiles) {
             set_rows(blockIdx.x);
@@ -512,7 +539,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
                 if (J >= (uint32_t)A_STAGES) wait_done(J - A_STAGES);
                 if (j < n1s) {
 #pragma unroll
-                    for (int u = 0; u < 8; u++) put_split(sa, u, xa[u]);
+                    for (int u = 0; u < 4; u++) put_split(sa, part * 4 + u, xa[u]);
                     if (j + 1 < n1s) load_a1((int)j + 1, xa);
                 } else {
                     if (j == n1s) {  // GEMM2 reads GEMM1's accumulator: every GEMM1 MMA must have completed
@@ -530,13 +557,20 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
                 mbar_arrive(sArdy + 8 * (J % A_STAGES));
             }
         }
-    } else if (tid == MLP_PRODUCERS) {
-        uint32_t it = 0;
+    } else if (warp_u == MLPP_PRODUCERS / 32) {
+        // The whole warp runs this loop with warp-uniform state and one ELECTED lane issues: in divergent code
+        // (`if (tid == ...)`) the compiler wraps every tcgen05.mma / commit / bulk copy in an elect-and-retry loop
+        // (ELECT, PLOP3, BRA.U.ANY: ~10 slow instructions per MMA), and that single thread, not the tensor pipe,
+        // set the pace of the kernel (measured: 83 % of its time in its own ~330 instructions per slab, tensor pipe
+        // 43 % busy).  No runtime modulo either: slab-in-tile counters run along.
+        const bool leader = elect_one();
         uint32_t my_tiles = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) my_tiles++;
         const uint32_t total = my_tiles * S;
-        auto issue_b = [&](uint32_t J) {
-            const uint32_t j = J % S;
+        constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version 1 | SWIZZLE_128B
+        auto desc = [&](uint32_t addr) -> uint64_t { return (uint64_t)DESC_HI << 32 | (((addr >> 4) & 0x3fffu) | (1u << 16)); };
+        const uint32_t idesc1 = idesc_tf32(TILE_M, P.n1), idesc2 = idesc_tf32(TILE_M, P.n2);
+        auto issue_b = [&](uint32_t J, uint32_t j) {  // j = J % S
             const bool g1 = j < n1s;
             const int n_pad = g1 ? P.n1 : P.n2;
             const uint32_t s = g1 ? j : j - n1s, bbytes = (uint32_t)n_pad * 128u;
@@ -544,34 +578,45 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
             const float* lo = (g1 ? P.w1_lo : P.w2_lo) + (size_t)s * n_pad * SLAB_K;
             const uint32_t bs = sBst + (J % B_STAGES) * B_STAGE_BYTES, bar = sFull + 8 * (J % B_STAGES);
             if (J >= (uint32_t)B_STAGES) wait_done(J - B_STAGES);
-            mbar_expect_tx(bar, 2 * bbytes);
-            bulk_g2s(bs, hi, bbytes, bar);
-            bulk_g2s(bs + B_SLAB_BYTES, lo, bbytes, bar);
+            if (leader) {
+                mbar_expect_tx(bar, 2 * bbytes);
+                bulk_g2s(bs, hi, bbytes, bar);
+                bulk_g2s(bs + B_SLAB_BYTES, lo, bbytes, bar);
+            }
         };
-        for (uint32_t J = 0; J < (uint32_t)(B_STAGES - 1) && J < total; J++) issue_b(J);
+        uint32_t jn = 0;  // slab-in-tile index of the next weight slab to request
+        for (uint32_t J = 0; J < (uint32_t)(B_STAGES - 1) && J < total; J++) {
+            issue_b(J, jn);
+            jn = jn + 1 == S ? 0 : jn + 1;
+        }
+        uint32_t j = 0, it = 0;
         for (uint32_t J = 0; J < total; J++) {
-            const uint32_t j = J % S;
-            if (j == 0 && J) it++;
             const bool g1 = j < n1s;
-            const uint32_t idesc = idesc_tf32(TILE_M, g1 ? P.n1 : P.n2);
+            const uint32_t idesc = g1 ? idesc1 : idesc2;
             const uint32_t acc = tmem + (g1 ? 0u : (uint32_t)ACC2_COL);
             const uint32_t first = g1 ? 0u : n1s;
             mbar_wait(sArdy + 8 * (J % A_STAGES), (J / A_STAGES) & 1u);
             mbar_wait(sFull + 8 * (J % B_STAGES), (J / B_STAGES) & 1u);
             if (j == n1s && it > 0) mbar_wait(sAccFree, (it - 1) & 1u);  // the epilogue of the previous tile has read acc2
             tc_fence_after();
-            const uint32_t aHi = sAst + (J % A_STAGES) * A_STAGE_BYTES, aLo = aHi + A_SLAB_BYTES;
-            const uint32_t bHi = sBst + (J % B_STAGES) * B_STAGE_BYTES, bLo = bHi + B_SLAB_BYTES;
+            const uint32_t aHi = sAst + (J % A_STAGES) * A_STAGE_BYTES, bHi = sBst + (J % B_STAGES) * B_STAGE_BYTES;
+            const uint64_t dAh = desc(aHi), dAl = desc(aHi + A_SLAB_BYTES), dBh = desc(bHi), dBl = desc(bHi + B_SLAB_BYTES);
+            if (leader) {
 #pragma unroll
-            for (int kk = 0; kk < 4; kk++) {
-                const uint32_t o = kk * 32;
-                umma_tf32(acc, smem_desc_sw128(aHi + o), smem_desc_sw128(bHi + o), idesc, (j != first || kk != 0) ? 1u : 0u);
-                umma_tf32(acc, smem_desc_sw128(aLo + o), smem_desc_sw128(bHi + o), idesc, 1u);
-                umma_tf32(acc, smem_desc_sw128(aHi + o), smem_desc_sw128(bLo + o), idesc, 1u);
+                for (int kk = 0; kk < 4; kk++) {  // 4 k-steps of 8 tf32 (32 bytes = 2 descriptor units) per 128-byte slab row
+                    umma_tf32(acc, dAh + 2 * kk, dBh + 2 * kk, idesc, (j != first || kk != 0) ? 1u : 0u);
+                    umma_tf32(acc, dAl + 2 * kk, dBh + 2 * kk, idesc, 1u);
+                    umma_tf32(acc, dAh + 2 * kk, dBl + 2 * kk, idesc, 1u);
+                }
+                umma_commit(sDone + 8 * (J % DONE_BARS));
+                if (j == S - 1) umma_commit(sAccFull);
             }
-            umma_commit(sDone + 8 * (J % DONE_BARS));
-            if (j == S - 1) umma_commit(sAccFull);
-            if (J + B_STAGES - 1 < total) issue_b(J + B_STAGES - 1);
+            __syncwarp();
+            if (J + B_STAGES - 1 < total) {
+                issue_b(J + B_STAGES - 1, jn);
+                jn = jn + 1 == S ? 0 : jn + 1;
+            }
+            if (++j == S) j = 0, it++;
         }
     } else if (epilogue) {
         const int H = P.h2;
@@ -592,7 +637,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
         };
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-            mbar_wait(sAccFull, it & 1u);
+            mbar_wait_relaxed(sAccFull, it & 1u);
             tc_fence_after();
             float sum = 0.f;
             for (int c0 = 0; c0 < H; c0 += 16) {
