@@ -48,6 +48,16 @@ __device__ __forceinline__ uint32_t select_in_word(uint32_t w, uint32_t r)
 template <bool SMEM>
 struct Chain {
     const DevInst& I;
+    // Copies of the instance fields the step loop reads.  In the batched kernels the DevInst sits in shared memory
+    // next to the chain state, and every shared-memory atomic of the walk may alias it as far as the compiler can
+    // tell: through the reference each pointer was re-read from shared memory after every atomic (measured: ~20 % of
+    // the step's instructions were those reloads and the generic->shared address conversions around them).
+    const uint32_t* __restrict__ row_ptr;
+    const uint32_t* __restrict__ lits;
+    const uint32_t* __restrict__ occ_ptr;
+    const uint32_t* __restrict__ occ;
+    const uint32_t* __restrict__ canon;
+    const uint32_t uniform_k, mwords;
     uint32_t* abits;
     uint32_t* vbits;
     uint32_t* l1;
@@ -56,8 +66,9 @@ struct Chain {
     uint32_t numfalse;
 
     __device__ __forceinline__ Chain(const DevInst& inst, uint32_t* slab, int lane_)
-        : I(inst), abits(slab), vbits(slab + inst.off_v), l1(slab + inst.off_l1), l2(inst.l2_pad ? slab + inst.off_l2 : nullptr),
-          lane(lane_), numfalse(0)
+        : I(inst), row_ptr(inst.row_ptr), lits(inst.lits), occ_ptr(inst.occ_ptr), occ(inst.occ), canon(inst.canon),
+          uniform_k(inst.uniform_k), mwords(inst.mwords), abits(slab), vbits(slab + inst.off_v), l1(slab + inst.off_l1),
+          l2(inst.l2_pad ? slab + inst.off_l2 : nullptr), lane(lane_), numfalse(0)
     {
     }
 
@@ -72,12 +83,12 @@ struct Chain {
 
     __device__ __forceinline__ void clause_range(uint32_t c, uint32_t& s, uint32_t& e) const
     {
-        if (I.uniform_k) {
-            s = c * I.uniform_k;
-            e = s + I.uniform_k;
+        if (uniform_k) {
+            s = c * uniform_k;
+            e = s + uniform_k;
         } else {
-            s = __ldg(I.row_ptr + c);
-            e = __ldg(I.row_ptr + c + 1);
+            s = __ldg(row_ptr + c);
+            e = __ldg(row_ptr + c + 1);
         }
     }
 
@@ -87,7 +98,7 @@ struct Chain {
         uint32_t s, e;
         clause_range(c, s, e);
         for (uint32_t j = s; j < e; j++) {
-            const uint32_t l = __ldg(I.lits + j);
+            const uint32_t l = __ldg(lits + j);
             const uint32_t v = l >> 1;
             uint32_t a = abit(v);
             if (v == flipped_var) a ^= 1u;
@@ -99,14 +110,13 @@ struct Chain {
     // find_violated_clauses (lib.rs:176-181): rebuild vbits / l1 / numfalse from scratch
     __device__ void full_scan()
     {
-        const uint32_t* canon = I.canon;
         numfalse = 0;
         for (uint32_t g = lane; g < I.l1_pad; g += 32) l1[g] = 0;
         __syncwarp();
         if (canon == nullptr) {
             for (uint32_t g = 0; g < I.ngroups; g++) {
                 uint32_t acc = 0, mine = 0;
-                const uint32_t wend = min(32u, I.mwords - g * 32u);
+                const uint32_t wend = min(32u, mwords - g * 32u);
                 for (uint32_t wi = 0; wi < wend; wi++) {
                     const uint32_t c = (g * 32u + wi) * 32u + lane;
                     const bool viol = c < I.m && violated(c, 0xffffffffu);
@@ -119,7 +129,7 @@ struct Chain {
                 numfalse += acc;
             }
         } else {
-            for (uint32_t w = lane; w < I.mwords; w += 32) vbits[w] = 0;
+            for (uint32_t w = lane; w < mwords; w += 32) vbits[w] = 0;
             __syncwarp();
             for (uint32_t base = 0; base < I.m; base += 32) {
                 const uint32_t c = base + lane;
@@ -191,7 +201,7 @@ struct Chain {
         }
         const uint32_t g = gb + pick64(l1 + gb, r, false);
         const uint32_t wi = g * 32u + lane;
-        const uint32_t word = wi < I.mwords ? vbits[wi] : 0u;
+        const uint32_t word = wi < mwords ? vbits[wi] : 0u;
         const uint32_t pc = __popc(word);
         const uint32_t incl = warp_incl_scan(pc, lane);
         const uint32_t src = __ffs(__ballot_sync(FULL, r < incl)) - 1;
@@ -205,14 +215,14 @@ struct Chain {
     // lib.rs:278-287 for one flipped variable (assignment already holds the new value)
     __device__ __forceinline__ void update_var(uint32_t v)
     {
-        const uint32_t os = __ldg(I.occ_ptr + v), oe = __ldg(I.occ_ptr + v + 1);
+        const uint32_t os = __ldg(occ_ptr + v), oe = __ldg(occ_ptr + v + 1);
         for (uint32_t base = os; base < oe; base += 32) {
             const uint32_t o = base + lane;
             int delta = 0;
             if (o < oe) {
-                const uint32_t cc = __ldg(I.occ + o);
+                const uint32_t cc = __ldg(occ + o);
                 const bool viol = violated(cc, 0xffffffffu);
-                const uint32_t id = I.canon ? __ldg(I.canon + cc) : cc;
+                const uint32_t id = canon ? __ldg(canon + cc) : cc;
                 const uint32_t bit = 1u << (id & 31);
                 if (viol) {
                     const uint32_t old = atomicOr(&vbits[id >> 5], bit);  // HashSet::insert
@@ -237,20 +247,20 @@ struct Chain {
     // greedy score of flipping v (lib.rs:236-256)
     __device__ __forceinline__ uint64_t greedy_score(uint32_t v, bool mapping) const
     {
-        const uint32_t os = __ldg(I.occ_ptr + v), oe = __ldg(I.occ_ptr + v + 1);
+        const uint32_t os = __ldg(occ_ptr + v), oe = __ldg(occ_ptr + v + 1);
         uint32_t after = 0, before = 0;
         for (uint32_t base = os; base < oe; base += 32) {
             const uint32_t o = base + lane;
             bool cnt_after = false, cnt_before = false;
             if (o < oe) {
-                const uint32_t cc = __ldg(I.occ + o);
+                const uint32_t cc = __ldg(occ + o);
                 const bool viol = violated(cc, v);
                 if (mapping) {
                     cnt_after = viol;  // every var_to_clauses entry counts (lib.rs:243-247)
                 } else {
                     // |find_violated_clauses(after flip)|: distinct contents only (lib.rs:249)
-                    const bool rep = (I.canon == nullptr || __ldg(I.canon + cc) == cc) &&
-                                     !(o > os && __ldg(I.occ + o - 1) == cc);
+                    const bool rep = (canon == nullptr || __ldg(canon + cc) == cc) &&
+                                     !(o > os && __ldg(occ + o - 1) == cc);
                     cnt_after = rep && viol;
                     cnt_before = rep && ((vbits[cc >> 5] >> (cc & 31)) & 1u);
                 }
@@ -354,6 +364,12 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
     }
 
     WarpStream rng(A.seed, chain, lane);
+    // (loop invariants out of the WalkArgs, which may live in shared memory: see Chain)
+    const double* __restrict__ ftab = A.ftab;
+    const double* __restrict__ cscale = A.cscale;
+    const double pfb = A.pfb;
+    const uint64_t nsteps = A.nsteps;
+    const bool mapping = A.mapping != 0;
 
     uint32_t best = I.m;  // lib.rs:203
     bool has_best = false;
@@ -385,7 +401,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
     int err = 0;
     uint32_t mark_mask = 0;  // lane i keeps the MT marks of literals [32 i, 32 i + 32) of the picked clause
 
-    while (ch.numfalse > 0 && steps < A.nsteps) {  // lib.rs:225
+    while (ch.numfalse > 0 && steps < nsteps) {  // lib.rs:225
         steps++;
         const uint32_t c = ch.select(rng.uniform_u32(ch.numfalse));  // lib.rs:229
         uint32_t s, e;
@@ -393,13 +409,13 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
         const uint32_t k = e - s;
         const double ugreedy = rng.next_f64();  // lib.rs:231: drawn on every step
 
-        if (ugreedy < A.pfb) {
+        if (ugreedy < pfb) {
             // ---- lib.rs:231-268 flip the literal with the fewest violations after the flip
             uint32_t best_v = 0;
             uint64_t min_viol = ~0ull;
             for (uint32_t j = 0; j < k; j++) {
-                const uint32_t v = __ldg(I.lits + s + j) >> 1;
-                const uint64_t viol = ch.greedy_score(v, A.mapping != 0);
+                const uint32_t v = __ldg(ch.lits + s + j) >> 1;
+                const uint64_t viol = ch.greedy_score(v, mapping);
                 if (viol < min_viol) {
                     min_viol = viol;
                     best_v = v;
@@ -425,7 +441,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
             for (uint32_t cb = 0; cb < k; cb += 32) {
                 const uint32_t j = cb + lane;
                 bool mark = false;
-                if (j < k) mark = u64_to_f64_53(rng.ck.u64_at(p0 + 2ull * j)) < __ldg(A.ftab + s + j);
+                if (j < k) mark = u64_to_f64_53(rng.ck.u64_at(p0 + 2ull * j)) < __ldg(ftab + s + j);
                 const uint32_t mask = __ballot_sync(FULL, mark);
                 if ((uint32_t)lane == (cb >> 5)) mark_mask = mask;
                 nmarks += __popc(mask);
@@ -435,7 +451,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
                 for (uint32_t cb = 0; cb < k; cb += 32) {
                     const uint32_t mask = __shfl_sync(FULL, mark_mask, cb >> 5);
                     if ((mask >> lane) & 1u) {
-                        const uint32_t v = __ldg(I.lits + s + cb + lane) >> 1;
+                        const uint32_t v = __ldg(ch.lits + s + cb + lane) >> 1;
                         atomicXor(&ch.abits[v >> 5], 1u << (v & 31));
                     }
                 }
@@ -446,7 +462,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
                     while (mask) {
                         const uint32_t j = __ffs(mask) - 1;
                         mask &= mask - 1;
-                        const uint32_t v = __ldg(I.lits + s + cb + j) >> 1;
+                        const uint32_t v = __ldg(ch.lits + s + cb + j) >> 1;
                         log_flip(v);
                         ch.update_var(v);
                     }
@@ -459,7 +475,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
                     const uint32_t mask = __shfl_sync(FULL, mark_mask, cb >> 5);
                     const uint32_t pc = __popc(mask);
                     if (pick < pc) {
-                        v = __ldg(I.lits + s + cb + select_in_word(mask, (uint32_t)pick)) >> 1;
+                        v = __ldg(ch.lits + s + cb + select_in_word(mask, (uint32_t)pick)) >> 1;
                         break;
                     }
                     pick -= pc;
@@ -476,7 +492,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
                 err = DERR_EMPTY_CLAUSE;
                 break;
             }
-            const uint32_t v = __ldg(I.lits + s + rng.uniform_u32(k)) >> 1;
+            const uint32_t v = __ldg(ch.lits + s + rng.uniform_u32(k)) >> 1;
             if (lane == 0) ch.abits[v >> 5] ^= 1u << (v & 31);
             __syncwarp();
             flips++;
@@ -489,7 +505,7 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
                 break;
             }
             // WeightedIndex::new's verdict and UniformFloat's scale come precomputed (build_flip_tables_kernel)
-            const double scale = __ldg(A.cscale + c);
+            const double scale = __ldg(cscale + c);
             if (!(scale > 0.0)) {
                 err = (int)(-scale);
                 break;
@@ -499,9 +515,9 @@ __device__ __forceinline__ void walk_generic_body(const WalkArgs& A, uint32_t bl
             uint32_t pick = 0;
             for (uint32_t cb = 0; cb + 1 < k; cb += 32) {
                 const uint32_t j = cb + lane;
-                pick += __popc(__ballot_sync(FULL, j + 1 < k && __ldg(A.ftab + s + j) <= x));
+                pick += __popc(__ballot_sync(FULL, j + 1 < k && __ldg(ftab + s + j) <= x));
             }
-            const uint32_t v = __ldg(I.lits + s + pick) >> 1;
+            const uint32_t v = __ldg(ch.lits + s + pick) >> 1;
             if (lane == 0) ch.abits[v >> 5] ^= 1u << (v & 31);
             __syncwarp();
             flips++;
@@ -562,7 +578,7 @@ __device__ __forceinline__ void load_item(WalkArgs& dst, const WalkArgs* src)
 }
 
 template <bool SMEM, int ALGO>
-__global__ void __launch_bounds__(128, 4) walk_generic_batch_kernel(const WalkArgs* __restrict__ items, const uint32_t* __restrict__ cta_begin,
+__global__ void __launch_bounds__(128, 8) walk_generic_batch_kernel(const WalkArgs* __restrict__ items, const uint32_t* __restrict__ cta_begin,
                                                                  uint32_t n_items)
 {
     extern __shared__ uint32_t smem_state[];
