@@ -183,7 +183,9 @@ int sls_gnn_forward_graph(sls_gnn_model *m, uint64_t n_node, uint64_t n_edge, co
                           const int32_t *senders, const int32_t *receivers, float *decoded, double *kernel_ms);
 /* batched form: builds the LCG graphs of n_inst parsed instances (LCG.get_graph,
  * python/src/sat_representations.py:607-666), runs one forward over the concatenation and returns
- * p[sum n_i] = P(x = True) per variable (and optionally decoded[sum N_i], N_i = 2 n_i + m_i). */
+ * p[sum n_i] = P(x = True) per variable (and optionally decoded[sum N_i], N_i = 2 n_i + m_i).  The instances
+ * become resident on the current device (as for sls_run_batch) and the graph arrays are derived there from their
+ * CSRs; a batch with an empty clause (which the reference drops, sat_instances.py:50) builds them on the host. */
 int sls_gnn_forward_lcg(sls_gnn_model *m, sls_instance *const *insts, uint32_t n_inst, float *prob, float *decoded,
                         double *kernel_ms);
 int sls_gnn_launch_count(const sls_gnn_model *m);
