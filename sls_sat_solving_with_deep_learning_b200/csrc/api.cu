@@ -11,6 +11,7 @@
 #include <new>
 #include <string>
 #include <thread>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/sls_b200.h"
@@ -179,12 +180,11 @@ int ensure_batch_on_device(sls_instance* const* insts, uint32_t n_inst)
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     std::vector<uint32_t> todo;
+    std::unordered_set<const sls_instance*> seen;  // the same handle may appear more than once in a batch
     for (uint32_t i = 0; i < n_inst; i++) {
         if (!insts[i]) return set_error(SLS_ERR_ARG, "NULL instance handle in batch");
         if (insts[i]->d_blob && insts[i]->device == dev) continue;
-        bool seen = false;  // the same handle may appear more than once in a batch
-        for (uint32_t j : todo) seen |= insts[j] == insts[i];
-        if (!seen) todo.push_back(i);
+        if (seen.insert(insts[i]).second) todo.push_back(i);
     }
     if (todo.empty()) return SLS_OK;
     const size_t chunk = 64;  // images alive at a time: bounds the host staging memory

@@ -539,10 +539,63 @@ int forward_lcg_device(sls_gnn_model* m, sls_instance* const* insts, uint32_t n_
 
 }  // namespace
 
+namespace {
+int forward_lcg_one(sls_gnn_model* m, sls_instance* const* insts, uint32_t n_inst, float* prob, float* decoded, double* kernel_ms);
+}
+
+// A batch is cut into chunks whose activation workspace stays below a budget (8 GB by default = ~380 instances of the
+// config-4 shape, far more than it takes to fill the machine; SLS_B200_GNN_WS_MB overrides it): 10,000 instances in one call
+// would otherwise ask for 208 GB.  Rows are independent of their tile neighbours, so chunking does not change a single bit.
 extern "C" int sls_gnn_forward_lcg(sls_gnn_model* m, sls_instance* const* insts, uint32_t n_inst, float* prob, float* decoded,
                                    double* kernel_ms)
 {
     if (!m || (n_inst && !insts)) return sls_set_error_internal(SLS_ERR_ARG, "NULL argument");
+    size_t budget = (size_t)8 << 30;
+    if (const char* e = std::getenv("SLS_B200_GNN_WS_MB")) budget = std::max<size_t>(1, (size_t)std::atoll(e)) << 20;
+    const size_t width = (size_t)std::max(m->embed, m->h2) * sizeof(float);
+    if (kernel_ms) *kernel_ms = 0.0;
+    int launches = 0;
+    uint32_t begin = 0;
+    int64_t v_off = 0, n_off = 0;
+    while (begin < n_inst || (n_inst == 0 && begin == 0)) {
+        uint32_t end = begin;
+        size_t need = 0;
+        int64_t v_cnt = 0, n_cnt = 0;
+        while (end < n_inst) {
+            if (!insts[end]) return sls_set_error_internal(SLS_ERR_ARG, "NULL instance handle in batch");
+            const slsb::HostInstance& h = insts[end]->host;
+            const size_t nodes = 2 * (size_t)h.n + h.m, edges = h.lits.size() + h.n;
+            const size_t bytes = (2 * edges + 4 * nodes) * width;  // two edge buffers, two node buffers, two aggregates
+            if (end > begin && need + bytes > budget) break;
+            need += bytes;
+            v_cnt += h.n;
+            n_cnt += (int64_t)nodes;  // upper bound (empty clauses have no node); only used when no clause is empty
+            end++;
+        }
+        double ms = 0.0;
+        // decoded offsets need the exact node count of a chunk: with empty clauses in play a chunked call cannot place them
+        if (decoded && (begin > 0 || end < n_inst))
+            for (uint32_t i = begin; i < end; i++)
+                for (uint32_t c = 0; c < insts[i]->host.m; c++)
+                    if (insts[i]->host.row_ptr[c] == insts[i]->host.row_ptr[c + 1])
+                        return sls_set_error_internal(SLS_ERR_ARG, "decoded output of a chunked batch needs instances without empty clauses");
+        int rc = forward_lcg_one(m, insts + begin, end - begin, prob ? prob + v_off : nullptr, decoded ? decoded + n_off : nullptr, &ms);
+        if (rc) return rc;
+        if (kernel_ms) *kernel_ms += ms;
+        launches += m->launches;
+        v_off += v_cnt;
+        n_off += n_cnt;
+        begin = end;
+        if (n_inst == 0) break;
+    }
+    m->launches = launches;
+    return SLS_OK;
+}
+
+namespace {
+
+int forward_lcg_one(sls_gnn_model* m, sls_instance* const* insts, uint32_t n_inst, float* prob, float* decoded, double* kernel_ms)
+{
     // Graph construction is per instance and independent: plan (count) in parallel, prefix the
     // offsets, fill every instance's slice of the batched arrays in parallel.
     std::vector<LcgPlan> plan(n_inst);
@@ -616,5 +669,7 @@ extern "C" int sls_gnn_forward_lcg(sls_gnn_model* m, sls_instance* const* insts,
     }
     return SLS_OK;
 }
+
+}  // namespace
 
 extern "C" int sls_gnn_launch_count(const sls_gnn_model* m) { return m ? m->launches : 0; }

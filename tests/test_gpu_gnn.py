@@ -85,6 +85,20 @@ def test_device_built_lcg_graph_equals_host_built(monkeypatch):
     assert np.array_equal(p_a, p_b)
 
 
+def test_large_batches_are_chunked_without_changing_results(monkeypatch):
+    # sls_gnn_forward_lcg cuts a batch into chunks by activation-workspace budget (10,000 instances in one call would
+    # need 208 GB); rows are independent of their tile neighbours, so the chunked result is bit-identical
+    names = ["r3sat_test_random_KCNF3_100_210_6416893", "g4sat_easy_ca_00092", "ref_tests_medium",
+             "r3sat_test_random_KCNF3_200_869_9397183", "r3sat_test_random_KCNF3_300_660_144280"]
+    insts = [eng.Instance.from_dimacs(golden_cnf(nm)) for nm in names] * 2
+    net = gnn.InteractionNetworkLCG(go.init_params(seed=13, bias_scale=0.1))
+    p_one, d_one = net.probabilities(insts, return_decoded=True)
+    monkeypatch.setenv("SLS_B200_GNN_WS_MB", "4")  # a few instances per chunk
+    p_chunks, d_chunks = net.probabilities(insts, return_decoded=True)
+    assert np.array_equal(d_one, d_chunks)
+    assert all(np.array_equal(a, b) for a, b in zip(p_one, p_chunks))
+
+
 def test_graph_edge_cases():
     params = go.init_params(seed=3, mlp_layers=(32, 32), num_steps=2, bias_scale=0.1)
     net = gnn.InteractionNetworkLCG(params, num_message_passing_steps=2)
