@@ -82,6 +82,16 @@ int sls_eval_assignments(sls_instance *inst, const uint8_t *assignments, uint64_
  * sls_eval_assignments -- measurement only, no reference equivalent */
 double sls_eval_last_kernel_ms(void);
 
+/* ---- clause neighbourhood of the LLL loss: replaces LCG.get_constraint_graph
+ *      (python/src/sat_representations.py:668-715, scipy C^T C of the variable-clause incidence).  Host-side, no GPU
+ *      needed.  var_of / clause_of: variable and clause index of every literal occurrence (the reference passes
+ *      floor(senders/2) and receivers - 2n of the LCG edge list without its last n pair edges).  Writes, for every
+ *      clause in increasing index, its neighbours in increasing index as senders[e] = clause + 2n, receivers[e] =
+ *      neighbour + 2n (the LCG node numbering the reference returns); *n_edge = number of edges.  Call with
+ *      capacity = 0 (buffers may be NULL) to size the buffers; SLS_ERR_ARG if capacity is too small. ----- */
+int sls_constraint_graph(uint32_t n_variables, uint32_t n_clauses, const int32_t *var_of, const int32_t *clause_of,
+                         uint64_t n_occurrences, int64_t *senders, int64_t *receivers, uint64_t capacity, uint64_t *n_edge);
+
 /* ---- solver: replaces run_sls_python / run_sls (lib.rs:103-149, :165-335) */
 typedef struct {
     int32_t algo;                /* SLS_ALGO_*            (algo_type_as_str) */

@@ -429,6 +429,28 @@ extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignmen
 
 extern "C" double sls_eval_last_kernel_ms(void) { return g_last_eval_ms; }
 
+// ------------------------------------------------------- constraint graph (host)
+extern "C" int sls_constraint_graph(uint32_t n_variables, uint32_t n_clauses, const int32_t* var_of, const int32_t* clause_of,
+                                    uint64_t n_occurrences, int64_t* senders, int64_t* receivers, uint64_t capacity, uint64_t* n_edge)
+{
+    if (!n_edge || (n_occurrences && (!var_of || !clause_of))) return set_error(SLS_ERR_ARG, "NULL argument");
+    for (uint64_t i = 0; i < n_occurrences; i++)
+        if (var_of[i] < 0 || (uint32_t)var_of[i] >= n_variables || clause_of[i] < 0 || (uint32_t)clause_of[i] >= n_clauses)
+            return set_error(SLS_ERR_ARG, "occurrence out of range");
+    const bool fill = senders && receivers && capacity;
+    if (!fill) {
+        *n_edge = slsb::constraint_graph(n_variables, n_clauses, var_of, clause_of, n_occurrences, nullptr, nullptr);
+        return SLS_OK;
+    }
+    const uint64_t need = slsb::constraint_graph(n_variables, n_clauses, var_of, clause_of, n_occurrences, nullptr, nullptr);
+    *n_edge = need;
+    if (need > capacity) return set_error(SLS_ERR_ARG, "constraint graph: capacity too small");
+    slsb::constraint_graph(n_variables, n_clauses, var_of, clause_of, n_occurrences, senders, receivers);
+    const int64_t off = 2 * (int64_t)n_variables;
+    for (uint64_t e = 0; e < need; e++) senders[e] += off, receivers[e] += off;
+    return SLS_OK;
+}
+
 // ------------------------------------------------------------------ solver
 struct sls_solver {
     sls_instance* inst = nullptr;

@@ -6,6 +6,8 @@
 #include "instance.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstring>
 
 namespace slsb {
@@ -203,6 +205,71 @@ std::string finalize_instance(HostInstance& h)
         }
     }
     return std::string();
+}
+
+uint64_t constraint_graph(uint32_t n_vars, uint32_t n_clauses, const int32_t* var_of, const int32_t* clause_of, uint64_t n_occ,
+                          int64_t* major, int64_t* minor)
+{
+    // clause -> variables and variable -> clauses by counting sort (stable in occurrence order)
+    std::vector<uint64_t> cptr(n_clauses + 1, 0), vptr(n_vars + 1, 0);
+    for (uint64_t i = 0; i < n_occ; i++) {
+        cptr[clause_of[i] + 1]++;
+        vptr[var_of[i] + 1]++;
+    }
+    for (uint32_t c = 0; c < n_clauses; c++) cptr[c + 1] += cptr[c];
+    for (uint32_t v = 0; v < n_vars; v++) vptr[v + 1] += vptr[v];
+    std::vector<uint32_t> cvar(n_occ), vcl(n_occ);
+    {
+        std::vector<uint64_t> cf(cptr.begin(), cptr.end() - 1), vf(vptr.begin(), vptr.end() - 1);
+        for (uint64_t i = 0; i < n_occ; i++) {
+            cvar[cf[clause_of[i]]++] = (uint32_t)var_of[i];
+            vcl[vf[var_of[i]]++] = (uint32_t)clause_of[i];
+        }
+    }
+    // neighbours of clause c = union over its variables of their clauses, without c; rows are independent
+    const unsigned T = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+    std::vector<uint64_t> rowcnt(n_clauses + 1, 0);
+    auto sweep = [&](bool fill) {
+        std::atomic<uint32_t> next{0};
+        auto work = [&] {
+            std::vector<uint32_t> stamp(n_clauses, 0), nb;
+            for (;;) {
+                const uint32_t c0 = next.fetch_add(256);
+                if (c0 >= n_clauses) break;
+                for (uint32_t c = c0; c < std::min(n_clauses, c0 + 256); c++) {
+                    nb.clear();
+                    for (uint64_t a = cptr[c]; a < cptr[c + 1]; a++) {
+                        const uint32_t v = cvar[a];
+                        for (uint64_t b = vptr[v]; b < vptr[v + 1]; b++) {
+                            const uint32_t d = vcl[b];
+                            if (d != c && stamp[d] != c + 1) {
+                                stamp[d] = c + 1;
+                                nb.push_back(d);
+                            }
+                        }
+                    }
+                    if (!fill) {
+                        rowcnt[c + 1] = nb.size();
+                    } else {
+                        std::sort(nb.begin(), nb.end());
+                        uint64_t o = rowcnt[c];
+                        for (uint32_t d : nb) {
+                            major[o] = c;
+                            minor[o++] = d;
+                        }
+                    }
+                }
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < T; t++) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+    };
+    sweep(false);
+    for (uint32_t c = 0; c < n_clauses; c++) rowcnt[c + 1] += rowcnt[c];
+    if (major && minor) sweep(true);
+    return rowcnt[n_clauses];
 }
 
 }  // namespace slsb

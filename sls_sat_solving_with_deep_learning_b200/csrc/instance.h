@@ -27,6 +27,13 @@ std::string parse_dimacs(const char* text, size_t len, HostInstance& out);
 // Fills occurrence lists, canonical clause ids and shape flags from row_ptr/lits.
 std::string finalize_instance(HostInstance& h);
 
+// Clause neighbourhood of the Lovasz-Local-Lemma loss (LCG.get_constraint_graph, python/src/sat_representations.py:668-715:
+// sparsity pattern of C^T C minus the diagonal): for every clause, in increasing clause index, the other clauses that share
+// a variable with it, in increasing index.  var_of / clause_of: one entry per literal occurrence.  Returns the edge count;
+// fills major / minor (clause indices, NOT yet offset by 2n) when they are non-null.
+uint64_t constraint_graph(uint32_t n_vars, uint32_t n_clauses, const int32_t* var_of, const int32_t* clause_of, uint64_t n_occ,
+                          int64_t* major, int64_t* minor);
+
 }  // namespace slsb
 
 // The opaque handle of include/sls_b200.h

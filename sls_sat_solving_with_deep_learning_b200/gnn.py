@@ -99,6 +99,30 @@ def get_model_probabilities(decoded_nodes, n_variables: int) -> np.ndarray:
     return (e / e.sum(axis=1, keepdims=True))[:n_variables, 1]
 
 
+def get_constraint_graph(n_variables: int, n_clauses: int, senders, receivers) -> dict:
+    """LCG.get_constraint_graph (sat_representations.py:668-715) with the reference's own arguments: the LCG edge list
+    (literal -> clause edges, then the n pair edges).  Two clauses are neighbours when they share a variable; the result is
+    the jraph-style dict of this module (``senders`` / ``receivers`` in LCG node numbering, clause c = node 2n + c, zero
+    ``edges`` / ``nodes``).  The reference takes its edge order from scipy's sparse product; here every clause lists its
+    neighbours in increasing index -- the same edge SET, which is all the LLL loss (segment sums) depends on."""
+    senders = np.asarray(senders, dtype=np.int64).reshape(-1)
+    receivers = np.asarray(receivers, dtype=np.int64).reshape(-1)
+    n_occ = len(senders) - int(n_variables)
+    var_of = np.ascontiguousarray(senders[:n_occ] // 2, dtype=np.int32)
+    clause_of = np.ascontiguousarray(receivers[:n_occ] - 2 * int(n_variables), dtype=np.int32)
+    lib = _lib.load()
+    n_edge = C.c_uint64(0)
+    _check(lib.sls_constraint_graph(int(n_variables), int(n_clauses), var_of.ctypes.data, clause_of.ctypes.data, n_occ, None, None, 0,
+                                    C.byref(n_edge)))
+    out_s = np.zeros(max(n_edge.value, 1), dtype=np.int64)
+    out_r = np.zeros(max(n_edge.value, 1), dtype=np.int64)
+    _check(lib.sls_constraint_graph(int(n_variables), int(n_clauses), var_of.ctypes.data, clause_of.ctypes.data, n_occ,
+                                    out_s.ctypes.data, out_r.ctypes.data, out_s.size, C.byref(n_edge)))
+    e = int(n_edge.value)
+    return {"n_node": int(n_clauses), "n_edge": e, "senders": out_s[:e], "receivers": out_r[:e],
+            "edges": np.zeros(e), "nodes": np.zeros(int(n_clauses))}
+
+
 class InteractionNetworkLCG:
     """The shipped oracle network: embedding + ``num_message_passing_steps`` interaction-network steps
     + Linear(1) readout on the literal-clause graph."""
