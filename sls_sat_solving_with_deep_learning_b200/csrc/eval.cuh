@@ -33,12 +33,18 @@ __device__ __forceinline__ void transpose32x8(uint32_t (&x)[SLICE_Q], int lane)
         const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
         const bool hi = (lane & j) != 0;
         const uint32_t keep = hi ? ~m : m;  // this lane's diagonal block stays
+        // the partner's off-diagonal block moves across by a rotation (the bits that wrap around land in positions
+        // `keep` masks out): one funnel shift instead of shift-left / shift-right / select
+        const uint32_t rot = hi ? 32u - (uint32_t)j : (uint32_t)j;
         uint32_t y[SLICE_Q];
+        // volatile: the eight shuffles of a round are issued back to back and wait together (left to itself the
+        // compiler serialises tile pairs to save registers and every pair pays the shuffle latency)
 #pragma unroll
-        for (uint32_t q = 0; q < SLICE_Q; q++) y[q] = __shfl_xor_sync(0xffffffffu, x[q], j);
+        for (uint32_t q = 0; q < SLICE_Q; q++)
+            asm volatile("shfl.sync.bfly.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(y[q]) : "r"(x[q]), "r"(j));
 #pragma unroll
         for (uint32_t q = 0; q < SLICE_Q; q++) {
-            const uint32_t moved = hi ? (y[q] >> j) : (y[q] << j);  // the partner's off-diagonal block, moved across
+            const uint32_t moved = __funnelshift_l(y[q], y[q], rot);
             x[q] = (x[q] & keep) | (moved & ~keep);
         }
     }
