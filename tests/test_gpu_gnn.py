@@ -99,6 +99,25 @@ def test_large_batches_are_chunked_without_changing_results(monkeypatch):
     assert all(np.array_equal(a, b) for a, b in zip(p_one, p_chunks))
 
 
+def test_many_tiles_per_persistent_cta():
+    # 40 instances = ~870 edge tiles and ~420 node tiles on 148 persistent CTAs: every CTA walks several tiles (barrier
+    # parities across tiles, accumulator hand-over to the epilogue warps, next-tile prefetch) and the last wave is ragged
+    insts, clause_lists = [], []
+    for i in range(40):
+        n, m = 200 + (i % 3), 855 + 7 * (i % 5)
+        clauses = random_ksat(n, m, 3, seed=100 + i)
+        insts.append(eng.Instance.from_clauses(n, clauses))
+        clause_lists.append(clauses)
+    params = go.init_params(seed=21, bias_scale=0.1)
+    net = gnn.InteractionNetworkLCG(params)
+    probs = net.probabilities(insts)
+    for i in (0, 17, 39):
+        ref = go.forward(params, go.lcg_graph(insts[i].n, clause_lists[i]), dtype=np.float64)
+        assert np.abs(probs[i] - go.model_probabilities(ref, insts[i].n)).max() < PROB_TOL, i
+    again = net.probabilities(insts)  # deterministic: same kernels, same order of additions
+    assert all(np.array_equal(a, b) for a, b in zip(probs, again))
+
+
 def test_graph_edge_cases():
     params = go.init_params(seed=3, mlp_layers=(32, 32), num_steps=2, bias_scale=0.1)
     net = gnn.InteractionNetworkLCG(params, num_message_passing_steps=2)
