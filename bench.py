@@ -295,7 +295,13 @@ def run_own(args, rank, world, local_rank):
                          # because instance and chain state never leave L2 / shared memory
                          "traffic": 6.37e6, "peak_source": peak_src,
                          "bytes_per_flip": BYTES_PER_FLIP, "kernel_ms": kms,
-                         "note": "latency-bound walk: state in shared memory, instance in L2; see DESIGN.md"},
+                         "note": "latency-bound walk: state in shared memory, instance in L2; see DESIGN.md",
+                         # what the kernel is actually served from: L2 -> SM sectors per flip (ncu lts__t_sectors_srcunit_tex_op_read
+                         # of the same launch: 300 B per flip) against the L2 rates measured on this pool with tools/ubench.cu
+                         # (profiles/r01_ubench_l2_latency.md), and the measured step latency of a chain alone on an SM
+                         "l2": {"achieved_gbs": R * NSTEPS * 300.0 / (kms * 1e-3) / 1e9, "random_sector_peak_gbs": 8193.7,
+                                "stream_peak_gbs": 17526.5, "lone_chain_ns_per_step": 920.0,
+                                "loaded_ns_per_step": kms * 1e6 / NSTEPS}},
         }
     if dist:
         dist.barrier()
