@@ -1059,7 +1059,17 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     std::vector<WalkArgs> items[NG];
     std::vector<uint32_t> cta_begin[NG], owner[NG];
     size_t smem_max[NG] = {0, 0, 0, 0, 0};
-    for (uint32_t i = 0; i < n_inst; i++) {
+    // Launch order inside a kernel: instances with the highest clause / variable ratio first.  Their chains are the ones
+    // that run the whole step budget; started last, a single such CTA would keep the launch alive long after the rest of
+    // the machine has drained.  (Outputs are addressed per instance, so the order is free.)
+    std::vector<uint32_t> order(n_inst);
+    for (uint32_t i = 0; i < n_inst; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        const HostInstance &hx = insts[x]->host, &hy = insts[y]->host;
+        return (uint64_t)hx.m * std::max<uint32_t>(hy.n, 1) > (uint64_t)hy.m * std::max<uint32_t>(hx.n, 1);
+    });
+    for (uint32_t oi = 0; oi < n_inst; oi++) {
+        const uint32_t i = order[oi];
         const DevInst& I = insts[i]->dev;
         const ItemPlan& pl = plan[i];
         WalkArgs a{};
