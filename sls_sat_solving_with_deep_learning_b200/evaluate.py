@@ -1,7 +1,7 @@
 """The reference's evaluation driver on the B200 engine.
 
-Mirror of ``load_model_and_test`` (python/src/evaluate_with_given_params.py:26-174): same arguments, same
-returned / saved ``total_array`` schema
+Mirrors of ``load_model_and_test`` (python/src/evaluate_with_given_params.py:26-174) and
+``load_model_and_test_two_models`` (:177-345): same arguments, same returned / saved ``total_array`` schema
 ``[[model_path], [model_details_list], n_array, alpha_array, energies_array_mean, energies_array_median,
 total_steps_array]``.  What changes is how the work is scheduled: the reference loops over the instances and,
 for each, runs an un-jitted GNN forward and one ``run_sls_python`` call; here all oracle probabilities come from
@@ -42,32 +42,24 @@ def dataset_instances(data_path: str):
     return [p.split("_sol.pkl")[0] for p in glob.glob(join(data_path, "*_sol.pkl"))]
 
 
-def load_model_and_test(
-    data_path,
-    model_path,
-    n_steps: int,
-    n_runs: int,
-    algo_type: str,
-    path_save=False,
-    keep_traj: bool = True,
-    pre_compute_mapping: bool = False,
-    prob_flip_best: float = 0,
-    seed: int | None = None,
-):
-    """See the module docstring.  ``seed`` (not in the reference, whose chains are seeded from OS entropy,
-    rust/src/lib.rs:206) makes the run reproducible: instance ``idx`` uses ``seed + idx``."""
+def _oracle(model_path, insts):
+    """(model_details_list, probabilities per instance) of one oracle, ``"uniform"`` included (:67-88, :118-123)."""
+    if model_path != "uniform":
+        net, md = model_io.load_oracle(model_path)
+        details = [md.inv_temp, md.alpha, md.beta, md.gamma, md.mlp_layers, md.graph_representation, md.network_type,
+                   md.return_candidates]
+        return details, net.probabilities(insts)  # one batched forward instead of one apply per instance (:116)
+    return [], [np.ones(i.n) / 2 for i in insts]  # :123
+
+
+def _evaluate(data_path, probs_of, n_steps, n_runs, algo_type, keep_traj, pre_compute_mapping, prob_flip_best, seed):
+    """The part both drivers share: instances, oracle probabilities for initialisation and resampling, the walks, the
+    per-step statistics.  ``probs_of(insts)`` returns (probabilities_initialize, probabilities_resample)."""
     if seed is None:
         seed = int.from_bytes(os.urandom(8), "little")
     stems = dataset_instances(data_path)
     insts = [Instance.from_dimacs(s + ".cnf") for s in stems]
-    if model_path != "uniform":
-        net, md = model_io.load_oracle(model_path)
-        model_details_list = [md.inv_temp, md.alpha, md.beta, md.gamma, md.mlp_layers, md.graph_representation,
-                              md.network_type, md.return_candidates]
-        probs = net.probabilities(insts)  # one batched forward instead of one apply per instance (:116)
-    else:
-        model_details_list = []
-        probs = [np.ones(i.n) / 2 for i in insts]  # :123
+    probs_i, probs_r = probs_of(insts)
 
     n_array, alpha_array = [], []
     for inst in insts:
@@ -80,7 +72,7 @@ def load_model_and_test(
     total_steps = []
     energies_array_mean, energies_array_median = [], []
     if not keep_traj:
-        results = run_sls_batch(insts, algo_type, probs, probs, n_steps - 1, n_runs, pre_compute_mapping, prob_flip_best,
+        results = run_sls_batch(insts, algo_type, probs_i, probs_r, n_steps - 1, n_runs, pre_compute_mapping, prob_flip_best,
                                 instance_seeds=seeds) if insts else []
         total_steps = [[int(s) for s in r.steps] for r in results]
     else:
@@ -92,10 +84,10 @@ def load_model_and_test(
         for w0 in range(0, len(insts), wave):
             solvers = []
             try:
-                for k, (inst, p, sd) in enumerate(zip(insts[w0:w0 + wave], probs[w0:w0 + wave], seeds[w0:w0 + wave])):
+                for inst, pi, pr, sd in zip(insts[w0:w0 + wave], probs_i[w0:w0 + wave], probs_r[w0:w0 + wave], seeds[w0:w0 + wave]):
                     s = ResidentSolver(inst, algo_type, n_steps - 1, n_runs, True, pre_compute_mapping, prob_flip_best, seed=sd)
                     solvers.append(s)
-                    s.set_weights(p, p)
+                    s.set_weights(pi, pr)
                 for k, s in enumerate(solvers):
                     s.launch(streams[k % len(streams)])
                 for s, inst, alpha in zip(solvers, insts[w0:w0 + wave], alpha_array[w0:w0 + wave]):
@@ -112,8 +104,67 @@ def load_model_and_test(
     if energies_array_mean:
         energies_array_mean = np.mean(energies_array_mean, axis=0)      # :161
         energies_array_median = np.mean(energies_array_median, axis=0)  # :162
-    total_array = [[model_path], [model_details_list], n_array, alpha_array, energies_array_mean, energies_array_median,
-                   total_steps_array]
+    return n_array, alpha_array, energies_array_mean, energies_array_median, total_steps_array
+
+
+def load_model_and_test(
+    data_path,
+    model_path,
+    n_steps: int,
+    n_runs: int,
+    algo_type: str,
+    path_save=False,
+    keep_traj: bool = True,
+    pre_compute_mapping: bool = False,
+    prob_flip_best: float = 0,
+    seed: int | None = None,
+):
+    """See the module docstring.  ``seed`` (not in the reference, whose chains are seeded from OS entropy,
+    rust/src/lib.rs:206) makes the run reproducible: instance ``idx`` uses ``seed + idx``."""
+    details = []
+
+    def probs_of(insts):
+        d, p = _oracle(model_path, insts)
+        details.append(d)
+        return p, p
+
+    rest = _evaluate(data_path, probs_of, n_steps, n_runs, algo_type, keep_traj, pre_compute_mapping, prob_flip_best, seed)
+    total_array = [[model_path], [details[0]], *rest]
+    if path_save:
+        np.save(path_save, np.array(total_array, dtype=object))
+    return total_array
+
+
+def load_model_and_test_two_models(
+    data_path,
+    model_path_initialize,
+    model_path_resample,
+    n_steps: int,
+    n_runs: int,
+    algo_type,
+    path_save=False,
+    keep_traj: bool = True,
+    pre_compute_mapping: bool = True,
+    prob_flip_best: float = 0,
+    seed: int | None = None,
+):
+    """Mirror of ``load_model_and_test_two_models`` (python/src/evaluate_with_given_params.py:177-345): one oracle (or
+    ``"uniform"``) for the initial assignment, another for the resampling / flip rule.  Returned / saved schema:
+    ``[[model_path_initialize, model_path_resample], [model_details_list_i, model_details_list_r], n_array, alpha_array,
+    energies_array_mean, energies_array_median, total_steps_array]``."""
+    details = []
+
+    def probs_of(insts):
+        di, pi = _oracle(model_path_initialize, insts)
+        if model_path_resample == model_path_initialize:
+            dr, pr = di, pi  # same file: one forward
+        else:
+            dr, pr = _oracle(model_path_resample, insts)
+        details.extend([di, dr])
+        return pi, pr
+
+    rest = _evaluate(data_path, probs_of, n_steps, n_runs, algo_type, keep_traj, pre_compute_mapping, prob_flip_best, seed)
+    total_array = [[model_path_initialize, model_path_resample], [details[0], details[1]], *rest]
     if path_save:
         np.save(path_save, np.array(total_array, dtype=object))
     return total_array

@@ -102,3 +102,37 @@ def test_model_file_protocol(data_dir, tmp_path):
     ref = reference_protocol(data_dir, probs_of, 200, 10, "moser", False, True, 0.0, 5)
     assert got[6].shape == ref[4].shape
     assert abs(got[6].mean() - ref[4].mean()) < 0.25 * ref[4].mean() + 5
+
+
+def test_two_models_protocol(data_dir, tmp_path):
+    # load_model_and_test_two_models (evaluate_with_given_params.py:177-345): separate oracles for the initial assignment
+    # and for the flip rule.  Uniform / uniform must reproduce the one-model driver; the schema carries both paths.
+    eng.set_device(0)
+    out = str(tmp_path / "two.npy")
+    two = evaluate.load_model_and_test_two_models(data_dir, "uniform", "uniform", 300, 12, "probsat", path_save=out,
+                                                  keep_traj=True, pre_compute_mapping=True, prob_flip_best=0, seed=31)
+    one = evaluate.load_model_and_test(data_dir, "uniform", 300, 12, "probsat", keep_traj=True, pre_compute_mapping=True,
+                                       prob_flip_best=0, seed=31)
+    assert two[0] == ["uniform", "uniform"] and two[1] == [[], []]
+    assert two[2] == one[2] and two[3] == one[3] and (two[6] == one[6]).all()
+    assert np.array_equal(two[4], one[4]) and np.array_equal(two[5], one[5])
+    assert len(np.load(out, allow_pickle=True)) == 7
+    # initial assignment from the exact solution (weights 0 / 1), uniform flip rule: every chain starts solved
+    stems = evaluate.dataset_instances(data_dir)
+
+    class Exact:  # stands in for an oracle file: _oracle() is the only consumer of model_io.load_oracle
+        pass
+
+    sols = []
+    for stem in stems:
+        oi = so.Instance.from_dimacs(stem + ".cnf")
+        r = oi.run_sls("probsat", np.full(oi.n, 0.5), np.full(oi.n, 0.5), 200000, 8, False, True, 0.0, seed=1)
+        assert r.best_energy == 0
+        sols.append(r.best_assignment.astype(np.float64))
+    orig = evaluate._oracle
+    evaluate._oracle = lambda path, insts: (["exact"], sols) if path == "exact" else orig(path, insts)
+    try:
+        got = evaluate.load_model_and_test_two_models(data_dir, "exact", "uniform", 50, 6, "moser", keep_traj=False, seed=2)
+    finally:
+        evaluate._oracle = orig
+    assert got[1] == [["exact"], []] and (got[6] == 0).all()
