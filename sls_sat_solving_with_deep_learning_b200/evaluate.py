@@ -168,3 +168,36 @@ def load_model_and_test_two_models(
     if path_save:
         np.save(path_save, np.array(total_array, dtype=object))
     return total_array
+
+
+def evaluate_moser_rust(cnf_paths, net, mode_probabilities: str = "model", n_steps_moser: int = 100, n_runs_moser: int = 1,
+                        seed: int | None = None):
+    """The training loop's Moser-Tardos probe (python/src/train_utils.py:244-318) on the batched path: for every
+    instance the oracle-guided MT walk (``"moser"``, ``n_steps_moser - 1`` steps, ``n_runs_moser`` runs, mapping on,
+    no greedy mix -- the keyword call of :293-303), of which only the best energy is used (:293, :305), and the mean
+    binary entropy of the oracle's probabilities (:306-316).  Returns ``(mean energy / n_clauses, mean entropy)``.
+
+    The reference walks a ``data_subset`` of its dataset object with a haiku network; here the caller passes the
+    ``.cnf`` paths (or parsed :class:`Instance` objects) of that subset and an :class:`gnn.InteractionNetworkLCG`
+    (ignored for ``mode_probabilities="uniform"``).  One batched forward, one batched solve."""
+    insts = [p if isinstance(p, Instance) else Instance.from_dimacs(p) for p in cnf_paths]
+    if mode_probabilities == "uniform":
+        probs = [np.ones(i.n) / 2 for i in insts]
+    elif mode_probabilities == "model":
+        probs = net.probabilities(insts)
+    else:
+        raise ValueError("not valid argument for mode_probabilities")  # the reference prints this and then fails (:284)
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    seeds = [(seed + idx) & 0xFFFFFFFFFFFFFFFF for idx in range(len(insts))]
+    results = run_sls_batch(insts, "moser", probs, probs, n_steps_moser - 1, n_runs_moser, True, 0.0, instance_seeds=seeds)
+    av_energies, av_entropies = [], []
+    for inst, p, r in zip(insts, probs, results):
+        row, _ = inst.csr()
+        n_clauses = int(np.count_nonzero(np.diff(row.astype(np.int64)) > 0))  # problem.params[1]: empty clauses dropped
+        av_energies.append(r.best_energy / n_clauses)
+        q = np.clip(np.asarray(p, dtype=np.float64), 0.0, 1.0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            h = -(np.where(q > 0, q * np.log2(q), 0.0) + np.where(q < 1, (1 - q) * np.log2(1 - q), 0.0))
+        av_entropies.append(float(np.mean(h)))  # scipy.stats.entropy(base=2) per variable, then the mean (:311-316)
+    return (float(np.mean(av_energies)), float(np.mean(av_entropies)))

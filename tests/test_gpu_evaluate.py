@@ -136,3 +136,31 @@ def test_two_models_protocol(data_dir, tmp_path):
     finally:
         evaluate._oracle = orig
     assert got[1] == [["exact"], []] and (got[6] == 0).all()
+
+
+def test_training_probe_evaluate_moser_rust(data_dir):
+    # train_utils.py:244-318: best energy of an oracle-guided MT run per instance / n_clauses, and the oracle's entropy
+    from scipy.stats import entropy
+
+    eng.set_device(0)
+    stems = evaluate.dataset_instances(data_dir)
+    paths = [s + ".cnf" for s in stems]
+    e_gpu, h_gpu = evaluate.evaluate_moser_rust(paths, None, "uniform", n_steps_moser=60, n_runs_moser=3, seed=9)
+    energies = []
+    for idx, p in enumerate(paths):
+        oi = so.Instance.from_dimacs(p)
+        w = np.ones(oi.n) / 2
+        r = oi.run_sls("moser", w, w, 59, 3, False, True, 0.0, seed=9 + idx)
+        energies.append(r.best_energy / oi.m)
+    assert e_gpu == pytest.approx(np.mean(energies), abs=1e-12) and h_gpu == pytest.approx(1.0)
+    # with a network: entropies as scipy computes them from the GPU probabilities
+    from sls_sat_solving_with_deep_learning_b200 import gnn
+
+    net = gnn.InteractionNetworkLCG(go.init_params(seed=4, bias_scale=0.2))
+    insts = [eng.Instance.from_dimacs(p) for p in paths]
+    _, h_model = evaluate.evaluate_moser_rust(insts, net, "model", n_steps_moser=20, n_runs_moser=2, seed=1)
+    probs = net.probabilities(insts)
+    ref = np.mean([np.mean([entropy([1 - q, q], base=2) for q in p]) for p in probs])
+    assert h_model == pytest.approx(ref, rel=1e-6)
+    with pytest.raises(ValueError):
+        evaluate.evaluate_moser_rust(paths, None, "something")
