@@ -200,7 +200,9 @@ extern "C" int sls_gnn_model_create(const float* blob, uint64_t blob_len, int32_
         return rc;
     }
     m->readout_b = *p;
-    cudaError_t e = cudaFuncSetAttribute(mlp_ln_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(mlp_ln_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
     if (e != cudaSuccess) {
         sls_gnn_model_free(m);
@@ -211,6 +213,8 @@ extern "C" int sls_gnn_model_create(const float* blob, uint64_t blob_len, int32_
 }
 
 namespace {
+
+constexpr int GNN_DEFAULT_CLUSTER = 1;
 
 struct DevBuf {
     void* p = nullptr;
@@ -238,10 +242,36 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
     if (one_tile) {
         mlp_ln_kernel<<<blocks, MLP_THREADS, MLP_SMEM_BYTES>>>(a);
     } else {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        mlp_ln_persistent_kernel<<<std::min<unsigned>(blocks, (unsigned)sms), MLPP_THREADS, MLP_SMEM_BYTES>>>(a);
+        // SLS_B200_GNN_CLUSTER = 1 | 2 | 4: CTAs per cluster sharing the weight stream by multicast (see the kernel)
+        const char* f = std::getenv("SLS_B200_GNN_CLUSTER");  // read per launch: the tests switch it
+        const int c = f ? std::atoi(f) : GNN_DEFAULT_CLUSTER;
+        const int cluster = c == 2 || c == 4 ? c : 1;
+        if (cluster == 1) {
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            mlp_ln_persistent_kernel<1><<<std::min<unsigned>(blocks, (unsigned)sms), MLPP_THREADS, MLP_SMEM_BYTES>>>(a);
+        } else {
+            void (*kern)(const MlpArgs) = cluster == 2 ? mlp_ln_persistent_kernel<2> : mlp_ln_persistent_kernel<4>;
+            cudaLaunchConfig_t cfg{};
+            cudaLaunchAttribute attr{};
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = (unsigned)cluster, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+            cfg.blockDim = dim3(MLPP_THREADS), cfg.dynamicSmemBytes = MLP_SMEM_BYTES, cfg.stream = 0;
+            cfg.attrs = &attr, cfg.numAttrs = 1;
+            // the grid is one wave of co-resident clusters (tiles are assigned statically): ask how many fit
+            static int max_clusters[5] = {0, 0, 0, 0, 0};
+            if (max_clusters[cluster] == 0) {
+                cfg.gridDim = dim3((unsigned)cluster);
+                int n = 0;
+                G_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+                if (n < 1) return sls_set_error_internal(SLS_ERR_CUDA, "no cluster of the oracle-forward kernel fits on this device");
+                max_clusters[cluster] = n;
+            }
+            const unsigned want = (blocks + (unsigned)cluster - 1) / (unsigned)cluster;
+            cfg.gridDim = dim3(std::min<unsigned>(want, (unsigned)max_clusters[cluster]) * (unsigned)cluster);
+            G_TRY(cudaLaunchKernelEx(&cfg, kern, a));
+        }
     }
     m->launches++;
     G_TRY(cudaGetLastError());

@@ -47,7 +47,8 @@ static constexpr int MLP_PRODUCERS = 128;                // warps 0-3: stage A r
 static constexpr int MLP_THREADS = MLP_PRODUCERS + 32;   // warp 4: one lane issues the weight copies and the MMAs
 static constexpr int PAR_BYTES = 3 * MAX_N * 4;          // b2 | ln_scale | ln_offset staged in shared memory
 static constexpr int OUT_PITCH = 204;                   // floats per row of the output tile (816 B: conflict-free 16-byte stores)
-static constexpr int MLP_SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + 256 + PAR_BYTES + 1024;  // + barriers + alignment slack
+static constexpr int BAR_BYTES = 256;                    // mbarriers + the TMEM base address
+static constexpr int MLP_SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + BAR_BYTES + PAR_BYTES + 1024;  // + alignment slack
 
 struct MlpArgs {
     // up to three gathered input segments: row i of the A matrix is
@@ -132,6 +133,29 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// the same arrival delivered to the barrier at this offset in every CTA of the cluster named by cta_mask
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cta_mask) : "memory");
+}
+// TMA bulk copy global -> the same shared-memory offset of every CTA in cta_mask; each destination CTA's mbarrier (same
+// offset) counts the bytes
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 // D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
@@ -170,13 +194,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// Round to the nearest TF32 value (10-bit mantissa).  The tensor core ignores the low 13 mantissa
-// bits of an fp32 operand, so operands are rounded explicitly before they are staged.
+// Round to the nearest TF32 value (10-bit mantissa), ties away from zero like cvt.rna.tf32.f32.  The tensor core ignores
+// the low 13 mantissa bits of an fp32 operand, so operands are rounded explicitly before they are staged.  sm_100 has no
+// conversion instruction for this: ptxas expands cvt.rna.tf32.f32 into the same add-and-mask plus an |x| < inf guard
+// (four instructions); activations and residuals here are finite, and inf maps to inf without the guard anyway, so the
+// two-instruction form is used -- the staging threads, not the tensor pipe, set the pace of the MLP kernel.
 __device__ __forceinline__ float round_tf32(float x)
 {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
 // ---- the fused update: LayerNorm(ReLU(Linear2(ReLU(Linear1(gathered rows))))) -------------------
@@ -428,8 +453,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
 static constexpr int MLPP_PRODUCERS = 256;
 static constexpr int MLPP_THREADS = MLPP_PRODUCERS + 32 + 128;
 
+// CL > 1: the CTAs of a cluster of CL run their tiles in lock step and share the weight stream.  Each CTA requests 1 / CL of
+// every weight slab and the copy engine multicasts it into the same stage of all CL CTAs, so the L2 -> SM weight traffic
+// (85 % of what the kernel reads: every tile needs all 1.38 MB of slab images) drops by CL.  A weight stage is written by
+// all CTAs of the cluster, so it may only be refilled when the MMAs of ALL of them have drained it: every slab's
+// tcgen05.commit is also multicast to `sFreeB` (count CL) of every CTA.  Every CTA of a cluster runs the same number of
+// tiles (tiles past the end gather the last row and store nothing).
+template <int CL>
 __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(const MlpArgs P)
 {
+    static_assert(CL == 1 || CL == 2 || CL == 4, "cluster size");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sAst = base;
@@ -439,8 +472,9 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
     const uint32_t sArdy = sDone + 8 * DONE_BARS;
     const uint32_t sAccFull = sArdy + 8 * A_STAGES;
     const uint32_t sAccFree = sAccFull + 8;
-    const uint32_t sTmem = sAccFree + 8;
-    const uint32_t sPar = sFull + 128;
+    const uint32_t sFreeB = sAccFree + 8;
+    const uint32_t sTmem = sFreeB + 8 * DONE_BARS;
+    const uint32_t sPar = sFull + BAR_BYTES;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
 
     const int tid = threadIdx.x;
@@ -451,11 +485,16 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
     const int prow = tid & (TILE_M - 1);  // producers: row of the tile (two threads per row)
     const int part = tid >> 7;            // producers: which half of a slab's 32 columns
     const int ntiles = (P.rows + TILE_M - 1) / TILE_M;
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...; in a cluster every CTA runs the count of the first one
+    const uint32_t my_tiles = CL > 1 ? (uint32_t)((ntiles + (int)gridDim.x - 1) / (int)gridDim.x)
+                                     : ((int)blockIdx.x < ntiles ? (uint32_t)((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) : 0u);
+    constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
 
     if (tid == 0) {
         for (int i = 0; i < B_STAGES; i++) mbar_init(sFull + 8 * i, 1);
         for (int i = 0; i < DONE_BARS; i++) mbar_init(sDone + 8 * i, 1);
-        for (int i = 0; i < A_STAGES; i++) mbar_init(sArdy + 8 * i, MLPP_PRODUCERS);
+        for (int i = 0; i < A_STAGES; i++) mbar_init(sArdy + 8 * i, MLPP_PRODUCERS / 32);
+        for (int i = 0; i < DONE_BARS; i++) mbar_init(sFreeB + 8 * i, CL);
         mbar_init(sAccFull, 1);
         mbar_init(sAccFree, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -472,6 +511,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no multicast copy or commit may reach a CTA whose barriers are not initialised yet
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + (sTmem - base));
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;  // a warp reaches the TMEM lane quarter warp % 4
@@ -526,35 +566,45 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
                 for (int q = 0; q < 4; q++) put_split(stage_base, half * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
             }
         };
-        float4 xa[4];
+        // gathered rows travel two slabs ahead of their use (even slabs of a tile in xa0, odd ones in xa1): one slab
+        // of lead did not cover the L2 / HBM latency (11 % of the producers' stall samples sat on the first use)
+        float4 xa0[4], xa1[4];
         uint32_t J = 0;
-        if ((int)blockIdx.x < ntiles) {
+        if (my_tiles > 0) {
             set_rows(blockIdx.x);
-            load_a1(0, xa);
+            load_a1(0, xa0);
+            load_a1(1, xa1);
         }
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int next_tile = tile + gridDim.x;
-            for (uint32_t j = 0; j < S; j++, J++) {
+        for (uint32_t it = 0; it < my_tiles; it++) {
+            const int next_tile = (int)(blockIdx.x + (it + 1) * gridDim.x);
+            auto slab = [&](uint32_t j, float4* xa) {
                 const uint32_t sa = sAst + (J % A_STAGES) * A_STAGE_BYTES;
                 if (J >= (uint32_t)A_STAGES) wait_done(J - A_STAGES);
                 if (j < n1s) {
 #pragma unroll
                     for (int u = 0; u < 4; u++) put_split(sa, part * 4 + u, xa[u]);
-                    if (j + 1 < n1s) load_a1((int)j + 1, xa);
+                    if (j + 2 < n1s) load_a1((int)j + 2, xa);
                 } else {
                     if (j == n1s) {  // GEMM2 reads GEMM1's accumulator: every GEMM1 MMA must have completed
                         wait_done(J - 1);
                         tc_fence_after();
-                        if (next_tile < ntiles) {  // the next tile's first slab travels while this tile's GEMM2 is staged
+                        if (it + 1 < my_tiles) {  // the next tile's first slabs travel while this tile's GEMM2 is staged
                             set_rows(next_tile);
-                            load_a1(0, xa);
+                            load_a1(0, xa0);
+                            load_a1(1, xa1);
                         }
                     }
                     stage_a2(sa, (int)(j - n1s));
                 }
                 fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive(sArdy + 8 * (J % A_STAGES));
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(sArdy + 8 * (J % A_STAGES));  // one arrival per producer warp
+                J++;
+            };
+            for (uint32_t j = 0; j < S; j += 2) {
+                slab(j, xa0);
+                if (j + 1 < S) slab(j + 1, xa1);
             }
         }
     } else if (warp_u == MLPP_PRODUCERS / 32) {
@@ -564,9 +614,8 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
         // set the pace of the kernel (measured: 83 % of its time in its own ~330 instructions per slab, tensor pipe
         // 43 % busy).  No runtime modulo either: slab-in-tile counters run along.
         const bool leader = elect_one();
-        uint32_t my_tiles = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) my_tiles++;
         const uint32_t total = my_tiles * S;
+        const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
         constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version 1 | SWIZZLE_128B
         auto desc = [&](uint32_t addr) -> uint64_t { return (uint64_t)DESC_HI << 32 | (((addr >> 4) & 0x3fffu) | (1u << 16)); };
         const uint32_t idesc1 = idesc_tf32(TILE_M, P.n1), idesc2 = idesc_tf32(TILE_M, P.n2);
@@ -577,11 +626,24 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
             const float* hi = (g1 ? P.w1_hi : P.w2_hi) + (size_t)s * n_pad * SLAB_K;
             const float* lo = (g1 ? P.w1_lo : P.w2_lo) + (size_t)s * n_pad * SLAB_K;
             const uint32_t bs = sBst + (J % B_STAGES) * B_STAGE_BYTES, bar = sFull + 8 * (J % B_STAGES);
-            if (J >= (uint32_t)B_STAGES) wait_done(J - B_STAGES);
-            if (leader) {
-                mbar_expect_tx(bar, 2 * bbytes);
-                bulk_g2s(bs, hi, bbytes, bar);
-                bulk_g2s(bs + B_SLAB_BYTES, lo, bbytes, bar);
+            if (CL == 1) {
+                if (J >= (uint32_t)B_STAGES) wait_done(J - B_STAGES);
+                if (leader) {
+                    mbar_expect_tx(bar, 2 * bbytes);
+                    bulk_g2s(bs, hi, bbytes, bar);
+                    bulk_g2s(bs + B_SLAB_BYTES, lo, bbytes, bar);
+                }
+            } else {
+                if (J >= (uint32_t)B_STAGES) {  // the stage is free in every CTA of the cluster
+                    const uint32_t Jf = J - B_STAGES;
+                    mbar_wait(sFreeB + 8 * (Jf % DONE_BARS), (Jf / DONE_BARS) & 1u);
+                }
+                if (leader) {
+                    const uint32_t part = bbytes / CL, off = crank * part;  // n_pad * 128 / CL: a multiple of 512
+                    mbar_expect_tx(bar, 2 * bbytes);  // own part + the parts the other CTAs send
+                    bulk_g2s_multicast(bs + off, reinterpret_cast<const uint8_t*>(hi) + off, part, bar, CL_MASK);
+                    bulk_g2s_multicast(bs + B_SLAB_BYTES + off, reinterpret_cast<const uint8_t*>(lo) + off, part, bar, CL_MASK);
+                }
             }
         };
         uint32_t jn = 0;  // slab-in-tile index of the next weight slab to request
@@ -609,6 +671,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
                     umma_tf32(acc, dAh + 2 * kk, dBl + 2 * kk, idesc, 1u);
                 }
                 umma_commit(sDone + 8 * (J % DONE_BARS));
+                if (CL > 1) umma_commit_multicast(sFreeB + 8 * (J % DONE_BARS), CL_MASK);
                 if (j == S - 1) umma_commit(sAccFull);
             }
             __syncwarp();
@@ -617,6 +680,10 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
                 jn = jn + 1 == S ? 0 : jn + 1;
             }
             if (++j == S) j = 0, it++;
+        }
+        if (CL > 1) {  // every arrival the other CTAs still send to this one has landed before this CTA may exit
+            for (uint32_t J = total > (uint32_t)DONE_BARS ? total - DONE_BARS : 0u; J < total; J++)
+                mbar_wait(sFreeB + 8 * (J % DONE_BARS), (J / DONE_BARS) & 1u);
         }
     } else if (epilogue) {
         const int H = P.h2;
@@ -635,8 +702,8 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
                 x[4 * q + 2] = fmaxf(x[4 * q + 2] + b.z, 0.f), x[4 * q + 3] = fmaxf(x[4 * q + 3] + b.w, 0.f);
             }
         };
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        for (uint32_t it = 0; it < my_tiles; it++) {
+            const int tile = (int)(blockIdx.x + it * gridDim.x);
             mbar_wait_relaxed(sAccFull, it & 1u);
             tc_fence_after();
             float sum = 0.f;
@@ -678,6 +745,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 

@@ -118,6 +118,26 @@ def test_many_tiles_per_persistent_cta():
     assert all(np.array_equal(a, b) for a, b in zip(probs, again))
 
 
+@pytest.mark.parametrize("cluster", [2, 4])
+def test_weight_multicast_clusters_are_bit_identical(cluster, monkeypatch):
+    # CTAs of a cluster share every weight slab (each requests 1 / cluster of it, the copy engine multicasts); rows, MMAs
+    # and their order per tile are unchanged, so the logits must not differ in a single bit -- for several tiles per
+    # CTA, a ragged last wave (dummy tiles), and for a batch smaller than one cluster's worth of tiles
+    for n_inst in (40, 1):
+        insts = []
+        for i in range(n_inst):
+            n, m = 200 + (i % 3), 855 + 7 * (i % 5)
+            insts.append(eng.Instance.from_clauses(n, random_ksat(n, m, 3, seed=300 + i)))
+        params = go.init_params(seed=22, bias_scale=0.1)
+        net = gnn.InteractionNetworkLCG(params)
+        monkeypatch.setenv("SLS_B200_GNN_CLUSTER", "1")
+        p1, d1 = net.probabilities(insts, return_decoded=True)
+        monkeypatch.setenv("SLS_B200_GNN_CLUSTER", str(cluster))
+        pc, dc = net.probabilities(insts, return_decoded=True)
+        assert np.array_equal(d1, dc)
+        assert all(np.array_equal(a, b) for a, b in zip(p1, pc))
+
+
 def test_graph_edge_cases():
     params = go.init_params(seed=3, mlp_layers=(32, 32), num_steps=2, bias_scale=0.1)
     net = gnn.InteractionNetworkLCG(params, num_message_passing_steps=2)
