@@ -203,6 +203,7 @@ extern "C" int sls_gnn_model_create(const float* blob, uint64_t blob_len, int32_
     cudaError_t e = cudaFuncSetAttribute(mlp_ln_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
     if (e != cudaSuccess) {
         sls_gnn_model_free(m);
@@ -246,7 +247,15 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
         const char* f = std::getenv("SLS_B200_GNN_CLUSTER");  // read per launch: the tests switch it
         const int c = f ? std::atoi(f) : GNN_DEFAULT_CLUSTER;
         const int cluster = c == 2 || c == 4 ? c : 1;
-        if (cluster == 1) {
+        // SLS_B200_GNN_A_TMEM=0 selects the kernel that stages the A operand in shared memory (and the cluster variants)
+        const char* ft = std::getenv("SLS_B200_GNN_A_TMEM");
+        const bool a_tmem = ft ? ft[0] != '0' : (f == nullptr);
+        if (a_tmem) {
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            mlp_ln_persistent_ts_kernel<<<std::min<unsigned>(blocks, (unsigned)sms), MLPP_THREADS, TS_SMEM_BYTES>>>(a);
+        } else if (cluster == 1) {
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

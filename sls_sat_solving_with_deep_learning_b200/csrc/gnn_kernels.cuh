@@ -749,6 +749,307 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
+// ---- the same update with the A operand in TENSOR MEMORY ---------------------------------------------------------
+// ncu of the kernel above (profiles/r01_gnn_mlp_ln_summary.md): the shared-memory data pipe (128 B per clock and SM) is what
+// the 3xTF32 product saturates, not the tensor pipe -- per slab the twelve MMAs read 12 x (4 KB of A + 6.6 KB of B), the
+// producers write 32 KB of A and the copy engine 52 KB of B: 1.5x what the pipe moves in the 1160 cycles the MMAs need, so
+// the tensor pipe cannot be more than ~65 % busy however the roles are balanced (measured 47-50 %; cheaper staging
+// code, deeper prefetch and multicast weight slabs all left the time unchanged).  Here the A operand never touches
+// shared memory: the producers write the split rows with tcgen05.st into three 32-column stages next to the two
+// accumulators (acc1 columns 0-207, acc2 208-415, A stages 416-511: 16 hi + 16 lo columns = 16 of a slab's 32 k-values)
+// and the MMAs take A from tensor memory (tcgen05.mma [d], [a], b-desc).  Shared memory then only carries the weight
+// slabs: 80 KB of B reads + 52 KB of B writes per slab, which fits under the MMA time, and the 64 KB of A stages become a
+// fourth weight stage.
+// A "unit" is half a slab (16 k-values, six MMAs).  Producer group g (warps 4g .. 4g+3, thread = row) stages the units
+// 2J + g, i.e. the columns it already gathers; unit U lives in A stage U % 3 and is released by its own tcgen05.commit
+// (sDone[U % 6]).
+static constexpr int TS_B_STAGES = 4;
+static constexpr int TS_A_STAGES = 3;
+static constexpr int TS_A_COL = 416;     // first A-stage column; 32 columns per stage
+static constexpr int TS_ACC2_COL = 208;
+static constexpr int TS_SMEM_BYTES = TS_B_STAGES * B_STAGE_BYTES + BAR_BYTES + PAR_BYTES + 1024;
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{ .reg .pred p;\n"
+        "  setp.ne.b32 p, %4, 0;\n"
+        "  tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p; }\n"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r)
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31]) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(const MlpArgs P)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sBst = base;
+    const uint32_t sFull = sBst + TS_B_STAGES * B_STAGE_BYTES;
+    const uint32_t sDone = sFull + 8 * TS_B_STAGES;
+    const uint32_t sArdy = sDone + 8 * DONE_BARS;
+    const uint32_t sAccFull = sArdy + 8 * TS_A_STAGES;
+    const uint32_t sAccFree = sAccFull + 8;
+    const uint32_t sTmem = sAccFree + 8;
+    const uint32_t sPar = sFull + BAR_BYTES;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const bool producer = tid < MLPP_PRODUCERS;
+    const bool epilogue = tid >= MLPP_PRODUCERS + 32;
+    const int prow = tid & (TILE_M - 1);   // producers: row of the tile = TMEM lane
+    const uint32_t grp = (uint32_t)tid >> 7;  // producers: which 16 of a slab's 32 columns, i.e. which units
+    const int ntiles = (P.rows + TILE_M - 1) / TILE_M;
+    const uint32_t my_tiles = (int)blockIdx.x < ntiles ? (uint32_t)((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) : 0u;
+
+    if (tid == 0) {
+        for (int i = 0; i < TS_B_STAGES; i++) mbar_init(sFull + 8 * i, 1);
+        for (int i = 0; i < DONE_BARS; i++) mbar_init(sDone + 8 * i, 1);
+        for (int i = 0; i < TS_A_STAGES; i++) mbar_init(sArdy + 8 * i, MLPP_PRODUCERS / 64);  // the four warps of one group
+        mbar_init(sAccFull, 1);
+        mbar_init(sAccFree, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < MAX_N; i += MLPP_THREADS) {
+        const bool in = i < P.h2;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + i * 4), "f"(i < P.n2 ? __ldg(P.b2 + i) : 0.f) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + (MAX_N + i) * 4), "f"(in ? __ldg(P.ln_scale + i) : 0.f) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + (2 * MAX_N + i) * 4), "f"(in ? __ldg(P.ln_offset + i) : 0.f) : "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + (sTmem - base));
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t n1s = (uint32_t)P.k1_slabs, n2s = (uint32_t)P.k2_slabs, S = n1s + n2s;
+    auto wait_unit = [&](uint32_t U) { mbar_wait(sDone + 8 * (U % DONE_BARS), (U / DONE_BARS) & 1u); };
+
+    if (producer) {
+        const int kA = P.d[0] + P.d[1] + P.d[2];
+        const float* rp[3] = {nullptr, nullptr, nullptr};
+        auto set_rows = [&](int tile) {
+            const int my_row = min(tile * TILE_M + prow, P.rows - 1);
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+                if (P.d[j] > 0) {
+                    const int r = P.idx[j] ? __ldg(P.idx[j] + my_row) : my_row;
+                    rp[j] = P.src[j] + (size_t)r * P.d[j];
+                }
+        };
+        auto load_a1 = [&](int s, float4* x) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int col = s * SLAB_K + ((int)grp * 4 + u) * 4;
+                x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col < kA) {
+                    const float* p = col < P.d[0] ? rp[0] + col : col < P.d[0] + P.d[1] ? rp[1] + (col - P.d[0]) : rp[2] + (col - P.d[0] - P.d[1]);
+                    x[u] = __ldg(reinterpret_cast<const float4*>(p));
+                }
+            }
+        };
+        // v[16] -> 16 hi | 16 lo columns of A stage U % 3
+        auto put_unit = [&](uint32_t U, const float* v) {
+            uint32_t r[32];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const float hi = round_tf32(v[i]);
+                r[i] = __float_as_uint(hi);
+                r[16 + i] = __float_as_uint(round_tf32(v[i] - hi));
+            }
+            tmem_st32(tmem + lane_base + (uint32_t)(TS_A_COL + 32 * (U % TS_A_STAGES)), r);
+        };
+        float4 xa0[4], xa1[4];
+        uint32_t J = 0;
+        if (my_tiles > 0) {
+            set_rows(blockIdx.x);
+            load_a1(0, xa0);
+            load_a1(1, xa1);
+        }
+        for (uint32_t it = 0; it < my_tiles; it++) {
+            const int next_tile = (int)(blockIdx.x + (it + 1) * gridDim.x);
+            auto slab = [&](uint32_t j, float4* xa) {
+                const uint32_t U = 2 * J + grp;
+                if (U >= (uint32_t)TS_A_STAGES) wait_unit(U - TS_A_STAGES);
+                float v[16];
+                if (j < n1s) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) v[4 * u] = xa[u].x, v[4 * u + 1] = xa[u].y, v[4 * u + 2] = xa[u].z, v[4 * u + 3] = xa[u].w;
+                    tc_fence_after();
+                    put_unit(U, v);
+                    if (j + 2 < n1s) load_a1((int)j + 2, xa);
+                } else {
+                    if (j == n1s) {  // GEMM2 reads GEMM1's accumulator: every GEMM1 MMA must have completed
+                        wait_unit(2 * J - 1);
+                        if (it + 1 < my_tiles) {
+                            set_rows(next_tile);
+                            load_a1(0, xa0);
+                            load_a1(1, xa1);
+                        }
+                    }
+                    tc_fence_after();
+                    const int c0 = (int)(j - n1s) * SLAB_K + (int)grp * 16;
+                    if (c0 < P.n1) {
+                        tmem_ld16(tmem + lane_base + (uint32_t)c0, v);
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + __ldg(P.b1 + c0 + i), 0.f);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] = 0.f;
+                    }
+                    put_unit(U, v);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(sArdy + 8 * (U % TS_A_STAGES));
+                J++;
+            };
+            for (uint32_t j = 0; j < S; j += 2) {
+                slab(j, xa0);
+                if (j + 1 < S) slab(j + 1, xa1);
+            }
+        }
+    } else if (warp_u == MLPP_PRODUCERS / 32) {
+        const bool leader = elect_one();
+        const uint32_t total = my_tiles * S;
+        constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version 1 | SWIZZLE_128B
+        auto desc = [&](uint32_t addr) -> uint64_t { return (uint64_t)DESC_HI << 32 | (((addr >> 4) & 0x3fffu) | (1u << 16)); };
+        const uint32_t idesc1 = idesc_tf32(TILE_M, P.n1), idesc2 = idesc_tf32(TILE_M, P.n2);
+        auto issue_b = [&](uint32_t J, uint32_t j) {  // j = J % S
+            const bool g1 = j < n1s;
+            const int n_pad = g1 ? P.n1 : P.n2;
+            const uint32_t s = g1 ? j : j - n1s, bbytes = (uint32_t)n_pad * 128u;
+            const float* hi = (g1 ? P.w1_hi : P.w2_hi) + (size_t)s * n_pad * SLAB_K;
+            const float* lo = (g1 ? P.w1_lo : P.w2_lo) + (size_t)s * n_pad * SLAB_K;
+            const uint32_t bs = sBst + (J % TS_B_STAGES) * B_STAGE_BYTES, bar = sFull + 8 * (J % TS_B_STAGES);
+            if (J >= (uint32_t)TS_B_STAGES) wait_unit(2 * (J - TS_B_STAGES) + 1);  // both units of the stage's last slab are done
+            if (leader) {
+                mbar_expect_tx(bar, 2 * bbytes);
+                bulk_g2s(bs, hi, bbytes, bar);
+                bulk_g2s(bs + B_SLAB_BYTES, lo, bbytes, bar);
+            }
+        };
+        // weights travel PF slabs ahead; the stage a request overwrites was read two slabs ago, so the issuer does not
+        // stall on the slab it has just queued
+        constexpr uint32_t PF = TS_B_STAGES - 2;
+        uint32_t jn = 0;
+        for (uint32_t J = 0; J < PF && J < total; J++) {
+            issue_b(J, jn);
+            jn = jn + 1 == S ? 0 : jn + 1;
+        }
+        uint32_t j = 0, it = 0;
+        for (uint32_t J = 0; J < total; J++) {
+            const bool g1 = j < n1s;
+            const uint32_t idesc = g1 ? idesc1 : idesc2;
+            const uint32_t acc = tmem + (g1 ? 0u : (uint32_t)TS_ACC2_COL);
+            const uint32_t first = g1 ? 0u : n1s;
+            mbar_wait(sFull + 8 * (J % TS_B_STAGES), (J / TS_B_STAGES) & 1u);
+            if (j == n1s && it > 0) mbar_wait(sAccFree, (it - 1) & 1u);  // the epilogue of the previous tile has read acc2
+            const uint32_t bHi = sBst + (J % TS_B_STAGES) * B_STAGE_BYTES;
+            const uint64_t dBh = desc(bHi), dBl = desc(bHi + B_SLAB_BYTES);
+#pragma unroll
+            for (uint32_t h = 0; h < 2; h++) {
+                const uint32_t U = 2 * J + h;
+                mbar_wait(sArdy + 8 * (U % TS_A_STAGES), (U / TS_A_STAGES) & 1u);
+                tc_fence_after();
+                const uint32_t a = tmem + (uint32_t)(TS_A_COL + 32 * (U % TS_A_STAGES));
+                if (leader) {
+#pragma unroll
+                    for (uint32_t q = 0; q < 2; q++) {  // k-step 2h + q of the slab: 8 tf32 = 8 columns of A, 32 bytes of a B row
+                        const uint32_t kk = 2 * h + q;
+                        umma_tf32_ts(acc, a + 8 * q, dBh + 2 * kk, idesc, (j != first || kk != 0) ? 1u : 0u);
+                        umma_tf32_ts(acc, a + 16 + 8 * q, dBh + 2 * kk, idesc, 1u);
+                        umma_tf32_ts(acc, a + 8 * q, dBl + 2 * kk, idesc, 1u);
+                    }
+                    umma_commit(sDone + 8 * (U % DONE_BARS));
+                    if (h == 1 && j == S - 1) umma_commit(sAccFull);
+                }
+                __syncwarp();
+            }
+            if (J + PF < total) {
+                issue_b(J + PF, jn);
+                jn = jn + 1 == S ? 0 : jn + 1;
+            }
+            if (++j == S) j = 0, it++;
+        }
+    } else if (epilogue) {
+        const int H = P.h2;
+        const int erow = (warp & 3) * 32 + (tid & 31);
+        auto lds4 = [](uint32_t a) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+            return v;
+        };
+        auto load_x = [&](int c0, float* x) {
+            tmem_ld16(tmem + lane_base + (uint32_t)(TS_ACC2_COL + c0), x);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float4 b = lds4(sPar + (c0 + 4 * q) * 4);
+                x[4 * q] = fmaxf(x[4 * q] + b.x, 0.f), x[4 * q + 1] = fmaxf(x[4 * q + 1] + b.y, 0.f);
+                x[4 * q + 2] = fmaxf(x[4 * q + 2] + b.z, 0.f), x[4 * q + 3] = fmaxf(x[4 * q + 3] + b.w, 0.f);
+            }
+        };
+        for (uint32_t it = 0; it < my_tiles; it++) {
+            const int tile = (int)(blockIdx.x + it * gridDim.x);
+            mbar_wait_relaxed(sAccFull, it & 1u);
+            tc_fence_after();
+            float sum = 0.f;
+            for (int c0 = 0; c0 < H; c0 += 16) {
+                float x[16];
+                load_x(c0, x);
+#pragma unroll
+                for (int i = 0; i < 16; i++) sum += x[i];
+            }
+            const float mean = sum / (float)H;
+            float sq = 0.f;
+            for (int c0 = 0; c0 < H; c0 += 16) {
+                float x[16];
+                load_x(c0, x);
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    if (c0 + i < H) sq += (x[i] - mean) * (x[i] - mean);
+            }
+            const float rstd = rsqrtf(sq / (float)H + 1e-5f);
+            const int row = tile * TILE_M + erow;
+            float* orow = P.out + (size_t)min(row, P.rows - 1) * H;
+            for (int c0 = 0; c0 < H; c0 += 16) {
+                float x[16];
+                load_x(c0, x);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (c0 + 4 * q < H && row < P.rows) {
+                        const float4 sc = lds4(sPar + (MAX_N + c0 + 4 * q) * 4), of = lds4(sPar + (2 * MAX_N + c0 + 4 * q) * 4);
+                        float4 y;
+                        y.x = (x[4 * q] - mean) * rstd * sc.x + of.x, y.y = (x[4 * q + 1] - mean) * rstd * sc.y + of.y;
+                        y.z = (x[4 * q + 2] - mean) * rstd * sc.z + of.z, y.w = (x[4 * q + 3] - mean) * rstd * sc.w + of.w;
+                        *reinterpret_cast<float4*>(orow + c0 + 4 * q) = y;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(sAccFree);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
 // ---- small kernels -------------------------------------------------------------------------------
 // Linear(2 -> D): out[i][c] = x[i][0]*w[0][c] + x[i][1]*w[1][c] + b[c]     (model.py:13-16)
 __global__ void embed_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,

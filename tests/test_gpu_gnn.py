@@ -138,6 +138,23 @@ def test_weight_multicast_clusters_are_bit_identical(cluster, monkeypatch):
         assert all(np.array_equal(a, b) for a, b in zip(p1, pc))
 
 
+def test_a_operand_in_tensor_memory_equals_shared_memory_staging(monkeypatch):
+    # default kernel: split rows written to TMEM (tcgen05.st), MMAs with A from tensor memory; SLS_B200_GNN_A_TMEM=0: rows
+    # staged in shared memory.  Same products accumulated in the same order: identical logits
+    insts = []
+    for i in range(24):
+        n, m = 150 + 5 * (i % 4), 600 + 11 * (i % 7)
+        insts.append(eng.Instance.from_clauses(n, random_ksat(n, m, 3, seed=500 + i)))
+    params = go.init_params(seed=23, bias_scale=0.1)
+    net = gnn.InteractionNetworkLCG(params)
+    monkeypatch.setenv("SLS_B200_GNN_A_TMEM", "1")
+    p1, d1 = net.probabilities(insts, return_decoded=True)
+    monkeypatch.setenv("SLS_B200_GNN_A_TMEM", "0")
+    p0, d0 = net.probabilities(insts, return_decoded=True)
+    assert np.array_equal(d1, d0)
+    assert all(np.array_equal(a, b) for a, b in zip(p1, p0))
+
+
 def test_graph_edge_cases():
     params = go.init_params(seed=3, mlp_layers=(32, 32), num_steps=2, bias_scale=0.1)
     net = gnn.InteractionNetworkLCG(params, num_message_passing_steps=2)
