@@ -72,6 +72,7 @@ struct MlpArgs {
     const float* ln_scale;   // [h2]
     const float* ln_offset;  // [h2]
     float* out;          // [rows][h2]
+    int32_t dbg;         // measurement only (SLS_B200_GNN_DBG): 2 = producers run the barrier protocol only, 4 = no gathers after a tile's first two slabs, 8 = no TMEM stores in GEMM1 (wrong results)
 };
 
 // ---- small PTX helpers -----------------------------------------------------------------------
@@ -204,6 +205,11 @@ __device__ __forceinline__ float round_tf32(float x)
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
+// The residual x - hi of the 3xTF32 product.  It is exact in fp32 (at most 13 significant bits) and is handed to the tensor
+// core as it is: the hardware drops its low mantissa bits, an error of 2^-11 of the residual = 2^-22 of x, below the fp32
+// rounding of the accumulation itself -- and one instruction instead of three on the staging threads' path.
+__device__ __forceinline__ float residual_tf32(float x, float hi) { return x - hi; }
+
 // ---- the fused update: LayerNorm(ReLU(Linear2(ReLU(Linear1(gathered rows))))) -------------------
 __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
 {
@@ -263,7 +269,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
     auto put_split = [&](uint32_t stage_base, int u, float4 x) {
         float4 hi, lo;
         hi.x = round_tf32(x.x), hi.y = round_tf32(x.y), hi.z = round_tf32(x.z), hi.w = round_tf32(x.w);
-        lo.x = round_tf32(x.x - hi.x), lo.y = round_tf32(x.y - hi.y), lo.z = round_tf32(x.z - hi.z), lo.w = round_tf32(x.w - hi.w);
+        lo.x = residual_tf32(x.x, hi.x), lo.y = residual_tf32(x.y, hi.y), lo.z = residual_tf32(x.z, hi.z), lo.w = residual_tf32(x.w, hi.w);
         const uint32_t off = sw128_off(tid, u);
         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + A_SLAB_BYTES + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
@@ -523,7 +529,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(cons
         auto put_split = [&](uint32_t stage_base, int u, float4 x) {
             float4 hi, lo;
             hi.x = round_tf32(x.x), hi.y = round_tf32(x.y), hi.z = round_tf32(x.z), hi.w = round_tf32(x.w);
-            lo.x = round_tf32(x.x - hi.x), lo.y = round_tf32(x.y - hi.y), lo.z = round_tf32(x.z - hi.z), lo.w = round_tf32(x.w - hi.w);
+            lo.x = residual_tf32(x.x, hi.x), lo.y = residual_tf32(x.y, hi.y), lo.z = residual_tf32(x.z, hi.z), lo.w = residual_tf32(x.w, hi.w);
             const uint32_t off = sw128_off(prow, u);
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + A_SLAB_BYTES + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
@@ -850,9 +856,33 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                 if (P.d[j] > 0) {
                     const int r = P.idx[j] ? __ldg(P.idx[j] + my_row) : my_row;
                     rp[j] = P.src[j] + (size_t)r * P.d[j];
+                    // The row is gathered slab by slab over the whole tile; ask L2 for all of it now (the two threads of a
+                    // row take alternate 128-byte lines).  Gathered rows come from HBM (the feature arrays are several
+                    // times the L2) and a register prefetch two slabs ahead did not cover that latency: measured 3.1 of
+                    // 24.6 ms per forward spent waiting for gathers.
+                    if (!(P.dbg & 16))
+                        for (int o = (int)grp * 32; o < P.d[j]; o += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp[j] + o));
                 }
         };
+        // segment widths that are multiples of 8 floats (every shipped layer: 32 and 200): a thread's 64 bytes of a slab are
+        // two whole 32-byte sectors, fetched with two 256-bit loads instead of four 128-bit ones
+        const bool wide = ((P.d[0] | P.d[1] | P.d[2]) & 7) == 0;
         auto load_a1 = [&](int s, float4* x) {
+            if (wide) {
+#pragma unroll
+                for (int u = 0; u < 4; u += 2) {
+                    const int col = s * SLAB_K + ((int)grp * 4 + u) * 4;
+                    x[u] = x[u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (col < kA) {
+                        const float* p = col < P.d[0] ? rp[0] + col : col < P.d[0] + P.d[1] ? rp[1] + (col - P.d[0]) : rp[2] + (col - P.d[0] - P.d[1]);
+                        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                     : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w), "=f"(x[u + 1].x), "=f"(x[u + 1].y),
+                                       "=f"(x[u + 1].z), "=f"(x[u + 1].w)
+                                     : "l"(p));
+                    }
+                }
+                return;
+            }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int col = s * SLAB_K + ((int)grp * 4 + u) * 4;
@@ -870,7 +900,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
             for (int i = 0; i < 16; i++) {
                 const float hi = round_tf32(v[i]);
                 r[i] = __float_as_uint(hi);
-                r[16 + i] = __float_as_uint(round_tf32(v[i] - hi));
+                r[16 + i] = __float_as_uint(residual_tf32(v[i], hi));
             }
             tmem_st32(tmem + lane_base + (uint32_t)(TS_A_COL + 32 * (U % TS_A_STAGES)), r);
         };
@@ -887,12 +917,21 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                 const uint32_t U = 2 * J + grp;
                 if (U >= (uint32_t)TS_A_STAGES) wait_unit(U - TS_A_STAGES);
                 float v[16];
-                if (j < n1s) {
+                if (P.dbg & 2) {
+                    if (j == n1s) wait_unit(2 * J - 1);
+                } else if (j < n1s) {
 #pragma unroll
                     for (int u = 0; u < 4; u++) v[4 * u] = xa[u].x, v[4 * u + 1] = xa[u].y, v[4 * u + 2] = xa[u].z, v[4 * u + 3] = xa[u].w;
                     tc_fence_after();
-                    put_unit(U, v);
-                    if (j + 2 < n1s) load_a1((int)j + 2, xa);
+                    if (P.dbg & 8) {  // gathers without the TMEM store
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) acc += v[i];
+                        if (acc == 1.2345e30f) P.out[0] = acc;
+                    } else {
+                        put_unit(U, v);
+                    }
+                    if (j + 2 < n1s && !(P.dbg & 4)) load_a1((int)j + 2, xa);
                 } else {
                     if (j == n1s) {  // GEMM2 reads GEMM1's accumulator: every GEMM1 MMA must have completed
                         wait_unit(2 * J - 1);
