@@ -237,10 +237,6 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
     a.w1_hi = w.w1_hi, a.w1_lo = w.w1_lo, a.b1 = w.b1, a.w2_hi = w.w2_hi, a.w2_lo = w.w2_lo, a.b2 = w.b2;
     a.ln_scale = w.ln_scale, a.ln_offset = w.ln_offset;
     a.out = out;
-    {
-        const char* fd = std::getenv("SLS_B200_GNN_DBG");
-        a.dbg = fd ? std::atoi(fd) : 0;
-    }
     const unsigned blocks = (unsigned)((rows + TILE_M - 1) / TILE_M);
     // persistent three-role kernel, one CTA per SM; SLS_B200_GNN_ONE_TILE=1 selects the one-tile-per-CTA kernel
     static const bool one_tile = [] { const char* f = std::getenv("SLS_B200_GNN_ONE_TILE"); return f && f[0] == '1'; }();

@@ -72,7 +72,6 @@ struct MlpArgs {
     const float* ln_scale;   // [h2]
     const float* ln_offset;  // [h2]
     float* out;          // [rows][h2]
-    int32_t dbg;         // measurement only (SLS_B200_GNN_DBG): 2 = producers run the barrier protocol only, 4 = no gathers after a tile's first two slabs, 8 = no TMEM stores in GEMM1 (wrong results)
 };
 
 // ---- small PTX helpers -----------------------------------------------------------------------
@@ -773,7 +772,7 @@ static constexpr int TS_B_STAGES = 4;
 static constexpr int TS_A_STAGES = 3;
 static constexpr int TS_A_COL = 416;     // first A-stage column; 32 columns per stage
 static constexpr int TS_ACC2_COL = 208;
-static constexpr int TS_SMEM_BYTES = TS_B_STAGES * B_STAGE_BYTES + BAR_BYTES + PAR_BYTES + 1024;
+static constexpr int TS_SMEM_BYTES = TS_B_STAGES * B_STAGE_BYTES + BAR_BYTES + PAR_BYTES + MAX_N * 4 + 1024;  // + b1
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
@@ -833,6 +832,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + i * 4), "f"(i < P.n2 ? __ldg(P.b2 + i) : 0.f) : "memory");
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + (MAX_N + i) * 4), "f"(in ? __ldg(P.ln_scale + i) : 0.f) : "memory");
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + (2 * MAX_N + i) * 4), "f"(in ? __ldg(P.ln_offset + i) : 0.f) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + (3 * MAX_N + i) * 4), "f"(i < P.n1 ? __ldg(P.b1 + i) : 0.f) : "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "r"(TMEM_COLS) : "memory");
@@ -860,8 +860,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                     // row take alternate 128-byte lines).  Gathered rows come from HBM (the feature arrays are several
                     // times the L2) and a register prefetch two slabs ahead did not cover that latency: measured 3.1 of
                     // 24.6 ms per forward spent waiting for gathers.
-                    if (!(P.dbg & 16))
-                        for (int o = (int)grp * 32; o < P.d[j]; o += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp[j] + o));
+                    for (int o = (int)grp * 32; o < P.d[j]; o += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp[j] + o));
                 }
         };
         // segment widths that are multiples of 8 floats (every shipped layer: 32 and 200): a thread's 64 bytes of a slab are
@@ -917,21 +916,12 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                 const uint32_t U = 2 * J + grp;
                 if (U >= (uint32_t)TS_A_STAGES) wait_unit(U - TS_A_STAGES);
                 float v[16];
-                if (P.dbg & 2) {
-                    if (j == n1s) wait_unit(2 * J - 1);
-                } else if (j < n1s) {
+                if (j < n1s) {
 #pragma unroll
                     for (int u = 0; u < 4; u++) v[4 * u] = xa[u].x, v[4 * u + 1] = xa[u].y, v[4 * u + 2] = xa[u].z, v[4 * u + 3] = xa[u].w;
                     tc_fence_after();
-                    if (P.dbg & 8) {  // gathers without the TMEM store
-                        float acc = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 16; i++) acc += v[i];
-                        if (acc == 1.2345e30f) P.out[0] = acc;
-                    } else {
-                        put_unit(U, v);
-                    }
-                    if (j + 2 < n1s && !(P.dbg & 4)) load_a1((int)j + 2, xa);
+                    put_unit(U, v);
+                    if (j + 2 < n1s) load_a1((int)j + 2, xa);
                 } else {
                     if (j == n1s) {  // GEMM2 reads GEMM1's accumulator: every GEMM1 MMA must have completed
                         wait_unit(2 * J - 1);
@@ -946,7 +936,12 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                     if (c0 < P.n1) {
                         tmem_ld16(tmem + lane_base + (uint32_t)c0, v);
 #pragma unroll
-                        for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + __ldg(P.b1 + c0 + i), 0.f);
+                        for (int q = 0; q < 4; q++) {
+                            float4 b;
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(sPar + (3 * MAX_N + c0 + 4 * q) * 4));
+                            v[4 * q] = fmaxf(v[4 * q] + b.x, 0.f), v[4 * q + 1] = fmaxf(v[4 * q + 1] + b.y, 0.f);
+                            v[4 * q + 2] = fmaxf(v[4 * q + 2] + b.z, 0.f), v[4 * q + 3] = fmaxf(v[4 * q + 3] + b.w, 0.f);
+                        }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 16; i++) v[i] = 0.f;
