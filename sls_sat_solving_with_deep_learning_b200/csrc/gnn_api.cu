@@ -326,10 +326,9 @@ int forward_device(sls_gnn_model* m, int64_t N, int64_t E, const float* d_nodes,
         de = H;
         // node update sees [nodes | segment_sum(new edges, senders) | segment_sum(new edges, receivers)]
         if (N) {
-            const unsigned blocks = (unsigned)((N * 32 + 255) / 256);
-            segment_sum_kernel<<<blocks, 256>>>(e, d_sptr, d_sids, sent, N, H);
-            segment_sum_kernel<<<blocks, 256>>>(e, d_rptr, d_rids, recv, N, H);
-            m->launches += 2;
+            const unsigned blocks = (unsigned)((2 * N * 32 + 255) / 256);
+            segment_sum_kernel<<<blocks, 256>>>(e, d_sptr, d_sids, sent, d_rptr, d_rids, recv, N, H);
+            m->launches += 1;
         }
         rc = launch_mlp(m, m->node_mlp[t], h, nullptr, dn, sent, nullptr, H, recv, nullptr, H, N, h2);
         if (rc) return rc;
