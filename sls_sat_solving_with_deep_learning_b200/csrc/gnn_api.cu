@@ -42,7 +42,8 @@ float round_tf32_host(float x)
 }
 
 struct DevMlp {
-    int k1 = 0, h1 = 0, h2 = 0, k1_slabs = 0, k2_slabs = 0, n1 = 0, n2 = 0;
+    int k1 = 0, h1 = 0, h2 = 0, k1_slabs = 0, k2_slabs = 0, n1 = 0, n2 = 0, k1_slabs_bf = 0, k2_slabs_bf = 0;
+    uint16_t *w1_b0 = nullptr, *w1_b1 = nullptr, *w2_b0 = nullptr, *w2_b1 = nullptr;  // two bf16 pieces, 64 k-values per slab row
     float *w1_hi = nullptr, *w1_lo = nullptr, *b1 = nullptr, *w2_hi = nullptr, *w2_lo = nullptr, *b2 = nullptr, *ln_scale = nullptr,
           *ln_offset = nullptr;
 };
@@ -52,6 +53,29 @@ struct DevMlp {
         cudaError_t _e = (expr);                                                                             \
         if (_e != cudaSuccess) return sls_set_error_internal(SLS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
+
+// round to nearest even to bfloat16 (the top 16 bits of an fp32)
+uint16_t bf16_bits_host(float x)
+{
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) != 0x7f800000u) u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+float bf16_value_host(uint16_t b)
+{
+    const uint32_t u = (uint32_t)b << 16;
+    float x;
+    std::memcpy(&x, &u, 4);
+    return x;
+}
+
+int upload_u16(const std::vector<uint16_t>& h, uint16_t** d)
+{
+    G_TRY(dmalloc(d, std::max<size_t>(h.size(), 1) * sizeof(uint16_t)));
+    if (!h.empty()) G_TRY(cudaMemcpy(*d, h.data(), h.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    return SLS_OK;
+}
 
 int upload(const std::vector<float>& h, float** d)
 {
@@ -108,6 +132,20 @@ int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& 
         const int u = k_in_slab >> 2, e = k_in_slab & 3;
         return (size_t)s * n_pad * SLAB_K + (size_t)(n >> 3) * 256 + (size_t)(n & 7) * 32 + (size_t)((u ^ (n & 7)) << 2) + e;
     };
+    // the same weights as two bf16 pieces b0 = bf16(w), b1 = bf16(w - b0): 64 k-values per 128-byte row, 16-byte unit = 8 values
+    constexpr int SLAB_KB = 64;
+    out.k1_slabs_bf = (k1 + SLAB_KB - 1) / SLAB_KB;
+    out.k2_slabs_bf = (h1 + SLAB_KB - 1) / SLAB_KB;
+    auto img_index_bf = [](int n_pad, int s, int n, int k_in_slab) {
+        const int u = k_in_slab >> 3, e = k_in_slab & 7;
+        return (size_t)s * n_pad * SLAB_KB + (size_t)(n >> 3) * 512 + (size_t)(n & 7) * 64 + (size_t)((u ^ (n & 7)) << 3) + e;
+    };
+    std::vector<uint16_t> w1b0((size_t)out.n1 * out.k1_slabs_bf * SLAB_KB, 0), w1b1(w1b0.size(), 0);
+    std::vector<uint16_t> w2b0((size_t)out.n2 * out.k2_slabs_bf * SLAB_KB, 0), w2b1(w2b0.size(), 0);
+    auto put_bf = [&](std::vector<uint16_t>& p0, std::vector<uint16_t>& p1, size_t ix, float w) {
+        p0[ix] = bf16_bits_host(w);
+        p1[ix] = bf16_bits_host(w - bf16_value_host(p0[ix]));
+    };
     std::vector<float> w1h((size_t)out.n1 * k1p, 0.f), w1l(w1h.size(), 0.f), b1(out.n1, 0.f);
     std::vector<float> w2h((size_t)out.n2 * k2p, 0.f), w2l(w2h.size(), 0.f), b2(out.n2, 0.f);
     for (int k = 0; k < k1; k++)
@@ -116,6 +154,7 @@ int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& 
             const size_t ix = img_index(out.n1, k / SLAB_K, n, k % SLAB_K);
             w1h[ix] = hi;
             w1l[ix] = round_tf32_host(w - hi);
+            put_bf(w1b0, w1b1, img_index_bf(out.n1, k / SLAB_KB, n, k % SLAB_KB), w);
         }
     p += (size_t)k1 * h1;
     std::copy(p, p + h1, b1.begin());
@@ -126,6 +165,7 @@ int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& 
             const size_t ix = img_index(out.n2, k / SLAB_K, n, k % SLAB_K);
             w2h[ix] = hi;
             w2l[ix] = round_tf32_host(w - hi);
+            put_bf(w2b0, w2b1, img_index_bf(out.n2, k / SLAB_KB, n, k % SLAB_KB), w);
         }
     p += (size_t)h1 * h2;
     std::copy(p, p + h2, b2.begin());
@@ -138,6 +178,10 @@ int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& 
         (rc = upload(of, &out.ln_offset)))
         return rc;
     for (float* q : {out.w1_hi, out.w1_lo, out.b1, out.w2_hi, out.w2_lo, out.b2, out.ln_scale, out.ln_offset}) m->allocs.push_back(q);
+    if ((rc = upload_u16(w1b0, &out.w1_b0)) || (rc = upload_u16(w1b1, &out.w1_b1)) || (rc = upload_u16(w2b0, &out.w2_b0)) ||
+        (rc = upload_u16(w2b1, &out.w2_b1)))
+        return rc;
+    for (uint16_t* q : {out.w1_b0, out.w1_b1, out.w2_b0, out.w2_b1}) m->allocs.push_back(q);
     return SLS_OK;
 }
 
@@ -203,7 +247,8 @@ extern "C" int sls_gnn_model_create(const float* blob, uint64_t blob_len, int32_
     cudaError_t e = cudaFuncSetAttribute(mlp_ln_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
     if (e != cudaSuccess) {
         sls_gnn_model_free(m);
@@ -216,6 +261,7 @@ extern "C" int sls_gnn_model_create(const float* blob, uint64_t blob_len, int32_
 namespace {
 
 constexpr int GNN_DEFAULT_CLUSTER = 1;
+constexpr bool GNN_DEFAULT_BF16X2 = true;
 
 struct DevBuf {
     void* p = nullptr;
@@ -237,6 +283,8 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
     a.w1_hi = w.w1_hi, a.w1_lo = w.w1_lo, a.b1 = w.b1, a.w2_hi = w.w2_hi, a.w2_lo = w.w2_lo, a.b2 = w.b2;
     a.ln_scale = w.ln_scale, a.ln_offset = w.ln_offset;
     a.out = out;
+    a.w1_b0 = w.w1_b0, a.w1_b1 = w.w1_b1, a.w2_b0 = w.w2_b0, a.w2_b1 = w.w2_b1;
+    a.k1_slabs_bf = w.k1_slabs_bf, a.k2_slabs_bf = w.k2_slabs_bf;
     const unsigned blocks = (unsigned)((rows + TILE_M - 1) / TILE_M);
     // persistent three-role kernel, one CTA per SM; SLS_B200_GNN_ONE_TILE=1 selects the one-tile-per-CTA kernel
     static const bool one_tile = [] { const char* f = std::getenv("SLS_B200_GNN_ONE_TILE"); return f && f[0] == '1'; }();
@@ -254,7 +302,13 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            mlp_ln_persistent_ts_kernel<<<std::min<unsigned>(blocks, (unsigned)sms), MLPP_THREADS, TS_SMEM_BYTES>>>(a);
+            // SLS_B200_GNN_PRECISION = bf16x2 (default: two bf16 pieces per operand on kind::f16) | tf32x3
+            const char* fp = std::getenv("SLS_B200_GNN_PRECISION");
+            const bool tf32x3 = fp ? std::strcmp(fp, "tf32x3") == 0 : !GNN_DEFAULT_BF16X2;
+            if (tf32x3)
+                mlp_ln_persistent_ts_kernel<false><<<std::min<unsigned>(blocks, (unsigned)sms), MLPP_THREADS, TS_SMEM_BYTES>>>(a);
+            else
+                mlp_ln_persistent_ts_kernel<true><<<std::min<unsigned>(blocks, (unsigned)sms), MLPP_THREADS, TS_SMEM_BYTES>>>(a);
         } else if (cluster == 1) {
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);

@@ -72,6 +72,13 @@ struct MlpArgs {
     const float* ln_scale;   // [h2]
     const float* ln_offset;  // [h2]
     float* out;          // [rows][h2]
+    // the same weights as two bf16 pieces (w = b0 + b1), slab images of 64 k-values per 128-byte row, for the kind::f16 kernel
+    const uint16_t* w1_b0;
+    const uint16_t* w1_b1;
+    const uint16_t* w2_b0;
+    const uint16_t* w2_b1;
+    int32_t k1_slabs_bf;  // ceil((d0+d1+d2)/64)
+    int32_t k2_slabs_bf;  // ceil(h1/64)
 };
 
 // ---- small PTX helpers -----------------------------------------------------------------------
@@ -774,6 +781,19 @@ static constexpr int TS_A_COL = 416;     // first A-stage column; 32 columns per
 static constexpr int TS_ACC2_COL = 208;
 static constexpr int TS_SMEM_BYTES = TS_B_STAGES * B_STAGE_BYTES + BAR_BYTES + PAR_BYTES + MAX_N * 4 + 1024;  // + b1
 
+// instruction descriptor for kind::f16 with bf16 operands: D = f32, A = B = bf16 (format 1), both K-major
+__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{ .reg .pred p;\n"
+        "  setp.ne.b32 p, %4, 0;\n"
+        "  tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p; }\n"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
@@ -795,8 +815,17 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r)
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// BF = true: the products are formed from two bf16 pieces per operand on kind::f16 (x = a0 + a1, w = b0 + b1; a0*b0 + a1*b0 +
+// a0*b1, fp32 accumulation) instead of 3xTF32.  A 128-byte weight row then holds 64 k-values and a unit 32 (two per TMEM
+// column), so every MMA covers twice the k-range in the same time: half the MMAs, weight bytes and barrier hand-overs per
+// tile.  16 mantissa bits per operand: max |dp| vs fp64 3.9e-5 in emulation (tools/precision_split_study.py; single-pass
+// TF32 1.75e-3, 3xTF32 1.9e-6), against the 1e-3 contract.
+template <bool BF>
 __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(const MlpArgs P)
 {
+    constexpr int NV = BF ? 32 : 16;        // k-values per thread and unit
+    constexpr int NQ = NV / 4;              // float4 per thread and slab
+    constexpr int SLABK = 2 * NV;           // k-values per weight slab (one 128-byte row)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sBst = base;
@@ -843,7 +872,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + (sTmem - base));
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t n1s = (uint32_t)P.k1_slabs, n2s = (uint32_t)P.k2_slabs, S = n1s + n2s;
+    const uint32_t n1s = (uint32_t)(BF ? P.k1_slabs_bf : P.k1_slabs), n2s = (uint32_t)(BF ? P.k2_slabs_bf : P.k2_slabs), S = n1s + n2s;
     auto wait_unit = [&](uint32_t U) { mbar_wait(sDone + 8 * (U % DONE_BARS), (U / DONE_BARS) & 1u); };
 
     if (producer) {
@@ -869,8 +898,8 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
         auto load_a1 = [&](int s, float4* x) {
             if (wide) {
 #pragma unroll
-                for (int u = 0; u < 4; u += 2) {
-                    const int col = s * SLAB_K + ((int)grp * 4 + u) * 4;
+                for (int u = 0; u < NQ; u += 2) {
+                    const int col = s * SLABK + (int)grp * NV + 4 * u;
                     x[u] = x[u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (col < kA) {
                         const float* p = col < P.d[0] ? rp[0] + col : col < P.d[0] + P.d[1] ? rp[1] + (col - P.d[0]) : rp[2] + (col - P.d[0] - P.d[1]);
@@ -883,8 +912,8 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                 return;
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int col = s * SLAB_K + ((int)grp * 4 + u) * 4;
+            for (int u = 0; u < NQ; u++) {
+                const int col = s * SLABK + (int)grp * NV + 4 * u;
                 x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (col < kA) {
                     const float* p = col < P.d[0] ? rp[0] + col : col < P.d[0] + P.d[1] ? rp[1] + (col - P.d[0]) : rp[2] + (col - P.d[0] - P.d[1]);
@@ -892,59 +921,77 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                 }
             }
         };
-        // v[16] -> 16 hi | 16 lo columns of A stage U % 3
+        // v[NV] -> the 32 columns of A stage U % 3: 16 hi | 16 lo (tf32), or 16 columns of a0 pairs | 16 of a1 pairs (bf16: the
+        // lower k in the low half of a column; a0 rounded half up, the residual truncated)
         auto put_unit = [&](uint32_t U, const float* v) {
             uint32_t r[32];
+            if constexpr (BF) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const float hi = round_tf32(v[i]);
-                r[i] = __float_as_uint(hi);
-                r[16 + i] = __float_as_uint(residual_tf32(v[i], hi));
+                for (int i = 0; i < 16; i++) {
+                    const uint32_t ue = __float_as_uint(v[2 * i]) + 0x8000u, uo = __float_as_uint(v[2 * i + 1]) + 0x8000u;
+                    r[i] = __byte_perm(ue, uo, 0x7632);
+                    const float re = v[2 * i] - __uint_as_float(ue & 0xffff0000u), ro = v[2 * i + 1] - __uint_as_float(uo & 0xffff0000u);
+                    r[16 + i] = __byte_perm(__float_as_uint(re), __float_as_uint(ro), 0x7632);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float hi = round_tf32(v[i]);
+                    r[i] = __float_as_uint(hi);
+                    r[16 + i] = __float_as_uint(residual_tf32(v[i], hi));
+                }
             }
             tmem_st32(tmem + lane_base + (uint32_t)(TS_A_COL + 32 * (U % TS_A_STAGES)), r);
         };
-        float4 xa0[4], xa1[4];
+        // tf32: even slabs of a tile in xa0, odd ones in xa1 (two slabs of lead); bf16: a slab lasts twice as long and holds
+        // twice the registers, one buffer and one slab of lead
+        constexpr int LEAD = BF ? 1 : 2;
+        float4 xa0[NQ], xa1[BF ? 1 : NQ];
         uint32_t J = 0;
         if (my_tiles > 0) {
             set_rows(blockIdx.x);
             load_a1(0, xa0);
-            load_a1(1, xa1);
+            if constexpr (!BF) load_a1(1, xa1);
         }
         for (uint32_t it = 0; it < my_tiles; it++) {
             const int next_tile = (int)(blockIdx.x + (it + 1) * gridDim.x);
             auto slab = [&](uint32_t j, float4* xa) {
                 const uint32_t U = 2 * J + grp;
                 if (U >= (uint32_t)TS_A_STAGES) wait_unit(U - TS_A_STAGES);
-                float v[16];
+                float v[NV];
                 if (j < n1s) {
 #pragma unroll
-                    for (int u = 0; u < 4; u++) v[4 * u] = xa[u].x, v[4 * u + 1] = xa[u].y, v[4 * u + 2] = xa[u].z, v[4 * u + 3] = xa[u].w;
+                    for (int u = 0; u < NQ; u++) v[4 * u] = xa[u].x, v[4 * u + 1] = xa[u].y, v[4 * u + 2] = xa[u].z, v[4 * u + 3] = xa[u].w;
                     tc_fence_after();
                     put_unit(U, v);
-                    if (j + 2 < n1s) load_a1((int)j + 2, xa);
+                    if (j + LEAD < n1s) load_a1((int)j + LEAD, xa);
                 } else {
                     if (j == n1s) {  // GEMM2 reads GEMM1's accumulator: every GEMM1 MMA must have completed
                         wait_unit(2 * J - 1);
                         if (it + 1 < my_tiles) {
                             set_rows(next_tile);
                             load_a1(0, xa0);
-                            load_a1(1, xa1);
+                            if constexpr (!BF) load_a1(1, xa1);
                         }
                     }
                     tc_fence_after();
-                    const int c0 = (int)(j - n1s) * SLAB_K + (int)grp * 16;
-                    if (c0 < P.n1) {
-                        tmem_ld16(tmem + lane_base + (uint32_t)c0, v);
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            float4 b;
-                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(sPar + (3 * MAX_N + c0 + 4 * q) * 4));
-                            v[4 * q] = fmaxf(v[4 * q] + b.x, 0.f), v[4 * q + 1] = fmaxf(v[4 * q + 1] + b.y, 0.f);
-                            v[4 * q + 2] = fmaxf(v[4 * q + 2] + b.z, 0.f), v[4 * q + 3] = fmaxf(v[4 * q + 3] + b.w, 0.f);
+                    for (int half = 0; half < NV / 16; half++) {
+                        const int c0 = (int)(j - n1s) * SLABK + (int)grp * NV + 16 * half;
+                        float* vh = v + 16 * half;
+                        if (c0 < P.n1) {
+                            tmem_ld16(tmem + lane_base + (uint32_t)c0, vh);
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                float4 b;
+                                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(sPar + (3 * MAX_N + c0 + 4 * q) * 4));
+                                vh[4 * q] = fmaxf(vh[4 * q] + b.x, 0.f), vh[4 * q + 1] = fmaxf(vh[4 * q + 1] + b.y, 0.f);
+                                vh[4 * q + 2] = fmaxf(vh[4 * q + 2] + b.z, 0.f), vh[4 * q + 3] = fmaxf(vh[4 * q + 3] + b.w, 0.f);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) vh[i] = 0.f;
                         }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; i++) v[i] = 0.f;
                     }
                     put_unit(U, v);
                 }
@@ -953,9 +1000,13 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                 if ((tid & 31) == 0) mbar_arrive(sArdy + 8 * (U % TS_A_STAGES));
                 J++;
             };
-            for (uint32_t j = 0; j < S; j += 2) {
-                slab(j, xa0);
-                if (j + 1 < S) slab(j + 1, xa1);
+            if constexpr (BF) {
+                for (uint32_t j = 0; j < S; j++) slab(j, xa0);
+            } else {
+                for (uint32_t j = 0; j < S; j += 2) {
+                    slab(j, xa0);
+                    if (j + 1 < S) slab(j + 1, xa1);
+                }
             }
         }
     } else if (warp_u == MLPP_PRODUCERS / 32) {
@@ -963,13 +1014,13 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
         const uint32_t total = my_tiles * S;
         constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version 1 | SWIZZLE_128B
         auto desc = [&](uint32_t addr) -> uint64_t { return (uint64_t)DESC_HI << 32 | (((addr >> 4) & 0x3fffu) | (1u << 16)); };
-        const uint32_t idesc1 = idesc_tf32(TILE_M, P.n1), idesc2 = idesc_tf32(TILE_M, P.n2);
+        const uint32_t idesc1 = BF ? idesc_bf16(TILE_M, P.n1) : idesc_tf32(TILE_M, P.n1), idesc2 = BF ? idesc_bf16(TILE_M, P.n2) : idesc_tf32(TILE_M, P.n2);
         auto issue_b = [&](uint32_t J, uint32_t j) {  // j = J % S
             const bool g1 = j < n1s;
             const int n_pad = g1 ? P.n1 : P.n2;
-            const uint32_t s = g1 ? j : j - n1s, bbytes = (uint32_t)n_pad * 128u;
-            const float* hi = (g1 ? P.w1_hi : P.w2_hi) + (size_t)s * n_pad * SLAB_K;
-            const float* lo = (g1 ? P.w1_lo : P.w2_lo) + (size_t)s * n_pad * SLAB_K;
+            const uint32_t s = g1 ? j : j - n1s, bbytes = (uint32_t)n_pad * 128u;  // one 128-byte row per output column, either format
+            const uint8_t* hi = reinterpret_cast<const uint8_t*>(BF ? (const void*)(g1 ? P.w1_b0 : P.w2_b0) : (const void*)(g1 ? P.w1_hi : P.w2_hi)) + (size_t)s * bbytes;
+            const uint8_t* lo = reinterpret_cast<const uint8_t*>(BF ? (const void*)(g1 ? P.w1_b1 : P.w2_b1) : (const void*)(g1 ? P.w1_lo : P.w2_lo)) + (size_t)s * bbytes;
             const uint32_t bs = sBst + (J % TS_B_STAGES) * B_STAGE_BYTES, bar = sFull + 8 * (J % TS_B_STAGES);
             if (J >= (uint32_t)TS_B_STAGES) wait_unit(2 * (J - TS_B_STAGES) + 1);  // both units of the stage's last slab are done
             if (leader) {
@@ -1006,9 +1057,15 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
 #pragma unroll
                     for (uint32_t q = 0; q < 2; q++) {  // k-step 2h + q of the slab: 8 tf32 = 8 columns of A, 32 bytes of a B row
                         const uint32_t kk = 2 * h + q;
-                        umma_tf32_ts(acc, a + 8 * q, dBh + 2 * kk, idesc, (j != first || kk != 0) ? 1u : 0u);
-                        umma_tf32_ts(acc, a + 16 + 8 * q, dBh + 2 * kk, idesc, 1u);
-                        umma_tf32_ts(acc, a + 8 * q, dBl + 2 * kk, idesc, 1u);
+                        if constexpr (BF) {
+                            umma_bf16_ts(acc, a + 8 * q, dBh + 2 * kk, idesc, (j != first || kk != 0) ? 1u : 0u);
+                            umma_bf16_ts(acc, a + 16 + 8 * q, dBh + 2 * kk, idesc, 1u);
+                            umma_bf16_ts(acc, a + 8 * q, dBl + 2 * kk, idesc, 1u);
+                        } else {
+                            umma_tf32_ts(acc, a + 8 * q, dBh + 2 * kk, idesc, (j != first || kk != 0) ? 1u : 0u);
+                            umma_tf32_ts(acc, a + 16 + 8 * q, dBh + 2 * kk, idesc, 1u);
+                            umma_tf32_ts(acc, a + 8 * q, dBl + 2 * kk, idesc, 1u);
+                        }
                     }
                     umma_commit(sDone + 8 * (U % DONE_BARS));
                     if (h == 1 && j == S - 1) umma_commit(sAccFull);

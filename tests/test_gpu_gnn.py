@@ -147,12 +147,32 @@ def test_a_operand_in_tensor_memory_equals_shared_memory_staging(monkeypatch):
         insts.append(eng.Instance.from_clauses(n, random_ksat(n, m, 3, seed=500 + i)))
     params = go.init_params(seed=23, bias_scale=0.1)
     net = gnn.InteractionNetworkLCG(params)
+    monkeypatch.setenv("SLS_B200_GNN_PRECISION", "tf32x3")  # the shared-memory kernels only exist in 3xTF32
     monkeypatch.setenv("SLS_B200_GNN_A_TMEM", "1")
     p1, d1 = net.probabilities(insts, return_decoded=True)
     monkeypatch.setenv("SLS_B200_GNN_A_TMEM", "0")
     p0, d0 = net.probabilities(insts, return_decoded=True)
     assert np.array_equal(d1, d0)
     assert all(np.array_equal(a, b) for a, b in zip(p1, p0))
+
+
+def test_bf16_pieces_and_3xtf32_agree_within_the_contract(monkeypatch):
+    # default: two bf16 pieces per operand on kind::f16 (a0*b0 + a1*b0 + a0*b1, 16 mantissa bits per operand); tf32x3: the
+    # compensated TF32 product.  Both against the fp64 restatement; emulation (tools/precision_split_study.py) predicts
+    # 3.9e-5 and 1.9e-6
+    n, m = 500, 2100
+    clauses = random_ksat(n, m, 3, seed=77)
+    inst = eng.Instance.from_clauses(n, clauses)
+    params = go.init_params(seed=42)
+    net = gnn.InteractionNetworkLCG(params)
+    ref = go.model_probabilities(go.forward(params, go.lcg_graph(n, clauses), dtype=np.float64), n)
+    monkeypatch.setenv("SLS_B200_GNN_PRECISION", "bf16x2")
+    p_bf = net.probabilities([inst])[0]
+    monkeypatch.setenv("SLS_B200_GNN_PRECISION", "tf32x3")
+    p_tf = net.probabilities([inst])[0]
+    assert np.abs(p_tf - ref).max() < 2e-5
+    assert np.abs(p_bf - ref).max() < 2e-4   # five times the emulated figure, five times under the contract
+    assert not np.array_equal(p_bf, p_tf)    # the switch does select two different kernels
 
 
 def test_graph_edge_cases():
