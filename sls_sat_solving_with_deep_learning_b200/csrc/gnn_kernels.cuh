@@ -878,13 +878,19 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
     if (producer) {
         const int kA = P.d[0] + P.d[1] + P.d[2];
         const float* rp[3] = {nullptr, nullptr, nullptr};
-        auto set_rows = [&](int tile) {
-            const int my_row = min(tile * TILE_M + prow, P.rows - 1);
+        // Row indices are read one tile ahead of the rows they address (nidx): at the GEMM1 -> GEMM2 hand-over the pointers of
+        // the next tile are formed from registers, not from a fresh load on the drain's critical path.
+        int nidx[3] = {0, 0, 0};
+        auto fetch_idx = [&](int tile) {
+            const int my_row = min(tile * TILE_M + prow, P.rows - 1);  // rows past the end re-read the last row; never stored
+#pragma unroll
+            for (int j = 0; j < 3; j++) nidx[j] = (P.d[j] > 0 && P.idx[j]) ? __ldg(P.idx[j] + my_row) : my_row;
+        };
+        auto set_rows = [&]() {  // pointers of the tile whose indices are in nidx
 #pragma unroll
             for (int j = 0; j < 3; j++)
                 if (P.d[j] > 0) {
-                    const int r = P.idx[j] ? __ldg(P.idx[j] + my_row) : my_row;
-                    rp[j] = P.src[j] + (size_t)r * P.d[j];
+                    rp[j] = P.src[j] + (size_t)nidx[j] * P.d[j];
                     // The row is gathered slab by slab over the whole tile; ask L2 for all of it now (the two threads of a
                     // row take alternate 128-byte lines).  Gathered rows come from HBM (the feature arrays are several
                     // times the L2) and a register prefetch two slabs ahead did not cover that latency: measured 3.1 of
@@ -949,9 +955,11 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
         float4 xa0[NQ], xa1[BF ? 1 : NQ];
         uint32_t J = 0;
         if (my_tiles > 0) {
-            set_rows(blockIdx.x);
+            fetch_idx(blockIdx.x);
+            set_rows();
             load_a1(0, xa0);
             if constexpr (!BF) load_a1(1, xa1);
+            fetch_idx((int)(blockIdx.x + gridDim.x));
         }
         for (uint32_t it = 0; it < my_tiles; it++) {
             const int next_tile = (int)(blockIdx.x + (it + 1) * gridDim.x);
@@ -969,9 +977,10 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                     if (j == n1s) {  // GEMM2 reads GEMM1's accumulator: every GEMM1 MMA must have completed
                         wait_unit(2 * J - 1);
                         if (it + 1 < my_tiles) {
-                            set_rows(next_tile);
+                            set_rows();
                             load_a1(0, xa0);
                             if constexpr (!BF) load_a1(1, xa1);
+                            fetch_idx(next_tile + (int)gridDim.x);
                         }
                     }
                     tc_fence_after();
