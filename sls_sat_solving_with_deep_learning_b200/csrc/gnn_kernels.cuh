@@ -818,7 +818,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r)
 // BF = true: the products are formed from two bf16 pieces per operand on kind::f16 (x = a0 + a1, w = b0 + b1; a0*b0 + a1*b0 +
 // a0*b1, fp32 accumulation) instead of 3xTF32.  A 128-byte weight row then holds 64 k-values and a unit 32 (two per TMEM
 // column), so every MMA covers twice the k-range in the same time: half the MMAs, weight bytes and barrier hand-overs per
-// tile.  16 mantissa bits per operand: max |dp| vs fp64 3.9e-5 in emulation (tools/precision_split_study.py; single-pass
+// tile.  16 mantissa bits per operand: max |dp| vs fp64 3.4e-5 in emulation, 2.7e-5 measured (tools/precision_split_study.py; single-pass
 // TF32 1.75e-3, 3xTF32 1.9e-6), against the 1e-3 contract.
 template <bool BF>
 __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(const MlpArgs P)
@@ -928,16 +928,18 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
             }
         };
         // v[NV] -> the 32 columns of A stage U % 3: 16 hi | 16 lo (tf32), or 16 columns of a0 pairs | 16 of a1 pairs (bf16: the
-        // lower k in the low half of a column; a0 rounded half up, the residual truncated)
+        // lower k in the low half of a column; both pieces rounded to nearest even)
         auto put_unit = [&](uint32_t U, const float* v) {
             uint32_t r[32];
             if constexpr (BF) {
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const uint32_t ue = __float_as_uint(v[2 * i]) + 0x8000u, uo = __float_as_uint(v[2 * i + 1]) + 0x8000u;
-                    r[i] = __byte_perm(ue, uo, 0x7632);
-                    const float re = v[2 * i] - __uint_as_float(ue & 0xffff0000u), ro = v[2 * i + 1] - __uint_as_float(uo & 0xffff0000u);
-                    r[16 + i] = __byte_perm(__float_as_uint(re), __float_as_uint(ro), 0x7632);
+                for (int i = 0; i < 16; i++) {  // one packing conversion per pair and piece (F2FP.BF16.PACK_AB)
+                    uint32_t a0, a1;
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a0) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+                    const float re = v[2 * i] - __uint_as_float(a0 << 16), ro = v[2 * i + 1] - __uint_as_float(a0 & 0xffff0000u);
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a1) : "f"(ro), "f"(re));
+                    r[i] = a0;
+                    r[16 + i] = a1;
                 }
             } else {
 #pragma unroll

@@ -23,7 +23,7 @@ def bf16(x):
     return ((u + np.uint32(0x7FFF) + ((u >> np.uint32(16)) & np.uint32(1))) & np.uint32(0xFFFF0000)).view(np.float32)
 
 
-def bf16_half_up(x):  # what the kernel's producers do: add half an ulp of the magnitude, truncate
+def bf16_half_up(x):  # a cheaper split that was tried first: add half an ulp of the magnitude, truncate
     u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
     return ((u + np.uint32(0x8000)) & np.uint32(0xFFFF0000)).view(np.float32)
 
@@ -53,7 +53,7 @@ MODES = {
     "3xTF32": (tf32, 2, [(0, 0), (1, 0), (0, 1)]),
     "bf16 x1": (bf16, 1, [(0, 0)]),
     "bf16 2 pieces, 3 terms": (bf16, 2, [(0, 0), (0, 1), (1, 0)]),
-    "bf16 2 pieces, 3 terms, kernel split of A": ("kernel", 2, [(0, 0), (0, 1), (1, 0)]),
+    "bf16 2 pieces, 3 terms, A: half-up + truncated residual": ("kernel", 2, [(0, 0), (0, 1), (1, 0)]),
     "bf16 2 pieces, 4 terms": (bf16, 2, [(0, 0), (0, 1), (1, 0), (1, 1)]),
     "bf16 3 pieces, 6 terms": (bf16, 3, [(0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (2, 0)]),
 }
@@ -110,4 +110,4 @@ if __name__ == "__main__":
             p = go.model_probabilities(forward_mode(params, g, mode), n)
             worst[k] = max(worst[k], float(np.abs(p - ref).max()))
     for k, v in worst.items():
-        print(f"{k:44s} max |dp| vs fp64 = {v:.2e}")
+        print(f"{k:56s} max |dp| vs fp64 = {v:.2e}")
