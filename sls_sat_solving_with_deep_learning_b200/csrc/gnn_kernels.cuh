@@ -929,8 +929,9 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
         };
         // v[NV] -> the 32 columns of A stage U % 3: 16 hi | 16 lo (tf32), or 16 columns of a0 pairs | 16 of a1 pairs (bf16: the
         // lower k in the low half of a column; both pieces rounded to nearest even)
-        auto put_unit = [&](uint32_t U, const float* v) {
-            uint32_t r[32];
+        // The split is register work and runs BEFORE the thread waits for its A stage; once the stage is free only the TMEM
+        // store, its wait and the barrier arrival are left on the stage's turn-around path.
+        auto pack_unit = [&](const float* v, uint32_t* r) {
             if constexpr (BF) {
 #pragma unroll
                 for (int i = 0; i < 16; i++) {  // one packing conversion per pair and piece (F2FP.BF16.PACK_AB)
@@ -949,6 +950,10 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                     r[16 + i] = __float_as_uint(residual_tf32(v[i], hi));
                 }
             }
+        };
+        auto store_unit = [&](uint32_t U, const uint32_t* r) {
+            if (U >= (uint32_t)TS_A_STAGES) wait_unit(U - TS_A_STAGES);
+            tc_fence_after();
             tmem_st32(tmem + lane_base + (uint32_t)(TS_A_COL + 32 * (U % TS_A_STAGES)), r);
         };
         // tf32: even slabs of a tile in xa0, odd ones in xa1 (two slabs of lead); bf16: a slab lasts twice as long and holds
@@ -967,13 +972,12 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
             const int next_tile = (int)(blockIdx.x + (it + 1) * gridDim.x);
             auto slab = [&](uint32_t j, float4* xa) {
                 const uint32_t U = 2 * J + grp;
-                if (U >= (uint32_t)TS_A_STAGES) wait_unit(U - TS_A_STAGES);
                 float v[NV];
+                uint32_t r[32];
                 if (j < n1s) {
 #pragma unroll
                     for (int u = 0; u < NQ; u++) v[4 * u] = xa[u].x, v[4 * u + 1] = xa[u].y, v[4 * u + 2] = xa[u].z, v[4 * u + 3] = xa[u].w;
-                    tc_fence_after();
-                    put_unit(U, v);
+                    pack_unit(v, r);
                     if (j + LEAD < n1s) load_a1((int)j + LEAD, xa);
                 } else {
                     if (j == n1s) {  // GEMM2 reads GEMM1's accumulator: every GEMM1 MMA must have completed
@@ -1004,8 +1008,9 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                             for (int i = 0; i < 16; i++) vh[i] = 0.f;
                         }
                     }
-                    put_unit(U, v);
+                    pack_unit(v, r);
                 }
+                store_unit(U, r);
                 tc_fence_before();
                 __syncwarp();
                 if ((tid & 31) == 0) mbar_arrive(sArdy + 8 * (U % TS_A_STAGES));
