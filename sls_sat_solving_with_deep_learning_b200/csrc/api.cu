@@ -49,6 +49,16 @@ int sls_set_error_internal(int code, const std::string& msg) { return set_error(
     } while (0)
 
 // ------------------------------------------------------------------ device
+// The evaluation driver keeps up to 32 small, latency-bound launches in flight on their own streams.  The driver maps
+// streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8) and launches that share a queue serialise:
+// measured 0.319 s per wave of 32 instances with 8 queues, 0.111 s with 32.  The variable is read when the context is
+// created, so it is set when the library is loaded -- unless the user has set it.
+namespace {
+struct ConnectionDefault {
+    ConnectionDefault() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", /*overwrite=*/0); }
+} g_connection_default;
+}  // namespace
+
 extern "C" int sls_device_count(int* count)
 {
     int c = 0;
