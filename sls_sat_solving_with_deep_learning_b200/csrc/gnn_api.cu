@@ -247,8 +247,9 @@ extern "C" int sls_gnn_model_create(const float* blob, uint64_t blob_len, int32_
     cudaError_t e = cudaFuncSetAttribute(mlp_ln_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
     if (e != cudaSuccess) {
         sls_gnn_model_free(m);
@@ -295,44 +296,47 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
         const char* f = std::getenv("SLS_B200_GNN_CLUSTER");  // read per launch: the tests switch it
         const int c = f ? std::atoi(f) : GNN_DEFAULT_CLUSTER;
         const int cluster = c == 2 || c == 4 ? c : 1;
-        // SLS_B200_GNN_A_TMEM=0 selects the kernel that stages the A operand in shared memory (and the cluster variants)
+        // SLS_B200_GNN_A_TMEM=0 selects the kernel that stages the A operand in shared memory (3xTF32 only)
         const char* ft = std::getenv("SLS_B200_GNN_A_TMEM");
-        const bool a_tmem = ft ? ft[0] != '0' : (f == nullptr);
+        const bool a_tmem = ft ? ft[0] != '0' : true;
+        // SLS_B200_GNN_PRECISION = bf16x2 (default: two bf16 pieces per operand on kind::f16) | tf32x3
+        const char* fp = std::getenv("SLS_B200_GNN_PRECISION");
+        const bool tf32x3 = fp ? std::strcmp(fp, "tf32x3") == 0 : !GNN_DEFAULT_BF16X2;
+        void (*kern)(const MlpArgs) = nullptr;
+        int cl = 1;
+        size_t smem = TS_SMEM_BYTES;
         if (a_tmem) {
-            int dev = 0, sms = 148;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            // SLS_B200_GNN_PRECISION = bf16x2 (default: two bf16 pieces per operand on kind::f16) | tf32x3
-            const char* fp = std::getenv("SLS_B200_GNN_PRECISION");
-            const bool tf32x3 = fp ? std::strcmp(fp, "tf32x3") == 0 : !GNN_DEFAULT_BF16X2;
-            if (tf32x3)
-                mlp_ln_persistent_ts_kernel<false><<<std::min<unsigned>(blocks, (unsigned)sms), MLPP_THREADS, TS_SMEM_BYTES>>>(a);
-            else
-                mlp_ln_persistent_ts_kernel<true><<<std::min<unsigned>(blocks, (unsigned)sms), MLPP_THREADS, TS_SMEM_BYTES>>>(a);
-        } else if (cluster == 1) {
-            int dev = 0, sms = 148;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            mlp_ln_persistent_kernel<1><<<std::min<unsigned>(blocks, (unsigned)sms), MLPP_THREADS, MLP_SMEM_BYTES>>>(a);
+            cl = (!tf32x3 && cluster == 2) ? 2 : 1;
+            kern = tf32x3 ? mlp_ln_persistent_ts_kernel<false, 1> : cl == 2 ? mlp_ln_persistent_ts_kernel<true, 2> : mlp_ln_persistent_ts_kernel<true, 1>;
         } else {
-            void (*kern)(const MlpArgs) = cluster == 2 ? mlp_ln_persistent_kernel<2> : mlp_ln_persistent_kernel<4>;
+            cl = cluster;
+            smem = MLP_SMEM_BYTES;
+            kern = cl == 1 ? mlp_ln_persistent_kernel<1> : cl == 2 ? mlp_ln_persistent_kernel<2> : mlp_ln_persistent_kernel<4>;
+        }
+        if (cl == 1) {
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            kern<<<std::min<unsigned>(blocks, (unsigned)sms), MLPP_THREADS, smem>>>(a);
+        } else {
             cudaLaunchConfig_t cfg{};
             cudaLaunchAttribute attr{};
             attr.id = cudaLaunchAttributeClusterDimension;
-            attr.val.clusterDim.x = (unsigned)cluster, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
-            cfg.blockDim = dim3(MLPP_THREADS), cfg.dynamicSmemBytes = MLP_SMEM_BYTES, cfg.stream = 0;
+            attr.val.clusterDim.x = (unsigned)cl, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+            cfg.blockDim = dim3(MLPP_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = 0;
             cfg.attrs = &attr, cfg.numAttrs = 1;
             // the grid is one wave of co-resident clusters (tiles are assigned statically): ask how many fit
-            static int max_clusters[5] = {0, 0, 0, 0, 0};
-            if (max_clusters[cluster] == 0) {
-                cfg.gridDim = dim3((unsigned)cluster);
+            static int max_clusters[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+            int& cached = max_clusters[a_tmem ? 1 : 0][cl];
+            if (cached == 0) {
+                cfg.gridDim = dim3((unsigned)cl);
                 int n = 0;
                 G_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
                 if (n < 1) return sls_set_error_internal(SLS_ERR_CUDA, "no cluster of the oracle-forward kernel fits on this device");
-                max_clusters[cluster] = n;
+                cached = n;
             }
-            const unsigned want = (blocks + (unsigned)cluster - 1) / (unsigned)cluster;
-            cfg.gridDim = dim3(std::min<unsigned>(want, (unsigned)max_clusters[cluster]) * (unsigned)cluster);
+            const unsigned want = (blocks + (unsigned)cl - 1) / (unsigned)cl;
+            cfg.gridDim = dim3(std::min<unsigned>(want, (unsigned)cached) * (unsigned)cl);
             G_TRY(cudaLaunchKernelEx(&cfg, kern, a));
         }
     }

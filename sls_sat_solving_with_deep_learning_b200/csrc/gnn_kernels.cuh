@@ -820,9 +820,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r)
 // column), so every MMA covers twice the k-range in the same time: half the MMAs, weight bytes and barrier hand-overs per
 // tile.  16 mantissa bits per operand: max |dp| vs fp64 3.4e-5 in emulation, 2.7e-5 measured (tools/precision_split_study.py; single-pass
 // TF32 1.75e-3, 3xTF32 1.9e-6), against the 1e-3 contract.
-template <bool BF>
+// CL = 2: the two CTAs of a cluster run their tiles in lock step; each requests half of every weight slab and the copy engine
+// multicasts it into the same stage of both (as in mlp_ln_persistent_kernel<CL>): the weight stream, 70 % of this kernel's
+// L2 -> SM traffic, is read from L2 once per pair.  A stage may be refilled when both CTAs' MMAs have drained it (sFreeB).
+template <bool BF, int CL>
 __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(const MlpArgs P)
 {
+    static_assert(CL == 1 || CL == 2, "cluster size");
+    constexpr int FREE_BARS = 2 * TS_B_STAGES;
+    constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
     constexpr int NV = BF ? 32 : 16;        // k-values per thread and unit
     constexpr int NQ = NV / 4;              // float4 per thread and slab
     constexpr int SLABK = 2 * NV;           // k-values per weight slab (one 128-byte row)
@@ -834,7 +840,8 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
     const uint32_t sArdy = sDone + 8 * DONE_BARS;
     const uint32_t sAccFull = sArdy + 8 * TS_A_STAGES;
     const uint32_t sAccFree = sAccFull + 8;
-    const uint32_t sTmem = sAccFree + 8;
+    const uint32_t sFreeB = sAccFree + 8;
+    const uint32_t sTmem = sFreeB + 8 * FREE_BARS;
     const uint32_t sPar = sFull + BAR_BYTES;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
 
@@ -846,7 +853,9 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
     const int prow = tid & (TILE_M - 1);   // producers: row of the tile = TMEM lane
     const uint32_t grp = (uint32_t)tid >> 7;  // producers: which 16 of a slab's 32 columns, i.e. which units
     const int ntiles = (P.rows + TILE_M - 1) / TILE_M;
-    const uint32_t my_tiles = (int)blockIdx.x < ntiles ? (uint32_t)((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) : 0u;
+    // in a cluster every CTA runs the tile count of the first one (tiles past the end gather the last row and store nothing)
+    const uint32_t my_tiles = CL > 1 ? (uint32_t)((ntiles + (int)gridDim.x - 1) / (int)gridDim.x)
+                                     : ((int)blockIdx.x < ntiles ? (uint32_t)((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) : 0u);
 
     if (tid == 0) {
         for (int i = 0; i < TS_B_STAGES; i++) mbar_init(sFull + 8 * i, 1);
@@ -854,6 +863,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
         for (int i = 0; i < TS_A_STAGES; i++) mbar_init(sArdy + 8 * i, MLPP_PRODUCERS / 64);  // the four warps of one group
         mbar_init(sAccFull, 1);
         mbar_init(sAccFree, 128);
+        for (int i = 0; i < FREE_BARS; i++) mbar_init(sFreeB + 8 * i, CL);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < MAX_N; i += MLPP_THREADS) {
@@ -869,6 +879,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no multicast copy or commit may reach a CTA whose barriers are not initialised yet
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + (sTmem - base));
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -1028,6 +1039,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
     } else if (warp_u == MLPP_PRODUCERS / 32) {
         const bool leader = elect_one();
         const uint32_t total = my_tiles * S;
+        const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
         constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version 1 | SWIZZLE_128B
         auto desc = [&](uint32_t addr) -> uint64_t { return (uint64_t)DESC_HI << 32 | (((addr >> 4) & 0x3fffu) | (1u << 16)); };
         const uint32_t idesc1 = BF ? idesc_bf16(TILE_M, P.n1) : idesc_tf32(TILE_M, P.n1), idesc2 = BF ? idesc_bf16(TILE_M, P.n2) : idesc_tf32(TILE_M, P.n2);
@@ -1038,11 +1050,24 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
             const uint8_t* hi = reinterpret_cast<const uint8_t*>(BF ? (const void*)(g1 ? P.w1_b0 : P.w2_b0) : (const void*)(g1 ? P.w1_hi : P.w2_hi)) + (size_t)s * bbytes;
             const uint8_t* lo = reinterpret_cast<const uint8_t*>(BF ? (const void*)(g1 ? P.w1_b1 : P.w2_b1) : (const void*)(g1 ? P.w1_lo : P.w2_lo)) + (size_t)s * bbytes;
             const uint32_t bs = sBst + (J % TS_B_STAGES) * B_STAGE_BYTES, bar = sFull + 8 * (J % TS_B_STAGES);
-            if (J >= (uint32_t)TS_B_STAGES) wait_unit(2 * (J - TS_B_STAGES) + 1);  // both units of the stage's last slab are done
-            if (leader) {
-                mbar_expect_tx(bar, 2 * bbytes);
-                bulk_g2s(bs, hi, bbytes, bar);
-                bulk_g2s(bs + B_SLAB_BYTES, lo, bbytes, bar);
+            if (CL == 1) {
+                if (J >= (uint32_t)TS_B_STAGES) wait_unit(2 * (J - TS_B_STAGES) + 1);  // both units of the stage's last slab are done
+                if (leader) {
+                    mbar_expect_tx(bar, 2 * bbytes);
+                    bulk_g2s(bs, hi, bbytes, bar);
+                    bulk_g2s(bs + B_SLAB_BYTES, lo, bbytes, bar);
+                }
+            } else {
+                if (J >= (uint32_t)TS_B_STAGES) {  // ... in every CTA of the cluster
+                    const uint32_t Jf = J - TS_B_STAGES;
+                    mbar_wait(sFreeB + 8 * (Jf % FREE_BARS), (Jf / FREE_BARS) & 1u);
+                }
+                if (leader) {
+                    const uint32_t part = bbytes / CL, off = crank * part;  // n_pad * 128 / CL: a multiple of 1024
+                    mbar_expect_tx(bar, 2 * bbytes);  // own part + the part the other CTA sends
+                    bulk_g2s_multicast(bs + off, hi + off, part, bar, CL_MASK);
+                    bulk_g2s_multicast(bs + B_SLAB_BYTES + off, lo + off, part, bar, CL_MASK);
+                }
             }
         };
         // weights travel PF slabs ahead; the stage a request overwrites was read two slabs ago, so the issuer does not
@@ -1084,6 +1109,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                         }
                     }
                     umma_commit(sDone + 8 * (U % DONE_BARS));
+                    if (CL > 1 && h == 1) umma_commit_multicast(sFreeB + 8 * (J % FREE_BARS), CL_MASK);
                     if (h == 1 && j == S - 1) umma_commit(sAccFull);
                 }
                 __syncwarp();
@@ -1093,6 +1119,10 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                 jn = jn + 1 == S ? 0 : jn + 1;
             }
             if (++j == S) j = 0, it++;
+        }
+        if (CL > 1) {  // every arrival the other CTA still sends to this one has landed before this CTA may exit
+            for (uint32_t J = total > (uint32_t)FREE_BARS ? total - FREE_BARS : 0u; J < total; J++)
+                mbar_wait(sFreeB + 8 * (J % FREE_BARS), (J / FREE_BARS) & 1u);
         }
     } else if (epilogue) {
         const int H = P.h2;
@@ -1154,6 +1184,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 

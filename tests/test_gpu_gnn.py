@@ -118,11 +118,16 @@ def test_many_tiles_per_persistent_cta():
     assert all(np.array_equal(a, b) for a, b in zip(probs, again))
 
 
-@pytest.mark.parametrize("cluster", [2, 4])
-def test_weight_multicast_clusters_are_bit_identical(cluster, monkeypatch):
+@pytest.mark.parametrize("cluster,kernel", [(2, "smem"), (4, "smem"), (2, "tmem")])
+def test_weight_multicast_clusters_are_bit_identical(cluster, kernel, monkeypatch):
     # CTAs of a cluster share every weight slab (each requests 1 / cluster of it, the copy engine multicasts); rows, MMAs
     # and their order per tile are unchanged, so the logits must not differ in a single bit -- for several tiles per
     # CTA, a ragged last wave (dummy tiles), and for a batch smaller than one cluster's worth of tiles
+    if kernel == "smem":  # A staged in shared memory: 3xTF32, clusters of 2 or 4
+        monkeypatch.setenv("SLS_B200_GNN_A_TMEM", "0")
+        monkeypatch.setenv("SLS_B200_GNN_PRECISION", "tf32x3")
+    else:                 # A in tensor memory, two bf16 pieces: clusters of 2
+        monkeypatch.setenv("SLS_B200_GNN_PRECISION", "bf16x2")
     for n_inst in (40, 1):
         insts = []
         for i in range(n_inst):
