@@ -29,20 +29,27 @@ t_build = time.perf_counter() - t0
 net = gnn.InteractionNetworkLCG(go.init_params(seed=42))
 net.probabilities(insts[:2])  # warm
 eng.run_sls_batch(insts[:4], "moser", [np.full(n, 0.5)] * 4, [np.full(n, 0.5)] * 4, 100, 100)
-t0 = time.perf_counter()
-probs = net.probabilities(insts)
-t_gnn = time.perf_counter() - t0
-gnn_ms = net.last_kernel_ms
-t0 = time.perf_counter()
-res = eng.run_sls_batch(insts, "moser", probs, probs, 10_000 - 1, 100)
-t_mt = time.perf_counter() - t0
-steps = sum(r.total_steps for r in res)
-flips = sum(r.total_flips for r in res)
-solved = sum(bool(r.found.any()) for r in res)
-print(json.dumps({
-    "instances": n_inst, "build_s": round(t_build, 3),
-    "oracle_forward": {"wall_s": round(t_gnn, 3), "device_ms": round(gnn_ms, 2), "instances_per_s": n_inst / t_gnn},
-    "moser_tardos": {"wall_s": round(t_mt, 3), "kernel_ms": round(res[0].kernel_ms, 2), "steps_per_s": steps / (res[0].kernel_ms * 1e-3),
-                     "flips_per_s": flips / (res[0].kernel_ms * 1e-3), "instances_solved": solved},
-    "end_to_end_instances_per_s": n_inst / (t_gnn + t_mt),
-}, indent=1))
+def pipeline():
+    t0 = time.perf_counter()
+    probs = net.probabilities(insts)
+    t_gnn = time.perf_counter() - t0
+    gnn_ms = net.last_kernel_ms
+    t0 = time.perf_counter()
+    res = eng.run_sls_batch(insts, "moser", probs, probs, 10_000 - 1, 100)
+    t_mt = time.perf_counter() - t0
+    steps = sum(r.total_steps for r in res)
+    flips = sum(r.total_flips for r in res)
+    solved = sum(bool(r.found.any()) for r in res)
+    return {
+        "oracle_forward": {"wall_s": round(t_gnn, 3), "device_ms": round(gnn_ms, 2), "instances_per_s": n_inst / t_gnn},
+        "moser_tardos": {"wall_s": round(t_mt, 3), "kernel_ms": round(res[0].kernel_ms, 2), "steps_per_s": steps / (res[0].kernel_ms * 1e-3),
+                         "flips_per_s": flips / (res[0].kernel_ms * 1e-3), "instances_solved": solved},
+        "end_to_end_instances_per_s": n_inst / (t_gnn + t_mt),
+    }
+
+
+# first pass: instances are uploaded and the activation workspace (8 GB chunks) is allocated inside the timed calls;
+# second pass: the same handles and workspace again, as every later batch of a 10,000-instance job finds them
+first = pipeline()
+steady = pipeline()
+print(json.dumps({"instances": n_inst, "build_s": round(t_build, 3), "first_pass": first, "steady_state": steady}, indent=1))
