@@ -315,10 +315,45 @@ def run_own(args, rank, world, local_rank):
             "value": f / dt, "unit": "flips/s", "cores": cores, "kind": "port",
             "sample": f"{nruns} of {CHAINS_PER_GPU} chains x {NSTEPS} steps, {cores} threads, parse included",
         }
+    # ---- second leg of the north star, reported beside the headline (rank 0, N=1 only; never part of `value`): the batched
+    # GNN oracle forward on BASELINE config 4's shape, random-init weights, device time by CUDA events inside the library
+    if rank == 0 and world == 1 and not args.no_oracle_forward:
+        try:
+            line["oracle_forward"] = oracle_forward_leg()
+        except Exception as exc:  # the headline line must survive a failure of the secondary leg
+            line["oracle_forward"] = {"error": f"{type(exc).__name__}: {exc}"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
+
+
+def oracle_forward_leg(n_inst: int = 256, reps: int = 3):
+    import sls_sat_solving_with_deep_learning_b200 as eng
+    from sls_sat_solving_with_deep_learning_b200 import gnn, synth as _synth
+
+    n, m = 500, 2100
+    insts = []
+    for i in range(n_inst):
+        row, lits = _synth.random_ksat_csr(n, m, 3, 20260104 + i)
+        insts.append(eng.Instance.from_csr(n, row, lits))
+    net = gnn.InteractionNetworkLCG(_synth.random_oracle_params(seed=42))
+    net.probabilities(insts)  # warm: uploads the instances, allocates the activation workspace
+    best_ms, best_wall = 1e30, 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        net.probabilities(insts)
+        best_wall = min(best_wall, time.perf_counter() - t0)
+        best_ms = min(best_ms, net.last_kernel_ms)
+    n_nodes, n_edges = 2 * n + m, 3 * m + n
+    flops = n_inst * (1.3984e6 * n_edges + 1.5328e6 * n_nodes)  # dense FLOPs as the reference computes them
+    return {
+        "workload": f"C4 shape: {n_inst} synthetic 3-SAT instances n={n} m={m} (LCG: {n_nodes} nodes, {n_edges} edges each), random-init interaction network",
+        "instances_per_s": n_inst / (best_ms * 1e-3), "device_ms": best_ms,
+        "e2e_instances_per_s": n_inst / best_wall, "precision": os.environ.get("SLS_B200_GNN_PRECISION", "bf16x2"),
+        "dense_tflops": flops / (best_ms * 1e-3) / 1e12, "gpu_launches": int(net.launch_count()),
+        "kernel": "gnn::mlp_ln_persistent_ts_kernel (tcgen05, A operand in TMEM) + segment_sum_kernel",
+    }
 
 
 def main():
@@ -329,6 +364,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-oracle-forward", action="store_true", help="skip the secondary GNN oracle-forward measurement")
     ap.add_argument("--nsteps-per-chain", type=int, default=NSTEPS,
                     help="profiling only: shorten the chains (the default is the BASELINE workload)")
     args = ap.parse_args()

@@ -38,3 +38,37 @@ def write_dimacs(path: str, n: int, row_ptr, signed_lits) -> None:
         for c in range(len(row_ptr) - 1):
             lines.append(" ".join(map(str, lits[row_ptr[c]:row_ptr[c + 1]])) + " 0\n")
         f.write("".join(lines))
+
+
+def random_oracle_params(seed: int = 42, mlp_layers=(200, 200), num_steps: int = 5, embed: int = 32):
+    """Random-init parameters of the reference's interaction network in haiku's layout ({module: {"w", "b"}} /
+    {"scale", "offset"}}, module names in construction order): Linear weights ~ truncated normal (+-2 sigma) with
+    sigma = 1 / sqrt(fan_in), zero biases, LayerNorm scale 1 / offset 0 -- haiku's defaults (model.py:13-16, :37-60, :144).
+    Stand-in for the pre-trained Data/models files, which are not shipped with the reference checkout."""
+    from .gnn import haiku_names
+
+    rng = np.random.default_rng(seed)
+    h1, h2 = mlp_layers
+
+    def lin(fan_in, fan_out):
+        w = np.clip(rng.standard_normal((fan_in, fan_out)), -2.0, 2.0) / np.sqrt(fan_in)
+        return {"w": w.astype(np.float32), "b": np.zeros(fan_out, dtype=np.float32)}
+
+    def ln(dim):
+        return {"scale": np.ones(dim, dtype=np.float32), "offset": np.zeros(dim, dtype=np.float32)}
+
+    names = haiku_names(num_steps)
+    params = {names["edge_embed"]: lin(2, embed), names["node_embed"]: lin(2, embed)}
+    e_dim = h_dim = embed
+    for t in range(num_steps):
+        st = names["steps"][t]
+        params[st["edge"]["ln"]] = ln(h2)
+        params[st["edge"]["l1"]] = lin(e_dim + 2 * h_dim, h1)
+        params[st["edge"]["l2"]] = lin(h1, h2)
+        params[st["node"]["ln"]] = ln(h2)
+        params[st["node"]["l1"]] = lin(h_dim + 2 * h2, h1)
+        params[st["node"]["l2"]] = lin(h1, h2)
+        e_dim = h_dim = h2
+    params[names["readout"]] = lin(h_dim, 1)
+    return params
+

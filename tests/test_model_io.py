@@ -63,3 +63,16 @@ def test_load_model_without_jax(tmp_path):
 
     blob, D, h1, h2 = gnn.pack_params(got, 2)
     assert (D, h1, h2) == (32, 32, 32) and blob.dtype == np.float32
+
+
+def test_random_oracle_params_have_the_reference_layout():
+    # synth.random_oracle_params is bench.py's stand-in for the absent Data/models files: haiku names in construction order,
+    # shapes of the interaction network with mlp_layers=[200, 200] (evaluate_with_given_params.py:97-101)
+    from sls_sat_solving_with_deep_learning_b200 import gnn, synth
+
+    params = synth.random_oracle_params(seed=1)
+    blob, embed, h1, h2 = gnn.pack_params(params, 5)
+    assert (embed, h1, h2) == (32, 200, 200)
+    assert blob.dtype == np.float32 and blob.size == 1_473_993  # 1.47 M parameters
+    assert set(params) == {"linear"} | {f"linear_{i}" for i in range(1, 23)} | {"layer_norm"} | {f"layer_norm_{i}" for i in range(1, 10)}
+    assert np.abs(params["linear_2"]["w"]).max() <= 2.0 / np.sqrt(96) + 1e-6
