@@ -1242,7 +1242,7 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restric
     for (int64_t base = s; base < t; base += 32) {
         const int cnt = (int)min((int64_t)32, t - base);
         const int32_t my_id = lane < cnt ? __ldg(ids + base + lane) : 0;
-#pragma unroll 4
+#pragma unroll 8
         for (int k = 0; k < cnt; k++) {
             const int32_t id = __shfl_sync(0xffffffffu, my_id, k);
             const float4* row = reinterpret_cast<const float4*>(e + (size_t)id * H);
