@@ -1,6 +1,9 @@
+"""Phases of one wave of the evaluation driver (32 instances x 100 chains x 10^5 steps with trajectories, each instance on its
+own CUDA stream): setup, launch, wait + summaries, trajectory statistics, teardown.  Used to find that 32 streams on the default
+8 hardware queues ran 8 launches at a time (CUDA_DEVICE_MAX_CONNECTIONS).  usage: python tools/prof_eval_wave.py"""
 import os, sys, time, tempfile
 import numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as g; g.build()
 import sls_sat_solving_with_deep_learning_b200 as eng
 from sls_sat_solving_with_deep_learning_b200 import synth, evaluate
