@@ -261,7 +261,8 @@ extern "C" int sls_gnn_model_create(const float* blob, uint64_t blob_len, int32_
 
 namespace {
 
-constexpr int GNN_DEFAULT_CLUSTER = 1;
+// two CTAs per cluster share every weight slab by multicast: 1-2 % on the bf16x2 kernel (15.98 -> 15.76 ms per forward), bit-identical
+constexpr int GNN_DEFAULT_CLUSTER = 2;
 constexpr bool GNN_DEFAULT_BF16X2 = true;
 
 struct DevBuf {
