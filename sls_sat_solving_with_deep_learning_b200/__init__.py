@@ -8,13 +8,7 @@ Public surface (mirrors the reference's interface for this path):
   get_violated_constraints, eval_assignments   clause evaluation (sat_representations.py:718-741)
   candidate_energies      the training loader's candidate energies (data_utils.py:123-129)
 """
-import os as _os
-
-# concurrent per-instance launches of the evaluation driver need more than the default 8 hardware queues; read at CUDA
-# context creation, so set before anything touches the device (see csrc/api.cu)
-_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-
-from .solver import (  # noqa: F401,E402
+from .solver import (  # noqa: F401
     ALGOS,
     Instance,
     PanicException,

@@ -49,15 +49,8 @@ int sls_set_error_internal(int code, const std::string& msg) { return set_error(
     } while (0)
 
 // ------------------------------------------------------------------ device
-// The evaluation driver keeps up to 32 small, latency-bound launches in flight on their own streams.  The driver maps
-// streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8) and launches that share a queue serialise:
-// measured 0.319 s per wave of 32 instances with 8 queues, 0.111 s with 32.  The variable is read when the context is
-// created, so it is set when the library is loaded -- unless the user has set it.
-namespace {
-struct ConnectionDefault {
-    ConnectionDefault() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", /*overwrite=*/0); }
-} g_connection_default;
-}  // namespace
+// (Loading the library changes no process-wide state: CUDA_DEVICE_MAX_CONNECTIONS, which the evaluation driver's waves of
+// concurrent launches profit from, is set by that driver -- evaluate.py -- and only if the user has not set it.)
 
 extern "C" int sls_device_count(int* count)
 {
@@ -175,6 +168,11 @@ int ensure_on_device(sls_instance* inst)
     CUDA_TRY(cudaGetDevice(&dev));
     if (inst->d_blob && inst->device == dev) return SLS_OK;
     if (inst->d_blob) {
+        // the handle holds ONE device image; solvers keep raw pointers into it, so it cannot move while any exists
+        if (inst->solver_refs.load() > 0)
+            return set_error(SLS_ERR_ARG, "the instance is resident on device " + std::to_string(inst->device) +
+                                              " and in use by a solver there; free the solver or use a second handle for device " +
+                                              std::to_string(dev));
         dfree(inst->d_blob);
         inst->d_blob = nullptr;
     }
@@ -213,6 +211,8 @@ int ensure_batch_on_device(sls_instance* const* insts, uint32_t n_inst)
         for (size_t k = 0; k < cnt; k++) {
             sls_instance* inst = insts[todo[base + k]];
             if (inst->d_blob) {
+                if (inst->solver_refs.load() > 0)
+                    return set_error(SLS_ERR_ARG, "an instance of the batch is in use by a solver on another device");
                 dfree(inst->d_blob);
                 inst->d_blob = nullptr;
             }
@@ -381,6 +381,7 @@ extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignmen
     EV_TRY(cudaEventCreate(&ev0));
     EV_TRY(cudaEventCreate(&ev1));
     if (I.n) EV_TRY(cudaMemcpy(d_bytes, assignments, batch * (size_t)I.n, cudaMemcpyHostToDevice));
+    InFlight mark;  // an error exit below waits for the device before its buffers are freed
     EV_TRY(cudaEventRecord(ev0));
     EV_TRY(cudaMemsetAsync(d_e, 0, batch * 4));
     if (I.n) {
@@ -423,6 +424,7 @@ extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignmen
     EV_TRY(cudaGetLastError());
     EV_TRY(cudaEventRecord(ev1));
     EV_TRY(cudaEventSynchronize(ev1));
+    InFlight::done();
     {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev0, ev1);
@@ -488,6 +490,10 @@ struct sls_solver {
     uint32_t* d_tbits = nullptr;     // HBM tier: transposed assignments of one chunk of slices
     uint32_t tbits_slices = 0;
     uint64_t log_cap = 0;
+    // per-run results + the error word: ONE device block (err | steps | flips | best_energy | found | has_best), fetched
+    // with one copy (sls_solver_fetch); the pointers below point into it
+    char* d_results = nullptr;
+    size_t results_bytes = 0, off_steps = 0, off_flips = 0, off_be = 0, off_found = 0, off_hasbest = 0;
     uint8_t* d_found = nullptr;
     uint8_t* d_has_best = nullptr;
     uint64_t* d_steps = nullptr;
@@ -495,8 +501,9 @@ struct sls_solver {
     uint64_t* d_flips = nullptr;
     uint32_t* d_traj = nullptr;
     int32_t* d_err = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_w = nullptr;  // ev_w: the weight tables are built (legacy default stream)
     cudaStream_t last_stream = nullptr;
+    bool launched = false;  // a launch has been enqueued and not yet waited for
     int launches = 0;
     double last_ms = 0.0;
 };
@@ -504,6 +511,10 @@ struct sls_solver {
 extern "C" void sls_solver_free(sls_solver* s)
 {
     if (!s) return;
+    // one wait for the solver's own work (its last launch and the weight-table build), then every buffer goes back to the pool
+    if (s->launched && s->ev1) cudaEventSynchronize(s->ev1);
+    if (s->ev_w) cudaEventSynchronize(s->ev_w);
+    if (s->inst) s->inst->solver_refs.fetch_sub(1);
     dfree(s->d_thr);
     dfree(s->d_w);
     dfree(s->d_crecx);
@@ -514,15 +525,11 @@ extern "C" void sls_solver_free(sls_solver* s)
     dfree(s->d_flip_log);
     dfree(s->d_nf_init);
     dfree(s->d_tbits);
-    dfree(s->d_found);
-    dfree(s->d_has_best);
-    dfree(s->d_steps);
-    dfree(s->d_best_energy);
-    dfree(s->d_flips);
+    dfree(s->d_results);
     dfree(s->d_traj);
-    dfree(s->d_err);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev_w) cudaEventDestroy(s->ev_w);
     delete s;
 }
 
@@ -538,6 +545,7 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
     sls_solver* s = new (std::nothrow) sls_solver();
     if (!s) return set_error(SLS_ERR_NOMEM, "out of memory");
     s->inst = inst;
+    inst->solver_refs.fetch_add(1);
     s->p = *params;
     const DevInst& I = inst->dev;
     const uint64_t R = params->nruns;
@@ -620,15 +628,23 @@ extern "C" int sls_solver_create(sls_instance* inst, const sls_run_params* param
             SC_TRY(dmalloc(&s->d_flip_log, R1 * s->log_cap * 4));
         }
     }
-    SC_TRY(dmalloc(&s->d_found, R1));
-    SC_TRY(dmalloc(&s->d_has_best, R1));
-    SC_TRY(dmalloc(&s->d_steps, R1 * 8));
-    SC_TRY(dmalloc(&s->d_best_energy, R1 * 4));
-    SC_TRY(dmalloc(&s->d_flips, R1 * 8));
-    SC_TRY(dmalloc(&s->d_err, 4));
+    s->off_steps = 256;
+    s->off_flips = s->off_steps + align_up(R1 * 8, 256);
+    s->off_be = s->off_flips + align_up(R1 * 8, 256);
+    s->off_found = s->off_be + align_up(R1 * 4, 256);
+    s->off_hasbest = s->off_found + align_up(R1, 256);
+    s->results_bytes = s->off_hasbest + align_up(R1, 256);
+    SC_TRY(dmalloc(&s->d_results, s->results_bytes));
+    s->d_err = reinterpret_cast<int32_t*>(s->d_results);
+    s->d_steps = reinterpret_cast<uint64_t*>(s->d_results + s->off_steps);
+    s->d_flips = reinterpret_cast<uint64_t*>(s->d_results + s->off_flips);
+    s->d_best_energy = reinterpret_cast<uint32_t*>(s->d_results + s->off_be);
+    s->d_found = reinterpret_cast<uint8_t*>(s->d_results + s->off_found);
+    s->d_has_best = reinterpret_cast<uint8_t*>(s->d_results + s->off_hasbest);
     if (params->return_trajectories) SC_TRY(dmalloc(&s->d_traj, R1 * (params->nsteps + 1) * 4));
-    SC_TRY(cudaEventCreate(&s->ev0));
-    SC_TRY(cudaEventCreate(&s->ev1));
+    SC_TRY(cudaEventCreateWithFlags(&s->ev0, cudaEventDefault));
+    SC_TRY(cudaEventCreateWithFlags(&s->ev1, cudaEventDefault));
+    SC_TRY(cudaEventCreateWithFlags(&s->ev_w, cudaEventDisableTiming));
     if (s->smem_bytes) {
         SC_TRY(cudaFuncSetAttribute(walk_generic_kernel_for<true>(params->algo), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)s->smem_bytes));
@@ -699,24 +715,28 @@ extern "C" int sls_solver_set_weights(sls_solver* s, const double* w_init, size_
         else
             return set_error(SLS_ERR_WEIGHTS, "weights_initialize: p is outside range [0.0, 1.0]");
     }
-    CUDA_TRY(cudaMemcpy(s->d_thr, thr.data(), size_t(n) * 8, cudaMemcpyHostToDevice));
+    // Nothing here waits for the device: the copies (pageable sources are staged before the call returns) and the table
+    // builders are enqueued on the legacy default stream, and the next launch -- on whatever stream -- waits for ev_w.
+    // A launch of this solver that is still running reads the old tables: wait for it first (stream order alone does not
+    // cover a launch on a non-blocking stream).
+    if (s->launched) CUDA_TRY(cudaEventSynchronize(s->ev1));
+    CUDA_TRY(cudaMemcpyAsync(s->d_thr, thr.data(), size_t(n) * 8, cudaMemcpyHostToDevice, nullptr));
     if (w_resample_len >= n && n)
-        CUDA_TRY(cudaMemcpy(s->d_w, w_resample, size_t(n) * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpyAsync(s->d_w, w_resample, size_t(n) * 8, cudaMemcpyHostToDevice, nullptr));
     else if (n)
-        CUDA_TRY(cudaMemset(s->d_w, 0, size_t(n) * 8));
+        CUDA_TRY(cudaMemsetAsync(s->d_w, 0, size_t(n) * 8, nullptr));
     if (s->d_crecx && s->inst->host.m) {
         // 64-byte clause records of the k<=3 kernel: literals + occurrence ranges + resample weights
         const DevInst& I = s->inst->dev;
         build_crecx_kernel<<<(I.m + 255) / 256, 256>>>(I.crec, I.occ_ptr, s->d_w, s->d_crecx, I.m, I.n, s->p.algo);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaDeviceSynchronize());
     }
     if (s->d_ftab && s->inst->host.m) {
         const DevInst& I = s->inst->dev;
         build_flip_tables_kernel<<<(I.m + 127) / 128, 128>>>(I, s->d_w, s->p.algo, s->d_ftab, s->d_cscale);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaDeviceSynchronize());
     }
+    CUDA_TRY(cudaEventRecord(s->ev_w, nullptr));
     s->weights_set = true;
     return SLS_OK;
 }
@@ -728,6 +748,7 @@ extern "C" int sls_solver_launch(sls_solver* s, void* cuda_stream)
     s->last_stream = st;
     s->launches = 0;
     if (s->p.nruns == 0) return SLS_OK;
+    CUDA_TRY(cudaStreamWaitEvent(st, s->ev_w, 0));  // the weight tables of sls_solver_set_weights
     CUDA_TRY(cudaMemsetAsync(s->d_err, 0, 4, st));
     const unsigned blocks = (unsigned)((s->p.nruns + s->wpb - 1) / s->wpb);
     const unsigned threads = s->wpb * 32;
@@ -764,6 +785,7 @@ extern "C" int sls_solver_launch(sls_solver* s, void* cuda_stream)
             walk_generic_kernel_for<false>(s->p.algo)<<<blocks, threads, 0, st>>>(s->args);
     }
     s->launches += 1;
+    s->launched = true;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s->ev1, st));
     return SLS_OK;
@@ -771,7 +793,7 @@ extern "C" int sls_solver_launch(sls_solver* s, void* cuda_stream)
 
 extern "C" int sls_solver_sync(sls_solver* s)
 {
-    if (s->p.nruns == 0) return SLS_OK;
+    if (s->p.nruns == 0 || !s->launched) return SLS_OK;
     CUDA_TRY(cudaEventSynchronize(s->ev1));
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
@@ -814,8 +836,11 @@ extern "C" int sls_solver_fetch(sls_solver* s, sls_run_result* res)
     int rc = sls_solver_sync(s);
     if (rc) return rc;
     res->kernel_ms = s->last_ms;
+    // everything the reduction needs in ONE device-to-host copy
+    std::vector<char> blk(s->results_bytes);
+    CUDA_TRY(cudaMemcpy(blk.data(), s->d_results, s->results_bytes, cudaMemcpyDeviceToHost));
     int32_t err = 0;
-    CUDA_TRY(cudaMemcpy(&err, s->d_err, 4, cudaMemcpyDeviceToHost));
+    std::memcpy(&err, blk.data(), 4);
     if (err) {
         const char* msg = err == DERR_ALL_ZERO       ? "probsat: AllWeightsZero"
                           : err == DERR_EMPTY_CLAUSE ? "an empty clause was selected"
@@ -823,14 +848,11 @@ extern "C" int sls_solver_fetch(sls_solver* s, sls_run_result* res)
                                                      : "clause too long for the Moser-Tardos kernel (k > 1024)";
         return set_error(err, msg);
     }
-    std::vector<uint8_t> found(R), has_best(R);
-    std::vector<uint64_t> steps(R), flips(R);
-    std::vector<uint32_t> be(R);
-    CUDA_TRY(cudaMemcpy(found.data(), s->d_found, R, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(has_best.data(), s->d_has_best, R, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(steps.data(), s->d_steps, R * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(flips.data(), s->d_flips, R * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(be.data(), s->d_best_energy, R * 4, cudaMemcpyDeviceToHost));
+    const uint8_t* found = reinterpret_cast<const uint8_t*>(blk.data() + s->off_found);
+    const uint8_t* has_best = reinterpret_cast<const uint8_t*>(blk.data() + s->off_hasbest);
+    const uint64_t* steps = reinterpret_cast<const uint64_t*>(blk.data() + s->off_steps);
+    const uint64_t* flips = reinterpret_cast<const uint64_t*>(blk.data() + s->off_flips);
+    const uint32_t* be = reinterpret_cast<const uint32_t*>(blk.data() + s->off_be);
     // lib.rs:320-334: strict '<' arg-min in run order starting from formula.len()
     uint64_t best = h.m;
     size_t winner = R;
@@ -853,9 +875,9 @@ extern "C" int sls_solver_fetch(sls_solver* s, sls_run_result* res)
             for (uint32_t v = 0; v < h.n; v++) res->best_assignment[v] = (bits[v >> 5] >> (v & 31)) & 1u;
         }
     }
-    if (res->found) std::memcpy(res->found, found.data(), R);
-    if (res->steps) std::memcpy(res->steps, steps.data(), R * 8);
-    if (res->flips_run) std::memcpy(res->flips_run, flips.data(), R * 8);
+    if (res->found) std::memcpy(res->found, found, R);
+    if (res->steps) std::memcpy(res->steps, steps, R * 8);
+    if (res->flips_run) std::memcpy(res->flips_run, flips, R * 8);
     if (res->best_energy_run)
         for (size_t r = 0; r < R; r++) res->best_energy_run[r] = be[r];
     if (s->p.return_trajectories) {
@@ -971,6 +993,8 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     if (params->return_trajectories)
         return set_error(SLS_ERR_ARG, "sls_run_batch does not return trajectories; use sls_run per instance for them");
     const uint64_t R = params->nruns;
+    for (uint32_t i = 0; i < n_inst; i++)
+        if (!insts[i]) return set_error(SLS_ERR_ARG, "NULL instance handle in batch");
     for (uint32_t i = 0; i < n_inst; i++) {
         results[i].best_energy = insts[i]->host.m;
         results[i].has_best_assignment = 0;
@@ -1038,27 +1062,28 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         }
     }
 
-    Pool p_thr, p_w, p_crecx, p_ftab, p_cscale, p_bits, p_found, p_hasbest, p_steps, p_flips, p_best, p_gstate, p_err, p_items, p_cta;
+    // per-run results and the per-instance error words share ONE pool (err | steps | flips | best | found | has_best):
+    // one device-to-host copy brings all of them back
+    Pool p_thr, p_w, p_crecx, p_ftab, p_cscale, p_bits, p_res, p_gstate;
+    const size_t ro_steps = align_up(size_t(n_inst) * 4, 256), ro_flips = ro_steps + align_up(tot_run * 8, 256),
+                 ro_best = ro_flips + align_up(tot_run * 8, 256), ro_found = ro_best + align_up(tot_run * 4, 256),
+                 ro_hasbest = ro_found + align_up(tot_run, 256), res_bytes = ro_hasbest + align_up(tot_run, 256);
     auto alloc = [&](Pool& p, size_t bytes) -> cudaError_t {
         p.size = std::max<size_t>(bytes, 16);
         return dmalloc(&p.base, p.size);
     };
+    InFlight mark;  // an error exit below waits for the device before the pools are freed
     CUDA_TRY(alloc(p_thr, tot_n * 8));
     CUDA_TRY(alloc(p_w, tot_n * 8));
     CUDA_TRY(alloc(p_crecx, tot_crecx * sizeof(uint4)));
     CUDA_TRY(alloc(p_ftab, tot_ftab * 8));
     CUDA_TRY(alloc(p_cscale, tot_cscale * 8));
     CUDA_TRY(alloc(p_bits, tot_bits * 4));
-    CUDA_TRY(alloc(p_found, tot_run));
-    CUDA_TRY(alloc(p_hasbest, tot_run));
-    CUDA_TRY(alloc(p_steps, tot_run * 8));
-    CUDA_TRY(alloc(p_flips, tot_run * 8));
-    CUDA_TRY(alloc(p_best, tot_run * 4));
+    CUDA_TRY(alloc(p_res, res_bytes));
     CUDA_TRY(alloc(p_gstate, tot_gstate * 4));
-    CUDA_TRY(alloc(p_err, size_t(n_inst) * 4));
-    CUDA_TRY(cudaMemcpy(p_thr.base, thr.data(), tot_n * 8, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(p_w.base, wres.data(), tot_n * 8, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemset(p_err.base, 0, size_t(n_inst) * 4));
+    CUDA_TRY(cudaMemcpyAsync(p_thr.base, thr.data(), tot_n * 8, cudaMemcpyHostToDevice, nullptr));
+    CUDA_TRY(cudaMemcpyAsync(p_w.base, wres.data(), tot_n * 8, cudaMemcpyHostToDevice, nullptr));
+    CUDA_TRY(cudaMemsetAsync(p_res.base, 0, ro_steps, nullptr));
 
     // ---- per-instance kernel arguments, grouped by variant: 0 = k3s, 1 = generic<smem>, 2 = generic<hbm>
     // (3 = k3d: two chains per warp, small k<=3 instances, 4 = four chains per warp for the smallest;
@@ -1098,13 +1123,13 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         a.gstate = pl.smem ? nullptr : reinterpret_cast<uint32_t*>(p_gstate.base) + pl.off_gstate;
         a.warps_per_block = pl.wpb;
         a.best_bits = reinterpret_cast<uint32_t*>(p_bits.base) + pl.off_bits;
-        a.found = reinterpret_cast<uint8_t*>(p_found.base) + pl.off_run;
-        a.has_best = reinterpret_cast<uint8_t*>(p_hasbest.base) + pl.off_run;
-        a.steps = reinterpret_cast<uint64_t*>(p_steps.base) + pl.off_run;
-        a.best_energy = reinterpret_cast<uint32_t*>(p_best.base) + pl.off_run;
-        a.flips = reinterpret_cast<uint64_t*>(p_flips.base) + pl.off_run;
+        a.found = reinterpret_cast<uint8_t*>(p_res.base + ro_found) + pl.off_run;
+        a.has_best = reinterpret_cast<uint8_t*>(p_res.base + ro_hasbest) + pl.off_run;
+        a.steps = reinterpret_cast<uint64_t*>(p_res.base + ro_steps) + pl.off_run;
+        a.best_energy = reinterpret_cast<uint32_t*>(p_res.base + ro_best) + pl.off_run;
+        a.flips = reinterpret_cast<uint64_t*>(p_res.base + ro_flips) + pl.off_run;
         a.traj = nullptr;
-        a.err = reinterpret_cast<int32_t*>(p_err.base) + i;
+        a.err = reinterpret_cast<int32_t*>(p_res.base) + i;
         if (!pl.k3 && params->algo != SLS_ALGO_SCHOENING) {
             a.ftab = reinterpret_cast<double*>(p_ftab.base) + pl.off_ftab;
             a.cscale = reinterpret_cast<double*>(p_cscale.base) + pl.off_cscale;
@@ -1133,16 +1158,24 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     }
     CUDA_TRY(cudaGetLastError());
 
-    cudaEvent_t ev0, ev1;
-    CUDA_TRY(cudaEventCreate(&ev0));
-    CUDA_TRY(cudaEventCreate(&ev1));
+    struct Events {  // destroyed on every exit path
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        ~Events()
+        {
+            if (ev0) cudaEventDestroy(ev0);
+            if (ev1) cudaEventDestroy(ev1);
+        }
+    } evs;
+    CUDA_TRY(cudaEventCreate(&evs.ev0));
+    CUDA_TRY(cudaEventCreate(&evs.ev1));
+    cudaEvent_t ev0 = evs.ev0, ev1 = evs.ev1;
     Pool d_items[NG], d_cta[NG];
     for (int g = 0; g < NG; g++) {
         if (items[g].empty()) continue;
         CUDA_TRY(alloc(d_items[g], items[g].size() * sizeof(WalkArgs)));
         CUDA_TRY(alloc(d_cta[g], cta_begin[g].size() * 4));
-        CUDA_TRY(cudaMemcpy(d_items[g].base, items[g].data(), items[g].size() * sizeof(WalkArgs), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(d_cta[g].base, cta_begin[g].data(), cta_begin[g].size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpyAsync(d_items[g].base, items[g].data(), items[g].size() * sizeof(WalkArgs), cudaMemcpyHostToDevice, nullptr));
+        CUDA_TRY(cudaMemcpyAsync(d_cta[g].base, cta_begin[g].data(), cta_begin[g].size() * 4, cudaMemcpyHostToDevice, nullptr));
     }
     const WalkK3BatchKernel k3_batch = walk_k3s_batch_kernel_for(params->algo, params->prob_flip_best);
     if (smem_max[0]) CUDA_TRY(cudaFuncSetAttribute(k3_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[0]));
@@ -1171,14 +1204,14 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev1));
     CUDA_TRY(cudaEventSynchronize(ev1));
+    InFlight::done();
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
 
-    // ---- results: pooled D2H, per-instance reduction (lib.rs:320-334)
-    std::vector<int32_t> err(n_inst);
-    CUDA_TRY(cudaMemcpy(err.data(), p_err.base, size_t(n_inst) * 4, cudaMemcpyDeviceToHost));
+    // ---- results: one pooled D2H, per-instance reduction (lib.rs:320-334)
+    std::vector<char> blk(res_bytes);
+    CUDA_TRY(cudaMemcpy(blk.data(), p_res.base, res_bytes, cudaMemcpyDeviceToHost));
+    const int32_t* err = reinterpret_cast<const int32_t*>(blk.data());
     for (uint32_t i = 0; i < n_inst; i++)
         if (err[i]) {
             const char* msg = err[i] == DERR_ALL_ZERO       ? "probsat: AllWeightsZero"
@@ -1187,14 +1220,11 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
                                                             : "clause too long for the Moser-Tardos kernel (k > 1024)";
             return set_error(err[i], std::string(msg) + " (instance " + std::to_string(i) + ")");
         }
-    std::vector<uint8_t> found(tot_run), has_best(tot_run);
-    std::vector<uint64_t> steps(tot_run), flips(tot_run);
-    std::vector<uint32_t> be(tot_run);
-    CUDA_TRY(cudaMemcpy(found.data(), p_found.base, tot_run, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(has_best.data(), p_hasbest.base, tot_run, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(steps.data(), p_steps.base, tot_run * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(flips.data(), p_flips.base, tot_run * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(be.data(), p_best.base, tot_run * 4, cudaMemcpyDeviceToHost));
+    const uint8_t* found = reinterpret_cast<const uint8_t*>(blk.data() + ro_found);
+    const uint8_t* has_best = reinterpret_cast<const uint8_t*>(blk.data() + ro_hasbest);
+    const uint64_t* steps = reinterpret_cast<const uint64_t*>(blk.data() + ro_steps);
+    const uint64_t* flips = reinterpret_cast<const uint64_t*>(blk.data() + ro_flips);
+    const uint32_t* be = reinterpret_cast<const uint32_t*>(blk.data() + ro_best);
     // best assignments: one copy of the whole pool when it is small (a batch of small instances would otherwise pay
     // one synchronous copy per instance), else only the winning chain's words
     std::vector<uint32_t> bits, all_bits;
@@ -1234,9 +1264,9 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
                 for (uint32_t v = 0; v < h.n; v++) r.best_assignment[v] = (wb[v >> 5] >> (v & 31)) & 1u;
             }
         }
-        if (r.found) std::memcpy(r.found, found.data() + pl.off_run, R);
-        if (r.steps) std::memcpy(r.steps, steps.data() + pl.off_run, R * 8);
-        if (r.flips_run) std::memcpy(r.flips_run, flips.data() + pl.off_run, R * 8);
+        if (r.found) std::memcpy(r.found, found + pl.off_run, R);
+        if (r.steps) std::memcpy(r.steps, steps + pl.off_run, R * 8);
+        if (r.flips_run) std::memcpy(r.flips_run, flips + pl.off_run, R * 8);
         if (r.best_energy_run)
             for (size_t q = 0; q < R; q++) r.best_energy_run[q] = be[pl.off_run + q];
     }

@@ -1,14 +1,20 @@
-// devmem.h -- device allocations of the library go through the driver's stream-ordered pool.
+// devmem.h -- device allocations of the library go through a PRIVATE stream-ordered pool.
 //
 // The reference-facing call (run_sls_python, rust/src/lib.rs:103-149) allocates and frees its working set on
 // every call; with cudaMalloc / cudaFree that is a page-table update per buffer and showed up as 10-350 ms of
 // jitter around a 180 ms kernel.  The pool keeps freed blocks mapped (up to the release threshold) so a repeated
-// call of the same shape allocates without talking to the OS.
+// call of the same shape allocates without talking to the OS.  The pool is the library's own (cudaMemPoolCreate):
+// the device's default pool and its release threshold, which belong to the host application, are left alone.
 //
 // Large buffers (GNN activations, HBM-tier chain state: hundreds of MB to tens of GB) do NOT go through the pool:
 // growing the pool by gigabytes costs ~30 ms per GB, and keeping such blocks cached would take them away from the
 // application's own allocator (torch uses cudaMalloc, which cannot see the pool's free memory).  They use plain
 // cudaMalloc / cudaFree, which is cheap at that size.
+//
+// Freeing: dfree() does NOT synchronise the device per buffer.  Its contract is "no work that uses the block is in
+// flight".  The synchronous entry points of the library end with a wait on their own work, and mark the time in between
+// with InFlight (below): a dfree reached while the calling thread's work may still be running -- an error path --
+// waits for the device ONCE and clears the mark.  sls_solver_free waits for the solver's last launch itself.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -25,6 +31,7 @@ constexpr size_t kPoolMaxBlock = 32u << 20;       // larger requests bypass the 
 struct DevMemState {
     std::mutex mu;
     cudaStream_t stream[kMaxDevices] = {};
+    cudaMemPool_t pool[kMaxDevices] = {};
     bool ready[kMaxDevices] = {};
     std::unordered_set<void*> direct;  // blocks that came from cudaMalloc
 };
@@ -36,25 +43,42 @@ inline DevMemState& devmem_state()
 }
 
 // Stream the pool operations of `device` are ordered on (created on first use; the device must be current).
-inline cudaError_t devmem_stream(int device, cudaStream_t* out)
+inline cudaError_t devmem_stream(int device, cudaStream_t* out, cudaMemPool_t* pool_out = nullptr)
 {
     DevMemState& st = devmem_state();
     if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
     std::lock_guard<std::mutex> lock(st.mu);
     if (!st.ready[device]) {
-        cudaMemPool_t pool;
-        cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaError_t e = cudaMemPoolCreate(&st.pool[device], &props);
         if (e != cudaSuccess) return e;
         uint64_t keep = kPoolKeepBytes;
-        e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        e = cudaMemPoolSetAttribute(st.pool[device], cudaMemPoolAttrReleaseThreshold, &keep);
         if (e != cudaSuccess) return e;
         e = cudaStreamCreateWithFlags(&st.stream[device], cudaStreamNonBlocking);
         if (e != cudaSuccess) return e;
         st.ready[device] = true;
     }
     *out = st.stream[device];
+    if (pool_out) *pool_out = st.pool[device];
     return cudaSuccess;
 }
+
+// "work of the calling thread that uses library buffers may still be running": set by the synchronous entry points
+// around their launches, cleared once they have waited for them.
+inline bool& devmem_inflight()
+{
+    static thread_local bool f = false;
+    return f;
+}
+struct InFlight {
+    InFlight() { devmem_inflight() = true; }
+    static void done() { devmem_inflight() = false; }
+};
 
 // Allocation on the current device, usable from any stream on return.
 template <class T>
@@ -75,10 +99,11 @@ inline cudaError_t dmalloc(T** p, size_t bytes)
     cudaError_t e = cudaGetDevice(&device);
     if (e != cudaSuccess) return e;
     cudaStream_t st;
-    e = devmem_stream(device, &st);
+    cudaMemPool_t pool;
+    e = devmem_stream(device, &st, &pool);
     if (e != cudaSuccess) return e;
     void* q = nullptr;
-    e = cudaMallocAsync(&q, bytes ? bytes : 1, st);
+    e = cudaMallocFromPoolAsync(&q, bytes ? bytes : 1, pool, st);
     if (e != cudaSuccess) return e;
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return e;
@@ -86,11 +111,15 @@ inline cudaError_t dmalloc(T** p, size_t bytes)
     return cudaSuccess;
 }
 
-// Same contract as cudaFree: waits for the device to be idle, so no kernel can still be using the block when
-// a later dmalloc hands it out again.  NULL is ignored.
+// The caller guarantees that no work using the block is in flight (see the header comment); a thread that is inside
+// an InFlight region waits for the device once.  NULL is ignored.
 inline void dfree(void* p)
 {
     if (!p) return;
+    if (devmem_inflight()) {
+        cudaDeviceSynchronize();
+        devmem_inflight() = false;
+    }
     {
         DevMemState& st = devmem_state();
         std::unique_lock<std::mutex> lock(st.mu);
@@ -109,10 +138,7 @@ inline void dfree(void* p)
     }
     if (attr.device != prev) cudaSetDevice(attr.device);
     cudaStream_t st;
-    if (devmem_stream(attr.device, &st) == cudaSuccess) {
-        cudaDeviceSynchronize();
-        cudaFreeAsync(p, st);
-    }
+    if (devmem_stream(attr.device, &st) == cudaSuccess) cudaFreeAsync(p, st);
     if (attr.device != prev) cudaSetDevice(prev);
 }
 

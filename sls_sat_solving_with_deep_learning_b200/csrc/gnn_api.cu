@@ -94,6 +94,7 @@ struct sls_gnn_model {
     float readout_b = 0.f;
     std::vector<void*> allocs;
     int launches = 0;
+    bool prefer_tf32x3 = false;  // this model's default product when SLS_B200_GNN_PRECISION is unset (see sls_gnn_model_create)
     // Activation workspace (edge / node feature ping-pong buffers and the two aggregates): one block, grown on
     // demand and kept across calls, so a repeated forward of the same batch shape allocates nothing.
     void* ws = nullptr;
@@ -244,13 +245,9 @@ extern "C" int sls_gnn_model_create(const float* blob, uint64_t blob_len, int32_
         return rc;
     }
     m->readout_b = *p;
-    cudaError_t e = cudaFuncSetAttribute(mlp_ln_persistent_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM_BYTES);
     if (e != cudaSuccess) {
         sls_gnn_model_free(m);
         return sls_set_error_internal(SLS_ERR_CUDA, std::string("cudaFuncSetAttribute(mlp_ln_kernel): ") + cudaGetErrorString(e));
@@ -263,7 +260,6 @@ namespace {
 
 // two CTAs per cluster share every weight slab by multicast: 1-2 % on the bf16x2 kernel (15.98 -> 15.76 ms per forward), bit-identical
 constexpr int GNN_DEFAULT_CLUSTER = 2;
-constexpr bool GNN_DEFAULT_BF16X2 = true;
 
 struct DevBuf {
     void* p = nullptr;
@@ -288,32 +284,17 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
     a.w1_b0 = w.w1_b0, a.w1_b1 = w.w1_b1, a.w2_b0 = w.w2_b0, a.w2_b1 = w.w2_b1;
     a.k1_slabs_bf = w.k1_slabs_bf, a.k2_slabs_bf = w.k2_slabs_bf;
     const unsigned blocks = (unsigned)((rows + TILE_M - 1) / TILE_M);
-    // persistent three-role kernel, one CTA per SM; SLS_B200_GNN_ONE_TILE=1 selects the one-tile-per-CTA kernel
-    static const bool one_tile = [] { const char* f = std::getenv("SLS_B200_GNN_ONE_TILE"); return f && f[0] == '1'; }();
-    if (one_tile) {
-        mlp_ln_kernel<<<blocks, MLP_THREADS, MLP_SMEM_BYTES>>>(a);
-    } else {
-        // SLS_B200_GNN_CLUSTER = 1 | 2 | 4: CTAs per cluster sharing the weight stream by multicast (see the kernel)
+    {
+        // SLS_B200_GNN_CLUSTER = 1 | 2: CTAs per cluster sharing the weight stream by multicast (see the kernel)
         const char* f = std::getenv("SLS_B200_GNN_CLUSTER");  // read per launch: the tests switch it
         const int c = f ? std::atoi(f) : GNN_DEFAULT_CLUSTER;
-        const int cluster = c == 2 || c == 4 ? c : 1;
-        // SLS_B200_GNN_A_TMEM=0 selects the kernel that stages the A operand in shared memory (3xTF32 only)
-        const char* ft = std::getenv("SLS_B200_GNN_A_TMEM");
-        const bool a_tmem = ft ? ft[0] != '0' : true;
-        // SLS_B200_GNN_PRECISION = bf16x2 (default: two bf16 pieces per operand on kind::f16) | tf32x3
+        // SLS_B200_GNN_PRECISION = bf16x2 (default: two bf16 pieces per operand on kind::f16) | tf32x3; a model whose
+        // parameters have a wide dynamic range is created with tf32x3 as its own default (sls_gnn_model_create)
         const char* fp = std::getenv("SLS_B200_GNN_PRECISION");
-        const bool tf32x3 = fp ? std::strcmp(fp, "tf32x3") == 0 : !GNN_DEFAULT_BF16X2;
-        void (*kern)(const MlpArgs) = nullptr;
-        int cl = 1;
-        size_t smem = TS_SMEM_BYTES;
-        if (a_tmem) {
-            cl = (!tf32x3 && cluster == 2) ? 2 : 1;
-            kern = tf32x3 ? mlp_ln_persistent_ts_kernel<false, 1> : cl == 2 ? mlp_ln_persistent_ts_kernel<true, 2> : mlp_ln_persistent_ts_kernel<true, 1>;
-        } else {
-            cl = cluster;
-            smem = MLP_SMEM_BYTES;
-            kern = cl == 1 ? mlp_ln_persistent_kernel<1> : cl == 2 ? mlp_ln_persistent_kernel<2> : mlp_ln_persistent_kernel<4>;
-        }
+        const bool tf32x3 = fp ? std::strcmp(fp, "tf32x3") == 0 : m->prefer_tf32x3;
+        const int cl = (!tf32x3 && c == 2) ? 2 : 1;
+        void (*kern)(const MlpArgs) = tf32x3 ? mlp_ln_persistent_ts_kernel<false, 1> : cl == 2 ? mlp_ln_persistent_ts_kernel<true, 2> : mlp_ln_persistent_ts_kernel<true, 1>;
+        const size_t smem = TS_SMEM_BYTES;
         if (cl == 1) {
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
@@ -327,17 +308,16 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
             cfg.blockDim = dim3(MLPP_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = 0;
             cfg.attrs = &attr, cfg.numAttrs = 1;
             // the grid is one wave of co-resident clusters (tiles are assigned statically): ask how many fit
-            static int max_clusters[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
-            int& cached = max_clusters[a_tmem ? 1 : 0][cl];
-            if (cached == 0) {
+            static int max_clusters = 0;
+            if (max_clusters == 0) {
                 cfg.gridDim = dim3((unsigned)cl);
                 int n = 0;
                 G_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
                 if (n < 1) return sls_set_error_internal(SLS_ERR_CUDA, "no cluster of the oracle-forward kernel fits on this device");
-                cached = n;
+                max_clusters = n;
             }
             const unsigned want = (blocks + (unsigned)cl - 1) / (unsigned)cl;
-            cfg.gridDim = dim3(std::min<unsigned>(want, (unsigned)cached) * (unsigned)cl);
+            cfg.gridDim = dim3(std::min<unsigned>(want, (unsigned)max_clusters) * (unsigned)cl);
             G_TRY(cudaLaunchKernelEx(&cfg, kern, a));
         }
     }

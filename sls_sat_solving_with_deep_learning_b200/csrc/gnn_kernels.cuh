@@ -32,23 +32,12 @@ namespace gnn {
 static constexpr int TILE_M = 128;       // rows per CTA = UMMA M
 static constexpr int SLAB_K = 32;        // tf32 elements per 128-byte swizzle row
 static constexpr int MAX_N = 208;        // padded output width (multiple of 16, >= hidden)
-static constexpr int A_SLAB_BYTES = TILE_M * 128;   // 16 KB
-static constexpr int B_SLAB_BYTES = MAX_N * 128;    // 26 KB
-// pipeline buffers: A_STAGES x (A_hi | A_lo) filled by the threads, B_STAGES x (B_hi | B_lo) filled
-// by TMA bulk copies of pre-swizzled weight slab images
-static constexpr int A_STAGES = 2;
-static constexpr int B_STAGES = 3;
-static constexpr int A_STAGE_BYTES = 2 * A_SLAB_BYTES;   // 32 KB
-static constexpr int B_STAGE_BYTES = 2 * B_SLAB_BYTES;   // 52 KB
-static constexpr int DONE_BARS = 6;                      // lcm(A_STAGES, B_STAGES): one per slab index mod 6
+static constexpr int B_SLAB_BYTES = MAX_N * 128;    // 26 KB: one weight slab image (one 128-byte row per output column)
+static constexpr int B_STAGE_BYTES = 2 * B_SLAB_BYTES;   // 52 KB: the two pieces of a slab (hi | lo, or b0 | b1)
+static constexpr int DONE_BARS = 6;                      // one mbarrier per unit index mod 6
 static constexpr int TMEM_COLS = 512;
-static constexpr int ACC2_COL = 256;
-static constexpr int MLP_PRODUCERS = 128;                // warps 0-3: stage A rows, run the epilogues (thread = row)
-static constexpr int MLP_THREADS = MLP_PRODUCERS + 32;   // warp 4: one lane issues the weight copies and the MMAs
 static constexpr int PAR_BYTES = 3 * MAX_N * 4;          // b2 | ln_scale | ln_offset staged in shared memory
-static constexpr int OUT_PITCH = 204;                   // floats per row of the output tile (816 B: conflict-free 16-byte stores)
 static constexpr int BAR_BYTES = 256;                    // mbarriers + the TMEM base address
-static constexpr int MLP_SMEM_BYTES = A_STAGES * A_STAGE_BYTES + B_STAGES * B_STAGE_BYTES + BAR_BYTES + PAR_BYTES + 1024;  // + alignment slack
 
 struct MlpArgs {
     // up to three gathered input segments: row i of the A matrix is
@@ -217,549 +206,20 @@ __device__ __forceinline__ float round_tf32(float x)
 __device__ __forceinline__ float residual_tf32(float x, float hi) { return x - hi; }
 
 // ---- the fused update: LayerNorm(ReLU(Linear2(ReLU(Linear1(gathered rows))))) -------------------
-__global__ void __launch_bounds__(MLP_THREADS, 1) mlp_ln_kernel(const MlpArgs P)
-{
-    extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B atoms need 1024-byte alignment
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sAst = base;                                   // A stages
-    const uint32_t sBst = base + A_STAGES * A_STAGE_BYTES;        // B stages
-    const uint32_t sFull = sBst + B_STAGES * B_STAGE_BYTES;       // B_STAGES "weights landed" mbarriers
-    const uint32_t sDone = sFull + 8 * B_STAGES;                  // DONE_BARS "MMAs of slab j done" mbarriers
-    const uint32_t sArdy = sDone + 8 * DONE_BARS;                 // A_STAGES "A stage filled by all producers" mbarriers
-    const uint32_t sTmem = sArdy + 8 * A_STAGES;                  // TMEM base address written by tcgen05.alloc
-    const uint32_t sPar = sFull + 128;                            // b2[MAX_N] | ln_scale[MAX_N] | ln_offset[MAX_N] (16-byte aligned)
-    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));   // generic alias of `base`
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int row0 = blockIdx.x * TILE_M;
-    const bool producer = tid < MLP_PRODUCERS;
-    const int my_row = min(row0 + (producer ? tid : 0), P.rows - 1);  // rows past the end re-read the last row; their output is not stored
-
-    if (tid == 0) {
-        for (int i = 0; i < B_STAGES; i++) mbar_init(sFull + 8 * i, 1);
-        for (int i = 0; i < DONE_BARS; i++) mbar_init(sDone + 8 * i, 1);
-        for (int i = 0; i < A_STAGES; i++) mbar_init(sArdy + 8 * i, MLP_PRODUCERS);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < MAX_N; i += MLP_THREADS) {  // epilogue parameters -> shared memory (read as broadcasts)
-        const bool in = i < P.h2;
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + i * 4), "f"(i < P.n2 ? __ldg(P.b2 + i) : 0.f) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + (MAX_N + i) * 4), "f"(in ? __ldg(P.ln_scale + i) : 0.f) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + (2 * MAX_N + i) * 4), "f"(in ? __ldg(P.ln_offset + i) : 0.f) : "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + (sTmem - base));
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;  // this warp's TMEM lane quarter (row = lane)
-
-    // source row pointers of this thread's A row
-    const float* rp[3];
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        rp[j] = nullptr;
-        if (P.d[j] > 0) {
-            const int r = P.idx[j] ? __ldg(P.idx[j] + my_row) : my_row;
-            rp[j] = P.src[j] + (size_t)r * P.d[j];
-        }
-    }
-    const int kA = P.d[0] + P.d[1] + P.d[2];
-
-    // write one 16-byte unit of this thread's row, split into TF32 hi / lo, into an A stage
-    auto put_split = [&](uint32_t stage_base, int u, float4 x) {
-        float4 hi, lo;
-        hi.x = round_tf32(x.x), hi.y = round_tf32(x.y), hi.z = round_tf32(x.z), hi.w = round_tf32(x.w);
-        lo.x = residual_tf32(x.x, hi.x), lo.y = residual_tf32(x.y, hi.y), lo.z = residual_tf32(x.z, hi.z), lo.w = residual_tf32(x.w, hi.w);
-        const uint32_t off = sw128_off(tid, u);
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + A_SLAB_BYTES + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
-    };
-    // GEMM1 A slab: this thread's gathered row, columns [32 s, 32 s + 32), into registers
-    auto load_a1 = [&](int s, float4* x) {
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int col = s * SLAB_K + u * 4;
-            x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col < kA) {
-                const float* p = col < P.d[0] ? rp[0] + col : col < P.d[0] + P.d[1] ? rp[1] + (col - P.d[0]) : rp[2] + (col - P.d[0] - P.d[1]);
-                x[u] = __ldg(reinterpret_cast<const float4*>(p));
-            }
-        }
-    };
-    // GEMM2 A slab: Y1 = ReLU(acc1 + b1), columns [32 s, 32 s + 32), straight out of TMEM
-    auto stage_a2 = [&](uint32_t stage_base, int s) {
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-            const int c0 = s * SLAB_K + half * 16;
-            float v[16];
-            if (c0 < P.n1) {
-                tmem_ld16(tmem + lane_base + (uint32_t)c0, v);
-#pragma unroll
-                for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + __ldg(P.b1 + c0 + i), 0.f);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; i++) v[i] = 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++) put_split(stage_base, half * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-        }
-    };
-
-    // Pipeline, warp-specialised.  Slabs of both GEMMs are numbered consecutively (j); slab j uses A
-    // stage j % 2 and B stage j % 3.
-    //   producers (threads 0..127): wait until slab j-2 is done, fill A stage j % 2 (GEMM1: gathered
-    //     rows prefetched into registers one slab ahead; GEMM2: ReLU(acc1 + b1) straight out of TMEM),
-    //     fence, arrive on sArdy[j % 2];
-    //   issuer (thread 128): keeps two weight slabs in flight (two TMA bulk copies per slab into B stage
-    //     j % 3 once slab j-3 is done, completion on sFull[j % 3]), waits for sArdy and sFull of slab j,
-    //     issues its 12 MMAs and a tcgen05.commit on sDone[j % 6].
-    // Nothing in the loop is a CTA-wide barrier, so staging of slab j+1 overlaps the MMAs of slab j.
-    auto wait_done = [&](uint32_t j) { mbar_wait(sDone + 8 * (j % DONE_BARS), (j / DONE_BARS) & 1u); };
-    const uint32_t n1s = (uint32_t)P.k1_slabs, n2s = (uint32_t)P.k2_slabs;
-    if (producer) {
-        float4 xa[8];
-        load_a1(0, xa);
-        for (uint32_t j = 0; j < n1s + n2s; j++) {
-            const uint32_t sa = sAst + (j % A_STAGES) * A_STAGE_BYTES;
-            if (j >= (uint32_t)A_STAGES) wait_done(j - A_STAGES);
-            if (j < n1s) {
-#pragma unroll
-                for (int u = 0; u < 8; u++) put_split(sa, u, xa[u]);
-                if (j + 1 < n1s) load_a1((int)j + 1, xa);
-            } else {
-                if (j == n1s) {  // GEMM2 reads GEMM1's accumulator: every GEMM1 MMA must have completed
-                    wait_done(n1s - 1);
-                    tc_fence_after();
-                }
-                stage_a2(sa, (int)(j - n1s));
-            }
-            fence_proxy_async();  // generic-proxy writes -> visible to the tensor-core (async) proxy
-            tc_fence_before();
-            mbar_arrive(sArdy + 8 * (j % A_STAGES));
-        }
-        wait_done(n1s + n2s - 1);  // the last slab's commit covers every MMA issued before it
-        tc_fence_after();
-    } else if (tid == MLP_PRODUCERS) {
-        auto issue_b = [&](uint32_t j) {
-            const bool g1 = j < n1s;
-            const int n_pad = g1 ? P.n1 : P.n2;
-            const uint32_t s = g1 ? j : j - n1s, bbytes = (uint32_t)n_pad * 128u;
-            const float* hi = (g1 ? P.w1_hi : P.w2_hi) + (size_t)s * n_pad * SLAB_K;
-            const float* lo = (g1 ? P.w1_lo : P.w2_lo) + (size_t)s * n_pad * SLAB_K;
-            const uint32_t bs = sBst + (j % B_STAGES) * B_STAGE_BYTES, bar = sFull + 8 * (j % B_STAGES);
-            if (j >= (uint32_t)B_STAGES) wait_done(j - B_STAGES);
-            mbar_expect_tx(bar, 2 * bbytes);
-            bulk_g2s(bs, hi, bbytes, bar);
-            bulk_g2s(bs + B_SLAB_BYTES, lo, bbytes, bar);
-        };
-        for (uint32_t j = 0; j < (uint32_t)(B_STAGES - 1) && j < n1s + n2s; j++) issue_b(j);
-        for (uint32_t j = 0; j < n1s + n2s; j++) {
-            const bool g1 = j < n1s;
-            const uint32_t idesc = idesc_tf32(TILE_M, g1 ? P.n1 : P.n2);
-            const uint32_t acc = tmem + (g1 ? 0u : (uint32_t)ACC2_COL);
-            const uint32_t first = g1 ? 0u : n1s;  // first slab of this GEMM overwrites the accumulator
-            mbar_wait(sArdy + 8 * (j % A_STAGES), (j / A_STAGES) & 1u);
-            mbar_wait(sFull + 8 * (j % B_STAGES), (j / B_STAGES) & 1u);
-            tc_fence_after();
-            const uint32_t aHi = sAst + (j % A_STAGES) * A_STAGE_BYTES, aLo = aHi + A_SLAB_BYTES;
-            const uint32_t bHi = sBst + (j % B_STAGES) * B_STAGE_BYTES, bLo = bHi + B_SLAB_BYTES;
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++) {  // 4 k-steps of 8 tf32 (32 bytes) per 128-byte slab row
-                const uint32_t o = kk * 32;
-                umma_tf32(acc, smem_desc_sw128(aHi + o), smem_desc_sw128(bHi + o), idesc, (j != first || kk != 0) ? 1u : 0u);
-                umma_tf32(acc, smem_desc_sw128(aLo + o), smem_desc_sw128(bHi + o), idesc, 1u);
-                umma_tf32(acc, smem_desc_sw128(aHi + o), smem_desc_sw128(bLo + o), idesc, 1u);
-            }
-            umma_commit(sDone + 8 * (j % DONE_BARS));
-            if (j + B_STAGES - 1 < n1s + n2s) issue_b(j + B_STAGES - 1);
-        }
-    }
-
-    // ---------------- epilogue 2: LayerNorm(ReLU(acc2 + b2)) -> shared tile -> coalesced global stores ----
-    if (producer) {
-        const int H = P.h2;
-        auto lds4 = [](uint32_t a) {
-            float4 v;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-            return v;
-        };
-        // x = ReLU(acc + b2) for 16 columns starting at c0 (columns >= H come out as 0: zero weights, zero bias)
-        auto load_x = [&](int c0, float* x) {
-            tmem_ld16(tmem + lane_base + (uint32_t)(ACC2_COL + c0), x);
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const float4 b = lds4(sPar + (c0 + 4 * q) * 4);
-                x[4 * q] = fmaxf(x[4 * q] + b.x, 0.f), x[4 * q + 1] = fmaxf(x[4 * q + 1] + b.y, 0.f);
-                x[4 * q + 2] = fmaxf(x[4 * q + 2] + b.z, 0.f), x[4 * q + 3] = fmaxf(x[4 * q + 3] + b.w, 0.f);
-            }
-        };
-        float sum = 0.f;
-        for (int c0 = 0; c0 < H; c0 += 16) {
-            float x[16];
-            load_x(c0, x);
-#pragma unroll
-            for (int i = 0; i < 16; i++) sum += x[i];  // padding columns contribute exact zeros
-        }
-        const float mean = sum / (float)H;
-        float sq = 0.f;
-        for (int c0 = 0; c0 < H; c0 += 16) {
-            float x[16];
-            load_x(c0, x);
-#pragma unroll
-            for (int i = 0; i < 16; i++)
-                if (c0 + i < H) sq += (x[i] - mean) * (x[i] - mean);
-        }
-        const float rstd = rsqrtf(sq / (float)H + 1e-5f);  // haiku LayerNorm: biased variance, eps = 1e-5
-        // the B stages are idle now (all MMAs done, all bulk copies consumed): use them as the output tile
-        const uint32_t sOut = sBst;
-        for (int c0 = 0; c0 < H; c0 += 16) {
-            float x[16];
-            load_x(c0, x);
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                if (c0 + 4 * q < H) {  // H is a multiple of 4
-                    const float4 sc = lds4(sPar + (MAX_N + c0 + 4 * q) * 4), of = lds4(sPar + (2 * MAX_N + c0 + 4 * q) * 4);
-                    const float y0 = (x[4 * q] - mean) * rstd * sc.x + of.x, y1 = (x[4 * q + 1] - mean) * rstd * sc.y + of.y;
-                    const float y2 = (x[4 * q + 2] - mean) * rstd * sc.z + of.z, y3 = (x[4 * q + 3] - mean) * rstd * sc.w + of.w;
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(sOut + (tid * OUT_PITCH + c0 + 4 * q) * 4), "f"(y0), "f"(y1),
-                                 "f"(y2), "f"(y3) : "memory");
-                }
-            }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(MLP_PRODUCERS) : "memory");  // producers only
-        const int rows_here = min(TILE_M, P.rows - row0);
-        const int q_per_row = H / 4;
-        float4* out4 = reinterpret_cast<float4*>(P.out + (size_t)row0 * H);
-        for (int i = tid; i < rows_here * q_per_row; i += MLP_PRODUCERS) {
-            const int r = i / q_per_row, q = i - r * q_per_row;
-            out4[i] = lds4(sOut + (r * OUT_PITCH + 4 * q) * 4);  // consecutive threads -> consecutive 16-byte chunks of the output
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
-}
-
-// ---- the same update as a persistent, three-role kernel ------------------------------------------
-// One CTA per SM walks over tiles (tile = blockIdx.x, += gridDim.x).  Roles:
-//   warps 0-3  producers: stage the A operand slab by slab (GEMM1: gathered rows; GEMM2: ReLU(acc1 + b1) out of TMEM);
-//   warp  4    one lane issues the weight copies (TMA bulk) and the MMAs;
-//   warps 5-8  epilogue: LayerNorm(ReLU(acc2 + b2)) out of TMEM straight to global memory.
-// With the epilogue on its own warps, the producers go from the last GEMM2 slab of a tile directly to the first GEMM1
-// slab of the next one, so the tensor pipe keeps running through the epilogue, the TMEM allocation, the barrier setup
-// and the parameter staging that the one-tile kernel pays per tile.  Slabs are numbered globally (J) across tiles, so
-// the stage / barrier parities of the one-tile kernel carry over unchanged; two more barriers hand acc2 back and forth:
+// One persistent CTA per SM walks over tiles of 128 rows (tile = blockIdx.x, += gridDim.x).  Roles:
+//   warps 0-7  producers: stage the A operand unit by unit (GEMM1: gathered rows; GEMM2: ReLU(acc1 + b1) out of TMEM);
+//   warp  8    one elected lane issues the weight copies (TMA bulk) and the MMAs;
+//   warps 9-12 epilogue: LayerNorm(ReLU(acc2 + b2)) out of TMEM straight to global memory.
+// Slabs are numbered globally (J) across tiles, so stage and barrier parities simply run on; two barriers hand acc2
+// back and forth:
 //   sAccFull (tcgen05.commit after the last slab of a tile) -> epilogue may read acc2,
 //   sAccFree (128 epilogue threads, after their last TMEM read) -> the issuer may overwrite acc2 (first GEMM2 MMA of
 //   the next tile).  acc1 needs no barrier: the producers read it (GEMM2 staging of tile t) before they stage, in
 //   program order, the GEMM1 slabs whose MMAs overwrite it.
-// Eight producer warps: two threads per row, each staging half of a slab (16 of its 32 columns).  A producer warp is
-// latency-bound (gather -> split -> swizzled stores, ~425 instructions per slab with four warps: measured 2.3x the MMA
-// time of a slab, tensor pipe 43 % busy); with eight, staging a slab takes about as long as its twelve MMAs.
+// (Round 1 also shipped two predecessors of this kernel -- one tile per CTA, and a persistent kernel with the A operand
+// staged in shared memory -- behind environment switches; they are retired, see git history and profiles/r01_gnn_*.)
 static constexpr int MLPP_PRODUCERS = 256;
 static constexpr int MLPP_THREADS = MLPP_PRODUCERS + 32 + 128;
-
-// CL > 1: the CTAs of a cluster of CL run their tiles in lock step and share the weight stream.  Each CTA requests 1 / CL of
-// every weight slab and the copy engine multicasts it into the same stage of all CL CTAs, so the L2 -> SM weight traffic
-// (85 % of what the kernel reads: every tile needs all 1.38 MB of slab images) drops by CL.  A weight stage is written by
-// all CTAs of the cluster, so it may only be refilled when the MMAs of ALL of them have drained it: every slab's
-// tcgen05.commit is also multicast to `sFreeB` (count CL) of every CTA.  Every CTA of a cluster runs the same number of
-// tiles (tiles past the end gather the last row and store nothing).
-template <int CL>
-__global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_kernel(const MlpArgs P)
-{
-    static_assert(CL == 1 || CL == 2 || CL == 4, "cluster size");
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t sAst = base;
-    const uint32_t sBst = base + A_STAGES * A_STAGE_BYTES;
-    const uint32_t sFull = sBst + B_STAGES * B_STAGE_BYTES;
-    const uint32_t sDone = sFull + 8 * B_STAGES;
-    const uint32_t sArdy = sDone + 8 * DONE_BARS;
-    const uint32_t sAccFull = sArdy + 8 * A_STAGES;
-    const uint32_t sAccFree = sAccFull + 8;
-    const uint32_t sFreeB = sAccFree + 8;
-    const uint32_t sTmem = sFreeB + 8 * DONE_BARS;
-    const uint32_t sPar = sFull + BAR_BYTES;
-    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5;
-    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // the same value, provably warp-uniform
-    const bool producer = tid < MLPP_PRODUCERS;
-    const bool epilogue = tid >= MLPP_PRODUCERS + 32;
-    const int prow = tid & (TILE_M - 1);  // producers: row of the tile (two threads per row)
-    const int part = tid >> 7;            // producers: which half of a slab's 32 columns
-    const int ntiles = (P.rows + TILE_M - 1) / TILE_M;
-    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...; in a cluster every CTA runs the count of the first one
-    const uint32_t my_tiles = CL > 1 ? (uint32_t)((ntiles + (int)gridDim.x - 1) / (int)gridDim.x)
-                                     : ((int)blockIdx.x < ntiles ? (uint32_t)((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) : 0u);
-    constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
-
-    if (tid == 0) {
-        for (int i = 0; i < B_STAGES; i++) mbar_init(sFull + 8 * i, 1);
-        for (int i = 0; i < DONE_BARS; i++) mbar_init(sDone + 8 * i, 1);
-        for (int i = 0; i < A_STAGES; i++) mbar_init(sArdy + 8 * i, MLPP_PRODUCERS / 32);
-        for (int i = 0; i < DONE_BARS; i++) mbar_init(sFreeB + 8 * i, CL);
-        mbar_init(sAccFull, 1);
-        mbar_init(sAccFree, 128);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < MAX_N; i += MLPP_THREADS) {
-        const bool in = i < P.h2;
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + i * 4), "f"(i < P.n2 ? __ldg(P.b2 + i) : 0.f) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + (MAX_N + i) * 4), "f"(in ? __ldg(P.ln_scale + i) : 0.f) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPar + (2 * MAX_N + i) * 4), "f"(in ? __ldg(P.ln_offset + i) : 0.f) : "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (CL > 1) cluster_sync_all();  // no multicast copy or commit may reach a CTA whose barriers are not initialised yet
-    tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + (sTmem - base));
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;  // a warp reaches the TMEM lane quarter warp % 4
-    const uint32_t n1s = (uint32_t)P.k1_slabs, n2s = (uint32_t)P.k2_slabs, S = n1s + n2s;
-    auto wait_done = [&](uint32_t J) { mbar_wait(sDone + 8 * (J % DONE_BARS), (J / DONE_BARS) & 1u); };
-
-    if (producer) {
-        const int kA = P.d[0] + P.d[1] + P.d[2];
-        auto put_split = [&](uint32_t stage_base, int u, float4 x) {
-            float4 hi, lo;
-            hi.x = round_tf32(x.x), hi.y = round_tf32(x.y), hi.z = round_tf32(x.z), hi.w = round_tf32(x.w);
-            lo.x = residual_tf32(x.x, hi.x), lo.y = residual_tf32(x.y, hi.y), lo.z = residual_tf32(x.z, hi.z), lo.w = residual_tf32(x.w, hi.w);
-            const uint32_t off = sw128_off(prow, u);
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + off), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(stage_base + A_SLAB_BYTES + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
-        };
-        const float* rp[3] = {nullptr, nullptr, nullptr};
-        auto set_rows = [&](int tile) {
-            const int my_row = min(tile * TILE_M + prow, P.rows - 1);  // rows past the end re-read the last row; never stored
-#pragma unroll
-            for (int j = 0; j < 3; j++)
-                if (P.d[j] > 0) {
-                    const int r = P.idx[j] ? __ldg(P.idx[j] + my_row) : my_row;
-                    rp[j] = P.src[j] + (size_t)r * P.d[j];
-                }
-        };
-        auto load_a1 = [&](int s, float4* x) {
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int col = s * SLAB_K + (part * 4 + u) * 4;
-                x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (col < kA) {
-                    const float* p = col < P.d[0] ? rp[0] + col : col < P.d[0] + P.d[1] ? rp[1] + (col - P.d[0]) : rp[2] + (col - P.d[0] - P.d[1]);
-                    x[u] = __ldg(reinterpret_cast<const float4*>(p));
-                }
-            }
-        };
-        auto stage_a2 = [&](uint32_t stage_base, int s) {
-            {
-                const int half = part;
-                const int c0 = s * SLAB_K + half * 16;
-                float v[16];
-                if (c0 < P.n1) {
-                    tmem_ld16(tmem + lane_base + (uint32_t)c0, v);
-#pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i] + __ldg(P.b1 + c0 + i), 0.f);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = 0.f;
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++) put_split(stage_base, half * 4 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-            }
-        };
-        // gathered rows travel two slabs ahead of their use (even slabs of a tile in xa0, odd ones in xa1): one slab
-        // of lead did not cover the L2 / HBM latency (11 % of the producers' stall samples sat on the first use)
-        float4 xa0[4], xa1[4];
-        uint32_t J = 0;
-        if (my_tiles > 0) {
-            set_rows(blockIdx.x);
-            load_a1(0, xa0);
-            load_a1(1, xa1);
-        }
-        for (uint32_t it = 0; it < my_tiles; it++) {
-            const int next_tile = (int)(blockIdx.x + (it + 1) * gridDim.x);
-            auto slab = [&](uint32_t j, float4* xa) {
-                const uint32_t sa = sAst + (J % A_STAGES) * A_STAGE_BYTES;
-                if (J >= (uint32_t)A_STAGES) wait_done(J - A_STAGES);
-                if (j < n1s) {
-#pragma unroll
-                    for (int u = 0; u < 4; u++) put_split(sa, part * 4 + u, xa[u]);
-                    if (j + 2 < n1s) load_a1((int)j + 2, xa);
-                } else {
-                    if (j == n1s) {  // GEMM2 reads GEMM1's accumulator: every GEMM1 MMA must have completed
-                        wait_done(J - 1);
-                        tc_fence_after();
-                        if (it + 1 < my_tiles) {  // the next tile's first slabs travel while this tile's GEMM2 is staged
-                            set_rows(next_tile);
-                            load_a1(0, xa0);
-                            load_a1(1, xa1);
-                        }
-                    }
-                    stage_a2(sa, (int)(j - n1s));
-                }
-                fence_proxy_async();
-                tc_fence_before();
-                __syncwarp();
-                if ((tid & 31) == 0) mbar_arrive(sArdy + 8 * (J % A_STAGES));  // one arrival per producer warp
-                J++;
-            };
-            for (uint32_t j = 0; j < S; j += 2) {
-                slab(j, xa0);
-                if (j + 1 < S) slab(j + 1, xa1);
-            }
-        }
-    } else if (warp_u == MLPP_PRODUCERS / 32) {
-        // The whole warp runs this loop with warp-uniform state and one ELECTED lane issues: in divergent code
-        // (`if (tid == ...)`) the compiler wraps every tcgen05.mma / commit / bulk copy in an elect-and-retry loop
-        // (ELECT, PLOP3, BRA.U.ANY: ~10 slow instructions per MMA), and that single thread, not the tensor pipe,
-        // set the pace of the kernel (measured: 83 % of its time in its own ~330 instructions per slab, tensor pipe
-        // 43 % busy).  No runtime modulo either: slab-in-tile counters run along.
-        const bool leader = elect_one();
-        const uint32_t total = my_tiles * S;
-        const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
-        constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version 1 | SWIZZLE_128B
-        auto desc = [&](uint32_t addr) -> uint64_t { return (uint64_t)DESC_HI << 32 | (((addr >> 4) & 0x3fffu) | (1u << 16)); };
-        const uint32_t idesc1 = idesc_tf32(TILE_M, P.n1), idesc2 = idesc_tf32(TILE_M, P.n2);
-        auto issue_b = [&](uint32_t J, uint32_t j) {  // j = J % S
-            const bool g1 = j < n1s;
-            const int n_pad = g1 ? P.n1 : P.n2;
-            const uint32_t s = g1 ? j : j - n1s, bbytes = (uint32_t)n_pad * 128u;
-            const float* hi = (g1 ? P.w1_hi : P.w2_hi) + (size_t)s * n_pad * SLAB_K;
-            const float* lo = (g1 ? P.w1_lo : P.w2_lo) + (size_t)s * n_pad * SLAB_K;
-            const uint32_t bs = sBst + (J % B_STAGES) * B_STAGE_BYTES, bar = sFull + 8 * (J % B_STAGES);
-            if (CL == 1) {
-                if (J >= (uint32_t)B_STAGES) wait_done(J - B_STAGES);
-                if (leader) {
-                    mbar_expect_tx(bar, 2 * bbytes);
-                    bulk_g2s(bs, hi, bbytes, bar);
-                    bulk_g2s(bs + B_SLAB_BYTES, lo, bbytes, bar);
-                }
-            } else {
-                if (J >= (uint32_t)B_STAGES) {  // the stage is free in every CTA of the cluster
-                    const uint32_t Jf = J - B_STAGES;
-                    mbar_wait(sFreeB + 8 * (Jf % DONE_BARS), (Jf / DONE_BARS) & 1u);
-                }
-                if (leader) {
-                    const uint32_t part = bbytes / CL, off = crank * part;  // n_pad * 128 / CL: a multiple of 512
-                    mbar_expect_tx(bar, 2 * bbytes);  // own part + the parts the other CTAs send
-                    bulk_g2s_multicast(bs + off, reinterpret_cast<const uint8_t*>(hi) + off, part, bar, CL_MASK);
-                    bulk_g2s_multicast(bs + B_SLAB_BYTES + off, reinterpret_cast<const uint8_t*>(lo) + off, part, bar, CL_MASK);
-                }
-            }
-        };
-        uint32_t jn = 0;  // slab-in-tile index of the next weight slab to request
-        for (uint32_t J = 0; J < (uint32_t)(B_STAGES - 1) && J < total; J++) {
-            issue_b(J, jn);
-            jn = jn + 1 == S ? 0 : jn + 1;
-        }
-        uint32_t j = 0, it = 0;
-        for (uint32_t J = 0; J < total; J++) {
-            const bool g1 = j < n1s;
-            const uint32_t idesc = g1 ? idesc1 : idesc2;
-            const uint32_t acc = tmem + (g1 ? 0u : (uint32_t)ACC2_COL);
-            const uint32_t first = g1 ? 0u : n1s;
-            mbar_wait(sArdy + 8 * (J % A_STAGES), (J / A_STAGES) & 1u);
-            mbar_wait(sFull + 8 * (J % B_STAGES), (J / B_STAGES) & 1u);
-            if (j == n1s && it > 0) mbar_wait(sAccFree, (it - 1) & 1u);  // the epilogue of the previous tile has read acc2
-            tc_fence_after();
-            const uint32_t aHi = sAst + (J % A_STAGES) * A_STAGE_BYTES, bHi = sBst + (J % B_STAGES) * B_STAGE_BYTES;
-            const uint64_t dAh = desc(aHi), dAl = desc(aHi + A_SLAB_BYTES), dBh = desc(bHi), dBl = desc(bHi + B_SLAB_BYTES);
-            if (leader) {
-#pragma unroll
-                for (int kk = 0; kk < 4; kk++) {  // 4 k-steps of 8 tf32 (32 bytes = 2 descriptor units) per 128-byte slab row
-                    umma_tf32(acc, dAh + 2 * kk, dBh + 2 * kk, idesc, (j != first || kk != 0) ? 1u : 0u);
-                    umma_tf32(acc, dAl + 2 * kk, dBh + 2 * kk, idesc, 1u);
-                    umma_tf32(acc, dAh + 2 * kk, dBl + 2 * kk, idesc, 1u);
-                }
-                umma_commit(sDone + 8 * (J % DONE_BARS));
-                if (CL > 1) umma_commit_multicast(sFreeB + 8 * (J % DONE_BARS), CL_MASK);
-                if (j == S - 1) umma_commit(sAccFull);
-            }
-            __syncwarp();
-            if (J + B_STAGES - 1 < total) {
-                issue_b(J + B_STAGES - 1, jn);
-                jn = jn + 1 == S ? 0 : jn + 1;
-            }
-            if (++j == S) j = 0, it++;
-        }
-        if (CL > 1) {  // every arrival the other CTAs still send to this one has landed before this CTA may exit
-            for (uint32_t J = total > (uint32_t)DONE_BARS ? total - DONE_BARS : 0u; J < total; J++)
-                mbar_wait(sFreeB + 8 * (J % DONE_BARS), (J / DONE_BARS) & 1u);
-        }
-    } else if (epilogue) {
-        const int H = P.h2;
-        const int erow = (warp & 3) * 32 + (tid & 31);  // row of the tile = TMEM lane
-        auto lds4 = [](uint32_t a) {
-            float4 v;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-            return v;
-        };
-        auto load_x = [&](int c0, float* x) {
-            tmem_ld16(tmem + lane_base + (uint32_t)(ACC2_COL + c0), x);
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const float4 b = lds4(sPar + (c0 + 4 * q) * 4);
-                x[4 * q] = fmaxf(x[4 * q] + b.x, 0.f), x[4 * q + 1] = fmaxf(x[4 * q + 1] + b.y, 0.f);
-                x[4 * q + 2] = fmaxf(x[4 * q + 2] + b.z, 0.f), x[4 * q + 3] = fmaxf(x[4 * q + 3] + b.w, 0.f);
-            }
-        };
-        for (uint32_t it = 0; it < my_tiles; it++) {
-            const int tile = (int)(blockIdx.x + it * gridDim.x);
-            mbar_wait_relaxed(sAccFull, it & 1u);
-            tc_fence_after();
-            float sum = 0.f;
-            for (int c0 = 0; c0 < H; c0 += 16) {
-                float x[16];
-                load_x(c0, x);
-#pragma unroll
-                for (int i = 0; i < 16; i++) sum += x[i];
-            }
-            const float mean = sum / (float)H;
-            float sq = 0.f;
-            for (int c0 = 0; c0 < H; c0 += 16) {
-                float x[16];
-                load_x(c0, x);
-#pragma unroll
-                for (int i = 0; i < 16; i++)
-                    if (c0 + i < H) sq += (x[i] - mean) * (x[i] - mean);
-            }
-            const float rstd = rsqrtf(sq / (float)H + 1e-5f);
-            const int row = tile * TILE_M + erow;
-            float* orow = P.out + (size_t)min(row, P.rows - 1) * H;
-            for (int c0 = 0; c0 < H; c0 += 16) {
-                float x[16];
-                load_x(c0, x);
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (c0 + 4 * q < H && row < P.rows) {  // H is a multiple of 4
-                        const float4 sc = lds4(sPar + (MAX_N + c0 + 4 * q) * 4), of = lds4(sPar + (2 * MAX_N + c0 + 4 * q) * 4);
-                        float4 y;
-                        y.x = (x[4 * q] - mean) * rstd * sc.x + of.x, y.y = (x[4 * q + 1] - mean) * rstd * sc.y + of.y;
-                        y.z = (x[4 * q + 2] - mean) * rstd * sc.z + of.z, y.w = (x[4 * q + 3] - mean) * rstd * sc.w + of.w;
-                        *reinterpret_cast<float4*>(orow + c0 + 4 * q) = y;
-                    }
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(sAccFree);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (CL > 1) cluster_sync_all();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
-}
 
 // ---- the same update with the A operand in TENSOR MEMORY ---------------------------------------------------------
 // ncu of the kernel above (profiles/r01_gnn_mlp_ln_summary.md): the shared-memory data pipe (128 B per clock and SM) is what

@@ -1,5 +1,6 @@
 // instance.h -- host-side CNF instance: DIMACS reader, clause CSR, occurrence CSR, HBM upload.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -43,6 +44,7 @@ struct sls_instance {
     int device = -1;
     void* d_blob = nullptr;   // one allocation holding every device array
     size_t blob_bytes = 0;
+    std::atomic<int> solver_refs{0};  // live sls_solver objects pointing into d_blob (the image may not move meanwhile)
 };
 
 // Makes every instance of a batch resident on the current device (defined in api.cu): images of the missing ones

@@ -490,9 +490,12 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
                 if (ALGO != ALGO_MOSER_SINGLE || j < 3) {
                     const uint32_t lit = selp(j == 0, q0.x, selp(j == 1, q0.y, q0.z));
                     // lib.rs:37-41.  Every lane writes the same new word: no lane-0 region, no atomic (the word is
-                    // read again only after the barrier that closes the re-evaluation)
+                    // read again only after the barrier that closes the re-evaluation).  The barrier between the read
+                    // and the write keeps this correct when the lanes do not run in lock step.
                     const uint32_t wa = sA + (lit >> 6) * 4u;
-                    sts32(wa, lds32(wa) ^ (1u << ((lit >> 1) & 31u)));
+                    const uint32_t old = lds32(wa);
+                    __syncwarp();
+                    sts32(wa, old ^ (1u << ((lit >> 1) & 31u)));
                     if (COUNT_FLIPS) flips++;
                     // no barrier: the re-evaluation never reads the flipped variable itself, and it ends with one
                     update_var(selp(j == 0, q1.x, selp(j == 1, q1.z, q2.x)), selp(j == 0, q1.y, selp(j == 1, q1.w, q2.y)), (lit & 1u) ^ 1u);

@@ -198,9 +198,11 @@ __device__ __forceinline__ void walk_k3h_body(const WalkArgs& A, uint32_t block,
                 }
                 __syncwarp();
             };
-            auto toggle = [&](uint32_t lit) {  // every lane writes the same new word
+            auto toggle = [&](uint32_t lit) {  // every lane writes the same new word: all lanes read before any lane writes
                 uint32_t* const wa = pA + (lit >> 6);
-                __stcg(wa, __ldcg(wa) ^ (1u << ((lit >> 1) & 31u)));
+                const uint32_t old = __ldcg(wa);
+                __syncwarp();
+                __stcg(wa, old ^ (1u << ((lit >> 1) & 31u)));
                 log_flip(lit >> 1);
             };
 

@@ -49,10 +49,49 @@ def _find(params, name):
     return params[hits[0]]
 
 
+def _natural_key(name: str):
+    """'scope/linear_10' -> ('scope/linear', 10); a module without a numeric suffix is number 0 (haiku's first)."""
+    head, _, tail = name.rpartition("_")
+    return (head, int(tail)) if head and tail.isdigit() else (name, 0)
+
+
+def resolve_modules(params, num_steps: int):
+    """Map the network's modules to the keys of ``params``.  First by haiku's names (:func:`haiku_names`); if a file
+    uses other names (another scope, another haiku version's numbering), by SHAPE AND CREATION ORDER: the modules
+    holding ``w`` / ``b`` (Linear) and those holding ``scale`` / ``offset`` (LayerNorm) are taken in natural order of
+    their numeric suffixes -- haiku numbers modules in construction order (model.py:13-16, :37-60, :144) and tree
+    operations sort keys alphabetically, so dict order itself is not trusted -- and assigned to edge embed, node
+    embed, per step edge l1 / l2, node l1 / l2, readout (LayerNorm: per step edge, node).  pack_params validates every
+    shape afterwards, so a wrong guess is an error, never a silently permuted model."""
+    names = haiku_names(num_steps)
+    try:
+        flat = [names["edge_embed"], names["node_embed"], names["readout"]]
+        for st in names["steps"]:
+            for kind in ("edge", "node"):
+                flat += [st[kind]["l1"], st[kind]["l2"], st[kind]["ln"]]
+        for nm in flat:
+            _find(params, nm)
+        return names
+    except ValueError:
+        pass
+    lin = sorted((k for k in params if "w" in params[k]), key=_natural_key)
+    lns = sorted((k for k in params if "scale" in params[k]), key=_natural_key)
+    if len(lin) != 3 + 4 * num_steps or len(lns) != 2 * num_steps:
+        raise ValueError(f"cannot map parameter modules: found {len(lin)} Linear and {len(lns)} LayerNorm modules, the "
+                         f"interaction network with {num_steps} steps has {3 + 4 * num_steps} and {2 * num_steps}")
+    out = {"edge_embed": lin[0], "node_embed": lin[1], "steps": [], "readout": lin[2 + 4 * num_steps]}
+    for t in range(num_steps):
+        out["steps"].append({
+            "edge": {"ln": lns[2 * t], "l1": lin[2 + 4 * t], "l2": lin[3 + 4 * t]},
+            "node": {"ln": lns[2 * t + 1], "l1": lin[4 + 4 * t], "l2": lin[5 + 4 * t]},
+        })
+    return out
+
+
 def pack_params(params, num_steps: int):
     """Flatten a haiku parameter dict into the float32 blob sls_gnn_model_create expects; returns
     (blob, embed_dim, h1, h2).  Shapes are validated against the interaction-network definition."""
-    names = haiku_names(num_steps)
+    names = resolve_modules(params, num_steps)
     f32 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float32))
     parts = []
     ee, ne = _find(params, names["edge_embed"]), _find(params, names["node_embed"])
@@ -206,7 +245,9 @@ def get_network_definition(network_type, graph_representation="LCG"):
 class _Transformed:
     """What ``hk.without_apply_rng(hk.transform(network_definition))`` gives the reference's call sites
     (evaluate_with_given_params.py:97-101): an object whose ``apply(params, graph)`` returns decoded_nodes [N,1].
-    The packed device copy of ``params`` is cached per parameter object."""
+    The packed device copy of the last ``params`` is cached together with a reference to the object and a fingerprint of
+    its arrays: the cache hits only for the very same object (``is``) with unchanged contents, so neither a recycled
+    address nor an in-place update can make the forward run with stale weights."""
 
     def __init__(self, fn):
         import functools
@@ -218,15 +259,30 @@ class _Transformed:
             f = f.func
         if f is not network_definition_interaction_lcg:
             raise ValueError("only get_network_definition('interaction', LCG) is supported")
-        self._cache = {}
+        self._params = None   # the cached object itself (keeps it alive: its address cannot be reused)
+        self._print = None
+        self._net = None
+
+    @staticmethod
+    def _fingerprint(params):
+        """Cheap content check of a haiku parameter dict: shapes plus a strided sample and the sum of every array
+        (1.5 M floats: ~1 ms, against ~10 ms for re-packing and re-uploading the model)."""
+        out = []
+        for mod in sorted(params):
+            for name in sorted(params[mod]):
+                a = np.asarray(params[mod][name])
+                flat = a.reshape(-1)
+                out.append((mod, name, a.shape, float(flat.sum(dtype=np.float64)), flat[:: max(1, flat.size // 16)].tobytes()))
+        return out
 
     def apply(self, params, graph):
-        key = id(params)
-        net = self._cache.get(key)
-        if net is None:
-            self._cache.clear()
-            net = self._cache[key] = InteractionNetworkLCG(params, self.steps)
-        return net.apply(graph)
+        fp = self._fingerprint(params)
+        if self._net is None or self._params is not params or self._print != fp:
+            if self._net is not None:
+                self._net.close()
+            self._net = InteractionNetworkLCG(params, self.steps)
+            self._params, self._print = params, fp
+        return self._net.apply(graph)
 
 
 def transform(network_definition):

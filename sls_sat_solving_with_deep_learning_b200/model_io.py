@@ -65,12 +65,20 @@ class _Stub:
 
 
 class _Unpickler(pickle.Unpickler):
-    SAFE_NUMPY = ("numpy", "numpy.core.multiarray", "numpy._core.multiarray", "numpy.core.numeric", "numpy._core.numeric",
-                  "numpy.dtypes", "numpy.core._multiarray_umath", "numpy._core._multiarray_umath")
+    # exact (module, name) pairs an ndarray / scalar / dtype pickle refers to -- nothing else of numpy is reachable
+    # (numpy.testing, f2py and distutils hold callables that execute code)
+    SAFE_NUMPY = {
+        (mod, name)
+        for mod in ("numpy.core.multiarray", "numpy._core.multiarray")
+        for name in ("_reconstruct", "scalar", "_frombuffer")
+    } | {("numpy", "ndarray"), ("numpy", "dtype"),
+         ("numpy.core.numeric", "_frombuffer"), ("numpy._core.numeric", "_frombuffer")}
 
     def find_class(self, module, name):
-        if module in self.SAFE_NUMPY or module.startswith("numpy."):
+        if (module, name) in self.SAFE_NUMPY:
             return super().find_class(module, name)
+        if module == "numpy.dtypes" and name.endswith("DType") and name[:-5].isalnum():
+            return super().find_class(module, name)  # dtype classes (numpy >= 1.25 pickles e.g. Float32DType)
         if module in ("builtins", "collections", "functools") and name in (
             "dict", "list", "tuple", "set", "frozenset", "float", "int", "complex", "bool", "str", "bytes", "slice",
             "OrderedDict", "partial", "object", "range",

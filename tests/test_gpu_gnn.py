@@ -118,16 +118,11 @@ def test_many_tiles_per_persistent_cta():
     assert all(np.array_equal(a, b) for a, b in zip(probs, again))
 
 
-@pytest.mark.parametrize("cluster,kernel", [(2, "smem"), (4, "smem"), (2, "tmem")])
-def test_weight_multicast_clusters_are_bit_identical(cluster, kernel, monkeypatch):
-    # CTAs of a cluster share every weight slab (each requests 1 / cluster of it, the copy engine multicasts); rows, MMAs
+def test_weight_multicast_clusters_are_bit_identical(monkeypatch):
+    # the two CTAs of a cluster share every weight slab (each requests half of it, the copy engine multicasts); rows, MMAs
     # and their order per tile are unchanged, so the logits must not differ in a single bit -- for several tiles per
     # CTA, a ragged last wave (dummy tiles), and for a batch smaller than one cluster's worth of tiles
-    if kernel == "smem":  # A staged in shared memory: 3xTF32, clusters of 2 or 4
-        monkeypatch.setenv("SLS_B200_GNN_A_TMEM", "0")
-        monkeypatch.setenv("SLS_B200_GNN_PRECISION", "tf32x3")
-    else:                 # A in tensor memory, two bf16 pieces: clusters of 2
-        monkeypatch.setenv("SLS_B200_GNN_PRECISION", "bf16x2")
+    monkeypatch.setenv("SLS_B200_GNN_PRECISION", "bf16x2")
     for n_inst in (40, 1):
         insts = []
         for i in range(n_inst):
@@ -137,28 +132,10 @@ def test_weight_multicast_clusters_are_bit_identical(cluster, kernel, monkeypatc
         net = gnn.InteractionNetworkLCG(params)
         monkeypatch.setenv("SLS_B200_GNN_CLUSTER", "1")
         p1, d1 = net.probabilities(insts, return_decoded=True)
-        monkeypatch.setenv("SLS_B200_GNN_CLUSTER", str(cluster))
+        monkeypatch.setenv("SLS_B200_GNN_CLUSTER", "2")
         pc, dc = net.probabilities(insts, return_decoded=True)
         assert np.array_equal(d1, dc)
         assert all(np.array_equal(a, b) for a, b in zip(p1, pc))
-
-
-def test_a_operand_in_tensor_memory_equals_shared_memory_staging(monkeypatch):
-    # default kernel: split rows written to TMEM (tcgen05.st), MMAs with A from tensor memory; SLS_B200_GNN_A_TMEM=0: rows
-    # staged in shared memory.  Same products accumulated in the same order: identical logits
-    insts = []
-    for i in range(24):
-        n, m = 150 + 5 * (i % 4), 600 + 11 * (i % 7)
-        insts.append(eng.Instance.from_clauses(n, random_ksat(n, m, 3, seed=500 + i)))
-    params = go.init_params(seed=23, bias_scale=0.1)
-    net = gnn.InteractionNetworkLCG(params)
-    monkeypatch.setenv("SLS_B200_GNN_PRECISION", "tf32x3")  # the shared-memory kernels only exist in 3xTF32
-    monkeypatch.setenv("SLS_B200_GNN_A_TMEM", "1")
-    p1, d1 = net.probabilities(insts, return_decoded=True)
-    monkeypatch.setenv("SLS_B200_GNN_A_TMEM", "0")
-    p0, d0 = net.probabilities(insts, return_decoded=True)
-    assert np.array_equal(d1, d0)
-    assert all(np.array_equal(a, b) for a, b in zip(p1, p0))
 
 
 def test_bf16_pieces_and_3xtf32_agree_within_the_contract(monkeypatch):
