@@ -199,6 +199,12 @@ int sls_gnn_forward_graph(sls_gnn_model *m, uint64_t n_node, uint64_t n_edge, co
 int sls_gnn_forward_lcg(sls_gnn_model *m, sls_instance *const *insts, uint32_t n_inst, float *prob, float *decoded,
                         double *kernel_ms);
 int sls_gnn_launch_count(const sls_gnn_model *m);
+/* measurement only (no reference equivalent): with profiling on, every forward brackets its kernels with CUDA events by
+ * class and sls_gnn_get_profile returns the device milliseconds of the LAST forward (of its last chunk, for a chunked
+ * batch): ms[0] edge updates, ms[1] node updates, ms[2] segment sums, ms[3] everything else (embeddings, indices,
+ * readout).  The events serialise nothing but cost a few microseconds per launch: leave it off in timed runs. */
+int sls_gnn_set_profile(sls_gnn_model *m, int on);
+int sls_gnn_get_profile(const sls_gnn_model *m, double ms[4]);
 
 #ifdef __cplusplus
 }

@@ -175,6 +175,14 @@ class Instance:
         _check(lib().orc_instance_from_csr(n, len(clauses), row.ctypes.data, flat.ctypes.data, C.byref(h)))
         return cls(h)
 
+    @classmethod
+    def from_csr(cls, n: int, row_ptr, signed_lits) -> "Instance":
+        row = np.ascontiguousarray(row_ptr, dtype=np.uint64)
+        flat = np.ascontiguousarray(signed_lits, dtype=np.int32)
+        h = C.c_void_p()
+        _check(lib().orc_instance_from_csr(n, len(row) - 1, row.ctypes.data, flat.ctypes.data, C.byref(h)))
+        return cls(h)
+
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:
             _lib.orc_instance_free(self._h)

@@ -129,6 +129,8 @@ SYMBOLS = {
     "sls_gnn_forward_graph": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_double)]),
     "sls_gnn_forward_lcg": (C.c_int, [_vp, C.POINTER(_vp), C.c_uint32, _vp, _vp, C.POINTER(C.c_double)]),
     "sls_gnn_launch_count": (C.c_int, [_vp]),
+    "sls_gnn_set_profile": (C.c_int, [_vp, C.c_int]),
+    "sls_gnn_get_profile": (C.c_int, [_vp, C.POINTER(C.c_double)]),
 }
 
 _lib = None

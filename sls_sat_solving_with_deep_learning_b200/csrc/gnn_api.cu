@@ -95,6 +95,8 @@ struct sls_gnn_model {
     std::vector<void*> allocs;
     int launches = 0;
     bool prefer_tf32x3 = false;  // this model's default product when SLS_B200_GNN_PRECISION is unset (see sls_gnn_model_create)
+    bool profile = false;        // sls_gnn_set_profile: event pairs around every kernel class of a forward
+    double prof_ms[4] = {0, 0, 0, 0};
     // Activation workspace (edge / node feature ping-pong buffers and the two aggregates): one block, grown on
     // demand and kept across calls, so a repeated forward of the same batch shape allocates nothing.
     void* ws = nullptr;
@@ -141,6 +143,14 @@ int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& 
         const int u = k_in_slab >> 3, e = k_in_slab & 7;
         return (size_t)s * n_pad * SLAB_KB + (size_t)(n >> 3) * 512 + (size_t)(n & 7) * 64 + (size_t)((u ^ (n & 7)) << 3) + e;
     };
+    // GEMM1's A operand reaches tensor memory through tcgen05.st.16x256b (four lanes per row, see the kernel's producer): inside
+    // every 64-k slab the k-value 32 h + 8 j + 4 q + 2 b + par (unit h, lane j of the row's quad, 8-column repeat q, column b of
+    // the lane's pair, element par) sits at position 16 (2 h + q) + 4 j + 2 b + par of the MMA's k-order.  W1's slab images
+    // carry the same order; W2 (A staged thread = row out of the first accumulator) keeps the natural one.
+    auto w1_perm = [](int kk) {
+        const int h = kk >> 5, r = kk & 31, j = r >> 3, q = (r >> 2) & 1, b = (r >> 1) & 1, par = r & 1;
+        return 16 * (2 * h + q) + 4 * j + 2 * b + par;
+    };
     std::vector<uint16_t> w1b0((size_t)out.n1 * out.k1_slabs_bf * SLAB_KB, 0), w1b1(w1b0.size(), 0);
     std::vector<uint16_t> w2b0((size_t)out.n2 * out.k2_slabs_bf * SLAB_KB, 0), w2b1(w2b0.size(), 0);
     auto put_bf = [&](std::vector<uint16_t>& p0, std::vector<uint16_t>& p1, size_t ix, float w) {
@@ -155,7 +165,7 @@ int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& 
             const size_t ix = img_index(out.n1, k / SLAB_K, n, k % SLAB_K);
             w1h[ix] = hi;
             w1l[ix] = round_tf32_host(w - hi);
-            put_bf(w1b0, w1b1, img_index_bf(out.n1, k / SLAB_KB, n, k % SLAB_KB), w);
+            put_bf(w1b0, w1b1, img_index_bf(out.n1, k / SLAB_KB, n, w1_perm(k % SLAB_KB)), w);
         }
     p += (size_t)k1 * h1;
     std::copy(p, p + h1, b1.begin());
@@ -327,16 +337,28 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
 }
 
 // the whole forward on device-resident inputs; decoded_dev[N]
+//
+// Workspace (one block, rows of H floats unless stated):
+//   eA [E] | sent [N] | recv [N] | zero [1] | eB [E]     one row-addressable array: the node update reads its two aggregates
+//                                                         through row indices relative to eA (agg_index_kernel), which point at
+//                                                         a summed row (degree >= 2), straight at the single edge row (degree 1)
+//                                                         or at the zero row (degree 0: clause nodes send nothing, positive
+//                                                         literals receive nothing -- 2/3 of an LCG graph's (node, direction)
+//                                                         pairs, which round 1 wrote as zeros and read back)
+//   hA [N] | hB [N] | e0 [E x D] | h0 [N x D] | four int32 index arrays [N]
+// The new edges of step t are written to eA (t even) or eB (t odd); every kernel reads rows it does not write.
 int forward_device(sls_gnn_model* m, int64_t N, int64_t E, const float* d_nodes, const float* d_edges, const uint8_t* d_node_type,
                    const uint8_t* d_edge_type, const int32_t* d_send,
                    const int32_t* d_recv, const int64_t* d_sptr, const int32_t* d_sids, const int64_t* d_rptr, const int32_t* d_rids,
                    float* d_decoded, cudaEvent_t ev0, cudaEvent_t ev1)
 {
     const int D = m->embed, H = m->h2;
-    const size_t ew = std::max(D, H), hw = std::max(D, H);
-    auto part = [](int64_t rows, size_t width) { return (size_t)(std::max<int64_t>(rows, 1) * width * sizeof(float) + 255) & ~(size_t)255; };
-    const size_t be = part(E, ew), bh = part(N, hw), ba = part(N, H);
-    const size_t need = 2 * be + 2 * bh + 2 * ba;
+    if (2 * E + 2 * N + 1 > 0x7fffffffll) return sls_set_error_internal(SLS_ERR_ARG, "graph too large for one call");
+    auto a256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t rowsH = (size_t)(2 * E + 2 * N + 1);
+    const size_t b_e = a256(rowsH * H * 4), b_h = a256((size_t)std::max<int64_t>(N, 1) * H * 4), b_e0 = a256((size_t)std::max<int64_t>(E, 1) * D * 4),
+                 b_h0 = a256((size_t)std::max<int64_t>(N, 1) * D * 4), b_ix = a256((size_t)std::max<int64_t>(N, 1) * 4);
+    const size_t need = b_e + 2 * b_h + b_e0 + b_h0 + 4 * b_ix;
     if (need > m->ws_bytes) {
         dfree(m->ws);
         m->ws = nullptr, m->ws_bytes = 0;
@@ -344,43 +366,103 @@ int forward_device(sls_gnn_model* m, int64_t N, int64_t E, const float* d_nodes,
         m->ws_bytes = need;
     }
     char* base = static_cast<char*>(m->ws);
-    float *e = (float*)base, *e2 = (float*)(base + be), *h = (float*)(base + 2 * be), *h2 = (float*)(base + 2 * be + bh);
-    float *sent = (float*)(base + 2 * be + 2 * bh), *recv = (float*)(base + 2 * be + 2 * bh + ba);
+    float* eA = (float*)base;
+    float* sent = eA + (size_t)E * H;
+    float* recv = sent + (size_t)N * H;
+    float* zero = recv + (size_t)N * H;
+    float* eB = zero + H;
+    float* hA = (float*)(base + b_e);
+    float* hB = (float*)(base + b_e + b_h);
+    float* e0 = (float*)(base + b_e + 2 * b_h);
+    float* h0 = (float*)(base + b_e + 2 * b_h + b_e0);
+    int32_t* ix = (int32_t*)(base + b_e + 2 * b_h + b_e0 + b_h0);
+    int32_t *sidxA = ix, *ridxA = (int32_t*)((char*)ix + b_ix), *sidxB = (int32_t*)((char*)ix + 2 * b_ix), *ridxB = (int32_t*)((char*)ix + 3 * b_ix);
+
+    // optional per-class device times (sls_gnn_set_profile): 0 edge update, 1 node update, 2 segment sums, 3 everything else
+    struct Rec {
+        int cls;
+        cudaEvent_t a, b;
+    };
+    std::vector<Rec> recs;
+    auto timed = [&](int cls, auto&& launch) -> int {
+        if (!m->profile) {
+            launch();
+            return SLS_OK;
+        }
+        Rec r{cls, nullptr, nullptr};
+        G_TRY(cudaEventCreate(&r.a));
+        G_TRY(cudaEventCreate(&r.b));
+        G_TRY(cudaEventRecord(r.a));
+        launch();
+        G_TRY(cudaEventRecord(r.b));
+        recs.push_back(r);
+        return SLS_OK;
+    };
+    int rc = SLS_OK;
     if (ev0) G_TRY(cudaEventRecord(ev0));
-    if (E && d_edge_type)
-        embed_onehot_kernel<<<(unsigned)((E * D + 255) / 256), 256>>>(d_edge_type, m->edge_embed_w, m->edge_embed_b, e, E, D);
-    else if (E)
-        embed_kernel<<<(unsigned)((E * D + 255) / 256), 256>>>(d_edges, m->edge_embed_w, m->edge_embed_b, e, E, D);
-    if (N && d_node_type)
-        embed_onehot_kernel<<<(unsigned)((N * D + 255) / 256), 256>>>(d_node_type, m->node_embed_w, m->node_embed_b, h, N, D);
-    else if (N)
-        embed_kernel<<<(unsigned)((N * D + 255) / 256), 256>>>(d_nodes, m->node_embed_w, m->node_embed_b, h, N, D);
-    m->launches += 2;
+    if ((rc = timed(3, [&] {
+             cudaMemsetAsync(zero, 0, (size_t)H * 4);
+             if (E && d_edge_type)
+                 embed_onehot_kernel<<<(unsigned)((E * D + 255) / 256), 256>>>(d_edge_type, m->edge_embed_w, m->edge_embed_b, e0, E, D);
+             else if (E)
+                 embed_kernel<<<(unsigned)((E * D + 255) / 256), 256>>>(d_edges, m->edge_embed_w, m->edge_embed_b, e0, E, D);
+             if (N && d_node_type)
+                 embed_onehot_kernel<<<(unsigned)((N * D + 255) / 256), 256>>>(d_node_type, m->node_embed_w, m->node_embed_b, h0, N, D);
+             else if (N)
+                 embed_kernel<<<(unsigned)((N * D + 255) / 256), 256>>>(d_nodes, m->node_embed_w, m->node_embed_b, h0, N, D);
+             if (N) agg_index_kernel<<<(unsigned)((N + 255) / 256), 256>>>(d_sptr, d_sids, d_rptr, d_rids, N, E, sidxA, ridxA, sidxB, ridxB);
+         })))
+        return rc;
+    m->launches += 3;
+    const float *e = e0, *h = h0;
     int de = D, dn = D;
     for (int t = 0; t < m->num_steps; t++) {
+        const bool even = (t & 1) == 0;
+        float* e_new = even ? eA : eB;
+        float* h_new = even ? hA : hB;
         // edge update sees [edges | nodes[senders] | nodes[receivers]]  (jraph InteractionNetwork + concatenated_args)
-        int rc = launch_mlp(m, m->edge_mlp[t], e, nullptr, de, h, d_send, dn, h, d_recv, dn, E, e2);
-        if (rc) return rc;
-        std::swap(e, e2);
+        int lrc = SLS_OK;
+        if ((rc = timed(0, [&] { lrc = launch_mlp(m, m->edge_mlp[t], e, nullptr, de, h, d_send, dn, h, d_recv, dn, E, e_new); })) || (rc = lrc)) return rc;
+        e = e_new;
         de = H;
-        // node update sees [nodes | segment_sum(new edges, senders) | segment_sum(new edges, receivers)]
+        // node update sees [nodes | segment_sum(new edges, senders) | segment_sum(new edges, receivers)]; only the sums over two
+        // or more edges are materialised
         if (N) {
-            const unsigned blocks = (unsigned)((2 * N * 32 + 255) / 256);
-            segment_sum_kernel<<<blocks, 256>>>(e, d_sptr, d_sids, sent, d_rptr, d_rids, recv, N, H);
+            const int64_t per_block = 256 / (H / 4), blocks = (2 * N + per_block - 1) / per_block;
+            if ((rc = timed(2, [&] {
+                     if (H == 200)
+                         segment_sum_flat_kernel<50><<<(unsigned)blocks, 256>>>(e, d_sptr, d_sids, sent, d_rptr, d_rids, recv, N, H);
+                     else
+                         segment_sum_flat_kernel<0><<<(unsigned)blocks, 256>>>(e, d_sptr, d_sids, sent, d_rptr, d_rids, recv, N, H);
+                 })))
+                return rc;
             m->launches += 1;
         }
-        rc = launch_mlp(m, m->node_mlp[t], h, nullptr, dn, sent, nullptr, H, recv, nullptr, H, N, h2);
-        if (rc) return rc;
-        std::swap(h, h2);
+        if ((rc = timed(1, [&] {
+                 lrc = launch_mlp(m, m->node_mlp[t], h, nullptr, dn, eA, even ? sidxA : sidxB, H, eA, even ? ridxA : ridxB, H, N, h_new);
+             })) ||
+            (rc = lrc))
+            return rc;
+        h = h_new;
         dn = H;
     }
     if (N) {
-        readout_kernel<<<(unsigned)((N * 32 + 255) / 256), 256>>>(h, m->readout_w, m->readout_b, d_decoded, N, H);
+        if ((rc = timed(3, [&] { readout_kernel<<<(unsigned)((N * 32 + 255) / 256), 256>>>(h, m->readout_w, m->readout_b, d_decoded, N, H); }))) return rc;
         m->launches++;
     }
     G_TRY(cudaGetLastError());
     if (ev1) G_TRY(cudaEventRecord(ev1));
-    G_TRY(cudaDeviceSynchronize());
+    G_TRY(cudaStreamSynchronize(nullptr));
+    if (m->profile) {
+        for (double& x : m->prof_ms) x = 0.0;
+        for (Rec& r : recs) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, r.a, r.b);
+            m->prof_ms[r.cls] += ms;
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+    }
     return SLS_OK;
 }
 
@@ -629,7 +711,7 @@ extern "C" int sls_gnn_forward_lcg(sls_gnn_model* m, sls_instance* const* insts,
     if (!m || (n_inst && !insts)) return sls_set_error_internal(SLS_ERR_ARG, "NULL argument");
     size_t budget = (size_t)8 << 30;
     if (const char* e = std::getenv("SLS_B200_GNN_WS_MB")) budget = std::max<size_t>(1, (size_t)std::atoll(e)) << 20;
-    const size_t width = (size_t)std::max(m->embed, m->h2) * sizeof(float);
+    const size_t wH = (size_t)m->h2 * sizeof(float), wD = (size_t)m->embed * sizeof(float);
     if (kernel_ms) *kernel_ms = 0.0;
     int launches = 0;
     uint32_t begin = 0;
@@ -642,7 +724,8 @@ extern "C" int sls_gnn_forward_lcg(sls_gnn_model* m, sls_instance* const* insts,
             if (!insts[end]) return sls_set_error_internal(SLS_ERR_ARG, "NULL instance handle in batch");
             const slsb::HostInstance& h = insts[end]->host;
             const size_t nodes = 2 * (size_t)h.n + h.m, edges = h.lits.size() + h.n;
-            const size_t bytes = (2 * edges + 4 * nodes) * width;  // two edge buffers, two node buffers, two aggregates
+            // forward_device's workspace: two edge buffers, two aggregates and two node buffers of width H, the embeddings, indices
+            const size_t bytes = (2 * edges + 4 * nodes) * wH + (edges + nodes) * wD + 16 * nodes;
             if (end > begin && need + bytes > budget) break;
             need += bytes;
             v_cnt += h.n;
@@ -750,3 +833,17 @@ int forward_lcg_one(sls_gnn_model* m, sls_instance* const* insts, uint32_t n_ins
 }  // namespace
 
 extern "C" int sls_gnn_launch_count(const sls_gnn_model* m) { return m ? m->launches : 0; }
+
+extern "C" int sls_gnn_set_profile(sls_gnn_model* m, int on)
+{
+    if (!m) return sls_set_error_internal(SLS_ERR_ARG, "NULL argument");
+    m->profile = on != 0;
+    return SLS_OK;
+}
+
+extern "C" int sls_gnn_get_profile(const sls_gnn_model* m, double ms[4])
+{
+    if (!m || !ms) return sls_set_error_internal(SLS_ERR_ARG, "NULL argument");
+    for (int i = 0; i < 4; i++) ms[i] = m->prof_ms[i];
+    return SLS_OK;
+}

@@ -190,6 +190,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// the same load without the wait (the caller overlaps it with other work and calls tmem_wait_ld before touching v), and its
+// 32-column form
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]),
+          "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+        "%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]),
+          "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]),
+          "=f"(v[21]), "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]),
+          "=f"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // Round to the nearest TF32 value (10-bit mantissa), ties away from zero like cvt.rna.tf32.f32.  The tensor core ignores
 // the low 13 mantissa bits of an fp32 operand, so operands are rounded explicitly before they are staged.  sm_100 has no
 // conversion instruction for this: ptxas expands cvt.rna.tf32.f32 into the same add-and-mask plus an |x| < inf guard
@@ -275,6 +298,16 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r)
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// 16 TMEM lanes starting at the lane in taddr, 32 columns: per 8-column repeat c (registers 4c .. 4c+3) lane l supplies
+// {row l / 4: columns 8c + 2 (l % 4), + 1;  row l / 4 + 8: the same columns}   (cute SM100_TMEM_STORE_16dp256b4x).  No wait.
+__device__ __forceinline__ void tmem_st16x256b_x4(uint32_t taddr, const uint32_t* r)
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+
 // BF = true: the products are formed from two bf16 pieces per operand on kind::f16 (x = a0 + a1, w = b0 + b1; a0*b0 + a1*b0 +
 // a0*b1, fp32 accumulation) instead of 3xTF32.  A 128-byte weight row then holds 64 k-values and a unit 32 (two per TMEM
 // column), so every MMA covers twice the k-range in the same time: half the MMAs, weight bytes and barrier hand-overs per
@@ -348,31 +381,98 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
 
     if (producer) {
         const int kA = P.d[0] + P.d[1] + P.d[2];
-        const float* rp[3] = {nullptr, nullptr, nullptr};
-        // Row indices are read one tile ahead of the rows they address (nidx): at the GEMM1 -> GEMM2 hand-over the pointers of
-        // the next tile are formed from registers, not from a fresh load on the drain's critical path.
-        int nidx[3] = {0, 0, 0};
-        auto fetch_idx = [&](int tile) {
-            const int my_row = min(tile * TILE_M + prow, P.rows - 1);  // rows past the end re-read the last row; never stored
-#pragma unroll
-            for (int j = 0; j < 3; j++) nidx[j] = (P.d[j] > 0 && P.idx[j]) ? __ldg(P.idx[j] + my_row) : my_row;
-        };
-        auto set_rows = [&]() {  // pointers of the tile whose indices are in nidx
-#pragma unroll
-            for (int j = 0; j < 3; j++)
-                if (P.d[j] > 0) {
-                    rp[j] = P.src[j] + (size_t)nidx[j] * P.d[j];
-                    // The row is gathered slab by slab over the whole tile; ask L2 for all of it now (the two threads of a
-                    // row take alternate 128-byte lines).  Gathered rows come from HBM (the feature arrays are several
-                    // times the L2) and a register prefetch two slabs ahead did not cover that latency: measured 3.1 of
-                    // 24.6 ms per forward spent waiting for gathers.
-                    for (int o = (int)grp * 32; o < P.d[j]; o += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp[j] + o));
-                }
-        };
-        // segment widths that are multiples of 8 floats (every shipped layer: 32 and 200): a thread's 64 bytes of a slab are
-        // two whole 32-byte sectors, fetched with two 256-bit loads instead of four 128-bit ones
+        // segment widths that are multiples of 8 floats (every shipped layer: 32 and 200): a 32-byte piece of a row never
+        // straddles two segments and is fetched with one 256-bit load
         const bool wide = ((P.d[0] | P.d[1] | P.d[2]) & 7) == 0;
-        auto load_a1 = [&](int s, float4* x) {
+        // ---- GEMM1 operand, two gather geometries ------------------------------------------------------------------
+        // BF (default): FOUR LANES PER ROW.  Lane (r8 = lane / 4, jq = lane % 4) of producer warp w fetches, for its rows
+        // 32 (w % 4) + r8 + 8 i (i = 0..3), the 32 bytes [8 jq, 8 jq + 8) of the unit's 32 k-values: a load instruction of
+        // the warp touches 8 rows x 128 contiguous bytes = 8 lines.  With thread = row (the tf32 path below) it touched 32
+        // lines for the same bytes, and the L1 tag stage -- one line per cycle -- was what paced the kernel (~1000 tag
+        // cycles per slab next to 1250 MMA cycles).  The quads match tcgen05.st's 16x256b shape (lane l holds two 32-bit
+        // columns of rows l / 4 and l / 4 + 8 per 8-column repeat), so a unit goes to tensor memory with two stores of 16
+        // rows; the k-values inside a unit land in a permuted column order, which the host bakes into the W1 slab images
+        // (gnn_api.cu: w1_perm) -- the contraction does not care in which order k is summed as long as A and B agree.
+        // !BF (tf32x3): thread = row, 32x32b stores (unchanged).
+        const int lane = tid & 31;
+        const int jq = lane & 3, r8 = lane >> 2;
+        const int qrow0 = (warp & 3) * 32 + r8;  // BF: first of this lane's four rows inside the tile
+        const float* rp[3] = {nullptr, nullptr, nullptr};   // !BF: this thread's row in each source
+        int nidx[3] = {0, 0, 0};
+        int qidx[3][4], qnext[3][4];                        // BF: row indices of the current / next tile (sources x rows)
+        // Row indices are read one tile ahead of the rows they address: at the GEMM1 -> GEMM2 hand-over the pointers of
+        // the next tile are formed from registers, not from a fresh load on the drain's critical path.
+        auto fetch_idx = [&](int tile) {
+            if constexpr (BF) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int my_row = min(tile * TILE_M + qrow0 + 8 * i, P.rows - 1);  // rows past the end re-read the last row; never stored
+#pragma unroll
+                    for (int j = 0; j < 3; j++) qnext[j][i] = (P.d[j] > 0 && P.idx[j]) ? __ldg(P.idx[j] + my_row) : my_row;
+                }
+            } else {
+                const int my_row = min(tile * TILE_M + prow, P.rows - 1);
+#pragma unroll
+                for (int j = 0; j < 3; j++) nidx[j] = (P.d[j] > 0 && P.idx[j]) ? __ldg(P.idx[j] + my_row) : my_row;
+            }
+        };
+        auto set_rows = [&]() {  // the tile whose indices were fetched last becomes the current one
+            if constexpr (BF) {
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        qidx[j][i] = qnext[j][i];
+                        // The row is gathered unit by unit over the whole tile; ask L2 for all of it now (the eight lanes
+                        // that share a row -- four per producer group -- take alternate 128-byte lines).  Gathered rows come
+                        // from HBM (the feature arrays are several times the L2).
+                        if (P.d[j] > 0) {
+                            const float* row = P.src[j] + (size_t)qidx[j][i] * P.d[j];
+                            for (int o = ((int)grp * 4 + jq) * 32; o < P.d[j]; o += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+                        }
+                    }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+                    if (P.d[j] > 0) {
+                        rp[j] = P.src[j] + (size_t)nidx[j] * P.d[j];
+                        for (int o = (int)grp * 32; o < P.d[j]; o += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp[j] + o));
+                    }
+            }
+        };
+        // BF: x[i] = the 8 k-values [8 jq, 8 jq + 8) of unit (slab s, group grp) in row i of this lane
+        auto load_q = [&](int s, float (*x)[8]) {
+            const int col = s * SLABK + (int)grp * NV + 8 * jq;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) x[i][e] = 0.f;
+                if (col >= kA) continue;
+                if (wide) {
+                    const int sj = col < P.d[0] ? 0 : col < P.d[0] + P.d[1] ? 1 : 2;
+                    const int c = col - (sj == 0 ? 0 : sj == 1 ? P.d[0] : P.d[0] + P.d[1]);
+                    const int ri = sj == 0 ? qidx[0][i] : sj == 1 ? qidx[1][i] : qidx[2][i];
+                    const float* p = P.src[sj] + (size_t)ri * P.d[sj] + c;
+                    // no L1 allocation: each byte is read once, by one thread
+                    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                 : "=f"(x[i][0]), "=f"(x[i][1]), "=f"(x[i][2]), "=f"(x[i][3]), "=f"(x[i][4]), "=f"(x[i][5]), "=f"(x[i][6]),
+                                   "=f"(x[i][7])
+                                 : "l"(p));
+                } else {  // odd widths: element by element (a piece may straddle two segments)
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const int ce = col + e;
+                        if (ce < kA) {
+                            const int sj = ce < P.d[0] ? 0 : ce < P.d[0] + P.d[1] ? 1 : 2;
+                            const int c = ce - (sj == 0 ? 0 : sj == 1 ? P.d[0] : P.d[0] + P.d[1]);
+                            const int ri = sj == 0 ? qidx[0][i] : sj == 1 ? qidx[1][i] : qidx[2][i];
+                            x[i][e] = __ldg(P.src[sj] + (size_t)ri * P.d[sj] + c);
+                        }
+                    }
+                }
+            }
+        };
+        auto load_a1 = [&](int s, float4* x) {  // !BF: thread = row
             if (wide) {
 #pragma unroll
                 for (int u = 0; u < NQ; u += 2) {
@@ -380,8 +480,6 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                     x[u] = x[u + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (col < kA) {
                         const float* p = col < P.d[0] ? rp[0] + col : col < P.d[0] + P.d[1] ? rp[1] + (col - P.d[0]) : rp[2] + (col - P.d[0] - P.d[1]);
-                        // no L1 allocation: each byte is read once, by one thread (measured 16.90 -> 16.12 ms per forward; the same
-                        // hint on the segment sums' row reads costs 2 %: their sender / receiver warps do share lines)
                         asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                                      : "=f"(x[u].x), "=f"(x[u].y), "=f"(x[u].z), "=f"(x[u].w), "=f"(x[u + 1].x), "=f"(x[u + 1].y),
                                        "=f"(x[u + 1].z), "=f"(x[u + 1].w)
@@ -404,17 +502,15 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
         // lower k in the low half of a column; both pieces rounded to nearest even)
         // The split is register work and runs BEFORE the thread waits for its A stage; once the stage is free only the TMEM
         // store, its wait and the barrier arrival are left on the stage's turn-around path.
+        auto split_pair = [](float lo_k, float hi_k, uint32_t& a0, uint32_t& a1) {  // one packing conversion per pair and piece
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a0) : "f"(hi_k), "f"(lo_k));
+            const float re = lo_k - __uint_as_float(a0 << 16), ro = hi_k - __uint_as_float(a0 & 0xffff0000u);
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a1) : "f"(ro), "f"(re));
+        };
         auto pack_unit = [&](const float* v, uint32_t* r) {
             if constexpr (BF) {
 #pragma unroll
-                for (int i = 0; i < 16; i++) {  // one packing conversion per pair and piece (F2FP.BF16.PACK_AB)
-                    uint32_t a0, a1;
-                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a0) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
-                    const float re = v[2 * i] - __uint_as_float(a0 << 16), ro = v[2 * i + 1] - __uint_as_float(a0 & 0xffff0000u);
-                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a1) : "f"(ro), "f"(re));
-                    r[i] = a0;
-                    r[16 + i] = a1;
-                }
+                for (int i = 0; i < 16; i++) split_pair(v[2 * i], v[2 * i + 1], r[i], r[16 + i]);
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
@@ -424,77 +520,139 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                 }
             }
         };
+        // BF, GEMM1: the lane's four rows x four pairs -> register order of two tcgen05.st.16x256b.x4 (rows i = 0,1 go to TMEM
+        // lanes r8, r8 + 8 of the warp's quadrant, rows i = 2,3 to lanes 16 + r8, 24 + r8).  Per 8-column repeat c a lane
+        // supplies {row lo: columns 2 jq, 2 jq + 1; row hi: the same columns}; repeats 0-1 are the a0 block, 2-3 the a1 block.
+        auto pack_quads = [&](const float (*x)[8], uint32_t* r) {
+#pragma unroll
+            for (int hs = 0; hs < 2; hs++)
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    const int i = 2 * hs + rr;
+#pragma unroll
+                    for (int pp = 0; pp < 4; pp++) {
+                        uint32_t a0, a1;
+                        split_pair(x[i][2 * pp], x[i][2 * pp + 1], a0, a1);
+                        const int c = pp >> 1, b = pp & 1;
+                        r[16 * hs + 4 * c + 2 * rr + b] = a0;
+                        r[16 * hs + 8 + 4 * c + 2 * rr + b] = a1;
+                    }
+                }
+        };
         auto store_unit = [&](uint32_t U, const uint32_t* r) {
             if (U >= (uint32_t)TS_A_STAGES) wait_unit(U - TS_A_STAGES);
             tc_fence_after();
             tmem_st32(tmem + lane_base + (uint32_t)(TS_A_COL + 32 * (U % TS_A_STAGES)), r);
         };
+        auto store_quads = [&](uint32_t U, const uint32_t* r) {
+            if (U >= (uint32_t)TS_A_STAGES) wait_unit(U - TS_A_STAGES);
+            tc_fence_after();
+            const uint32_t a = tmem + lane_base + (uint32_t)(TS_A_COL + 32 * (U % TS_A_STAGES));
+            tmem_st16x256b_x4(a, r);
+            tmem_st16x256b_x4(a + (16u << 16), r + 16);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        };
         // tf32: even slabs of a tile in xa0, odd ones in xa1 (two slabs of lead); bf16: a slab lasts twice as long and holds
         // twice the registers, one buffer and one slab of lead
         constexpr int LEAD = BF ? 1 : 2;
-        float4 xa0[NQ], xa1[BF ? 1 : NQ];
+        float4 xa0[BF ? 1 : NQ], xa1[BF ? 1 : NQ];
+        float xq[BF ? 4 : 1][8];
         uint32_t J = 0;
+        auto first_loads = [&]() {
+            if constexpr (BF) {
+                load_q(0, xq);
+            } else {
+                load_a1(0, xa0);
+                load_a1(1, xa1);
+            }
+        };
         if (my_tiles > 0) {
             fetch_idx(blockIdx.x);
             set_rows();
-            load_a1(0, xa0);
-            if constexpr (!BF) load_a1(1, xa1);
+            first_loads();
             fetch_idx((int)(blockIdx.x + gridDim.x));
         }
+        auto publish = [&](uint32_t U) {  // the unit is in its A stage: hand it to the issuer
+            tc_fence_before();
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(sArdy + 8 * (U % TS_A_STAGES));
+            J++;
+        };
+        // GEMM2's operand comes out of GEMM1's accumulator: NV columns of this thread's TMEM lane, requested without waiting
+        // (zeros beyond the padded width)
+        float vg[NV];
+        auto request_acc1 = [&](uint32_t j2) {
+            const int c0 = (int)j2 * SLABK + (int)grp * NV;
+            if constexpr (BF) {
+                if (c0 + 32 <= P.n1)
+                    tmem_ld32_nowait(tmem + lane_base + (uint32_t)c0, vg);
+                else if (c0 < P.n1)
+                    tmem_ld16_nowait(tmem + lane_base + (uint32_t)c0, vg);
+            } else {
+                if (c0 < P.n1) tmem_ld16_nowait(tmem + lane_base + (uint32_t)c0, vg);
+            }
+        };
         for (uint32_t it = 0; it < my_tiles; it++) {
             const int next_tile = (int)(blockIdx.x + (it + 1) * gridDim.x);
-            auto slab = [&](uint32_t j, float4* xa) {
+            // ---- GEMM1: gathered rows
+            auto gemm1_unit = [&](uint32_t j, float4* xa) {
                 const uint32_t U = 2 * J + grp;
-                float v[NV];
                 uint32_t r[32];
-                if (j < n1s) {
+                if constexpr (BF) {
+                    pack_quads(xq, r);
+                    if (j + LEAD < n1s) load_q((int)j + LEAD, xq);
+                    store_quads(U, r);
+                } else {
+                    float v[NV];
 #pragma unroll
                     for (int u = 0; u < NQ; u++) v[4 * u] = xa[u].x, v[4 * u + 1] = xa[u].y, v[4 * u + 2] = xa[u].z, v[4 * u + 3] = xa[u].w;
                     pack_unit(v, r);
                     if (j + LEAD < n1s) load_a1((int)j + LEAD, xa);
-                } else {
-                    if (j == n1s) {  // GEMM2 reads GEMM1's accumulator: every GEMM1 MMA must have completed
-                        wait_unit(2 * J - 1);
-                        if (it + 1 < my_tiles) {
-                            set_rows();
-                            load_a1(0, xa0);
-                            if constexpr (!BF) load_a1(1, xa1);
-                            fetch_idx(next_tile + (int)gridDim.x);
-                        }
-                    }
-                    tc_fence_after();
-#pragma unroll
-                    for (int half = 0; half < NV / 16; half++) {
-                        const int c0 = (int)(j - n1s) * SLABK + (int)grp * NV + 16 * half;
-                        float* vh = v + 16 * half;
-                        if (c0 < P.n1) {
-                            tmem_ld16(tmem + lane_base + (uint32_t)c0, vh);
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                float4 b;
-                                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(sPar + (3 * MAX_N + c0 + 4 * q) * 4));
-                                vh[4 * q] = fmaxf(vh[4 * q] + b.x, 0.f), vh[4 * q + 1] = fmaxf(vh[4 * q + 1] + b.y, 0.f);
-                                vh[4 * q + 2] = fmaxf(vh[4 * q + 2] + b.z, 0.f), vh[4 * q + 3] = fmaxf(vh[4 * q + 3] + b.w, 0.f);
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; i++) vh[i] = 0.f;
-                        }
-                    }
-                    pack_unit(v, r);
+                    store_unit(U, r);
                 }
-                store_unit(U, r);
-                tc_fence_before();
-                __syncwarp();
-                if ((tid & 31) == 0) mbar_arrive(sArdy + 8 * (U % TS_A_STAGES));
-                J++;
+                publish(U);
             };
             if constexpr (BF) {
-                for (uint32_t j = 0; j < S; j++) slab(j, xa0);
+                for (uint32_t j = 0; j < n1s; j++) gemm1_unit(j, xa0);
             } else {
-                for (uint32_t j = 0; j < S; j += 2) {
-                    slab(j, xa0);
-                    if (j + 1 < S) slab(j + 1, xa1);
+                for (uint32_t j = 0; j < n1s; j += 2) {
+                    gemm1_unit(j, xa0);
+                    if (j + 1 < n1s) gemm1_unit(j + 1, xa1);
+                }
+            }
+            // ---- GEMM2: ReLU(acc1 + b1).  Every GEMM1 MMA must have completed; from then on the whole accumulator is there, so
+            // the request for the next unit's columns is in flight while this one is converted, stored and published, and the
+            // next tile's row pointers / first gathers are set up only after the first unit is on its way to the tensor pipe
+            // (measured: with that work and one TMEM round trip per unit on the critical path, the GEMM2 phase took 2.7x its
+            // MMA time and, chained with the epilogue through acc2, set the kernel's period)
+            wait_unit(2 * J - 1);
+            tc_fence_after();
+            request_acc1(0);
+            for (uint32_t j2 = 0; j2 < n2s; j2++) {
+                const uint32_t U = 2 * J + grp;
+                const int c0 = (int)j2 * SLABK + (int)grp * NV;
+                float v[NV];
+                uint32_t r[32];
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < NV; i += 4) {
+                    if (c0 + i < P.n1) {
+                        float4 b;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(sPar + (3 * MAX_N + c0 + i) * 4));
+                        v[i] = fmaxf(vg[i] + b.x, 0.f), v[i + 1] = fmaxf(vg[i + 1] + b.y, 0.f);
+                        v[i + 2] = fmaxf(vg[i + 2] + b.z, 0.f), v[i + 3] = fmaxf(vg[i + 3] + b.w, 0.f);
+                    } else {
+                        v[i] = v[i + 1] = v[i + 2] = v[i + 3] = 0.f;
+                    }
+                }
+                if (j2 + 1 < n2s) request_acc1(j2 + 1);
+                pack_unit(v, r);
+                store_unit(U, r);
+                publish(U);
+                if (j2 == 0 && it + 1 < my_tiles) {
+                    set_rows();
+                    first_loads();
+                    fetch_idx(next_tile + (int)gridDim.x);
                 }
             }
         }
@@ -594,54 +752,79 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
             return v;
         };
-        auto load_x = [&](int c0, float* x) {
-            tmem_ld16(tmem + lane_base + (uint32_t)(TS_ACC2_COL + c0), x);
+        // acc2 is read TWICE per tile, 32 columns per TMEM load, the next load in flight while a chunk is processed: once for the
+        // row statistics, once to normalise and store.  (Round 1 read it three times in 16-column loads, each followed by its
+        // own wait; the epilogue then took longer than GEMM1 and, chained with GEMM2 through acc2 -- GEMM2 of the next tile
+        // may only start when the epilogue has released the accumulator -- set the kernel's period.)
+        // One-pass statistics about a pivot: with d = x - c (c = the row's first value), mean = c + sum(d) / H and
+        // var = (sum(d^2) - sum(d)^2 / H) / H; the pivot keeps the subtraction benign (|mean - c| is of the order of the
+        // standard deviation), unlike the raw sum of squares.
+        const int NCH = (P.n2 + 31) / 32;  // chunks of 32 columns; the last one may hold 16
+        float xb[32];
+        auto request = [&](int ch) {
+            const int c0 = 32 * ch;
+            if (c0 + 32 <= P.n2)
+                tmem_ld32_nowait(tmem + lane_base + (uint32_t)(TS_ACC2_COL + c0), xb);
+            else
+                tmem_ld16_nowait(tmem + lane_base + (uint32_t)(TS_ACC2_COL + c0), xb);
+        };
+        auto bias_relu = [&](int c0, float* x) {  // x = ReLU(acc2 + b2) for the chunk in xb (columns past n2: untouched)
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const float4 b = lds4(sPar + (c0 + 4 * q) * 4);
-                x[4 * q] = fmaxf(x[4 * q] + b.x, 0.f), x[4 * q + 1] = fmaxf(x[4 * q + 1] + b.y, 0.f);
-                x[4 * q + 2] = fmaxf(x[4 * q + 2] + b.z, 0.f), x[4 * q + 3] = fmaxf(x[4 * q + 3] + b.w, 0.f);
+            for (int q = 0; q < 8; q++) {
+                if (c0 + 4 * q < P.n2) {
+                    const float4 b = lds4(sPar + (c0 + 4 * q) * 4);
+                    x[4 * q] = fmaxf(xb[4 * q] + b.x, 0.f), x[4 * q + 1] = fmaxf(xb[4 * q + 1] + b.y, 0.f);
+                    x[4 * q + 2] = fmaxf(xb[4 * q + 2] + b.z, 0.f), x[4 * q + 3] = fmaxf(xb[4 * q + 3] + b.w, 0.f);
+                }
             }
         };
         for (uint32_t it = 0; it < my_tiles; it++) {
             const int tile = (int)(blockIdx.x + it * gridDim.x);
             mbar_wait_relaxed(sAccFull, it & 1u);
             tc_fence_after();
-            float sum = 0.f;
-            for (int c0 = 0; c0 < H; c0 += 16) {
-                float x[16];
-                load_x(c0, x);
+            float sd = 0.f, sd2 = 0.f, pivot = 0.f;
+            request(0);
+            for (int ch = 0; ch < NCH; ch++) {
+                float x[32];
+                tmem_wait_ld();
+                bias_relu(32 * ch, x);
+                if (ch + 1 < NCH) request(ch + 1);
+                if (ch == 0) pivot = x[0];
 #pragma unroll
-                for (int i = 0; i < 16; i++) sum += x[i];
+                for (int i = 0; i < 32; i++)
+                    if (32 * ch + i < H) {
+                        const float d = x[i] - pivot;
+                        sd += d;
+                        sd2 = fmaf(d, d, sd2);
+                    }
             }
-            const float mean = sum / (float)H;
-            float sq = 0.f;
-            for (int c0 = 0; c0 < H; c0 += 16) {
-                float x[16];
-                load_x(c0, x);
-#pragma unroll
-                for (int i = 0; i < 16; i++)
-                    if (c0 + i < H) sq += (x[i] - mean) * (x[i] - mean);
-            }
-            const float rstd = rsqrtf(sq / (float)H + 1e-5f);
+            const float md = sd / (float)H, mean = pivot + md;
+            const float rstd = rsqrtf(fmaxf(sd2 / (float)H - md * md, 0.f) + 1e-5f);
             const int row = tile * TILE_M + erow;
             float* orow = P.out + (size_t)min(row, P.rows - 1) * H;
-            for (int c0 = 0; c0 < H; c0 += 16) {
-                float x[16];
-                load_x(c0, x);
+            request(0);
+            for (int ch = 0; ch < NCH; ch++) {
+                float x[32];
+                tmem_wait_ld();
+                bias_relu(32 * ch, x);
+                if (ch + 1 < NCH) {
+                    request(ch + 1);
+                } else {  // the last read of acc2 has landed: GEMM2 of the next tile may overwrite it while this chunk is stored
+                    tc_fence_before();
+                    mbar_arrive(sAccFree);
+                }
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (c0 + 4 * q < H && row < P.rows) {
-                        const float4 sc = lds4(sPar + (MAX_N + c0 + 4 * q) * 4), of = lds4(sPar + (2 * MAX_N + c0 + 4 * q) * 4);
+                for (int q = 0; q < 8; q++) {
+                    const int c = 32 * ch + 4 * q;
+                    if (c < H && row < P.rows) {
+                        const float4 sc = lds4(sPar + (MAX_N + c) * 4), of = lds4(sPar + (2 * MAX_N + c) * 4);
                         float4 y;
                         y.x = (x[4 * q] - mean) * rstd * sc.x + of.x, y.y = (x[4 * q + 1] - mean) * rstd * sc.y + of.y;
                         y.z = (x[4 * q + 2] - mean) * rstd * sc.z + of.z, y.w = (x[4 * q + 3] - mean) * rstd * sc.w + of.w;
-                        *reinterpret_cast<float4*>(orow + c0 + 4 * q) = y;
+                        *reinterpret_cast<float4*>(orow + c) = y;
                     }
                 }
             }
-            tc_fence_before();
-            mbar_arrive(sAccFree);
         }
     }
     tc_fence_before();
@@ -673,52 +856,75 @@ __global__ void embed_onehot_kernel(const uint8_t* __restrict__ type, const floa
     out[i] = w[(int)type[i / D] * D + c] + b[c];
 }
 
-// jraph.utils.segment_sum over a CSR of edge ids (edge order inside a segment = increasing edge id,
-// i.e. the order a sequential scatter-add visits them): out[v] = sum_{j in [ptr[v], ptr[v+1])} e[ids[j]]
-// One warp per node, 16-byte loads (lane l owns float4 l and l+32 of the row), edge ids fetched 32 at
-// a time and broadcast by shuffle so the row loads of consecutive edges are independent and in flight
-// together.  The additions of one output element happen in list order (deterministic).
-// Both sums of a node in one launch: warp 2v adds the rows of the edges node v sends, warp 2v+1 those it receives.  Nodes and
-// edges of an instance are contiguous in a batch, so the two sweeps over an instance's edge rows (5.4 MB at n=500) happen in
-// the same time window and the second one is served by L2; as two launches each sweep read all of e (1.4 GB for 256
-// instances) from HBM.  The order of additions inside each sum is unchanged.
-__global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restrict__ e, const int64_t* __restrict__ ptr0,
-                                                          const int32_t* __restrict__ ids0, float* __restrict__ out0,
-                                                          const int64_t* __restrict__ ptr1, const int32_t* __restrict__ ids1,
-                                                          float* __restrict__ out1, int64_t n_node, int H)
+// jraph.utils.segment_sum over a CSR of edge ids (edge order inside a segment = increasing edge id, i.e. the order a
+// sequential scatter-add visits them): out[v] = sum_{j in [ptr[v], ptr[v+1])} e[ids[j]], for both directions of every node in
+// one launch (pair 2v = the edges node v sends, pair 2v+1 = those it receives; nodes and edges of an instance are contiguous
+// in a batch, so the two sweeps over an instance's edge rows fall into the same time window and the second is served by L2).
+// ONE THREAD PER (pair, 16-byte column): consecutive threads read consecutive 16 bytes of the same edge row, every lane of a
+// warp has work (round 1's warp-per-pair form left 14 of 32 lanes idle on the second half of an 800-byte row), and a pair
+// with fewer than two edges is not summed at all: the node update reads the zero row or the edge row itself through
+// agg_index_kernel's indices.  Four row loads in flight per thread; the additions of an output element happen in list order
+// (deterministic, same values as a sequential scatter-add).
+// Q4 = float4 per row as a compile-time constant (50 for the shipped H = 200: the thread -> (pair, column) split is a
+// multiply-shift instead of a division), 0 = taken from H at run time.  A block serves 256 / q4 whole pairs.
+template <int Q4>
+__global__ void __launch_bounds__(256) segment_sum_flat_kernel(const float* __restrict__ e, const int64_t* __restrict__ ptr0,
+                                                               const int32_t* __restrict__ ids0, float* __restrict__ out0,
+                                                               const int64_t* __restrict__ ptr1, const int32_t* __restrict__ ids1,
+                                                               float* __restrict__ out1, int64_t n_node, int H)
 {
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t v = w >> 1;
-    const int lane = threadIdx.x & 31;
+    const uint32_t q4 = Q4 ? (uint32_t)Q4 : (uint32_t)H >> 2;  // float4 per row
+    const uint32_t per_block = 256u / q4;
+    const uint32_t lp = threadIdx.x / q4;
+    if (lp >= per_block) return;
+    const uint32_t q = threadIdx.x - lp * q4;
+    const int64_t pair = (int64_t)blockIdx.x * per_block + lp;
+    const int64_t v = pair >> 1;
     if (v >= n_node) return;
-    const bool second = (w & 1) != 0;
+    const bool second = (pair & 1) != 0;
     const int64_t* __restrict__ ptr = second ? ptr1 : ptr0;
+    const int64_t s = __ldg(ptr + v), end = __ldg(ptr + v + 1);
+    if (end - s < 2) return;
     const int32_t* __restrict__ ids = second ? ids1 : ids0;
-    float* __restrict__ out = second ? out1 : out0;
-    const int64_t s = ptr[v], t = ptr[v + 1];
-    const int q = H >> 2;  // float4 per row (H is a multiple of 4, at most 64 float4 = 256 columns)
-    const bool has0 = lane < q, has1 = lane + 32 < q;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-    for (int64_t base = s; base < t; base += 32) {
-        const int cnt = (int)min((int64_t)32, t - base);
-        const int32_t my_id = lane < cnt ? __ldg(ids + base + lane) : 0;
-#pragma unroll 8
-        for (int k = 0; k < cnt; k++) {
-            const int32_t id = __shfl_sync(0xffffffffu, my_id, k);
-            const float4* row = reinterpret_cast<const float4*>(e + (size_t)id * H);
-            if (has0) {
-                const float4 x = __ldg(row + lane);
-                a0.x += x.x, a0.y += x.y, a0.z += x.z, a0.w += x.w;
-            }
-            if (has1) {
-                const float4 x = __ldg(row + lane + 32);
-                a1.x += x.x, a1.y += x.y, a1.z += x.z, a1.w += x.w;
-            }
-        }
+    const float4* __restrict__ rows = reinterpret_cast<const float4*>(e) + q;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    // four edges per round, all four row loads issued before the first addition; a short last round re-reads the segment's
+    // last row (a cache hit) and leaves it out of the sum, so no round is a chain of dependent loads
+    for (int64_t k = s; k < end; k += 4) {
+        const int64_t last = end - 1;
+        const int32_t i0 = __ldg(ids + k), i1 = __ldg(ids + min(k + 1, last)), i2 = __ldg(ids + min(k + 2, last)), i3 = __ldg(ids + min(k + 3, last));
+        const float4 x0 = __ldg(rows + (size_t)i0 * q4), x1 = __ldg(rows + (size_t)i1 * q4), x2 = __ldg(rows + (size_t)i2 * q4),
+                     x3 = __ldg(rows + (size_t)i3 * q4);
+        a.x += x0.x, a.y += x0.y, a.z += x0.z, a.w += x0.w;
+        if (k + 1 < end) a.x += x1.x, a.y += x1.y, a.z += x1.z, a.w += x1.w;
+        if (k + 2 < end) a.x += x2.x, a.y += x2.y, a.z += x2.z, a.w += x2.w;
+        if (k + 3 < end) a.x += x3.x, a.y += x3.y, a.z += x3.z, a.w += x3.w;
     }
-    float4* o = reinterpret_cast<float4*>(out + (size_t)v * H);
-    if (has0) o[lane] = a0;
-    if (has1) o[lane + 32] = a1;
+    reinterpret_cast<float4*>((second ? out1 : out0) + (size_t)v * H)[q] = a;
+}
+
+// Row indices of a node's two aggregates in the array [eA (E rows) | sent (N) | recv (N) | zero (1) | eB (E)] (gnn_api.cu,
+// forward_device), one set per buffer the step's new edges live in (A = eA, B = eB): degree 0 -> the zero row, degree 1 ->
+// the edge row itself, degree >= 2 -> the row segment_sum_flat_kernel writes for this node.
+__global__ void agg_index_kernel(const int64_t* __restrict__ sptr, const int32_t* __restrict__ sids, const int64_t* __restrict__ rptr,
+                                 const int32_t* __restrict__ rids, int64_t N, int64_t E, int32_t* __restrict__ sidxA,
+                                 int32_t* __restrict__ ridxA, int32_t* __restrict__ sidxB, int32_t* __restrict__ ridxB)
+{
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= N) return;
+    const int64_t zero = E + 2 * N, eb = zero + 1;
+    {
+        const int64_t s = sptr[v], d = sptr[v + 1] - s;
+        const int64_t one = d == 1 ? sids[s] : 0;
+        sidxA[v] = (int32_t)(d == 0 ? zero : d == 1 ? one : E + v);
+        sidxB[v] = (int32_t)(d == 0 ? zero : d == 1 ? eb + one : E + v);
+    }
+    {
+        const int64_t s = rptr[v], d = rptr[v + 1] - s;
+        const int64_t one = d == 1 ? rids[s] : 0;
+        ridxA[v] = (int32_t)(d == 0 ? zero : d == 1 ? one : E + N + v);
+        ridxB[v] = (int32_t)(d == 0 ? zero : d == 1 ? eb + one : E + N + v);
+    }
 }
 
 // readout Linear(H -> 1): one warp per node (model.py:144)

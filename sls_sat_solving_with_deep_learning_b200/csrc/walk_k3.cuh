@@ -132,6 +132,11 @@ __device__ __forceinline__ uint2 lds64(uint32_t a)
     return v;
 }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+// the same store issued by the lanes with `on` set only, as ONE predicated instruction (no branch region)
+__device__ __forceinline__ void sts32_if(uint32_t a, uint32_t v, bool on)
+{
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u32 [%0], %1; }" ::"r"(a), "r"(v), "r"((uint32_t)on) : "memory");
+}
 __device__ __forceinline__ void atoms_xor(uint32_t a, uint32_t v)
 {
     asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
@@ -489,13 +494,11 @@ __device__ __forceinline__ void walk_k3s_body(const WalkArgs& A, uint32_t block,
                 }
                 if (ALGO != ALGO_MOSER_SINGLE || j < 3) {
                     const uint32_t lit = selp(j == 0, q0.x, selp(j == 1, q0.y, q0.z));
-                    // lib.rs:37-41.  Every lane writes the same new word: no lane-0 region, no atomic (the word is
-                    // read again only after the barrier that closes the re-evaluation).  The barrier between the read
-                    // and the write keeps this correct when the lanes do not run in lock step.
+                    // lib.rs:37-41.  Lane 0 alone reads and rewrites the word (one predicated store: no branch region, no
+                    // atomic, and no assumption about the lanes running in lock step); the word is read again only after
+                    // the barrier that closes the re-evaluation
                     const uint32_t wa = sA + (lit >> 6) * 4u;
-                    const uint32_t old = lds32(wa);
-                    __syncwarp();
-                    sts32(wa, old ^ (1u << ((lit >> 1) & 31u)));
+                    sts32_if(wa, lds32(wa) ^ (1u << ((lit >> 1) & 31u)), lane == 0);
                     if (COUNT_FLIPS) flips++;
                     // no barrier: the re-evaluation never reads the flipped variable itself, and it ends with one
                     update_var(selp(j == 0, q1.x, selp(j == 1, q1.z, q2.x)), selp(j == 0, q1.y, selp(j == 1, q1.w, q2.y)), (lit & 1u) ^ 1u);

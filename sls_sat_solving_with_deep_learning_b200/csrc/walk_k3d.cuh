@@ -378,12 +378,10 @@ __device__ __forceinline__ void walk_k3d_body(const WalkArgs& A, uint32_t block,
             const uint32_t j = (dY <= x ? 1u : 0u) + (dZ <= x ? 1u : 0u);
             const uint32_t lit = selp(j == 0, q0.x, selp(j == 1, q0.y, q0.z));
             {
-                // every lane of the half writes the same new word; the barrier between the read and the write makes that
-                // independent of the lanes running in lock step (an idle chain reads record 0's word and writes nothing)
+                // the first lane of the chain's sub-warp alone reads and rewrites the word (one predicated store; an idle
+                // chain reads record 0's word and writes nothing); it is read again only after update_var's barrier
                 const uint32_t wa = sA + (lit >> 6) * 4u;
-                const uint32_t old = lds32(wa);
-                __syncwarp();
-                if (flip) sts32(wa, old ^ (1u << ((lit >> 1) & 31u)));
+                sts32_if(wa, lds32(wa) ^ (1u << ((lit >> 1) & 31u)), flip && l16 == 0);
             }
             update_var(selp(j == 0, q1.x, selp(j == 1, q1.z, q2.x)), flip ? selp(j == 0, q1.y, selp(j == 1, q1.w, q2.y)) : 0u,
                        (lit & 1u) ^ 1u);

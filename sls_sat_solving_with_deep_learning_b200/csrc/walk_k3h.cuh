@@ -198,11 +198,10 @@ __device__ __forceinline__ void walk_k3h_body(const WalkArgs& A, uint32_t block,
                 }
                 __syncwarp();
             };
-            auto toggle = [&](uint32_t lit) {  // every lane writes the same new word: all lanes read before any lane writes
+            auto toggle = [&](uint32_t lit) {  // lane 0 alone reads and rewrites the word (one predicated store)
                 uint32_t* const wa = pA + (lit >> 6);
-                const uint32_t old = __ldcg(wa);
-                __syncwarp();
-                __stcg(wa, old ^ (1u << ((lit >> 1) & 31u)));
+                const uint32_t nw = __ldcg(wa) ^ (1u << ((lit >> 1) & 31u));
+                asm volatile("{ .reg .pred p; setp.eq.u32 p, %2, 0; @p st.global.cg.u32 [%0], %1; }" ::"l"(wa), "r"(nw), "r"((uint32_t)lane) : "memory");
                 log_flip(lit >> 1);
             };
 

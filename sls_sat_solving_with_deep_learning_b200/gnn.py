@@ -227,6 +227,16 @@ class InteractionNetworkLCG:
     def launch_count(self) -> int:
         return _lib.load().sls_gnn_launch_count(self._h)
 
+    def set_profile(self, on: bool) -> None:
+        """Measurement only: bracket every kernel class of the following forwards with CUDA events."""
+        _check(_lib.load().sls_gnn_set_profile(self._h, int(bool(on))))
+
+    def profile(self) -> dict:
+        """Device milliseconds of the last forward by kernel class (needs :meth:`set_profile`)."""
+        ms = (C.c_double * 4)()
+        _check(_lib.load().sls_gnn_get_profile(self._h, ms))
+        return {"edge_update_ms": ms[0], "node_update_ms": ms[1], "segment_sum_ms": ms[2], "other_ms": ms[3]}
+
 
 def network_definition_interaction_lcg(graph, mlp_layers, num_message_passing_steps: int = 5):
     """Marker with the reference's signature (model.py:127-144).  It is never traced: :func:`transform` recognises

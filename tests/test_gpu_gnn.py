@@ -196,3 +196,63 @@ def test_reference_call_site_shape():
     assert decoded_nodes.shape == (problem_graph["n_node"], 1) and np.abs(model_probabilities - ref).max() < PROB_TOL
     with pytest.raises(ValueError):
         gnn.get_network_definition("GCN", "LCG")
+
+
+def _harsh_params(seed, weight_scale, ln_sigma):
+    p = go.init_params(seed=seed, bias_scale=0.3)
+    rng = np.random.default_rng(seed + 1)
+    for mod in p.values():
+        if "w" in mod:
+            mod["w"] = (mod["w"] * weight_scale).astype(np.float32)
+        else:
+            mod["scale"] = (1.0 + ln_sigma * rng.standard_normal(mod["scale"].shape)).astype(np.float32)
+            mod["offset"] = (ln_sigma * rng.standard_normal(mod["offset"].shape)).astype(np.float32)
+    return p
+
+
+@pytest.mark.parametrize("weight_scale,ln_sigma", [(8.0, 0.0), (1.0, 0.5), (8.0, 0.5), (0.125, 0.5)])
+def test_numerics_with_parameters_unlike_the_random_init(weight_scale, ln_sigma):
+    # trained parameters are not haiku's mild random init: weights 8x larger / smaller, LayerNorm scales ~ N(1, 0.5) and
+    # offsets ~ N(0, 0.5), and graphs with long clauses (G4SAT: k up to 297, variable occurrences in the hundreds, so the
+    # aggregates span a wide range).  Both product forms must stay inside the contract against the fp64 forward.
+    params = _harsh_params(11, weight_scale, ln_sigma)
+    net = gnn.InteractionNetworkLCG(params)
+    for name in ("g4sat_hard_ps_00041", "ref_tests_medium", "g4sat_easy_ca_00092"):
+        inst = eng.Instance.from_dimacs(golden_cnf(name))
+        ref = go.model_probabilities(go.forward(params, go.lcg_graph(inst.n, clauses_of(inst)), dtype=np.float64), inst.n)
+        p = net.probabilities([inst])[0]
+        assert np.abs(p - ref).max() < PROB_TOL, (name, float(np.abs(p - ref).max()))
+
+
+def test_gpu_forward_matches_the_independent_torch_model():
+    # second CPU model (oracle/gnn_torch.py: torch fp32, scatter-add aggregation, F.layer_norm, module names replayed from the
+    # construction order): the GPU must agree with it as it does with the NumPy restatement
+    from oracle import gnn_torch as gt
+
+    n, m = 300, 1260
+    clauses = random_ksat(n, m, 3, seed=31)
+    inst = eng.Instance.from_clauses(n, clauses)
+    params = go.init_params(seed=13, bias_scale=0.2)
+    net = gnn.InteractionNetworkLCG(params)
+    p_gpu = net.probabilities([inst])[0]
+    row, lits = inst.csr()
+    p_torch = gt.probabilities(params, n, row, lits)
+    assert np.abs(p_gpu - p_torch).max() < 2e-4
+
+
+def test_transformed_apply_does_not_serve_stale_parameters():
+    # the packed device model is cached per parameter OBJECT and content: an in-place update and a different dict must
+    # both be seen (the cache was keyed by id(params) alone)
+    n = 40
+    graph = go.lcg_graph(n, random_ksat(n, 160, 3, seed=9))
+    network = gnn.without_apply_rng(gnn.transform(gnn.get_network_definition("interaction", "LCG")))
+    a = go.init_params(seed=5)
+    d0 = network.apply(a, graph)
+    assert np.array_equal(d0, network.apply(a, graph))
+    a["linear_22"]["b"] = a["linear_22"]["b"] + 1.0   # readout bias: every logit moves by one
+    d1 = network.apply(a, graph)
+    assert np.allclose(d1, d0 + 1.0, atol=1e-5)
+    b = go.init_params(seed=6)
+    d2 = network.apply(b, graph)
+    ref = go.forward(b, graph, dtype=np.float64)
+    assert np.abs(gnn.get_model_probabilities(d2, n) - go.model_probabilities(ref, n)).max() < PROB_TOL

@@ -560,3 +560,105 @@ def test_batch_two_chains_per_warp_matches_oracle(expected, algo, dual, monkeypa
             assert (r.best_assignment is None) == (o.best_assignment is None)
             if r.best_assignment is not None:
                 assert (r.best_assignment == o.best_assignment).all(), i
+
+
+# ---- BASELINE config 5 at full instance size --------------------------------------------------
+def test_walk_c5_full_size_hbm_tier_matches_oracle_on_sampled_chains():
+    # n = 10^6, m = 4 * 10^6 (the C5 instance of bench.py): 512 chains = two slices of the sliced initialisation, chain state in
+    # HBM (640 KB per chain), three-level rank select.  The CPU oracle re-runs single chains by their global index -- first /
+    # last chain of each slice and two in the middle -- and every one must match step for step.
+    from sls_sat_solving_with_deep_learning_b200 import synth
+
+    n, m, R, S = 1_000_000, 4_000_000, 512, 120
+    row, lits = synth.random_ksat_csr(n, m, 3, 20260105)
+    gi = eng.Instance.from_csr(n, row, lits)
+    oi = so.Instance.from_csr(n, row, lits)
+    w = np.full(n, 0.5)
+    for algo in ("probsat", "moser"):
+        s = eng.ResidentSolver(gi, algo, S, R, True, True, 0.0, seed=9)
+        assert s.variant == "walk_k3h<hbm>"
+        s.set_weights(w, w)
+        s.launch()
+        g = s.fetch()
+        s.close()
+        assert (g.steps == S).all() and not g.found.any()  # alpha = 4.0: nobody solves it in 120 steps
+        for j in (0, 131, 255, 256, 300, 511):
+            o = oi.run_sls(algo, w, w, S, 1, True, True, 0.0, seed=9, chain_offset=j)
+            assert (g.trajectories[j] == o.trajectories[0]).all(), (algo, j)
+            assert g.best_energy_run[j] == o.best_energy_run[0] and g.flips_run[j] == o.flips_run[0], (algo, j)
+        # the reduction over runs (lib.rs:320-334) and the winner's assignment, checked through the clause evaluation
+        winner = int(np.argmin(g.best_energy_run))
+        assert g.best_energy == g.best_energy_run[winner]
+        assert oi.energy(g.best_assignment) == g.best_energy
+
+
+# ---- sharding helpers on the CUDA engine --------------------------------------------------------
+def test_sharding_helpers_drive_the_cuda_engine():
+    # tests/test_sharding_gloo.py exercises sharding.py's collectives with world_size 2 on the CPU oracle; here the same
+    # functions run with the CUDA engine behind them and NCCL as the backend (one rank per visible GPU box = 1 here;
+    # bench.py --gpus N runs them over N ranks)
+    import torch
+    import torch.distributed as dist
+
+    from sls_sat_solving_with_deep_learning_b200 import sharding
+
+    torch.cuda.set_device(0)
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29731", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+        created = True
+    try:
+        name = "r3sat_test_random_KCNF3_200_869_9397183"
+        gi, oi = both(name)
+        w = np.random.default_rng(5).uniform(0.2, 0.8, gi.n)
+        R = 37
+        res = sharding.run_sls_sharded(
+            lambda off, cnt: eng.run_sls(gi, "probsat", w, w, 3000, cnt, False, True, 0.0, seed=21, chain_offset=off),
+            R, gi.n, gi.m, device="cuda")
+        o = oi.run_sls("probsat", w, w, 3000, R, False, True, 0.0, seed=21)
+        assert (res.steps == o.steps).all() and (res.found == o.found).all() and res.best_energy == o.best_energy
+        assert (res.best_assignment is None) == (o.best_assignment is None)
+        if o.best_assignment is not None:
+            assert (res.best_assignment == o.best_assignment).all()
+        # a batch split by instance: every instance keeps its own seed
+        names = [name, "r3sat_test_random_KCNF3_100_210_6416893", "ref_tests_medium"]
+        insts = [eng.Instance.from_dimacs(golden_cnf(nm)) for nm in names]
+        oracles = [so.Instance.from_dimacs(golden_cnf(nm)) for nm in names]
+        ws = [np.full(i.n, 0.5) for i in insts]
+
+        def runner(idx):
+            return eng.run_sls_batch([insts[i] for i in idx], "moser", [ws[i] for i in idx], [ws[i] for i in idx], 500, 16,
+                                     instance_seeds=[100 + i for i in idx])
+
+        found, steps, best, flips = sharding.run_batch_sharded(runner, [i.m for i in insts], 16, device="cuda")
+        for i, oi_ in enumerate(oracles):
+            o = oi_.run_sls("moser", ws[i], ws[i], 500, 16, False, True, 0.0, seed=100 + i)
+            assert (steps[i] == o.steps).all() and (found[i] == o.found).all() and best[i] == o.best_energy and flips[i] == o.total_flips
+    finally:
+        if created:
+            dist.destroy_process_group()
+
+
+def test_instance_cannot_migrate_under_a_live_solver():
+    # one device image per handle: with a solver holding pointers into it, moving the image to another GPU is refused
+    # (single-GPU box: the guard's bookkeeping is checked through solver lifetimes on the same device)
+    gi, _ = both("ref_tests_medium")
+    w = np.full(gi.n, 0.5)
+    s1 = eng.ResidentSolver(gi, "probsat", 50, 4, False, True, 0.0, seed=1)
+    s2 = eng.ResidentSolver(gi, "moser", 50, 4, False, True, 0.0, seed=1)
+    s1.set_weights(w, w)
+    s1.launch()
+    s1.close()
+    s2.set_weights(w, w)
+    s2.launch()
+    r = s2.fetch()
+    s2.close()
+    assert r.steps.shape == (4,)
+    if eng.device_count() > 1:
+        s3 = eng.ResidentSolver(gi, "probsat", 50, 4, False, True, 0.0, seed=1)
+        eng.set_device(1)
+        with pytest.raises(eng.PanicException):
+            eng.run_sls(gi, "probsat", w, w, 10, 2)
+        eng.set_device(0)
+        s3.close()

@@ -76,3 +76,36 @@ def test_random_oracle_params_have_the_reference_layout():
     assert blob.dtype == np.float32 and blob.size == 1_473_993  # 1.47 M parameters
     assert set(params) == {"linear"} | {f"linear_{i}" for i in range(1, 23)} | {"layer_norm"} | {f"layer_norm_{i}" for i in range(1, 10)}
     assert np.abs(params["linear_2"]["w"]).max() <= 2.0 / np.sqrt(96) + 1e-6
+
+
+def test_pack_params_maps_modules_by_shape_and_order_when_names_differ():
+    # the haiku names are from memory -- a file with another scope or numbering must still load, by creation
+    # order and shape, and a wrong guess must be an error
+    from oracle import gnn_oracle as go
+    from sls_sat_solving_with_deep_learning_b200 import gnn
+
+    params = go.init_params(seed=3, mlp_layers=(32, 32), num_steps=2, bias_scale=0.1)
+    blob, D, h1, h2 = gnn.pack_params(params, 2)
+    # (1) scoped names, keys sorted alphabetically (what a jax tree operation leaves behind)
+    scoped = {f"net/~/{k}": v for k, v in sorted(params.items())}
+    blob2, *_ = gnn.pack_params(scoped, 2)
+    assert np.array_equal(blob, blob2)
+    # (2) another numbering scheme: creation order survives as the numeric suffix
+    lin = sorted((k for k in params if "w" in params[k]), key=gnn._natural_key)
+    lns = sorted((k for k in params if "scale" in params[k]), key=gnn._natural_key)
+    renamed = {f"dense_{i + 3}": params[k] for i, k in enumerate(lin)}
+    renamed.update({f"norm_{i}": params[k] for i, k in enumerate(lns)})
+    blob3, *_ = gnn.pack_params(dict(sorted(renamed.items())), 2)
+    assert np.array_equal(blob, blob3)
+    # (3) a module too few: refused
+    import pytest
+
+    broken = dict(renamed)
+    broken.pop("norm_1")
+    with pytest.raises(ValueError):
+        gnn.pack_params(broken, 2)
+    # (4) right count, wrong order (two layers swapped): the shape check catches it
+    swapped = dict(renamed)
+    swapped["dense_5"], swapped["dense_6"] = swapped["dense_6"], swapped["dense_5"]
+    with pytest.raises(ValueError):
+        gnn.pack_params(swapped, 2)

@@ -277,3 +277,32 @@ def test_c_oracle_and_naive_model_agree_in_distribution(algo, pfb, mapping):
     for r in (c, p):
         assert all((t[-1] == 0) == bool(f) for t, f in zip(r.trajectories, r.found))
         assert all(len(t) == s + 1 for t, s in zip(r.trajectories, r.steps))
+
+
+# ---- the two CPU models of the GNN forward ---------------------------------------------------------------------------
+@pytest.mark.parametrize("layers,steps,bias", [((200, 200), 5, 0.0), ((200, 200), 5, 0.3), ((32, 32), 2, 0.2), ((64, 48), 3, 0.2)])
+def test_numpy_and_torch_gnn_models_agree(layers, steps, bias):
+    # oracle/gnn_oracle.py (NumPy, the checker of the CUDA kernels) and oracle/gnn_torch.py (torch fp32: graph from flat
+    # literal arrays, names replayed from the construction order, index_add_ aggregation, F.layer_norm) share no code;
+    # they must agree to fp32 rounding on mixed clause lengths and on a 3-SAT graph
+    from oracle import gnn_oracle as go
+    from oracle import gnn_torch as gt
+
+    from conftest import random_ksat
+
+    cases = [(60, random_ksat(60, 250, 3, seed=5)), (7, [(1, -2), (3,), (-1, -2, 3, 7), (4, 5, -6), (-7, 2)])]
+    for n, clauses in cases:
+        params = go.init_params(seed=42, mlp_layers=layers, num_steps=steps, bias_scale=bias)
+        graph = go.lcg_graph(n, clauses)
+        ref64 = go.forward(params, graph, dtype=np.float64, num_steps=steps)
+        t = gt.forward(params, *gt.graph_from_clauses(n, clauses), mlp_layers=layers, num_message_passing_steps=steps).numpy()
+        assert t.shape == ref64.shape
+        assert np.abs(t - ref64).max() < 5e-5
+        import torch
+
+        p_t = gt.model_probabilities(torch.from_numpy(t), n)
+        assert np.abs(p_t - go.model_probabilities(ref64, n)).max() < 1e-5
+        # identical graph arrays from the two builders
+        nodes, edges, snd, rcv = gt.graph_from_clauses(n, clauses)
+        assert np.array_equal(nodes.numpy(), graph["nodes"]) and np.array_equal(edges.numpy(), graph["edges"])
+        assert np.array_equal(snd.numpy(), graph["senders"]) and np.array_equal(rcv.numpy(), graph["receivers"])

@@ -37,6 +37,11 @@ for r in range(reps):
     wall = time.perf_counter() - t0
     best = min(best, net.last_kernel_ms)
     print(f"rep {r}: device {net.last_kernel_ms:.2f} ms, wall {wall*1e3:.1f} ms, launches {net.launch_count()}")
+net.set_profile(True)
+net.probabilities(insts)
+prof = net.profile()
+net.set_profile(False)
+print("profile (ms, events around every launch):", json.dumps(prof))
 # spot-check one instance against the fp64 restatement
 row, lits = insts[0].csr()
 clauses = [lits[int(row[c]):int(row[c + 1])].tolist() for c in range(m)]

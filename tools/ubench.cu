@@ -1,7 +1,9 @@
 // ubench.cu -- B200 micro-benchmarks behind the roofline denominators that MEASURED_PEAKS.json does not hold
 // ("L2 peak must be measured on the box") and behind the latency model of the walk kernels.
-//   build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/_build/ubench tools/ubench.cu
-//   run:    tools/_build/ubench            (prints one JSON object)
+//   library (what bench.py loads so that every roofline denominator is measured IN THE RUN, on the bench box):
+//           nvcc -gencode arch=compute_100a,code=sm_100a -O3 -shared -Xcompiler -fPIC -o tools/_build/libubench.so tools/ubench.cu
+//           extern "C" int slsub_measure(char* json, size_t cap, int with_hbm)   -> 0 / CUDA error code
+//   stand-alone: add -DUBENCH_MAIN, run tools/_build/ubench (prints the same JSON object)
 // Bandwidth legs (all SMs, working set resident in the 126 MB L2 unless stated):
 //   l2_stream      coalesced 16-byte loads over a 32 MB buffer, many passes
 //   l2_sector32    random 32-byte sectors (one 256-bit load per lane) from a 32 MB table: the access of the
@@ -16,14 +18,18 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
+
+#include <stdexcept>
+#include <string>
 
 #define CK(x)                                                                                   \
     do {                                                                                        \
         cudaError_t e_ = (x);                                                                   \
         if (e_ != cudaSuccess) {                                                                \
             fprintf(stderr, "%s:%d %s: %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
-            exit(1);                                                                            \
+            throw std::runtime_error(cudaGetErrorString(e_));                                   \
         }                                                                                       \
     } while (0)
 
@@ -154,25 +160,30 @@ static float time_ms(F&& launch, int reps = 5)
     return best;
 }
 
-int main()
+static std::string measure(bool with_hbm)
 {
+    std::string out;
+    char tmp[512];
+#define P(...) do { snprintf(tmp, sizeof tmp, __VA_ARGS__); out += tmp; } while (0)
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
     int sms = 0, clock_khz = 0;
-    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
-    CK(cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, 0));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, dev));
     uint32_t* sink;
     CK(cudaMalloc(&sink, 4));
     const size_t small_bytes = 32u << 20;
     uint4* small;
     CK(cudaMalloc(&small, small_bytes));
     CK(cudaMemset(small, 0, small_bytes));
-    printf("{\"sms\": %d, \"sm_clock_mhz\": %.0f", sms, clock_khz / 1000.0);
+    P("{\"sms\": %d, \"sm_clock_mhz\": %.0f", sms, clock_khz / 1000.0);
 
     {  // L2 streaming
         const int passes = 64, blocks = sms * 8, threads = 256;
         const float ms = time_ms([&] { stream_kernel<<<blocks, threads>>>(small, small_bytes / 16, passes, sink); });
-        printf(", \"l2_stream_gbs\": %.1f", passes * (double)small_bytes / ms * 1e-6);
+        P(", \"l2_stream_gbs\": %.1f", passes * (double)small_bytes / ms * 1e-6);
         const float ms2 = time_ms([&] { stream_kernel<<<blocks, threads>>>(small, small_bytes / 32, passes, sink); });
-        printf(", \"l2_stream_16mb_gbs\": %.1f", passes * (double)small_bytes / 2 / ms2 * 1e-6);
+        P(", \"l2_stream_16mb_gbs\": %.1f", passes * (double)small_bytes / 2 / ms2 * 1e-6);
     }
     {  // L2 random 32-byte sectors
         const int iters = 256, blocks = sms * 8, threads = 256;
@@ -180,7 +191,7 @@ int main()
         const float ms4 = time_ms([&] { sector32_kernel<4><<<blocks, threads>>>(small, mask, iters, sink); });
         const float ms8 = time_ms([&] { sector32_kernel<8><<<blocks, threads>>>(small, mask, iters / 2, sink); });
         const double bytes = (double)blocks * threads * iters * 4 * 32;
-        printf(", \"l2_sector32_gbs_4_in_flight\": %.1f, \"l2_sector32_gbs_8_in_flight\": %.1f", bytes / ms4 * 1e-6, bytes / ms8 * 1e-6);
+        P(", \"l2_sector32_gbs_4_in_flight\": %.1f, \"l2_sector32_gbs_8_in_flight\": %.1f", bytes / ms4 * 1e-6, bytes / ms8 * 1e-6);
     }
     {  // the walk's record accesses, 28 warps per SM like the C2 launch, dependent per warp
         const int iters = 20000, blocks = sms * 7, threads = 128;
@@ -188,10 +199,10 @@ int main()
         const float msA = time_ms([&] { rec64_kernel<<<blocks, threads>>>(small, mask64, iters, sink); }, 3);
         const float msB = time_ms([&] { rec16_run_kernel<<<blocks, threads>>>(small, mask16, 12, iters, sink); }, 3);
         const double warps = (double)blocks * threads / 32;
-        printf(", \"l2_rec64_dependent\": {\"ns_per_link\": %.1f, \"gbs\": %.1f}", msA * 1e6 / iters, warps * iters * 64 / msA * 1e-6);
-        printf(", \"l2_rec16x12_dependent\": {\"ns_per_link\": %.1f, \"gbs\": %.1f}", msB * 1e6 / iters, warps * iters * 12 * 16 / msB * 1e-6);
+        P(", \"l2_rec64_dependent\": {\"ns_per_link\": %.1f, \"gbs\": %.1f}", msA * 1e6 / iters, warps * iters * 64 / msA * 1e-6);
+        P(", \"l2_rec16x12_dependent\": {\"ns_per_link\": %.1f, \"gbs\": %.1f}", msB * 1e6 / iters, warps * iters * 12 * 16 / msB * 1e-6);
     }
-    {  // HBM random sectors
+    if (with_hbm) {  // HBM random sectors
         const size_t big_bytes = 4ull << 30;
         uint4* big;
         CK(cudaMalloc(&big, big_bytes));
@@ -199,7 +210,7 @@ int main()
         const int iters = 64, blocks = sms * 8, threads = 256;
         const uint32_t mask = (uint32_t)(big_bytes / 32 - 1);
         const float ms = time_ms([&] { sector32_kernel<8><<<blocks, threads>>>(big, mask, iters, sink); }, 3);
-        printf(", \"hbm_sector32_gbs\": %.1f", (double)blocks * threads * iters * 8 * 32 / ms * 1e-6);
+        P(", \"hbm_sector32_gbs\": %.1f", (double)blocks * threads * iters * 8 * 32 / ms * 1e-6);
         CK(cudaFree(big));
     }
     {  // latencies
@@ -225,10 +236,38 @@ int main()
         long long hc[LAT_N];
         CK(cudaMemcpy(hc, cyc, sizeof(hc), cudaMemcpyDeviceToHost));
         const char* names[LAT_N] = {"l2_hit", "lds", "shfl_up_add", "shfl_idx_add", "vote_popc_add", "redux_or_add", "redux_add_add", "atoms_ret", "match_any_add"};
-        printf(", \"latency_cycles\": {");
-        for (int i = 0; i < LAT_N; i++) printf("%s\"%s\": %.1f", i ? ", " : "", names[i], (double)hc[i] / iters);
-        printf("}");
+        P(", \"latency_cycles\": {");
+        for (int i = 0; i < LAT_N; i++) P("%s\"%s\": %.1f", i ? ", " : "", names[i], (double)hc[i] / iters);
+        P("}");
+        CK(cudaFree(chase));
+        CK(cudaFree(cyc));
     }
-    printf("}\n");
+    P("}");
+#undef P
+    CK(cudaFree(small));
+    CK(cudaFree(sink));
+    return out;
+}
+
+extern "C" int slsub_measure(char* json, size_t cap, int with_hbm)
+{
+    try {
+        const std::string s = measure(with_hbm != 0);
+        if (s.size() + 1 > cap) return -1;
+        std::memcpy(json, s.c_str(), s.size() + 1);
+        return 0;
+    } catch (const std::exception&) {
+        return (int)cudaGetLastError() ? (int)cudaGetLastError() : 1;
+    }
+}
+
+#ifdef UBENCH_MAIN
+int main()
+{
+    static char buf[1 << 14];
+    const int rc = slsub_measure(buf, sizeof buf, 1);
+    if (rc) return 1;
+    puts(buf);
     return 0;
 }
+#endif
