@@ -14,6 +14,8 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "lib", "libsls_b200.so")
+if os.environ.get("SLS_B200_LIB"):  # development hook: A/B runs of differently built libraries (tools/)
+    LIB_PATH = os.path.abspath(os.environ["SLS_B200_LIB"])
 _SOURCES = ["csrc/api.cu", "csrc/gnn_api.cu", "csrc/instance.cpp"]
 def _headers():
     """Every header the library is built from (staleness check): all of csrc/ plus the public C header."""
@@ -41,6 +43,8 @@ def _nvcc() -> str:
 
 
 def is_stale() -> bool:
+    if os.environ.get("SLS_B200_LIB"):
+        return False  # an explicitly chosen library is used as it is
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)

@@ -137,8 +137,11 @@ int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& 
     };
     // the same weights as two bf16 pieces b0 = bf16(w), b1 = bf16(w - b0): 64 k-values per 128-byte row, 16-byte unit = 8 values
     constexpr int SLAB_KB = 64;
-    out.k1_slabs_bf = (k1 + SLAB_KB - 1) / SLAB_KB;
-    out.k2_slabs_bf = (h1 + SLAB_KB - 1) / SLAB_KB;
+    // one more k-value per GEMM: the kernel appends a constant 1 to every A row and the images hold the bias in that weight
+    // row (b1 behind the k1 gathered columns, b2 behind the h1 hidden columns), so the bias is added by the tensor core and
+    // neither the GEMM2 staging nor the epilogue loads it (two bf16 pieces like every weight: 16 mantissa bits)
+    out.k1_slabs_bf = (k1 + 1 + SLAB_KB - 1) / SLAB_KB;
+    out.k2_slabs_bf = (h1 + 1 + SLAB_KB - 1) / SLAB_KB;
     auto img_index_bf = [](int n_pad, int s, int n, int k_in_slab) {
         const int u = k_in_slab >> 3, e = k_in_slab & 7;
         return (size_t)s * n_pad * SLAB_KB + (size_t)(n >> 3) * 512 + (size_t)(n & 7) * 64 + (size_t)((u ^ (n & 7)) << 3) + e;
@@ -169,6 +172,7 @@ int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& 
         }
     p += (size_t)k1 * h1;
     std::copy(p, p + h1, b1.begin());
+    for (int n = 0; n < h1; n++) put_bf(w1b0, w1b1, img_index_bf(out.n1, k1 / SLAB_KB, n, w1_perm(k1 % SLAB_KB)), p[n]);
     p += h1;
     for (int k = 0; k < h1; k++)
         for (int n = 0; n < h2; n++) {
@@ -180,6 +184,7 @@ int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& 
         }
     p += (size_t)h1 * h2;
     std::copy(p, p + h2, b2.begin());
+    for (int n = 0; n < h2; n++) put_bf(w2b0, w2b1, img_index_bf(out.n2, h1 / SLAB_KB, n, h1 % SLAB_KB), p[n]);
     p += h2;
     std::vector<float> sc(p, p + h2), of(p + h2, p + 2 * h2);
     p += 2 * h2;
@@ -287,12 +292,28 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
     a.idx[0] = i0, a.idx[1] = i1, a.idx[2] = i2;
     a.d[0] = d0, a.d[1] = d1, a.d[2] = d2;
     a.rows = (int32_t)rows;
-    a.k1_slabs = w.k1_slabs, a.k2_slabs = w.k2_slabs, a.n1 = w.n1, a.n2 = w.n2, a.h2 = w.h2;
+    a.k1_slabs = w.k1_slabs, a.k2_slabs = w.k2_slabs, a.n1 = w.n1, a.n2 = w.n2, a.h2 = w.h2, a.h1 = w.h1;
     a.w1_hi = w.w1_hi, a.w1_lo = w.w1_lo, a.b1 = w.b1, a.w2_hi = w.w2_hi, a.w2_lo = w.w2_lo, a.b2 = w.b2;
     a.ln_scale = w.ln_scale, a.ln_offset = w.ln_offset;
     a.out = out;
     a.w1_b0 = w.w1_b0, a.w1_b1 = w.w1_b1, a.w2_b0 = w.w2_b0, a.w2_b1 = w.w2_b1;
     a.k1_slabs_bf = w.k1_slabs_bf, a.k2_slabs_bf = w.k2_slabs_bf;
+    a.trace = nullptr;
+#ifdef GNN_TRACE
+    // development build: stamps of the launch number SLS_B200_GNN_TRACE_LAUNCH (counted over the process) go to the file
+    // SLS_B200_GNN_TRACE names, after the launch has finished
+    static int launch_no = 0;
+    static unsigned long long* d_trace = nullptr;
+    const char* tf = std::getenv("SLS_B200_GNN_TRACE");
+    const char* tl = std::getenv("SLS_B200_GNN_TRACE_LAUNCH");
+    const bool trace_this = tf && launch_no == (tl ? std::atoi(tl) : 0);
+    launch_no++;
+    if (trace_this) {
+        if (!d_trace) cudaMalloc(&d_trace, TRACE_WORDS * 8);
+        cudaMemset(d_trace, 0, TRACE_WORDS * 8);
+        a.trace = d_trace;
+    }
+#endif
     const unsigned blocks = (unsigned)((rows + TILE_M - 1) / TILE_M);
     {
         // SLS_B200_GNN_CLUSTER = 1 | 2: CTAs per cluster sharing the weight stream by multicast (see the kernel)
@@ -333,6 +354,19 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
     }
     m->launches++;
     G_TRY(cudaGetLastError());
+#ifdef GNN_TRACE
+    if (trace_this) {
+        cudaDeviceSynchronize();
+        std::vector<unsigned long long> h(TRACE_WORDS);
+        cudaMemcpy(h.data(), d_trace, TRACE_WORDS * 8, cudaMemcpyDeviceToHost);
+        if (FILE* f = std::fopen(tf, "wb")) {
+            const int hdr[4] = {a.k1_slabs_bf, a.k2_slabs_bf, (int)rows, TRACE_WORDS};
+            std::fwrite(hdr, 4, 4, f);
+            std::fwrite(h.data(), 8, h.size(), f);
+            std::fclose(f);
+        }
+    }
+#endif
     return SLS_OK;
 }
 
@@ -428,13 +462,8 @@ int forward_device(sls_gnn_model* m, int64_t N, int64_t E, const float* d_nodes,
         // node update sees [nodes | segment_sum(new edges, senders) | segment_sum(new edges, receivers)]; only the sums over two
         // or more edges are materialised
         if (N) {
-            const int64_t per_block = 256 / (H / 4), blocks = (2 * N + per_block - 1) / per_block;
-            if ((rc = timed(2, [&] {
-                     if (H == 200)
-                         segment_sum_flat_kernel<50><<<(unsigned)blocks, 256>>>(e, d_sptr, d_sids, sent, d_rptr, d_rids, recv, N, H);
-                     else
-                         segment_sum_flat_kernel<0><<<(unsigned)blocks, 256>>>(e, d_sptr, d_sids, sent, d_rptr, d_rids, recv, N, H);
-                 })))
+            const unsigned blocks = (unsigned)((2 * N * 32 + 255) / 256);
+            if ((rc = timed(2, [&] { segment_sum_kernel<<<blocks, 256>>>(e, d_sptr, d_sids, sent, d_rptr, d_rids, recv, N, H); })))
                 return rc;
             m->launches += 1;
         }

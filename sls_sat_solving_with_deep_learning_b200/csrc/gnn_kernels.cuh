@@ -25,6 +25,7 @@
 // are split on the host, activations while they are staged.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace gnn {
@@ -50,6 +51,7 @@ struct MlpArgs {
     int32_t k2_slabs;    // ceil(h1/32)
     int32_t n1, n2;      // padded output widths of the two linears (multiples of 16, <= 208)
     int32_t h2;          // true output width (LayerNorm length)
+    int32_t h1;          // true hidden width (the bf16 images carry b2 as weight row h1, b1 as weight row d0+d1+d2: see pack_mlp)
     // weights as shared-memory slab images: [k_slabs][n_pad * 32] floats, slab s holding W^T[n][32 s .. 32 s + 31]
     // already in the K-major SWIZZLE_128B layout (sw128_off), so one bulk copy per slab stages it
     const float* w1_hi;  // TF32-rounded weights
@@ -68,7 +70,17 @@ struct MlpArgs {
     const uint16_t* w2_b1;
     int32_t k1_slabs_bf;  // ceil((d0+d1+d2)/64)
     int32_t k2_slabs_bf;  // ceil(h1/64)
+    // development builds (-DGNN_TRACE): clock64 stamps of CTA 0's roles, see tools/gnn_trace.py; nullptr otherwise
+    unsigned long long* trace;
 };
+
+#ifdef GNN_TRACE
+#define GNN_STAMP(slot) do { if (P.trace && blockIdx.x == 0) P.trace[(slot)] = (unsigned long long)clock64(); } while (0)
+#else
+#define GNN_STAMP(slot) do { } while (0)
+#endif
+static constexpr int TRACE_TILE0 = 3, TRACE_TILES = 3;   // tiles of CTA 0 that are traced
+static constexpr int TRACE_ISSUER = 0, TRACE_PROD = 4096, TRACE_EPI = 8192, TRACE_WORDS = 8192 + 64;
 
 // ---- small PTX helpers -----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -242,6 +254,8 @@ __device__ __forceinline__ float residual_tf32(float x, float hi) { return x - h
 // (Round 1 also shipped two predecessors of this kernel -- one tile per CTA, and a persistent kernel with the A operand
 // staged in shared memory -- behind environment switches; they are retired, see git history and profiles/r01_gnn_*.)
 static constexpr int MLPP_PRODUCERS = 256;
+static constexpr int MLPP_EPILOGUE0 = MLPP_PRODUCERS + 32;   // first epilogue thread
+static constexpr int MLPP_ISSUER_WARP = MLPP_PRODUCERS / 32;
 static constexpr int MLPP_THREADS = MLPP_PRODUCERS + 32 + 128;
 
 // ---- the same update with the A operand in TENSOR MEMORY ---------------------------------------------------------
@@ -262,7 +276,8 @@ static constexpr int TS_B_STAGES = 4;
 static constexpr int TS_A_STAGES = 3;
 static constexpr int TS_A_COL = 416;     // first A-stage column; 32 columns per stage
 static constexpr int TS_ACC2_COL = 208;
-static constexpr int TS_SMEM_BYTES = TS_B_STAGES * B_STAGE_BYTES + BAR_BYTES + PAR_BYTES + MAX_N * 4 + 1024;  // + b1
+static constexpr int TS_OUT_BYTES = 4 * 32 * 64;  // epilogue staging: per warp 32 rows x 16 columns, see the store pass
+static constexpr int TS_SMEM_BYTES = TS_B_STAGES * B_STAGE_BYTES + BAR_BYTES + PAR_BYTES + MAX_N * 4 + TS_OUT_BYTES + 1024;  // + b1
 
 // instruction descriptor for kind::f16 with bf16 operands: D = f32, A = B = bf16 (format 1), both K-major
 __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n)
@@ -336,13 +351,14 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
     const uint32_t sFreeB = sAccFree + 8;
     const uint32_t sTmem = sFreeB + 8 * FREE_BARS;
     const uint32_t sPar = sFull + BAR_BYTES;
+    const uint32_t sOut = sPar + PAR_BYTES + MAX_N * 4;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
     const bool producer = tid < MLPP_PRODUCERS;
-    const bool epilogue = tid >= MLPP_PRODUCERS + 32;
+    const bool epilogue = tid >= MLPP_EPILOGUE0 && tid < MLPP_EPILOGUE0 + 128;
     const int prow = tid & (TILE_M - 1);   // producers: row of the tile = TMEM lane
     const uint32_t grp = (uint32_t)tid >> 7;  // producers: which 16 of a slab's 32 columns, i.e. which units
     const int ntiles = (P.rows + TILE_M - 1) / TILE_M;
@@ -447,7 +463,10 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
             for (int i = 0; i < 4; i++) {
 #pragma unroll
                 for (int e = 0; e < 8; e++) x[i][e] = 0.f;
-                if (col >= kA) continue;
+                if (col >= kA) {
+                    if (col == kA) x[i][0] = 1.f;  // the constant-one column: W1's image holds b1 in this row (wide: kA % 8 == 0)
+                    continue;
+                }
                 if (wide) {
                     const int sj = col < P.d[0] ? 0 : col < P.d[0] + P.d[1] ? 1 : 2;
                     const int c = col - (sj == 0 ? 0 : sj == 1 ? P.d[0] : P.d[0] + P.d[1]);
@@ -467,6 +486,8 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                             const int c = ce - (sj == 0 ? 0 : sj == 1 ? P.d[0] : P.d[0] + P.d[1]);
                             const int ri = sj == 0 ? qidx[0][i] : sj == 1 ? qidx[1][i] : qidx[2][i];
                             x[i][e] = __ldg(P.src[sj] + (size_t)ri * P.d[sj] + c);
+                        } else if (ce == kA) {
+                            x[i][e] = 1.f;
                         }
                     }
                 }
@@ -572,16 +593,20 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
             first_loads();
             fetch_idx((int)(blockIdx.x + gridDim.x));
         }
+        uint32_t trace_it = 0;
         auto publish = [&](uint32_t U) {  // the unit is in its A stage: hand it to the issuer
             tc_fence_before();
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(sArdy + 8 * (U % TS_A_STAGES));
+#ifdef GNN_TRACE
+            if ((tid & 127) == 0 && trace_it >= (uint32_t)TRACE_TILE0 && trace_it < (uint32_t)(TRACE_TILE0 + TRACE_TILES))
+                GNN_STAMP(TRACE_PROD + U - 2 * TRACE_TILE0 * S);
+#endif
             J++;
         };
         // GEMM2's operand comes out of GEMM1's accumulator: NV columns of this thread's TMEM lane, requested without waiting
         // (zeros beyond the padded width)
-        float vg[NV];
-        auto request_acc1 = [&](uint32_t j2) {
+        auto request_acc1 = [&](uint32_t j2, float* vg) {
             const int c0 = (int)j2 * SLABK + (int)grp * NV;
             if constexpr (BF) {
                 if (c0 + 32 <= P.n1)
@@ -594,6 +619,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
         };
         for (uint32_t it = 0; it < my_tiles; it++) {
             const int next_tile = (int)(blockIdx.x + (it + 1) * gridDim.x);
+            trace_it = it;
             // ---- GEMM1: gathered rows
             auto gemm1_unit = [&](uint32_t j, float4* xa) {
                 const uint32_t U = 2 * J + grp;
@@ -620,43 +646,57 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                     if (j + 1 < n1s) gemm1_unit(j + 1, xa1);
                 }
             }
-            // ---- GEMM2: ReLU(acc1 + b1).  Every GEMM1 MMA must have completed; from then on the whole accumulator is there, so
-            // the request for the next unit's columns is in flight while this one is converted, stored and published, and the
-            // next tile's row pointers / first gathers are set up only after the first unit is on its way to the tensor pipe
-            // (measured: with that work and one TMEM round trip per unit on the critical path, the GEMM2 phase took 2.7x its
-            // MMA time and, chained with the epilogue through acc2, set the kernel's period)
+            // ---- GEMM2: ReLU(acc1 + b1).  Every GEMM1 MMA must have completed.  One 32-column TMEM load per unit, and the next
+            // tile's row pointers / first gathers are set up only after the first unit is on its way to the tensor pipe
+            // (measured in round 2: with that work and two TMEM round trips per unit on the critical path, the GEMM2 phase took
+            // 2.7x its MMA time and, chained with the epilogue through acc2, set the kernel's period)
             wait_unit(2 * J - 1);
-            tc_fence_after();
-            request_acc1(0);
+            if (it + 1 < my_tiles) {
+                set_rows();
+                first_loads();
+                fetch_idx(next_tile + (int)gridDim.x);
+            }
             for (uint32_t j2 = 0; j2 < n2s; j2++) {
                 const uint32_t U = 2 * J + grp;
-                const int c0 = (int)j2 * SLABK + (int)grp * NV;
                 float v[NV];
                 uint32_t r[32];
-                tmem_wait_ld();
+                tc_fence_after();
 #pragma unroll
-                for (int i = 0; i < NV; i += 4) {
-                    if (c0 + i < P.n1) {
-                        float4 b;
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(sPar + (3 * MAX_N + c0 + i) * 4));
-                        v[i] = fmaxf(vg[i] + b.x, 0.f), v[i + 1] = fmaxf(vg[i + 1] + b.y, 0.f);
-                        v[i + 2] = fmaxf(vg[i + 2] + b.z, 0.f), v[i + 3] = fmaxf(vg[i + 3] + b.w, 0.f);
+                for (int half = 0; half < NV / 16; half++) {
+                    const int c0 = (int)j2 * SLABK + (int)grp * NV + 16 * half;
+                    float* vh = v + 16 * half;
+                    if (c0 < P.n1) {
+                        tmem_ld16(tmem + lane_base + (uint32_t)c0, vh);
+                        if constexpr (BF) {  // b1 came through the GEMM (constant-one column of A): only the ReLU is left
+#pragma unroll
+                            for (int i = 0; i < 16; i++) vh[i] = fmaxf(vh[i], 0.f);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                float4 b;
+                                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(sPar + (3 * MAX_N + c0 + 4 * q) * 4));
+                                vh[4 * q] = fmaxf(vh[4 * q] + b.x, 0.f), vh[4 * q + 1] = fmaxf(vh[4 * q + 1] + b.y, 0.f);
+                                vh[4 * q + 2] = fmaxf(vh[4 * q + 2] + b.z, 0.f), vh[4 * q + 3] = fmaxf(vh[4 * q + 3] + b.w, 0.f);
+                            }
+                        }
                     } else {
-                        v[i] = v[i + 1] = v[i + 2] = v[i + 3] = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) vh[i] = 0.f;
+                    }
+                    if constexpr (BF) {  // the constant-one column behind the hidden activation: W2's image holds b2 in row h1
+                        if (c0 <= P.h1 && P.h1 < c0 + 16) {
+#pragma unroll
+                            for (int i = 0; i < 16; i++)
+                                if (c0 + i == P.h1) vh[i] = 1.f;
+                        }
                     }
                 }
-                if (j2 + 1 < n2s) request_acc1(j2 + 1);
                 pack_unit(v, r);
                 store_unit(U, r);
                 publish(U);
-                if (j2 == 0 && it + 1 < my_tiles) {
-                    set_rows();
-                    first_loads();
-                    fetch_idx(next_tile + (int)gridDim.x);
-                }
             }
         }
-    } else if (warp_u == MLPP_PRODUCERS / 32) {
+    } else if (warp_u == MLPP_ISSUER_WARP) {
         const bool leader = elect_one();
         const uint32_t total = my_tiles * S;
         const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
@@ -704,14 +744,28 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
             const uint32_t idesc = g1 ? idesc1 : idesc2;
             const uint32_t acc = tmem + (g1 ? 0u : (uint32_t)TS_ACC2_COL);
             const uint32_t first = g1 ? 0u : n1s;
+#ifdef GNN_TRACE
+            const bool tr = leader && it >= (uint32_t)TRACE_TILE0 && it < (uint32_t)(TRACE_TILE0 + TRACE_TILES);
+            const uint32_t tb = TRACE_ISSUER + 8 * ((it - TRACE_TILE0) * S + j);
+            if (tr) GNN_STAMP(tb + 0);
+#endif
             mbar_wait(sFull + 8 * (J % TS_B_STAGES), (J / TS_B_STAGES) & 1u);
+#ifdef GNN_TRACE
+            if (tr) GNN_STAMP(tb + 1);
+#endif
             if (j == n1s && it > 0) mbar_wait(sAccFree, (it - 1) & 1u);  // the epilogue of the previous tile has read acc2
+#ifdef GNN_TRACE
+            if (tr) GNN_STAMP(tb + 2);
+#endif
             const uint32_t bHi = sBst + (J % TS_B_STAGES) * B_STAGE_BYTES;
             const uint64_t dBh = desc(bHi), dBl = desc(bHi + B_SLAB_BYTES);
 #pragma unroll
             for (uint32_t h = 0; h < 2; h++) {
                 const uint32_t U = 2 * J + h;
                 mbar_wait(sArdy + 8 * (U % TS_A_STAGES), (U / TS_A_STAGES) & 1u);
+#ifdef GNN_TRACE
+                if (tr) GNN_STAMP(tb + 3 + 2 * h);
+#endif
                 tc_fence_after();
                 const uint32_t a = tmem + (uint32_t)(TS_A_COL + 32 * (U % TS_A_STAGES));
                 if (leader) {
@@ -732,12 +786,18 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                     if (CL > 1 && h == 1) umma_commit_multicast(sFreeB + 8 * (J % FREE_BARS), CL_MASK);
                     if (h == 1 && j == S - 1) umma_commit(sAccFull);
                 }
+#ifdef GNN_TRACE
+                if (tr) GNN_STAMP(tb + 4 + 2 * h);
+#endif
                 __syncwarp();
             }
             if (J + PF < total) {
                 issue_b(J + PF, jn);
                 jn = jn + 1 == S ? 0 : jn + 1;
             }
+#ifdef GNN_TRACE
+            if (tr) GNN_STAMP(tb + 7);
+#endif
             if (++j == S) j = 0, it++;
         }
         if (CL > 1) {  // every arrival the other CTA still sends to this one has landed before this CTA may exit
@@ -752,14 +812,31 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
             return v;
         };
-        // acc2 is read TWICE per tile, 32 columns per TMEM load, the next load in flight while a chunk is processed: once for the
-        // row statistics, once to normalise and store.  (Round 1 read it three times in 16-column loads, each followed by its
-        // own wait; the epilogue then took longer than GEMM1 and, chained with GEMM2 through acc2 -- GEMM2 of the next tile
-        // may only start when the epilogue has released the accumulator -- set the kernel's period.)
+        // acc2 is read ONCE per tile.  Reading tensor memory is slow while the tensor pipe runs (measured ~900 cycles per
+        // 32-column load), and GEMM2 of the next tile may only start when the epilogue has released acc2: with the three
+        // passes of round 1 (sum, variance, normalise) the epilogue held the accumulator for 27,000 cycles per tile -- longer
+        // than GEMM1 -- and the chain epilogue -> GEMM2 -> epilogue set the kernel's period (issuer trace: 9,500 of a tile's
+        // 34,000 cycles waiting for acc2).  Now:
+        //   pass A (thread = row = TMEM lane): per 32-column chunk ReLU(acc2 [+ b2]), row statistics, and the RAW values stored
+        //           to their place in `out` (through shared memory, so that four lanes write 64 contiguous bytes of a row);
+        //           after the last chunk acc2 is released;
+        //   pass B: the warp re-reads its 32 raw rows from L2 (they were written microseconds ago), a row at a time, fully
+        //           coalesced, normalises with the row's statistics (shuffled from the lane that owns the row) and the lane's
+        //           own columns of scale / offset (registers), and overwrites them.
         // One-pass statistics about a pivot: with d = x - c (c = the row's first value), mean = c + sum(d) / H and
         // var = (sum(d^2) - sum(d)^2 / H) / H; the pivot keeps the subtraction benign (|mean - c| is of the order of the
         // standard deviation), unlike the raw sum of squares.
         const int NCH = (P.n2 + 31) / 32;  // chunks of 32 columns; the last one may hold 16
+        const uint32_t lane_e = (uint32_t)tid & 31u, wbase = sOut + (uint32_t)(warp & 3) * 2048u;
+        const int q4 = H >> 2;  // float4 per row
+        // this lane's columns in pass B: float4 lane_e and lane_e + 32 of a row
+        float4 gsc[2], gof[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const int c = 4 * ((int)lane_e + 32 * t);
+            gsc[t] = c < H ? lds4(sPar + (MAX_N + c) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gof[t] = c < H ? lds4(sPar + (2 * MAX_N + c) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         float xb[32];
         auto request = [&](int ch) {
             const int c0 = 32 * ch;
@@ -768,63 +845,129 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
             else
                 tmem_ld16_nowait(tmem + lane_base + (uint32_t)(TS_ACC2_COL + c0), xb);
         };
-        auto bias_relu = [&](int c0, float* x) {  // x = ReLU(acc2 + b2) for the chunk in xb (columns past n2: untouched)
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                if (c0 + 4 * q < P.n2) {
-                    const float4 b = lds4(sPar + (c0 + 4 * q) * 4);
-                    x[4 * q] = fmaxf(xb[4 * q] + b.x, 0.f), x[4 * q + 1] = fmaxf(xb[4 * q + 1] + b.y, 0.f);
-                    x[4 * q + 2] = fmaxf(xb[4 * q + 2] + b.z, 0.f), x[4 * q + 3] = fmaxf(xb[4 * q + 3] + b.w, 0.f);
-                }
-            }
-        };
         for (uint32_t it = 0; it < my_tiles; it++) {
             const int tile = (int)(blockIdx.x + it * gridDim.x);
+            const int row0 = tile * TILE_M + (warp & 3) * 32;  // first row of this warp
             mbar_wait_relaxed(sAccFull, it & 1u);
+#ifdef GNN_TRACE
+            if (tid == MLPP_EPILOGUE0 && it >= (uint32_t)TRACE_TILE0 && it < (uint32_t)(TRACE_TILE0 + TRACE_TILES)) GNN_STAMP(TRACE_EPI + 4 * (it - TRACE_TILE0));
+#endif
             tc_fence_after();
             float sd = 0.f, sd2 = 0.f, pivot = 0.f;
             request(0);
             for (int ch = 0; ch < NCH; ch++) {
                 float x[32];
                 tmem_wait_ld();
-                bias_relu(32 * ch, x);
-                if (ch + 1 < NCH) request(ch + 1);
-                if (ch == 0) pivot = x[0];
+#ifdef GNN_TRACE
+                const bool trc = (ch == 3 || ch == 4) && tid == MLPP_EPILOGUE0 && it == (uint32_t)TRACE_TILE0;
+                if (trc) GNN_STAMP(TRACE_EPI + 32 + 8 * (ch - 3));
+#endif
+                if constexpr (BF) {  // b2 came through the GEMM
 #pragma unroll
-                for (int i = 0; i < 32; i++)
-                    if (32 * ch + i < H) {
-                        const float d = x[i] - pivot;
-                        sd += d;
-                        sd2 = fmaf(d, d, sd2);
+                    for (int i = 0; i < 32; i++) x[i] = fmaxf(xb[i], 0.f);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        if (32 * ch + 4 * q < P.n2) {
+                            const float4 b = lds4(sPar + (32 * ch + 4 * q) * 4);
+                            x[4 * q] = fmaxf(xb[4 * q] + b.x, 0.f), x[4 * q + 1] = fmaxf(xb[4 * q + 1] + b.y, 0.f);
+                            x[4 * q + 2] = fmaxf(xb[4 * q + 2] + b.z, 0.f), x[4 * q + 3] = fmaxf(xb[4 * q + 3] + b.w, 0.f);
+                        }
                     }
-            }
-            const float md = sd / (float)H, mean = pivot + md;
-            const float rstd = rsqrtf(fmaxf(sd2 / (float)H - md * md, 0.f) + 1e-5f);
-            const int row = tile * TILE_M + erow;
-            float* orow = P.out + (size_t)min(row, P.rows - 1) * H;
-            request(0);
-            for (int ch = 0; ch < NCH; ch++) {
-                float x[32];
-                tmem_wait_ld();
-                bias_relu(32 * ch, x);
+                }
+#ifdef GNN_TRACE
+                if (trc) GNN_STAMP(TRACE_EPI + 33 + 8 * (ch - 3));
+#endif
                 if (ch + 1 < NCH) {
                     request(ch + 1);
-                } else {  // the last read of acc2 has landed: GEMM2 of the next tile may overwrite it while this chunk is stored
+                } else {  // the last read of acc2 has landed: GEMM2 of the next tile may overwrite it
                     tc_fence_before();
                     mbar_arrive(sAccFree);
+#ifdef GNN_TRACE
+                    if (tid == MLPP_EPILOGUE0 && it >= (uint32_t)TRACE_TILE0 && it < (uint32_t)(TRACE_TILE0 + TRACE_TILES)) GNN_STAMP(TRACE_EPI + 4 * (it - TRACE_TILE0) + 1);
+#endif
                 }
+#ifdef GNN_TRACE
+                if (trc) GNN_STAMP(TRACE_EPI + 34 + 8 * (ch - 3));
+#endif
+                if (ch == 0) pivot = x[0];
+                {  // four partial sums per moment: the additions of a chunk are not one dependent chain
+                    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const int c = 32 * ch + 4 * q;
-                    if (c < H && row < P.rows) {
-                        const float4 sc = lds4(sPar + (MAX_N + c) * 4), of = lds4(sPar + (2 * MAX_N + c) * 4);
-                        float4 y;
-                        y.x = (x[4 * q] - mean) * rstd * sc.x + of.x, y.y = (x[4 * q + 1] - mean) * rstd * sc.y + of.y;
-                        y.z = (x[4 * q + 2] - mean) * rstd * sc.z + of.z, y.w = (x[4 * q + 3] - mean) * rstd * sc.w + of.w;
-                        *reinterpret_cast<float4*>(orow + c) = y;
+                    for (int i = 0; i < 32; i++) {
+                        const float d = (32 * ch + i < H) ? x[i] - pivot : 0.f;
+                        s1[i & 3] += d;
+                        s2[i & 3] = fmaf(d, d, s2[i & 3]);
+                    }
+                    sd += (s1[0] + s1[1]) + (s1[2] + s1[3]);
+                    sd2 += (s2[0] + s2[1]) + (s2[2] + s2[3]);
+                }
+#ifdef GNN_TRACE
+                if (trc) GNN_STAMP(TRACE_EPI + 35 + 8 * (ch - 3));
+#endif
+                // raw values to `out` through shared memory: each lane parks 16 columns of its row (four 16-byte units, unit
+                // index XORed with (row / 2) % 4: conflict-free both ways), then four lanes store 64 contiguous bytes of one
+                // row -- a store instruction covers 8 rows x 2 full sectors instead of 32 rows x half a sector
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    const int c16 = 32 * ch + 16 * half;
+                    if (c16 < H) {
+#pragma unroll
+                        for (uint32_t u = 0; u < 4; u++)
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(wbase + lane_e * 64u + ((u ^ ((lane_e >> 1) & 3u)) << 4)),
+                                         "f"(x[16 * half + 4 * u]), "f"(x[16 * half + 4 * u + 1]), "f"(x[16 * half + 4 * u + 2]), "f"(x[16 * half + 4 * u + 3])
+                                         : "memory");
+                        __syncwarp();
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; k++) {
+                            const uint32_t r = 8u * k + (lane_e >> 2), u = lane_e & 3u;
+                            const float4 y = lds4(wbase + r * 64u + ((u ^ ((r >> 1) & 3u)) << 4));
+                            const int grow = row0 + (int)r, col = c16 + 4 * (int)u;
+                            if (col < H && grow < P.rows) *reinterpret_cast<float4*>(P.out + (size_t)grow * H + col) = y;
+                        }
+                        __syncwarp();
+#ifdef GNN_TRACE
+                        if (trc) GNN_STAMP(TRACE_EPI + 36 + half + 8 * (ch - 3));
+#endif
                     }
                 }
             }
+#ifdef GNN_TRACE
+            if (tid == MLPP_EPILOGUE0 && it >= (uint32_t)TRACE_TILE0 && it < (uint32_t)(TRACE_TILE0 + TRACE_TILES)) GNN_STAMP(TRACE_EPI + 4 * (it - TRACE_TILE0) + 2);
+#endif
+            const float md = sd / (float)H, mean = pivot + md;
+            const float rstd = rsqrtf(fmaxf(sd2 / (float)H - md * md, 0.f) + 1e-5f);
+            // ---- pass B: the warp's rows again, from L2 (ld.global.cg: the lines were written by other lanes of this warp;
+            // the barrier above ordered those stores), four rows in flight
+            const int nrows = min(32, P.rows - row0);  // warp-uniform; <= 0 for a warp past the end
+            for (int r0 = 0; r0 < nrows; r0 += 4) {
+                float4 v[4][2];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float4* rowp = reinterpret_cast<const float4*>(P.out + (size_t)(row0 + min(r0 + k, nrows - 1)) * H);
+#pragma unroll
+                    for (int t = 0; t < 2; t++)
+                        if ((int)lane_e + 32 * t < q4) v[k][t] = __ldcg(rowp + lane_e + 32 * t);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float m = __shfl_sync(0xffffffffu, mean, (r0 + k) & 31), rs = __shfl_sync(0xffffffffu, rstd, (r0 + k) & 31);
+                    if (r0 + k < nrows) {
+                        float4* rowp = reinterpret_cast<float4*>(P.out + (size_t)(row0 + r0 + k) * H);
+#pragma unroll
+                        for (int t = 0; t < 2; t++)
+                            if ((int)lane_e + 32 * t < q4) {
+                                float4 y;
+                                y.x = (v[k][t].x - m) * rs * gsc[t].x + gof[t].x, y.y = (v[k][t].y - m) * rs * gsc[t].y + gof[t].y;
+                                y.z = (v[k][t].z - m) * rs * gsc[t].z + gof[t].z, y.w = (v[k][t].w - m) * rs * gsc[t].w + gof[t].w;
+                                rowp[lane_e + 32 * t] = y;
+                            }
+                    }
+                }
+            }
+#ifdef GNN_TRACE
+            if (tid == MLPP_EPILOGUE0 && it >= (uint32_t)TRACE_TILE0 && it < (uint32_t)(TRACE_TILE0 + TRACE_TILES)) GNN_STAMP(TRACE_EPI + 4 * (it - TRACE_TILE0) + 3);
+#endif
         }
     }
     tc_fence_before();
@@ -858,49 +1001,54 @@ __global__ void embed_onehot_kernel(const uint8_t* __restrict__ type, const floa
 
 // jraph.utils.segment_sum over a CSR of edge ids (edge order inside a segment = increasing edge id, i.e. the order a
 // sequential scatter-add visits them): out[v] = sum_{j in [ptr[v], ptr[v+1])} e[ids[j]], for both directions of every node in
-// one launch (pair 2v = the edges node v sends, pair 2v+1 = those it receives; nodes and edges of an instance are contiguous
-// in a batch, so the two sweeps over an instance's edge rows fall into the same time window and the second is served by L2).
-// ONE THREAD PER (pair, 16-byte column): consecutive threads read consecutive 16 bytes of the same edge row, every lane of a
-// warp has work (round 1's warp-per-pair form left 14 of 32 lanes idle on the second half of an 800-byte row), and a pair
-// with fewer than two edges is not summed at all: the node update reads the zero row or the edge row itself through
-// agg_index_kernel's indices.  Four row loads in flight per thread; the additions of an output element happen in list order
-// (deterministic, same values as a sequential scatter-add).
-// Q4 = float4 per row as a compile-time constant (50 for the shipped H = 200: the thread -> (pair, column) split is a
-// multiply-shift instead of a division), 0 = taken from H at run time.  A block serves 256 / q4 whole pairs.
-template <int Q4>
-__global__ void __launch_bounds__(256) segment_sum_flat_kernel(const float* __restrict__ e, const int64_t* __restrict__ ptr0,
-                                                               const int32_t* __restrict__ ids0, float* __restrict__ out0,
-                                                               const int64_t* __restrict__ ptr1, const int32_t* __restrict__ ids1,
-                                                               float* __restrict__ out1, int64_t n_node, int H)
+// one launch: warp 2v adds the rows of the edges node v sends, warp 2v+1 those it receives (nodes and edges of an instance are
+// contiguous in a batch, so the two sweeps over an instance's edge rows fall into the same time window and the second is
+// served by L2).  16-byte loads (lane l owns float4 l and l+32 of the row), edge ids fetched 32 at a time and broadcast by
+// shuffle so that the row loads of consecutive edges are independent and eight are in flight per lane.  The additions of one
+// output element happen in list order (deterministic, same values as a sequential scatter-add).
+// A pair with fewer than two edges is not summed at all: the node update reads the zero row or the edge row itself through
+// agg_index_kernel's indices (2/3 of an LCG graph's pairs: clause nodes send nothing, positive literals receive nothing,
+// negative literals receive only their pair edge).
+// (Round 2 also measured one thread per (pair, 16-byte column) -- no idle lanes on the second half of an 800-byte row -- at
+// 4.2 ms per forward against 3.4 ms for this form: four loads in flight per thread were too few.)
+__global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restrict__ e, const int64_t* __restrict__ ptr0,
+                                                          const int32_t* __restrict__ ids0, float* __restrict__ out0,
+                                                          const int64_t* __restrict__ ptr1, const int32_t* __restrict__ ids1,
+                                                          float* __restrict__ out1, int64_t n_node, int H)
 {
-    const uint32_t q4 = Q4 ? (uint32_t)Q4 : (uint32_t)H >> 2;  // float4 per row
-    const uint32_t per_block = 256u / q4;
-    const uint32_t lp = threadIdx.x / q4;
-    if (lp >= per_block) return;
-    const uint32_t q = threadIdx.x - lp * q4;
-    const int64_t pair = (int64_t)blockIdx.x * per_block + lp;
-    const int64_t v = pair >> 1;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t v = w >> 1;
+    const int lane = threadIdx.x & 31;
     if (v >= n_node) return;
-    const bool second = (pair & 1) != 0;
+    const bool second = (w & 1) != 0;
     const int64_t* __restrict__ ptr = second ? ptr1 : ptr0;
-    const int64_t s = __ldg(ptr + v), end = __ldg(ptr + v + 1);
-    if (end - s < 2) return;
+    const int64_t s = __ldg(ptr + v), t = __ldg(ptr + v + 1);
+    if (t - s < 2) return;
     const int32_t* __restrict__ ids = second ? ids1 : ids0;
-    const float4* __restrict__ rows = reinterpret_cast<const float4*>(e) + q;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    // four edges per round, all four row loads issued before the first addition; a short last round re-reads the segment's
-    // last row (a cache hit) and leaves it out of the sum, so no round is a chain of dependent loads
-    for (int64_t k = s; k < end; k += 4) {
-        const int64_t last = end - 1;
-        const int32_t i0 = __ldg(ids + k), i1 = __ldg(ids + min(k + 1, last)), i2 = __ldg(ids + min(k + 2, last)), i3 = __ldg(ids + min(k + 3, last));
-        const float4 x0 = __ldg(rows + (size_t)i0 * q4), x1 = __ldg(rows + (size_t)i1 * q4), x2 = __ldg(rows + (size_t)i2 * q4),
-                     x3 = __ldg(rows + (size_t)i3 * q4);
-        a.x += x0.x, a.y += x0.y, a.z += x0.z, a.w += x0.w;
-        if (k + 1 < end) a.x += x1.x, a.y += x1.y, a.z += x1.z, a.w += x1.w;
-        if (k + 2 < end) a.x += x2.x, a.y += x2.y, a.z += x2.z, a.w += x2.w;
-        if (k + 3 < end) a.x += x3.x, a.y += x3.y, a.z += x3.z, a.w += x3.w;
+    float* __restrict__ out = second ? out1 : out0;
+    const int q = H >> 2;  // float4 per row (H is a multiple of 4, at most 64 float4 = 256 columns)
+    const bool has0 = lane < q, has1 = lane + 32 < q;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    for (int64_t base = s; base < t; base += 32) {
+        const int cnt = (int)min((int64_t)32, t - base);
+        const int32_t my_id = lane < cnt ? __ldg(ids + base + lane) : 0;
+#pragma unroll 8
+        for (int k = 0; k < cnt; k++) {
+            const int32_t id = __shfl_sync(0xffffffffu, my_id, k);
+            const float4* row = reinterpret_cast<const float4*>(e + (size_t)id * H);
+            if (has0) {
+                const float4 x = __ldg(row + lane);
+                a0.x += x.x, a0.y += x.y, a0.z += x.z, a0.w += x.w;
+            }
+            if (has1) {
+                const float4 x = __ldg(row + lane + 32);
+                a1.x += x.x, a1.y += x.y, a1.z += x.z, a1.w += x.w;
+            }
+        }
     }
-    reinterpret_cast<float4*>((second ? out1 : out0) + (size_t)v * H)[q] = a;
+    float4* o = reinterpret_cast<float4*>(out + (size_t)v * H);
+    if (has0) o[lane] = a0;
+    if (has1) o[lane + 32] = a1;
 }
 
 // Row indices of a node's two aggregates in the array [eA (E rows) | sent (N) | recv (N) | zero (1) | eB (E)] (gnn_api.cu,
