@@ -484,7 +484,7 @@ def leg_c4_pipeline(ctx):
         "instances_per_s": n_fw / (best_ms * 1e-3), "device_ms": best_ms, "e2e_instances_per_s": n_fw / best_wall,
         "precision": os.environ.get("SLS_B200_GNN_PRECISION", "bf16x2"), "dense_tflops": flops / (best_ms * 1e-3) / 1e12,
         "gpu_launches": launches, "kernel_class_ms": prof,
-        "kernel": "gnn::mlp_ln_persistent_ts_kernel (tcgen05 kind::f16, A operand in TMEM) + segment_sum_flat_kernel",
+        "kernel": "gnn::mlp_ln_persistent_ts_kernel (tcgen05 kind::f16, A operand in TMEM) + segment_sum_kernel",
         "roofline": {
             "bound": "tensor", "achieved": flops / (mlp_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
             "frac": flops / (mlp_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"],
@@ -620,22 +620,26 @@ def leg_clause_eval(ctx):
     peak = ub.get("l2_sector32_gbs_8_in_flight") or ub.get("l2_sector32_gbs_4_in_flight")
     out = {"workload": f"{B} random assignments x the C5 instance ({C5_M} clauses), host buffers in / out"}
     for name, vb in (("energy_only", None), ("with_violated_bits", bits)):
-        best, wall = 1e30, 1e30
+        best, kern, wall = 1e30, 1e30, 1e30
         for _ in range(3):
             t0 = time.perf_counter()
             rc = lib.sls_eval_assignments(inst._h, a.ctypes.data, B, vb.ctypes.data if vb is not None else None, energy.ctypes.data)
             wall = min(wall, time.perf_counter() - t0)
             if rc != 0:
                 raise RuntimeError(lib.sls_last_error().decode())
-            best = min(best, eng.eval_last_kernel_ms())
+            if eng.eval_last_kernel_ms() < best:
+                best, kern = eng.eval_last_kernel_ms(), eng.eval_last_eval_kernel_ms()
         out[name] = {
-            "value": B * C5_M / (best * 1e-3), "unit": "clause evaluations/s", "device_ms": best,
+            # value: both device kernels (byte -> bit-slice transposition of the 1 GB of assignment bytes + evaluation);
+            # the roofline is the evaluation kernel's own (kernel_ms)
+            "value": B * C5_M / (best * 1e-3), "unit": "clause evaluations/s", "device_ms": best, "kernel_ms": kern,
+            "kernel": "eval_energy_sliced_kernel" if vb is None else "eval_sliced_kernel<out>",
             "e2e": {"value": B * C5_M / wall, "unit": "clause evaluations/s", "h2d_bytes_per_step": int(a.nbytes),
                     "d2h_bytes_per_step": int(energy.nbytes + (vb.nbytes if vb is not None else 0))},
-            "roofline": {"bound": "l2 random sectors", "contract_bound": "hbm", "achieved": sector_bytes / (best * 1e-3) / 1e9, "peak": peak,
-                         "unit": "GB/s", "frac": (sector_bytes / (best * 1e-3) / 1e9 / peak) if peak else None, "traffic": None,
+            "roofline": {"bound": "l2 random sectors", "contract_bound": "hbm", "achieved": sector_bytes / (kern * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": (sector_bytes / (kern * 1e-3) / 1e9 / peak) if peak else None, "traffic": None,
                          "peak_source": "measured in this run (tools/ubench.cu l2_sector32)",
-                         "hbm_algorithmic_gbs": (B / 256 * C5_M * 12 + B * C5_N / 8 + (B * C5_M / 8 if vb is not None else 0)) / (best * 1e-3) / 1e9},
+                         "hbm_algorithmic_gbs": (B / 256 * C5_M * 12 + B * C5_N / 8 + (B * C5_M / 8 if vb is not None else 0)) / (kern * 1e-3) / 1e9},
             "mean_energy": float(energy.mean()),
         }
     if ctx["cpu"]:

@@ -81,6 +81,8 @@ int sls_eval_assignments(sls_instance *inst, const uint8_t *assignments, uint64_
 /* device time (ms, CUDA events: transposition + evaluation kernels, no copies) of the calling thread's last
  * sls_eval_assignments -- measurement only, no reference equivalent */
 double sls_eval_last_kernel_ms(void);
+/* ... and of its evaluation kernel alone (the byte -> bit-slice transposition of the assignments excluded) */
+double sls_eval_last_eval_kernel_ms(void);
 
 /* ---- clause neighbourhood of the LLL loss: replaces LCG.get_constraint_graph
  *      (python/src/sat_representations.py:668-715, scipy C^T C of the variable-clause incidence).  Host-side, no GPU

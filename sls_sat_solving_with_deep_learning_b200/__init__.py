@@ -17,6 +17,7 @@ from .solver import (  # noqa: F401
     candidate_energies,
     device_count,
     eval_assignments,
+    eval_last_eval_kernel_ms,
     eval_last_kernel_ms,
     get_violated_constraints,
     run_sls,

@@ -112,6 +112,7 @@ SYMBOLS = {
     "sls_instance_get_csr": (C.c_int, [_vp, _vp, _vp]),
     "sls_eval_assignments": (C.c_int, [_vp, _vp, C.c_uint64, _vp, _vp]),
     "sls_eval_last_kernel_ms": (C.c_double, []),
+    "sls_eval_last_eval_kernel_ms": (C.c_double, []),
     "sls_constraint_graph": (C.c_int, [C.c_uint32, C.c_uint32, _vp, _vp, C.c_uint64, _vp, _vp, C.c_uint64, _vp]),
     "sls_run": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_size_t, C.POINTER(RunParams), C.POINTER(RunResult)]),
     "sls_run_batch": (C.c_int, [C.POINTER(_vp), C.c_uint32, _vp, _vp, _vp, _vp, C.POINTER(RunParams), C.POINTER(RunResult)]),

@@ -336,6 +336,7 @@ extern "C" int sls_instance_get_csr(const sls_instance* inst, uint64_t* row_ptr,
 
 // ------------------------------------------------------- clause evaluation
 static thread_local double g_last_eval_ms = 0.0;  // device time of the calling thread's last sls_eval_assignments
+static thread_local double g_last_eval_only_ms = 0.0;  // ... of its evaluation kernel alone (without the transposition)
 
 extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignments, uint64_t batch,
                                     uint32_t* violated_bits, uint32_t* energy)
@@ -353,7 +354,7 @@ extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignmen
     if (nslices > 65535) return set_error(SLS_ERR_ARG, "batch too large for one call (max 16776960 rows)");
     uint8_t* d_bytes = nullptr;
     uint32_t *d_tq = nullptr, *d_v = nullptr, *d_e = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr;
     auto cleanup = [&] {
         dfree(d_bytes);
         dfree(d_tq);
@@ -361,6 +362,7 @@ extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignmen
         dfree(d_e);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (evm) cudaEventDestroy(evm);
     };
     const size_t n1 = std::max<uint32_t>(I.n, 1);
     // device rows of violated bits are padded to whole tiles so that a tile row is one aligned 32-byte sector
@@ -380,6 +382,7 @@ extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignmen
     if (violated_bits) EV_TRY(dmalloc(&d_v, batch * (size_t)pitch * 4));
     EV_TRY(cudaEventCreate(&ev0));
     EV_TRY(cudaEventCreate(&ev1));
+    EV_TRY(cudaEventCreate(&evm));
     if (I.n) EV_TRY(cudaMemcpy(d_bytes, assignments, batch * (size_t)I.n, cudaMemcpyHostToDevice));
     InFlight mark;  // an error exit below waits for the device before its buffers are freed
     EV_TRY(cudaEventRecord(ev0));
@@ -388,6 +391,7 @@ extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignmen
         const uint64_t total = nslices * I.n;
         transpose_assignments_kernel<<<(unsigned)((total + 255) / 256), 256>>>(d_bytes, d_tq, I.n, batch, (uint32_t)nslices);
     }
+    EV_TRY(cudaEventRecord(evm));
     {
         constexpr int WARPS = 4;
         // Small tiles-per-CTA: with many more CTAs per slice than the machine holds, the resident CTAs belong to
@@ -429,6 +433,8 @@ extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignmen
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev0, ev1);
         g_last_eval_ms = ms;
+        cudaEventElapsedTime(&ms, evm, ev1);
+        g_last_eval_only_ms = ms;
     }
     if (energy) EV_TRY(cudaMemcpy(energy, d_e, batch * 4, cudaMemcpyDeviceToHost));
     if (violated_bits)
@@ -440,6 +446,7 @@ extern "C" int sls_eval_assignments(sls_instance* inst, const uint8_t* assignmen
 }
 
 extern "C" double sls_eval_last_kernel_ms(void) { return g_last_eval_ms; }
+extern "C" double sls_eval_last_eval_kernel_ms(void) { return g_last_eval_only_ms; }
 
 // ------------------------------------------------------- constraint graph (host)
 extern "C" int sls_constraint_graph(uint32_t n_variables, uint32_t n_clauses, const int32_t* var_of, const int32_t* clause_of,

@@ -806,7 +806,6 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
         }
     } else if (epilogue) {
         const int H = P.h2;
-        const int erow = (warp & 3) * 32 + (tid & 31);
         auto lds4 = [](uint32_t a) {
             float4 v;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));

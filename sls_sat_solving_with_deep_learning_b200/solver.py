@@ -148,6 +148,11 @@ def eval_last_kernel_ms() -> float:
     return float(_lib.load().sls_eval_last_kernel_ms())
 
 
+def eval_last_eval_kernel_ms() -> float:
+    """... of its evaluation kernel alone (the transposition of the assignment bytes into bit slices excluded)."""
+    return float(_lib.load().sls_eval_last_eval_kernel_ms())
+
+
 def candidate_energies(inst: Instance, candidates) -> np.ndarray:
     """Energies of a stack of candidate assignments as the training loader computes them
     (python/src/data_utils.py:123-129: ``vmap(get_violated_constraints)`` over the candidates, summed and divided
