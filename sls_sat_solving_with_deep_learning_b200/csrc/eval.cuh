@@ -18,7 +18,7 @@ namespace slsb {
 // not at its byte rate).  A lane owns one clause and evaluates it for the whole slice with bitwise ops;
 // the 32 clauses of a warp form 32x32 bit tiles that are transposed in registers (5 shuffle rounds per tile
 // instead of 32 ballots) so that each assignment gets its violated-set word; the words of 8 consecutive
-// clause words are staged in shared memory and leave as whole 32-byte sectors per assignment.
+// clause words are collected in registers and leave as one whole 32-byte sector per assignment (a 256-bit store).
 static constexpr uint32_t SLICE_W = 256, SLICE_Q = SLICE_W / 32, TILE_WORDS = 8;
 
 // Transposes of the eight 32x32 bit tiles a row of clauses holds (x[q], one tile row per lane): on return lane b
@@ -176,7 +176,6 @@ __global__ void __launch_bounds__(WARPS * 32) eval_sliced_kernel(const DevInst I
                                                                  uint32_t* __restrict__ vout, uint32_t pitch,
                                                                  uint32_t* __restrict__ energy, uint64_t batch, uint32_t tiles_per_block)
 {
-    __shared__ uint32_t stage[OUT ? WARPS : 1][OUT ? SLICE_W : 1][TILE_WORDS + 1];  // +1: the column stores of a tile hit 32 banks
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const uint32_t slice = blockIdx.y;
@@ -194,7 +193,13 @@ __global__ void __launch_bounds__(WARPS * 32) eval_sliced_kernel(const DevInst I
     const uint32_t t0 = min(t_end, t_begin + warp * per_warp), t1 = min(t_end, t0 + per_warp);
     ClauseRows rows(I, tq, t0 * TILE_WORDS * 32u + lane);
     for (uint32_t t = t0; t < t1; t++) {
-#pragma unroll 1
+        // After the transposition lane b holds, for each of its eight assignments 32q + b, the violated-set word of the row.
+        // The eight rows of a tile are kept in registers (acc[q][wi]) and leave as ONE 32-byte sector per assignment: a
+        // 256-bit store per lane and q, no staging in shared memory (round 1 staged the tile: 64 shared-memory stores, 64
+        // loads and 64 four-byte global stores per tile next to the 320 shuffles of the transpositions -- ncu: the kernel
+        // was bound by the shared-memory / shuffle instruction queue, mio_throttle + short_scoreboard).
+        uint32_t acc[OUT ? SLICE_Q : 1][OUT ? TILE_WORDS : 1];
+#pragma unroll
         for (uint32_t wi = 0; wi < TILE_WORDS; wi++) {
             uint32_t viol[SLICE_Q];
             rows.next(viol);
@@ -202,18 +207,19 @@ __global__ void __launch_bounds__(WARPS * 32) eval_sliced_kernel(const DevInst I
 #pragma unroll
             for (uint32_t q = 0; q < SLICE_Q; q++) {
                 my_energy[q] += __popc(viol[q]);
-                if (OUT) stage[warp][32u * q + lane][wi] = viol[q];
+                if (OUT) acc[q][wi] = viol[q];
             }
         }
         if (OUT) {
-            __syncwarp();
-            // one store instruction = 4 assignments x 8 words = four whole sectors
-            const uint32_t j = lane & 7u, w = t * TILE_WORDS + j;
-            for (uint32_t r = 0; r < SLICE_W / 4; r++) {
-                const uint32_t a = r * 4u + (lane >> 3);
-                if (a < valid && w < pitch) __stcs(vout + (b0 + a) * (size_t)pitch + w, stage[warp][a][j]);  // written once, never re-read here
+            const uint32_t w = t * TILE_WORDS;  // pitch is a multiple of TILE_WORDS: the sector lies inside the row
+#pragma unroll
+            for (uint32_t q = 0; q < SLICE_Q; q++) {
+                const uint32_t a = 32u * q + lane;
+                if (a < valid)  // written once, never re-read here: evict-first
+                    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(vout + (b0 + a) * (size_t)pitch + w), "r"(acc[q][0]),
+                                 "r"(acc[q][1]), "r"(acc[q][2]), "r"(acc[q][3]), "r"(acc[q][4]), "r"(acc[q][5]), "r"(acc[q][6]), "r"(acc[q][7])
+                                 : "memory");
             }
-            __syncwarp();
         }
     }
     if (energy) {
