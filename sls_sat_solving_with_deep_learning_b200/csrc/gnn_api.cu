@@ -462,7 +462,7 @@ int forward_device(sls_gnn_model* m, int64_t N, int64_t E, const float* d_nodes,
         // node update sees [nodes | segment_sum(new edges, senders) | segment_sum(new edges, receivers)]; only the sums over two
         // or more edges are materialised
         if (N) {
-            const unsigned blocks = (unsigned)((2 * N * 32 + 255) / 256);
+            const unsigned blocks = (unsigned)((N * 32 + 255) / 256);
             if ((rc = timed(2, [&] { segment_sum_kernel<<<blocks, 256>>>(e, d_sptr, d_sids, sent, d_rptr, d_rids, recv, N, H); })))
                 return rc;
             m->launches += 1;

@@ -1000,9 +1000,8 @@ __global__ void embed_onehot_kernel(const uint8_t* __restrict__ type, const floa
 
 // jraph.utils.segment_sum over a CSR of edge ids (edge order inside a segment = increasing edge id, i.e. the order a
 // sequential scatter-add visits them): out[v] = sum_{j in [ptr[v], ptr[v+1])} e[ids[j]], for both directions of every node in
-// one launch: warp 2v adds the rows of the edges node v sends, warp 2v+1 those it receives (nodes and edges of an instance are
-// contiguous in a batch, so the two sweeps over an instance's edge rows fall into the same time window and the second is
-// served by L2).  16-byte loads (lane l owns float4 l and l+32 of the row), edge ids fetched 32 at a time and broadcast by
+// one launch (nodes and edges of an instance are contiguous in a batch, so the two sweeps over an instance's edge rows fall
+// into the same time window and the second is served by L2).  16-byte loads (lane l owns float4 l and l+32 of the row), edge ids fetched 32 at a time and broadcast by
 // shuffle so that the row loads of consecutive edges are independent and eight are in flight per lane.  The additions of one
 // output element happen in list order (deterministic, same values as a sequential scatter-add).
 // A pair with fewer than two edges is not summed at all: the node update reads the zero row or the edge row itself through
@@ -1015,39 +1014,43 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restric
                                                           const int64_t* __restrict__ ptr1, const int32_t* __restrict__ ids1,
                                                           float* __restrict__ out1, int64_t n_node, int H)
 {
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t v = w >> 1;
+    // one warp per NODE, both directions one after the other: in an LCG graph a node needs at most one of the two sums (literals
+    // send, clauses receive), so every warp of the launch has exactly one sum to do; with a warp per (node, direction) half of
+    // the warps of every CTA retired at once and their slots stayed empty until the CTA's other warps were done
+    const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (v >= n_node) return;
-    const bool second = (w & 1) != 0;
-    const int64_t* __restrict__ ptr = second ? ptr1 : ptr0;
-    const int64_t s = __ldg(ptr + v), t = __ldg(ptr + v + 1);
-    if (t - s < 2) return;
-    const int32_t* __restrict__ ids = second ? ids1 : ids0;
-    float* __restrict__ out = second ? out1 : out0;
     const int q = H >> 2;  // float4 per row (H is a multiple of 4, at most 64 float4 = 256 columns)
     const bool has0 = lane < q, has1 = lane + 32 < q;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-    for (int64_t base = s; base < t; base += 32) {
-        const int cnt = (int)min((int64_t)32, t - base);
-        const int32_t my_id = lane < cnt ? __ldg(ids + base + lane) : 0;
+#pragma unroll 1
+    for (int dir = 0; dir < 2; dir++) {
+        const int64_t* __restrict__ ptr = dir ? ptr1 : ptr0;
+        const int64_t s = __ldg(ptr + v), t = __ldg(ptr + v + 1);
+        if (t - s < 2) continue;
+        const int32_t* __restrict__ ids = dir ? ids1 : ids0;
+        float* __restrict__ out = dir ? out1 : out0;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        for (int64_t base = s; base < t; base += 32) {
+            const int cnt = (int)min((int64_t)32, t - base);
+            const int32_t my_id = lane < cnt ? __ldg(ids + base + lane) : 0;
 #pragma unroll 8
-        for (int k = 0; k < cnt; k++) {
-            const int32_t id = __shfl_sync(0xffffffffu, my_id, k);
-            const float4* row = reinterpret_cast<const float4*>(e + (size_t)id * H);
-            if (has0) {
-                const float4 x = __ldg(row + lane);
-                a0.x += x.x, a0.y += x.y, a0.z += x.z, a0.w += x.w;
-            }
-            if (has1) {
-                const float4 x = __ldg(row + lane + 32);
-                a1.x += x.x, a1.y += x.y, a1.z += x.z, a1.w += x.w;
+            for (int k = 0; k < cnt; k++) {
+                const int32_t id = __shfl_sync(0xffffffffu, my_id, k);
+                const float4* row = reinterpret_cast<const float4*>(e + (size_t)id * H);
+                if (has0) {
+                    const float4 x = __ldg(row + lane);
+                    a0.x += x.x, a0.y += x.y, a0.z += x.z, a0.w += x.w;
+                }
+                if (has1) {
+                    const float4 x = __ldg(row + lane + 32);
+                    a1.x += x.x, a1.y += x.y, a1.z += x.z, a1.w += x.w;
+                }
             }
         }
+        float4* o = reinterpret_cast<float4*>(out + (size_t)v * H);
+        if (has0) o[lane] = a0;
+        if (has1) o[lane + 32] = a1;
     }
-    float4* o = reinterpret_cast<float4*>(out + (size_t)v * H);
-    if (has0) o[lane] = a0;
-    if (has1) o[lane + 32] = a1;
 }
 
 // Row indices of a node's two aggregates in the array [eA (E rows) | sent (N) | recv (N) | zero (1) | eB (E)] (gnn_api.cu,
