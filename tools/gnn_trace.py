@@ -36,13 +36,6 @@ x = t[EPI + 32: EPI + 48]
 if x[0]:
     names = ["TMEM wait returned", "ReLU done", "next request issued", "statistics done", "half 0 stored", "half 1 stored"]
     for ch in (3, 4):
-        print(f"pass A, chunk {ch} of the first traced tile (cycles since chunk 3's TMEM wait returned):")
+        print(f"pass A, chunk {ch} of the first traced tile (stamps; arithmetic may float across them):")
         for i, nm in enumerate(names):
             print(f"  {nm:22s} +{int(x[8 * (ch - 3) + i] - x[0])}")
-
-print("raw latency of a 32-column tcgen05.ld + wait at the start of the first traced tile's epilogue (cycles):", int(t[EPI + 48]), int(t[EPI + 49]),
-      "; with eight global stores of the lane in flight:", int(t[EPI + 50]), int(t[EPI + 51]))
-
-ph = [int(v) for v in t[EPI + 56: EPI + 64]]
-print("pass A of the first traced tile, cycles summed over its chunks: TMEM wait", ph[0], "| ReLU (and, per half, the work before the parking stores)", ph[6], "| issuing the next TMEM request", ph[7],
-      "| parking stores issued", ph[1], "| barrier", ph[2], "| staging loads + global stores issued", ph[3], "| barrier", ph[4], "| loop / request", ph[5])
