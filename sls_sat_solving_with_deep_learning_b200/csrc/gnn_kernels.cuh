@@ -256,7 +256,11 @@ __device__ __forceinline__ float residual_tf32(float x, float hi) { return x - h
 static constexpr int MLPP_PRODUCERS = 256;
 static constexpr int MLPP_EPILOGUE0 = MLPP_PRODUCERS + 32;   // first epilogue thread
 static constexpr int MLPP_ISSUER_WARP = MLPP_PRODUCERS / 32;
-static constexpr int MLPP_THREADS = MLPP_PRODUCERS + 32 + 128;
+// warps 13-15: normalisers (pass B of the epilogue: no tensor memory involved, so any warp can do it).  13 warps are allocated
+// as 16 anyway (the 128-register cap comes from there), so the three extra warps cost nothing.
+static constexpr int MLPP_NORM0 = MLPP_EPILOGUE0 + 128;      // first normaliser thread
+static constexpr int MLPP_NORM_WARPS = 3;
+static constexpr int MLPP_THREADS = MLPP_NORM0 + 32 * MLPP_NORM_WARPS;
 
 // ---- the same update with the A operand in TENSOR MEMORY ---------------------------------------------------------
 // ncu of the kernel above (profiles/r01_gnn_mlp_ln_summary.md): the shared-memory data pipe (128 B per clock and SM) is what
@@ -277,7 +281,8 @@ static constexpr int TS_A_STAGES = 3;
 static constexpr int TS_A_COL = 416;     // first A-stage column; 32 columns per stage
 static constexpr int TS_ACC2_COL = 208;
 static constexpr int TS_OUT_BYTES = 4 * 32 * 64;  // epilogue staging: per warp 32 rows x 16 columns, see the store pass
-static constexpr int TS_SMEM_BYTES = TS_B_STAGES * B_STAGE_BYTES + BAR_BYTES + PAR_BYTES + MAX_N * 4 + TS_OUT_BYTES + 1024;  // + b1
+static constexpr int TS_STAT_BYTES = 2 * TILE_M * 8;  // per tile parity: (rstd, -mean * rstd) of every row, epilogue -> normalisers
+static constexpr int TS_SMEM_BYTES = TS_B_STAGES * B_STAGE_BYTES + BAR_BYTES + PAR_BYTES + MAX_N * 4 + TS_OUT_BYTES + TS_STAT_BYTES + 1024;  // + b1
 
 // instruction descriptor for kind::f16 with bf16 operands: D = f32, A = B = bf16 (format 1), both K-major
 __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n)
@@ -349,9 +354,12 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
     const uint32_t sAccFull = sArdy + 8 * TS_A_STAGES;
     const uint32_t sAccFree = sAccFull + 8;
     const uint32_t sFreeB = sAccFree + 8;
-    const uint32_t sTmem = sFreeB + 8 * FREE_BARS;
+    const uint32_t sStatF = sFreeB + 8 * FREE_BARS;   // [2] a tile's row statistics are in shared memory (4 epilogue warps arrive)
+    const uint32_t sStatE = sStatF + 16;              // [2] ... and have been consumed (3 normaliser warps arrive)
+    const uint32_t sTmem = sStatE + 16;
     const uint32_t sPar = sFull + BAR_BYTES;
     const uint32_t sOut = sPar + PAR_BYTES + MAX_N * 4;
+    const uint32_t sStat = sOut + TS_OUT_BYTES;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
 
     const int tid = threadIdx.x;
@@ -372,6 +380,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
         for (int i = 0; i < TS_A_STAGES; i++) mbar_init(sArdy + 8 * i, MLPP_PRODUCERS / 64);  // the four warps of one group
         mbar_init(sAccFull, 1);
         mbar_init(sAccFree, 128);
+        for (int i = 0; i < 2; i++) mbar_init(sStatF + 8 * i, 4), mbar_init(sStatE + 8 * i, MLPP_NORM_WARPS);
         for (int i = 0; i < FREE_BARS; i++) mbar_init(sFreeB + 8 * i, CL);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -819,23 +828,14 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
         //   pass A (thread = row = TMEM lane): per 32-column chunk ReLU(acc2 [+ b2]), row statistics, and the RAW values stored
         //           to their place in `out` (through shared memory, so that four lanes write 64 contiguous bytes of a row);
         //           after the last chunk acc2 is released;
-        //   pass B: the warp re-reads its 32 raw rows from L2 (they were written microseconds ago), a row at a time, fully
-        //           coalesced, normalises with the row's statistics (shuffled from the lane that owns the row) and the lane's
-        //           own columns of scale / offset (registers), and overwrites them.
+        //   pass B (the three normaliser warps below): the tile's raw rows again, from L2 (they were written microseconds ago), a row
+        //           at a time, fully coalesced, normalised with the row's statistics (handed over through shared memory) and the
+        //           lane's own columns of scale / offset (registers), and overwritten.
         // One-pass statistics about a pivot: with d = x - c (c = the row's first value), mean = c + sum(d) / H and
         // var = (sum(d^2) - sum(d)^2 / H) / H; the pivot keeps the subtraction benign (|mean - c| is of the order of the
         // standard deviation), unlike the raw sum of squares.
         const int NCH = (P.n2 + 31) / 32;  // chunks of 32 columns; the last one may hold 16
         const uint32_t lane_e = (uint32_t)tid & 31u, wbase = sOut + (uint32_t)(warp & 3) * 2048u;
-        const int q4 = H >> 2;  // float4 per row
-        // this lane's columns in pass B: float4 lane_e and lane_e + 32 of a row
-        float4 gsc[2], gof[2];
-#pragma unroll
-        for (int t = 0; t < 2; t++) {
-            const int c = 4 * ((int)lane_e + 32 * t);
-            gsc[t] = c < H ? lds4(sPar + (MAX_N + c) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            gof[t] = c < H ? lds4(sPar + (2 * MAX_N + c) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         float xb[32];
         auto request = [&](int ch) {
             const int c0 = 32 * ch;
@@ -936,37 +936,77 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
 #endif
             const float md = sd / (float)H, mean = pivot + md;
             const float rstd = rsqrtf(fmaxf(sd2 / (float)H - md * md, 0.f) + 1e-5f);
-            // ---- pass B: the warp's rows again, from L2 (ld.global.cg: the lines were written by other lanes of this warp;
-            // the barrier above ordered those stores), four rows in flight
-            const int nrows = min(32, P.rows - row0);  // warp-uniform; <= 0 for a warp past the end
-            for (int r0 = 0; r0 < nrows; r0 += 4) {
-                float4 v[4][2];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float4* rowp = reinterpret_cast<const float4*>(P.out + (size_t)(row0 + min(r0 + k, nrows - 1)) * H);
-#pragma unroll
-                    for (int t = 0; t < 2; t++)
-                        if ((int)lane_e + 32 * t < q4) v[k][t] = __ldcg(rowp + lane_e + 32 * t);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float m = __shfl_sync(0xffffffffu, mean, (r0 + k) & 31), rs = __shfl_sync(0xffffffffu, rstd, (r0 + k) & 31);
-                    if (r0 + k < nrows) {
-                        float4* rowp = reinterpret_cast<float4*>(P.out + (size_t)(row0 + r0 + k) * H);
-#pragma unroll
-                        for (int t = 0; t < 2; t++)
-                            if ((int)lane_e + 32 * t < q4) {
-                                float4 y;
-                                y.x = (v[k][t].x - m) * rs * gsc[t].x + gof[t].x, y.y = (v[k][t].y - m) * rs * gsc[t].y + gof[t].y;
-                                y.z = (v[k][t].z - m) * rs * gsc[t].z + gof[t].z, y.w = (v[k][t].w - m) * rs * gsc[t].w + gof[t].w;
-                                rowp[lane_e + 32 * t] = y;
-                            }
-                    }
-                }
+            // ---- hand the rows to the normaliser warps: statistics into shared memory (double-buffered by tile parity), raw rows
+            // already in `out`.  The barrier arrival releases this warp's global and shared stores to the CTA.
+            {
+                const uint32_t par = it & 1u;
+                if (it >= 2) mbar_wait(sStatE + 8 * par, ((it >> 1) - 1u) & 1u);  // the normalisers are done with tile it - 2
+                const uint32_t sa = sStat + par * (TILE_M * 8) + ((uint32_t)(warp & 3) * 32u + lane_e) * 8u;
+                asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(sa), "f"(rstd), "f"(-mean * rstd) : "memory");
+                __threadfence_block();
+                __syncwarp();
+                if (lane_e == 0) mbar_arrive(sStatF + 8 * par);
             }
 #ifdef GNN_TRACE
             if (tid == MLPP_EPILOGUE0 && it >= (uint32_t)TRACE_TILE0 && it < (uint32_t)(TRACE_TILE0 + TRACE_TILES)) GNN_STAMP(TRACE_EPI + 4 * (it - TRACE_TILE0) + 3);
 #endif
+        }
+    }
+    else if (tid >= MLPP_NORM0) {
+        // ---- pass B of the epilogue on its own warps: the tile's 128 raw rows again, from L2 (ld.global.cg: they were written by the
+        // epilogue warps of this CTA microseconds ago; the mbarrier orders those stores), a row at a time, fully coalesced, normalised
+        // with the row's statistics (broadcast loads from shared memory) and this lane's own columns of scale / offset (registers),
+        // and overwritten.  Warp h takes rows h, h + 3, ...; four rows in flight.
+        const int H = P.h2, q4 = H >> 2;
+        const uint32_t lane_n = (uint32_t)tid & 31u;
+        const int hid = (tid - MLPP_NORM0) >> 5;
+        auto lds4n = [](uint32_t a) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+            return v;
+        };
+        float4 gsc[2], gof[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const int c = 4 * ((int)lane_n + 32 * t);
+            gsc[t] = c < H ? lds4n(sPar + (MAX_N + c) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gof[t] = c < H ? lds4n(sPar + (2 * MAX_N + c) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const bool t0_ok = (int)lane_n < q4, t1_ok = (int)lane_n + 32 < q4;
+        for (uint32_t it = 0; it < my_tiles; it++) {
+            const int tile = (int)(blockIdx.x + it * gridDim.x);
+            const uint32_t par = it & 1u;
+            mbar_wait_relaxed(sStatF + 8 * par, (it >> 1) & 1u);
+            const int nrows = min(TILE_M, P.rows - tile * TILE_M);  // <= 0 for a tile past the end (cluster padding)
+            for (int r0 = hid; r0 < nrows; r0 += 4 * MLPP_NORM_WARPS) {
+                float4 v[4][2];
+                float2 st[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int r = min(r0 + k * MLPP_NORM_WARPS, nrows - 1);
+                    const float4* rowp = reinterpret_cast<const float4*>(P.out + (size_t)(tile * TILE_M + r) * H);
+                    if (t0_ok) v[k][0] = __ldcg(rowp + lane_n);
+                    if (t1_ok) v[k][1] = __ldcg(rowp + lane_n + 32);
+                    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(st[k].x), "=f"(st[k].y) : "r"(sStat + par * (TILE_M * 8) + (uint32_t)r * 8u));
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int r = r0 + k * MLPP_NORM_WARPS;
+                    if (r < nrows) {
+                        float4* rowp = reinterpret_cast<float4*>(P.out + (size_t)(tile * TILE_M + r) * H);
+#pragma unroll
+                        for (int t = 0; t < 2; t++)
+                            if (t ? t1_ok : t0_ok) {  // y = ((v - mean) * rstd) * scale + offset as two FMAs per element
+                                float4 y;
+                                y.x = fmaf(fmaf(v[k][t].x, st[k].x, st[k].y), gsc[t].x, gof[t].x), y.y = fmaf(fmaf(v[k][t].y, st[k].x, st[k].y), gsc[t].y, gof[t].y);
+                                y.z = fmaf(fmaf(v[k][t].z, st[k].x, st[k].y), gsc[t].z, gof[t].z), y.w = fmaf(fmaf(v[k][t].w, st[k].x, st[k].y), gsc[t].w, gof[t].w);
+                                rowp[lane_n + 32 * t] = y;
+                            }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane_n == 0) mbar_arrive(sStatE + 8 * par);
         }
     }
     tc_fence_before();
