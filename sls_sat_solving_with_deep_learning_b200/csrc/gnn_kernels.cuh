@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
     const uint32_t sFreeB = sAccFree + 8;
     const uint32_t sStatF = sFreeB + 8 * FREE_BARS;   // [2] a tile's row statistics are in shared memory (4 epilogue warps arrive)
     const uint32_t sStatE = sStatF + 16;              // [2] ... and have been consumed (3 normaliser warps arrive)
-    const uint32_t sTmem = sStatE + 16;
+    const uint32_t sAcc1Full = sStatE + 16;           // every GEMM1 MMA of the tile has completed (tcgen05.commit): acc1 may be read
+    const uint32_t sTmem = sAcc1Full + 8;
     const uint32_t sPar = sFull + BAR_BYTES;
     const uint32_t sOut = sPar + PAR_BYTES + MAX_N * 4;
     const uint32_t sStat = sOut + TS_OUT_BYTES;
@@ -380,6 +381,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
         for (int i = 0; i < TS_A_STAGES; i++) mbar_init(sArdy + 8 * i, MLPP_PRODUCERS / 64);  // the four warps of one group
         mbar_init(sAccFull, 1);
         mbar_init(sAccFree, 128);
+        mbar_init(sAcc1Full, 1);
         for (int i = 0; i < 2; i++) mbar_init(sStatF + 8 * i, 4), mbar_init(sStatE + 8 * i, MLPP_NORM_WARPS);
         for (int i = 0; i < FREE_BARS; i++) mbar_init(sFreeB + 8 * i, CL);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -655,55 +657,20 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                     if (j + 1 < n1s) gemm1_unit(j + 1, xa1);
                 }
             }
-            // ---- GEMM2: ReLU(acc1 + b1).  Every GEMM1 MMA must have completed.  One 32-column TMEM load per unit, and the next
-            // tile's row pointers / first gathers are set up only after the first unit is on its way to the tensor pipe
-            // (measured in round 2: with that work and two TMEM round trips per unit on the critical path, the GEMM2 phase took
-            // 2.7x its MMA time and, chained with the epilogue through acc2, set the kernel's period)
-            wait_unit(2 * J - 1);
+            // ---- GEMM2's operand (ReLU of the first accumulator) is staged by the EPILOGUE warps (see there): the producers go
+            // straight on to the next tile -- row pointers, first gathers, indices one tile further ahead -- and their unit
+            // counter skips the GEMM2 units
             if (it + 1 < my_tiles) {
                 set_rows();
                 first_loads();
                 fetch_idx(next_tile + (int)gridDim.x);
+                // The next unit of this group needs the A stage of a GEMM2 unit.  The per-unit barriers are waited for by parity,
+                // which is sound only if no completion of the same barrier is skipped: walk through the units in between, in
+                // order (each is at most one completion ahead of what this thread has already seen).
+                const uint32_t last = 2 * (J + n2s) + grp - (uint32_t)TS_A_STAGES;
+                for (uint32_t u = 2 * J - 1; u <= last; u++) wait_unit(u);
             }
-            for (uint32_t j2 = 0; j2 < n2s; j2++) {
-                const uint32_t U = 2 * J + grp;
-                float v[NV];
-                uint32_t r[32];
-                tc_fence_after();
-#pragma unroll
-                for (int half = 0; half < NV / 16; half++) {
-                    const int c0 = (int)j2 * SLABK + (int)grp * NV + 16 * half;
-                    float* vh = v + 16 * half;
-                    if (c0 < P.n1) {
-                        tmem_ld16(tmem + lane_base + (uint32_t)c0, vh);
-                        if constexpr (BF) {  // b1 came through the GEMM (constant-one column of A): only the ReLU is left
-#pragma unroll
-                            for (int i = 0; i < 16; i++) vh[i] = fmaxf(vh[i], 0.f);
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                float4 b;
-                                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(sPar + (3 * MAX_N + c0 + 4 * q) * 4));
-                                vh[4 * q] = fmaxf(vh[4 * q] + b.x, 0.f), vh[4 * q + 1] = fmaxf(vh[4 * q + 1] + b.y, 0.f);
-                                vh[4 * q + 2] = fmaxf(vh[4 * q + 2] + b.z, 0.f), vh[4 * q + 3] = fmaxf(vh[4 * q + 3] + b.w, 0.f);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; i++) vh[i] = 0.f;
-                    }
-                    if constexpr (BF) {  // the constant-one column behind the hidden activation: W2's image holds b2 in row h1
-                        if (c0 <= P.h1 && P.h1 < c0 + 16) {
-#pragma unroll
-                            for (int i = 0; i < 16; i++)
-                                if (c0 + i == P.h1) vh[i] = 1.f;
-                        }
-                    }
-                }
-                pack_unit(v, r);
-                store_unit(U, r);
-                publish(U);
-            }
+            J += n2s;
         }
     } else if (warp_u == MLPP_ISSUER_WARP) {
         const bool leader = elect_one();
@@ -794,6 +761,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                     umma_commit(sDone + 8 * (U % DONE_BARS));
                     if (CL > 1 && h == 1) umma_commit_multicast(sFreeB + 8 * (J % FREE_BARS), CL_MASK);
                     if (h == 1 && j == S - 1) umma_commit(sAccFull);
+                    if (h == 1 && j == n1s - 1) umma_commit(sAcc1Full);
                 }
 #ifdef GNN_TRACE
                 if (tr) GNN_STAMP(tb + 4 + 2 * h);
@@ -847,6 +815,79 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
         for (uint32_t it = 0; it < my_tiles; it++) {
             const int tile = (int)(blockIdx.x + it * gridDim.x);
             const int row0 = tile * TILE_M + (warp & 3) * 32;  // first row of this warp
+            // ---- GEMM2's A operand: ReLU(acc1 [+ b1]) of this tile, thread = row = TMEM lane, both units of every slab.  These
+            // warps are idle between their pass A of the previous tile (done well inside GEMM1 of this one) and this tile's
+            // acc2; the producers, who staged these units in round 1, were what the issuer waited for (10,500 cycles per tile)
+            // once the epilogue was off the critical path.  acc1 needs no barrier of its own: the issuer consumes units in order,
+            // so GEMM1 of the next tile overwrites acc1 only after the last of these units -- i.e. its read -- is published.
+            {
+                const uint32_t Jt = it * S + n1s;   // global index of the tile's first GEMM2 slab
+                // a barrier of its own, one completion per tile: the per-unit barriers are waited for by parity, which is only
+                // sound for a waiter that has seen the previous completion of the same barrier -- this warp has not
+                mbar_wait(sAcc1Full, it & 1u);
+                tc_fence_after();
+                for (uint32_t j2 = 0; j2 < n2s; j2++) {
+#pragma unroll 1
+                    for (uint32_t g = 0; g < 2; g++) {
+                        const uint32_t U = 2 * (Jt + j2) + g;
+                        float v[NV];
+                        uint32_t r[32];
+#pragma unroll
+                        for (int half = 0; half < NV / 16; half++) {
+                            const int c0 = (int)j2 * SLABK + (int)g * NV + 16 * half;
+                            float* vh = v + 16 * half;
+                            if (c0 < P.n1) {
+                                tmem_ld16(tmem + lane_base + (uint32_t)c0, vh);
+                                if constexpr (BF) {  // b1 came through the GEMM (constant-one column of A): only the ReLU is left
+#pragma unroll
+                                    for (int i = 0; i < 16; i++) vh[i] = fmaxf(vh[i], 0.f);
+                                } else {
+#pragma unroll
+                                    for (int q = 0; q < 4; q++) {
+                                        const float4 b = lds4(sPar + (3 * MAX_N + c0 + 4 * q) * 4);
+                                        vh[4 * q] = fmaxf(vh[4 * q] + b.x, 0.f), vh[4 * q + 1] = fmaxf(vh[4 * q + 1] + b.y, 0.f);
+                                        vh[4 * q + 2] = fmaxf(vh[4 * q + 2] + b.z, 0.f), vh[4 * q + 3] = fmaxf(vh[4 * q + 3] + b.w, 0.f);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; i++) vh[i] = 0.f;
+                            }
+                            if constexpr (BF) {  // the constant-one column behind the hidden activation: W2's image holds b2 in row h1
+                                if (c0 <= P.h1 && P.h1 < c0 + 16) {
+#pragma unroll
+                                    for (int i = 0; i < 16; i++)
+                                        if (c0 + i == P.h1) vh[i] = 1.f;
+                                }
+                            }
+                        }
+                        if constexpr (BF) {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) {  // one packing conversion per pair and piece (see the producers' split_pair)
+                                uint32_t a0, a1;
+                                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a0) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+                                const float re = v[2 * i] - __uint_as_float(a0 << 16), ro = v[2 * i + 1] - __uint_as_float(a0 & 0xffff0000u);
+                                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a1) : "f"(ro), "f"(re));
+                                r[i] = a0;
+                                r[16 + i] = a1;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) {
+                                const float hi = round_tf32(v[i]);
+                                r[i] = __float_as_uint(hi);
+                                r[16 + i] = __float_as_uint(residual_tf32(v[i], hi));
+                            }
+                        }
+                        if (U >= (uint32_t)TS_A_STAGES) wait_unit(U - TS_A_STAGES);
+                        tc_fence_after();
+                        tmem_st32(tmem + lane_base + (uint32_t)(TS_A_COL + 32 * (U % TS_A_STAGES)), r);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane_e == 0) mbar_arrive(sArdy + 8 * (U % TS_A_STAGES));
+                    }
+                }
+            }
             mbar_wait_relaxed(sAccFull, it & 1u);
 #ifdef GNN_TRACE
             if (tid == MLPP_EPILOGUE0 && it >= (uint32_t)TRACE_TILE0 && it < (uint32_t)(TRACE_TILE0 + TRACE_TILES)) GNN_STAMP(TRACE_EPI + 4 * (it - TRACE_TILE0));
