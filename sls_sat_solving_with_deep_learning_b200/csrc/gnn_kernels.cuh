@@ -35,10 +35,17 @@ static constexpr int SLAB_K = 32;        // tf32 elements per 128-byte swizzle r
 static constexpr int MAX_N = 208;        // padded output width (multiple of 16, >= hidden)
 static constexpr int B_SLAB_BYTES = MAX_N * 128;    // 26 KB: one weight slab image (one 128-byte row per output column)
 static constexpr int B_STAGE_BYTES = 2 * B_SLAB_BYTES;   // 52 KB: the two pieces of a slab (hi | lo, or b0 | b1)
-static constexpr int DONE_BARS = 6;                      // one mbarrier per unit index mod 6
+// One mbarrier per unit index mod DONE_BARS, waited for by PARITY.  A parity wait for completion k of a barrier is sound only
+// while the barrier stands at k or k + 1 completions: (a) the unit DONE_BARS before the awaited one must be known complete,
+// (b) the unit DONE_BARS after it must be unable to complete before the waiter moves on.  The producers skip the GEMM2 units
+// of a tile (the epilogue warps stage those), i.e. up to 2 * ceil(MAX_N / 32) = 14 units between two of their waits, and the
+// issuer runs through those units without them: (a) needs DONE_BARS >= 14 + 2; (b) holds because the awaited unit's third
+// successor is the one the waiter is about to stage.  (With 6 barriers a producer that reached its wait late found the
+// barrier two completions ahead and slept until a completion that depended on itself.)
+static constexpr int DONE_BARS = 16;
 static constexpr int TMEM_COLS = 512;
 static constexpr int PAR_BYTES = 3 * MAX_N * 4;          // b2 | ln_scale | ln_offset staged in shared memory
-static constexpr int BAR_BYTES = 256;                    // mbarriers + the TMEM base address
+static constexpr int BAR_BYTES = 384;                    // mbarriers + the TMEM base address
 
 struct MlpArgs {
     // up to three gathered input segments: row i of the A matrix is
@@ -664,11 +671,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                 set_rows();
                 first_loads();
                 fetch_idx(next_tile + (int)gridDim.x);
-                // The next unit of this group needs the A stage of a GEMM2 unit.  The per-unit barriers are waited for by parity,
-                // which is sound only if no completion of the same barrier is skipped: walk through the units in between, in
-                // order (each is at most one completion ahead of what this thread has already seen).
-                const uint32_t last = 2 * (J + n2s) + grp - (uint32_t)TS_A_STAGES;
-                for (uint32_t u = 2 * J - 1; u <= last; u++) wait_unit(u);
+                // the next unit of this group waits for the A stage of a GEMM2 unit like for any other (DONE_BARS above)
             }
             J += n2s;
         }
