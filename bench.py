@@ -63,6 +63,7 @@ BYTES_PER_FLIP = bytes_per_step(K, K * ALPHA, 1.0)  # probSAT: one flip per step
 # ---- C1 / C4 / C5 shapes ("Config shorthands") ------------------------------------------------------
 C1_INSTANCES, C1_RUNS, C1_NSTEPS, C1_CPU_STRIDE = 2052, 100, 100_000, 16
 C4_INSTANCES, C4_N, C4_M, C4_RUNS, C4_NSTEPS, C4_SEED = 10_000, 500, 2100, 100, 10_000 - 1, 20260104
+C4_CHUNK = int(os.environ.get("SLS_BENCH_C4_CHUNK", "1000"))  # instances per pipeline chunk (pipeline.solve_with_oracle)
 C5_N, C5_M, C5_CHAINS, C5_NSTEPS, C5_SEED = 1_000_000, 4_000_000, 65_536, 1000, 20260105
 ALL_LEGS = ("c2_moser", "c1_batch", "c4_pipeline", "c5", "clause_eval")
 
@@ -423,15 +424,12 @@ def leg_c4_pipeline(ctx):
     keep = {}
 
     def runner(idx):
-        t0 = time.perf_counter()
-        insts = [eng.Instance.from_csr(C4_N, *csrs[i]) for i in idx]
-        t1 = time.perf_counter()
-        probs = net.probabilities(insts)
-        t2 = time.perf_counter()
-        res = eng.run_sls_batch(insts, "moser", probs, probs, C4_NSTEPS, C4_RUNS, True, 0.0, instance_seeds=[1 + i for i in idx])
-        t3 = time.perf_counter()
-        stage.update(build_s=t1 - t0, forward_s=t2 - t1, forward_device_ms=net.last_kernel_ms, walk_s=t3 - t2,
-                     walk_kernel_ms=res[0].kernel_ms if res else 0.0)
+        # the product's pipeline: chunks of C4_CHUNK instances, handle build / forward / walk overlapped on three threads
+        st = {}
+        res, _, insts = ctx["pipeline"].solve_with_oracle(
+            net, [csrs[i] for i in idx], "moser", C4_NSTEPS, C4_RUNS, make_instance=lambda c: eng.Instance.from_csr(C4_N, *c),
+            instance_seeds=[1 + i for i in idx], chunk=C4_CHUNK, keep_instances=True, stats=st)
+        stage.update(st)
         keep["insts"] = insts
         return res
 
@@ -452,7 +450,8 @@ def leg_c4_pipeline(ctx):
         "walk_steps_per_s": int(steps.sum()) / (per_stage["walk_kernel_ms"] * 1e-3),
         "e2e": {"value": C4_INSTANCES / wall, "unit": "instances/s", "h2d_bytes_per_step": int(C4_INSTANCES * (C4_M * 3 * 32 + C4_M * 80 + C4_N * 40)),
                 "d2h_bytes_per_step": int(C4_INSTANCES * (C4_N * 4 + C4_RUNS * 22)),
-                "includes": "CSR -> handles, instance upload, LCG graphs on the device, forward, p to the host and back as weights, walk, D2H, gather"},
+                "includes": "CSR -> handles, instance upload, LCG graphs on the device, forward, p to the host and back as weights, walk, D2H, gather; "
+                            f"pipeline.solve_with_oracle in chunks of {C4_CHUNK} instances, the three stages overlapped (stage times are sums over chunks)"},
         "gpu_launches": None,
     }
     # ---- the oracle forward by itself: one workspace chunk (256 instances), device time, kernel classes, rooflines
@@ -482,7 +481,7 @@ def leg_c4_pipeline(ctx):
     fw = {
         "workload": f"C4 shape: {n_fw} instances n={C4_N} m={C4_M} (LCG: {n_nodes} nodes, {n_edges} edges each), random-init interaction network",
         "instances_per_s": n_fw / (best_ms * 1e-3), "device_ms": best_ms, "e2e_instances_per_s": n_fw / best_wall,
-        "precision": os.environ.get("SLS_B200_GNN_PRECISION", "bf16x2"), "dense_tflops": flops / (best_ms * 1e-3) / 1e12,
+        "precision": os.environ.get("SLS_B200_GNN_PRECISION", "fp16x2"), "dense_tflops": flops / (best_ms * 1e-3) / 1e12,
         "gpu_launches": launches, "kernel_class_ms": prof,
         "kernel": "gnn::mlp_ln_persistent_ts_kernel (tcgen05 kind::f16, A operand in TMEM) + segment_sum_kernel",
         "roofline": {
@@ -721,7 +720,7 @@ def run_own(args, rank, world, local_rank):
     import torch
 
     import sls_sat_solving_with_deep_learning_b200 as eng
-    from sls_sat_solving_with_deep_learning_b200 import gnn, sharding, synth
+    from sls_sat_solving_with_deep_learning_b200 import gnn, pipeline, sharding, synth
 
     if not torch.cuda.is_available() or eng.device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
@@ -863,7 +862,7 @@ def run_own(args, rank, world, local_rank):
     line = None
     if rank == 0:
         achieved = R * NSTEPS * BYTES_PER_FLIP / (kms * 1e-3) / 1e9
-        # L2 -> SM sectors per flip of one walk_k3s launch (ncu lts__t_sectors_srcunit_tex_op_read, profiles/r01_final_walk_k3s_summary.md)
+        # L2 -> SM sectors per flip of one walk_k3s launch (ncu lts__t_sectors_srcunit_tex_op_read, profiles/r02_walk_k3s_summary.md)
         l2_bytes_per_flip = 300.0
         line = {
             "metric": "variable flips/sec", "value": value, "unit": "flips/s",
@@ -888,8 +887,8 @@ def run_own(args, rank, world, local_rank):
                 "bound": "latency", "contract_bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of one walk_k3s launch (ncu --set full,
-                # profiles/r01_final_walk_k3s_summary.md): independent of the step count, instance and state never leave L2 / smem
-                "traffic": 6.37e6, "traffic_source": "ncu capture, profiles/r01_final_walk_k3s_summary.md (not measurable inside a run)",
+                # profiles/r02_walk_k3s_summary.md): independent of the step count, instance and state never leave L2 / smem
+                "traffic": 6.18e6, "traffic_source": "ncu capture of this kernel in the bench command, profiles/r02_walk_k3s_summary.md (not measurable inside a run)",
                 "peak_source": pk["source"], "bytes_per_flip": BYTES_PER_FLIP, "kernel_ms": kms,
                 "l2": {"achieved_gbs": R * NSTEPS * l2_bytes_per_flip / (kms * 1e-3) / 1e9,
                        "random_sector_peak_gbs": (ubench or {}).get("l2_sector32_gbs_8_in_flight"),
@@ -917,7 +916,7 @@ def run_own(args, rank, world, local_rank):
         }
 
     # ---- the other legs: every rank takes part (sharded work, collectives); rank 0 reports.  A failing leg fails the run.
-    ctx = {"eng": eng, "gnn": gnn, "synth": synth, "sharding": sharding, "torch": torch, "dist": dist, "rank": rank, "world": world,
+    ctx = {"eng": eng, "gnn": gnn, "synth": synth, "sharding": sharding, "pipeline": pipeline, "torch": torch, "dist": dist, "rank": rank, "world": world,
            "steps": args.steps, "cpu": cpu, "peaks": pk, "ubench": ubench, "flush": flush, "c2_inst": inst, "c2_w": w, "c2_path": path,
            "c2_h2d": h2d, "c2_d2h": d2h}
     results = {}

@@ -1099,7 +1099,7 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     const bool no_quad = [] { const char* f = std::getenv("SLS_B200_NO_QUAD"); return f && f[0] == '1'; }();
     constexpr int NG = 5;
     std::vector<WalkArgs> items[NG];
-    std::vector<uint32_t> cta_begin[NG], owner[NG];
+    std::vector<uint32_t> cta_begin[NG], blk_begin[NG], owner[NG];
     size_t smem_max[NG] = {0, 0, 0, 0, 0};
     // Launch order inside a kernel: instances with the highest clause / variable ratio first.  Their chains are the ones
     // that run the whole step budget; started last, a single such CTA would keep the launch alive long after the rest of
@@ -1140,12 +1140,7 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         if (!pl.k3 && params->algo != SLS_ALGO_SCHOENING) {
             a.ftab = reinterpret_cast<double*>(p_ftab.base) + pl.off_ftab;
             a.cscale = reinterpret_cast<double*>(p_cscale.base) + pl.off_cscale;
-            if (I.m)
-                build_flip_tables_kernel<<<(I.m + 127) / 128, 128>>>(I, a.w, params->algo, const_cast<double*>(a.ftab),
-                                                                     const_cast<double*>(a.cscale));
         }
-        if (pl.k3 && I.m)
-            build_crecx_kernel<<<(I.m + 255) / 256, 256>>>(I.crec, I.occ_ptr, a.w, const_cast<uint4*>(a.crecx), I.m, I.n, params->algo);
         // small k<=3 instances run two chains per warp (walk_k3d.cuh): 4 warps = 8 chains per CTA
         const bool dual = pl.k3 && !no_dual && walk_k3d_supports(a);
         const bool quad = dual && !no_quad && walk_k3q_supports(a);
@@ -1157,7 +1152,9 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
             smem_bytes = size_t(chains_per_cta) * (size_t(I.slab_words) + HRING_WORDS) * 4;
         }
         const int g = quad ? 4 : dual ? 3 : pl.k3 ? 0 : pl.smem ? 1 : 2;
-        if (cta_begin[g].empty()) cta_begin[g].push_back(0);
+        if (cta_begin[g].empty()) cta_begin[g].push_back(0), blk_begin[g].push_back(0);
+        // per-weights tables (clause records / flip tables): built by one launch per group, below
+        blk_begin[g].push_back(blk_begin[g].back() + ((a.crecx || a.ftab) ? (I.m + 255) / 256 : 0));
         cta_begin[g].push_back(cta_begin[g].back() + (uint32_t)((R + chains_per_cta - 1) / chains_per_cta));
         items[g].push_back(a);
         owner[g].push_back(i);
@@ -1179,10 +1176,16 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     Pool d_items[NG], d_cta[NG];
     for (int g = 0; g < NG; g++) {
         if (items[g].empty()) continue;
+        const size_t nb = cta_begin[g].size();  // = blk_begin[g].size(): both tables in one allocation and one copy
+        cta_begin[g].insert(cta_begin[g].end(), blk_begin[g].begin(), blk_begin[g].end());
         CUDA_TRY(alloc(d_items[g], items[g].size() * sizeof(WalkArgs)));
-        CUDA_TRY(alloc(d_cta[g], cta_begin[g].size() * 4));
+        CUDA_TRY(alloc(d_cta[g], 2 * nb * 4));
         CUDA_TRY(cudaMemcpyAsync(d_items[g].base, items[g].data(), items[g].size() * sizeof(WalkArgs), cudaMemcpyHostToDevice, nullptr));
-        CUDA_TRY(cudaMemcpyAsync(d_cta[g].base, cta_begin[g].data(), cta_begin[g].size() * 4, cudaMemcpyHostToDevice, nullptr));
+        CUDA_TRY(cudaMemcpyAsync(d_cta[g].base, cta_begin[g].data(), 2 * nb * 4, cudaMemcpyHostToDevice, nullptr));
+        cta_begin[g].resize(nb);
+        if (blk_begin[g].back())
+            build_tables_batch_kernel<<<blk_begin[g].back(), 256>>>(reinterpret_cast<const WalkArgs*>(d_items[g].base),
+                                                                    reinterpret_cast<const uint32_t*>(d_cta[g].base) + nb, (uint32_t)items[g].size());
     }
     const WalkK3BatchKernel k3_batch = walk_k3s_batch_kernel_for(params->algo, params->prob_flip_best);
     if (smem_max[0]) CUDA_TRY(cudaFuncSetAttribute(k3_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max[0]));

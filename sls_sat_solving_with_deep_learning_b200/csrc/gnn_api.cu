@@ -5,9 +5,11 @@
 //   LCG.get_graph + get_problem_from_cnf          python/src/sat_representations.py:607-666,
 //                                                 python/src/sat_instances.py:50-73  (sls_gnn_forward_lcg)
 //   LCG.get_model_probabilities                   python/src/sat_representations.py:775-780
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -44,6 +46,7 @@ float round_tf32_host(float x)
 struct DevMlp {
     int k1 = 0, h1 = 0, h2 = 0, k1_slabs = 0, k2_slabs = 0, n1 = 0, n2 = 0, k1_slabs_bf = 0, k2_slabs_bf = 0;
     uint16_t *w1_b0 = nullptr, *w1_b1 = nullptr, *w2_b0 = nullptr, *w2_b1 = nullptr;  // two bf16 pieces, 64 k-values per slab row
+    uint16_t *w1_h0 = nullptr, *w1_h1 = nullptr, *w2_h0 = nullptr, *w2_h1 = nullptr;  // two fp16 pieces, same images
     float *w1_hi = nullptr, *w1_lo = nullptr, *b1 = nullptr, *w2_hi = nullptr, *w2_lo = nullptr, *b2 = nullptr, *ln_scale = nullptr,
           *ln_offset = nullptr;
 };
@@ -62,6 +65,14 @@ uint16_t bf16_bits_host(float x)
     if ((u & 0x7f800000u) != 0x7f800000u) u += 0x7fffu + ((u >> 16) & 1u);
     return (uint16_t)(u >> 16);
 }
+// round to nearest even to IEEE half, saturating at the largest finite value (what cvt.rn.satfinite.f16x2.f32 does on the device)
+uint16_t f16_bits_host(float x)
+{
+    if (x > 65504.f) x = 65504.f;
+    if (x < -65504.f) x = -65504.f;
+    return __half_as_ushort(__float2half_rn(x));
+}
+float f16_value_host(uint16_t b) { return __half2float(__ushort_as_half(b)); }
 float bf16_value_host(uint16_t b)
 {
     const uint32_t u = (uint32_t)b << 16;
@@ -95,6 +106,7 @@ struct sls_gnn_model {
     std::vector<void*> allocs;
     int launches = 0;
     bool prefer_tf32x3 = false;  // this model's default product when SLS_B200_GNN_PRECISION is unset (see sls_gnn_model_create)
+    bool f16_range_ok = true;    // every weight and bias is finite and within fp16's range: fp16 pieces are the default
     bool profile = false;        // sls_gnn_set_profile: event pairs around every kernel class of a forward
     double prof_ms[4] = {0, 0, 0, 0};
     // Activation workspace (edge / node feature ping-pong buffers and the two aggregates): one block, grown on
@@ -156,9 +168,22 @@ int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& 
     };
     std::vector<uint16_t> w1b0((size_t)out.n1 * out.k1_slabs_bf * SLAB_KB, 0), w1b1(w1b0.size(), 0);
     std::vector<uint16_t> w2b0((size_t)out.n2 * out.k2_slabs_bf * SLAB_KB, 0), w2b1(w2b0.size(), 0);
+    std::vector<uint16_t> w1h0(w1b0.size(), 0), w1h1(w1b0.size(), 0), w2h0(w2b0.size(), 0), w2h1(w2b0.size(), 0);
+    std::vector<uint16_t>* twin[4][2] = {{&w1b0, &w1h0}, {&w1b1, &w1h1}, {&w2b0, &w2h0}, {&w2b1, &w2h1}};
+    auto f16_twin = [&](std::vector<uint16_t>& v) -> std::vector<uint16_t>& {
+        for (auto& t : twin)
+            if (t[0] == &v) return *t[1];
+        return v;
+    };
+    // both 16-bit formats in one pass: w = p0 + p1 with p0 = round(w), p1 = round(w - p0); fp16 pieces carry 11 + 11 mantissa bits
+    // (bf16: 8 + 8), at the price of fp16's range -- see sls_gnn_model_create for when they are the default
     auto put_bf = [&](std::vector<uint16_t>& p0, std::vector<uint16_t>& p1, size_t ix, float w) {
         p0[ix] = bf16_bits_host(w);
         p1[ix] = bf16_bits_host(w - bf16_value_host(p0[ix]));
+        std::vector<uint16_t>&h0 = f16_twin(p0), &h1v = f16_twin(p1);
+        h0[ix] = f16_bits_host(w);
+        h1v[ix] = f16_bits_host(w - f16_value_host(h0[ix]));
+        if (!(std::fabs(w) <= 65504.f)) m->f16_range_ok = false;
     };
     std::vector<float> w1h((size_t)out.n1 * k1p, 0.f), w1l(w1h.size(), 0.f), b1(out.n1, 0.f);
     std::vector<float> w2h((size_t)out.n2 * k2p, 0.f), w2l(w2h.size(), 0.f), b2(out.n2, 0.f);
@@ -187,6 +212,15 @@ int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& 
     for (int n = 0; n < h2; n++) put_bf(w2b0, w2b1, img_index_bf(out.n2, h1 / SLAB_KB, n, h1 % SLAB_KB), p[n]);
     p += h2;
     std::vector<float> sc(p, p + h2), of(p + h2, p + 2 * h2);
+    {
+        // What the next GEMM gathers are this LayerNorm's outputs and sums of them over a node's edges: |y| <= |scale| sqrt(h2)
+        // + |offset|.  fp16 pieces are the model's default only while a few hundred such rows can be summed inside fp16's
+        // range (any model near the initialisation: the bound is 14); otherwise the model keeps fp32's range with bf16 pieces.
+        float smax = 0.f, omax = 0.f;
+        for (float v : sc) smax = std::max(smax, std::fabs(v));
+        for (float v : of) omax = std::max(omax, std::fabs(v));
+        if (!(smax * std::sqrt((float)h2) + omax <= 256.f)) m->f16_range_ok = false;
+    }
     p += 2 * h2;
     int rc;
     if ((rc = upload(w1h, &out.w1_hi)) || (rc = upload(w1l, &out.w1_lo)) || (rc = upload(b1, &out.b1)) || (rc = upload(w2h, &out.w2_hi)) ||
@@ -198,6 +232,10 @@ int pack_mlp(sls_gnn_model* m, const float*& p, int k1, int h1, int h2, DevMlp& 
         (rc = upload_u16(w2b1, &out.w2_b1)))
         return rc;
     for (uint16_t* q : {out.w1_b0, out.w1_b1, out.w2_b0, out.w2_b1}) m->allocs.push_back(q);
+    if ((rc = upload_u16(w1h0, &out.w1_h0)) || (rc = upload_u16(w1h1, &out.w1_h1)) || (rc = upload_u16(w2h0, &out.w2_h0)) ||
+        (rc = upload_u16(w2h1, &out.w2_h1)))
+        return rc;
+    for (uint16_t* q : {out.w1_h0, out.w1_h1, out.w2_h0, out.w2_h1}) m->allocs.push_back(q);
     return SLS_OK;
 }
 
@@ -260,9 +298,10 @@ extern "C" int sls_gnn_model_create(const float* blob, uint64_t blob_len, int32_
         return rc;
     }
     m->readout_b = *p;
-    cudaError_t e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_ln_persistent_ts_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
+    cudaError_t e = cudaSuccess;
+    for (auto kern : {mlp_ln_persistent_ts_kernel<0, 1>, mlp_ln_persistent_ts_kernel<1, 1>, mlp_ln_persistent_ts_kernel<1, 2>,
+                      mlp_ln_persistent_ts_kernel<2, 1>, mlp_ln_persistent_ts_kernel<2, 2>})
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
     if (e != cudaSuccess) {
         sls_gnn_model_free(m);
         return sls_set_error_internal(SLS_ERR_CUDA, std::string("cudaFuncSetAttribute(mlp_ln_kernel): ") + cudaGetErrorString(e));
@@ -319,12 +358,20 @@ int launch_mlp(sls_gnn_model* m, const DevMlp& w, const float* s0, const int32_t
         // SLS_B200_GNN_CLUSTER = 1 | 2: CTAs per cluster sharing the weight stream by multicast (see the kernel)
         const char* f = std::getenv("SLS_B200_GNN_CLUSTER");  // read per launch: the tests switch it
         const int c = f ? std::atoi(f) : GNN_DEFAULT_CLUSTER;
-        // SLS_B200_GNN_PRECISION = bf16x2 (default: two bf16 pieces per operand on kind::f16) | tf32x3; a model whose
-        // parameters have a wide dynamic range is created with tf32x3 as its own default (sls_gnn_model_create)
+        // SLS_B200_GNN_PRECISION = fp16x2 | bf16x2 | tf32x3.  Default fp16x2: two fp16 pieces per operand on kind::f16, three
+        // product terms a0*b0 + a1*b0 + a0*b1 with fp32 accumulation -- 22 mantissa bits per operand at the cost of three
+        // 16-bit MMAs (tools/precision_split_study.py: max |dp| 3e-6 against fp64, the fp32 restatement itself 2e-6; bf16
+        // pieces 3e-5 at the same cost; 3xTF32 2e-6 at twice the tensor time).  fp16's range: activations beyond 65504
+        // saturate piece by piece (exact up to 131008), weights beyond it switch the model to bf16x2 (pack_mlp).
         const char* fp = std::getenv("SLS_B200_GNN_PRECISION");
-        const bool tf32x3 = fp ? std::strcmp(fp, "tf32x3") == 0 : m->prefer_tf32x3;
+        const int prec = fp ? (std::strcmp(fp, "tf32x3") == 0 ? 0 : std::strcmp(fp, "bf16x2") == 0 ? 1 : 2)
+                            : (m->prefer_tf32x3 ? 0 : m->f16_range_ok ? 2 : 1);
+        if (prec == 2) a.w1_b0 = w.w1_h0, a.w1_b1 = w.w1_h1, a.w2_b0 = w.w2_h0, a.w2_b1 = w.w2_h1;
+        const bool tf32x3 = prec == 0;
         const int cl = (!tf32x3 && c == 2) ? 2 : 1;
-        void (*kern)(const MlpArgs) = tf32x3 ? mlp_ln_persistent_ts_kernel<false, 1> : cl == 2 ? mlp_ln_persistent_ts_kernel<true, 2> : mlp_ln_persistent_ts_kernel<true, 1>;
+        void (*kern)(const MlpArgs) = tf32x3      ? mlp_ln_persistent_ts_kernel<0, 1>
+                                      : prec == 1 ? (cl == 2 ? mlp_ln_persistent_ts_kernel<1, 2> : mlp_ln_persistent_ts_kernel<1, 1>)
+                                                  : (cl == 2 ? mlp_ln_persistent_ts_kernel<2, 2> : mlp_ln_persistent_ts_kernel<2, 1>);
         const size_t smem = TS_SMEM_BYTES;
         if (cl == 1) {
             int dev = 0, sms = 148;

@@ -86,7 +86,10 @@ struct MlpArgs {
 #else
 #define GNN_STAMP(slot) do { } while (0)
 #endif
-static constexpr int TRACE_TILE0 = 3, TRACE_TILES = 3;   // tiles of CTA 0 that are traced
+#ifndef GNN_TRACE_TILE0
+#define GNN_TRACE_TILE0 3
+#endif
+static constexpr int TRACE_TILE0 = GNN_TRACE_TILE0, TRACE_TILES = 3;   // tiles of CTA 0 that are traced (-DGNN_TRACE_TILE0=50: mid-launch)
 static constexpr int TRACE_ISSUER = 0, TRACE_PROD = 4096, TRACE_EPI = 8192, TRACE_WORDS = 8192 + 64;
 
 // ---- small PTX helpers -----------------------------------------------------------------------
@@ -296,6 +299,26 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n)
 {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// kind::f16 with fp16 operands: a_format = b_format = 0 (F16), fp32 accumulator
+__host__ __device__ constexpr uint32_t idesc_f16(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
+// x = a0 + a1 for a pair of k-values, packed two to a 32-bit column (the lower k in the low half): a0 = round(x), a1 =
+// round(x - a0), both to nearest even; one packing conversion per pair and piece.  fp16 saturates at the largest finite value
+// instead of producing infinities (the residual then carries what is left, exact up to twice the range).
+template <bool F16>
+__device__ __forceinline__ void split_pair16(float lo_k, float hi_k, uint32_t& a0, uint32_t& a1)
+{
+    if constexpr (F16) {
+        float f_lo, f_hi;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(a0) : "f"(hi_k), "f"(lo_k));
+        asm("{ .reg .b16 l, h;\n  mov.b32 {l, h}, %2;\n  cvt.f32.f16 %0, l;\n  cvt.f32.f16 %1, h; }" : "=f"(f_lo), "=f"(f_hi) : "r"(a0));
+        const float re = lo_k - f_lo, ro = hi_k - f_hi;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(a1) : "f"(ro), "f"(re));
+    } else {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a0) : "f"(hi_k), "f"(lo_k));
+        const float re = lo_k - __uint_as_float(a0 << 16), ro = hi_k - __uint_as_float(a0 & 0xffff0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a1) : "f"(ro), "f"(re));
+    }
+}
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
@@ -343,10 +366,15 @@ __device__ __forceinline__ void tmem_st16x256b_x4(uint32_t taddr, const uint32_t
 // CL = 2: the two CTAs of a cluster run their tiles in lock step; each requests half of every weight slab and the copy engine
 // multicasts it into the same stage of both (as in mlp_ln_persistent_kernel<CL>): the weight stream, 70 % of this kernel's
 // L2 -> SM traffic, is read from L2 once per pair.  A stage may be refilled when both CTAs' MMAs have drained it (sFreeB).
-template <bool BF, int CL>
+// PREC: 0 = 3xTF32 (kind::tf32), 1 = two bf16 pieces per operand, 2 = two fp16 pieces per operand (both kind::f16, same
+// staging and images; only the conversions and the instruction descriptor's operand formats differ)
+template <int PREC, int CL>
 __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(const MlpArgs P)
 {
     static_assert(CL == 1 || CL == 2, "cluster size");
+    static_assert(PREC >= 0 && PREC <= 2, "precision");
+    constexpr bool BF = PREC != 0;   // "two 16-bit pieces" path
+    constexpr bool F16 = PREC == 2;
     constexpr int FREE_BARS = 2 * TS_B_STAGES;
     constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
     constexpr int NV = BF ? 32 : 16;        // k-values per thread and unit
@@ -541,11 +569,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
         // lower k in the low half of a column; both pieces rounded to nearest even)
         // The split is register work and runs BEFORE the thread waits for its A stage; once the stage is free only the TMEM
         // store, its wait and the barrier arrival are left on the stage's turn-around path.
-        auto split_pair = [](float lo_k, float hi_k, uint32_t& a0, uint32_t& a1) {  // one packing conversion per pair and piece
-            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a0) : "f"(hi_k), "f"(lo_k));
-            const float re = lo_k - __uint_as_float(a0 << 16), ro = hi_k - __uint_as_float(a0 & 0xffff0000u);
-            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a1) : "f"(ro), "f"(re));
-        };
+        auto split_pair = [](float lo_k, float hi_k, uint32_t& a0, uint32_t& a1) { split_pair16<F16>(lo_k, hi_k, a0, a1); };
         auto pack_unit = [&](const float* v, uint32_t* r) {
             if constexpr (BF) {
 #pragma unroll
@@ -681,7 +705,8 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
         const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
         constexpr uint32_t DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version 1 | SWIZZLE_128B
         auto desc = [&](uint32_t addr) -> uint64_t { return (uint64_t)DESC_HI << 32 | (((addr >> 4) & 0x3fffu) | (1u << 16)); };
-        const uint32_t idesc1 = BF ? idesc_bf16(TILE_M, P.n1) : idesc_tf32(TILE_M, P.n1), idesc2 = BF ? idesc_bf16(TILE_M, P.n2) : idesc_tf32(TILE_M, P.n2);
+        const uint32_t idesc1 = F16 ? idesc_f16(TILE_M, P.n1) : BF ? idesc_bf16(TILE_M, P.n1) : idesc_tf32(TILE_M, P.n1);
+        const uint32_t idesc2 = F16 ? idesc_f16(TILE_M, P.n2) : BF ? idesc_bf16(TILE_M, P.n2) : idesc_tf32(TILE_M, P.n2);
         auto issue_b = [&](uint32_t J, uint32_t j) {  // j = J % S
             const bool g1 = j < n1s;
             const int n_pad = g1 ? P.n1 : P.n2;
@@ -867,12 +892,7 @@ __global__ void __launch_bounds__(MLPP_THREADS, 1) mlp_ln_persistent_ts_kernel(c
                         if constexpr (BF) {
 #pragma unroll
                             for (int i = 0; i < 16; i++) {  // one packing conversion per pair and piece (see the producers' split_pair)
-                                uint32_t a0, a1;
-                                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a0) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
-                                const float re = v[2 * i] - __uint_as_float(a0 << 16), ro = v[2 * i + 1] - __uint_as_float(a0 & 0xffff0000u);
-                                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a1) : "f"(ro), "f"(re));
-                                r[i] = a0;
-                                r[16 + i] = a1;
+                                split_pair16<F16>(v[2 * i], v[2 * i + 1], r[i], r[16 + i]);
                             }
                         } else {
 #pragma unroll

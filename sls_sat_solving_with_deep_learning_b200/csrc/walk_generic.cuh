@@ -282,11 +282,9 @@ __device__ __forceinline__ double flip_prob(uint32_t a, double w) { return a ? (
 //   MT rules:  ftab[s+j] = flip probability of literal j
 //   probSAT:   ftab[s+j] = sum of the flip probabilities of literals 0..j, cscale[c] = UniformFloat's scale, or
 //              -(DERR_WEIGHTS | DERR_ALL_ZERO) when WeightedIndex::new fails on this clause
-__global__ void build_flip_tables_kernel(const DevInst I, const double* __restrict__ w, int algo, double* __restrict__ ftab,
-                                         double* __restrict__ cscale)
+__device__ __forceinline__ void build_flip_tables_clause(const DevInst& I, const double* __restrict__ w, int algo, double* __restrict__ ftab,
+                                                         double* __restrict__ cscale, uint32_t c)
 {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= I.m) return;
     uint32_t s, e;
     if (I.uniform_k) {
         s = c * I.uniform_k;
@@ -318,6 +316,13 @@ __global__ void build_flip_tables_kernel(const DevInst I, const double* __restri
             while (scale * (1.0 - 0x1p-52) >= run) scale = __longlong_as_double(__double_as_longlong(scale) - 1);
         cscale[c] = scale;
     }
+}
+
+__global__ void build_flip_tables_kernel(const DevInst I, const double* __restrict__ w, int algo, double* __restrict__ ftab,
+                                         double* __restrict__ cscale)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < I.m) build_flip_tables_clause(I, w, algo, ftab, cscale, c);
 }
 
 // ALGO is compile-time: every instantiation carries only its own flip rule (fewer registers, shorter loop)

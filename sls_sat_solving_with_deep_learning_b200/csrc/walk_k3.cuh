@@ -41,11 +41,9 @@ __host__ __device__ inline bool walk_k3_supports(const WalkArgs& a)
 //   crecx[c] = { {l0,l1,l2, k | err<<8}, {os0,ol0,os1,ol1}, {os2,ol2, X}, {Y, Z} }   (X, Y, Z doubles)
 //   probSAT:  X = scale, Y = cum0, Z = cum1;  err = DERR_WEIGHTS / DERR_ALL_ZERO if WeightedIndex::new fails
 //   MT rules: X = fp0,   Y = fp1,  Z = fp2    (absent literals: 0)
-__global__ void build_crecx_kernel(const uint4* __restrict__ crec, const uint32_t* __restrict__ occ_ptr,
-                                   const double* __restrict__ w, uint4* __restrict__ crecx, uint32_t m, uint32_t n, int algo)
+__device__ __forceinline__ void build_crecx_clause(const uint4* __restrict__ crec, const uint32_t* __restrict__ occ_ptr,
+                                                   const double* __restrict__ w, uint4* __restrict__ crecx, uint32_t c, uint32_t n, int algo)
 {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= m) return;
     const uint4 cr = crec[c];
     uint32_t lit[3] = {cr.x, cr.y, cr.z};
     uint32_t os[3], ol[3];
@@ -90,6 +88,28 @@ __global__ void build_crecx_kernel(const uint4* __restrict__ crec, const uint32_
     out[2] = make_uint4(os[2], ol[2], (uint32_t)__double2loint(X), (uint32_t)__double2hiint(X));
     out[3] = make_uint4((uint32_t)__double2loint(Y), (uint32_t)__double2hiint(Y), (uint32_t)__double2loint(Z),
                         (uint32_t)__double2hiint(Z));
+}
+
+__global__ void build_crecx_kernel(const uint4* __restrict__ crec, const uint32_t* __restrict__ occ_ptr,
+                                   const double* __restrict__ w, uint4* __restrict__ crecx, uint32_t m, uint32_t n, int algo)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < m) build_crecx_clause(crec, occ_ptr, w, crecx, c, n, algo);
+}
+
+// Batched form (sls_run_batch): the tables of every item of a launch group in ONE launch.  blk_begin[i] = first 256-clause
+// block of item i (n_items + 1 entries).  An item carries either a clause-record pool (k <= 3 kernels) or the generic
+// kernels' flip tables; Schoening's rule needs neither.
+__global__ void build_tables_batch_kernel(const WalkArgs* __restrict__ items, const uint32_t* __restrict__ blk_begin, uint32_t n_items)
+{
+    const uint32_t it = find_item(blk_begin, n_items, blockIdx.x);
+    const WalkArgs& a = items[it];
+    const uint32_t c = (blockIdx.x - __ldg(blk_begin + it)) * blockDim.x + threadIdx.x;
+    if (c >= a.inst.m) return;
+    if (a.crecx)
+        build_crecx_clause(a.inst.crec, a.inst.occ_ptr, a.w, const_cast<uint4*>(a.crecx), c, a.inst.n, a.algo);
+    else if (a.ftab)
+        build_flip_tables_clause(a.inst, a.w, a.algo, const_cast<double*>(a.ftab), const_cast<double*>(a.cscale), c);
 }
 
 // inclusive warp scan, two instructions per level (shuffle with predicate + predicated add)

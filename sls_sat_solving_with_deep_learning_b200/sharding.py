@@ -132,15 +132,17 @@ def run_batch_sharded(runner: Callable, costs: Sequence[float], nruns: int, *, d
     mine = instance_shard(costs, world)[rank]
     results = runner(mine) if mine else []
     dev = torch.device(device)
-    found = torch.zeros((n_inst, nruns), dtype=torch.int32, device=dev)
-    steps = torch.zeros((n_inst, nruns), dtype=torch.int64, device=dev)
-    best = torch.zeros(n_inst, dtype=torch.int64, device=dev)
-    flips = torch.zeros(n_inst, dtype=torch.int64, device=dev)
+    # this rank's rows are filled on the host and travel to the device as four tables (not two small copies per instance)
+    h_found = np.zeros((n_inst, nruns), dtype=np.int32)
+    h_steps = np.zeros((n_inst, nruns), dtype=np.int64)
+    h_best = np.zeros(n_inst, dtype=np.int64)
+    h_flips = np.zeros(n_inst, dtype=np.int64)
     for i, r in zip(mine, results):
-        found[i] = torch.as_tensor(np.asarray(r.found, dtype=np.int32), device=dev)
-        steps[i] = torch.as_tensor(np.asarray(r.steps, dtype=np.int64), device=dev)
-        best[i] = int(r.best_energy)
-        flips[i] = int(r.total_flips)
+        h_found[i] = np.asarray(r.found, dtype=np.int32)
+        h_steps[i] = np.asarray(r.steps, dtype=np.int64)
+        h_best[i] = int(r.best_energy)
+        h_flips[i] = int(r.total_flips)
+    found, steps, best, flips = (torch.from_numpy(a).to(dev) for a in (h_found, h_steps, h_best, h_flips))
     for t in (found, steps, best, flips):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return found.cpu().numpy().astype(bool), steps.cpu().numpy().astype(np.uint64), best.cpu().numpy(), flips.cpu().numpy()

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -43,8 +44,18 @@ def device_count() -> int:
     return c.value
 
 
+_thread_device = threading.local()
+
+
 def set_device(device: int) -> None:
+    """Select the CUDA device of the calling thread (cudaSetDevice semantics: a new thread starts on device 0)."""
     _check(_lib.load().sls_set_device(device))
+    _thread_device.index = int(device)
+
+
+def current_device() -> int:
+    """The device this thread selected with :func:`set_device` (0 if it never did)."""
+    return getattr(_thread_device, "index", 0)
 
 
 class Instance:

@@ -119,7 +119,7 @@ def test_many_tiles_per_persistent_cta():
 
 
 @pytest.mark.timeout(240, method="thread")  # a hung kernel blocks inside a C call: only the thread method ends it
-@pytest.mark.parametrize("precision", ["bf16x2", "tf32x3"])
+@pytest.mark.parametrize("precision", ["fp16x2", "bf16x2", "tf32x3"])
 def test_batch_size_sweep_terminates_and_rows_do_not_depend_on_the_batch(monkeypatch, precision):
     # Round 2 found a hang at 8 and at 64 instances of the config-4 shape (and at none of the sizes the other tests use): a
     # producer warp that reached a parity wait late found its mbarrier two completions ahead.  Timing decides whether that
@@ -144,8 +144,8 @@ def test_weight_multicast_clusters_are_bit_identical(monkeypatch):
     # the two CTAs of a cluster share every weight slab (each requests half of it, the copy engine multicasts); rows, MMAs
     # and their order per tile are unchanged, so the logits must not differ in a single bit -- for several tiles per
     # CTA, a ragged last wave (dummy tiles), and for a batch smaller than one cluster's worth of tiles
-    monkeypatch.setenv("SLS_B200_GNN_PRECISION", "bf16x2")
-    for n_inst in (40, 1):
+    for prec, n_inst in (("fp16x2", 40), ("fp16x2", 1), ("bf16x2", 40)):
+        monkeypatch.setenv("SLS_B200_GNN_PRECISION", prec)
         insts = []
         for i in range(n_inst):
             n, m = 200 + (i % 3), 855 + 7 * (i % 5)
@@ -160,23 +160,78 @@ def test_weight_multicast_clusters_are_bit_identical(monkeypatch):
         assert all(np.array_equal(a, b) for a, b in zip(p1, pc))
 
 
-def test_bf16_pieces_and_3xtf32_agree_within_the_contract(monkeypatch):
-    # default: two bf16 pieces per operand on kind::f16 (a0*b0 + a1*b0 + a0*b1, 16 mantissa bits per operand); tf32x3: the
-    # compensated TF32 product.  Both against the fp64 restatement; emulation (tools/precision_split_study.py) predicts
-    # 3.4e-5 and 1.9e-6
+def test_the_three_product_forms_agree_within_the_contract(monkeypatch):
+    # default fp16x2: two fp16 pieces per operand on kind::f16 (a0*b0 + a1*b0 + a0*b1, 22 mantissa bits per operand); bf16x2: the
+    # same with bf16 pieces (16 bits, fp32's range); tf32x3: the compensated TF32 product.  All against the fp64 restatement;
+    # the emulation (tools/precision_split_study.py) predicts 3.3e-6, 3.4e-5 and 1.8e-6
     n, m = 500, 2100
     clauses = random_ksat(n, m, 3, seed=77)
     inst = eng.Instance.from_clauses(n, clauses)
     params = go.init_params(seed=42)
     net = gnn.InteractionNetworkLCG(params)
     ref = go.model_probabilities(go.forward(params, go.lcg_graph(n, clauses), dtype=np.float64), n)
-    monkeypatch.setenv("SLS_B200_GNN_PRECISION", "bf16x2")
-    p_bf = net.probabilities([inst])[0]
+    p_default = net.probabilities([inst])[0]
+    got = {}
+    for prec in ("fp16x2", "bf16x2", "tf32x3"):
+        monkeypatch.setenv("SLS_B200_GNN_PRECISION", prec)
+        got[prec] = net.probabilities([inst])[0]
+    err = {k: float(np.abs(v - ref).max()) for k, v in got.items()}
+    print(err)
+    assert err["tf32x3"] < 2e-5
+    assert err["fp16x2"] < 2e-5   # five times the emulated figure, fifty times under the contract
+    assert err["bf16x2"] < 2e-4
+    assert np.array_equal(p_default, got["fp16x2"])  # the default for a model whose weights fit fp16's range
+    assert not np.array_equal(got["bf16x2"], got["tf32x3"]) and not np.array_equal(got["bf16x2"], got["fp16x2"])  # three kernels
+
+
+def test_fp16_pieces_saturate_and_out_of_range_models_default_to_bf16(monkeypatch):
+    # fp16's range is the price of its precision.  (1) A model whose LayerNorm outputs are large (scale x 3000: sums over a
+    # variable's occurrences pass 131008 = what two saturating pieces carry) is created with bf16 pieces as its default and
+    # stays inside the contract; forcing fp16x2 on it loses accuracy but never produces infinities (cvt.rn.satfinite).
+    # (2) The same for a model with a weight outside the range.
+    n, m = 60, 250
+    clauses = random_ksat(n, m, 3, seed=9)
+    graph = go.lcg_graph(n, clauses)
+    params = go.init_params(seed=5, bias_scale=0.1)
+    names = go.param_names(go.NUM_STEPS)
+    big = {k: dict(v) for k, v in params.items()}
+    for kind in ("edge", "node"):  # ONE step's LayerNorms: the next step's LayerNorm takes the factor out again, the model stays
+        ln = names["steps"][1][kind]["ln"]  # well conditioned, but the GEMMs in between see activations x 3000
+        big[ln]["scale"] = np.asarray(big[ln]["scale"], dtype=np.float32) * 3000.0
+        big[ln]["offset"] = np.asarray(big[ln]["offset"], dtype=np.float32) * 3000.0
+    ref = go.model_probabilities(go.forward(big, graph, dtype=np.float64), n)
+    inst = eng.Instance.from_clauses(n, clauses)
+    monkeypatch.setenv("SLS_B200_GNN_PRECISION", "fp16x2")
+    p = gnn.InteractionNetworkLCG(big).probabilities([inst])[0]
     monkeypatch.setenv("SLS_B200_GNN_PRECISION", "tf32x3")
-    p_tf = net.probabilities([inst])[0]
-    assert np.abs(p_tf - ref).max() < 2e-5
-    assert np.abs(p_bf - ref).max() < 2e-4   # five times the emulated figure, five times under the contract
-    assert not np.array_equal(p_bf, p_tf)    # the switch does select two different kernels
+    p_tf = gnn.InteractionNetworkLCG(big).probabilities([inst])[0]
+    print("activations x3000: fp16x2", np.abs(p - ref).max(), "tf32x3", np.abs(p_tf - ref).max())
+    assert np.abs(p_tf - ref).max() < PROB_TOL
+    assert np.isfinite(p).all()
+    monkeypatch.delenv("SLS_B200_GNN_PRECISION")
+    net_big = gnn.InteractionNetworkLCG(big)
+    p_auto = net_big.probabilities([inst])[0]
+    assert np.abs(p_auto - ref).max() < PROB_TOL
+    monkeypatch.setenv("SLS_B200_GNN_PRECISION", "bf16x2")
+    assert np.array_equal(p_auto, net_big.probabilities([inst])[0])  # LayerNorm outputs this large: the model's default is bf16x2
+    huge = {k: dict(v) for k, v in params.items()}
+    for k, v in huge.items():
+        if "scale" in v:
+            v["scale"] = np.asarray(v["scale"], dtype=np.float32) * 1.0e6  # far outside: most of every row saturates
+    monkeypatch.setenv("SLS_B200_GNN_PRECISION", "fp16x2")
+    assert np.isfinite(gnn.InteractionNetworkLCG(huge).probabilities([inst])[0]).all()
+    monkeypatch.delenv("SLS_B200_GNN_PRECISION")
+    wide = {k: dict(v) for k, v in params.items()}
+    first = names["steps"][0]["edge"]["l1"]
+    w = np.array(wide[first]["w"], dtype=np.float32)
+    w[0, 0] = 1.0e5  # outside fp16
+    wide[first]["w"] = w
+    ref_w = go.model_probabilities(go.forward(wide, graph, dtype=np.float64), n)
+    net_w = gnn.InteractionNetworkLCG(wide)
+    p_w = net_w.probabilities([inst])[0]
+    monkeypatch.setenv("SLS_B200_GNN_PRECISION", "bf16x2")
+    assert np.array_equal(p_w, net_w.probabilities([inst])[0])  # the model's default became bf16x2
+    assert np.abs(p_w - ref_w).max() < PROB_TOL
 
 
 def test_graph_edge_cases():
@@ -278,3 +333,29 @@ def test_transformed_apply_does_not_serve_stale_parameters():
     d2 = network.apply(b, graph)
     ref = go.forward(b, graph, dtype=np.float64)
     assert np.abs(gnn.get_model_probabilities(d2, n) - go.model_probabilities(ref, n)).max() < PROB_TOL
+
+
+def test_pipeline_equals_the_monolithic_calls():
+    # pipeline.solve_with_oracle cuts the batch into chunks that travel through three threads (handles, forward, walk);
+    # chains are keyed by (instance seed, chain id) and rows of the forward do not depend on their batch, so the chunked,
+    # overlapped run returns the same bits as one forward + one run_sls_batch over everything
+    from sls_sat_solving_with_deep_learning_b200 import pipeline
+
+    shapes = [(120 + 7 * (i % 5), 480 + 11 * (i % 7), 700 + i) for i in range(23)]
+    clause_lists = [random_ksat(n, m, 3, seed=s) for n, m, s in shapes]
+    net = gnn.InteractionNetworkLCG(go.init_params(seed=31, bias_scale=0.1))
+    insts = [eng.Instance.from_clauses(n, cl) for (n, _, _), cl in zip(shapes, clause_lists)]
+    seeds = [1000 + 3 * i for i in range(len(insts))]
+    p_all = net.probabilities(insts)
+    r_all = eng.run_sls_batch(insts, "moser", p_all, p_all, 400, 16, instance_seeds=seeds)
+    stats = {}
+    r_pipe, p_pipe = pipeline.solve_with_oracle(
+        net, list(zip(shapes, clause_lists)), "moser", 400, 16, chunk=5, instance_seeds=seeds, stats=stats,
+        make_instance=lambda sc: eng.Instance.from_clauses(sc[0][0], sc[1]))
+    assert len(r_pipe) == len(insts)
+    for a, b, pa, pb in zip(r_all, r_pipe, p_all, p_pipe):
+        assert np.array_equal(pa, pb)
+        assert np.array_equal(a.steps, b.steps) and np.array_equal(a.found, b.found)
+        assert a.best_energy == b.best_energy and a.total_flips == b.total_flips
+        assert np.array_equal(a.best_assignment, b.best_assignment)
+    assert stats["walk_kernel_ms"] > 0 and stats["forward_device_ms"] > 0

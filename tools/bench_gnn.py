@@ -48,5 +48,5 @@ clauses = [lits[int(row[c]):int(row[c + 1])].tolist() for c in range(m)]
 ref = go.model_probabilities(go.forward(params, go.lcg_graph(n, clauses), dtype=np.float64), n)
 err = float(np.abs(p[0] - ref).max())
 print(json.dumps({"instances": n_inst, "device_ms": best, "instances_per_s": n_inst / (best * 1e-3),
-                  "dense_tflops": flops / (best * 1e-3) / 1e12, "precision": os.environ.get("SLS_B200_GNN_PRECISION", "bf16x2"), "mma_tflops_issued": 3 * flops / (best * 1e-3) / 1e12,
+                  "dense_tflops": flops / (best * 1e-3) / 1e12, "precision": os.environ.get("SLS_B200_GNN_PRECISION", "fp16x2"), "mma_tflops_issued": 3 * flops / (best * 1e-3) / 1e12,
                   "max_abs_dp_vs_fp64": err}))

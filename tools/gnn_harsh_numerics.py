@@ -1,4 +1,4 @@
-"""How far do the two product forms of the oracle-forward kernel (bf16x2, tf32x3) stay from an fp64 forward when the
+"""How far do the two product forms of the oracle-forward kernel (fp16x2, bf16x2, tf32x3) stay from an fp64 forward when the
 parameters are NOT haiku's mild random init: weights scaled up, LayerNorm scales / offsets spread out, graphs with long
 clauses (G4SAT shapes, k up to 297).  usage: python tools/gnn_harsh_numerics.py"""
 import json
@@ -52,7 +52,7 @@ for wscale, ln_sigma in ((1.0, 0.0), (8.0, 0.0), (1.0, 0.5), (8.0, 0.5), (0.125,
         ref32 = go.model_probabilities(go.forward(params, go.lcg_graph(inst.n, clauses), dtype=np.float32), inst.n)
         row = {"weights_x": wscale, "ln_sigma": ln_sigma, "graph": name, "max_k": inst.max_clause_len,
                "numpy_fp32": float(np.abs(ref32 - ref).max())}
-        for prec in ("bf16x2", "tf32x3"):
+        for prec in ("fp16x2", "bf16x2", "tf32x3"):
             os.environ["SLS_B200_GNN_PRECISION"] = prec
             p = net.probabilities([inst])[0]
             row[prec] = float(np.abs(p - ref).max())
@@ -60,4 +60,4 @@ for wscale, ln_sigma in ((1.0, 0.0), (8.0, 0.0), (1.0, 0.5), (8.0, 0.5), (0.125,
         print(json.dumps(row), flush=True)
     net.close()
 os.environ.pop("SLS_B200_GNN_PRECISION", None)
-print("worst bf16x2", max(r["bf16x2"] for r in out), "worst tf32x3", max(r["tf32x3"] for r in out))
+print("worst fp16x2", max(r["fp16x2"] for r in out), "worst bf16x2", max(r["bf16x2"] for r in out), "worst tf32x3", max(r["tf32x3"] for r in out))

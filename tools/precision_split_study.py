@@ -33,6 +33,11 @@ def bf16_trunc(x):
     return (u & np.uint32(0xFFFF0000)).view(np.float32)
 
 
+def fp16(x):  # round to nearest even, subnormals and overflow as the hardware conversion
+    with np.errstate(over="ignore"):
+        return np.asarray(x, dtype=np.float32).astype(np.float16).astype(np.float32)
+
+
 def split_kernel(x, rnd, pieces):  # first piece rounded half up, residual truncated
     a0 = bf16_half_up(x)
     return [a0, bf16_trunc((np.asarray(x, dtype=np.float32) - a0).astype(np.float32))]
@@ -56,6 +61,9 @@ MODES = {
     "bf16 2 pieces, 3 terms, A: half-up + truncated residual": ("kernel", 2, [(0, 0), (0, 1), (1, 0)]),
     "bf16 2 pieces, 4 terms": (bf16, 2, [(0, 0), (0, 1), (1, 0), (1, 1)]),
     "bf16 3 pieces, 6 terms": (bf16, 3, [(0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (2, 0)]),
+    "fp16 x1": (fp16, 1, [(0, 0)]),
+    "fp16 A 2 pieces x B 1 piece, 2 terms": (fp16, 2, [(0, 0), (1, 0)]),
+    "fp16 2 pieces, 3 terms": (fp16, 2, [(0, 0), (0, 1), (1, 0)]),
 }
 
 
@@ -96,10 +104,27 @@ def forward_mode(params, graph, mode):
     return h @ P[names["readout"]]["w"] + P[names["readout"]]["b"]
 
 
+def harsh(params, weights_x, ln_sigma, seed=5):
+    """the parameter families of tools/gnn_harsh_numerics.py: Linear weights scaled, LayerNorm scale ~ N(1, s), offset ~ N(0, s)"""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for k, v in params.items():
+        v = {kk: np.array(vv, dtype=np.float32) for kk, vv in v.items()}
+        if "w" in v:
+            v["w"] = v["w"] * np.float32(weights_x)
+        if "scale" in v and ln_sigma > 0:
+            v["scale"] = (1.0 + ln_sigma * rng.standard_normal(v["scale"].shape)).astype(np.float32)
+            v["offset"] = (ln_sigma * rng.standard_normal(v["offset"].shape)).astype(np.float32)
+        out[k] = v
+    return out
+
+
 if __name__ == "__main__":
     n_inst = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     n, m = 500, 2100
     params = go.init_params(seed=42)
+    if len(sys.argv) > 3:
+        params = harsh(params, float(sys.argv[2]), float(sys.argv[3]))
     worst = {k: 0.0 for k in MODES}
     for i in range(n_inst):
         row, lits = synth.random_ksat_csr(n, m, 3, 20260104 + i)
