@@ -63,7 +63,7 @@ BYTES_PER_FLIP = bytes_per_step(K, K * ALPHA, 1.0)  # probSAT: one flip per step
 # ---- C1 / C4 / C5 shapes ("Config shorthands") ------------------------------------------------------
 C1_INSTANCES, C1_RUNS, C1_NSTEPS, C1_CPU_STRIDE = 2052, 100, 100_000, 16
 C4_INSTANCES, C4_N, C4_M, C4_RUNS, C4_NSTEPS, C4_SEED = 10_000, 500, 2100, 100, 10_000 - 1, 20260104
-C4_CHUNK = int(os.environ.get("SLS_BENCH_C4_CHUNK", "1000"))  # instances per pipeline chunk (pipeline.solve_with_oracle)
+C4_CHUNK = int(os.environ.get("SLS_BENCH_C4_CHUNK", "500"))  # instances per pipeline chunk (pipeline.solve_with_oracle)
 C5_N, C5_M, C5_CHAINS, C5_NSTEPS, C5_SEED = 1_000_000, 4_000_000, 65_536, 1000, 20260105
 ALL_LEGS = ("c2_moser", "c1_batch", "c4_pipeline", "c5", "clause_eval")
 

@@ -71,7 +71,7 @@ def staged(stages: Sequence[Callable], items, depth: int = 2) -> list:
 
 
 def solve_with_oracle(net, sources, algo: str, nsteps: int, nruns: int, *, make_instance: Callable | None = None,
-                      instance_seeds=None, chunk: int = 1024, pre_compute_mapping: bool = True, prob_flip_best: float = 0.0,
+                      instance_seeds=None, chunk: int = 500, pre_compute_mapping: bool = True, prob_flip_best: float = 0.0,
                       device: int | None = None, keep_instances: bool = False, stats: dict | None = None):
     """``net.probabilities`` on every instance, then ``run_sls_batch`` with those probabilities as ``weights_initialize`` and
     ``weights_resample`` (the evaluation script's oracle-guided run, evaluate_with_given_params.py:116-147), chunk by chunk
@@ -80,8 +80,8 @@ def solve_with_oracle(net, sources, algo: str, nsteps: int, nruns: int, *, make_
     ``sources``: one entry per instance -- an :class:`Instance`, or whatever ``make_instance`` turns into one (a DIMACS path,
     a ``(n, row_ptr, signed_lits)`` CSR triple ...).  ``instance_seeds``: one seed per instance (default 1 + index).
     Returns ``(results, probabilities)``: lists in source order of :class:`SlsResult` and of p[n_i]; with ``keep_instances``
-    a third list holds the handles.  ``stats`` (optional dict) receives the summed stage times in seconds and the summed
-    device times in ms."""
+    a third list holds the handles.  ``stats`` (optional dict) receives the summed stage times in seconds, the summed
+    device times in ms and ``timeline``: (stage, first instance of the chunk, start s, end s) per stage call."""
     sources = list(sources)
     k = len(sources)
     seeds = list(range(1, k + 1)) if instance_seeds is None else [int(s) for s in instance_seeds]
@@ -89,7 +89,11 @@ def solve_with_oracle(net, sources, algo: str, nsteps: int, nruns: int, *, make_
         raise ValueError("instance_seeds needs one seed per instance")
     import time
 
-    acc = {"build_s": 0.0, "forward_s": 0.0, "forward_device_ms": 0.0, "walk_s": 0.0, "walk_kernel_ms": 0.0}
+    acc = {"build_s": 0.0, "forward_s": 0.0, "forward_device_ms": 0.0, "walk_s": 0.0, "walk_kernel_ms": 0.0, "timeline": []}
+    t_origin = time.perf_counter()
+
+    def stamp(stage, lo, t0):  # (stage, first instance of the chunk, start, end) in seconds since the call
+        acc["timeline"].append((stage, lo, round(t0 - t_origin, 4), round(time.perf_counter() - t_origin, 4)))
 
     dev = _solver.current_device() if device is None else int(device)
 
@@ -101,6 +105,7 @@ def solve_with_oracle(net, sources, algo: str, nsteps: int, nruns: int, *, make_
         hi = min(lo + chunk, k)
         insts = [s if isinstance(s, _solver.Instance) else make_instance(s) for s in sources[lo:hi]]
         acc["build_s"] += time.perf_counter() - t0
+        stamp("build", lo, t0)
         return lo, insts
 
     def forward(x):
@@ -110,6 +115,7 @@ def solve_with_oracle(net, sources, algo: str, nsteps: int, nruns: int, *, make_
         probs = net.probabilities(insts)
         acc["forward_s"] += time.perf_counter() - t0
         acc["forward_device_ms"] += net.last_kernel_ms
+        stamp("forward", lo, t0)
         return lo, insts, probs
 
     def walk(x):
@@ -120,6 +126,7 @@ def solve_with_oracle(net, sources, algo: str, nsteps: int, nruns: int, *, make_
                                     instance_seeds=seeds[lo:lo + len(insts)])
         acc["walk_s"] += time.perf_counter() - t0
         acc["walk_kernel_ms"] += res[0].kernel_ms if res else 0.0
+        stamp("walk", lo, t0)
         return res, probs, (insts if keep_instances else None)
 
     if make_instance is None and any(not isinstance(s, _solver.Instance) for s in sources):

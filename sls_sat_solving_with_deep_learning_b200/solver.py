@@ -312,20 +312,25 @@ def run_sls_batch(
     instances = list(instances)
     k = len(instances)
     p = _make_params(algo, nsteps, nruns, False, pre_compute_mapping, prob_flip_best, seed, chain_offset)
+    same = weights_resample is weights_initialize  # the oracle-guided call: one list for both (no second conversion)
     wi = [_weights(w) for w in weights_initialize]
-    wr = [_weights(w) for w in weights_resample]
+    wr = wi if same else [_weights(w) for w in weights_resample]
     if len(wi) != k or len(wr) != k:
         raise ValueError("one weight vector per instance is required")
     lens = [max(len(a), len(b)) for a, b in zip(wi, wr)]
     off = np.zeros(k + 1, dtype=np.uint64)
     off[1:] = np.cumsum(lens)
-    cat_i = np.zeros(max(int(off[-1]), 1), dtype=np.float64)
-    cat_r = np.zeros(max(int(off[-1]), 1), dtype=np.float64)
     for i in range(k):
         if len(wi[i]) < instances[i].n or (len(wr[i]) < instances[i].n and algo != "schoening"):
             raise PanicException(4, "weights shorter than var_count")
-        cat_i[int(off[i]): int(off[i]) + len(wi[i])] = wi[i]
-        cat_r[int(off[i]): int(off[i]) + len(wr[i])] = wr[i]
+    if same:
+        cat_i = cat_r = np.concatenate(wi) if k and int(off[-1]) else np.zeros(1, dtype=np.float64)
+    else:
+        cat_i = np.zeros(max(int(off[-1]), 1), dtype=np.float64)
+        cat_r = np.zeros(max(int(off[-1]), 1), dtype=np.float64)
+        for i in range(k):
+            cat_i[int(off[i]): int(off[i]) + len(wi[i])] = wi[i]
+            cat_r[int(off[i]): int(off[i]) + len(wr[i])] = wr[i]
     bufs = [_Buffers(inst.n, nruns, nsteps, False) for inst in instances]
     results = (_lib.RunResult * max(k, 1))(*[b.res for b in bufs])
     handles = (C.c_void_p * max(k, 1))(*[inst._h.value for inst in instances])
