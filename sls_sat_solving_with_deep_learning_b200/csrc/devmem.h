@@ -6,10 +6,13 @@
 // call of the same shape allocates without talking to the OS.  The pool is the library's own (cudaMemPoolCreate):
 // the device's default pool and its release threshold, which belong to the host application, are left alone.
 //
-// Large buffers (GNN activations, HBM-tier chain state: hundreds of MB to tens of GB) do NOT go through the pool:
+// Large buffers (GNN activations, HBM-tier chain state: more than 512 MB, up to tens of GB) do NOT go through the pool:
 // growing the pool by gigabytes costs ~30 ms per GB, and keeping such blocks cached would take them away from the
 // application's own allocator (torch uses cudaMalloc, which cannot see the pool's free memory).  They use plain
-// cudaMalloc / cudaFree, which is cheap at that size.
+// cudaMalloc / cudaFree.  The limit was 32 MB until the chunked forward -> walk pipeline (pipeline.py) showed what that costs
+// when two host threads use the library at once: a cudaMalloc / cudaFree pair of a 67 MB table per walk call stalled BOTH
+// threads for 0.5-0.8 s in 1-3 of every 20 calls (cudaFree waits for the device and serialises with the other thread's
+// allocations); with those blocks in the pool the same run has no such outliers (2300 instead of 1650-1930 instances/s).
 //
 // Freeing: dfree() does NOT synchronise the device per buffer.  Its contract is "no work that uses the block is in
 // flight".  The synchronous entry points of the library end with a wait on their own work, and mark the time in between
@@ -19,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_set>
 
@@ -26,7 +30,7 @@ namespace slsb {
 
 constexpr int kMaxDevices = 64;
 constexpr uint64_t kPoolKeepBytes = 4ull << 30;  // freed memory above this goes back to the driver at the next sync
-constexpr size_t kPoolMaxBlock = 32u << 20;       // larger requests bypass the pool
+constexpr size_t kPoolMaxBlock = 512u << 20;      // larger requests bypass the pool (SLS_B200_POOL_MAX_BLOCK_MB)
 
 struct DevMemState {
     std::mutex mu;
@@ -57,6 +61,7 @@ inline cudaError_t devmem_stream(int device, cudaStream_t* out, cudaMemPool_t* p
         cudaError_t e = cudaMemPoolCreate(&st.pool[device], &props);
         if (e != cudaSuccess) return e;
         uint64_t keep = kPoolKeepBytes;
+        if (const char* f = std::getenv("SLS_B200_POOL_KEEP_MB")) keep = (uint64_t)std::strtoull(f, nullptr, 10) << 20;
         e = cudaMemPoolSetAttribute(st.pool[device], cudaMemPoolAttrReleaseThreshold, &keep);
         if (e != cudaSuccess) return e;
         e = cudaStreamCreateWithFlags(&st.stream[device], cudaStreamNonBlocking);
@@ -85,7 +90,11 @@ template <class T>
 inline cudaError_t dmalloc(T** p, size_t bytes)
 {
     *p = nullptr;
-    if (bytes > kPoolMaxBlock) {
+    static const size_t max_block = [] {
+        const char* f = std::getenv("SLS_B200_POOL_MAX_BLOCK_MB");
+        return f ? (size_t)std::strtoull(f, nullptr, 10) << 20 : kPoolMaxBlock;
+    }();
+    if (bytes > max_block) {
         void* q = nullptr;
         const cudaError_t e = cudaMalloc(&q, bytes);
         if (e != cudaSuccess) return e;

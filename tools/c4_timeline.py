@@ -1,5 +1,6 @@
 """Gantt view of pipeline.solve_with_oracle on the config-4 shape: which stage of which chunk ran when (host wall clock).
 usage: python tools/c4_timeline.py [instances] [chunk]"""
+import gc
 import os
 import sys
 import time
@@ -17,6 +18,8 @@ net = gnn.InteractionNetworkLCG(synth.random_oracle_params(seed=42))
 warm = [eng.Instance.from_csr(n, *c) for c in csrs[:4]]
 pw = net.probabilities(warm)
 eng.run_sls_batch(warm, "moser", pw, pw, 100, 100)
+if os.environ.get("C4_NO_GC"):
+    gc.disable()
 st = {}
 t0 = time.perf_counter()
 pipeline.solve_with_oracle(net, csrs, "moser", 9999, 100, make_instance=lambda c: eng.Instance.from_csr(n, *c), chunk=chunk, stats=st)
@@ -24,4 +27,5 @@ wall = time.perf_counter() - t0
 print(f"{k} instances, chunk {chunk}: wall {wall:.3f} s = {k / wall:.0f} instances/s; forward device {st['forward_device_ms']:.0f} ms, "
       f"walk kernels {st['walk_kernel_ms']:.0f} ms")
 for stage, lo, a, b in sorted(st["timeline"], key=lambda x: x[2]):
-    print(f"{stage:8s} chunk@{lo:6d}  {a:7.3f} -> {b:7.3f}  ({(b - a) * 1e3:6.0f} ms)")
+    if stage != "build" and (b - a) * 1e3 > 1.5 * (1e3 * wall / (k / chunk)) or os.environ.get("C4_ALL"):
+        print(f"{stage:8s} chunk@{lo:6d}  {a:7.3f} -> {b:7.3f}  ({(b - a) * 1e3:6.0f} ms)")
