@@ -429,7 +429,10 @@ def leg_c4_pipeline(ctx):
         res, _, insts = ctx["pipeline"].solve_with_oracle(
             net, [csrs[i] for i in idx], "moser", C4_NSTEPS, C4_RUNS, make_instance=lambda c: eng.Instance.from_csr(C4_N, *c),
             instance_seeds=[1 + i for i in idx], chunk=C4_CHUNK, keep_instances=True, stats=st)
-        stage.update(st)
+        stage.update({k: v for k, v in st.items() if k != "timeline"})  # sums over the chunks; the Gantt view is tools/c4_timeline.py
+        if os.environ.get("SLS_BENCH_C4_TIMELINE") and ctx["rank"] == 0:
+            for row in sorted(st["timeline"], key=lambda x: x[2]):
+                print("c4 timeline", row, file=sys.stderr)
         keep["insts"] = insts
         return res
 
