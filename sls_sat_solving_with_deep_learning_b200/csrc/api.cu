@@ -121,13 +121,16 @@ void build_image(const HostInstance& h, InstImage& img)
     }
 }
 
-// One allocation and ONE host-to-device copy per instance.
-int commit_image(sls_instance* inst, const InstImage& img, int dev)
+// One allocation and ONE host-to-device copy per instance.  The copy is issued on the memory pool's own non-blocking stream
+// and the CALLER waits for that stream (once per instance, or once per group of a batch): an upload then neither waits for
+// nor delays kernels of other host threads on the default stream -- pipeline.solve_with_oracle uploads the next chunk while
+// the walk of the previous one runs.
+int commit_image(sls_instance* inst, const InstImage& img, int dev, cudaStream_t up)
 {
     const HostInstance& h = inst->host;
     char* blob = nullptr;
     CUDA_TRY(dmalloc(&blob, img.bytes.size()));
-    cudaError_t e = cudaMemcpy(blob, img.bytes.data(), img.bytes.size(), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpyAsync(blob, img.bytes.data(), img.bytes.size(), cudaMemcpyHostToDevice, up);
     if (e != cudaSuccess) {
         dfree(blob);
         return set_error(SLS_ERR_CUDA, std::string("cudaMemcpy(instance): ") + cudaGetErrorString(e));
@@ -178,7 +181,12 @@ int ensure_on_device(sls_instance* inst)
     }
     InstImage img;
     build_image(inst->host, img);
-    return commit_image(inst, img, dev);
+    cudaStream_t up;
+    CUDA_TRY(devmem_stream(dev, &up));
+    const int rc = commit_image(inst, img, dev, up);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(up));  // the image is complete before any kernel of any stream may read it
+    return SLS_OK;
 }
 
 // The same for a batch: the images of the instances that are not resident yet are built by up to 16 host threads,
@@ -196,6 +204,8 @@ int ensure_batch_on_device(sls_instance* const* insts, uint32_t n_inst)
     }
     if (todo.empty()) return SLS_OK;
     const size_t chunk = 64;  // images alive at a time: bounds the host staging memory
+    cudaStream_t up;
+    CUDA_TRY(devmem_stream(dev, &up));
     std::vector<InstImage> imgs(std::min(chunk, todo.size()));
     for (size_t base = 0; base < todo.size(); base += chunk) {
         const size_t cnt = std::min(chunk, todo.size() - base);
@@ -216,9 +226,10 @@ int ensure_batch_on_device(sls_instance* const* insts, uint32_t n_inst)
                 dfree(inst->d_blob);
                 inst->d_blob = nullptr;
             }
-            int rc = commit_image(inst, imgs[k], dev);
+            int rc = commit_image(inst, imgs[k], dev, up);
             if (rc) return rc;
         }
+        CUDA_TRY(cudaStreamSynchronize(up));  // before the staging images are rebuilt, and before anything reads the copies
     }
     return SLS_OK;
 }

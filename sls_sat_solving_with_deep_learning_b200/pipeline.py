@@ -6,7 +6,7 @@ The stages of a chunk are (1) handles: CSR / DIMACS -> :class:`Instance` (host: 
 forward (instance upload, LCG graphs on the device, the GNN kernels, probabilities back to the host) and (3) the batched
 walk (weights -> thresholds on the host, one launch per kernel family, results back).  One call per stage over the whole
 batch leaves the GPU idle while the host prepares the next stage -- on the config-4 shape the device is busy 3.2 s of 5.2 s.
-Here the batch is cut into chunks that travel through three worker threads (the C library releases the GIL; its calls are
+Here the batch is cut into chunks that travel through three (or, with two model handles, four) worker threads (the C library releases the GIL; its calls are
 thread-safe: thread-local error state, a locked memory pool); the device work of one chunk runs under the host work of its
 neighbours.  Results do not depend on the chunking: instance i is solved with ``instance_seeds[i]`` and chains are keyed
 by (seed, chain id) only.
@@ -22,37 +22,57 @@ from . import solver as _solver
 _STOP = object()
 
 
-def staged(stages: Sequence[Callable], items, depth: int = 2) -> list:
-    """Run ``stages[k](x)`` for every item, stage k of item i overlapping stage k+1 of item i-1 (one thread per stage, bounded
-    queues of ``depth`` items between them).  Returns the last stage's outputs in item order; the first exception of any
-    stage is re-raised after the threads have drained."""
+def staged(stages: Sequence, items, depth: int = 2) -> list:
+    """Run the stages over every item, stage k of item i overlapping stage k+1 of item i-1.  A stage is a callable (one worker
+    thread) or a list of callables (one worker thread each, taking items as they come -- e.g. two forward workers on two model
+    handles); bounded queues of ``depth`` items connect the stages and every stage hands its results on in ITEM ORDER.  Returns
+    the last stage's outputs in item order; the first exception of any stage is re-raised after the threads have drained."""
     items = list(items)
+    stages = [list(s) if isinstance(s, (list, tuple)) else [s] for s in stages]
     qs = [queue.Queue(maxsize=depth) for _ in range(len(stages) + 1)]
     failure: list[BaseException] = []
+    turn = [threading.Condition() for _ in stages]
+    next_out = [0] * len(stages)      # sequence number the stage hands on next
+    live = [len(s) for s in stages]   # workers of the stage that have not seen the end of the input yet
 
-    def work(k):
+    def work(k, fn):
         while True:
             x = qs[k].get()
             if x is _STOP:
-                qs[k + 1].put(_STOP)
+                qs[k].put(_STOP)  # for the stage's other workers
+                with turn[k]:
+                    live[k] -= 1
+                    last = live[k] == 0
+                if last:
+                    qs[k].get()  # the marker this worker has just put back
+                    qs[k + 1].put(_STOP)
                 return
-            if failure:
-                continue  # drain: keep the upstream producers from blocking on a full queue
-            try:
-                qs[k + 1].put(stages[k](x))
-            except BaseException as e:  # noqa: BLE001 -- PanicException (the reference's panic) is a BaseException
-                failure.append(e)
+            seq, val = x
+            y = None
+            if not failure:
+                try:
+                    y = fn(val)
+                except BaseException as e:  # noqa: BLE001 -- PanicException (the reference's panic) is a BaseException
+                    failure.append(e)
+            with turn[k]:  # hand on in item order (a failed or skipped item only advances the counter)
+                while next_out[k] != seq:
+                    turn[k].wait()
+            if not failure:
+                qs[k + 1].put((seq, y))
+            with turn[k]:
+                next_out[k] += 1
+                turn[k].notify_all()
 
-    threads = [threading.Thread(target=work, args=(k,), daemon=True) for k in range(len(stages))]
+    threads = [threading.Thread(target=work, args=(k, fn), daemon=True) for k, fns in enumerate(stages) for fn in fns]
     for t in threads:
         t.start()
     out = []
 
     def feed():
-        for x in items:
+        for seq, x in enumerate(items):
             if failure:
                 break
-            qs[0].put(x)
+            qs[0].put((seq, x))
         qs[0].put(_STOP)
 
     feeder = threading.Thread(target=feed, daemon=True)
@@ -61,7 +81,7 @@ def staged(stages: Sequence[Callable], items, depth: int = 2) -> list:
         y = qs[-1].get()
         if y is _STOP:
             break
-        out.append(y)
+        out.append(y[1])
     feeder.join()
     for t in threads:
         t.join()
@@ -77,6 +97,9 @@ def solve_with_oracle(net, sources, algo: str, nsteps: int, nruns: int, *, make_
     ``weights_resample`` (the evaluation script's oracle-guided run, evaluate_with_given_params.py:116-147), chunk by chunk
     with the stages overlapped.
 
+    ``net``: an :class:`~.gnn.InteractionNetworkLCG`, or a list of them built from the same parameters -- one forward worker
+    thread per handle (a handle owns its activation workspace, so two handles let the forward of chunk i+2 be queued while
+    the walk of chunk i+1 is still being prepared on the host).
     ``sources``: one entry per instance -- an :class:`Instance`, or whatever ``make_instance`` turns into one (a DIMACS path,
     a ``(n, row_ptr, signed_lits)`` CSR triple ...).  ``instance_seeds``: one seed per instance (default 1 + index).
     Returns ``(results, probabilities)``: lists in source order of :class:`SlsResult` and of p[n_i]; with ``keep_instances``
@@ -108,15 +131,20 @@ def solve_with_oracle(net, sources, algo: str, nsteps: int, nruns: int, *, make_
         stamp("build", lo, t0)
         return lo, insts
 
-    def forward(x):
-        lo, insts = x
-        pin_device()
-        t0 = time.perf_counter()
-        probs = net.probabilities(insts)
-        acc["forward_s"] += time.perf_counter() - t0
-        acc["forward_device_ms"] += net.last_kernel_ms
-        stamp("forward", lo, t0)
-        return lo, insts, probs
+    lock = threading.Lock()
+
+    def forward_on(one_net):
+        def forward(x):
+            lo, insts = x
+            pin_device()
+            t0 = time.perf_counter()
+            probs = one_net.probabilities(insts)
+            with lock:
+                acc["forward_s"] += time.perf_counter() - t0
+                acc["forward_device_ms"] += one_net.last_kernel_ms
+                stamp("forward", lo, t0)
+            return lo, insts, probs
+        return forward
 
     def walk(x):
         lo, insts, probs = x
@@ -131,7 +159,8 @@ def solve_with_oracle(net, sources, algo: str, nsteps: int, nruns: int, *, make_
 
     if make_instance is None and any(not isinstance(s, _solver.Instance) for s in sources):
         raise ValueError("sources that are not Instance handles need make_instance")
-    parts = staged([build, forward, walk], range(0, k, max(int(chunk), 1)))
+    nets = list(net) if isinstance(net, (list, tuple)) else [net]
+    parts = staged([build, [forward_on(one) for one in nets], walk], range(0, k, max(int(chunk), 1)))
     results = [r for p in parts for r in p[0]]
     probs = [q for p in parts for q in p[1]]
     if stats is not None:

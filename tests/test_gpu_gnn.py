@@ -359,3 +359,8 @@ def test_pipeline_equals_the_monolithic_calls():
         assert a.best_energy == b.best_energy and a.total_flips == b.total_flips
         assert np.array_equal(a.best_assignment, b.best_assignment)
     assert stats["walk_kernel_ms"] > 0 and stats["forward_device_ms"] > 0
+    # two model handles = two forward workers; results still in source order and bit-identical
+    net2 = gnn.InteractionNetworkLCG(go.init_params(seed=31, bias_scale=0.1))
+    r_two, p_two = pipeline.solve_with_oracle([net, net2], insts, "moser", 400, 16, chunk=3, instance_seeds=seeds)
+    for a, b, pa, pb in zip(r_all, r_two, p_all, p_two):
+        assert np.array_equal(pa, pb) and np.array_equal(a.steps, b.steps) and a.total_flips == b.total_flips

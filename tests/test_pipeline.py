@@ -32,6 +32,29 @@ def test_staged_keeps_item_order_and_overlaps_stages():
     assert active["max"] >= 2  # different items were in different stages at the same time
 
 
+def test_staged_multi_worker_stage_hands_on_in_item_order():
+    seen = []
+
+    def slow_or_fast(tag):
+        def f(x):
+            time.sleep(0.02 if (x % 2 == 0) == (tag == "a") else 0.001)  # the two workers finish out of order
+            return (x, tag)
+        return f
+
+    def last(y):
+        seen.append(y[0])
+        return y
+
+    for n in (0, 1, 2, 7, 20):
+        del seen[:]
+        out = pipeline.staged([lambda x: x, [slow_or_fast("a"), slow_or_fast("b")], last], range(n), depth=2)
+        assert [o[0] for o in out] == list(range(n)) and seen == list(range(n))
+        if n >= 7:
+            assert {o[1] for o in out} == {"a", "b"}  # both workers took part
+    with pytest.raises(ValueError):
+        pipeline.staged([lambda x: x, [slow_or_fast("a"), lambda x: (_ for _ in ()).throw(ValueError("boom"))], last], range(30))
+
+
 def test_staged_without_items_and_with_one_stage():
     assert pipeline.staged([lambda x: x], []) == []
     assert pipeline.staged([lambda x: 2 * x], [1, 2, 3], depth=1) == [2, 4, 6]
@@ -74,6 +97,11 @@ def test_solve_with_oracle_chunks_seeds_and_order(monkeypatch):
     assert [len(p) for p in probs] == [3 + t for t in range(10)]
     assert calls == [((0, 1, 2, 3), (100, 101, 102, 103)), ((4, 5, 6, 7), (104, 105, 106, 107)), ((8, 9), (108, 109))]
     assert stats["walk_kernel_ms"] == 6.0 and stats["forward_device_ms"] == 3.0
+    del calls[:]
+    res2, _ = pipeline.solve_with_oracle([FakeNet(), FakeNet()], list(range(10)), "moser", 100, 4, chunk=3,
+                                         make_instance=lambda t: SimpleNamespace(tag=t, n=3 + t),
+                                         instance_seeds=[100 + t for t in range(10)])
+    assert [r.tag for r in res2] == list(range(10)) and [c[0] for c in calls] == [(0, 1, 2), (3, 4, 5), (6, 7, 8), (9,)]
     with pytest.raises(ValueError):
         pipeline.solve_with_oracle(FakeNet(), [1, 2], "moser", 1, 1)  # not handles and no make_instance
     with pytest.raises(ValueError):
