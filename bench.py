@@ -63,7 +63,8 @@ BYTES_PER_FLIP = bytes_per_step(K, K * ALPHA, 1.0)  # probSAT: one flip per step
 # ---- C1 / C4 / C5 shapes ("Config shorthands") ------------------------------------------------------
 C1_INSTANCES, C1_RUNS, C1_NSTEPS, C1_CPU_STRIDE = 2052, 100, 100_000, 16
 C4_INSTANCES, C4_N, C4_M, C4_RUNS, C4_NSTEPS, C4_SEED = 10_000, 500, 2100, 100, 10_000 - 1, 20260104
-C4_CHUNK = int(os.environ.get("SLS_BENCH_C4_CHUNK", "500"))  # instances per pipeline chunk (pipeline.solve_with_oracle)
+C4_CHUNK = int(os.environ.get("SLS_BENCH_C4_CHUNK", "1000"))  # instances per pipeline chunk (pipeline.solve_with_oracle)
+C4_HANDLES = int(os.environ.get("SLS_BENCH_C4_HANDLES", "2"))  # model handles = forward worker threads of the pipeline
 C5_N, C5_M, C5_CHAINS, C5_NSTEPS, C5_SEED = 1_000_000, 4_000_000, 65_536, 1000, 20260105
 ALL_LEGS = ("c2_moser", "c1_batch", "c4_pipeline", "c5", "clause_eval")
 
@@ -417,9 +418,14 @@ def leg_c4_pipeline(ctx):
     csrs = {i: csr_of(shapes[i]) for i in mine}
     params = synth.random_oracle_params(seed=42)
     net = gnn.InteractionNetworkLCG(params)
-    warm = [eng.Instance.from_csr(C4_N, *csrs[i]) for i in mine[:4]]
-    pw = net.probabilities(warm)
-    eng.run_sls_batch(warm, "moser", pw, pw, 100, C4_RUNS)
+    # warm-up on one chunk of the real size (handles that are dropped again): the library's memory pool and the forward's
+    # workspace reach their working size before the timed pass -- a fresh process otherwise spends 0.5-1.5 s of the first
+    # chunks in cudaMalloc (measured: 1620-1910 instances/s for the first runs on a box, 2430 once the allocations are warm)
+    nets = [net] + [gnn.InteractionNetworkLCG(params) for _ in range(C4_HANDLES - 1)]
+    warm = [eng.Instance.from_csr(C4_N, *csrs[i]) for i in mine[:C4_CHUNK]]
+    pw = [one.probabilities(warm) for one in nets][0]
+    eng.run_sls_batch(warm, "moser", pw, pw, C4_NSTEPS, C4_RUNS)
+    del warm, pw
     stage = {"build_s": 0.0, "forward_s": 0.0, "forward_device_ms": 0.0, "walk_s": 0.0, "walk_kernel_ms": 0.0}
     keep = {}
 
@@ -427,7 +433,7 @@ def leg_c4_pipeline(ctx):
         # the product's pipeline: chunks of C4_CHUNK instances, handle build / forward / walk overlapped on three threads
         st = {}
         res, _, insts = ctx["pipeline"].solve_with_oracle(
-            net, [csrs[i] for i in idx], "moser", C4_NSTEPS, C4_RUNS, make_instance=lambda c: eng.Instance.from_csr(C4_N, *c),
+            nets if len(nets) > 1 else net, [csrs[i] for i in idx], "moser", C4_NSTEPS, C4_RUNS, make_instance=lambda c: eng.Instance.from_csr(C4_N, *c),
             instance_seeds=[1 + i for i in idx], chunk=C4_CHUNK, keep_instances=True, stats=st)
         stage.update({k: v for k, v in st.items() if k != "timeline"})  # sums over the chunks; the Gantt view is tools/c4_timeline.py
         if os.environ.get("SLS_BENCH_C4_TIMELINE") and ctx["rank"] == 0:
@@ -454,7 +460,7 @@ def leg_c4_pipeline(ctx):
         "e2e": {"value": C4_INSTANCES / wall, "unit": "instances/s", "h2d_bytes_per_step": int(C4_INSTANCES * (C4_M * 3 * 32 + C4_M * 80 + C4_N * 40)),
                 "d2h_bytes_per_step": int(C4_INSTANCES * (C4_N * 4 + C4_RUNS * 22)),
                 "includes": "CSR -> handles, instance upload, LCG graphs on the device, forward, p to the host and back as weights, walk, D2H, gather; "
-                            f"pipeline.solve_with_oracle in chunks of {C4_CHUNK} instances, the three stages overlapped (stage times are sums over chunks)"},
+                            f"pipeline.solve_with_oracle in chunks of {C4_CHUNK} instances, {C4_HANDLES} forward worker(s), the stages overlapped (stage times are sums over chunks)"},
         "gpu_launches": None,
     }
     # ---- the oracle forward by itself: one workspace chunk (256 instances), device time, kernel classes, rooflines
@@ -518,7 +524,8 @@ def leg_c4_pipeline(ctx):
                                          "rates combined as a sequential pipeline"}
     leg["oracle_forward"] = fw
     leg["roofline"] = fw["roofline"]
-    net.close()
+    for one in nets:
+        one.close()
     return leg
 
 

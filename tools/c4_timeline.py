@@ -18,9 +18,10 @@ csrs = [synth.random_ksat_csr(n, m, 3, 20260104 + i) for i in range(k)]
 params = synth.random_oracle_params(seed=42)
 nets = [gnn.InteractionNetworkLCG(params) for _ in range(handles)]
 net = nets[0]
-warm = [eng.Instance.from_csr(n, *c) for c in csrs[:4]]
+warm = [eng.Instance.from_csr(n, *c) for c in csrs[:chunk]]  # a chunk of the real size: pool and workspace at working size
 pw = [n_.probabilities(warm) for n_ in nets][0]
-eng.run_sls_batch(warm, "moser", pw, pw, 100, 100)
+eng.run_sls_batch(warm, "moser", pw, pw, 9999, 100)
+del warm, pw
 if os.environ.get("C4_NO_GC"):
     gc.disable()
 st = {}
