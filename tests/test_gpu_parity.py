@@ -331,6 +331,20 @@ def test_walk_c2_shape_statistics_and_invariants():
 
 
 # ---- batched form: many instances per launch ---------------------------------------------------
+@pytest.mark.parametrize("algo", ["schoening", "moser_single"])
+def test_batch_table_building_covers_every_flip_rule(expected, algo):
+    # a batch builds the per-weights tables of all its instances with one launch per kernel family (clause records for the
+    # k <= 3 kernels, flip tables for the generic one, nothing for Schoening's rule): the rules the larger test below leaves out
+    names = sorted(expected)[:6]
+    insts = [eng.Instance.from_dimacs(golden_cnf(nm)) for nm in names]
+    rng = np.random.default_rng(12)
+    w = [rng.uniform(0.1, 0.9, i.n) for i in insts]
+    batch = eng.run_sls_batch(insts, algo, w, w, 200, 12, True, 0.0, seed=90)
+    for i, (nm, b) in enumerate(zip(names, batch)):
+        o = so.Instance.from_dimacs(golden_cnf(nm)).run_sls(algo, w[i], w[i], 200, 12, False, True, 0.0, seed=90 + i)
+        assert (b.steps == o.steps).all() and (b.found == o.found).all() and b.best_energy == o.best_energy, nm
+
+
 @pytest.mark.parametrize("algo", ["moser", "probsat"])
 @pytest.mark.parametrize("force", [{}, {"SLS_B200_FORCE_STATE": "hbm"}, {"SLS_B200_FORCE_GENERIC": "1"}])
 def test_batch_equals_per_instance_runs(expected, algo, force, monkeypatch):
