@@ -494,6 +494,7 @@ struct sls_solver {
     int device = 0;
     int num_sms = 0;
     bool weights_set = false;
+    bool thr_has_always_true = false;  // some weights_initialize entry is exactly 1 (Bernoulli's ALWAYS_TRUE threshold)
     std::string variant;
     // device buffers
     uint64_t* d_thr = nullptr;
@@ -724,15 +725,17 @@ extern "C" int sls_solver_set_weights(sls_solver* s, const double* w_init, size_
     }
     // rand 0.8.5 Bernoulli::new(p): p_int = (p * 2^64) as u64; p == 1 is ALWAYS_TRUE; else p must be in [0,1)
     std::vector<uint64_t> thr(std::max<uint32_t>(n, 1));
+    bool any_one = false;
     for (uint32_t i = 0; i < n; i++) {
         const double p = w_init[i];
         if (p >= 0.0 && p < 1.0)
             thr[i] = (uint64_t)(p * 18446744073709551616.0);
         else if (p == 1.0)
-            thr[i] = ~0ull;
+            thr[i] = ~0ull, any_one = true;
         else
             return set_error(SLS_ERR_WEIGHTS, "weights_initialize: p is outside range [0.0, 1.0]");
     }
+    s->thr_has_always_true = any_one;
     // Nothing here waits for the device: the copies (pageable sources are staged before the call returns) and the table
     // builders are enqueued on the legacy default stream, and the next launch -- on whatever stream -- waits for ev_w.
     // A launch of this solver that is still running reads the old tables: wait for it first (stream order alone does not
@@ -782,7 +785,10 @@ extern "C" int sls_solver_launch(sls_solver* s, void* cuda_stream)
         for (uint32_t s0 = 0; s0 < nslices; s0 += s->tbits_slices) {
             const uint32_t cnt = std::min(s->tbits_slices, nslices - s0);
             dim3 g1((I.nwords + words_per_block - 1) / words_per_block, cnt);
-            init_assign_sliced_kernel<<<g1, 256, 0, st>>>(s->args, s->d_tbits, s0, words_per_block);
+            if (s->thr_has_always_true)
+                init_assign_sliced_kernel<true><<<g1, 256, 0, st>>>(s->args, s->d_tbits, s0, words_per_block);
+            else
+                init_assign_sliced_kernel<false><<<g1, 256, 0, st>>>(s->args, s->d_tbits, s0, words_per_block);
             dim3 g2((I.ngroups + SCAN_WARPS - 1) / SCAN_WARPS, cnt);
             init_scan_sliced_kernel<SCAN_WARPS><<<g2, SCAN_WARPS * 32, 0, st>>>(s->args, s->d_tbits, s0);
             s->launches += 2;

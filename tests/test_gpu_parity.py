@@ -427,6 +427,26 @@ def test_walk_hbm_tier_more_chains_than_one_slice(monkeypatch):
         assert_same_run(g, o)
 
 
+@pytest.mark.parametrize("n", [217, 224, 256])  # ragged last assignment word, 32 variables + dummy bit, whole words only
+def test_walk_hbm_tier_initialisation_with_certain_variables(n, monkeypatch):
+    # weights_initialize with exact 0 and 1 (Bernoulli's ALWAYS_TRUE threshold) and without: the sliced init kernel has an
+    # instantiation for either case, a whole-word path (128-bit threshold loads) and a tail path
+    monkeypatch.setenv("SLS_B200_FORCE_STATE", "hbm")
+    clauses = random_ksat(n, int(3.2 * n), 3, seed=400 + n)
+    gi = eng.Instance.from_clauses(n, clauses)
+    oi = so.Instance.from_clauses(n, clauses)
+    rng = np.random.default_rng(n)
+    for with_ones in (True, False):
+        w = rng.uniform(0.05, 0.95, n)
+        w[rng.choice(n, 9, replace=False)] = 0.0
+        if with_ones:
+            w[rng.choice(n, 11, replace=False)] = 1.0
+            w[n - 1] = 1.0  # the last variable of the ragged word
+        g = eng.run_sls(gi, "moser", w, np.clip(w, 0.05, 0.95), 40, 270, True, True, 0.0, seed=21)
+        o = oi.run_sls("moser", w, np.clip(w, 0.05, 0.95), 40, 270, True, True, 0.0, seed=21)
+        assert_same_run(g, o)
+
+
 def test_walk_hbm_tier_flip_log_best_assignment(monkeypatch):
     # HBM tier with a short step budget: the best assignment is rebuilt from the flip log
     monkeypatch.setenv("SLS_B200_FORCE_STATE", "hbm")
