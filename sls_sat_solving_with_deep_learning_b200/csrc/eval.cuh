@@ -177,7 +177,8 @@ __global__ void transpose_assignments_kernel(const uint8_t* __restrict__ bytes, 
 // OUT = false: energies only (no staging buffer, twice the resident warps).
 // (168 registers, three CTAs per SM.  Round 2 measured four and five CTAs per SM through launch bounds: 128 / 96 registers with
 // 128 / 304 bytes of spills, 0.50 / 0.55 ms against 0.46 ms.)
-template <int WARPS, bool OUT>
+// NL: literals fetched and gathered ahead per clause (3 for uniform k <= 3: no redundant fourth gather; else 4 + a tail loop)
+template <int WARPS, bool OUT, int NL = 4>
 __global__ void __launch_bounds__(WARPS * 32) eval_sliced_kernel(const DevInst I, const uint32_t* __restrict__ tq_all,
                                                                  uint32_t* __restrict__ vout, uint32_t pitch,
                                                                  uint32_t* __restrict__ energy, uint64_t batch, uint32_t tiles_per_block)
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(WARPS * 32) eval_sliced_kernel(const DevInst I
     // a warp owns a contiguous run of tiles, so the row pipeline runs through from its first to its last row
     const uint32_t per_warp = tiles_per_block / WARPS;  // tiles_per_block is a multiple of WARPS
     const uint32_t t0 = min(t_end, t_begin + warp * per_warp), t1 = min(t_end, t0 + per_warp);
-    ClauseRows rows(I, tq, t0 * TILE_WORDS * 32u + lane);
+    ClauseRowsT<NL> rows(I, tq, t0 * TILE_WORDS * 32u + lane);
     for (uint32_t t = t0; t < t1; t++) {
         // After the transposition lane b holds, for each of its eight assignments 32q + b, the violated-set word of the row.
         // The eight rows of a tile are kept in registers (acc[q][wi]) and leave as ONE 32-byte sector per assignment: a

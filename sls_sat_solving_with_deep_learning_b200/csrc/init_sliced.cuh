@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) init_assign_sliced_kernel(const WalkArgs 
 
 // grid: (level-1 groups / WARPS, slices in this launch); each warp owns one level-1 group = 32 vbits
 // words = 1024 clauses = 4 tiles and produces, for each of the slice's 256 chains, those words and the counter.
-template <int WARPS>
+template <int WARPS, int NL = 4>
 __global__ void __launch_bounds__(WARPS * 32) init_scan_sliced_kernel(const WalkArgs A, const uint32_t* __restrict__ tq_all, uint32_t slice0)
 {
     __shared__ uint32_t stage[WARPS][SLICE_W][TILE_WORDS + 1];
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(WARPS * 32) init_scan_sliced_kernel(const Walk
     uint32_t acc[SLICE_Q];  // lane b, entry q: violated clauses of chain run0 + 32q + b in this group
 #pragma unroll
     for (uint32_t q = 0; q < SLICE_Q; q++) acc[q] = 0;
-    ClauseRows rows(I, tq, g * 1024u + lane);  // the 32 rows of the group, pipelined across its four tiles
+    ClauseRowsT<NL> rows(I, tq, g * 1024u + lane);  // the 32 rows of the group, pipelined across its four tiles
     for (uint32_t t = 0; t < 32 / TILE_WORDS; t++) {
         const uint32_t w0 = g * 32u + t * TILE_WORDS;  // first vbits word of the tile (whole groups exist in the slab)
 #pragma unroll 1
