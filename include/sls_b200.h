@@ -177,7 +177,10 @@ const char *sls_solver_variant(const sls_solver *s);
  *      ("interaction" + LCG: python/src/model.py:127-144, call sites
  *      python/src/evaluate_with_given_params.py:116, :297, :306 and python/src/train_utils.py:279)
  *      and LCG.get_model_probabilities (python/src/sat_representations.py:756-780).
- *      The dense layers run on tcgen05 tensor cores (TF32 inputs, FP32 accumulate). ------------- */
+ *      The dense layers run on tcgen05 tensor cores with FP32 accumulation: every operand is split into two fp16
+ *      pieces (22 mantissa bits; three kind::f16 product terms) -- probabilities within 1e-5 of an fp64 forward.
+ *      A model whose weights or LayerNorm outputs leave fp16's range is created with two bf16 pieces instead
+ *      (16 bits, fp32's range); SLS_B200_GNN_PRECISION = fp16x2 | bf16x2 | tf32x3 overrides per call. ------------- */
 typedef struct sls_gnn_model sls_gnn_model;
 
 /* blob = all parameters as float32 in haiku construction order (python/src/model.py:11-61):
