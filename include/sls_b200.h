@@ -51,6 +51,11 @@ const char *sls_last_error(void);
 /* ---- device ------------------------------------------------------------ */
 int sls_device_count(int *count);
 int sls_set_device(int device); /* per calling thread, like cudaSetDevice */
+/* Grow the library's private device memory pool (current device) so that `bytes` are mapped and cached, capped at the pool's
+ * release threshold (4 GB).  The pool otherwise grows on demand; mapping new memory waits for the kernels that are running,
+ * so a host thread that uploads instances while another thread's walk kernel runs stalls for a kernel's length per growth
+ * step (pipeline.solve_with_oracle reserves its working set up front).  No reference counterpart: the reference has no device. */
+int sls_device_pool_reserve(uint64_t bytes);
 
 /* ---- instance: replaces DimacsParser::parse + CnfFormula (lib.rs:115-118)
  *      and the var_to_clauses mapping (lib.rs:186-199).  The clause CSR and the

@@ -101,6 +101,7 @@ SYMBOLS = {
     "sls_last_error": (C.c_char_p, []),
     "sls_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "sls_set_device": (C.c_int, [C.c_int]),
+    "sls_device_pool_reserve": (C.c_int, [C.c_uint64]),
     "sls_instance_from_dimacs": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
     "sls_instance_from_dimacs_text": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(_vp)]),
     "sls_instance_from_csr": (C.c_int, [C.c_uint32, C.c_uint32, _vp, _vp, C.POINTER(_vp)]),

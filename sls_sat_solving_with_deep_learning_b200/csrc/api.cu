@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -67,6 +68,27 @@ extern "C" int sls_device_count(int* count)
 extern "C" int sls_set_device(int device)
 {
     CUDA_TRY(cudaSetDevice(device));
+    return SLS_OK;
+}
+
+extern "C" int sls_device_pool_reserve(uint64_t bytes)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaStream_t st;
+    cudaMemPool_t pool;
+    CUDA_TRY(devmem_stream(dev, &st, &pool));
+    uint64_t keep = 0;
+    CUDA_TRY(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    bytes = std::min<uint64_t>(bytes, keep);  // what lies above the threshold would be unmapped again at the next synchronisation
+    uint64_t have = 0;
+    CUDA_TRY(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &have));
+    if (bytes <= have) return SLS_OK;
+    // one block of the missing size, allocated and freed: the pool keeps it mapped and serves later requests out of it
+    void* q = nullptr;
+    CUDA_TRY(cudaMallocFromPoolAsync(&q, (size_t)(bytes - have), pool, st));
+    CUDA_TRY(cudaFreeAsync(q, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return SLS_OK;
 }
 
@@ -1036,6 +1058,23 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         results[i].kernel_ms = 0.0;
     }
     if (n_inst == 0 || R == 0) return SLS_OK;
+    // SLS_B200_DEBUG_PHASES=1: wall-clock phases of the call on stderr (development aid for pipeline.py's Gantt view)
+    static const bool dbg_phases = std::getenv("SLS_B200_DEBUG_PHASES") != nullptr;
+    const auto ph0 = std::chrono::steady_clock::now();
+    auto ph_ms = [ph0] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ph0).count(); };
+    double ph[6] = {0, 0, 0, 0, 0, 0};
+    struct PhasePrinter {  // declared before the pools: runs after their frees
+        bool on;
+        const double* ph;
+        decltype(ph_ms)& now;
+        uint32_t n;
+        ~PhasePrinter()
+        {
+            if (on)
+                std::fprintf(stderr, "sls_run_batch(%u): plan %.1f | weights+pools+H2D %.1f | enqueue %.1f | device wait %.1f | D2H+reduce %.1f | frees %.1f ms\n", n,
+                             ph[0], ph[1] - ph[0], ph[2] - ph[1], ph[3] - ph[2], ph[4] - ph[3], now() - ph[4]);
+        }
+    } phase_printer{dbg_phases, ph, ph_ms, n_inst};
 
     int device = 0, num_sms = 0, max_smem_optin = 0, smem_per_sm = 0;
     CUDA_TRY(cudaGetDevice(&device));
@@ -1076,6 +1115,7 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         if (!pl.smem) tot_gstate += R * size_t(I.slab_words);
     }
 
+    ph[0] = ph_ms();  // plan (+ upload of instances that were not resident)
     // ---- weights: validate and convert on the host, one upload per pool
     std::vector<uint64_t> thr(tot_n, 0);
     std::vector<double> wres(tot_n, 0.0);
@@ -1188,6 +1228,7 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         smem_max[g] = std::max(smem_max[g], smem_bytes);
     }
     CUDA_TRY(cudaGetLastError());
+    ph[1] = ph_ms();  // weights, pools, H2D, items
 
     struct Events {  // destroyed on every exit path
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1240,7 +1281,9 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev1));
+    ph[2] = ph_ms();  // tables + launches enqueued
     CUDA_TRY(cudaEventSynchronize(ev1));
+    ph[3] = ph_ms();  // device done
     InFlight::done();
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
@@ -1307,5 +1350,6 @@ extern "C" int sls_run_batch(sls_instance* const* insts, uint32_t n_inst, const 
         if (r.best_energy_run)
             for (size_t q = 0; q < R; q++) r.best_energy_run[q] = be[pl.off_run + q];
     }
+    ph[4] = ph_ms();
     return SLS_OK;
 }

@@ -66,6 +66,20 @@ inline cudaError_t devmem_stream(int device, cudaStream_t* out, cudaMemPool_t* p
         if (e != cudaSuccess) return e;
         e = cudaStreamCreateWithFlags(&st.stream[device], cudaStreamNonBlocking);
         if (e != cudaSuccess) return e;
+        // SLS_B200_POOL_RESERVE_MB: grow the pool to this size once, now (one block, allocated and freed: it stays cached up to
+        // the release threshold).  The pool otherwise grows on demand, and growing maps new memory -- which waits for the kernels
+        // that are running: a host thread that uploads instances while another thread's walk kernel runs (pipeline.py) then
+        // stalls for a kernel's length per growth step.
+        if (const char* f = std::getenv("SLS_B200_POOL_RESERVE_MB")) {
+            const size_t bytes = (size_t)std::strtoull(f, nullptr, 10) << 20;
+            void* q = nullptr;
+            if (bytes && cudaMallocFromPoolAsync(&q, bytes, st.pool[device], st.stream[device]) == cudaSuccess) {
+                cudaFreeAsync(q, st.stream[device]);
+                cudaStreamSynchronize(st.stream[device]);
+            } else {
+                cudaGetLastError();
+            }
+        }
         st.ready[device] = true;
     }
     *out = st.stream[device];

@@ -92,7 +92,7 @@ def staged(stages: Sequence, items, depth: int = 2) -> list:
 
 def solve_with_oracle(net, sources, algo: str, nsteps: int, nruns: int, *, make_instance: Callable | None = None,
                       instance_seeds=None, chunk: int = 500, pre_compute_mapping: bool = True, prob_flip_best: float = 0.0,
-                      device: int | None = None, keep_instances: bool = False, stats: dict | None = None):
+                      device: int | None = None, keep_instances: bool = False, stats: dict | None = None, reserve: bool = True):
     """``net.probabilities`` on every instance, then ``run_sls_batch`` with those probabilities as ``weights_initialize`` and
     ``weights_resample`` (the evaluation script's oracle-guided run, evaluate_with_given_params.py:116-147), chunk by chunk
     with the stages overlapped.
@@ -103,7 +103,8 @@ def solve_with_oracle(net, sources, algo: str, nsteps: int, nruns: int, *, make_
     ``sources``: one entry per instance -- an :class:`Instance`, or whatever ``make_instance`` turns into one (a DIMACS path,
     a ``(n, row_ptr, signed_lits)`` CSR triple ...).  ``instance_seeds``: one seed per instance (default 1 + index).
     Returns ``(results, probabilities)``: lists in source order of :class:`SlsResult` and of p[n_i]; with ``keep_instances``
-    a third list holds the handles.  ``stats`` (optional dict) receives the summed stage times in seconds, the summed
+    a third list holds the handles.  ``reserve``: map the device memory pool's working set
+    before the first upload (see :func:`~.solver.reserve_device_pool`).  ``stats`` (optional dict) receives the summed stage times in seconds, the summed
     device times in ms and ``timeline``: (stage, first instance of the chunk, start s, end s) per stage call."""
     sources = list(sources)
     k = len(sources)
@@ -127,6 +128,12 @@ def solve_with_oracle(net, sources, algo: str, nsteps: int, nruns: int, *, make_
         t0 = time.perf_counter()
         hi = min(lo + chunk, k)
         insts = [s if isinstance(s, _solver.Instance) else make_instance(s) for s in sources[lo:hi]]
+        if lo == 0 and reserve and insts:
+            # the device images of all instances (about 24 bytes per literal occurrence, 16 per clause, 8 per variable) and the
+            # per-chunk buffers of two chunks in flight, mapped now: growing the pool later would wait for the walk kernels
+            per = sum(24 * i.num_lits + 16 * i.m + 8 * i.n + 4096 for i in insts) / len(insts)
+            pin_device()
+            _solver.reserve_device_pool(int(1.25 * per * k + 3 * per * len(insts)) + (256 << 20))
         acc["build_s"] += time.perf_counter() - t0
         stamp("build", lo, t0)
         return lo, insts

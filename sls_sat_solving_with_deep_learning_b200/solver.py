@@ -53,6 +53,12 @@ def set_device(device: int) -> None:
     _thread_device.index = int(device)
 
 
+def reserve_device_pool(nbytes: int) -> None:
+    """Grow the library's device memory pool to ``nbytes`` now (capped at its 4 GB release threshold) instead of step by step
+    under running kernels (sls_device_pool_reserve)."""
+    _check(_lib.load().sls_device_pool_reserve(int(max(nbytes, 0))))
+
+
 def current_device() -> int:
     """The device this thread selected with :func:`set_device` (0 if it never did)."""
     return getattr(_thread_device, "index", 0)

@@ -87,9 +87,11 @@ def test_solve_with_oracle_chunks_seeds_and_order(monkeypatch):
 
     monkeypatch.setattr(pipeline._solver, "run_sls_batch", fake_batch)
     monkeypatch.setattr(pipeline._solver, "set_device", lambda d: None)
+    reserved = []
+    monkeypatch.setattr(pipeline._solver, "reserve_device_pool", reserved.append)
     stats = {}
     res, probs = pipeline.solve_with_oracle(FakeNet(), list(range(10)), "moser", 100, 4, chunk=4,
-                                            make_instance=lambda t: SimpleNamespace(tag=t, n=3 + t),
+                                            make_instance=lambda t: SimpleNamespace(tag=t, n=3 + t, m=12, num_lits=36),
                                             instance_seeds=[100 + t for t in range(10)], stats=stats)
     assert [r.tag for r in res] == list(range(10))
     assert [r.seed for r in res] == [100 + t for t in range(10)]
@@ -97,10 +99,11 @@ def test_solve_with_oracle_chunks_seeds_and_order(monkeypatch):
     assert [len(p) for p in probs] == [3 + t for t in range(10)]
     assert calls == [((0, 1, 2, 3), (100, 101, 102, 103)), ((4, 5, 6, 7), (104, 105, 106, 107)), ((8, 9), (108, 109))]
     assert stats["walk_kernel_ms"] == 6.0 and stats["forward_device_ms"] == 3.0
+    assert len(reserved) == 1 and reserved[0] > 10 * (24 * 36 + 16 * 12)  # the pool's working set is mapped once, up front
     del calls[:]
     res2, _ = pipeline.solve_with_oracle([FakeNet(), FakeNet()], list(range(10)), "moser", 100, 4, chunk=3,
-                                         make_instance=lambda t: SimpleNamespace(tag=t, n=3 + t),
-                                         instance_seeds=[100 + t for t in range(10)])
+                                         make_instance=lambda t: SimpleNamespace(tag=t, n=3 + t, m=12, num_lits=36),
+                                         instance_seeds=[100 + t for t in range(10)], reserve=False)
     assert [r.tag for r in res2] == list(range(10)) and [c[0] for c in calls] == [(0, 1, 2), (3, 4, 5), (6, 7, 8), (9,)]
     with pytest.raises(ValueError):
         pipeline.solve_with_oracle(FakeNet(), [1, 2], "moser", 1, 1)  # not handles and no make_instance
