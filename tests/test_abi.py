@@ -105,3 +105,9 @@ def test_compute_fails_loudly_without_gpu():
         eng.run_sls(gi, "moser", w, w, 10, 2)
     with pytest.raises(eng.PanicException):
         eng.eval_assignments(gi, np.zeros((1, gi.n)))
+    from sls_sat_solving_with_deep_learning_b200 import pipeline, solver
+
+    with pytest.raises(eng.PanicException):
+        solver.reserve_device_pool(1 << 20)
+    with pytest.raises(eng.PanicException):  # the pipeline's first device call (the pool reservation) fails: no silent CPU path
+        pipeline.solve_with_oracle(object(), [gi], "moser", 10, 2)
